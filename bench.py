@@ -1,0 +1,303 @@
+#!/usr/bin/env python
+"""bench.py -- the reference's headline hot path on B200: MF-GP posterior over the grid + coverage step.
+
+One "step" = one coverage iteration of the workload (default: BASELINE.json config 4 -- synthetic 1024x1024 grid,
+4096 MF training samples, 64 agents):
+    factor the training covariance (K assembly -> blocked Cholesky -> L^-1 -> whitened observations)
+    -> fused posterior mean + variance over every grid point
+    -> both bounded-Voronoi partitions in one pass (loss, weighted centroids, per-cell max-variance arg-max)
+    -> O(agents) host finishing (Qhull polygons, centroid / loss arithmetic), exactly what simulator.todescato does.
+`value` = grid points / s with everything resident in HBM; `e2e` = the same iteration through the drop-in Python API
+with HOST numpy buffers (grid upload, mu/var download, re-upload into the coverage functions) inside the timed region.
+N > 1 (torchrun, one rank per GPU): the grid is sharded contiguously over ranks (strong scaling), every rank
+factorises the (small) training system redundantly, per-cell partial sums / arg-max are combined with NCCL.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c4|c3|c2]
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from tests import synth  # noqa: E402
+
+WORKLOADS = {
+    # name: (grid side, N training, agents, description)
+    "c4": (1024, 4096, 64, "c4: synthetic 1024x1024 grid, 4096 MF samples (1024 lofi + 3072 hifi), 64 agents"),
+    "c3": (256, 1024, 16, "c3: synthetic 256x256 grid, 1024 MF samples, 16 agents"),
+    "c2": (51, 309, 8, "c2-like: 51x51 grid, 309 MF samples, 8 agents"),
+}
+DGEMM_PEAK_TFLOPS = 35.41   # cuBLAS DGEMM 8192^3 measured on this pool's B200 (profiles/r01_dgemm_peak.json);
+#                             MEASURED_PEAKS.json carries no FP64 figure.  DMMA issue peak: 37.15 (r01_fp64_pipes.log)
+
+
+def make_workload(name):
+    n, N, A, desc = WORKLOADS[name]
+    xy = synth.grid(n)
+    f = synth.truth_function(xy)
+    X_L, y_L, X_H, y_H = synth.training_set(xy, f, N)
+    return dict(name=name, desc=desc, n=n, N=N, A=A, xy=xy, f=f, X_L=X_L, y_L=y_L, X_H=X_H, y_H=y_H,
+                pos=synth.agents(A, 7), cen=synth.agents(A, 8))
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag = index, [], set(), False
+        self.max_mhz = None
+
+    def run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            names = {nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap",
+                     nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+                     nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                     nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                     nv.nvmlClocksThrottleReasonHwPowerBrakeSlowdown: "hw_power_brake"}
+            while not self.stop_flag:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for bit, nm in names.items():
+                    if r & bit:
+                        self.reasons.add(nm)
+                time.sleep(0.1)
+        except Exception as e:   # NVML missing: report that rather than fake numbers
+            self.reasons.add(f"nvml_unavailable:{type(e).__name__}")
+
+    def result(self):
+        self.stop_flag = True
+        self.join(timeout=2)
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port of the reference path on the host cores
+# ---------------------------------------------------------------------------------------------------------------------
+
+def cpu_step(w, sample_pts):
+    """The same iteration with the oracle (numpy/scipy, all BLAS threads) on a bounded sample of the grid."""
+    from oracle import coverage as ocov
+    from oracle import gp as ogp
+    p = ogp.GPParams.from_hyp(synth.MF_HYP)
+    xy = w["xy"][:sample_pts]
+    truth = np.column_stack((xy, w["f"][:sample_pts]))
+    t0 = time.perf_counter()
+    L = ogp.cholesky(ogp.train_cov(p, w["X_L"], w["X_H"]))
+    mu, var = ogp.posterior(p, xy, w["X_L"], w["y_L"], w["X_H"], w["y_H"], L=L, chunk=4096)
+    bbox = ocov.bounding_box_of(w["xy"])
+    ocov.compute_loss(ocov.voronoi_bounded(w["pos"], bbox), truth)
+    lv = ocov.voronoi_bounded(w["cen"], bbox)
+    ocov.compute_centroids(lv, xy, mu)
+    mem_ok = True
+    try:
+        ocov.compute_max_var(lv, truth, var)
+    except ValueError:      # a bounded sample can leave cells empty; the reference raises there
+        mem_ok = False
+    return time.perf_counter() - t0, mem_ok
+
+
+def cpu_sample_points(w):
+    return {"c4": 16384, "c3": 16384, "c2": 2601}[w["name"]]
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    w = make_workload(args.workload)
+    pts = cpu_sample_points(w)
+    for _ in range(min(args.warmup, 1)):
+        cpu_step(w, pts)
+    times = [cpu_step(w, pts)[0] for _ in range(args.steps)]
+    t = float(np.mean(times))
+    value = pts / t
+    line = base_line(args, w, value, t * 1e3)
+    line.update({"impl": "reference", "dtype": "f64", "gpu_launches": 0,
+                 "cpu_baseline": {"value": value, "unit": "grid-points/s", "cores": os.cpu_count(), "kind": "port",
+                                  "sample": f"first {pts} of {w['xy'].shape[0]} grid points per step, full N={w['N']} "
+                                            "training set, oracle (numpy/scipy restatement of the reference; the "
+                                            "reference's own G x G predict cannot run at this size)"},
+                 "e2e": {"value": value, "unit": "grid-points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+    print(json.dumps(line))
+
+
+def base_line(args, w, value, ms):
+    return {"metric": "GP posterior mean+var + coverage step, grid-points/s (coverage iterations/s = 1000/ms_per_step)",
+            "value": value, "unit": "grid-points/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "data": "synthetic",
+            "config": {"workload": w["desc"], "grid_points": int(w["xy"].shape[0]), "train_points": int(w["N"]),
+                       "agents": int(w["A"]), "parallelism": f"grid-sharded x{args.gpus}",
+                       "l2_policy": "inputs larger than L2 (W 134 MB + 40 B/grid point streamed; K/W rewritten every "
+                                    "step)" if w["name"] == "c4" else "L2 flushed between steps (256 MB write)"}}
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------------------------------
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from mfgp_coverage_b200 import _native as nat
+    from mfgp_coverage_b200 import _coverage as cv
+    from mfgp_coverage_b200 import sharding
+    from mfgp_coverage_b200 import simulator as sim
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    w = make_workload(args.workload)
+    G = w["xy"].shape[0]
+    bbox = np.array([0.0, 1.0, 0.0, 1.0])
+    lo, hi = sharding.shard_bounds(G, world, rank)
+
+    model = sim.init_MFGP(synth.MF_HYP, np.column_stack((w["X_L"], w["y_L"])))
+    model.updt_info(w["X_L"], w["y_L"], w["X_H"], w["y_H"])          # uploads the training set once
+    eng = model.engine
+    grid = cv.CoverageGrid(w["xy"][lo:hi], w["f"][lo:hi], base_index=lo)
+    mu = torch.empty(hi - lo, dtype=torch.float64, device=dev)
+    var = torch.empty(hi - lo, dtype=torch.float64, device=dev)
+    flush = torch.empty(64 << 20, dtype=torch.float32, device=dev) if w["name"] != "c4" else None
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    post_ms = []
+
+    def device_step(timed):
+        if flush is not None:
+            flush.zero_()
+        eng.refactor(check=False)                                     # K -> L -> W -> z  (train set resident)
+        if timed:
+            ev[0].record()
+        eng.posterior(grid.xy, mu, var)
+        if timed:
+            ev[1].record()
+        loss_vor = sim.voronoi_bounded(w["pos"], bbox)
+        lloyd_vor = sim.voronoi_bounded(w["cen"], bbox)
+        res = grid.assign_reduce(lloyd_vor, loss_vor, w=mu, var=var)
+        sharding.allreduce_partials(res)
+        loss = cv.loss_from_partials(res["lossp"].cpu().numpy(), loss_vor.areas())
+        cent = cv.centroids_from_partials(res["cent"].cpu().numpy(), lloyd_vor.areas(), 0.0, 1.0, 0.0, 1.0)
+        idx = res["amax_idx"].cpu().numpy()
+        if timed:
+            post_ms.append(ev[0].elapsed_time(ev[1]))                 # .cpu() above synchronised the stream
+        return loss, cent, idx
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed_region(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = None
+        for _ in range(steps):
+            out = fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)      # device timeline; the host work of a step sits between its kernels
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms / steps, out
+
+    for _ in range(args.warmup):
+        device_step(False)
+    eng.check_factor()
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = nat.lib().mfgp_launch_count()
+    ms_dev, out = timed_region(lambda: device_step(True), args.steps)
+    launches = nat.lib().mfgp_launch_count() - l0
+    clocks = sampler.result()
+
+    # end-to-end through the drop-in API with host buffers (rank-local slice of the grid)
+    xs_host = np.ascontiguousarray(w["xy"][lo:hi])
+    truth_host = np.ascontiguousarray(np.column_stack((w["xy"][lo:hi], w["f"][lo:hi])))
+    empty_x, empty_y = np.empty((0, 2)), np.empty((0, 1))
+
+    def e2e_step():
+        model.updt_hifi(empty_x, empty_y)                 # the reference refits every iteration (simulator.py:888-891)
+        mu_h, var_h = model.predict(xs_host)              # H2D grid, D2H mean + variance
+        loss_vor = sim.voronoi_bounded(w["pos"], bbox)
+        lloyd_vor = sim.voronoi_bounded(w["cen"], bbox)
+        g = cv.CoverageGrid(xs_host, truth_host[:, 2], base_index=lo)          # H2D grid + truth
+        res = g.assign_reduce(lloyd_vor, loss_vor, w=torch.from_numpy(mu_h[:, 0]).to(dev),
+                              var=torch.from_numpy(var_h).to(dev))             # H2D mean + variance
+        sharding.allreduce_partials(res)
+        loss = cv.loss_from_partials(res["lossp"].cpu().numpy(), loss_vor.areas())
+        cent = cv.centroids_from_partials(res["cent"].cpu().numpy(), lloyd_vor.areas(), 0.0, 1.0, 0.0, 1.0)
+        return loss, cent, res["amax_idx"].cpu().numpy()
+
+    e2e_step()
+    ms_e2e, out_e2e = timed_region(e2e_step, max(1, min(args.steps, 3)))
+    npts = hi - lo
+    h2d = npts * (16 + 16 + 8 + 8 + 8)
+    d2h = npts * 16 + w["A"] * 8 * 8
+
+    if rank == 0:
+        value = G / (ms_dev * 1e-3)
+        N = w["N"]
+        npad = eng.npad
+        flops = float(npts) * N * N + 4.0 * npts * N            # algorithmic: triangular solve + mean + column norm
+        pm = float(np.mean(post_ms))
+        achieved = flops / (pm * 1e-3) * 1e-12
+        line = base_line(args, w, value, ms_dev)
+        line.update({
+            "dtype": "f64", "clocks": clocks, "gpu_launches": int(launches),
+            "e2e": {"value": G / (ms_e2e * 1e-3), "unit": "grid-points/s", "h2d_bytes_per_step": int(h2d),
+                    "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e},
+            "roofline": {"bound": "tensor", "kernel": "posterior_kernel (DMMA fp64)", "achieved": achieved,
+                         "peak": DGEMM_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": achieved / DGEMM_PEAK_TFLOPS,
+                         "traffic": None, "kernel_ms": pm, "kernel_share_of_step": pm / ms_dev,
+                         "peak_source": "cuBLAS DGEMM 8192^3 measured on this pool (profiles/r01_dgemm_peak.json); "
+                                        "MEASURED_PEAKS.json has no FP64 figure; DMMA issue peak 37.15"},
+            "check": {"loss": float(out[0]), "loss_e2e": float(out_e2e[0]), "npad": int(npad)},
+        })
+        if world == 1:
+            pts = cpu_sample_points(w)
+            t, _ = cpu_step(w, pts)
+            line["cpu_baseline"] = {"value": pts / t, "unit": "grid-points/s", "cores": os.cpu_count(), "kind": "port",
+                                    "sample": f"one step on the first {pts} of {G} grid points, full N={N} training "
+                                              f"set ({t:.1f} s), oracle = numpy/scipy restatement of the reference"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,125 @@
+/* mfgp_b200.h -- C-ABI of the B200-native hot path of mfgp-coverage (libmfgp_b200.so).
+ *
+ * The reference (pure Python) has no FFI; its seam is the Python call surface of gaussian_process.py and
+ * simulator.py.  Each entry point below names the reference call site it replaces (file:line under the
+ * reference repository).  Conventions:
+ *   - every pointer is a caller-owned DEVICE pointer unless the parameter name ends in `_host`;
+ *   - sizes are int64_t, parameters are EVALUATED (non-log) doubles in `mfgp_params`;
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*) unless documented as blocking;
+ *   - return value: 0 = ok, negative = MFGP_ERR_*; no exceptions, no allocation inside (workspaces are
+ *     caller-provided, sizes from mfgp_workspace_bytes);
+ *   - matrices are row-major fp64; the training set is ordered [X_L ; X_H] as in gaussian_process.py:527-528;
+ *   - `npad` is the training size N = NL + NH rounded up to a multiple of MFGP_TILE (64); factor / inverse
+ *     buffers are npad x npad with leading dimension `ld` >= npad, padding rows/cols hold the identity.
+ */
+#ifndef MFGP_B200_H
+#define MFGP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MFGP_TILE 64
+
+#define MFGP_OK 0
+#define MFGP_ERR_INVALID (-1)   /* bad argument (null pointer, size, alignment) */
+#define MFGP_ERR_NOT_SPD (-2)   /* Cholesky hit a non-positive pivot: numpy raises LinAlgError here */
+#define MFGP_ERR_CUDA (-3)      /* a CUDA runtime call failed; see mfgp_last_error */
+#define MFGP_ERR_EMPTY_CELL (-4)/* a Voronoi cell holds no grid point: np.amax([]) raises ValueError here */
+
+/* Evaluated hyper-parameters.  gaussian_process.py:132,:248-251 (SF) and :411-416,:510-514 (MF):
+ * scale = exp(hyp[1|4]), length = exp(hyp[2|5]), rho = exp(hyp[6]), noise = exp(hyp[3] | hyp[7], hyp[8]) added to the
+ * diagonal UN-squared, jitter = 1e-8 (:42,:298).  Means are passed evaluated so both the current exp() convention and
+ * the 2020 raw convention of the logged goldens can be served.  Single fidelity: multi = 0, NL = 0, *_L ignored. */
+typedef struct mfgp_params {
+    double s_L, l_L;        /* lofi kernel: output scale, length scale          */
+    double s_H, l_H;        /* hifi (or the only) kernel                          */
+    double rho;             /* AR1 cross-fidelity scale                           */
+    double noise_L, noise_H;
+    double mean_L, mean_H;
+    double jitter;
+    int32_t multi;          /* 1 = two-level AR1 MFGP, 0 = SFGP                   */
+    int32_t reserved;
+} mfgp_params;
+
+const char* mfgp_version(void);
+const char* mfgp_last_error(void);          /* text of the last CUDA error seen by this thread */
+int64_t mfgp_launch_count(void);            /* kernels launched by this library since load (bench.py's gpu_launches) */
+int64_t mfgp_npad(int64_t n);               /* n rounded up to MFGP_TILE (at least MFGP_TILE)  */
+int64_t mfgp_workspace_bytes(int64_t npad); /* scratch needed by mfgp_cholesky / mfgp_tri_inverse */
+
+/* ---- GP fit: replaces SFGP.updt_info gaussian_process.py:229-255 and MFGP.updt_info :493-529 ------------------- */
+
+/* K[npad,ld] = full symmetric training covariance + (noise + jitter) I; padding = identity.  Also writes the scaled
+ * training coordinates Tt[npad,4] = (x/l_L, y/l_L, x/l_H, y/l_H) used by mfgp_posterior (:77-78 divides before
+ * differencing).  Replaces the K assembly at gaussian_process.py:253 / :523-528. */
+int mfgp_build_train_cov(const double* Xt, int64_t NL, int64_t NH, const mfgp_params* p_host,
+                         double* K, int64_t npad, int64_t ld, double* Tt, void* stream);
+
+/* In-place lower Cholesky of K[npad,ld] (np.linalg.cholesky at gaussian_process.py:254 / :529).  Blocked, trailing
+ * updates on FP64 tensor cores (DMMA).  Also writes the inverses of the 64x64 diagonal blocks into the diagonal
+ * blocks of W (may be NULL).  `info` (device int32): 0, or 1 + index of the first non-positive pivot. */
+int mfgp_cholesky(double* K, int64_t npad, int64_t ld, double* W, int64_t ldw, int32_t* info, void* work,
+                  void* stream);
+
+/* W[npad,ldw] = L^-1 (lower; strict upper part zeroed), by recursive block doubling on DMMA.  Needs the diagonal
+ * 64x64 blocks of W already inverted by mfgp_cholesky.  Stands in for the four general solves at
+ * gaussian_process.py:141,:145 / :431,:434. */
+int mfgp_tri_inverse(const double* L, int64_t npad, int64_t ld, double* W, int64_t ldw, void* work, void* stream);
+
+/* z[npad] = W (y - mean): y[N] raw observations ordered [y_L ; y_H]; centring as gaussian_process.py:133 / :419-424. */
+int mfgp_whiten(const double* W, int64_t npad, int64_t ldw, const double* y, int64_t NL, int64_t NH,
+                const mfgp_params* p_host, double* z, void* stream);
+
+/* ---- GP posterior: replaces SFGP.predict gaussian_process.py:121-148 and MFGP.predict :401-438 ------------------ */
+
+/* mu[G] = mean_H + psi^T K^-1 (y-m), var[G] = k(0) - |W psi|^2 for the G points Xs[G,2].  Fused: psi tiles are
+ * generated on chip, multiplied by W on DMMA and reduced; psi / V never reach HBM.  N = NL+NH may be 0 (prior).
+ * If Vc != NULL the whitened cross-covariance V = W psi^T is also stored, Vc[n*ldv + g] (for choi_greedy). */
+int mfgp_posterior(const double* Xs, int64_t G, const double* Tt, int64_t NL, int64_t NH,
+                   const double* W, int64_t npad, int64_t ldw, const double* z, const mfgp_params* p_host,
+                   double* mu, double* var, double* Vc, int64_t ldv, void* stream);
+
+/* ---- coverage step: replaces simulator.py in_polygon :105-124, compute_loss :194-228, compute_centroids :231-283,
+ *      compute_max_var :286-323, compute_sample_clusters :377-412 ------------------------------------------------ */
+
+/* One pass over the grid for up to two bounded-Voronoi partitions:
+ *   partition C ("lloyd", seeds_c[Ac,2]): cent[Ac,4] = {sum w, sum w*x, sum w*y, count},
+ *                                          amax_val[Ac], amax_idx[Ac] = per-cell max of var and its FIRST grid index
+ *                                          (np.argmax semantics; -1 for an empty cell);
+ *   partition P ("loss",  seeds_p[Ap,2]): lossp[Ap,2] = {sum |x-seed|^2 f, count}.
+ * Membership: nearest seed when the two smallest squared distances differ by more than tie_tol, otherwise the
+ * reference's exact crossings test (matplotlib point_in_path, restated) against the cell polygons
+ * poly_xy[nvert,2] / poly_off[A+1] (Qhull vertex order; nvert == poly_off[A]); a point may then fall in 0, 1 or several cells, exactly as in
+ * the reference.  tie_tol = +inf forces the crossings test everywhere.  w / var / f / member_* may be NULL to skip
+ * the corresponding output; Ac or Ap may be 0.  member_c[G, ceil(Ac/64)] receives the membership bit masks.
+ * `base_index` is added to grid indices (grid sharding).  Deterministic (no floating-point atomics). */
+int cov_assign_reduce(const double* xy, const double* w, const double* var, const double* f, int64_t G,
+                      int64_t base_index,
+                      const double* seeds_c, int64_t Ac, const double* poly_xy_c, const int32_t* poly_off_c, int64_t nvert_c,
+                      const double* seeds_p, int64_t Ap, const double* poly_xy_p, const int32_t* poly_off_p, int64_t nvert_p,
+                      double tie_tol,
+                      double* cent, double* amax_val, int64_t* amax_idx, double* lossp,
+                      uint64_t* member_c, void* work, int64_t work_bytes, void* stream);
+int64_t cov_workspace_bytes(int64_t G, int64_t Ac, int64_t Ap);
+
+/* Global first-index argmax of v[G] (np.argmax at simulator.py:352): out_val[1], out_idx[1]. */
+int cov_argmax(const double* v, int64_t G, int64_t base_index, double* out_val, int64_t* out_idx, void* work,
+               int64_t work_bytes, void* stream);
+
+/* ---- Choi greedy sample planner: replaces compute_sample_points simulator.py:326-374 ---------------------------- */
+
+/* Greedy max-variance selection on the cached V (rows [0,n0) valid, capacity rows `cap`, row stride ldv >= G):
+ * while max(var) > threshold: j = first argmax; append the bordered-Cholesky row for x_j (hifi level, pseudo-
+ * observation = current mean, so mu is unchanged); var -= v^2.  Picks (grid indices) go to picks_host[<= max_picks];
+ * returns the number of picks (>= 0) or a negative error.  BLOCKING (synchronises `stream` once per pick). */
+int64_t choi_greedy(const double* Xs, int64_t G, double* Vc, int64_t ldv, int64_t n0, int64_t cap, double* var,
+                    const mfgp_params* p_host, double threshold, int64_t max_picks, int64_t* picks_host,
+                    void* work, int64_t work_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MFGP_B200_H */

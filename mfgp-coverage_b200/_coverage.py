@@ -1,0 +1,205 @@
+"""Device-side coverage step: grid-resident state and the calls into libmfgp_b200's cov_* / choi_* entry points.
+
+`CoverageGrid` keeps the environment grid (coordinates, ground truth) in HBM for the whole simulation and owns the
+output / workspace buffers of `cov_assign_reduce`; `BoundedVoronoi` is the host-side polygon set the reference gets
+from scipy/Qhull (simulator.py:154-191), flattened for the device.
+"""
+import ctypes
+import math
+
+import numpy as np
+import torch
+from scipy.spatial import Voronoi
+
+from . import _native as nat
+
+EPS = 0.1            # boundary cushion, simulator.py:33
+TIE_TOL = 1e-9       # |d2_second - d2_best| below which the exact crossings test decides membership
+
+
+def in_box(points, bounding_box):
+    """simulator.py:139-151."""
+    return np.logical_and(np.logical_and(bounding_box[0] - EPS <= points[:, 0], points[:, 0] <= bounding_box[1] + EPS),
+                          np.logical_and(bounding_box[2] - EPS <= points[:, 1], points[:, 1] <= bounding_box[3] + EPS))
+
+
+class BoundedVoronoi:
+    """Bounded Voronoi partition as the reference builds it (simulator.py:154-191): seeds inside the cushioned box are
+    mirrored across its four sides, Qhull computes the diagram of the 5A points and the first A regions are the
+    bounded cells.  Keeps the reference's attribute names (`vertices`, `filtered_points`, `filtered_regions`)."""
+
+    def __init__(self, points, bounding_box):
+        points = np.asarray(points, dtype=np.float64)
+        keep = in_box(points, bounding_box)
+        c = points[keep, :]
+        left = np.copy(c)
+        left[:, 0] = bounding_box[0] - (left[:, 0] - bounding_box[0] + EPS)
+        right = np.copy(c)
+        right[:, 0] = bounding_box[1] + (bounding_box[1] - right[:, 0] + EPS)
+        down = np.copy(c)
+        down[:, 1] = bounding_box[2] - (down[:, 1] - bounding_box[2] + EPS)
+        up = np.copy(c)
+        up[:, 1] = bounding_box[3] + (bounding_box[3] - up[:, 1] + EPS)
+        pts = np.concatenate((c, left, right, down, up), axis=0)
+        vor = Voronoi(pts)
+        self.vertices = vor.vertices
+        self.filtered_points = c
+        self.filtered_regions = [list(vor.regions[r]) for r in vor.point_region[:vor.npoints // 5]]
+        self.bounding_box = np.asarray(bounding_box, dtype=np.float64)
+        # the argmin fast path equals the polygon test only when every seed lies inside the domain box proper
+        self.seeds_inside = bool(np.all((c[:, 0] >= bounding_box[0]) & (c[:, 0] <= bounding_box[1]) &
+                                        (c[:, 1] >= bounding_box[2]) & (c[:, 1] <= bounding_box[3])))
+        self._flat = None
+
+    def __len__(self):
+        return len(self.filtered_regions)
+
+    def cell_vertices(self, i):
+        return self.vertices[self.filtered_regions[i], :]
+
+    def areas(self):
+        """Shoelace area per cell (simulator.py:127-136)."""
+        out = np.empty(len(self))
+        for i in range(len(self)):
+            v = self.cell_vertices(i)
+            x, y = v[:, 0], v[:, 1]
+            out[i] = 0.5 * np.abs(np.dot(x, np.roll(y, 1)) - np.dot(y, np.roll(x, 1)))
+        return out
+
+    def flat(self):
+        """(seeds[A,2], poly_xy[nvert,2], poly_off[A+1]) as contiguous host arrays."""
+        if self._flat is None:
+            off = np.zeros(len(self) + 1, dtype=np.int32)
+            chunks = []
+            for i in range(len(self)):
+                v = self.cell_vertices(i)
+                chunks.append(v)
+                off[i + 1] = off[i] + v.shape[0]
+            poly = np.ascontiguousarray(np.concatenate(chunks, axis=0), dtype=np.float64) if chunks else np.empty((0, 2))
+            self._flat = (np.ascontiguousarray(self.filtered_points, dtype=np.float64), poly, off)
+        return self._flat
+
+
+def polygon_partition(seeds, polygons):
+    """A partition from explicit polygons (list of [n_i,2] arrays); used for in_polygon / sample clustering."""
+    bv = BoundedVoronoi.__new__(BoundedVoronoi)
+    verts = np.concatenate(polygons, axis=0) if polygons else np.empty((0, 2))
+    regions, o = [], 0
+    for p in polygons:
+        regions.append(list(range(o, o + len(p))))
+        o += len(p)
+    bv.vertices = verts
+    bv.filtered_points = np.asarray(seeds, dtype=np.float64).reshape(-1, 2)
+    bv.filtered_regions = regions
+    bv.seeds_inside = False
+    bv._flat = None
+    return bv
+
+
+class _DevPartition:
+    def __init__(self, vor, device):
+        seeds, poly, off = vor.flat()
+        self.A = int(seeds.shape[0])
+        self.nvert = int(off[-1])
+        self.seeds = torch.from_numpy(seeds).to(device)
+        self.poly = torch.from_numpy(poly if poly.size else np.zeros((1, 2))).to(device)
+        self.off = torch.from_numpy(off).to(device)
+
+
+class CoverageGrid:
+    """Grid points xy[G,2] (+ optional truth f[G]) resident on the device, with reusable output buffers."""
+
+    def __init__(self, xy_host, f_host=None, device=None, base_index=0):
+        nat.require_cuda()
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        xy = np.ascontiguousarray(xy_host, dtype=np.float64).reshape(-1, 2)
+        self.G = int(xy.shape[0])
+        self.base_index = int(base_index)
+        self.xy = torch.from_numpy(xy).to(self.device)
+        self.f = None if f_host is None else torch.from_numpy(
+            np.ascontiguousarray(f_host, dtype=np.float64).reshape(-1)).to(self.device)
+        self._work = None
+        self._work_key = None
+
+    def _workspace(self, Ac, Ap):
+        need = int(nat.lib().cov_workspace_bytes(self.G, max(Ac, 1), Ap))
+        if self._work is None or self._work.numel() * 8 < need:
+            self._work = torch.empty(need // 8 + 8, dtype=torch.float64, device=self.device)
+        return self._work
+
+    def assign_reduce(self, lloyd_vor=None, loss_vor=None, w=None, var=None, want_members=False, tie_tol=None):
+        """One fused pass.  Returns a dict of DEVICE tensors: cent[Ac,4], amax_val[Ac], amax_idx[Ac], lossp[Ap,2],
+        members[G,words] (optional)."""
+        dev = self.device
+        C = _DevPartition(lloyd_vor, dev) if lloyd_vor is not None and len(lloyd_vor) else None
+        P = _DevPartition(loss_vor, dev) if loss_vor is not None and len(loss_vor) else None
+        Ac = C.A if C else 0
+        Ap = P.A if P else 0
+        if tie_tol is None:
+            tie_tol = TIE_TOL
+            for v in (lloyd_vor, loss_vor):
+                if v is not None and not v.seeds_inside:
+                    tie_tol = math.inf      # polygons are not plain nearest-seed cells: crossings test everywhere
+        f64 = dict(dtype=torch.float64, device=dev)
+        out = {}
+        cent = torch.empty((Ac, 4), **f64) if Ac else None
+        amax_val = torch.empty(Ac, **f64) if Ac else None
+        amax_idx = torch.empty(Ac, dtype=torch.int64, device=dev) if Ac else None
+        lossp = torch.empty((Ap, 2), **f64) if Ap else None
+        words = (max(Ac, Ap) + 63) // 64
+        words = 1 if words <= 1 else (2 if words == 2 else 4)
+        members = torch.zeros((self.G, words), dtype=torch.int64, device=dev) if (want_members and Ac) else None
+        work = self._workspace(Ac, Ap)
+        rc = nat.lib().cov_assign_reduce(
+            nat.ptr(self.xy), nat.ptr(w), nat.ptr(var), nat.ptr(self.f), self.G, self.base_index,
+            nat.ptr(C.seeds) if C else None, Ac, nat.ptr(C.poly) if C else None, nat.ptr(C.off) if C else None,
+            C.nvert if C else 0,
+            nat.ptr(P.seeds) if P else None, Ap, nat.ptr(P.poly) if P else None, nat.ptr(P.off) if P else None,
+            P.nvert if P else 0,
+            ctypes.c_double(tie_tol), nat.ptr(cent), nat.ptr(amax_val), nat.ptr(amax_idx), nat.ptr(lossp),
+            nat.ptr(members), nat.ptr(work), work.numel() * 8, nat.stream_ptr())
+        nat.check(rc, "cov_assign_reduce")
+        out.update(cent=cent, amax_val=amax_val, amax_idx=amax_idx, lossp=lossp, members=members)
+        return out
+
+    def argmax(self, v_dev):
+        """First-index argmax of a device vector (np.argmax semantics): returns (value, index) device tensors."""
+        val = torch.empty(1, dtype=torch.float64, device=self.device)
+        idx = torch.empty(1, dtype=torch.int64, device=self.device)
+        work = self._workspace(1, 0)
+        nat.check(nat.lib().cov_argmax(nat.ptr(v_dev), int(v_dev.numel()), self.base_index, nat.ptr(val),
+                                       nat.ptr(idx), nat.ptr(work), work.numel() * 8, nat.stream_ptr()), "cov_argmax")
+        return val, idx
+
+
+# ---- host finishing of the per-cell partial sums (O(A) scalar work, same arithmetic as the reference) ----------------
+
+def loss_from_partials(lossp, areas):
+    """simulator.py:215-219: sum_i mean(point_loss_i) * area_i, accumulated in cell order."""
+    loss = 0
+    with np.errstate(invalid="ignore", divide="ignore"):
+        for i in range(lossp.shape[0]):
+            loss += (lossp[i, 0] / lossp[i, 1]) * areas[i]
+    return loss
+
+
+def centroids_from_partials(cent, areas, xmin, xmax, ymin, ymax):
+    """simulator.py:256-271: c = (mean(w p) area) / (mean(w) area), clamped to the grid's extent."""
+    A = cent.shape[0]
+    out = np.empty((A, 2))
+    with np.errstate(invalid="ignore", divide="ignore"):
+        for i in range(A):
+            n = cent[i, 3]
+            f_integral = (cent[i, 0] / n) * areas[i]
+            w_integral = np.array([cent[i, 1] / n, cent[i, 2] / n]) * areas[i]
+            c = w_integral / f_integral
+            if c[0] < xmin:
+                c[0] = xmin
+            if c[0] > xmax:
+                c[0] = xmax
+            if c[1] < ymin:
+                c[1] = ymin
+            if c[1] > ymax:
+                c[1] = ymax
+            out[i] = c
+    return out

@@ -1,0 +1,147 @@
+"""Device-side state of one GP model and the calls into libmfgp_b200 that operate on it.
+
+`DeviceGP` owns the HBM-resident buffers of a model -- training points Xt[cap,2], observations y[cap], covariance /
+Cholesky factor K[npad,npad], its inverse W[npad,npad], scaled coordinates Tt[npad,4], whitened observations z[npad]
+-- and sequences the C-ABI calls of include/mfgp_b200.h on the current CUDA stream.  torch provides memory and
+streams only.  Layout notes are in DESIGN.md ("Data layout in HBM").
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _native as nat
+
+
+def params_struct(p):
+    """p: dict with the evaluated parameters (see gaussian_process.evaluate_hyp)."""
+    return nat.MfgpParams(p["s_L"], p["l_L"], p["s_H"], p["l_H"], p["rho"], p["noise_L"], p["noise_H"],
+                          p["mean_L"], p["mean_H"], p["jitter"], int(p["multi"]), 0)
+
+
+class DeviceGP:
+    def __init__(self, device=None):
+        nat.require_cuda()
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.NL = 0
+        self.NH = 0
+        self.npad = 0
+        self.cap = 0          # allocated padded size of K / W
+        self.Xt = self.y = self.K = self.W = self.Tt = self.z = self.work = None
+        self.info = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self.params = None
+        self.pstruct = None
+        self.fitted = False
+
+    # -- memory -------------------------------------------------------------------------------------------------------
+    def _reserve(self, n):
+        need = nat.npad(n)
+        if need <= self.cap:
+            return
+        cap = max(need, nat.npad(int(self.cap * 1.5)))
+        f64 = dict(dtype=torch.float64, device=self.device)
+        self.K = torch.empty((cap, cap), **f64)
+        self.W = torch.empty((cap, cap), **f64)
+        self.Tt = torch.empty((cap, 4), **f64)
+        self.z = torch.empty(cap, **f64)
+        self.Xt = torch.empty((cap, 2), **f64)
+        self.y = torch.empty(cap, **f64)
+        self.work = torch.empty(int(nat.lib().mfgp_workspace_bytes(cap)) // 8 + 8, **f64)
+        self.cap = cap
+
+    @property
+    def N(self):
+        return self.NL + self.NH
+
+    def set_params(self, params):
+        self.params = dict(params)
+        self.pstruct = params_struct(params)
+
+    # -- fit ----------------------------------------------------------------------------------------------------------
+    def fit(self, Xt_host, y_host, NL, NH, params, check=True):
+        """Upload the training set ([X_L; X_H], [y_L; y_H]) and factorise.  Replaces updt_info
+        (gaussian_process.py:229-255, :493-529)."""
+        N = NL + NH
+        self.params = dict(params)
+        self.pstruct = params_struct(params)
+        self.NL, self.NH = int(NL), int(NH)
+        self.fitted = True
+        if N == 0:
+            self.npad = 0
+            return
+        self._reserve(N)
+        xt = torch.from_numpy(np.ascontiguousarray(Xt_host, dtype=np.float64).reshape(N, 2))
+        yy = torch.from_numpy(np.ascontiguousarray(y_host, dtype=np.float64).reshape(N))
+        self.Xt[:N].copy_(xt, non_blocking=False)
+        self.y[:N].copy_(yy, non_blocking=False)
+        self.refactor(check=check)
+
+    def refactor(self, check=True):
+        """K assembly -> Cholesky -> inverse -> whitening for the data already resident in Xt / y."""
+        N = self.N
+        lib = nat.lib()
+        st = nat.stream_ptr()
+        npad = nat.npad(N)
+        self.npad = npad
+        ld = self.cap
+        pp = ctypes.byref(self.pstruct)
+        nat.check(lib.mfgp_build_train_cov(nat.ptr(self.Xt), self.NL, self.NH, pp, nat.ptr(self.K), npad, ld,
+                                           nat.ptr(self.Tt), st), "mfgp_build_train_cov")
+        nat.check(lib.mfgp_cholesky(nat.ptr(self.K), npad, ld, nat.ptr(self.W), ld, nat.ptr(self.info),
+                                    nat.ptr(self.work), st), "mfgp_cholesky")
+        nat.check(lib.mfgp_tri_inverse(nat.ptr(self.K), npad, ld, nat.ptr(self.W), ld, nat.ptr(self.work), st),
+                  "mfgp_tri_inverse")
+        nat.check(lib.mfgp_whiten(nat.ptr(self.W), npad, ld, nat.ptr(self.y), self.NL, self.NH, pp, nat.ptr(self.z),
+                                  st), "mfgp_whiten")
+        if check:
+            self.check_factor()
+
+    def check_factor(self):
+        info = int(self.info.item())
+        if info != 0:
+            raise np.linalg.LinAlgError(f"Matrix is not positive definite (pivot {info - 1})")
+
+    def append_hifi(self, X_new_host, y_new_host, check=True):
+        """updt / updt_hifi (gaussian_process.py:257-268, :531-542): new points go to the END of [X_L; X_H]; the factor
+        is rebuilt from scratch, as in the reference (which does so even when nothing was added)."""
+        k = 0 if X_new_host is None else int(np.asarray(X_new_host).reshape(-1, 2).shape[0])
+        if k:
+            N = self.N
+            if N + k > self.cap:
+                old_x, old_y = self.Xt, self.y
+                self._reserve(N + k)
+                if N:
+                    self.Xt[:N].copy_(old_x[:N])
+                    self.y[:N].copy_(old_y[:N])
+            self.Xt[N:N + k].copy_(torch.from_numpy(np.ascontiguousarray(X_new_host, dtype=np.float64).reshape(k, 2)))
+            self.y[N:N + k].copy_(torch.from_numpy(np.ascontiguousarray(y_new_host, dtype=np.float64).reshape(k)))
+            self.NH += k
+        if self.N:
+            self.refactor(check=check)
+
+    # -- posterior ----------------------------------------------------------------------------------------------------
+    def posterior(self, xs_dev, mu_out=None, var_out=None, vcache=None):
+        """Posterior mean / variance for device-resident points xs_dev[G,2].  Replaces predict
+        (gaussian_process.py:121-148, :401-438), diagonal only.  Returns device tensors (mu[G], var[G])."""
+        G = int(xs_dev.shape[0])
+        f64 = dict(dtype=torch.float64, device=self.device)
+        mu = torch.empty(G, **f64) if mu_out is None else mu_out
+        var = torch.empty(G, **f64) if var_out is None else var_out
+        lib = nat.lib()
+        ldv = 0 if vcache is None else int(vcache.shape[1])
+        nat.check(lib.mfgp_posterior(nat.ptr(xs_dev), G, nat.ptr(self.Tt), self.NL, self.NH, nat.ptr(self.W),
+                                     self.npad, self.cap, nat.ptr(self.z), ctypes.byref(self.pstruct), nat.ptr(mu),
+                                     nat.ptr(var), nat.ptr(vcache), ldv, nat.stream_ptr()), "mfgp_posterior")
+        return mu, var
+
+    def clone(self):
+        other = DeviceGP(self.device)
+        other.NL, other.NH, other.npad, other.cap = self.NL, self.NH, self.npad, self.cap
+        other.params = None if self.params is None else dict(self.params)
+        other.pstruct = None if self.params is None else params_struct(self.params)
+        other.fitted = self.fitted
+        for name in ("Xt", "y", "K", "W", "Tt", "z", "work"):
+            t = getattr(self, name)
+            setattr(other, name, None if t is None else t.clone())
+        other.info = self.info.clone()
+        return other

@@ -1,0 +1,106 @@
+"""ctypes binding of libmfgp_b200.so (the C-ABI of include/mfgp_b200.h).
+
+There is NO fallback: if the shared library is missing or a GPU is not present the product raises.  PyTorch is used
+only for plumbing (device memory, streams, NCCL); every arithmetic step of the hot path runs in the CUDA library.
+"""
+import ctypes
+import os
+from ctypes import POINTER, Structure, c_char_p, c_double, c_int, c_int32, c_int64, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libmfgp_b200.so")
+
+MFGP_OK, MFGP_ERR_INVALID, MFGP_ERR_NOT_SPD, MFGP_ERR_CUDA, MFGP_ERR_EMPTY_CELL = 0, -1, -2, -3, -4
+TILE = 64
+
+
+class NativeLibraryMissing(RuntimeError):
+    pass
+
+
+class MfgpParams(Structure):
+    _fields_ = [("s_L", c_double), ("l_L", c_double), ("s_H", c_double), ("l_H", c_double), ("rho", c_double),
+                ("noise_L", c_double), ("noise_H", c_double), ("mean_L", c_double), ("mean_H", c_double),
+                ("jitter", c_double), ("multi", c_int32), ("reserved", c_int32)]
+
+
+# name -> (restype, argtypes); this table is also what tests/test_abi.py checks against include/mfgp_b200.h
+SIGNATURES = {
+    "mfgp_version": (c_char_p, []),
+    "mfgp_last_error": (c_char_p, []),
+    "mfgp_launch_count": (c_int64, []),
+    "mfgp_npad": (c_int64, [c_int64]),
+    "mfgp_workspace_bytes": (c_int64, [c_int64]),
+    "mfgp_build_train_cov": (c_int, [c_void_p, c_int64, c_int64, POINTER(MfgpParams), c_void_p, c_int64, c_int64,
+                                     c_void_p, c_void_p]),
+    "mfgp_cholesky": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
+    "mfgp_tri_inverse": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_void_p]),
+    "mfgp_whiten": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64, POINTER(MfgpParams), c_void_p,
+                            c_void_p]),
+    "mfgp_posterior": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64, c_void_p,
+                               POINTER(MfgpParams), c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+    "cov_assign_reduce": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64,
+                                  c_void_p, c_int64, c_void_p, c_void_p, c_int64,
+                                  c_void_p, c_int64, c_void_p, c_void_p, c_int64,
+                                  c_double, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
+                                  c_void_p]),
+    "cov_workspace_bytes": (c_int64, [c_int64, c_int64, c_int64]),
+    "cov_argmax": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+    "choi_greedy": (c_int64, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_void_p, POINTER(MfgpParams),
+                              c_double, c_int64, POINTER(c_int64), c_void_p, c_int64, c_void_p]),
+}
+
+_lib = None
+
+
+def lib():
+    """The loaded shared library; raises NativeLibraryMissing (never falls back to a CPU path)."""
+    global _lib
+    if _lib is None:
+        if not os.path.isfile(LIB_PATH):
+            raise NativeLibraryMissing(
+                f"{LIB_PATH} not found: build it with `make -C {os.path.dirname(LIB_PATH)}` "
+                "(or `python -c 'import __graft_entry__ as g; g.build()'`). There is no CPU fallback.")
+        handle = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = handle
+    return _lib
+
+
+def last_error():
+    return lib().mfgp_last_error().decode()
+
+
+def check(rc, what):
+    if rc == MFGP_OK:
+        return
+    if rc == MFGP_ERR_CUDA:
+        raise RuntimeError(f"{what}: CUDA error: {last_error()}")
+    if rc == MFGP_ERR_INVALID:
+        raise ValueError(f"{what}: invalid argument")
+    raise RuntimeError(f"{what}: error code {rc}")
+
+
+def npad(n):
+    return max(TILE, (int(n) + TILE - 1) // TILE * TILE)
+
+
+def ptr(t):
+    """Device pointer of a torch tensor (or None -> NULL)."""
+    return None if t is None else c_void_p(t.data_ptr())
+
+
+def stream_ptr(stream=None):
+    import torch
+    s = stream if stream is not None else torch.cuda.current_stream()
+    return c_void_p(s.cuda_stream)
+
+
+def require_cuda():
+    import torch
+    if not torch.cuda.is_available():
+        raise RuntimeError("mfgp_coverage_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    lib()

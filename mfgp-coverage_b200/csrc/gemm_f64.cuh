@@ -1,0 +1,137 @@
+// Batched fp64 tile GEMM on DMMA for the factorisation kernels (Cholesky panel solve, SYRK trailing update,
+// block-doubling triangular inverse).  All dimensions are multiples of 64 (buffers are padded to MFGP_TILE), so there
+// is no edge handling.  C[M,N] = alpha * A[M,K] * op(B) + beta * C, row-major, one 64x64 C tile per 128-thread CTA
+// (2x2 warps, 32x32 per warp = 4x4 DMMA 8x8 tiles), K streamed in 16-wide cp.async double-buffered slabs.
+#pragma once
+#include "common.cuh"
+
+namespace mfgp {
+
+enum GemmMode : int {
+    GEMM_GENERAL = 0,
+    GEMM_SYRK_LOWER = 1,   // only C tiles with row-tile >= col-tile are computed (B must be A, B_TRANS)
+    GEMM_A_LOWER = 2,      // A[M,K=M] lower triangular: k < m0 + 64
+    GEMM_B_LOWER = 3       // B[K=N,N] (not transposed) lower triangular: k >= n0
+};
+
+struct GemmArgs {
+    const double* A; int64_t lda; int64_t strideA;
+    const double* B; int64_t ldb; int64_t strideB;
+    double* C; int64_t ldc; int64_t strideC;
+    int M, N, K;
+    double alpha, beta;
+    int mode;
+};
+
+constexpr int GT = 64;        // C tile
+constexpr int GK = 16;        // K slab
+constexpr int GLD = GK + 4;   // padded smem row (doubles): rows land on distinct 8-bank groups for the fragment reads
+constexpr int GLDB = GT + 4;  // padded row for the non-transposed B slab [GK][GT]
+
+template <bool B_TRANS>
+__global__ void __launch_bounds__(128) gemm_f64_kernel(GemmArgs g) {
+    const int m0 = blockIdx.y * GT, n0 = blockIdx.x * GT;
+    if (g.mode == GEMM_SYRK_LOWER && n0 > m0) return;
+    const double* A = g.A + (int64_t)blockIdx.z * g.strideA;
+    const double* B = g.B + (int64_t)blockIdx.z * g.strideB;
+    double* C = g.C + (int64_t)blockIdx.z * g.strideC;
+
+    __shared__ __align__(16) double As[2][GT * GLD];
+    __shared__ __align__(16) double Bs[2][B_TRANS ? GT * GLD : GK * GLDB];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = (warp >> 1) * 32, wn = (warp & 1) * 32;
+    const int gq = lane >> 2, tq = lane & 3;
+
+    int kbeg = 0, kend = g.K;
+    if (g.mode == GEMM_A_LOWER) kend = min(g.K, m0 + GT);
+    if (g.mode == GEMM_B_LOWER) kbeg = n0;
+
+    double acc[4][4][2];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+    auto stage = [&](int buf, int k0) {
+        // A slab: 64 rows x 16 doubles = 512 16-byte chunks
+#pragma unroll
+        for (int c = tid; c < GT * (GK / 2); c += 128) {
+            int r = c >> 3, q = c & 7;
+            cp_async16(&As[buf][r * GLD + q * 2], A + (int64_t)(m0 + r) * g.lda + k0 + q * 2, true);
+        }
+        if (B_TRANS) {
+#pragma unroll
+            for (int c = tid; c < GT * (GK / 2); c += 128) {
+                int r = c >> 3, q = c & 7;
+                cp_async16(&Bs[buf][r * GLD + q * 2], B + (int64_t)(n0 + r) * g.ldb + k0 + q * 2, true);
+            }
+        } else {
+#pragma unroll
+            for (int c = tid; c < GK * (GT / 2); c += 128) {
+                int r = c >> 5, q = c & 31;
+                cp_async16(&Bs[buf][r * GLDB + q * 2], B + (int64_t)(k0 + r) * g.ldb + n0 + q * 2, true);
+            }
+        }
+        cp_async_commit();
+    };
+
+    const int nslab = (kend - kbeg) / GK;
+    if (nslab > 0) stage(0, kbeg);
+    for (int s = 0; s < nslab; s++) {
+        const int buf = s & 1;
+        if (s + 1 < nslab) {
+            stage(buf ^ 1, kbeg + (s + 1) * GK);
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < GK; kk += 4) {
+            double a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) a[i] = As[buf][(wm + i * 8 + gq) * GLD + kk + tq];
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                b[j] = B_TRANS ? Bs[buf][(wn + j * 8 + gq) * GLD + kk + tq] : Bs[buf][(kk + tq) * GLDB + wn + j * 8 + gq];
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+        }
+        __syncthreads();
+    }
+
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int64_t row = m0 + wm + i * 8 + gq;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            double2* p = reinterpret_cast<double2*>(C + row * g.ldc + n0 + wn + j * 8 + tq * 2);
+            double2 out;
+            if (g.beta != 0.0) {
+                double2 old = *p;
+                out.x = g.alpha * acc[i][j][0] + g.beta * old.x;
+                out.y = g.alpha * acc[i][j][1] + g.beta * old.y;
+            } else {
+                out.x = g.alpha * acc[i][j][0];
+                out.y = g.alpha * acc[i][j][1];
+            }
+            *p = out;
+        }
+    }
+}
+
+inline int launch_gemm(const GemmArgs& g, bool b_trans, int batch, cudaStream_t st) {
+    if (g.M <= 0 || g.N <= 0 || batch <= 0) return MFGP_OK;
+    dim3 grid(g.N / GT, g.M / GT, batch);
+    if (b_trans)
+        gemm_f64_kernel<true><<<grid, 128, 0, st>>>(g);
+    else
+        gemm_f64_kernel<false><<<grid, 128, 0, st>>>(g);
+    MFGP_LAUNCH_CHECK();
+    return MFGP_OK;
+}
+
+}  // namespace mfgp

@@ -1,0 +1,257 @@
+// GP fit on the device: training covariance, blocked Cholesky, triangular inverse, whitened observations.
+// Replaces SFGP.updt_info (reference gaussian_process.py:229-255) and MFGP.updt_info (:493-529).
+#include "common.cuh"
+#include "gemm_f64.cuh"
+
+namespace mfgp {
+
+// ---- K assembly ------------------------------------------------------------------------------------------------------
+// K_LL = k_L + noise_L I, K_LH = rho k_L, K_HH = rho^2 k_L + k_H + noise_H I, then + jitter I (gaussian_process.py:
+// 523-529); SF: k + noise I + jitter I (:253-254).  Padding rows/cols [N, npad) carry the identity.
+__global__ void build_train_cov_kernel(const double* __restrict__ Xt, int NL, int NH, DevParams p, double* __restrict__ K,
+                                       int npad, int64_t ld, double* __restrict__ Tt) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.y * blockDim.y + threadIdx.y;
+    const int N = NL + NH;
+    if (i >= npad || j >= npad) return;
+    double v;
+    if (i >= N || j >= N) {
+        v = (i == j) ? 1.0 : 0.0;
+    } else {
+        const double xi = Xt[2 * i], yi = Xt[2 * i + 1], xj = Xt[2 * j], yj = Xt[2 * j + 1];
+        const bool iL = i < NL, jL = j < NL;
+        if (p.multi) {
+            const double kL = rbf_scaled(xi / p.l_L, yi / p.l_L, xj / p.l_L, yj / p.l_L, p.s_L);
+            if (iL && jL) {
+                v = kL;
+                if (i == j) v = v + p.noise_L;
+            } else if (iL != jL) {
+                v = p.rho * kL;
+            } else {
+                const double kH = rbf_scaled(xi / p.l_H, yi / p.l_H, xj / p.l_H, yj / p.l_H, p.s_H);
+                v = __dadd_rn(__dmul_rn(p.rho2, kL), kH);
+                if (i == j) v = v + p.noise_H;
+            }
+        } else {
+            v = rbf_scaled(xi / p.l_H, yi / p.l_H, xj / p.l_H, yj / p.l_H, p.s_H);
+            if (i == j) v = v + p.noise_H;
+        }
+        if (i == j) v = v + p.jitter;
+    }
+    K[(int64_t)i * ld + j] = v;
+    if (j == 0 && Tt != nullptr) {
+        double4 t = make_double4(0.0, 0.0, 0.0, 0.0);
+        if (i < N) {
+            const double xi = Xt[2 * i], yi = Xt[2 * i + 1];
+            t = make_double4(xi / p.l_L, yi / p.l_L, xi / p.l_H, yi / p.l_H);
+        }
+        reinterpret_cast<double4*>(Tt)[i] = t;
+    }
+}
+
+// ---- 64x64 diagonal block: Cholesky + inverse in one CTA --------------------------------------------------------------
+constexpr int PB = 64;
+constexpr int PLD = PB + 1;
+
+__global__ void __launch_bounds__(256) potrf_diag_kernel(double* __restrict__ A, int64_t ld, double* __restrict__ Winv,
+                                                         int64_t ldw, int32_t* __restrict__ info, int jblk) {
+    extern __shared__ __align__(16) double potrf_smem[];   // 2 x 64x65 doubles: above the 48 KB static limit
+    double* S = potrf_smem;
+    double* X = potrf_smem + PB * PLD;
+    __shared__ int bad;
+    const int tid = threadIdx.x;
+    if (tid == 0) bad = 0;
+    for (int e = tid; e < PB * PB; e += 256) {
+        const int r = e >> 6, c = e & 63;
+        S[r * PLD + c] = (c <= r) ? A[(int64_t)r * ld + c] : 0.0;
+    }
+    for (int j = 0; j < PB; j++) {
+        __syncthreads();
+        const double piv = S[j * PLD + j];
+        if (!(piv > 0.0)) {     // uniform: every thread reads the same pivot
+            if (tid == 0) {
+                bad = 1;
+                atomicCAS(info, 0, jblk * PB + j + 1);
+            }
+            break;
+        }
+        const double d = sqrt(piv);
+        __syncthreads();
+        if (tid == 0) S[j * PLD + j] = d;
+        if (tid > j && tid < PB) S[tid * PLD + j] = S[tid * PLD + j] / d;
+        __syncthreads();
+        // trailing update of the lower triangle right of column j: rows i > j, columns j < c <= i
+        const int rem = PB - 1 - j;
+        for (int e = tid; e < rem * rem; e += 256) {
+            const int i = j + 1 + e / rem, c = j + 1 + e % rem;
+            if (c <= i) S[i * PLD + c] -= S[i * PLD + j] * S[c * PLD + j];
+        }
+    }
+    __syncthreads();
+    if (bad) {   // leave a harmless identity so later kernels stay finite; the host raises on `info`
+        for (int e = tid; e < PB * PB; e += 256) {
+            const int r = e >> 6, c = e & 63;
+            S[r * PLD + c] = (r == c) ? 1.0 : 0.0;
+        }
+        __syncthreads();
+    }
+    for (int e = tid; e < PB * PB; e += 256) {
+        const int r = e >> 6, c = e & 63;
+        if (c <= r) A[(int64_t)r * ld + c] = S[r * PLD + c];
+    }
+    // inverse: thread c solves L x = e_c by forward substitution (column c of L^-1), two partial sums for ILP
+    if (tid < PB) {
+        const int c = tid;
+        for (int i = 0; i < c; i++) X[i * PLD + c] = 0.0;
+        for (int i = c; i < PB; i++) {
+            double s0 = (i == c) ? 1.0 : 0.0, s1 = 0.0;
+            int k = c;
+            for (; k + 1 < i; k += 2) {
+                s0 -= S[i * PLD + k] * X[k * PLD + c];
+                s1 -= S[i * PLD + k + 1] * X[(k + 1) * PLD + c];
+            }
+            if (k < i) s0 -= S[i * PLD + k] * X[k * PLD + c];
+            X[i * PLD + c] = (s0 + s1) / S[i * PLD + i];
+        }
+    }
+    __syncthreads();
+    if (Winv != nullptr)
+        for (int e = tid; e < PB * PB; e += 256) {
+            const int r = e >> 6, c = e & 63;
+            Winv[(int64_t)r * ldw + c] = X[r * PLD + c];
+        }
+}
+
+__global__ void zero_offdiag_blocks_kernel(double* __restrict__ W, int npad, int64_t ldw) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.y;
+    if (j >= npad) return;
+    if ((i >> 6) != (j >> 6)) W[(int64_t)i * ldw + j] = 0.0;
+}
+
+// z = W (y - mean): one warp per row; W is lower triangular so only k <= row contributes
+__global__ void whiten_kernel(const double* __restrict__ W, int npad, int64_t ldw, const double* __restrict__ y, int NL,
+                              int NH, double mean_L, double mean_H, double* __restrict__ z) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= npad) return;
+    const int N = NL + NH;
+    const int kmax = min(row + 1, N);
+    double s = 0.0;
+    for (int k = lane; k < kmax; k += 32) {
+        const double yc = y[k] - (k < NL ? mean_L : mean_H);
+        s += W[(int64_t)row * ldw + k] * yc;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) z[row] = s;
+}
+
+}  // namespace mfgp
+
+using namespace mfgp;
+
+extern "C" int64_t mfgp_npad(int64_t n) {
+    if (n <= 0) return MFGP_TILE;
+    return (n + MFGP_TILE - 1) / MFGP_TILE * MFGP_TILE;
+}
+
+extern "C" int64_t mfgp_workspace_bytes(int64_t npad) {
+    return npad * npad * 2 + (int64_t)PB * PB * 8 + 256;   // T blocks of the inverse (npad^2/4 doubles) + one 64x64 block
+}
+
+extern "C" int mfgp_build_train_cov(const double* Xt, int64_t NL, int64_t NH, const mfgp_params* p_host, double* K,
+                                    int64_t npad, int64_t ld, double* Tt, void* stream) {
+    if (!p_host || !K || NL < 0 || NH < 0 || npad < NL + NH || npad % MFGP_TILE || ld < npad) return MFGP_ERR_INVALID;
+    if (NL + NH > 0 && !Xt) return MFGP_ERR_INVALID;
+    if (!p_host->multi && NL != 0) return MFGP_ERR_INVALID;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    dim3 block(32, 8), grid((unsigned)((npad + 31) / 32), (unsigned)((npad + 7) / 8));
+    build_train_cov_kernel<<<grid, block, 0, st>>>(Xt, (int)NL, (int)NH, make_dev_params(*p_host), K, (int)npad, ld, Tt);
+    MFGP_LAUNCH_CHECK();
+    return MFGP_OK;
+}
+
+extern "C" int mfgp_cholesky(double* K, int64_t npad, int64_t ld, double* W, int64_t ldw, int32_t* info, void* work,
+                             void* stream) {
+    if (!K || !info || npad <= 0 || npad % MFGP_TILE || ld < npad) return MFGP_ERR_INVALID;
+    if (!W && !work) return MFGP_ERR_INVALID;
+    if (W && ldw < npad) return MFGP_ERR_INVALID;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    MFGP_CUDA_CHECK(cudaMemsetAsync(info, 0, sizeof(int32_t), st));
+    const int nb = (int)(npad / PB);
+    constexpr int POTRF_SMEM = 2 * PB * PLD * sizeof(double);
+    MFGP_CUDA_CHECK(cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, POTRF_SMEM));
+    for (int j = 0; j < nb; j++) {
+        double* Ajj = K + (int64_t)j * PB * (ld + 1);
+        double* Wjj = W ? W + (int64_t)j * PB * (ldw + 1) : static_cast<double*>(work);
+        const int64_t ldi = W ? ldw : PB;
+        potrf_diag_kernel<<<1, 256, POTRF_SMEM, st>>>(Ajj, ld, Wjj, ldi, info, j);
+        MFGP_LAUNCH_CHECK();
+        const int rem = (int)(npad - (int64_t)(j + 1) * PB);
+        if (rem <= 0) break;
+        double* A21 = K + (int64_t)(j + 1) * PB * ld + (int64_t)j * PB;
+        GemmArgs t{};   // L21 = A21 * inv(L11)^T, in place
+        t.A = A21; t.lda = ld; t.B = Wjj; t.ldb = ldi; t.C = A21; t.ldc = ld;
+        t.M = rem; t.N = PB; t.K = PB; t.alpha = 1.0; t.beta = 0.0; t.mode = GEMM_GENERAL;
+        int rc = launch_gemm(t, true, 1, st);
+        if (rc) return rc;
+        GemmArgs s{};   // A22 -= L21 L21^T (lower tiles)
+        s.A = A21; s.lda = ld; s.B = A21; s.ldb = ld; s.C = K + (int64_t)(j + 1) * PB * (ld + 1); s.ldc = ld;
+        s.M = rem; s.N = rem; s.K = PB; s.alpha = -1.0; s.beta = 1.0; s.mode = GEMM_SYRK_LOWER;
+        rc = launch_gemm(s, true, 1, st);
+        if (rc) return rc;
+    }
+    return MFGP_OK;
+}
+
+extern "C" int mfgp_tri_inverse(const double* L, int64_t npad, int64_t ld, double* W, int64_t ldw, void* work,
+                                void* stream) {
+    if (!L || !W || !work || npad <= 0 || npad % MFGP_TILE || ld < npad || ldw < npad) return MFGP_ERR_INVALID;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    double* T = static_cast<double*>(work);
+    {
+        dim3 grid((unsigned)((npad + 255) / 256), (unsigned)npad);
+        zero_offdiag_blocks_kernel<<<grid, 256, 0, st>>>(W, (int)npad, ldw);
+        MFGP_LAUNCH_CHECK();
+    }
+    // block doubling: [[W11,0],[W21,W22]] with W21 = -W22 (L21 W11); all pairs of one level are independent
+    for (int64_t b = PB; b < npad; b *= 2) {
+        const int nfull = (int)(npad / (2 * b));
+        const int64_t rem = npad - 2 * b * nfull;
+        for (int pass = 0; pass < 2; pass++) {
+            int batch;
+            int64_t top, h;
+            if (pass == 0) { batch = nfull; top = 0; h = b; }
+            else { batch = (rem > b) ? 1 : 0; top = 2 * b * nfull; h = rem - b; }
+            if (batch == 0) continue;
+            GemmArgs g1{};   // T = L21 * W11   (W11 lower: k >= n0)
+            g1.A = L + (top + b) * ld + top; g1.lda = ld; g1.strideA = 2 * b * (ld + 1);
+            g1.B = W + top * (ldw + 1); g1.ldb = ldw; g1.strideB = 2 * b * (ldw + 1);
+            g1.C = T; g1.ldc = b; g1.strideC = b * b;
+            g1.M = (int)h; g1.N = (int)b; g1.K = (int)b; g1.alpha = 1.0; g1.beta = 0.0; g1.mode = GEMM_B_LOWER;
+            int rc = launch_gemm(g1, false, batch, st);
+            if (rc) return rc;
+            GemmArgs g2{};   // W21 = -W22 * T  (W22 lower: k < m0 + 64)
+            g2.A = W + (top + b) * (ldw + 1); g2.lda = ldw; g2.strideA = 2 * b * (ldw + 1);
+            g2.B = T; g2.ldb = b; g2.strideB = b * b;
+            g2.C = W + (top + b) * ldw + top; g2.ldc = ldw; g2.strideC = 2 * b * (ldw + 1);
+            g2.M = (int)h; g2.N = (int)b; g2.K = (int)h; g2.alpha = -1.0; g2.beta = 0.0; g2.mode = GEMM_A_LOWER;
+            rc = launch_gemm(g2, false, batch, st);
+            if (rc) return rc;
+        }
+    }
+    return MFGP_OK;
+}
+
+extern "C" int mfgp_whiten(const double* W, int64_t npad, int64_t ldw, const double* y, int64_t NL, int64_t NH,
+                           const mfgp_params* p_host, double* z, void* stream) {
+    if (!W || !z || !p_host || npad <= 0 || npad % MFGP_TILE || ldw < npad || NL + NH > npad) return MFGP_ERR_INVALID;
+    if (NL + NH > 0 && !y) return MFGP_ERR_INVALID;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int wpb = 8;
+    whiten_kernel<<<(unsigned)((npad + wpb - 1) / wpb), wpb * 32, 0, st>>>(W, (int)npad, ldw, y, (int)NL, (int)NH,
+                                                                          p_host->mean_L, p_host->mean_H, z);
+    MFGP_LAUNCH_CHECK();
+    return MFGP_OK;
+}

@@ -1,0 +1,194 @@
+"""gaussian_process.py -- drop-in for the reference module of the same name, backed by libmfgp_b200 on a B200.
+
+Mirrors the call surface of the reference's `SFGP` (gaussian_process.py:23-268) and `MFGP` (:271-578) that the
+coverage algorithms use: construction from arrays, `hyp` assigned after construction (simulator.py:72-73, :99-100),
+`updt_info`, `updt` / `updt_hifi`, `predict`, and `copy.deepcopy` support.  Differences, both deliberate:
+
+  * `predict(X_star)` returns `(mu[G,1], var[G])` -- the posterior VARIANCE VECTOR, not the G x G covariance matrix
+    (gaussian_process.py:146, :435-436) of which the reference's callers only ever take `np.diag`
+    (simulator.py:301, :341, :685, :855).  A 1M-point grid would need an 8 TB matrix.
+  * hyper-parameter training (`train`, `likelihood`; autograd + L-BFGS, offline) is out of scope; the `*_hyp.csv`
+    files it produces are consumed unchanged.
+
+Every arithmetic step runs on the GPU through the C-ABI in include/mfgp_b200.h; there is no CPU fallback.
+"""
+import copy
+
+import numpy as np
+import torch
+
+from ._engine import DeviceGP
+
+JITTER = 1e-8
+
+
+def evaluate_hyp(hyp, raw_means=False):
+    """Log-scaled hyper-parameters -> evaluated parameters (dict).
+
+    4 entries [mu, s^2, L, noise] (gaussian_process.py:132, :248-251) or 9 entries
+    [mu_lo, s^2_lo, L_lo, mu_hi, s^2_hi, L_hi, rho, noise_lo, noise_hi] (:411-416, :510-514).  `raw_means=True` selects
+    the 2020 convention (mean = hyp[0], not exp(hyp[0])) that the reference's older logged runs were produced with."""
+    hyp = np.asarray(hyp, dtype=np.float64).reshape(-1)
+    if hyp.size == 4:
+        mean = hyp[0] if raw_means else np.exp(hyp[0])
+        return dict(multi=0, s_L=0.0, l_L=1.0, s_H=float(np.exp(hyp[1])), l_H=float(np.exp(hyp[2])), rho=1.0,
+                    noise_L=0.0, noise_H=float(np.exp(hyp[3])), mean_L=0.0, mean_H=float(mean), jitter=JITTER)
+    if hyp.size == 9:
+        rho = np.exp(hyp[6])
+        if raw_means:
+            mean_L = hyp[0]
+            mean_H = rho * mean_L + hyp[3]
+        else:
+            mean_L = np.exp(hyp[0])
+            mean_H = rho * mean_L + np.exp(hyp[3])
+        return dict(multi=1, s_L=float(np.exp(hyp[1])), l_L=float(np.exp(hyp[2])), s_H=float(np.exp(hyp[4])),
+                    l_H=float(np.exp(hyp[5])), rho=float(rho), noise_L=float(np.exp(hyp[7])),
+                    noise_H=float(np.exp(hyp[8])), mean_L=float(mean_L), mean_H=float(mean_H), jitter=JITTER)
+    raise TypeError("Hyperparameters must be of length 4 (single-fidelity) or 9 (multi-fidelity)")
+
+
+def prior_variance(params):
+    """k(x, x) of the empty model: what `np.amax(var_star)` evaluates to at simulator.py:672, :842, :1014."""
+    if params["multi"]:
+        return params["rho"] ** 2 * params["s_L"] + params["s_H"]
+    return params["s_H"]
+
+
+class _GPBase:
+    raw_means = False     # set True to reproduce runs logged with the pre-exp() mean convention
+
+    def _init_device(self):
+        self._dev = DeviceGP()
+        self._grid_key = None
+        self._grid_dev = None
+        self.L = np.empty([0, 0])
+
+    @property
+    def engine(self):
+        return self._dev
+
+    def params(self):
+        return evaluate_hyp(self.hyp, self.raw_means)
+
+    def _upload_grid(self, X_star):
+        xs = np.ascontiguousarray(X_star, dtype=np.float64).reshape(-1, 2)
+        host = torch.from_numpy(xs)
+        return host.to(self._dev.device, non_blocking=False)
+
+    def predict_device(self, xs_dev, mu_out=None, var_out=None, vcache=None):
+        """Posterior on device-resident points; returns device tensors (mu[G], var[G])."""
+        if not self._dev.fitted:
+            self._refit(check=True)
+        return self._dev.posterior(xs_dev, mu_out, var_out, vcache)
+
+    def predict(self, X_star):
+        """Posterior mean [G,1] and variance [G] at X_star[G,2] (host arrays in, host arrays out)."""
+        xs_dev = self._upload_grid(X_star)
+        mu, var = self.predict_device(xs_dev)
+        return mu.cpu().numpy().reshape(-1, 1), var.cpu().numpy()
+
+    def factor(self):
+        """Lower Cholesky factor L[N,N] as a host array (the reference keeps it in `self.L`)."""
+        d = self._dev
+        if d.N == 0:
+            return np.empty([0, 0])
+        return torch.tril(d.K[:d.N, :d.N]).cpu().numpy()
+
+    def __deepcopy__(self, memo):
+        cls = self.__class__
+        other = cls.__new__(cls)
+        memo[id(self)] = other
+        for k, v in self.__dict__.items():
+            if k == "_dev":
+                other._dev = v.clone()
+            elif k in ("_grid_dev", "_grid_key"):
+                setattr(other, k, None)
+            else:
+                setattr(other, k, copy.deepcopy(v, memo))
+        return other
+
+
+class SFGP(_GPBase):
+    """Single-fidelity GP (reference gaussian_process.py:23-268)."""
+
+    def __init__(self, X, y, len):
+        self.D = X.shape[1]
+        self.X = X
+        self.y = y
+        hyp = np.log(np.ones(self.D + 1))
+        self.idx_theta = np.arange(hyp.shape[0])
+        hyp = np.concatenate([hyp, np.array([-4.0])])
+        hyp[0] = -4.0
+        hyp[2] = np.log(len)
+        self.hyp = hyp
+        self.jitter = JITTER
+        self._init_device()
+
+    def _refit(self, check=True):
+        N = self.X.shape[0]
+        self._dev.fit(self.X, self.y, 0, N, self.params(), check=check)
+
+    def updt_info(self, X_new, y_new):
+        self.X = X_new
+        self.y = y_new
+        self._refit()
+
+    def updt(self, X_addition, y_addition):
+        self.X = np.vstack((self.X, X_addition))
+        self.y = np.vstack((self.y, y_addition))
+        d = self._dev
+        if d.fitted and d.N + np.asarray(X_addition).reshape(-1, 2).shape[0] == self.X.shape[0]:
+            d.set_params(self.params())
+            d.append_hifi(X_addition, y_addition)      # device already holds the old rows: upload only the new ones
+        else:
+            self._refit()
+
+
+class MFGP(_GPBase):
+    """Two-level AR1 multi-fidelity GP (reference gaussian_process.py:271-578)."""
+
+    def __init__(self, X_L, y_L, X_H, y_H, len_L, len_H):
+        self.D = X_H.shape[1]
+        self.X_L = X_L
+        self.y_L = y_L
+        self.X_H = X_H
+        self.y_H = y_H
+        hyp = np.ones(self.D + 1)
+        hyp[0] = 0
+        self.idx_theta_L = np.arange(hyp.shape[0])
+        hyp = np.concatenate((hyp, hyp))
+        self.idx_theta_H = np.arange(self.idx_theta_L[-1] + 1, hyp.shape[0])
+        hyp = np.concatenate((hyp, np.array([-1.0]), np.array([0, 0])))
+        hyp[0] = 0
+        hyp[3] = 0
+        hyp[2] = np.log(len_L)
+        hyp[5] = np.log(len_H)
+        self.hyp = hyp
+        self.jitter = JITTER
+        self._init_device()
+
+    def _refit(self, check=True):
+        NL, NH = self.X_L.shape[0], self.X_H.shape[0]
+        Xt = np.vstack((np.asarray(self.X_L, dtype=np.float64).reshape(-1, 2),
+                        np.asarray(self.X_H, dtype=np.float64).reshape(-1, 2)))
+        y = np.vstack((np.asarray(self.y_L, dtype=np.float64).reshape(-1, 1),
+                       np.asarray(self.y_H, dtype=np.float64).reshape(-1, 1)))
+        self._dev.fit(Xt, y, NL, NH, self.params(), check=check)
+
+    def updt_info(self, X_L_new, y_L_new, X_H_new, y_H_new):
+        self.X_L = X_L_new
+        self.y_L = y_L_new
+        self.X_H = X_H_new
+        self.y_H = y_H_new
+        self._refit()
+
+    def updt_hifi(self, X_H_addition, y_H_addition):
+        self.X_H = np.vstack((self.X_H, X_H_addition))
+        self.y_H = np.vstack((self.y_H, y_H_addition))
+        d = self._dev
+        k = np.asarray(X_H_addition).reshape(-1, 2).shape[0]
+        if d.fitted and d.NL == self.X_L.shape[0] and d.NH + k == self.X_H.shape[0]:
+            d.set_params(self.params())
+            d.append_hifi(X_H_addition, y_H_addition)
+        else:
+            self._refit()

@@ -1,0 +1,120 @@
+"""runner.py -- drop-in for the reference's batch driver (reference runner.py:33-171).
+
+`run_sim(args)` keeps the reference's 12-tuple and algorithm-name substring dispatch (runner.py:46-59); `run()` keeps
+its experiment literals as keyword defaults (runner.py:80-100), the hyper-parameter / prior selection rules
+(`"mf" in algo`, `"_n" in algo`, :119-128) and the three CSVs per algorithm `{prefix}_{algo}_{loss,agent,sample}.csv`
+written with pandas' default index column (:150-156), so `analysis.py` keeps working on the output.
+
+The reference fans simulations out over a `multiprocessing.Pool` of CPU workers (:131-141).  Here `n_processors`
+worker processes are spawned one per GPU slot (worker r uses device r % #GPUs) and the replicate simulations are
+sharded over them -- run-sharding, no communication until the host concatenates the logs (:144-147).
+"""
+import random
+import time
+
+import numpy as np
+import pandas as pd
+
+line_break = "\n" + "".join(["-" for i in range(100)]) + "\n"
+slash_break = "\n" + "".join(["/" for i in range(100)]) + "\n"
+
+eps = 0.1
+
+
+def run_sim(args):
+    """reference runner.py:33-69."""
+    from .simulator import choi, lloyd, periodic, todescato
+    (out_name, algo, sim_num, iterations, agents, truth, sigma_n, prior, hyp, console, plotter, log) = args
+    print(line_break + f"Start Simulation {sim_num} : {algo}" + line_break)
+    sim_start = time.time()
+    x_positions = [random.random() for i in range(agents)]
+    y_positions = [random.random() for i in range(agents)]
+    positions = np.column_stack((x_positions, y_positions))
+    if "choi" in algo:
+        fn = choi
+    elif "todescato" in algo:
+        fn = todescato
+    elif "lloyd" in algo:
+        fn = lloyd
+    elif "periodic" in algo:
+        fn = periodic
+    else:
+        raise ValueError("Invalid simulation algorithm specified.")
+    loss_log_t, agent_log_t, sample_log_t = fn(algo, sim_num, iterations, agents, positions, truth, sigma_n, prior,
+                                               hyp, console, plotter, log)
+    plotter.save(f"{out_name}.png") if plotter else None
+    sim_end = time.time()
+    print(line_break + f"End Simulation {sim_num} : {algo}\nTime : {sim_end - sim_start}" + line_break)
+    return loss_log_t, agent_log_t, sample_log_t
+
+
+def _worker(rank, world, args, seed, queue):
+    import torch
+    torch.cuda.set_device(rank % max(torch.cuda.device_count(), 1))
+    if seed is not None:
+        random.seed(seed + rank)
+    out = {}
+    for i in range(rank, len(args), world):       # run-sharding: simulation i goes to worker i mod world
+        out[i] = run_sim(args[i])
+    queue.put(out)
+
+
+def _map_sims(args, n_processors, seed=None):
+    if n_processors <= 1:
+        if seed is not None:
+            random.seed(seed)
+        return [run_sim(a) for a in args]
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    queue = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, n_processors, args, seed, queue)) for r in range(n_processors)]
+    for p in procs:
+        p.start()
+    merged = {}
+    for _ in procs:
+        merged.update(queue.get())
+    for p in procs:
+        p.join()
+    return [merged[i] for i in range(len(args))]
+
+
+def run(n_processors=4, name="Data/australia9", prefix="Data/australia9.3", agents=16, iterations=120,
+        simulations=100, sigma_n=0.1, console=False, log=True, plotter=None, algorithms=None, seed=None,
+        null_prior_path="Data/null_prior.csv"):
+    """reference runner.py:72-161.  Keyword defaults are the literals the reference hard-codes."""
+    np.random.seed(1234)
+    if algorithms is None:
+        algorithms = ["todescato_nsf", "choi_nsf", "todescato_hsf", "choi_hsf", "todescato_hmf", "choi_hmf", "lloyd"]
+    truth = pd.read_csv(f"{name}_hifi.csv")
+    mf_hyp = pd.read_csv(f"{name}_mf_hyp.csv")
+    sf_hyp = pd.read_csv(f"{name}_sf_hyp.csv")
+    null_prior = pd.read_csv(null_prior_path)
+    human_prior = pd.read_csv(f"{name}_prior.csv")
+    for algo in algorithms:
+        print(slash_break + f"Start Algorithm : {algo}" + slash_break)
+        algo_start = time.time()
+        out_name = f"{prefix}_{algo}"
+        loss_log, agent_log, sample_log = [], [], []
+        hyp = mf_hyp if "mf" in algo else sf_hyp
+        prior = null_prior if "_n" in algo else human_prior
+        args = [(out_name, algo, sim_num, iterations, agents, truth, sigma_n, prior, hyp, console, plotter, log)
+                for sim_num in range(simulations)]
+        out = _map_sims(args, n_processors, seed)
+        for sim_num in range(simulations):
+            loss_log.extend(out[sim_num][0])
+            agent_log.extend(out[sim_num][1])
+            sample_log.extend(out[sim_num][2])
+        if log:
+            pd.DataFrame(loss_log).to_csv(f"{out_name}_loss.csv")
+            pd.DataFrame(agent_log).to_csv(f"{out_name}_agent.csv")
+            pd.DataFrame(sample_log).to_csv(f"{out_name}_sample.csv")
+        algo_end = time.time()
+        print(slash_break + f"End Algorithm : {algo}\nTime : {algo_end - algo_start}\n"
+                            f"Time/Sim : {(algo_end - algo_start) / simulations}" + slash_break)
+
+
+if __name__ == "__main__":
+    start = time.time()
+    run(n_processors=4)
+    end = time.time()
+    print(slash_break + slash_break + f"runner.py Total Time : {end - start}\n" + slash_break + slash_break)

@@ -1,0 +1,86 @@
+"""Multi-GPU sharding of the hot path: one process per GPU, torch.distributed for the plumbing.
+
+Two axes, both taken from the reference's own parallelism:
+
+  * GRID sharding (config c4): the G grid points are split into contiguous slices, one per rank -- the reference's
+    experimental `predict_multiproc` slicing (gaussian_process_numba.py:478-503).  The posterior is then
+    communication-free.  The training factor is needed by every rank: rank 0 factorises and broadcasts W = L^-1 and
+    z (NCCL over NVLink; 134 MB at N = 4096), or every rank factorises redundantly (`replicate_factor=True`, no
+    collective at all; chosen by measurement).  The coverage step all-reduces only O(agents) numbers:
+    per-cell partial sums (SUM) and the per-cell (max variance, first index) pairs (all-gather + local merge, lowest
+    global index wins ties exactly as np.argmax on the unsharded array).
+  * RUN sharding (config c5, replicate sweeps): independent simulations, `runner._map_sims` -- no collective.
+
+The merge logic is plain tensor code so that it is exercised on CPU with the gloo backend (tests/test_sharding_gloo.py).
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(G, world, rank):
+    """Contiguous slice [lo, hi) of rank `rank` (sizes differ by at most one, like np.array_split)."""
+    base, extra = divmod(G, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def merge_argmax(vals, idxs):
+    """vals[R, A], idxs[R, A] (global indices, -1 = empty) -> per-cell (max value, LOWEST index attaining it)."""
+    vals = vals.clone()
+    big = torch.iinfo(torch.int64).max
+    empty = idxs < 0
+    vals[empty] = -float("inf")
+    best = vals.max(dim=0).values
+    cand = torch.where((vals == best.unsqueeze(0)) & ~empty, idxs, torch.full_like(idxs, big))
+    bidx = cand.min(dim=0).values
+    bidx = torch.where(bidx == big, torch.full_like(bidx, -1), bidx)
+    return best, bidx
+
+
+def allreduce_partials(res, group=None):
+    """In-place combination of the outputs of CoverageGrid.assign_reduce across ranks."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return res
+    world = dist.get_world_size(group)
+    if res.get("cent") is not None:
+        dist.all_reduce(res["cent"], op=dist.ReduceOp.SUM, group=group)
+    if res.get("lossp") is not None:
+        dist.all_reduce(res["lossp"], op=dist.ReduceOp.SUM, group=group)
+    if res.get("amax_val") is not None:
+        A = res["amax_val"].numel()
+        vals = [torch.empty_like(res["amax_val"]) for _ in range(world)]
+        idxs = [torch.empty_like(res["amax_idx"]) for _ in range(world)]
+        dist.all_gather(vals, res["amax_val"].contiguous(), group=group)
+        dist.all_gather(idxs, res["amax_idx"].contiguous(), group=group)
+        v, i = merge_argmax(torch.stack(vals).reshape(world, A), torch.stack(idxs).reshape(world, A))
+        res["amax_val"].copy_(v)
+        res["amax_idx"].copy_(i)
+    return res
+
+
+def broadcast_factor(engine, src=0, group=None):
+    """Broadcast the fitted factor state (W, z, Tt) of `engine` (a DeviceGP) from rank `src` to all ranks."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return
+    n = engine.npad
+    for t in (engine.W[:n], engine.z[:n], engine.Tt[:n]):
+        dist.broadcast(t, src=src, group=group)
+
+
+class ShardedGrid:
+    """Rank-local slice of the grid plus the collectives that turn rank-local reductions into global ones."""
+
+    def __init__(self, xy_host, f_host=None, group=None):
+        from ._coverage import CoverageGrid
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        xy_host = np.asarray(xy_host, dtype=np.float64).reshape(-1, 2)
+        self.G_total = xy_host.shape[0]
+        self.lo, self.hi = shard_bounds(self.G_total, self.world, self.rank)
+        self.local = CoverageGrid(xy_host[self.lo:self.hi], None if f_host is None else np.asarray(f_host)[self.lo:self.hi],
+                                  base_index=self.lo)
+
+    def assign_reduce(self, *a, **k):
+        return allreduce_partials(self.local.assign_reduce(*a, **k), self.group)

@@ -1,0 +1,7 @@
+"""Importable alias for the package directory `mfgp-coverage_b200/` (a hyphen is not a valid module name)."""
+import os as _os
+
+__path__ = [_os.path.join(_os.path.dirname(_os.path.abspath(__file__)), "mfgp-coverage_b200")]
+with open(_os.path.join(__path__[0], "__init__.py")) as _f:
+    exec(compile(_f.read(), _os.path.join(__path__[0], "__init__.py"), "exec"))
+del _f

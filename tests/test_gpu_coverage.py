@@ -1,0 +1,83 @@
+"""GPU parity: coverage step (membership, loss, centroids, per-cell max variance) vs the oracle."""
+import numpy as np
+import pytest
+
+from oracle import coverage as ocov
+from tests import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup(n, A, seed, on_grid=False):
+    xy = synth.grid(n)
+    f = synth.truth_function(xy)
+    truth = np.column_stack((xy, f))
+    seeds = synth.agents(A, seed)
+    if on_grid:     # agents sitting on grid points: grid points lie exactly on bisectors (tie handling)
+        rng = np.random.default_rng(seed)
+        seeds = xy[rng.choice(xy.shape[0], A, replace=False)].copy()
+    return xy, f, truth, seeds
+
+
+@pytest.mark.parametrize("n,A,seed,on_grid", [(51, 8, 1, False), (51, 8, 2, True), (51, 4, 3, True), (64, 16, 4, False),
+                                              (101, 64, 5, False), (51, 16, 6, True), (33, 70, 7, False)])
+def test_coverage_functions_match_oracle(n, A, seed, on_grid):
+    from mfgp_coverage_b200 import simulator as sim
+    xy, f, truth, seeds = _setup(n, A, seed, on_grid)
+    bbox = ocov.bounding_box_of(xy)
+    rng = np.random.default_rng(seed + 100)
+    mu = rng.normal(0.3, 0.2, xy.shape[0])          # weights may be negative (posterior mean)
+    var = rng.random(xy.shape[0])
+    var[rng.choice(xy.shape[0], 50)] = var.max()    # plant exact duplicates of the maximum: first index must win
+    ovor = ocov.voronoi_bounded(seeds, bbox)
+    vor = sim.voronoi_bounded(seeds, bbox)
+    # membership bit-exact, ties included
+    want = ocov.membership(ovor, xy)
+    from mfgp_coverage_b200._coverage import CoverageGrid
+    res = CoverageGrid(xy, f).assign_reduce(lloyd_vor=vor, want_members=True)
+    m = res["members"].cpu().numpy().view(np.uint64)
+    got = np.stack([((m[:, i // 64] >> np.uint64(i % 64)) & np.uint64(1)).astype(bool) for i in range(A)])
+    assert np.array_equal(got, want)
+    # reductions
+    loss_o = ocov.compute_loss(ovor, truth)
+    loss = sim.compute_loss(vor, truth)
+    assert abs(loss - loss_o) <= 1e-9 * abs(loss_o)
+    cen_o = ocov.compute_centroids(ovor, xy, mu.reshape(-1, 1))
+    cen = sim.compute_centroids(vor, xy, mu.reshape(-1, 1))
+    assert np.max(np.abs(cen - cen_o)) <= 1e-9
+    xy_o, mv_o, idx_o = ocov.compute_max_var(ovor, truth, var)
+    xy_g, mv_g = sim.compute_max_var(vor, truth, var)
+    assert np.array_equal(xy_g, xy_o) and np.array_equal(mv_g, mv_o)
+
+
+def test_in_polygon_and_clusters():
+    from mfgp_coverage_b200 import simulator as sim
+    xy, f, truth, seeds = _setup(51, 8, 11, True)
+    bbox = ocov.bounding_box_of(xy)
+    ovor = ocov.voronoi_bounded(seeds, bbox)
+    vor = sim.voronoi_bounded(seeds, bbox)
+    for i in range(8):
+        v = ovor.cell_vertices(i)
+        assert np.array_equal(sim.in_polygon(xy[:, 0], xy[:, 1], v[:, 0], v[:, 1]),
+                              ocov.in_polygon(xy[:, 0], xy[:, 1], v[:, 0], v[:, 1]))
+    pts = xy[np.random.default_rng(0).choice(xy.shape[0], 40, replace=False)]
+    co = ocov.compute_sample_clusters(ovor, pts)
+    cg = sim.compute_sample_clusters(vor, pts)
+    assert all(np.array_equal(a, b) for a, b in zip(co, cg))
+
+
+def test_empty_cell_raises_like_numpy():
+    from mfgp_coverage_b200 import simulator as sim
+    xy = synth.grid(5)
+    truth = np.column_stack((xy, np.ones(25)))
+    seeds = np.array([[0.5, 0.5], [0.5001, 0.5001], [0.1, 0.9]])       # the sliver between two close seeds is empty?
+    seeds = np.array([[0.1, 0.1], [0.12, 0.12], [0.125, 0.125], [0.9, 0.9]])
+    bbox = ocov.bounding_box_of(xy)
+    vor = sim.voronoi_bounded(seeds, bbox)
+    ovor = ocov.voronoi_bounded(seeds, bbox)
+    counts = ocov.membership(ovor, xy).sum(axis=1)
+    if counts.min() > 0:
+        pytest.skip("configuration has no empty cell")
+    with pytest.raises(ValueError):
+        sim.compute_max_var(vor, truth, np.ones(25))
+    assert np.isnan(sim.compute_loss(vor, truth)) == np.isnan(ocov.compute_loss(ovor, truth))

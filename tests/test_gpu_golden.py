@@ -1,0 +1,145 @@
+"""GPU parity against committed fixtures produced by the UNMODIFIED reference (oracle/make_golden.py) and against the
+reference's own logged CSVs.  Everything goes through the C-ABI via the drop-in modules."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-9
+
+
+def _load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name), allow_pickle=False)
+
+
+def _model(hyp, XL, yL, XH, yH, raw_means=False):
+    from mfgp_coverage_b200.gaussian_process import MFGP, SFGP
+    if hyp.size == 9:
+        m = MFGP(XL, yL, XH, yH, 1, 1)
+        m.raw_means = raw_means
+        m.hyp = hyp
+        m.updt_info(XL, yL, XH, yH)
+    else:
+        m = SFGP(XH, yH, 1)
+        m.raw_means = raw_means
+        m.hyp = hyp
+        m.updt_info(XH, yH)
+    return m
+
+
+def test_live_reference_gp_cases(golden_dir):
+    g = _load(golden_dir, "ref_gp_cases.npz")
+    xs = g["xs"]
+    from mfgp_coverage_b200.gaussian_process import evaluate_hyp, prior_variance
+    for k in range(int(g["ncases"])):
+        hyp = g[f"c{k}_hyp"]
+        m = _model(hyp, g[f"c{k}_XL"], g[f"c{k}_yL"], g[f"c{k}_XH"], g[f"c{k}_yH"])
+        mu, var = m.predict(xs)
+        k0 = prior_variance(evaluate_hyp(hyp))
+        assert np.max(np.abs(var - g[f"c{k}_var"])) <= TOL * k0, k
+        assert np.max(np.abs(mu[:, 0] - g[f"c{k}_mu"])) <= TOL * max(1.0, np.max(np.abs(g[f"c{k}_mu"]))), k
+        L = g[f"c{k}_L"]
+        if L.size:
+            assert np.max(np.abs(m.factor() - L)) <= 1e-10 * np.max(np.abs(L)), k
+
+
+def test_logged_ex_gp_known_answer(golden_dir):
+    """Data/ex_gp.csv iteration 0: per-point posterior of the 25-point lofi prior, 2020 raw-mean convention."""
+    g = _load(golden_dir, "logged_ex_gp.npz")
+    pr = g["prior"]
+    m = _model(g["hyp"], pr[:, :2], pr[:, 2:3], np.empty((0, 2)), np.empty((0, 1)), raw_means=True)
+    mu, var = m.predict(g["xs"])
+    assert np.max(np.abs(var - g["var"])) <= 1e-9 * np.max(g["var"])
+    assert np.max(np.abs(mu[:, 0] - g["mu"])) <= 1e-9
+
+
+def test_live_reference_coverage_cases(golden_dir):
+    from mfgp_coverage_b200 import simulator as sim
+    from mfgp_coverage_b200._coverage import CoverageGrid, polygon_partition
+    g = _load(golden_dir, "ref_coverage_cases.npz")
+    truth = g["truth"]
+    xs = np.ascontiguousarray(truth[:, :2])
+    bbox = np.array([xs[:, 0].min(), xs[:, 0].max(), xs[:, 1].min(), xs[:, 1].max()])
+    for k in range(int(g["ncases"])):
+        seeds = g[f"c{k}_seeds"]
+        A = seeds.shape[0]
+        # (1) with the polygons the reference's Qhull produced (stored): membership must be bit-exact, ties included
+        off = g[f"c{k}_off"]
+        polys = [g[f"c{k}_poly"][off[i]:off[i + 1]] for i in range(A)]
+        part = polygon_partition(seeds, polys)
+        part.seeds_inside = True
+        res = CoverageGrid(xs, truth[:, 2]).assign_reduce(lloyd_vor=part, want_members=True)
+        m = res["members"].cpu().numpy().view(np.uint64)
+        got = np.stack([((m[:, i // 64] >> np.uint64(i % 64)) & np.uint64(1)).astype(bool) for i in range(A)])
+        want = np.unpackbits(g[f"c{k}_member"], axis=1)[:, :xs.shape[0]].astype(bool)
+        assert np.array_equal(got, want), k
+        # (2) through the drop-in functions (Qhull run again here)
+        vor = sim.voronoi_bounded(seeds, bbox)
+        loss = sim.compute_loss(vor, truth)
+        assert abs(loss - float(g[f"c{k}_loss"])) <= TOL * abs(float(g[f"c{k}_loss"])), k
+        cen = sim.compute_centroids(vor, xs, g[f"c{k}_mu"].reshape(-1, 1))
+        assert np.max(np.abs(cen - g[f"c{k}_cent"])) <= TOL, k
+        axy, mv = sim.compute_max_var(vor, truth, g[f"c{k}_var"])
+        assert np.array_equal(axy, g[f"c{k}_argmax_xy"]) and np.array_equal(mv[:, 0], g[f"c{k}_maxvar"]), k
+
+
+def test_logged_australia6_lloyd_chain(golden_dir):
+    """Data/australia6_lloyd_{agent,loss}.csv: 120 iterations of the coverage step reproduced from iteration-0 positions."""
+    import pandas as pd
+    from mfgp_coverage_b200 import simulator as sim
+    g = _load(golden_dir, "logged_australia6_lloyd.npz")
+    inp = _load(golden_dir, "inputs_australia6.npz")
+    truth = pd.DataFrame(inp["truth"], columns=["X", "Y", "f_H"])
+    for s in (0, 1):
+        pos = g[f"s{s}_pos"][0].copy()
+        T, A = g[f"s{s}_pos"].shape[:2]
+        loss_log, agent_log, _ = sim.lloyd("lloyd", s, T, A, pos, truth, 0.1, None, None, False, None, True)
+        loss = np.array([r["Loss"] for r in loss_log])
+        cen = np.array([[r["XCentroid"], r["YCentroid"]] for r in agent_log]).reshape(T, A, 2)
+        assert np.max(np.abs(loss - g[f"s{s}_loss"]) / g[f"s{s}_loss"]) <= TOL
+        assert np.max(np.abs(cen - g[f"s{s}_cent"])) <= TOL
+
+
+@pytest.mark.parametrize("fname,ds,hyp_key,raw,use_prior", [("logged_two_corners_hmf.npz", "two_corners", "mf_hyp", True, True),
+                                                            ("logged_australia6_nsf.npz", "australia6", "sf_hyp", False, False)])
+def test_logged_gp_run_replay(golden_dir, fname, ds, hyp_key, raw, use_prior):
+    """Replay of a logged todescato run: logged samples in, logged centroids / VarMax / XMax out."""
+    from mfgp_coverage_b200 import simulator as sim
+    from mfgp_coverage_b200._coverage import CoverageGrid
+    from mfgp_coverage_b200.gaussian_process import evaluate_hyp, prior_variance
+    g = _load(golden_dir, fname)
+    inp = _load(golden_dir, f"inputs_{ds}.npz")
+    truth = inp["truth"]
+    xs = np.ascontiguousarray(truth[:, :2])
+    bbox = np.array([xs[:, 0].min(), xs[:, 0].max(), xs[:, 1].min(), xs[:, 1].max()])
+    hyp = inp[hyp_key]
+    prior = inp["prior"] if use_prior else None
+    model = sim.init_MFGP(hyp, prior) if hyp.size == 9 else sim.init_SFGP(hyp, prior)
+    model.raw_means = raw
+    if hyp.size == 9:
+        model.updt_info(model.X_L, model.y_L, model.X_H, model.y_H)
+    else:
+        model.updt_info(model.X, model.y)
+    k0 = prior_variance(evaluate_hyp(hyp, raw))
+    assert abs(k0 - g["var0"][0, 0]) <= 1e-12 * k0
+    grid = CoverageGrid(xs, truth[:, 2])
+    T, A = g["pos"].shape[:2]
+    seeds = g["pos"][0]
+    for t in range(T):
+        smp = g["samples"][g["samples"][:, 0] == t]
+        x_new, y_new = smp[:, 2:4], smp[:, 4:5]
+        model.updt_hifi(x_new, y_new) if hyp.size == 9 else model.updt(x_new, y_new)
+        mu, var = model.predict_device(grid.xy)
+        vor = sim.voronoi_bounded(seeds, bbox)
+        res = grid.assign_reduce(lloyd_vor=vor, w=mu, var=var)
+        from mfgp_coverage_b200._coverage import centroids_from_partials
+        cen = centroids_from_partials(res["cent"].cpu().numpy(), vor.areas(), bbox[0], bbox[1], bbox[2], bbox[3])
+        vmax = res["amax_val"].cpu().numpy()
+        idx = res["amax_idx"].cpu().numpy()
+        assert np.max(np.abs(cen - g["cent"][t])) <= TOL, t
+        assert np.max(np.abs(vmax - g["varmax"][t])) <= TOL * k0, t
+        # XMax: accept another index only where the variances tie to 1e-12 (symmetric priors)
+        bad = xs[idx, 0] != g["xmax"][t]
+        assert not np.any(bad & (np.abs(vmax - g["varmax"][t]) > 1e-12 * k0)), t
+        seeds = g["cent"][t]
