@@ -5,58 +5,114 @@
 //   mu  = mean_H + v . z   z = W (y - mean)
 //   var = k(0)  - v . v
 //
-// One CTA owns BN grid points and walks the row blocks of W top to bottom.  Per K slab it stages a BM x BK tile of W
-// with cp.async and GENERATES the BK x BN tile of psi on chip (exp on the FP64 pipe), multiplies them on the FP64
-// tensor cores (DMMA 8x8x4) and, per row block, folds v into the two running column reductions.  psi and V never
-// reach HBM (unless the caller asks for the V cache of the Choi planner).
+// One CTA owns BN = 32 grid points and walks the 512-row blocks of W top to bottom; psi and V never reach HBM
+// (unless the caller asks for the V cache of the Choi planner).  Warp-specialised, 384 threads:
+//   * producer warp group (4 warps): one elected thread streams 512x16 tiles of W from L2/HBM with TMA
+//     (cp.async.bulk.tensor, 128B swizzle) into a 3-stage shared-memory ring; all 128 producer threads GENERATE the
+//     matching 16x32 tile of psi (fp64 exp) into the same stage.  mbarriers (full/empty per stage) carry the hand-off.
+//   * consumer warp groups (8 warps): read A/B fragments from the ring and issue DMMA.8x8x4 into 128 KB of register
+//     accumulators (512x32 fp64), then fold each finished row block of V into the two running column reductions.
+// setmaxnreg moves registers from the producers (56) to the consumers (224); the two must balance exactly within the
+// CTA pool of 384 x 168 registers, otherwise the consumers' setmaxnreg.inc never completes.
 //
-// Why the tile is tall (BM = 512 rows x BN = 32 points): DMMA and DFMA share one datapath on sm_100a and an fp64 exp
-// costs ~23 FP64 lane-slots (profiles/r01_fp64_pipes.log), so every regenerated psi element is paid in MMA time; a
-// psi element is reused BM times per generation, i.e. the exp overhead is ~2*23/BM of the MMA work (9% at 512).
+// Why the tile is tall: DMMA and DFMA share one datapath on sm_100a and an fp64 exp costs ~23 FP64 lane-slots
+// (profiles/r01_fp64_pipes.log), so every regenerated psi element is paid in MMA time; with BM = 512 a psi element is
+// reused 512 times per generation (exp ~ 9% of the MMA work at N = 4096).  v1 of this kernel (single-role CTA,
+// cp.async double buffer) sat at 52% DMMA-pipe utilisation with the psi-generation load latency and the barrier
+// phases exposed (profiles/r01_posterior_v1_ncu_summary.txt); the producer/consumer split hides both.
 // Triangular structure: slabs right of the diagonal are never visited, and inside the diagonal square each warp
 // skips the 8-row tiles that lie entirely above the diagonal (rows are interleaved over warps so this stays balanced).
+#include <cuda.h>
+
 #include "common.cuh"
 
 namespace mfgp {
 
+constexpr int P_BM = 512;            // rows of W per row block
+constexpr int P_BN = 32;             // grid points per CTA
+constexpr int P_BK = 16;             // K slab (16 doubles = one 128-byte swizzle row)
+constexpr int P_STAGES = 3;
+constexpr int P_CONSUMER_WARPS = 8;
+constexpr int P_PRODUCER_WARPS = 4;
+constexpr int P_THREADS = (P_CONSUMER_WARPS + P_PRODUCER_WARPS) * 32;
+constexpr int P_MI = 8;              // 8-row tiles per consumer warp
+constexpr int P_NI = 4;              // 8-column tiles per consumer warp
+constexpr int P_PLD = P_BK + 4;      // padded psi row (doubles)
+constexpr int P_W_STAGE_BYTES = P_BM * P_BK * 8;            // 65536
+constexpr int P_PSI_STAGE_BYTES = P_BN * P_PLD * 8;         // 5120
+constexpr int P_SMEM_BYTES = P_STAGES * (P_W_STAGE_BYTES + P_PSI_STAGE_BYTES) + P_BN * 4 * 8 +
+                             P_CONSUMER_WARPS * P_BN * 2 * 8 + 2 * P_STAGES * 8 + 1024 /* alignment slack */;
+
 struct PostArgs {
     const double* Xs; int64_t G;
     const double* Tt; int NL, NH;
-    const double* W; int npad; int64_t ldw;
+    int npad;
     const double* z;
     double* mu; double* var;
     double* Vc; int64_t ldv;
     DevParams p;
 };
 
-template <int WARPS_M, int MI, int NI, int BK>
-struct PostCfg {
-    static constexpr int BM = WARPS_M * MI * 8;
-    static constexpr int BN = NI * 8;
-    static constexpr int THREADS = WARPS_M * 32;
-    static constexpr int LDS = BK + 4;     // padded smem row in doubles (conflict-free fragment reads)
-    static constexpr size_t smem_bytes() {
-        return sizeof(double) * (2 * BM * LDS + 2 * BN * LDS + BN * 4 + WARPS_M * BN * 2);
-    }
-};
+// ---- mbarrier / TMA / setmaxnreg primitives (PTX) ---------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {   // adds to the tx-count, no arrival
+    asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n" ::"r"(dst),
+        "l"(map), "r"(c0), "r"(c1), "r"(bar)
+        : "memory");
+}
+template <int R>
+__device__ __forceinline__ void reg_alloc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(R)); }
+template <int R>
+__device__ __forceinline__ void reg_dealloc() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(R)); }
 
-template <int WARPS_M, int MI, int NI, int BK>
-__global__ void __launch_bounds__(WARPS_M * 32, 1) posterior_kernel(PostArgs a) {
-    using Cfg = PostCfg<WARPS_M, MI, NI, BK>;
-    constexpr int BM = Cfg::BM, BN = Cfg::BN, THREADS = Cfg::THREADS, LDS = Cfg::LDS;
-    extern __shared__ __align__(16) double smem[];
-    double* Ws = smem;                          // [2][BM][LDS]
-    double* Ps = Ws + 2 * BM * LDS;             // [2][BN][LDS]   psi tile, point-major, k contiguous
-    double* xs = Ps + 2 * BN * LDS;             // [BN][4]        grid coords / l_L, / l_H
-    double* colacc = xs + BN * 4;               // [WARPS_M][BN][2]  per-warp running (sum v^2, sum v z)
+// MMA row slot g (0..7) of an 8-row tile <-> row of the tile.  With the TMA 128B swizzle (16-byte chunk index XOR
+// row%8) a half-warp must touch rows whose row%8 differ in bits 1..2 to hit 16 distinct bank pairs: 0,2,4,6 | 1,3,5,7.
+__device__ __forceinline__ int row_perm(int g) { return ((g & 3) << 1) | (g >> 2); }
+
+__global__ void __launch_bounds__(P_THREADS, 1)
+posterior_kernel(const __grid_constant__ CUtensorMap wmap, PostArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* Wst = smem;                                                        // [S][512][16] doubles, swizzled
+    double* Pst = reinterpret_cast<double*>(smem + P_STAGES * P_W_STAGE_BYTES); // [S][32][20]
+    double* xs = Pst + P_STAGES * P_BN * P_PLD;                                 // [32][4]
+    double* colacc = xs + P_BN * 4;                                             // [8][32][2]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(colacc + P_CONSUMER_WARPS * P_BN * 2);
+    const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + P_STAGES);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int gq = lane >> 2, tq = lane & 3;
-    const int64_t g0 = (int64_t)blockIdx.x * BN;
+    const int64_t g0 = (int64_t)blockIdx.x * P_BN;
     const int N = a.NL + a.NH;
     const DevParams& p = a.p;
 
-    for (int e = tid; e < BN; e += THREADS) {
+    if (tid == 0) {
+        for (int s = 0; s < P_STAGES; s++) {
+            mbar_init(full0 + 8 * s, P_PRODUCER_WARPS * 32);     // every producer thread arrives once per fill
+            mbar_init(empty0 + 8 * s, P_CONSUMER_WARPS);         // one arrive per consumer warp per drain
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    for (int e = tid; e < P_BN; e += P_THREADS) {
         int64_t g = g0 + e;
         if (g >= a.G) g = a.G - 1;
         const double x = a.Xs[2 * g], y = a.Xs[2 * g + 1];
@@ -65,172 +121,201 @@ __global__ void __launch_bounds__(WARPS_M * 32, 1) posterior_kernel(PostArgs a) 
         xs[e * 4 + 2] = x / p.l_H;
         xs[e * 4 + 3] = y / p.l_H;
     }
-    for (int e = tid; e < WARPS_M * BN * 2; e += THREADS) colacc[e] = 0.0;
+    for (int e = tid; e < P_CONSUMER_WARPS * P_BN * 2; e += P_THREADS) colacc[e] = 0.0;
     __syncthreads();
 
-    const int nrb = (a.npad + BM - 1) / BM;
-    for (int rb = 0; rb < nrb; rb++) {
-        const int row0 = rb * BM;
-        const int kmax = min(a.npad, row0 + BM);
-        const int nslab = kmax / BK;
+    const int nrb = (a.npad + P_BM - 1) / P_BM;
 
-        double acc[MI][NI][2];
+    if (warp >= P_CONSUMER_WARPS) {
+        // =============================== PRODUCERS ===============================
+        reg_dealloc<56>();   // pool = 384 x 168: 128 x (168-56) freed == 256 x (224-168) claimed by the consumers
+        const int pt = tid - P_CONSUMER_WARPS * 32;       // 0..127
+        const int k = pt & 15;                            // column of the slab this thread generates
+        const int gbase = pt >> 4;                        // grid points gbase, gbase+8, gbase+16, gbase+24
+        int it = 0;
+        for (int rb = 0; rb < nrb; rb++) {
+            const int row0 = rb * P_BM;
+            const int nslab = min(a.npad, row0 + P_BM) / P_BK;
+            for (int s = 0; s < nslab; s++, it++) {
+                const int stage = it % P_STAGES;
+                const uint32_t parity = (it / P_STAGES) & 1;
+                const int n = s * P_BK + k;
+                double4 t = make_double4(0.0, 0.0, 0.0, 0.0);
+                if (n < N) t = reinterpret_cast<const double4*>(a.Tt)[n];    // issued before the wait: latency overlaps
+                mbar_wait(empty0 + 8 * stage, parity ^ 1);
+                if (pt == 0) {
+                    mbar_expect_tx(full0 + 8 * stage, P_W_STAGE_BYTES);
+                    const uint32_t dst = smem_u32(Wst + stage * P_W_STAGE_BYTES);
+                    tma_load_2d(dst, &wmap, s * P_BK, row0, full0 + 8 * stage);
+                    tma_load_2d(dst + P_W_STAGE_BYTES / 2, &wmap, s * P_BK, row0 + P_BM / 2, full0 + 8 * stage);
+                }
+                // psi tile: element (point gi, training column n); gaussian_process.py:426-429 / :139
+                double* pdst = Pst + stage * P_BN * P_PLD;
 #pragma unroll
-        for (int i = 0; i < MI; i++)
-#pragma unroll
-            for (int j = 0; j < NI; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
-
-        auto stage = [&](int buf, int k0) {
-            // W tile: BM rows x BK doubles, 16-byte chunks; rows past npad are zero-filled
-            double* wdst = Ws + buf * BM * LDS;
-#pragma unroll 4
-            for (int c = tid; c < BM * (BK / 2); c += THREADS) {
-                const int r = c / (BK / 2), q = c % (BK / 2);
-                const int row = row0 + r;
-                const bool ok = row < a.npad;
-                cp_async16(wdst + r * LDS + q * 2, a.W + (int64_t)(ok ? row : 0) * a.ldw + k0 + q * 2, ok);
-            }
-            cp_async_commit();
-            // psi tile: element (point gi, training column k0 + k); gaussian_process.py:426-429 / :139
-            double* pdst = Ps + buf * BN * LDS;
-            for (int e = tid; e < BN * BK; e += THREADS) {
-                const int k = e % BK, gi = e / BK;
-                const int n = k0 + k;
-                double v = 0.0;
-                if (n < N) {
-                    const double4 t = reinterpret_cast<const double4*>(a.Tt)[n];
-                    if (p.multi) {
-                        const double kL = rbf_scaled(xs[gi * 4 + 0], xs[gi * 4 + 1], t.x, t.y, p.s_L);
-                        if (n < a.NL) {
-                            v = p.rho * kL;
+                for (int i = 0; i < 4; i++) {
+                    const int gi = gbase + 8 * i;
+                    double v = 0.0;
+                    if (n < N) {
+                        if (p.multi) {
+                            const double kL = rbf_scaled(xs[gi * 4 + 0], xs[gi * 4 + 1], t.x, t.y, p.s_L);
+                            if (n < a.NL) {
+                                v = p.rho * kL;
+                            } else {
+                                const double kH = rbf_scaled(xs[gi * 4 + 2], xs[gi * 4 + 3], t.z, t.w, p.s_H);
+                                v = __dadd_rn(__dmul_rn(p.rho2, kL), kH);
+                            }
                         } else {
-                            const double kH = rbf_scaled(xs[gi * 4 + 2], xs[gi * 4 + 3], t.z, t.w, p.s_H);
-                            v = __dadd_rn(__dmul_rn(p.rho2, kL), kH);
-                        }
-                    } else {
-                        v = rbf_scaled(xs[gi * 4 + 2], xs[gi * 4 + 3], t.z, t.w, p.s_H);
-                    }
-                }
-                pdst[gi * LDS + k] = v;
-            }
-        };
-
-        // last k (inclusive) at which the 8-row tile mi of this warp still has a non-zero W entry; -1 = tile unused
-        int klim[MI];
-#pragma unroll
-        for (int i = 0; i < MI; i++) {
-            const int r = row0 + (i * WARPS_M + warp) * 8;
-            klim[i] = (r < a.npad) ? r + 7 : -1;
-        }
-
-        stage(0, 0);
-        for (int s = 0; s < nslab; s++) {
-            const int buf = s & 1;
-            const int k0 = s * BK;
-            if (s + 1 < nslab) {
-                stage(buf ^ 1, k0 + BK);
-                cp_async_wait<1>();
-            } else {
-                cp_async_wait<0>();
-            }
-            __syncthreads();
-            const double* wsrc = Ws + buf * BM * LDS;
-            const double* psrc = Ps + buf * BN * LDS;
-            const bool full = (k0 + BK <= row0) && (row0 + BM <= a.npad);
-            if (full) {
-#pragma unroll
-                for (int kk = 0; kk < BK; kk += 4) {
-                    double af[MI], bf[NI];
-#pragma unroll
-                    for (int i = 0; i < MI; i++) af[i] = wsrc[((i * WARPS_M + warp) * 8 + gq) * LDS + kk + tq];
-#pragma unroll
-                    for (int j = 0; j < NI; j++) bf[j] = psrc[(j * 8 + gq) * LDS + kk + tq];
-#pragma unroll
-                    for (int i = 0; i < MI; i++)
-#pragma unroll
-                        for (int j = 0; j < NI; j++) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
-                }
-            } else {
-#pragma unroll
-                for (int kk = 0; kk < BK; kk += 4) {
-                    double bf[NI];
-#pragma unroll
-                    for (int j = 0; j < NI; j++) bf[j] = psrc[(j * 8 + gq) * LDS + kk + tq];
-#pragma unroll
-                    for (int i = 0; i < MI; i++) {
-                        if (k0 + kk <= klim[i]) {   // warp-uniform
-                            const double af = wsrc[((i * WARPS_M + warp) * 8 + gq) * LDS + kk + tq];
-#pragma unroll
-                            for (int j = 0; j < NI; j++) dmma884(acc[i][j][0], acc[i][j][1], af, bf[j]);
+                            v = rbf_scaled(xs[gi * 4 + 2], xs[gi * 4 + 3], t.z, t.w, p.s_H);
                         }
                     }
+                    pdst[gi * P_PLD + k] = v;
                 }
+                mbar_arrive(full0 + 8 * stage);      // release: this thread's psi stores are visible to the waiters
             }
-            __syncthreads();
         }
+    } else {
+        // =============================== CONSUMERS ===============================
+        reg_alloc<224>();
+        const int gq = lane >> 2, tq = lane & 3;
+        const int pr = row_perm(gq);
+        // byte offset of this lane's A element inside an 8-row tile for k-step kk: row pr, 16B-chunk ((kk+tq)/2)^pr
+        int aoff[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) aoff[j] = pr * 128 + ((((j * 4 + tq) >> 1) ^ pr) << 4) + ((tq & 1) << 3);
+        int it = 0;
+        for (int rb = 0; rb < nrb; rb++) {
+            const int row0 = rb * P_BM;
+            const int nslab = min(a.npad, row0 + P_BM) / P_BK;
 
-        // fold this row block of V into the column reductions (and the V cache if requested)
-        double sq[NI][2], dt[NI][2];
+            double acc[P_MI][P_NI][2];
 #pragma unroll
-        for (int j = 0; j < NI; j++) sq[j][0] = sq[j][1] = dt[j][0] = dt[j][1] = 0.0;
+            for (int i = 0; i < P_MI; i++)
 #pragma unroll
-        for (int i = 0; i < MI; i++) {
-            const int row = row0 + (i * WARPS_M + warp) * 8 + gq;
-            if (row < a.npad) {
-                const double zr = a.z[row];
+                for (int j = 0; j < P_NI; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+            // last k (inclusive) at which 8-row tile i of this warp still has a non-zero W entry; -1 = tile unused
+            int klim[P_MI];
 #pragma unroll
-                for (int j = 0; j < NI; j++) {
-                    const double v0 = acc[i][j][0], v1 = acc[i][j][1];
-                    sq[j][0] += v0 * v0;
-                    sq[j][1] += v1 * v1;
-                    dt[j][0] += v0 * zr;
-                    dt[j][1] += v1 * zr;
-                    if (a.Vc != nullptr && row < N) {
-                        const int64_t g = g0 + j * 8 + tq * 2;
-                        double* dst = a.Vc + (int64_t)row * a.ldv + g;
-                        if (g + 1 < a.G && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
-                            *reinterpret_cast<double2*>(dst) = make_double2(v0, v1);
-                        } else {
-                            if (g < a.G) dst[0] = v0;
-                            if (g + 1 < a.G) dst[1] = v1;
+            for (int i = 0; i < P_MI; i++) {
+                const int r = row0 + (i * P_CONSUMER_WARPS + warp) * 8;
+                klim[i] = (r < a.npad) ? r + 7 : -1;
+            }
+
+            for (int s = 0; s < nslab; s++, it++) {
+                const int stage = it % P_STAGES;
+                const uint32_t parity = (it / P_STAGES) & 1;
+                const int k0 = s * P_BK;
+                mbar_wait(full0 + 8 * stage, parity);
+                const uint8_t* wsrc = Wst + stage * P_W_STAGE_BYTES + warp * 8 * 128;     // tile i adds i*8 warps*8 rows
+                const double* psrc = Pst + stage * P_BN * P_PLD;
+                const bool full = (k0 + P_BK <= row0) && (row0 + P_BM <= a.npad);
+                if (full) {
+                    double af[2][P_MI], bf[2][P_NI];
+#pragma unroll
+                    for (int i = 0; i < P_MI; i++)
+                        af[0][i] = *reinterpret_cast<const double*>(wsrc + i * (P_CONSUMER_WARPS * 8 * 128) + aoff[0]);
+#pragma unroll
+                    for (int j = 0; j < P_NI; j++) bf[0][j] = psrc[(j * 8 + gq) * P_PLD + tq];
+#pragma unroll
+                    for (int ks = 0; ks < 4; ks++) {
+                        const int cur = ks & 1, nxt = cur ^ 1;
+                        if (ks < 3) {
+#pragma unroll
+                            for (int i = 0; i < P_MI; i++)
+                                af[nxt][i] = *reinterpret_cast<const double*>(wsrc + i * (P_CONSUMER_WARPS * 8 * 128) + aoff[ks + 1]);
+#pragma unroll
+                            for (int j = 0; j < P_NI; j++) bf[nxt][j] = psrc[(j * 8 + gq) * P_PLD + (ks + 1) * 4 + tq];
+                        }
+#pragma unroll
+                        for (int i = 0; i < P_MI; i++)
+#pragma unroll
+                            for (int j = 0; j < P_NI; j++) dmma884(acc[i][j][0], acc[i][j][1], af[cur][i], bf[cur][j]);
+                    }
+                } else {
+#pragma unroll
+                    for (int ks = 0; ks < 4; ks++) {
+                        double bf[P_NI];
+#pragma unroll
+                        for (int j = 0; j < P_NI; j++) bf[j] = psrc[(j * 8 + gq) * P_PLD + ks * 4 + tq];
+#pragma unroll
+                        for (int i = 0; i < P_MI; i++) {
+                            if (k0 + ks * 4 <= klim[i]) {   // warp-uniform
+                                const double af =
+                                    *reinterpret_cast<const double*>(wsrc + i * (P_CONSUMER_WARPS * 8 * 128) + aoff[ks]);
+#pragma unroll
+                                for (int j = 0; j < P_NI; j++) dmma884(acc[i][j][0], acc[i][j][1], af, bf[j]);
+                            }
                         }
                     }
                 }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(empty0 + 8 * stage);
             }
-        }
+
+            // fold this row block of V into the column reductions (and the V cache if requested)
+            double sq[P_NI][2], dt[P_NI][2];
 #pragma unroll
-        for (int j = 0; j < NI; j++)
+            for (int j = 0; j < P_NI; j++) sq[j][0] = sq[j][1] = dt[j][0] = dt[j][1] = 0.0;
 #pragma unroll
-            for (int c = 0; c < 2; c++) {
+            for (int i = 0; i < P_MI; i++) {
+                const int row = row0 + (i * P_CONSUMER_WARPS + warp) * 8 + pr;
+                if (row < a.npad) {
+                    const double zr = a.z[row];
 #pragma unroll
-                for (int o = 4; o < 32; o <<= 1) {
-                    sq[j][c] += __shfl_xor_sync(0xffffffffu, sq[j][c], o);
-                    dt[j][c] += __shfl_xor_sync(0xffffffffu, dt[j][c], o);
+                    for (int j = 0; j < P_NI; j++) {
+                        const double v0 = acc[i][j][0], v1 = acc[i][j][1];
+                        sq[j][0] += v0 * v0;
+                        sq[j][1] += v1 * v1;
+                        dt[j][0] += v0 * zr;
+                        dt[j][1] += v1 * zr;
+                        if (a.Vc != nullptr && row < N) {
+                            const int64_t g = g0 + j * 8 + tq * 2;
+                            double* dst = a.Vc + (int64_t)row * a.ldv + g;
+                            if (g + 1 < a.G && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+                                *reinterpret_cast<double2*>(dst) = make_double2(v0, v1);
+                            } else {
+                                if (g < a.G) dst[0] = v0;
+                                if (g + 1 < a.G) dst[1] = v1;
+                            }
+                        }
+                    }
                 }
             }
-        if (gq == 0) {
 #pragma unroll
-            for (int j = 0; j < NI; j++)
+            for (int j = 0; j < P_NI; j++)
 #pragma unroll
                 for (int c = 0; c < 2; c++) {
-                    double* slot = colacc + (warp * BN + j * 8 + tq * 2 + c) * 2;
-                    slot[0] += sq[j][c];
-                    slot[1] += dt[j][c];
-                }
-        }
-    }
-    __syncthreads();
-    for (int e = tid; e < BN; e += THREADS) {
-        const int64_t g = g0 + e;
-        if (g < a.G) {
-            double s = 0.0, d = 0.0;
 #pragma unroll
-            for (int w = 0; w < WARPS_M; w++) {
-                s += colacc[(w * BN + e) * 2 + 0];
-                d += colacc[(w * BN + e) * 2 + 1];
+                    for (int o = 4; o < 32; o <<= 1) {
+                        sq[j][c] += __shfl_xor_sync(0xffffffffu, sq[j][c], o);
+                        dt[j][c] += __shfl_xor_sync(0xffffffffu, dt[j][c], o);
+                    }
+                }
+            if (gq == 0) {
+#pragma unroll
+                for (int j = 0; j < P_NI; j++)
+#pragma unroll
+                    for (int c = 0; c < 2; c++) {
+                        double* slot = colacc + (warp * P_BN + j * 8 + tq * 2 + c) * 2;
+                        slot[0] += sq[j][c];
+                        slot[1] += dt[j][c];
+                    }
             }
-            a.var[g] = p.k0 - s;
-            a.mu[g] = p.mean_H + d;
+        }
+        // consumers only: named barrier 1 over the 256 consumer threads, then the final per-point results
+        asm volatile("bar.sync 1, %0;\n" ::"n"(P_CONSUMER_WARPS * 32) : "memory");
+        if (tid < P_BN) {
+            const int64_t g = g0 + tid;
+            if (g < a.G) {
+                double s = 0.0, d = 0.0;
+#pragma unroll
+                for (int w = 0; w < P_CONSUMER_WARPS; w++) {
+                    s += colacc[(w * P_BN + tid) * 2 + 0];
+                    d += colacc[(w * P_BN + tid) * 2 + 1];
+                }
+                a.var[g] = p.k0 - s;
+                a.mu[g] = p.mean_H + d;
+            }
         }
     }
 }
@@ -243,14 +328,34 @@ __global__ void posterior_prior_kernel(int64_t G, double mean, double k0, double
     }
 }
 
-template <int WARPS_M, int MI, int NI, int BK>
-int launch_posterior(const PostArgs& a, cudaStream_t st) {
-    using Cfg = PostCfg<WARPS_M, MI, NI, BK>;
-    auto kern = posterior_kernel<WARPS_M, MI, NI, BK>;
-    MFGP_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::smem_bytes()));
-    const unsigned grid = (unsigned)((a.G + Cfg::BN - 1) / Cfg::BN);
-    kern<<<grid, Cfg::THREADS, Cfg::smem_bytes(), st>>>(a);
-    MFGP_LAUNCH_CHECK();
+// cuTensorMapEncodeTiled through the runtime's driver entry point query (no link-time dependency on libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int make_w_tensor_map(CUtensorMap* map, const double* W, int64_t npad, int64_t ldw) {
+    static EncodeTiledFn encode = nullptr;
+    if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        MFGP_CUDA_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        if (qres != cudaDriverEntryPointSuccess || !fn) {
+            set_last_error("cuTensorMapEncodeTiled entry point unavailable", cudaErrorUnknown);
+            return MFGP_ERR_CUDA;
+        }
+        encode = reinterpret_cast<EncodeTiledFn>(fn);
+    }
+    const cuuint64_t gdim[2] = {(cuuint64_t)npad, (cuuint64_t)npad};       // {columns (contiguous), rows}
+    const cuuint64_t gstride[1] = {(cuuint64_t)ldw * sizeof(double)};      // row pitch in bytes
+    const cuuint32_t box[2] = {(cuuint32_t)P_BK, (cuuint32_t)(P_BM / 2)};  // 16 doubles (128 B) x 256 rows
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(W), gdim, gstride, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);          // out-of-range rows read as zero
+    if (r != CUDA_SUCCESS) {
+        set_last_error("cuTensorMapEncodeTiled failed", cudaErrorInvalidValue);
+        return MFGP_ERR_CUDA;
+    }
     return MFGP_OK;
 }
 
@@ -273,12 +378,18 @@ extern "C" int mfgp_posterior(const double* Xs, int64_t G, const double* Tt, int
         return MFGP_OK;
     }
     if (!Tt || !W || !z || npad < N || npad % MFGP_TILE || ldw < npad) return MFGP_ERR_INVALID;
+    if ((reinterpret_cast<uintptr_t>(W) & 15) || (ldw & 1)) return MFGP_ERR_INVALID;     // TMA: 16-byte aligned rows
     if (!p_host->multi && NL != 0) return MFGP_ERR_INVALID;
     if (Vc && ldv < G) return MFGP_ERR_INVALID;
+    CUtensorMap wmap;
+    int rc = make_w_tensor_map(&wmap, W, npad, ldw);
+    if (rc) return rc;
     PostArgs a;
-    a.Xs = Xs; a.G = G; a.Tt = Tt; a.NL = (int)NL; a.NH = (int)NH; a.W = W; a.npad = (int)npad; a.ldw = ldw; a.z = z;
+    a.Xs = Xs; a.G = G; a.Tt = Tt; a.NL = (int)NL; a.NH = (int)NH; a.npad = (int)npad; a.z = z;
     a.mu = mu; a.var = var; a.Vc = Vc; a.ldv = ldv; a.p = dp;
-    if (npad <= 128) return launch_posterior<4, 4, 4, 16>(a, st);     // BM = 128: small models (c1/c2 early iterations)
-    if (npad <= 256) return launch_posterior<8, 4, 4, 16>(a, st);     // BM = 256
-    return launch_posterior<8, 8, 4, 16>(a, st);                       // BM = 512, BN = 32
+    MFGP_CUDA_CHECK(cudaFuncSetAttribute(posterior_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_BYTES));
+    const unsigned grid = (unsigned)((G + P_BN - 1) / P_BN);
+    posterior_kernel<<<grid, P_THREADS, P_SMEM_BYTES, st>>>(wmap, a);
+    MFGP_LAUNCH_CHECK();
+    return MFGP_OK;
 }
