@@ -82,6 +82,20 @@ int mfgp_posterior(const double* Xs, int64_t G, const double* Tt, int64_t NL, in
                    const double* W, int64_t npad, int64_t ldw, const double* z, const mfgp_params* p_host,
                    double* mu, double* var, double* Vc, int64_t ldv, void* stream);
 
+/* Tensor-product grids (every grid of the reference: distribution.py:337-339 builds `[[i, j] for i in g for j in g]`).
+ * The RBF kernel is separable per axis, so psi[g][n] = TLx[ix][n]*TLy[iy][n] + THx[ix][n]*THy[iy][n] with
+ * (ix, iy) = divmod(g, ny) and the scales / rho / padding folded into the x tables: 2 flops per element instead of two
+ * fp64 exp, which matters because exp and DMMA share the FP64 pipe.  mfgp_grid_tables fills the four tables
+ * ([nx|ny][ldt], ldt >= npad) from the axis values ux[nx], uy[ny] after every fit; mfgp_posterior_grid is
+ * mfgp_posterior for the flat x-major index range [g_lo, g_lo + G) (grid sharding passes a sub-range). */
+int mfgp_grid_tables(const double* ux, int64_t nx, const double* uy, int64_t ny, const double* Tt, int64_t NL, int64_t NH,
+                     int64_t npad, const mfgp_params* p_host, double* TLx, double* TLy, double* THx, double* THy,
+                     int64_t ldt, void* stream);
+int mfgp_posterior_grid(int64_t ny, int64_t g_lo, int64_t G, const double* TLx, const double* TLy, const double* THx,
+                        const double* THy, int64_t ldt, int64_t NL, int64_t NH, const double* W, int64_t npad,
+                        int64_t ldw, const double* z, const mfgp_params* p_host, double* mu, double* var, double* Vc,
+                        int64_t ldv, void* stream);
+
 /* ---- coverage step: replaces simulator.py in_polygon :105-124, compute_loss :194-228, compute_centroids :231-283,
  *      compute_max_var :286-323, compute_sample_clusters :377-412 ------------------------------------------------ */
 

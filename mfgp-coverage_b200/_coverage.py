@@ -109,7 +109,9 @@ class _DevPartition:
 class CoverageGrid:
     """Grid points xy[G,2] (+ optional truth f[G]) resident on the device, with reusable output buffers."""
 
-    def __init__(self, xy_host, f_host=None, device=None, base_index=0):
+    def __init__(self, xy_host, f_host=None, device=None, base_index=0, axes=None):
+        """`axes`: TensorAxes of the FULL grid when xy_host is a contiguous slice [base_index, base_index+G) of a
+        tensor-product grid (grid sharding); detected automatically when xy_host is itself a whole tensor grid."""
         nat.require_cuda()
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         xy = np.ascontiguousarray(xy_host, dtype=np.float64).reshape(-1, 2)
@@ -120,6 +122,11 @@ class CoverageGrid:
             np.ascontiguousarray(f_host, dtype=np.float64).reshape(-1)).to(self.device)
         self._work = None
         self._work_key = None
+        if axes is None and base_index == 0:
+            from ._engine import TensorAxes, detect_tensor_grid
+            t = detect_tensor_grid(xy)
+            axes = TensorAxes(t[0], t[1], self.device) if t is not None else None
+        self.axes = axes
 
     def _workspace(self, Ac, Ap):
         need = int(nat.lib().cov_workspace_bytes(self.G, max(Ac, 1), Ap))

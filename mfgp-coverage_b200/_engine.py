@@ -13,6 +13,32 @@ import torch
 from . import _native as nat
 
 
+class TensorAxes:
+    """Axis values of a tensor-product grid `[[x, y] for x in ux for y in uy]` (x-major, distribution.py:337-339)."""
+
+    def __init__(self, ux_host, uy_host, device):
+        self.nx, self.ny = int(len(ux_host)), int(len(uy_host))
+        self.ux = torch.from_numpy(np.ascontiguousarray(ux_host, dtype=np.float64)).to(device)
+        self.uy = torch.from_numpy(np.ascontiguousarray(uy_host, dtype=np.float64)).to(device)
+
+
+def detect_tensor_grid(xy):
+    """(ux, uy) if xy[G,2] is exactly `[[x, y] for x in ux for y in uy]` (bitwise), else None.  O(G), vectorised."""
+    xy = np.asarray(xy, dtype=np.float64)
+    G = xy.shape[0]
+    if G < 4:
+        return None
+    change = np.nonzero(xy[1:, 0] != xy[0, 0])[0]
+    ny = int(change[0]) + 1 if change.size else G
+    if ny < 2 or G % ny:
+        return None
+    nx = G // ny
+    ux, uy = xy[::ny, 0].copy(), xy[:ny, 1].copy()
+    if nx * ny != G or not np.array_equal(xy[:, 0], np.repeat(ux, ny)) or not np.array_equal(xy[:, 1], np.tile(uy, nx)):
+        return None
+    return ux, uy
+
+
 def params_struct(p):
     """p: dict with the evaluated parameters (see gaussian_process.evaluate_hyp)."""
     return nat.MfgpParams(p["s_L"], p["l_L"], p["s_H"], p["l_H"], p["rho"], p["noise_L"], p["noise_H"],
@@ -32,6 +58,8 @@ class DeviceGP:
         self.params = None
         self.pstruct = None
         self.fitted = False
+        self.fit_id = 0               # bumped by every refactor: grid tables are rebuilt lazily when stale
+        self._tab = None              # (axes key, fit_id, TLx, TLy, THx, THy, ldt)
 
     # -- memory -------------------------------------------------------------------------------------------------------
     def _reserve(self, n):
@@ -93,8 +121,29 @@ class DeviceGP:
                   "mfgp_tri_inverse")
         nat.check(lib.mfgp_whiten(nat.ptr(self.W), npad, ld, nat.ptr(self.y), self.NL, self.NH, pp, nat.ptr(self.z),
                                   st), "mfgp_whiten")
+        self.fit_id += 1
         if check:
             self.check_factor()
+
+    def grid_tables(self, axes):
+        """Per-axis factor tables of the separable kernel for a tensor-product grid (`axes` = TensorAxes), rebuilt
+        after every refit (mfgp_grid_tables)."""
+        if self._tab is not None and self._tab[0] is axes and self._tab[1] == self.fit_id:
+            return self._tab[2:]
+        ldt = self.cap
+        need = (axes.nx + axes.ny) * ldt * 2
+        buf = self._tab[7] if (self._tab is not None and self._tab[7].numel() >= need) else \
+            torch.empty(need, dtype=torch.float64, device=self.device)
+        TLx = buf[:axes.nx * ldt]
+        TLy = buf[axes.nx * ldt:(axes.nx + axes.ny) * ldt]
+        THx = buf[(axes.nx + axes.ny) * ldt:(2 * axes.nx + axes.ny) * ldt]
+        THy = buf[(2 * axes.nx + axes.ny) * ldt:need]
+        nat.check(nat.lib().mfgp_grid_tables(nat.ptr(axes.ux), axes.nx, nat.ptr(axes.uy), axes.ny, nat.ptr(self.Tt),
+                                             self.NL, self.NH, self.npad, ctypes.byref(self.pstruct), nat.ptr(TLx),
+                                             nat.ptr(TLy), nat.ptr(THx), nat.ptr(THy), ldt, nat.stream_ptr()),
+                  "mfgp_grid_tables")
+        self._tab = (axes, self.fit_id, TLx, TLy, THx, THy, ldt, buf)
+        return self._tab[2:]
 
     def check_factor(self):
         info = int(self.info.item())
@@ -120,15 +169,24 @@ class DeviceGP:
             self.refactor(check=check)
 
     # -- posterior ----------------------------------------------------------------------------------------------------
-    def posterior(self, xs_dev, mu_out=None, var_out=None, vcache=None):
+    def posterior(self, xs_dev, mu_out=None, var_out=None, vcache=None, axes=None, g_lo=0):
         """Posterior mean / variance for device-resident points xs_dev[G,2].  Replaces predict
-        (gaussian_process.py:121-148, :401-438), diagonal only.  Returns device tensors (mu[G], var[G])."""
+        (gaussian_process.py:121-148, :401-438), diagonal only.  Returns device tensors (mu[G], var[G]).
+        If `axes` (TensorAxes) is given the points are the flat x-major range [g_lo, g_lo+G) of that tensor-product
+        grid and the separable-kernel path (mfgp_posterior_grid) is used."""
         G = int(xs_dev.shape[0])
         f64 = dict(dtype=torch.float64, device=self.device)
         mu = torch.empty(G, **f64) if mu_out is None else mu_out
         var = torch.empty(G, **f64) if var_out is None else var_out
         lib = nat.lib()
         ldv = 0 if vcache is None else int(vcache.shape[1])
+        if axes is not None and self.N > 0:
+            TLx, TLy, THx, THy, ldt, _ = self.grid_tables(axes)
+            nat.check(lib.mfgp_posterior_grid(axes.ny, int(g_lo), G, nat.ptr(TLx), nat.ptr(TLy), nat.ptr(THx),
+                                              nat.ptr(THy), ldt, self.NL, self.NH, nat.ptr(self.W), self.npad, self.cap,
+                                              nat.ptr(self.z), ctypes.byref(self.pstruct), nat.ptr(mu), nat.ptr(var),
+                                              nat.ptr(vcache), ldv, nat.stream_ptr()), "mfgp_posterior_grid")
+            return mu, var
         nat.check(lib.mfgp_posterior(nat.ptr(xs_dev), G, nat.ptr(self.Tt), self.NL, self.NH, nat.ptr(self.W),
                                      self.npad, self.cap, nat.ptr(self.z), ctypes.byref(self.pstruct), nat.ptr(mu),
                                      nat.ptr(var), nat.ptr(vcache), ldv, nat.stream_ptr()), "mfgp_posterior")
@@ -144,4 +202,5 @@ class DeviceGP:
             t = getattr(self, name)
             setattr(other, name, None if t is None else t.clone())
         other.info = self.info.clone()
+        other.fit_id = self.fit_id
         return other

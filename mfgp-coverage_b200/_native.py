@@ -39,6 +39,11 @@ SIGNATURES = {
                             c_void_p]),
     "mfgp_posterior": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64, c_void_p,
                                POINTER(MfgpParams), c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+    "mfgp_grid_tables": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64,
+                                 POINTER(MfgpParams), c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+    "mfgp_posterior_grid": (c_int, [c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64,
+                                    c_int64, c_void_p, c_int64, c_int64, c_void_p, POINTER(MfgpParams), c_void_p,
+                                    c_void_p, c_void_p, c_int64, c_void_p]),
     "cov_assign_reduce": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64,
                                   c_void_p, c_int64, c_void_p, c_void_p, c_int64,
                                   c_void_p, c_int64, c_void_p, c_void_p, c_int64,

@@ -12,7 +12,7 @@
 //     matching 16x32 tile of psi (fp64 exp) into the same stage.  mbarriers (full/empty per stage) carry the hand-off.
 //   * consumer warp groups (8 warps): read A/B fragments from the ring and issue DMMA.8x8x4 into 128 KB of register
 //     accumulators (512x32 fp64), then fold each finished row block of V into the two running column reductions.
-// setmaxnreg moves registers from the producers (56) to the consumers (224); the two must balance exactly within the
+// setmaxnreg moves registers from the producers (72) to the consumers (216); the two must balance exactly within the
 // CTA pool of 384 x 168 registers, otherwise the consumers' setmaxnreg.inc never completes.
 //
 // Why the tile is tall: DMMA and DFMA share one datapath on sm_100a and an fp64 exp costs ~23 FP64 lane-slots
@@ -44,7 +44,11 @@ constexpr int P_SMEM_BYTES = P_STAGES * (P_W_STAGE_BYTES + P_PSI_STAGE_BYTES) + 
                              P_CONSUMER_WARPS * P_BN * 2 * 8 + 2 * P_STAGES * 8 + 1024 /* alignment slack */;
 
 struct PostArgs {
-    const double* Xs; int64_t G;
+    const double* Xs; int64_t G;         // general mode: explicit points
+    // grid mode (tensor-product grid, x-major): point g_lo + g <-> (ix, iy) = divmod(g_lo + g, ny); per-axis tables
+    // TLx[nx][ldt], TLy[ny][ldt], THx[nx][ldt], THy[ny][ldt] with psi[g][n] = TLx[ix][n]*TLy[iy][n] + THx[ix][n]*THy[iy][n]
+    const double* TLx; const double* TLy; const double* THx; const double* THy;
+    int64_t ldt; int64_t g_lo; int ny;
     const double* Tt; int NL, NH;
     int npad;
     const double* z;
@@ -89,6 +93,7 @@ __device__ __forceinline__ void reg_dealloc() { asm volatile("setmaxnreg.dec.syn
 // row%8) a half-warp must touch rows whose row%8 differ in bits 1..2 to hit 16 distinct bank pairs: 0,2,4,6 | 1,3,5,7.
 __device__ __forceinline__ int row_perm(int g) { return ((g & 3) << 1) | (g >> 2); }
 
+template <bool GRID>
 __global__ void __launch_bounds__(P_THREADS, 1)
 posterior_kernel(const __grid_constant__ CUtensorMap wmap, PostArgs a) {
     extern __shared__ uint8_t smem_raw[];
@@ -112,14 +117,16 @@ posterior_kernel(const __grid_constant__ CUtensorMap wmap, PostArgs a) {
         }
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
-    for (int e = tid; e < P_BN; e += P_THREADS) {
-        int64_t g = g0 + e;
-        if (g >= a.G) g = a.G - 1;
-        const double x = a.Xs[2 * g], y = a.Xs[2 * g + 1];
-        xs[e * 4 + 0] = x / p.l_L;
-        xs[e * 4 + 1] = y / p.l_L;
-        xs[e * 4 + 2] = x / p.l_H;
-        xs[e * 4 + 3] = y / p.l_H;
+    if (!GRID) {
+        for (int e = tid; e < P_BN; e += P_THREADS) {
+            int64_t g = g0 + e;
+            if (g >= a.G) g = a.G - 1;
+            const double x = a.Xs[2 * g], y = a.Xs[2 * g + 1];
+            xs[e * 4 + 0] = x / p.l_L;
+            xs[e * 4 + 1] = y / p.l_L;
+            xs[e * 4 + 2] = x / p.l_H;
+            xs[e * 4 + 3] = y / p.l_H;
+        }
     }
     for (int e = tid; e < P_CONSUMER_WARPS * P_BN * 2; e += P_THREADS) colacc[e] = 0.0;
     __syncthreads();
@@ -128,10 +135,22 @@ posterior_kernel(const __grid_constant__ CUtensorMap wmap, PostArgs a) {
 
     if (warp >= P_CONSUMER_WARPS) {
         // =============================== PRODUCERS ===============================
-        reg_dealloc<56>();   // pool = 384 x 168: 128 x (168-56) freed == 256 x (224-168) claimed by the consumers
+        reg_dealloc<72>();   // pool = 384 x 168: 128 x (168-72) freed == 256 x (216-168) claimed by the consumers
         const int pt = tid - P_CONSUMER_WARPS * 32;       // 0..127
         const int k = pt & 15;                            // column of the slab this thread generates
         const int gbase = pt >> 4;                        // grid points gbase, gbase+8, gbase+16, gbase+24
+        // grid mode: table row offsets of this thread's four points (x-major flat index -> ix, iy)
+        int offx[4], offy[4];          // element offsets (host checks (nx|ny) * ldt < 2^31)
+        if (GRID) {
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                int64_t g = g0 + gbase + 8 * i;
+                if (g >= a.G) g = a.G - 1;
+                g += a.g_lo;
+                offx[i] = (int)((g / a.ny) * a.ldt);
+                offy[i] = (int)((g % a.ny) * a.ldt);
+            }
+        }
         int it = 0;
         for (int rb = 0; rb < nrb; rb++) {
             const int row0 = rb * P_BM;
@@ -140,8 +159,20 @@ posterior_kernel(const __grid_constant__ CUtensorMap wmap, PostArgs a) {
                 const int stage = it % P_STAGES;
                 const uint32_t parity = (it / P_STAGES) & 1;
                 const int n = s * P_BK + k;
+                // operands of this slab are fetched BEFORE waiting for the ring slot: the L2 latency overlaps the wait
                 double4 t = make_double4(0.0, 0.0, 0.0, 0.0);
-                if (n < N) t = reinterpret_cast<const double4*>(a.Tt)[n];    // issued before the wait: latency overlaps
+                double lx[4], ly[4], hx[4], hy[4];
+                if (GRID) {
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        lx[i] = __ldg(a.TLx + offx[i] + n);
+                        ly[i] = __ldg(a.TLy + offy[i] + n);
+                        hx[i] = __ldg(a.THx + offx[i] + n);
+                        hy[i] = __ldg(a.THy + offy[i] + n);
+                    }
+                } else if (n < N) {
+                    t = reinterpret_cast<const double4*>(a.Tt)[n];
+                }
                 mbar_wait(empty0 + 8 * stage, parity ^ 1);
                 if (pt == 0) {
                     mbar_expect_tx(full0 + 8 * stage, P_W_STAGE_BYTES);
@@ -155,7 +186,9 @@ posterior_kernel(const __grid_constant__ CUtensorMap wmap, PostArgs a) {
                 for (int i = 0; i < 4; i++) {
                     const int gi = gbase + 8 * i;
                     double v = 0.0;
-                    if (n < N) {
+                    if (GRID) {
+                        v = fma(hx[i], hy[i], lx[i] * ly[i]);      // scales, rho and padding zeros are folded into T?x
+                    } else if (n < N) {
                         if (p.multi) {
                             const double kL = rbf_scaled(xs[gi * 4 + 0], xs[gi * 4 + 1], t.x, t.y, p.s_L);
                             if (n < a.NL) {
@@ -175,7 +208,7 @@ posterior_kernel(const __grid_constant__ CUtensorMap wmap, PostArgs a) {
         }
     } else {
         // =============================== CONSUMERS ===============================
-        reg_alloc<224>();
+        reg_alloc<216>();
         const int gq = lane >> 2, tq = lane & 3;
         const int pr = row_perm(gq);
         // byte offset of this lane's A element inside an 8-row tile for k-step kk: row pr, 16B-chunk ((kk+tq)/2)^pr
@@ -328,6 +361,30 @@ __global__ void posterior_prior_kernel(int64_t G, double mean, double k0, double
     }
 }
 
+// Per-axis factor tables of the separable RBF kernel on a tensor-product grid.  For axis value u and training point n:
+//   TL[u][n] = cL[n] * exp(-0.5 (u/l_L - X_n/l_L)^2)  (x axis; the y-axis table carries no coefficient)
+// with cL = rho*s_L for lofi columns, rho^2*s_L for hifi columns (MF), 0 for SF / padding; cH = s_H for hifi, else 0.
+// exp(a)exp(b) replaces the reference's exp(a+b) (gaussian_process.py:79): a few ulp, far inside the 1e-9 tolerance.
+__global__ void grid_tables_kernel(const double* __restrict__ u, int nu, int axis, const double* __restrict__ Tt, int NL, int NH,
+                                   int npad, DevParams p, double* __restrict__ TL, double* __restrict__ TH, int64_t ldt) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    const int iu = blockIdx.y;
+    if (n >= npad || iu >= nu) return;
+    const int N = NL + NH;
+    double vl = 0.0, vh = 0.0;
+    if (n < N) {
+        const double4 t = reinterpret_cast<const double4*>(Tt)[n];
+        const double uv = u[iu];
+        const double dl = uv / p.l_L - (axis == 0 ? t.x : t.y);
+        const double dh = uv / p.l_H - (axis == 0 ? t.z : t.w);
+        const bool lo = n < NL;
+        if (p.multi) vl = exp(-0.5 * (dl * dl)) * (axis == 0 ? (lo ? p.rho * p.s_L : p.rho2 * p.s_L) : 1.0);
+        if (!lo) vh = exp(-0.5 * (dh * dh)) * (axis == 0 ? p.s_H : 1.0);
+    }
+    TL[(int64_t)iu * ldt + n] = vl;
+    TH[(int64_t)iu * ldt + n] = vh;
+}
+
 // cuTensorMapEncodeTiled through the runtime's driver entry point query (no link-time dependency on libcuda)
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -363,33 +420,72 @@ static int make_w_tensor_map(CUtensorMap* map, const double* W, int64_t npad, in
 
 using namespace mfgp;
 
+static int posterior_common(PostArgs& a, bool grid, const double* W, int64_t npad, int64_t ldw, const mfgp_params* p_host,
+                            cudaStream_t st) {
+    const DevParams dp = make_dev_params(*p_host);
+    a.p = dp;
+    const int64_t N = (int64_t)a.NL + a.NH;
+    if (N == 0) {   // empty model: constant mean and prior variance (gaussian_process.py:139-146 with no data)
+        posterior_prior_kernel<<<(unsigned)((a.G + 255) / 256), 256, 0, st>>>(a.G, dp.mean_H, dp.k0, a.mu, a.var);
+        MFGP_LAUNCH_CHECK();
+        return MFGP_OK;
+    }
+    if (!W || !a.z || npad < N || npad % MFGP_TILE || ldw < npad) return MFGP_ERR_INVALID;
+    if ((reinterpret_cast<uintptr_t>(W) & 15) || (ldw & 1)) return MFGP_ERR_INVALID;     // TMA: 16-byte aligned rows
+    if (!p_host->multi && a.NL != 0) return MFGP_ERR_INVALID;
+    if (a.Vc && a.ldv < a.G) return MFGP_ERR_INVALID;
+    CUtensorMap wmap;
+    int rc = make_w_tensor_map(&wmap, W, npad, ldw);
+    if (rc) return rc;
+    a.npad = (int)npad;
+    const unsigned nblk = (unsigned)((a.G + P_BN - 1) / P_BN);
+    if (grid) {
+        MFGP_CUDA_CHECK(cudaFuncSetAttribute(posterior_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_BYTES));
+        posterior_kernel<true><<<nblk, P_THREADS, P_SMEM_BYTES, st>>>(wmap, a);
+    } else {
+        MFGP_CUDA_CHECK(cudaFuncSetAttribute(posterior_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_BYTES));
+        posterior_kernel<false><<<nblk, P_THREADS, P_SMEM_BYTES, st>>>(wmap, a);
+    }
+    MFGP_LAUNCH_CHECK();
+    return MFGP_OK;
+}
+
 extern "C" int mfgp_posterior(const double* Xs, int64_t G, const double* Tt, int64_t NL, int64_t NH, const double* W,
                               int64_t npad, int64_t ldw, const double* z, const mfgp_params* p_host, double* mu,
                               double* var, double* Vc, int64_t ldv, void* stream) {
     if (!p_host || !mu || !var || G < 0 || NL < 0 || NH < 0) return MFGP_ERR_INVALID;
     if (G == 0) return MFGP_OK;
-    if (!Xs) return MFGP_ERR_INVALID;
+    if (!Xs || (NL + NH > 0 && !Tt)) return MFGP_ERR_INVALID;
+    PostArgs a{};
+    a.Xs = Xs; a.G = G; a.Tt = Tt; a.NL = (int)NL; a.NH = (int)NH; a.z = z; a.mu = mu; a.var = var; a.Vc = Vc; a.ldv = ldv;
+    return posterior_common(a, false, W, npad, ldw, p_host, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int mfgp_grid_tables(const double* ux, int64_t nx, const double* uy, int64_t ny, const double* Tt, int64_t NL,
+                                int64_t NH, int64_t npad, const mfgp_params* p_host, double* TLx, double* TLy, double* THx,
+                                double* THy, int64_t ldt, void* stream) {
+    if (!ux || !uy || !Tt || !p_host || !TLx || !TLy || !THx || !THy || nx <= 0 || ny <= 0 || npad < NL + NH || ldt < npad)
+        return MFGP_ERR_INVALID;
+    if (nx * ldt >= (1LL << 31) || ny * ldt >= (1LL << 31)) return MFGP_ERR_INVALID;   // kernel uses 32-bit table offsets
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const DevParams dp = make_dev_params(*p_host);
-    const int64_t N = NL + NH;
-    if (N == 0) {   // empty model: constant mean and prior variance (gaussian_process.py:139-146 with no data)
-        posterior_prior_kernel<<<(unsigned)((G + 255) / 256), 256, 0, st>>>(G, dp.mean_H, dp.k0, mu, var);
-        MFGP_LAUNCH_CHECK();
-        return MFGP_OK;
-    }
-    if (!Tt || !W || !z || npad < N || npad % MFGP_TILE || ldw < npad) return MFGP_ERR_INVALID;
-    if ((reinterpret_cast<uintptr_t>(W) & 15) || (ldw & 1)) return MFGP_ERR_INVALID;     // TMA: 16-byte aligned rows
-    if (!p_host->multi && NL != 0) return MFGP_ERR_INVALID;
-    if (Vc && ldv < G) return MFGP_ERR_INVALID;
-    CUtensorMap wmap;
-    int rc = make_w_tensor_map(&wmap, W, npad, ldw);
-    if (rc) return rc;
-    PostArgs a;
-    a.Xs = Xs; a.G = G; a.Tt = Tt; a.NL = (int)NL; a.NH = (int)NH; a.npad = (int)npad; a.z = z;
-    a.mu = mu; a.var = var; a.Vc = Vc; a.ldv = ldv; a.p = dp;
-    MFGP_CUDA_CHECK(cudaFuncSetAttribute(posterior_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_BYTES));
-    const unsigned grid = (unsigned)((G + P_BN - 1) / P_BN);
-    posterior_kernel<<<grid, P_THREADS, P_SMEM_BYTES, st>>>(wmap, a);
+    dim3 gx((unsigned)((npad + 127) / 128), (unsigned)nx), gy((unsigned)((npad + 127) / 128), (unsigned)ny);
+    grid_tables_kernel<<<gx, 128, 0, st>>>(ux, (int)nx, 0, Tt, (int)NL, (int)NH, (int)npad, dp, TLx, THx, ldt);
+    MFGP_LAUNCH_CHECK();
+    grid_tables_kernel<<<gy, 128, 0, st>>>(uy, (int)ny, 1, Tt, (int)NL, (int)NH, (int)npad, dp, TLy, THy, ldt);
     MFGP_LAUNCH_CHECK();
     return MFGP_OK;
+}
+
+extern "C" int mfgp_posterior_grid(int64_t ny, int64_t g_lo, int64_t G, const double* TLx, const double* TLy,
+                                   const double* THx, const double* THy, int64_t ldt, int64_t NL, int64_t NH,
+                                   const double* W, int64_t npad, int64_t ldw, const double* z, const mfgp_params* p_host,
+                                   double* mu, double* var, double* Vc, int64_t ldv, void* stream) {
+    if (!p_host || !mu || !var || G < 0 || NL < 0 || NH < 0 || ny <= 0 || g_lo < 0) return MFGP_ERR_INVALID;
+    if (G == 0) return MFGP_OK;
+    if (NL + NH > 0 && (!TLx || !TLy || !THx || !THy || ldt < npad)) return MFGP_ERR_INVALID;
+    PostArgs a{};
+    a.G = G; a.TLx = TLx; a.TLy = TLy; a.THx = THx; a.THy = THy; a.ldt = ldt; a.g_lo = g_lo; a.ny = (int)ny;
+    a.NL = (int)NL; a.NH = (int)NH; a.z = z; a.mu = mu; a.var = var; a.Vc = Vc; a.ldv = ldv;
+    return posterior_common(a, true, W, npad, ldw, p_host, static_cast<cudaStream_t>(stream));
 }

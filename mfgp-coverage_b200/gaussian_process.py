@@ -56,6 +56,7 @@ def prior_variance(params):
 
 class _GPBase:
     raw_means = False     # set True to reproduce runs logged with the pre-exp() mean convention
+    use_separable = True  # tensor-product grids: per-axis factor tables instead of one exp per (point, sample) pair
 
     def _init_device(self):
         self._dev = DeviceGP()
@@ -75,16 +76,26 @@ class _GPBase:
         host = torch.from_numpy(xs)
         return host.to(self._dev.device, non_blocking=False)
 
-    def predict_device(self, xs_dev, mu_out=None, var_out=None, vcache=None):
-        """Posterior on device-resident points; returns device tensors (mu[G], var[G])."""
+    def predict_device(self, xs_dev, mu_out=None, var_out=None, vcache=None, grid=None):
+        """Posterior on device-resident points; returns device tensors (mu[G], var[G]).  `grid`: the CoverageGrid the
+        points belong to -- if it is (a slice of) a tensor-product grid the separable-kernel path is used."""
         if not self._dev.fitted:
             self._refit(check=True)
-        return self._dev.posterior(xs_dev, mu_out, var_out, vcache)
+        axes = getattr(grid, "axes", None) if (grid is not None and self.use_separable) else None
+        g_lo = grid.base_index if axes is not None else 0
+        return self._dev.posterior(xs_dev, mu_out, var_out, vcache, axes=axes, g_lo=g_lo)
 
     def predict(self, X_star):
         """Posterior mean [G,1] and variance [G] at X_star[G,2] (host arrays in, host arrays out)."""
+        from ._engine import TensorAxes, detect_tensor_grid
         xs_dev = self._upload_grid(X_star)
-        mu, var = self.predict_device(xs_dev)
+        axes = None
+        if self.use_separable:
+            t = detect_tensor_grid(X_star)
+            axes = TensorAxes(t[0], t[1], self._dev.device) if t is not None else None
+        if not self._dev.fitted:
+            self._refit(check=True)
+        mu, var = self._dev.posterior(xs_dev, axes=axes)
         return mu.cpu().numpy().reshape(-1, 1), var.cpu().numpy()
 
     def factor(self):

@@ -175,7 +175,7 @@ def compute_sample_points(model, x_star, threshold, console=False, return_indice
     chunk = 128
     cap = n + chunk
     Vc = torch.empty((cap, G), dtype=torch.float64, device=dev)
-    _, var = model.predict_device(grid.xy, vcache=Vc if n else None)
+    _, var = model.predict_device(grid.xy, vcache=Vc if n else None, grid=grid)
     lib = cv.nat.lib()
     work = torch.empty(int(lib.cov_workspace_bytes(G, 1, 0)) // 8 + (G // 256 + 2) * 2 + 64, dtype=torch.float64,
                        device=dev)
@@ -283,7 +283,7 @@ class _Sim:
         loss_vor = voronoi_bounded(positions, bb)
         lloyd_vor = voronoi_bounded(centroids_t, bb)
         if model is not None:
-            model.predict_device(self.grid.xy, self.mu, self.var)
+            model.predict_device(self.grid.xy, self.mu, self.var, grid=self.grid)
             res = self.grid.assign_reduce(lloyd_vor, loss_vor, w=self.mu, var=self.var)
         else:
             res = self.grid.assign_reduce(lloyd_vor, loss_vor, w=weights)
@@ -417,7 +417,7 @@ def _explore_exploit(kind, title, sim_num, iterations, agents, positions, truth,
     print("Max Initial Predictive Variance: " + str(max_var_0)) if console else None
     sim = _Sim(truth)
     truth_arr = sim.truth_arr
-    model.predict_device(sim.grid.xy, sim.mu, sim.var)
+    model.predict_device(sim.grid.xy, sim.mu, sim.var, grid=sim.grid)
     max_var_t = float(sim.grid.argmax(sim.var)[0].item()) * np.ones((agents, 1))
     prob_explore_t = todescato_prob(max_var_t, max_var_0) if kind == "todescato" else np.zeros((agents, 1))
     explore_t = np.zeros((agents, 1))

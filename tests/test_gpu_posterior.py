@@ -97,3 +97,42 @@ def test_not_spd_raises_linalgerror():
     eng = DeviceGP()
     with pytest.raises(np.linalg.LinAlgError):
         eng.fit(X, np.zeros((3, 1)), 0, 3, params)
+
+
+@pytest.mark.parametrize("N,multi", [(130, True), (600, True), (200, False)])
+def test_general_point_list_path(N, multi):
+    """Scattered (non tensor-grid) points and the forced general path: one exp per (point, sample) pair."""
+    from mfgp_coverage_b200._engine import detect_tensor_grid
+    xy = synth.grid(40)
+    f = synth.truth_function(xy)
+    X_L, y_L, X_H, y_H = synth.training_set(xy, f, N, multi=multi)
+    hyp = synth.MF_HYP if multi else synth.SF_HYP
+    p, om, m = _models(hyp, X_L, y_L, X_H, y_H)
+    pts = np.random.default_rng(3).random((3001, 2))
+    assert detect_tensor_grid(pts) is None
+    for q, sep in ((pts, True), (xy, False)):
+        m.use_separable = sep
+        mu_o, var_o = om.predict(q)
+        mu, var = m.predict(q)
+        assert np.max(np.abs(var - var_o)) <= TOL * p.k0
+        assert np.max(np.abs(mu[:, 0] - mu_o)) <= TOL * max(1.0, np.max(np.abs(mu_o)))
+
+
+def test_separable_path_on_a_grid_slice():
+    """Grid sharding: a contiguous slice [lo, hi) of a tensor grid goes through the separable path with the full axes."""
+    import torch
+    from mfgp_coverage_b200._coverage import CoverageGrid
+    from mfgp_coverage_b200._engine import TensorAxes, detect_tensor_grid
+    xy = synth.grid(37)               # 37 is not a multiple of the 32-point CTA tile: tiles straddle grid rows
+    f = synth.truth_function(xy)
+    X_L, y_L, X_H, y_H = synth.training_set(xy, f, 150)
+    p, om, m = _models(synth.MF_HYP, X_L, y_L, X_H, y_H)
+    ux, uy = detect_tensor_grid(xy)
+    assert len(ux) == 37 and len(uy) == 37
+    mu_o, var_o = om.predict(xy)
+    lo, hi = 401, 1203
+    axes = TensorAxes(ux, uy, torch.device("cuda"))
+    g = CoverageGrid(xy[lo:hi], f[lo:hi], base_index=lo, axes=axes)
+    mu, var = m.predict_device(g.xy, grid=g)
+    assert np.max(np.abs(var.cpu().numpy() - var_o[lo:hi])) <= TOL * p.k0
+    assert np.max(np.abs(mu.cpu().numpy() - mu_o[lo:hi])) <= TOL
