@@ -172,31 +172,42 @@ def run_ours(args):
     model = sim.init_MFGP(synth.MF_HYP, np.column_stack((w["X_L"], w["y_L"])))
     model.updt_info(w["X_L"], w["y_L"], w["X_H"], w["y_H"])          # uploads the training set once
     eng = model.engine
-    grid = cv.CoverageGrid(w["xy"][lo:hi], w["f"][lo:hi], base_index=lo)
+    from mfgp_coverage_b200._engine import TensorAxes, detect_tensor_grid
+    tg = detect_tensor_grid(w["xy"])                                   # the synthetic grids are tensor-product grids
+    axes = TensorAxes(tg[0], tg[1], dev) if tg is not None else None
+    grid = cv.CoverageGrid(w["xy"][lo:hi], w["f"][lo:hi], base_index=lo, axes=axes)
     mu = torch.empty(hi - lo, dtype=torch.float64, device=dev)
     var = torch.empty(hi - lo, dtype=torch.float64, device=dev)
     flush = torch.empty(64 << 20, dtype=torch.float32, device=dev) if w["name"] != "c4" else None
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-    post_ms = []
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    post_ms, fit_ms, cov_ms = [], [], []
 
     def device_step(timed):
         if flush is not None:
             flush.zero_()
+        if timed:
+            ev[3].record()
         eng.refactor(check=False)                                     # K -> L -> W -> z  (train set resident)
+        if axes is not None:
+            eng.grid_tables(axes)                                     # per-axis factor tables of the separable kernel
         if timed:
             ev[0].record()
-        eng.posterior(grid.xy, mu, var)
+        eng.posterior(grid.xy, mu, var, axes=axes, g_lo=lo)
         if timed:
             ev[1].record()
         loss_vor = sim.voronoi_bounded(w["pos"], bbox)
         lloyd_vor = sim.voronoi_bounded(w["cen"], bbox)
         res = grid.assign_reduce(lloyd_vor, loss_vor, w=mu, var=var)
+        if timed:
+            ev[2].record()
         sharding.allreduce_partials(res)
         loss = cv.loss_from_partials(res["lossp"].cpu().numpy(), loss_vor.areas())
         cent = cv.centroids_from_partials(res["cent"].cpu().numpy(), lloyd_vor.areas(), 0.0, 1.0, 0.0, 1.0)
         idx = res["amax_idx"].cpu().numpy()
         if timed:
             post_ms.append(ev[0].elapsed_time(ev[1]))                 # .cpu() above synchronised the stream
+            fit_ms.append(ev[3].elapsed_time(ev[0]))
+            cov_ms.append(ev[1].elapsed_time(ev[2]))                  # includes the host Qhull calls before the launch
         return loss, cent, idx
 
     def barrier():
@@ -272,7 +283,11 @@ def run_ours(args):
                          "traffic": None, "kernel_ms": pm, "kernel_share_of_step": pm / ms_dev,
                          "peak_source": "cuBLAS DGEMM 8192^3 measured on this pool (profiles/r01_dgemm_peak.json); "
                                         "MEASURED_PEAKS.json has no FP64 figure; DMMA issue peak 37.15"},
-            "check": {"loss": float(out[0]), "loss_e2e": float(out_e2e[0]), "npad": int(npad)},
+            "breakdown_ms": {"fit(K+chol+inverse+whiten+tables)": float(np.mean(fit_ms)), "posterior": pm,
+                             "qhull+coverage_kernels": float(np.mean(cov_ms)),
+                             "d2h+host_finish": ms_dev - pm - float(np.mean(fit_ms)) - float(np.mean(cov_ms))},
+            "check": {"loss": float(out[0]), "loss_e2e": float(out_e2e[0]), "npad": int(npad),
+                      "separable_grid_path": axes is not None},
         })
         if world == 1:
             pts = cpu_sample_points(w)

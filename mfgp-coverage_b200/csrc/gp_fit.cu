@@ -50,6 +50,12 @@ __global__ void build_train_cov_kernel(const double* __restrict__ Xt, int NL, in
 }
 
 // ---- 64x64 diagonal block: Cholesky + inverse in one CTA --------------------------------------------------------------
+// Shared-memory resident, 256 threads, rolled loops (a fully unrolled register version is instruction-fetch bound).
+// Factor: right-looking with ONE barrier per column and no divide / sqrt on the critical path -- column j is left
+// UNSCALED (u = L sqrt(p_j)), every thread takes r = rsqrt(p_j), the trailing update is a[i][c] -= u_i u_c r^2, and
+// L = u r is applied to all columns in one pass at the end (r_j is also 1 / L[j][j], so the inverse needs no divide).
+// Inverse: block doubling inside the CTA, X21 = -X22 (L21 X11) for block sizes 8 -> 16 -> 32, all pairs of a level in
+// parallel, the product L21 X11 parked in the (finally zero) upper-right block of X.
 constexpr int PB = 64;
 constexpr int PLD = PB + 1;
 
@@ -58,33 +64,33 @@ __global__ void __launch_bounds__(256) potrf_diag_kernel(double* __restrict__ A,
     extern __shared__ __align__(16) double potrf_smem[];   // 2 x 64x65 doubles: above the 48 KB static limit
     double* S = potrf_smem;
     double* X = potrf_smem + PB * PLD;
+    __shared__ double rs[PB];        // 1/sqrt(pivot) == 1/L[j][j]
     __shared__ int bad;
     const int tid = threadIdx.x;
+    const int ti = tid >> 4, tc = tid & 15;      // 16 x 16 thread grid for the trailing update
     if (tid == 0) bad = 0;
     for (int e = tid; e < PB * PB; e += 256) {
         const int r = e >> 6, c = e & 63;
         S[r * PLD + c] = (c <= r) ? A[(int64_t)r * ld + c] : 0.0;
+        X[r * PLD + c] = 0.0;
     }
     for (int j = 0; j < PB; j++) {
         __syncthreads();
-        const double piv = S[j * PLD + j];
-        if (!(piv > 0.0)) {     // uniform: every thread reads the same pivot
-            if (tid == 0) {
+        double piv = S[j * PLD + j];
+        if (!(piv > 0.0)) {     // uniform: np.linalg.cholesky raises here (gaussian_process.py:254 / :529)
+            if (tid == 0 && !bad) {
                 bad = 1;
                 atomicCAS(info, 0, jblk * PB + j + 1);
             }
-            break;
+            piv = 1.0;
         }
-        const double d = sqrt(piv);
-        __syncthreads();
-        if (tid == 0) S[j * PLD + j] = d;
-        if (tid > j && tid < PB) S[tid * PLD + j] = S[tid * PLD + j] / d;
-        __syncthreads();
-        // trailing update of the lower triangle right of column j: rows i > j, columns j < c <= i
-        const int rem = PB - 1 - j;
-        for (int e = tid; e < rem * rem; e += 256) {
-            const int i = j + 1 + e / rem, c = j + 1 + e % rem;
-            if (c <= i) S[i * PLD + c] -= S[i * PLD + j] * S[c * PLD + j];
+        const double r = rsqrt(piv);
+        const double ip = r * r;
+        if (tid == 0) rs[j] = r;
+        // trailing update over rows i > j, columns j < c <= i (16x16 threads tile the block)
+        for (int i = j + 1 + ti; i < PB; i += 16) {
+            const double f = S[i * PLD + j] * ip;
+            for (int c = j + 1 + tc; c <= i; c += 16) S[i * PLD + c] = fma(-f, S[c * PLD + j], S[i * PLD + c]);
         }
     }
     __syncthreads();
@@ -93,33 +99,59 @@ __global__ void __launch_bounds__(256) potrf_diag_kernel(double* __restrict__ A,
             const int r = e >> 6, c = e & 63;
             S[r * PLD + c] = (r == c) ? 1.0 : 0.0;
         }
-        __syncthreads();
+        if (tid < PB) rs[tid] = 1.0;
+    } else {
+        for (int e = tid; e < PB * PB; e += 256) {
+            const int r = e >> 6, c = e & 63;
+            if (c <= r) S[r * PLD + c] *= rs[c];
+        }
     }
+    __syncthreads();
     for (int e = tid; e < PB * PB; e += 256) {
         const int r = e >> 6, c = e & 63;
         if (c <= r) A[(int64_t)r * ld + c] = S[r * PLD + c];
     }
-    // inverse: thread c solves L x = e_c by forward substitution (column c of L^-1), two partial sums for ILP
-    if (tid < PB) {
-        const int c = tid;
-        for (int i = 0; i < c; i++) X[i * PLD + c] = 0.0;
-        for (int i = c; i < PB; i++) {
-            double s0 = (i == c) ? 1.0 : 0.0, s1 = 0.0;
-            int k = c;
-            for (; k + 1 < i; k += 2) {
-                s0 -= S[i * PLD + k] * X[k * PLD + c];
-                s1 -= S[i * PLD + k + 1] * X[(k + 1) * PLD + c];
+    if (Winv == nullptr) return;
+    // level 0: the eight 8x8 diagonal blocks, one warp each, lane c < 8 solves column c by forward substitution
+    {
+        const int b0 = (tid >> 5) * 8, c = tid & 31;
+        if (c < 8) {
+            for (int i = c; i < 8; i++) {
+                double s = (i == c) ? 1.0 : 0.0;
+                for (int k = c; k < i; k++) s = fma(-S[(b0 + i) * PLD + b0 + k], X[(b0 + k) * PLD + b0 + c], s);
+                X[(b0 + i) * PLD + b0 + c] = s * rs[b0 + i];
             }
-            if (k < i) s0 -= S[i * PLD + k] * X[k * PLD + c];
-            X[i * PLD + c] = (s0 + s1) / S[i * PLD + i];
+        }
+    }
+    for (int bs = 8, sh = 3; bs < PB; bs <<= 1, sh++) {
+        const int total = 32 * bs;                  // (64 / 2bs) pairs x bs^2 elements
+        __syncthreads();
+        for (int e = tid; e < total; e += 256) {    // T = L21 X11 (X11 lower triangular: k >= c)
+            const int t = e >> (2 * sh), rem = e & (bs * bs - 1), i = rem >> sh, c = rem & (bs - 1);
+            const int top = 2 * bs * t;
+            double s = 0.0;
+            for (int k = c; k < bs; k++) s = fma(S[(top + bs + i) * PLD + top + k], X[(top + k) * PLD + top + c], s);
+            X[(top + i) * PLD + top + bs + c] = s;
+        }
+        __syncthreads();
+        for (int e = tid; e < total; e += 256) {    // X21 = -X22 T (X22 lower triangular: k <= i)
+            const int t = e >> (2 * sh), rem = e & (bs * bs - 1), i = rem >> sh, c = rem & (bs - 1);
+            const int top = 2 * bs * t;
+            double s = 0.0;
+            for (int k = 0; k <= i; k++) s = fma(X[(top + bs + i) * PLD + top + bs + k], X[(top + k) * PLD + top + bs + c], s);
+            X[(top + bs + i) * PLD + top + c] = -s;
+        }
+        __syncthreads();
+        for (int e = tid; e < total; e += 256) {    // clear the parked product
+            const int t = e >> (2 * sh), rem = e & (bs * bs - 1), i = rem >> sh, c = rem & (bs - 1);
+            X[(2 * bs * t + i) * PLD + 2 * bs * t + bs + c] = 0.0;
         }
     }
     __syncthreads();
-    if (Winv != nullptr)
-        for (int e = tid; e < PB * PB; e += 256) {
-            const int r = e >> 6, c = e & 63;
-            Winv[(int64_t)r * ldw + c] = X[r * PLD + c];
-        }
+    for (int e = tid; e < PB * PB; e += 256) {
+        const int r = e >> 6, c = e & 63;
+        Winv[(int64_t)r * ldw + c] = X[r * PLD + c];
+    }
 }
 
 __global__ void zero_offdiag_blocks_kernel(double* __restrict__ W, int npad, int64_t ldw) {

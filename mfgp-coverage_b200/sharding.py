@@ -73,14 +73,17 @@ class ShardedGrid:
 
     def __init__(self, xy_host, f_host=None, group=None):
         from ._coverage import CoverageGrid
+        from ._engine import TensorAxes, detect_tensor_grid
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         xy_host = np.asarray(xy_host, dtype=np.float64).reshape(-1, 2)
         self.G_total = xy_host.shape[0]
         self.lo, self.hi = shard_bounds(self.G_total, self.world, self.rank)
+        tg = detect_tensor_grid(xy_host)
+        axes = TensorAxes(tg[0], tg[1], torch.device("cuda", torch.cuda.current_device())) if tg is not None else None
         self.local = CoverageGrid(xy_host[self.lo:self.hi], None if f_host is None else np.asarray(f_host)[self.lo:self.hi],
-                                  base_index=self.lo)
+                                  base_index=self.lo, axes=axes)
 
     def assign_reduce(self, *a, **k):
         return allreduce_partials(self.local.assign_reduce(*a, **k), self.group)
