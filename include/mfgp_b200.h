@@ -77,10 +77,11 @@ int mfgp_whiten(const double* W, int64_t npad, int64_t ldw, const double* y, int
 
 /* mu[G] = mean_H + psi^T K^-1 (y-m), var[G] = k(0) - |W psi|^2 for the G points Xs[G,2].  Fused: psi tiles are
  * generated on chip, multiplied by W on DMMA and reduced; psi / V never reach HBM.  N = NL+NH may be 0 (prior).
- * If Vc != NULL the whitened cross-covariance V = W psi^T is also stored, Vc[n*ldv + g] (for choi_greedy). */
+ * If Vc != NULL the whitened cross-covariance V = W psi^T is also stored, Vc[n*ldv + g] (for choi_greedy); if
+ * qred != NULL the variance reduction |W psi|^2 is stored as well (var = k(0) - qred loses it when qred ~ ulp). */
 int mfgp_posterior(const double* Xs, int64_t G, const double* Tt, int64_t NL, int64_t NH,
                    const double* W, int64_t npad, int64_t ldw, const double* z, const mfgp_params* p_host,
-                   double* mu, double* var, double* Vc, int64_t ldv, void* stream);
+                   double* mu, double* var, double* qred, double* Vc, int64_t ldv, void* stream);
 
 /* Tensor-product grids (every grid of the reference: distribution.py:337-339 builds `[[i, j] for i in g for j in g]`).
  * The RBF kernel is separable per axis, so psi[g][n] = TLx[ix][n]*TLy[iy][n] + THx[ix][n]*THy[iy][n] with
@@ -93,8 +94,8 @@ int mfgp_grid_tables(const double* ux, int64_t nx, const double* uy, int64_t ny,
                      int64_t ldt, void* stream);
 int mfgp_posterior_grid(int64_t ny, int64_t g_lo, int64_t G, const double* TLx, const double* TLy, const double* THx,
                         const double* THy, int64_t ldt, int64_t NL, int64_t NH, const double* W, int64_t npad,
-                        int64_t ldw, const double* z, const mfgp_params* p_host, double* mu, double* var, double* Vc,
-                        int64_t ldv, void* stream);
+                        int64_t ldw, const double* z, const mfgp_params* p_host, double* mu, double* var, double* qred,
+                        double* Vc, int64_t ldv, void* stream);
 
 /* ---- coverage step: replaces simulator.py in_polygon :105-124, compute_loss :194-228, compute_centroids :231-283,
  *      compute_max_var :286-323, compute_sample_clusters :377-412 ------------------------------------------------ */
@@ -109,28 +110,35 @@ int mfgp_posterior_grid(int64_t ny, int64_t g_lo, int64_t G, const double* TLx, 
  * poly_xy[nvert,2] / poly_off[A+1] (Qhull vertex order; nvert == poly_off[A]); a point may then fall in 0, 1 or several cells, exactly as in
  * the reference.  tie_tol = +inf forces the crossings test everywhere.  w / var / f / member_* may be NULL to skip
  * the corresponding output; Ac or Ap may be 0.  member_c[G, ceil(Ac/64)] receives the membership bit masks.
- * `base_index` is added to grid indices (grid sharding).  Deterministic (no floating-point atomics). */
+ * `base_index` is added to grid indices (grid sharding).  Deterministic (no floating-point atomics).
+ * Arg-max ties (amax_k0, amax_rel): two variances are tied when they differ by at most amax_rel * (amax_k0 - smaller),
+ * a tolerance relative to the variance REDUCTION; ties go to the LOWEST index (np.argmax returns the first index).
+ * This reproduces both ways the reference's variances tie: bit-identical values at mirror-image points of a symmetric
+ * prior (tolerance >> arithmetic noise) and the 1-ulp plateaus of k0 - q far from all data (tolerance << 1 ulp, exact
+ * compare).  amax_rel = 0: plain first-index arg-max.  Callers in simulator.py pass k(0) and 1e-10. */
 int cov_assign_reduce(const double* xy, const double* w, const double* var, const double* f, int64_t G,
                       int64_t base_index,
                       const double* seeds_c, int64_t Ac, const double* poly_xy_c, const int32_t* poly_off_c, int64_t nvert_c,
                       const double* seeds_p, int64_t Ap, const double* poly_xy_p, const int32_t* poly_off_p, int64_t nvert_p,
-                      double tie_tol,
+                      double tie_tol, double amax_k0, double amax_rel,
                       double* cent, double* amax_val, int64_t* amax_idx, double* lossp,
                       uint64_t* member_c, void* work, int64_t work_bytes, void* stream);
 int64_t cov_workspace_bytes(int64_t G, int64_t Ac, int64_t Ap);
 
 /* Global first-index argmax of v[G] (np.argmax at simulator.py:352): out_val[1], out_idx[1]. */
-int cov_argmax(const double* v, int64_t G, int64_t base_index, double* out_val, int64_t* out_idx, void* work,
-               int64_t work_bytes, void* stream);
+int cov_argmax(const double* v, int64_t G, int64_t base_index, double k0, double rel, double* out_val, int64_t* out_idx,
+               void* work, int64_t work_bytes, void* stream);
 
 /* ---- Choi greedy sample planner: replaces compute_sample_points simulator.py:326-374 ---------------------------- */
 
 /* Greedy max-variance selection on the cached V (rows [0,n0) valid, capacity rows `cap`, row stride ldv >= G):
- * while max(var) > threshold: j = first argmax; append the bordered-Cholesky row for x_j (hifi level, pseudo-
- * observation = current mean, so mu is unchanged); var -= v^2.  Picks (grid indices) go to picks_host[<= max_picks];
+ * while max(var) > threshold: j = first argmax (tie rule as above with k0 = k(0), rel = tie_rel); append the bordered-
+ * Cholesky row for x_j (hifi level, pseudo-observation = current mean, so mu is unchanged); qred += v^2 and
+ * var = k(0) - qred (recomputed, never decremented: the reference re-predicts from scratch).  Picks (grid indices) go to picks_host[<= max_picks];
  * returns the number of picks (>= 0) or a negative error.  BLOCKING (synchronises `stream` once per pick). */
 int64_t choi_greedy(const double* Xs, int64_t G, double* Vc, int64_t ldv, int64_t n0, int64_t cap, double* var,
-                    const mfgp_params* p_host, double threshold, int64_t max_picks, int64_t* picks_host,
+                    double* qred, const mfgp_params* p_host, double threshold, double tie_rel, int64_t max_picks,
+                    int64_t* picks_host,
                     void* work, int64_t work_bytes, void* stream);
 
 #ifdef __cplusplus

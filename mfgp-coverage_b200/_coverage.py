@@ -15,6 +15,7 @@ from . import _native as nat
 
 EPS = 0.1            # boundary cushion, simulator.py:33
 TIE_TOL = 1e-9       # |d2_second - d2_best| below which the exact crossings test decides membership
+AMAX_REL = 1e-10     # arg-max ties: |dvar| <= AMAX_REL * (k(0) - var) counts as tied, first index wins (argmax.cuh)
 
 
 def in_box(points, bounding_box):
@@ -134,7 +135,8 @@ class CoverageGrid:
             self._work = torch.empty(need // 8 + 8, dtype=torch.float64, device=self.device)
         return self._work
 
-    def assign_reduce(self, lloyd_vor=None, loss_vor=None, w=None, var=None, want_members=False, tie_tol=None):
+    def assign_reduce(self, lloyd_vor=None, loss_vor=None, w=None, var=None, want_members=False, tie_tol=None,
+                      amax_k0=0.0, amax_rel=0.0):
         """One fused pass.  Returns a dict of DEVICE tensors: cent[Ac,4], amax_val[Ac], amax_idx[Ac], lossp[Ap,2],
         members[G,words] (optional)."""
         dev = self.device
@@ -163,18 +165,19 @@ class CoverageGrid:
             C.nvert if C else 0,
             nat.ptr(P.seeds) if P else None, Ap, nat.ptr(P.poly) if P else None, nat.ptr(P.off) if P else None,
             P.nvert if P else 0,
-            ctypes.c_double(tie_tol), nat.ptr(cent), nat.ptr(amax_val), nat.ptr(amax_idx), nat.ptr(lossp),
+            ctypes.c_double(tie_tol), ctypes.c_double(amax_k0), ctypes.c_double(amax_rel), nat.ptr(cent), nat.ptr(amax_val), nat.ptr(amax_idx), nat.ptr(lossp),
             nat.ptr(members), nat.ptr(work), work.numel() * 8, nat.stream_ptr())
         nat.check(rc, "cov_assign_reduce")
         out.update(cent=cent, amax_val=amax_val, amax_idx=amax_idx, lossp=lossp, members=members)
         return out
 
-    def argmax(self, v_dev):
+    def argmax(self, v_dev, k0=0.0, rel=0.0):
         """First-index argmax of a device vector (np.argmax semantics): returns (value, index) device tensors."""
         val = torch.empty(1, dtype=torch.float64, device=self.device)
         idx = torch.empty(1, dtype=torch.int64, device=self.device)
         work = self._workspace(1, 0)
-        nat.check(nat.lib().cov_argmax(nat.ptr(v_dev), int(v_dev.numel()), self.base_index, nat.ptr(val),
+        nat.check(nat.lib().cov_argmax(nat.ptr(v_dev), int(v_dev.numel()), self.base_index, ctypes.c_double(k0), ctypes.c_double(rel),
+                                       nat.ptr(val),
                                        nat.ptr(idx), nat.ptr(work), work.numel() * 8, nat.stream_ptr()), "cov_argmax")
         return val, idx
 

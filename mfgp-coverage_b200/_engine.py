@@ -169,7 +169,7 @@ class DeviceGP:
             self.refactor(check=check)
 
     # -- posterior ----------------------------------------------------------------------------------------------------
-    def posterior(self, xs_dev, mu_out=None, var_out=None, vcache=None, axes=None, g_lo=0):
+    def posterior(self, xs_dev, mu_out=None, var_out=None, vcache=None, axes=None, g_lo=0, q_out=None):
         """Posterior mean / variance for device-resident points xs_dev[G,2].  Replaces predict
         (gaussian_process.py:121-148, :401-438), diagonal only.  Returns device tensors (mu[G], var[G]).
         If `axes` (TensorAxes) is given the points are the flat x-major range [g_lo, g_lo+G) of that tensor-product
@@ -185,11 +185,13 @@ class DeviceGP:
             nat.check(lib.mfgp_posterior_grid(axes.ny, int(g_lo), G, nat.ptr(TLx), nat.ptr(TLy), nat.ptr(THx),
                                               nat.ptr(THy), ldt, self.NL, self.NH, nat.ptr(self.W), self.npad, self.cap,
                                               nat.ptr(self.z), ctypes.byref(self.pstruct), nat.ptr(mu), nat.ptr(var),
-                                              nat.ptr(vcache), ldv, nat.stream_ptr()), "mfgp_posterior_grid")
+                                              nat.ptr(q_out), nat.ptr(vcache), ldv, nat.stream_ptr()),
+                      "mfgp_posterior_grid")
             return mu, var
         nat.check(lib.mfgp_posterior(nat.ptr(xs_dev), G, nat.ptr(self.Tt), self.NL, self.NH, nat.ptr(self.W),
                                      self.npad, self.cap, nat.ptr(self.z), ctypes.byref(self.pstruct), nat.ptr(mu),
-                                     nat.ptr(var), nat.ptr(vcache), ldv, nat.stream_ptr()), "mfgp_posterior")
+                                     nat.ptr(var), nat.ptr(q_out), nat.ptr(vcache), ldv, nat.stream_ptr()),
+                  "mfgp_posterior")
         return mu, var
 
     def clone(self):

@@ -38,21 +38,23 @@ SIGNATURES = {
     "mfgp_whiten": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64, POINTER(MfgpParams), c_void_p,
                             c_void_p]),
     "mfgp_posterior": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64, c_void_p,
-                               POINTER(MfgpParams), c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+                               POINTER(MfgpParams), c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "mfgp_grid_tables": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64,
                                  POINTER(MfgpParams), c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "mfgp_posterior_grid": (c_int, [c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64,
                                     c_int64, c_void_p, c_int64, c_int64, c_void_p, POINTER(MfgpParams), c_void_p,
-                                    c_void_p, c_void_p, c_int64, c_void_p]),
+                                    c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "cov_assign_reduce": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64,
                                   c_void_p, c_int64, c_void_p, c_void_p, c_int64,
                                   c_void_p, c_int64, c_void_p, c_void_p, c_int64,
-                                  c_double, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
-                                  c_void_p]),
+                                  c_double, c_double, c_double, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                  c_void_p, c_int64, c_void_p]),
     "cov_workspace_bytes": (c_int64, [c_int64, c_int64, c_int64]),
-    "cov_argmax": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
-    "choi_greedy": (c_int64, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_void_p, POINTER(MfgpParams),
-                              c_double, c_int64, POINTER(c_int64), c_void_p, c_int64, c_void_p]),
+    "cov_argmax": (c_int, [c_void_p, c_int64, c_int64, c_double, c_double, c_void_p, c_void_p, c_void_p, c_int64,
+                           c_void_p]),
+    "choi_greedy": (c_int64, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p,
+                              POINTER(MfgpParams), c_double, c_double, c_int64, POINTER(c_int64), c_void_p, c_int64,
+                              c_void_p]),
 }
 
 _lib = None

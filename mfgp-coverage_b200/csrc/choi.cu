@@ -22,6 +22,8 @@ struct ChoiArgs {
     double* var;
     const long long* pick;                   // device: grid index of the point being appended
     DevParams p;
+    TieRule tol;                             // arg-max tie rule
+    double* q;                               // running sum of v^2 per grid point (variance reduction)
     double* pv; long long* pi;               // per-block argmax candidates of the updated variance
 };
 
@@ -50,7 +52,7 @@ __global__ void __launch_bounds__(CH_THREADS) choi_append_kernel(ChoiArgs a) {
     const double xj = a.Xs[2 * j], yj = a.Xs[2 * j + 1];
 
     const int64_t g = (int64_t)blockIdx.x * CH_COLS + tid * 2;
-    double bv = -DBL_MAX; long long bi = 0x7fffffffffffffffLL;
+    ArgMax best{0.0, -1};
     if (g < a.G) {
         const bool pair = (g + 1 < a.G) && ((a.ldv & 1) == 0);
         double s0 = 0.0, s1 = 0.0;
@@ -89,24 +91,20 @@ __global__ void __launch_bounds__(CH_THREADS) choi_append_kernel(ChoiArgs a) {
                 }
                 const double v = (k - (c ? s1 : s0)) / d;
                 a.Vc[(int64_t)a.n * a.ldv + gg] = v;
-                const double nv = a.var[gg] - v * v;
+                const double nq = a.q[gg] + v * v;         // var is recomputed from the accumulated reduction, as the
+                a.q[gg] = nq;                              // reference's full predict does (k** - psi beta), never decremented
+                const double nv = p.k0 - nq;
                 a.var[gg] = nv;
-                if (nv > bv) { bv = nv; bi = gg; }
+                best = argmax_combine(best, ArgMax{nv, (long long)gg}, a.tol);
             }
         }
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
-        const long long oi = __shfl_xor_sync(0xffffffffu, bi, o);
-        if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
-    }
-    if (lane == 0) { sv[warp] = bv; si[warp] = bi; }
+    best = argmax_warp(best, a.tol);
+    if (lane == 0) { sv[warp] = best.v; si[warp] = best.i; }
     __syncthreads();
     if (tid == 0) {
-        for (int w = 1; w < CH_THREADS / 32; w++)
-            if (sv[w] > bv || (sv[w] == bv && si[w] < bi)) { bv = sv[w]; bi = si[w]; }
-        a.pv[blockIdx.x] = bv; a.pi[blockIdx.x] = bi;
+        for (int w = 1; w < CH_THREADS / 32; w++) best = argmax_combine(best, ArgMax{sv[w], si[w]}, a.tol);
+        a.pv[blockIdx.x] = best.v; a.pi[blockIdx.x] = best.i;
     }
 }
 
@@ -115,9 +113,10 @@ __global__ void __launch_bounds__(CH_THREADS) choi_append_kernel(ChoiArgs a) {
 using namespace mfgp;
 
 extern "C" int64_t choi_greedy(const double* Xs, int64_t G, double* Vc, int64_t ldv, int64_t n0, int64_t cap, double* var,
-                               const mfgp_params* p_host, double threshold, int64_t max_picks, int64_t* picks_host,
+                               double* q, const mfgp_params* p_host, double threshold, double tie_rel, int64_t max_picks,
+                               int64_t* picks_host,
                                void* work, int64_t work_bytes, void* stream) {
-    if (!Xs || !Vc || !var || !p_host || !picks_host || !work || G <= 0 || ldv < G || n0 < 0 || cap < n0) return MFGP_ERR_INVALID;
+    if (!Xs || !Vc || !var || !q || !p_host || !picks_host || !work || G <= 0 || ldv < G || n0 < 0 || cap < n0) return MFGP_ERR_INVALID;
     const int nblocks = (int)((G + CH_COLS - 1) / CH_COLS);
     const int64_t need = (int64_t)nblocks * 16 + 64 + cov_workspace_bytes(G, 1, 0);
     if (work_bytes < need) return MFGP_ERR_INVALID;
@@ -128,7 +127,9 @@ extern "C" int64_t choi_greedy(const double* Xs, int64_t G, double* Vc, int64_t 
     int64_t* d_idx = reinterpret_cast<int64_t*>(d_val + 1);
     void* awork = d_idx + 7;
     const int64_t awork_bytes = work_bytes - ((char*)awork - (char*)work);
-    int rc = cov_argmax(var, G, 0, d_val, d_idx, awork, awork_bytes, st);
+    const DevParams dp0 = make_dev_params(*p_host);
+    const TieRule tol{dp0.k0, tie_rel > 0.0 ? tie_rel : 0.0};
+    int rc = cov_argmax(var, G, 0, tol.k0, tol.rel, d_val, d_idx, awork, awork_bytes, st);
     if (rc) return rc;
     struct { double val; int64_t idx; } h;
     const DevParams dp = make_dev_params(*p_host);
@@ -142,13 +143,13 @@ extern "C" int64_t choi_greedy(const double* Xs, int64_t G, double* Vc, int64_t 
         picks_host[picks++] = h.idx;
         ChoiArgs a;
         a.Xs = Xs; a.G = G; a.Vc = Vc; a.ldv = ldv; a.n = (int)n; a.var = var;
-        a.pick = reinterpret_cast<const long long*>(d_idx); a.p = dp; a.pv = pv; a.pi = pi;
+        a.pick = reinterpret_cast<const long long*>(d_idx); a.p = dp; a.tol = tol; a.q = q; a.pv = pv; a.pi = pi;
         const size_t smem = sizeof(double) * (size_t)(n > 0 ? n : 1);
         if (smem > 48 * 1024)
             MFGP_CUDA_CHECK(cudaFuncSetAttribute(choi_append_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         choi_append_kernel<<<nblocks, CH_THREADS, smem, st>>>(a);
         MFGP_LAUNCH_CHECK();
-        argmax_final_kernel<<<1, 32, 0, st>>>(pv, pi, nblocks, d_val, d_idx);
+        argmax_final_kernel<<<1, 32, 0, st>>>(pv, pi, nblocks, tol, d_val, d_idx);
         MFGP_LAUNCH_CHECK();
         n++;
     }

@@ -33,6 +33,7 @@ struct CovArgs {
     int64_t G; int64_t base_index;
     CovPartition C, P;
     double tie_tol;
+    TieRule amax_tol;     // tie rule of the per-cell arg-max (see argmax_combine)
     uint64_t* member_c;
     double* partials;     // [nblocks][C.A*C_SLOTS + P.A*P_SLOTS]
 };
@@ -160,20 +161,15 @@ __global__ void __launch_bounds__(COV_THREADS) cov_assign_reduce_kernel(CovArgs 
                     const double s1 = warp_sum(mine ? wx : 0.0);
                     const double s2 = warp_sum(mine ? wy : 0.0);
                     const int cnt = __popc(__ballot_sync(0xffffffffu, mine));
-                    double bv = mine ? vv : -DBL_MAX;
-                    long long bidx = mine ? (long long)(a.base_index + g) : 0x7fffffffffffffffLL;
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) {
-                        const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
-                        const long long oi = __shfl_xor_sync(0xffffffffu, bidx, o);
-                        if (ov > bv || (ov == bv && oi < bidx)) { bv = ov; bidx = oi; }
-                    }
+                    const ArgMax am = argmax_warp(ArgMax{vv, mine ? (long long)(a.base_index + g) : -1LL}, a.amax_tol);
                     if (lane == 0) {
                         double* slot = wacc + c * C_SLOTS;
                         slot[0] += s0; slot[1] += s1; slot[2] += s2; slot[3] += (double)cnt;
                         long long* islot = reinterpret_cast<long long*>(slot);
-                        // later points have larger indices, so a strict '>' keeps the first index on ties
-                        if (a.var && (bv > slot[4] || islot[5] < 0)) { slot[4] = bv; islot[5] = bidx; }
+                        if (a.var) {
+                            const ArgMax r = argmax_combine(ArgMax{slot[4], islot[5]}, am, a.amax_tol);
+                            slot[4] = r.v; islot[5] = r.i;
+                        }
                     }
                     m[k] &= ~(1ull << bit);
                 }
@@ -219,14 +215,12 @@ __global__ void __launch_bounds__(COV_THREADS) cov_assign_reduce_kernel(CovArgs 
             for (int w = 0; w < COV_WARPS; w++) s += s_acc[w * stride + i];
             out[i] = s;
         } else if (slot == 4) {
-            double bv = -DBL_MAX; long long bidx = -1;
-            for (int w = 0; w < COV_WARPS; w++) {
-                const double v = s_acc[w * stride + i];
-                const long long id = reinterpret_cast<const long long*>(s_acc)[w * stride + i + 1];
-                if (id >= 0 && (bidx < 0 || v > bv || (v == bv && id < bidx))) { bv = v; bidx = id; }
-            }
-            out[i] = bv;
-            reinterpret_cast<long long*>(out)[i + 1] = bidx;
+            ArgMax best{0.0, -1};
+            for (int w = 0; w < COV_WARPS; w++)
+                best = argmax_combine(best, ArgMax{s_acc[w * stride + i], reinterpret_cast<const long long*>(s_acc)[w * stride + i + 1]},
+                                      a.amax_tol);
+            out[i] = best.v;
+            reinterpret_cast<long long*>(out)[i + 1] = best.i;
         }
     }
     for (int i = tid; i < Ap * P_SLOTS; i += COV_THREADS) {
@@ -236,7 +230,7 @@ __global__ void __launch_bounds__(COV_THREADS) cov_assign_reduce_kernel(CovArgs 
     }
 }
 
-__global__ void cov_finalize_kernel(const double* __restrict__ partials, int nblocks, int Ac, int Ap, double* __restrict__ cent,
+__global__ void cov_finalize_kernel(const double* __restrict__ partials, int nblocks, int Ac, int Ap, TieRule amax_tol, double* __restrict__ cent,
                                     double* __restrict__ amax_val, int64_t* __restrict__ amax_idx, double* __restrict__ lossp) {
     const int stride = Ac * C_SLOTS + Ap * P_SLOTS;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -247,14 +241,13 @@ __global__ void cov_finalize_kernel(const double* __restrict__ partials, int nbl
         if (cent) cent[i] = acc;
     } else if (i < Ac * 5) {
         const int c = i - Ac * 4;
-        double bv = -DBL_MAX; long long bidx = -1;
-        for (int b = 0; b < nblocks; b++) {
-            const double v = partials[(int64_t)b * stride + c * C_SLOTS + 4];
-            const long long id = reinterpret_cast<const long long*>(partials)[(int64_t)b * stride + c * C_SLOTS + 5];
-            if (id >= 0 && (bidx < 0 || v > bv || (v == bv && id < bidx))) { bv = v; bidx = id; }
-        }
-        if (amax_val) amax_val[c] = bv;
-        if (amax_idx) amax_idx[c] = bidx;
+        ArgMax best{0.0, -1};
+        for (int b = 0; b < nblocks; b++)
+            best = argmax_combine(best, ArgMax{partials[(int64_t)b * stride + c * C_SLOTS + 4],
+                                               reinterpret_cast<const long long*>(partials)[(int64_t)b * stride + c * C_SLOTS + 5]},
+                                  amax_tol);
+        if (amax_val) amax_val[c] = best.v;
+        if (amax_idx) amax_idx[c] = best.i;
     } else if (i < Ac * 5 + Ap * 2) {
         const int j = i - Ac * 5;
         double acc = 0.0;
@@ -277,7 +270,7 @@ extern "C" int64_t cov_workspace_bytes(int64_t G, int64_t Ac, int64_t Ap) {
 extern "C" int cov_assign_reduce(const double* xy, const double* w, const double* var, const double* f, int64_t G,
                                  int64_t base_index, const double* seeds_c, int64_t Ac, const double* poly_xy_c,
                                  const int32_t* poly_off_c, int64_t nvert_c, const double* seeds_p, int64_t Ap,
-                                 const double* poly_xy_p, const int32_t* poly_off_p, int64_t nvert_p, double tie_tol, double* cent, double* amax_val,
+                                 const double* poly_xy_p, const int32_t* poly_off_p, int64_t nvert_p, double tie_tol, double amax_k0, double amax_rel, double* cent, double* amax_val,
                                  int64_t* amax_idx, double* lossp, uint64_t* member_c, void* work, int64_t work_bytes,
                                  void* stream) {
     if (!xy || G <= 0 || Ac < 0 || Ap < 0 || Ac + Ap == 0 || Ac > COV_MAX_CELLS || Ap > COV_MAX_CELLS) return MFGP_ERR_INVALID;
@@ -291,7 +284,7 @@ extern "C" int cov_assign_reduce(const double* xy, const double* w, const double
     a.xy = xy; a.w = w; a.var = var; a.f = f; a.G = G; a.base_index = base_index;
     a.C = {seeds_c, (int)Ac, poly_xy_c, poly_off_c};
     a.P = {seeds_p, (int)Ap, poly_xy_p, poly_off_p};
-    a.tie_tol = tie_tol; a.member_c = member_c; a.partials = static_cast<double*>(work);
+    a.tie_tol = tie_tol; a.amax_tol = TieRule{amax_k0, amax_rel > 0.0 ? amax_rel : 0.0}; a.member_c = member_c; a.partials = static_cast<double*>(work);
     const int stride = (int)(Ac * C_SLOTS + Ap * P_SLOTS);
     const size_t smem = sizeof(double) * (2 * Ac + 2 * Ap + 2 * (size_t)nvc + 2 * (size_t)nvp + (size_t)COV_WARPS * stride) +
                         sizeof(int) * (Ac + Ap + 2);
@@ -310,22 +303,23 @@ extern "C" int cov_assign_reduce(const double* xy, const double* w, const double
     else rc = launch(cov_assign_reduce_kernel<4>);
     if (rc) return rc;
     const int nfin = (int)(Ac * 5 + Ap * 2);
-    cov_finalize_kernel<<<(nfin + 127) / 128, 128, 0, st>>>(a.partials, nblocks, (int)Ac, (int)Ap, cent, amax_val, amax_idx, lossp);
+    cov_finalize_kernel<<<(nfin + 127) / 128, 128, 0, st>>>(a.partials, nblocks, (int)Ac, (int)Ap, a.amax_tol, cent, amax_val, amax_idx, lossp);
     MFGP_LAUNCH_CHECK();
     return MFGP_OK;
 }
 
-extern "C" int cov_argmax(const double* v, int64_t G, int64_t base_index, double* out_val, int64_t* out_idx, void* work,
-                          int64_t work_bytes, void* stream) {
+extern "C" int cov_argmax(const double* v, int64_t G, int64_t base_index, double k0, double rel, double* out_val,
+                          int64_t* out_idx, void* work, int64_t work_bytes, void* stream) {
+    const TieRule tol{k0, rel > 0.0 ? rel : 0.0};
     if (!v || G <= 0 || !out_val || !out_idx || !work) return MFGP_ERR_INVALID;
     const int nblocks = cov_blocks(G);
     if (work_bytes < (int64_t)nblocks * 16) return MFGP_ERR_INVALID;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     double* pv = static_cast<double*>(work);
     long long* pi = reinterpret_cast<long long*>(pv + nblocks);
-    argmax_partial_kernel<<<nblocks, 256, 0, st>>>(v, G, base_index, pv, pi);
+    argmax_partial_kernel<<<nblocks, 256, 0, st>>>(v, G, base_index, tol, pv, pi);
     MFGP_LAUNCH_CHECK();
-    argmax_final_kernel<<<1, 32, 0, st>>>(pv, pi, nblocks, out_val, out_idx);
+    argmax_final_kernel<<<1, 32, 0, st>>>(pv, pi, nblocks, tol, out_val, out_idx);
     MFGP_LAUNCH_CHECK();
     return MFGP_OK;
 }

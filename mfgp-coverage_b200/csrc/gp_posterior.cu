@@ -52,7 +52,7 @@ struct PostArgs {
     const double* Tt; int NL, NH;
     int npad;
     const double* z;
-    double* mu; double* var;
+    double* mu; double* var; double* qout;   // qout (optional): sum of v^2, the variance reduction
     double* Vc; int64_t ldv;
     DevParams p;
 };
@@ -348,16 +348,19 @@ posterior_kernel(const __grid_constant__ CUtensorMap wmap, PostArgs a) {
                 }
                 a.var[g] = p.k0 - s;
                 a.mu[g] = p.mean_H + d;
+                if (a.qout) a.qout[g] = s;
             }
         }
     }
 }
 
-__global__ void posterior_prior_kernel(int64_t G, double mean, double k0, double* __restrict__ mu, double* __restrict__ var) {
+__global__ void posterior_prior_kernel(int64_t G, double mean, double k0, double* __restrict__ mu, double* __restrict__ var,
+                                       double* __restrict__ q) {
     const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (g < G) {
         mu[g] = mean;
         var[g] = k0;
+        if (q) q[g] = 0.0;
     }
 }
 
@@ -426,7 +429,7 @@ static int posterior_common(PostArgs& a, bool grid, const double* W, int64_t npa
     a.p = dp;
     const int64_t N = (int64_t)a.NL + a.NH;
     if (N == 0) {   // empty model: constant mean and prior variance (gaussian_process.py:139-146 with no data)
-        posterior_prior_kernel<<<(unsigned)((a.G + 255) / 256), 256, 0, st>>>(a.G, dp.mean_H, dp.k0, a.mu, a.var);
+        posterior_prior_kernel<<<(unsigned)((a.G + 255) / 256), 256, 0, st>>>(a.G, dp.mean_H, dp.k0, a.mu, a.var, a.qout);
         MFGP_LAUNCH_CHECK();
         return MFGP_OK;
     }
@@ -452,12 +455,12 @@ static int posterior_common(PostArgs& a, bool grid, const double* W, int64_t npa
 
 extern "C" int mfgp_posterior(const double* Xs, int64_t G, const double* Tt, int64_t NL, int64_t NH, const double* W,
                               int64_t npad, int64_t ldw, const double* z, const mfgp_params* p_host, double* mu,
-                              double* var, double* Vc, int64_t ldv, void* stream) {
+                              double* var, double* qred, double* Vc, int64_t ldv, void* stream) {
     if (!p_host || !mu || !var || G < 0 || NL < 0 || NH < 0) return MFGP_ERR_INVALID;
     if (G == 0) return MFGP_OK;
     if (!Xs || (NL + NH > 0 && !Tt)) return MFGP_ERR_INVALID;
     PostArgs a{};
-    a.Xs = Xs; a.G = G; a.Tt = Tt; a.NL = (int)NL; a.NH = (int)NH; a.z = z; a.mu = mu; a.var = var; a.Vc = Vc; a.ldv = ldv;
+    a.Xs = Xs; a.G = G; a.Tt = Tt; a.NL = (int)NL; a.NH = (int)NH; a.z = z; a.mu = mu; a.var = var; a.qout = qred; a.Vc = Vc; a.ldv = ldv;
     return posterior_common(a, false, W, npad, ldw, p_host, static_cast<cudaStream_t>(stream));
 }
 
@@ -480,12 +483,12 @@ extern "C" int mfgp_grid_tables(const double* ux, int64_t nx, const double* uy, 
 extern "C" int mfgp_posterior_grid(int64_t ny, int64_t g_lo, int64_t G, const double* TLx, const double* TLy,
                                    const double* THx, const double* THy, int64_t ldt, int64_t NL, int64_t NH,
                                    const double* W, int64_t npad, int64_t ldw, const double* z, const mfgp_params* p_host,
-                                   double* mu, double* var, double* Vc, int64_t ldv, void* stream) {
+                                   double* mu, double* var, double* qred, double* Vc, int64_t ldv, void* stream) {
     if (!p_host || !mu || !var || G < 0 || NL < 0 || NH < 0 || ny <= 0 || g_lo < 0) return MFGP_ERR_INVALID;
     if (G == 0) return MFGP_OK;
     if (NL + NH > 0 && (!TLx || !TLy || !THx || !THy || ldt < npad)) return MFGP_ERR_INVALID;
     PostArgs a{};
     a.G = G; a.TLx = TLx; a.TLy = TLy; a.THx = THx; a.THy = THy; a.ldt = ldt; a.g_lo = g_lo; a.ny = (int)ny;
-    a.NL = (int)NL; a.NH = (int)NH; a.z = z; a.mu = mu; a.var = var; a.Vc = Vc; a.ldv = ldv;
+    a.NL = (int)NL; a.NH = (int)NH; a.z = z; a.mu = mu; a.var = var; a.qout = qred; a.Vc = Vc; a.ldv = ldv;
     return posterior_common(a, true, W, npad, ldw, p_host, static_cast<cudaStream_t>(stream));
 }

@@ -76,14 +76,14 @@ class _GPBase:
         host = torch.from_numpy(xs)
         return host.to(self._dev.device, non_blocking=False)
 
-    def predict_device(self, xs_dev, mu_out=None, var_out=None, vcache=None, grid=None):
+    def predict_device(self, xs_dev, mu_out=None, var_out=None, vcache=None, grid=None, q_out=None):
         """Posterior on device-resident points; returns device tensors (mu[G], var[G]).  `grid`: the CoverageGrid the
         points belong to -- if it is (a slice of) a tensor-product grid the separable-kernel path is used."""
         if not self._dev.fitted:
             self._refit(check=True)
         axes = getattr(grid, "axes", None) if (grid is not None and self.use_separable) else None
         g_lo = grid.base_index if axes is not None else 0
-        return self._dev.posterior(xs_dev, mu_out, var_out, vcache, axes=axes, g_lo=g_lo)
+        return self._dev.posterior(xs_dev, mu_out, var_out, vcache, axes=axes, g_lo=g_lo, q_out=q_out)
 
     def predict(self, X_star):
         """Posterior mean [G,1] and variance [G] at X_star[G,2] (host arrays in, host arrays out)."""

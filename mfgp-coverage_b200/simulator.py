@@ -175,7 +175,8 @@ def compute_sample_points(model, x_star, threshold, console=False, return_indice
     chunk = 128
     cap = n + chunk
     Vc = torch.empty((cap, G), dtype=torch.float64, device=dev)
-    _, var = model.predict_device(grid.xy, vcache=Vc if n else None, grid=grid)
+    q = torch.empty(G, dtype=torch.float64, device=dev)
+    _, var = model.predict_device(grid.xy, vcache=Vc if n else None, grid=grid, q_out=q)
     lib = cv.nat.lib()
     work = torch.empty(int(lib.cov_workspace_bytes(G, 1, 0)) // 8 + (G // 256 + 2) * 2 + 64, dtype=torch.float64,
                        device=dev)
@@ -184,8 +185,9 @@ def compute_sample_points(model, x_star, threshold, console=False, return_indice
     while True:
         room = cap - n
         buf = (ctypes.c_int64 * room)()
-        k = lib.choi_greedy(cv.nat.ptr(grid.xy), G, cv.nat.ptr(Vc), G, n, cap, cv.nat.ptr(var),
-                            ctypes.byref(eng.pstruct), ctypes.c_double(float(threshold)), room, buf,
+        k = lib.choi_greedy(cv.nat.ptr(grid.xy), G, cv.nat.ptr(Vc), G, n, cap, cv.nat.ptr(var), cv.nat.ptr(q),
+                            ctypes.byref(eng.pstruct), ctypes.c_double(float(threshold)),
+                            ctypes.c_double(cv.AMAX_REL), room, buf,
                             cv.nat.ptr(work), work.numel() * 8, cv.nat.stream_ptr())
         if k < 0:
             cv.nat.check(int(k), "choi_greedy")
@@ -284,7 +286,8 @@ class _Sim:
         lloyd_vor = voronoi_bounded(centroids_t, bb)
         if model is not None:
             model.predict_device(self.grid.xy, self.mu, self.var, grid=self.grid)
-            res = self.grid.assign_reduce(lloyd_vor, loss_vor, w=self.mu, var=self.var)
+            res = self.grid.assign_reduce(lloyd_vor, loss_vor, w=self.mu, var=self.var,
+                                          amax_k0=prior_variance(model.params()), amax_rel=cv.AMAX_REL)
         else:
             res = self.grid.assign_reduce(lloyd_vor, loss_vor, w=weights)
         loss_t = cv.loss_from_partials(res["lossp"].cpu().numpy(), loss_vor.areas())
@@ -418,7 +421,7 @@ def _explore_exploit(kind, title, sim_num, iterations, agents, positions, truth,
     sim = _Sim(truth)
     truth_arr = sim.truth_arr
     model.predict_device(sim.grid.xy, sim.mu, sim.var, grid=sim.grid)
-    max_var_t = float(sim.grid.argmax(sim.var)[0].item()) * np.ones((agents, 1))
+    max_var_t = float(sim.grid.argmax(sim.var)[0].item()) * np.ones((agents, 1))     # value only: ties irrelevant
     prob_explore_t = todescato_prob(max_var_t, max_var_0) if kind == "todescato" else np.zeros((agents, 1))
     explore_t = np.zeros((agents, 1))
     prev_positions = np.copy(positions)
