@@ -98,13 +98,22 @@ def polygon_partition(seeds, polygons):
 
 
 class _DevPartition:
+    """Seeds, polygon vertices and polygon offsets of one partition on the device (ONE packed upload)."""
+
     def __init__(self, vor, device):
         seeds, poly, off = vor.flat()
         self.A = int(seeds.shape[0])
         self.nvert = int(off[-1])
-        self.seeds = torch.from_numpy(seeds).to(device)
-        self.poly = torch.from_numpy(poly if poly.size else np.zeros((1, 2))).to(device)
-        self.off = torch.from_numpy(off).to(device)
+        nb_s, nb_p = self.A * 16, max(self.nvert, 1) * 16
+        host = np.zeros(nb_s + nb_p + (self.A + 2) // 2 * 8, dtype=np.uint8)
+        host[:nb_s] = seeds.reshape(-1).view(np.uint8)
+        if self.nvert:
+            host[nb_s:nb_s + self.nvert * 16] = poly.reshape(-1).view(np.uint8)
+        host[nb_s + nb_p:nb_s + nb_p + (self.A + 1) * 4] = off.view(np.uint8)
+        buf = torch.from_numpy(host).to(device)
+        self.seeds = buf[:nb_s].view(torch.float64)
+        self.poly = buf[nb_s:nb_s + nb_p].view(torch.float64)
+        self.off = buf[nb_s + nb_p:].view(torch.int32)
 
 
 class CoverageGrid:
@@ -135,26 +144,42 @@ class CoverageGrid:
             self._work = torch.empty(need // 8 + 8, dtype=torch.float64, device=self.device)
         return self._work
 
+    def upload(self, vor):
+        """Device copy of a partition (BoundedVoronoi / polygon_partition); pass the result to assign_reduce to reuse it."""
+        if vor is None or isinstance(vor, _DevPartition):
+            return vor
+        if not len(vor):
+            return None
+        d = _DevPartition(vor, self.device)
+        d.seeds_inside = bool(vor.seeds_inside)
+        return d
+
     def assign_reduce(self, lloyd_vor=None, loss_vor=None, w=None, var=None, want_members=False, tie_tol=None,
-                      amax_k0=0.0, amax_rel=0.0):
+                      amax_k0=0.0, amax_rel=0.0, out=None):
         """One fused pass.  Returns a dict of DEVICE tensors: cent[Ac,4], amax_val[Ac], amax_idx[Ac], lossp[Ap,2],
-        members[G,words] (optional)."""
+        members[G,words] (optional).  `out`: a dict returned by an earlier call with the same cell counts, reused."""
         dev = self.device
-        C = _DevPartition(lloyd_vor, dev) if lloyd_vor is not None and len(lloyd_vor) else None
-        P = _DevPartition(loss_vor, dev) if loss_vor is not None and len(loss_vor) else None
+        C = self.upload(lloyd_vor)
+        P = self.upload(loss_vor)
         Ac = C.A if C else 0
         Ap = P.A if P else 0
         if tie_tol is None:
             tie_tol = TIE_TOL
-            for v in (lloyd_vor, loss_vor):
+            for v in (C, P):
                 if v is not None and not v.seeds_inside:
                     tie_tol = math.inf      # polygons are not plain nearest-seed cells: crossings test everywhere
         f64 = dict(dtype=torch.float64, device=dev)
-        out = {}
-        cent = torch.empty((Ac, 4), **f64) if Ac else None
-        amax_val = torch.empty(Ac, **f64) if Ac else None
-        amax_idx = torch.empty(Ac, dtype=torch.int64, device=dev) if Ac else None
-        lossp = torch.empty((Ap, 2), **f64) if Ap else None
+        reuse = out is not None and not want_members and \
+            (out["cent"].shape[0] if out.get("cent") is not None else 0) == Ac and \
+            (out["lossp"].shape[0] if out.get("lossp") is not None else 0) == Ap
+        if reuse:
+            cent, amax_val, amax_idx, lossp = out["cent"], out["amax_val"], out["amax_idx"], out["lossp"]
+        else:
+            out = {}
+            cent = torch.empty((Ac, 4), **f64) if Ac else None
+            amax_val = torch.empty(Ac, **f64) if Ac else None
+            amax_idx = torch.empty(Ac, dtype=torch.int64, device=dev) if Ac else None
+            lossp = torch.empty((Ap, 2), **f64) if Ap else None
         words = (max(Ac, Ap) + 63) // 64
         words = 1 if words <= 1 else (2 if words == 2 else 4)
         members = torch.zeros((self.G, words), dtype=torch.int64, device=dev) if (want_members and Ac) else None

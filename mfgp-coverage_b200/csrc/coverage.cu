@@ -12,6 +12,7 @@
 // Reductions are deterministic: a fixed butterfly inside the warp per distinct cell, per-warp shared-memory slots,
 // per-block partials in global memory, and a second kernel that adds the block partials in block order.
 #include <cfloat>
+#include <climits>
 
 #include "common.cuh"
 #include "argmax.cuh"
@@ -36,6 +37,9 @@ struct CovArgs {
     TieRule amax_tol;     // tie rule of the per-cell arg-max (see argmax_combine)
     uint64_t* member_c;
     double* partials;     // [nblocks][C.A*C_SLOTS + P.A*P_SLOTS]
+    const uint4* buckets_c; const uint4* buckets_p;   // candidate tables (cov_build_buckets_kernel)
+    const double* geom_c; const double* geom_p;       // {x0, y0, 1/h} of each table
+    int nb_c, nb_p;
 };
 
 // matplotlib _path.h point_in_path_impl, radius 0, no codes (implicitly closed polygon): SURVEY.md Appendix A.1
@@ -63,39 +67,244 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
-// membership words of one point in one partition
+constexpr int CELL_NONE = -1, CELL_TIE = -2;
+constexpr int CA_THREADS = 128, CA_WARPS = CA_THREADS / 32, CA_BLOCKS_PER_SM = 6;   // assignment kernel CTA shape
+constexpr int BK_MAX = 15;            // candidate ids per bucket entry (16 bytes: count + 15 ids)
+constexpr unsigned BK_OVERFLOW = 255; // count byte: scan all seeds
+
+// ---- candidate buckets -------------------------------------------------------------------------------------------------
+// A coarse nb x nb bucket grid over the bounding box of the cell polygons; entry (ix, iy) lists every seed that can be
+// the nearest one -- or within tie_tol of the nearest -- for ANY point of the bucket's box.  For a point p in the box
+// best(p) <= M := min_c maxdist2(c, box), and a seed with dist2(p, c) <= best(p) + tie_tol has
+// mindist2(c, box) <= M + tie_tol; boxes are inflated and the threshold carries relative slack, so the list is a superset
+// and the per-point best / runner-up / gap decisions are IDENTICAL to a brute-force scan over all seeds.  Border buckets
+// are unbounded outwards (points outside the polygons' box) and, like buckets with more than 15 candidates, are marked
+// "scan all seeds".
+struct BucketGrid {
+    const uint4* table; int nb; double x0, y0, inv_h;   // bucket (ix, iy) = floor((p - origin) * inv_h), clamped
+};
+
+__global__ void __launch_bounds__(128) cov_build_buckets_kernel(const double* __restrict__ seeds, int A,
+                                                                const double* __restrict__ poly_xy, int nvert, int nb,
+                                                                double tie_tol, uint4* __restrict__ table,
+                                                                double* __restrict__ geom /* x0, y0, inv_h */) {
+    extern __shared__ __align__(16) double bsm[];      // [2*A] seeds + [4*4] bbox partials
+    double* s_seeds = bsm;
+    double* s_box = bsm + 2 * A;
+    const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
+    for (int i = tid; i < 2 * A; i += 128) s_seeds[i] = seeds[i];
+    // bounding box of the polygon vertices (every CTA recomputes it: nvert is a few hundred)
+    double x0 = DBL_MAX, x1 = -DBL_MAX, y0 = DBL_MAX, y1 = -DBL_MAX;
+    for (int i = tid; i < nvert; i += 128) {
+        const double2 v = reinterpret_cast<const double2*>(poly_xy)[i];
+        x0 = fmin(x0, v.x); x1 = fmax(x1, v.x); y0 = fmin(y0, v.y); y1 = fmax(y1, v.y);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        x0 = fmin(x0, __shfl_xor_sync(0xffffffffu, x0, o)); x1 = fmax(x1, __shfl_xor_sync(0xffffffffu, x1, o));
+        y0 = fmin(y0, __shfl_xor_sync(0xffffffffu, y0, o)); y1 = fmax(y1, __shfl_xor_sync(0xffffffffu, y1, o));
+    }
+    if (lane == 0) { s_box[wib * 4] = x0; s_box[wib * 4 + 1] = x1; s_box[wib * 4 + 2] = y0; s_box[wib * 4 + 3] = y1; }
+    __syncthreads();
+#pragma unroll
+    for (int w = 0; w < 4; w++) {
+        x0 = fmin(x0, s_box[w * 4]); x1 = fmax(x1, s_box[w * 4 + 1]);
+        y0 = fmin(y0, s_box[w * 4 + 2]); y1 = fmax(y1, s_box[w * 4 + 3]);
+    }
+    const double h = fmax(x1 - x0, y1 - y0) / nb;
+    const int bucket = blockIdx.x * 128 + tid;
+    if (bucket == 0) { geom[0] = x0; geom[1] = y0; geom[2] = 1.0 / h; }
+    if (bucket >= nb * nb) return;
+    const int ix = bucket % nb, iy = bucket / nb;
+    unsigned e[4] = {BK_OVERFLOW, 0u, 0u, 0u};
+    const bool border = ix == 0 || iy == 0 || ix == nb - 1 || iy == nb - 1;
+    if (!border && tie_tol < 1e300) {
+        const double pad = 1e-6 * h;
+        const double bx0 = x0 + ix * h - pad, bx1 = x0 + (ix + 1) * h + pad;
+        const double by0 = y0 + iy * h - pad, by1 = y0 + (iy + 1) * h + pad;
+        double M = DBL_MAX;
+        for (int c = 0; c < A; c++) {
+            const double sx = s_seeds[2 * c], sy = s_seeds[2 * c + 1];
+            const double dxm = fmax(sx - bx0, bx1 - sx), dym = fmax(sy - by0, by1 - sy);
+            M = fmin(M, dxm * dxm + dym * dym);
+        }
+        const double T = M * (1.0 + 1e-9) + tie_tol + 1e-300;
+        unsigned w0 = 0, w1 = 0, w2 = 0, w3 = 0;
+        int count = 0;
+        for (int c = 0; c < A; c++) {      // ascending seed order, as the brute-force scan
+            const double sx = s_seeds[2 * c], sy = s_seeds[2 * c + 1];
+            const double dxn = fmax(fmax(bx0 - sx, sx - bx1), 0.0), dyn = fmax(fmax(by0 - sy, sy - by1), 0.0);
+            if (dxn * dxn + dyn * dyn <= T) {
+                const int k = count + 1;                   // byte position in the 16-byte entry
+                const unsigned v = (unsigned)c << (8 * (k & 3));
+                if (k < 4) w0 |= v; else if (k < 8) w1 |= v; else if (k < 12) w2 |= v; else if (k < 16) w3 |= v;
+                count++;
+            }
+        }
+        if (count <= BK_MAX) { e[0] = w0 | (unsigned)count; e[1] = w1; e[2] = w2; e[3] = w3; }
+    }
+    table[bucket] = make_uint4(e[0], e[1], e[2], e[3]);
+}
+
+// nearest-seed cell of one point: CELL_TIE when the runner-up is within tie_tol (the crossings test decides later)
+__device__ __forceinline__ int classify_point(const BucketGrid& bg, const double* __restrict__ s_seeds, int A, double x,
+                                              double y, double tie_tol) {
+    int ix = (int)((x - bg.x0) * bg.inv_h), iy = (int)((y - bg.y0) * bg.inv_h);
+    ix = min(max(ix, 0), bg.nb - 1);
+    iy = min(max(iy, 0), bg.nb - 1);
+    const uint4 e = __ldg(bg.table + iy * bg.nb + ix);
+    const unsigned cnt = e.x & 0xffu;
+    if (cnt == 1) return (e.x >> 8) & 0xffu;       // the bucket lies inside one cell (margin > tie_tol): no distances needed
+    double best = DBL_MAX, second = DBL_MAX;
+    int bi = CELL_NONE;
+    if (cnt != BK_OVERFLOW) {
+        for (unsigned k = 1; k <= cnt; k++) {
+            const unsigned wsel = (k >> 2) == 0 ? e.x : ((k >> 2) == 1 ? e.y : ((k >> 2) == 2 ? e.z : e.w));
+            const int c = (wsel >> (8 * (k & 3))) & 0xffu;
+            const double dx = x - s_seeds[2 * c], dy = y - s_seeds[2 * c + 1];
+            const double d = fma(dx, dx, dy * dy);
+            if (d < best) { second = best; best = d; bi = c; }
+            else if (d < second) second = d;
+        }
+    } else {
+        for (int c = 0; c < A; c++) {
+            const double dx = x - s_seeds[2 * c], dy = y - s_seeds[2 * c + 1];
+            const double d = fma(dx, dx, dy * dy);
+            if (d < best) { second = best; best = d; bi = c; }
+            else if (d < second) second = d;
+        }
+    }
+    return (second - best > tie_tol) ? bi : CELL_TIE;
+}
+
+// membership words of one point (test / in_polygon output): the nearest cell, or the crossings test for tie points
 template <int WORDS>
-__device__ __forceinline__ void point_membership(const CovPartition& part, const double* __restrict__ s_seeds,
-                                                 const double* __restrict__ s_poly, const int* __restrict__ s_off,
-                                                 double x, double y, double tie_tol, uint64_t (&m)[WORDS]) {
+__device__ __noinline__ void write_members(uint64_t* __restrict__ dst, int cell, const double* __restrict__ s_poly,
+                                           const int* __restrict__ s_off, int A, double x, double y) {
+    uint64_t m[WORDS];
 #pragma unroll
     for (int k = 0; k < WORDS; k++) m[k] = 0;
-    double best = DBL_MAX, second = DBL_MAX;
-    int bi = -1;
-    for (int c = 0; c < part.A; c++) {
-        const double dx = x - s_seeds[2 * c], dy = y - s_seeds[2 * c + 1];
-        const double d = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
-        if (d < best) { second = best; best = d; bi = c; }
-        else if (d < second) second = d;
-    }
-    if (second - best > tie_tol) {
+    if (cell >= 0) {
 #pragma unroll
         for (int k = 0; k < WORDS; k++)
-            if ((bi >> 6) == k) m[k] = 1ull << (bi & 63);
+            if ((cell >> 6) == k) m[k] = 1ull << (cell & 63);
     } else {
-        for (int c = 0; c < part.A; c++) {
-            const int o = s_off[c], n = s_off[c + 1] - o;
-            if (crossings_inside(s_poly + 2 * o, n, x, y)) {
+        for (int c = 0; c < A; c++)
+            if (crossings_inside(s_poly + 2 * s_off[c], s_off[c + 1] - s_off[c], x, y)) {
 #pragma unroll
                 for (int k = 0; k < WORDS; k++)
                     if ((c >> 6) == k) m[k] |= 1ull << (c & 63);
             }
+    }
+#pragma unroll
+    for (int k = 0; k < WORDS; k++) dst[k] = m[k];
+}
+
+// Warp-level tie-aware arg-max of one (value, index) pair per lane (index < 0: lane has no entry): the exact maximum
+// by butterfly, then the LOWEST index among the lanes within the tie band of that maximum (TieRule, argmax.cuh).
+__device__ __forceinline__ ArgMax argmax_warp_band(ArgMax x, TieRule t) {
+    double vmax = x.i >= 0 ? x.v : -DBL_MAX;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) vmax = fmax(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+    const double tol = t.rel > 0.0 ? fmax(t.rel * (t.k0 - vmax), 0.0) : 0.0;
+    long long idx = (x.i >= 0 && vmax - x.v <= tol) ? x.i : LLONG_MAX;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const long long other = __shfl_xor_sync(0xffffffffu, idx, o);
+        idx = other < idx ? other : idx;
+    }
+    return ArgMax{vmax, idx == LLONG_MAX ? -1LL : idx};
+}
+
+__device__ __forceinline__ void slot_add_c(double* __restrict__ slot, double s0, double s1, double s2, int cnt, ArgMax am,
+                                           bool with_var, TieRule tol) {
+    slot[0] += s0; slot[1] += s1; slot[2] += s2; slot[3] += (double)cnt;
+    if (with_var) {
+        long long* islot = reinterpret_cast<long long*>(slot);
+        const ArgMax r = argmax_combine(ArgMax{slot[4], islot[5]}, am, tol);
+        slot[4] = r.v; islot[5] = r.i;
+    }
+}
+
+// the lane-local running sums of the cell a warp has been inside -> the warp's slot of that cell
+__device__ __noinline__ void flush_c(double s0, double s1, double s2, int cnt, double amv, long long ami, double* __restrict__ slot,
+                                     bool with_var, TieRule tol, int lane) {
+    s0 = warp_sum(s0); s1 = warp_sum(s1); s2 = warp_sum(s2);
+    cnt = __reduce_add_sync(0xffffffffu, cnt);
+    ArgMax am{amv, ami};
+    if (with_var) am = argmax_warp_band(am, tol);
+    if (lane == 0) slot_add_c(slot, s0, s1, s2, cnt, am, with_var, tol);
+}
+__device__ __noinline__ void flush_p(double s0, int cnt, double* __restrict__ slot, int lane) {
+    s0 = warp_sum(s0);
+    cnt = __reduce_add_sync(0xffffffffu, cnt);
+    if (lane == 0) { slot[0] += s0; slot[1] += (double)cnt; }
+}
+
+// Row straddles a cell border (or holds tie points): one fixed butterfly per distinct cell, straight into the slots.
+// Tie points (within tie_tol of a bisector): the reference's crossings test against EVERY cell polygon decides --
+// 0, 1 or several cells.
+__device__ __noinline__ void mixed_c(int A, bool with_var, TieRule tol, const double* __restrict__ s_poly,
+                                     const int* __restrict__ s_off, double* __restrict__ wacc, int cell, double x, double y,
+                                     double wv, double vv, long long gidx, int lane) {
+    unsigned pending = __ballot_sync(0xffffffffu, cell >= 0);
+    while (pending) {
+        const int c = __shfl_sync(0xffffffffu, cell, __ffs(pending) - 1);
+        const bool mine = cell == c;
+        const unsigned who = __ballot_sync(0xffffffffu, mine);
+        const double s0 = warp_sum(mine ? wv : 0.0), s1 = warp_sum(mine ? wv * x : 0.0), s2 = warp_sum(mine ? wv * y : 0.0);
+        ArgMax am{vv, mine ? gidx : -1LL};
+        if (with_var) am = argmax_warp_band(am, tol);
+        if (lane == 0) slot_add_c(wacc + c * C_SLOTS, s0, s1, s2, __popc(who), am, with_var, tol);
+        pending &= ~who;
+    }
+    if (__any_sync(0xffffffffu, cell == CELL_TIE)) {
+        for (int c = 0; c < A; c++) {
+            const bool mine = cell == CELL_TIE && crossings_inside(s_poly + 2 * s_off[c], s_off[c + 1] - s_off[c], x, y);
+            const unsigned who = __ballot_sync(0xffffffffu, mine);
+            if (!who) continue;
+            const double s0 = warp_sum(mine ? wv : 0.0), s1 = warp_sum(mine ? wv * x : 0.0), s2 = warp_sum(mine ? wv * y : 0.0);
+            ArgMax am{vv, mine ? gidx : -1LL};
+            if (with_var) am = argmax_warp_band(am, tol);
+            if (lane == 0) slot_add_c(wacc + c * C_SLOTS, s0, s1, s2, __popc(who), am, with_var, tol);
+        }
+    }
+}
+__device__ __noinline__ void mixed_p(int A, const double* __restrict__ s_seeds, const double* __restrict__ s_poly,
+                                     const int* __restrict__ s_off, double* __restrict__ wacc_p, int cell, double x, double y,
+                                     double fv, int lane) {
+    unsigned pending = __ballot_sync(0xffffffffu, cell >= 0);
+    while (pending) {
+        const int c = __shfl_sync(0xffffffffu, cell, __ffs(pending) - 1);
+        const bool mine = cell == c;
+        const unsigned who = __ballot_sync(0xffffffffu, mine);
+        const double dx = x - s_seeds[2 * c], dy = y - s_seeds[2 * c + 1];
+        const double pl = __dmul_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), fv);     // simulator.py:215-216
+        const double s0 = warp_sum(mine ? pl : 0.0);
+        if (lane == 0) { wacc_p[c * P_SLOTS] += s0; wacc_p[c * P_SLOTS + 1] += (double)__popc(who); }
+        pending &= ~who;
+    }
+    if (__any_sync(0xffffffffu, cell == CELL_TIE)) {
+        for (int c = 0; c < A; c++) {
+            const bool mine = cell == CELL_TIE && crossings_inside(s_poly + 2 * s_off[c], s_off[c + 1] - s_off[c], x, y);
+            const unsigned who = __ballot_sync(0xffffffffu, mine);
+            if (!who) continue;
+            const double dx = x - s_seeds[2 * c], dy = y - s_seeds[2 * c + 1];
+            const double pl = __dmul_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), fv);
+            const double s0 = warp_sum(mine ? pl : 0.0);
+            if (lane == 0) { wacc_p[c * P_SLOTS] += s0; wacc_p[c * P_SLOTS + 1] += (double)__popc(who); }
         }
     }
 }
 
+// Each warp owns a contiguous range of 32-point rows (lane = point: coalesced 40 B/point streams, the next row's
+// loads in flight while the current one is processed).  Per row and partition: bucket lookup -> a handful of candidate
+// seeds -> nearest / runner-up cell.  While the whole warp stays inside ONE cell (the common case: consecutive grid
+// points) every lane just adds into its own registers; the warp reduces only when it moves to another cell.  Rows
+// that straddle a border or hold tie points take the butterfly-per-cell path.  Deterministic: fixed point -> lane ->
+// warp -> block order.
 template <int WORDS>
-__global__ void __launch_bounds__(COV_THREADS) cov_assign_reduce_kernel(CovArgs a) {
+__global__ void __launch_bounds__(CA_THREADS, CA_BLOCKS_PER_SM) cov_assign_reduce_kernel(CovArgs a) {
     extern __shared__ __align__(16) double sm[];
     const int Ac = a.C.A, Ap = a.P.A;
     const int nvc = Ac ? a.C.poly_off[Ac] : 0, nvp = Ap ? a.P.poly_off[Ap] : 0;
@@ -103,157 +312,191 @@ __global__ void __launch_bounds__(COV_THREADS) cov_assign_reduce_kernel(CovArgs 
     double* s_seed_p = s_seed_c + 2 * Ac;        // [Ap*2]
     double* s_poly_c = s_seed_p + 2 * Ap;        // [nvc*2]
     double* s_poly_p = s_poly_c + 2 * nvc;       // [nvp*2]
-    double* s_acc = s_poly_p + 2 * nvp;          // [COV_WARPS][Ac*C_SLOTS + Ap*P_SLOTS]
+    double* s_acc = s_poly_p + 2 * nvp;          // [CA_WARPS][Ac*C_SLOTS + Ap*P_SLOTS]
     const int stride = Ac * C_SLOTS + Ap * P_SLOTS;
-    int* s_off_c = reinterpret_cast<int*>(s_acc + COV_WARPS * stride);   // [Ac+1]
+    int* s_off_c = reinterpret_cast<int*>(s_acc + CA_WARPS * stride);   // [Ac+1]
     int* s_off_p = s_off_c + (Ac + 1);                                    // [Ap+1]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int i = tid; i < 2 * Ac; i += COV_THREADS) s_seed_c[i] = a.C.seeds[i];
-    for (int i = tid; i < 2 * Ap; i += COV_THREADS) s_seed_p[i] = a.P.seeds[i];
-    for (int i = tid; i < 2 * nvc; i += COV_THREADS) s_poly_c[i] = a.C.poly_xy[i];
-    for (int i = tid; i < 2 * nvp; i += COV_THREADS) s_poly_p[i] = a.P.poly_xy[i];
-    for (int i = tid; i <= Ac && Ac; i += COV_THREADS) s_off_c[i] = a.C.poly_off[i];
-    for (int i = tid; i <= Ap && Ap; i += COV_THREADS) s_off_p[i] = a.P.poly_off[i];
-    for (int i = tid; i < COV_WARPS * stride; i += COV_THREADS) s_acc[i] = 0.0;
+    for (int i = tid; i < 2 * Ac; i += CA_THREADS) s_seed_c[i] = a.C.seeds[i];
+    for (int i = tid; i < 2 * Ap; i += CA_THREADS) s_seed_p[i] = a.P.seeds[i];
+    for (int i = tid; i < 2 * nvc; i += CA_THREADS) s_poly_c[i] = a.C.poly_xy[i];
+    for (int i = tid; i < 2 * nvp; i += CA_THREADS) s_poly_p[i] = a.P.poly_xy[i];
+    for (int i = tid; i <= Ac && Ac; i += CA_THREADS) s_off_c[i] = a.C.poly_off[i];
+    for (int i = tid; i <= Ap && Ap; i += CA_THREADS) s_off_p[i] = a.P.poly_off[i];
+    for (int i = tid; i < CA_WARPS * stride; i += CA_THREADS) s_acc[i] = 0.0;
     __syncthreads();
     double* wacc = s_acc + warp * stride;
-    if (lane == 0)
-        for (int c = 0; c < Ac; c++) {
-            wacc[c * C_SLOTS + 4] = -DBL_MAX;
-            reinterpret_cast<long long*>(wacc)[c * C_SLOTS + 5] = -1;
-        }
+    for (int c = lane; c < Ac; c += 32) {
+        wacc[c * C_SLOTS + 4] = -DBL_MAX;
+        reinterpret_cast<long long*>(wacc)[c * C_SLOTS + 5] = -1;
+    }
     __syncwarp();
+    const bool polygon_mode = !(a.tie_tol < 1e300);    // arbitrary polygons: the crossings test decides everywhere
+    const bool with_var = a.var != nullptr;
+    BucketGrid bgc{a.buckets_c, a.nb_c, 0.0, 0.0, 0.0}, bgp{a.buckets_p, a.nb_p, 0.0, 0.0, 0.0};
+    if (Ac) { bgc.x0 = a.geom_c[0]; bgc.y0 = a.geom_c[1]; bgc.inv_h = a.geom_c[2]; }
+    if (Ap) { bgp.x0 = a.geom_p[0]; bgp.y0 = a.geom_p[1]; bgp.inv_h = a.geom_p[2]; }
 
-    for (int64_t base = (int64_t)blockIdx.x * COV_THREADS; base < a.G; base += (int64_t)gridDim.x * COV_THREADS) {
-        const int64_t g = base + tid;
-        const bool valid = g < a.G;
-        double x = 0, y = 0, wv = 0, vv = 0, fv = 0;
-        if (valid) {
-            const double2 p = reinterpret_cast<const double2*>(a.xy)[g];
-            x = p.x; y = p.y;
-            if (a.w) wv = a.w[g];
-            if (a.var) vv = a.var[g];
-            if (a.f) fv = a.f[g];
+    // contiguous split of the 32-point rows over all warps of the grid
+    const int64_t nrows = (a.G + 31) / 32;
+    const int64_t nwarps = (int64_t)gridDim.x * CA_WARPS, gw = (int64_t)blockIdx.x * CA_WARPS + warp;
+    const int64_t r0 = gw * nrows / nwarps, r1 = (gw + 1) * nrows / nwarps;
+
+    double c_s0 = 0.0, c_s1 = 0.0, c_s2 = 0.0, p_s0 = 0.0;      // lane-local sums of the current cell (C / P partition)
+    int c_cnt = 0, p_cnt = 0;
+    ArgMax c_am{0.0, -1};
+    double c_tol = 0.0;       // tie band of c_am (TieRule) -- refreshed when the index moves
+    int cur_c = CELL_NONE, cur_p = CELL_NONE;
+    const TieRule tol = a.amax_tol;
+    const double tie_tol = a.tie_tol;
+    const int64_t base_index = a.base_index;
+
+    double2 nxy = make_double2(0.0, 0.0);
+    double nw = 0.0, nv = 0.0, nf = 0.0;
+    auto fetch = [&](int64_t row) {
+        const int64_t g = row * 32 + lane;
+        if (row < r1 && g < a.G) {
+            nxy = __ldg(reinterpret_cast<const double2*>(a.xy) + g);
+            if (a.w) nw = __ldg(a.w + g);
+            if (with_var) nv = __ldg(a.var + g);
+            if (a.f) nf = __ldg(a.f + g);
         }
+    };
+    fetch(r0);
+#pragma unroll 1
+    for (int64_t row = r0; row < r1; row++) {
+        const int64_t g = row * 32 + lane;
+        const bool valid = g < a.G;
+        const double x = nxy.x, y = nxy.y, wv = nw, vv = nv, fv = nf;
+        fetch(row + 1);
         if (Ac) {
-            uint64_t m[WORDS];
-            point_membership<WORDS>(a.C, s_seed_c, s_poly_c, s_off_c, x, y, a.tie_tol, m);
-            if (!valid) {
-#pragma unroll
-                for (int k = 0; k < WORDS; k++) m[k] = 0;
-            }
-            if (a.member_c && valid) {
-#pragma unroll
-                for (int k = 0; k < WORDS; k++) a.member_c[g * WORDS + k] = m[k];
-            }
-            const double wx = wv * x, wy = wv * y;
-#pragma unroll
-            for (int k = 0; k < WORDS; k++) {
-                unsigned pending;
-                while ((pending = __ballot_sync(0xffffffffu, m[k] != 0)) != 0) {
-                    const int leader = __ffs(pending) - 1;
-                    const uint64_t lm = __shfl_sync(0xffffffffu, m[k], leader);
-                    const int bit = __ffsll((long long)lm) - 1;
-                    const bool mine = (m[k] >> bit) & 1ull;
-                    const int c = k * 64 + bit;
-                    const double s0 = warp_sum(mine ? wv : 0.0);
-                    const double s1 = warp_sum(mine ? wx : 0.0);
-                    const double s2 = warp_sum(mine ? wy : 0.0);
-                    const int cnt = __popc(__ballot_sync(0xffffffffu, mine));
-                    const ArgMax am = argmax_warp(ArgMax{vv, mine ? (long long)(a.base_index + g) : -1LL}, a.amax_tol);
-                    if (lane == 0) {
-                        double* slot = wacc + c * C_SLOTS;
-                        slot[0] += s0; slot[1] += s1; slot[2] += s2; slot[3] += (double)cnt;
-                        long long* islot = reinterpret_cast<long long*>(slot);
-                        if (a.var) {
-                            const ArgMax r = argmax_combine(ArgMax{slot[4], islot[5]}, am, a.amax_tol);
-                            slot[4] = r.v; islot[5] = r.i;
+            const int cell = !valid ? CELL_NONE : (polygon_mode ? CELL_TIE : classify_point(bgc, s_seed_c, Ac, x, y, tie_tol));
+            if (a.member_c && valid) write_members<WORDS>(a.member_c + g * WORDS, cell, s_poly_c, s_off_c, Ac, x, y);
+            const int c0 = __shfl_sync(0xffffffffu, cell, 0);       // lane 0 is valid whenever the row holds any point
+            if (c0 >= 0 && __all_sync(0xffffffffu, cell == c0 || cell == CELL_NONE)) {
+                if (c0 != cur_c) {
+                    if (cur_c >= 0) flush_c(c_s0, c_s1, c_s2, c_cnt, c_am.v, c_am.i, wacc + cur_c * C_SLOTS, with_var, tol, lane);
+                    c_s0 = c_s1 = c_s2 = 0.0; c_cnt = 0; c_am = ArgMax{0.0, -1};
+                    cur_c = c0;
+                }
+                if (cell == c0) {
+                    c_s0 += wv; c_s1 += wv * x; c_s2 += wv * y; c_cnt++;
+                    if (with_var) {      // == argmax_combine(c_am, {vv, idx}) for an index above c_am.i, a few instructions
+                        if (c_am.i < 0 || vv - c_am.v > c_tol) {
+                            c_am = ArgMax{vv, (long long)(base_index + g)};
+                            c_tol = tol.rel > 0.0 ? fmax(tol.rel * (tol.k0 - vv), 0.0) : 0.0;
+                        } else if (vv > c_am.v) {
+                            c_am.v = vv;
                         }
                     }
-                    m[k] &= ~(1ull << bit);
                 }
+            } else {
+                mixed_c(Ac, with_var, tol, s_poly_c, s_off_c, wacc, cell, x, y, wv, vv, (long long)(base_index + g), lane);
             }
         }
         if (Ap) {
-            uint64_t m[WORDS];
-            point_membership<WORDS>(a.P, s_seed_p, s_poly_p, s_off_p, x, y, a.tie_tol, m);
-            if (!valid) {
-#pragma unroll
-                for (int k = 0; k < WORDS; k++) m[k] = 0;
-            }
-#pragma unroll
-            for (int k = 0; k < WORDS; k++) {
-                unsigned pending;
-                while ((pending = __ballot_sync(0xffffffffu, m[k] != 0)) != 0) {
-                    const int leader = __ffs(pending) - 1;
-                    const uint64_t lm = __shfl_sync(0xffffffffu, m[k], leader);
-                    const int bit = __ffsll((long long)lm) - 1;
-                    const bool mine = (m[k] >> bit) & 1ull;
-                    const int c = k * 64 + bit;
-                    // simulator.py:215-216: (dx^2 + dy^2) * f
-                    const double dx = x - s_seed_p[2 * c], dy = y - s_seed_p[2 * c + 1];
-                    const double pl = __dmul_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), fv);
-                    const double s0 = warp_sum(mine ? pl : 0.0);
-                    const int cnt = __popc(__ballot_sync(0xffffffffu, mine));
-                    if (lane == 0) {
-                        double* slot = wacc + Ac * C_SLOTS + c * P_SLOTS;
-                        slot[0] += s0; slot[1] += (double)cnt;
-                    }
-                    m[k] &= ~(1ull << bit);
+            const int cell = !valid ? CELL_NONE : (polygon_mode ? CELL_TIE : classify_point(bgp, s_seed_p, Ap, x, y, tie_tol));
+            const int c0 = __shfl_sync(0xffffffffu, cell, 0);
+            if (c0 >= 0 && __all_sync(0xffffffffu, cell == c0 || cell == CELL_NONE)) {
+                if (c0 != cur_p) {
+                    if (cur_p >= 0) flush_p(p_s0, p_cnt, wacc + Ac * C_SLOTS + cur_p * P_SLOTS, lane);
+                    p_s0 = 0.0; p_cnt = 0;
+                    cur_p = c0;
                 }
+                if (cell == c0) {
+                    const double dx = x - s_seed_p[2 * c0], dy = y - s_seed_p[2 * c0 + 1];
+                    p_s0 += __dmul_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), fv);     // simulator.py:215-216
+                    p_cnt++;
+                }
+            } else {
+                mixed_p(Ap, s_seed_p, s_poly_p, s_off_p, wacc + Ac * C_SLOTS, cell, x, y, fv, lane);
             }
         }
     }
+    if (cur_c >= 0) flush_c(c_s0, c_s1, c_s2, c_cnt, c_am.v, c_am.i, wacc + cur_c * C_SLOTS, with_var, tol, lane);
+    if (cur_p >= 0) flush_p(p_s0, p_cnt, wacc + Ac * C_SLOTS + cur_p * P_SLOTS, lane);
     __syncthreads();
     // block partial = warp slots combined in warp order
-    double* out = a.partials + (int64_t)blockIdx.x * stride;
-    for (int i = tid; i < Ac * C_SLOTS; i += COV_THREADS) {
+    // partials are laid out [slot][block] so the finalize kernel reads them coalesced
+    double* out = a.partials + blockIdx.x;
+    const int64_t pld = gridDim.x;
+    for (int i = tid; i < Ac * C_SLOTS; i += CA_THREADS) {
         const int slot = i % C_SLOTS;
         if (slot < 4) {
             double s = 0.0;
-            for (int w = 0; w < COV_WARPS; w++) s += s_acc[w * stride + i];
-            out[i] = s;
+            for (int w = 0; w < CA_WARPS; w++) s += s_acc[w * stride + i];
+            out[i * pld] = s;
         } else if (slot == 4) {
             ArgMax best{0.0, -1};
-            for (int w = 0; w < COV_WARPS; w++)
+            for (int w = 0; w < CA_WARPS; w++)
                 best = argmax_combine(best, ArgMax{s_acc[w * stride + i], reinterpret_cast<const long long*>(s_acc)[w * stride + i + 1]},
                                       a.amax_tol);
-            out[i] = best.v;
-            reinterpret_cast<long long*>(out)[i + 1] = best.i;
+            out[i * pld] = best.v;
+            reinterpret_cast<long long*>(out)[(i + 1) * pld] = best.i;
         }
     }
-    for (int i = tid; i < Ap * P_SLOTS; i += COV_THREADS) {
+    for (int i = tid; i < Ap * P_SLOTS; i += CA_THREADS) {
         double s = 0.0;
-        for (int w = 0; w < COV_WARPS; w++) s += s_acc[w * stride + Ac * C_SLOTS + i];
-        out[Ac * C_SLOTS + i] = s;
+        for (int w = 0; w < CA_WARPS; w++) s += s_acc[w * stride + Ac * C_SLOTS + i];
+        out[(Ac * C_SLOTS + i) * pld] = s;
     }
 }
 
-__global__ void cov_finalize_kernel(const double* __restrict__ partials, int nblocks, int Ac, int Ap, TieRule amax_tol, double* __restrict__ cent,
-                                    double* __restrict__ amax_val, int64_t* __restrict__ amax_idx, double* __restrict__ lossp) {
-    const int stride = Ac * C_SLOTS + Ap * P_SLOTS;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+// One warp per output: lanes stride over the block partials in block order, then a fixed butterfly.
+__global__ void __launch_bounds__(256) cov_finalize_kernel(const double* __restrict__ partials, int nblocks, int Ac, int Ap,
+                                                           TieRule amax_tol, double* __restrict__ cent, double* __restrict__ amax_val,
+                                                           int64_t* __restrict__ amax_idx, double* __restrict__ lossp) {
+    const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    const int64_t pld = nblocks;
     if (i < Ac * 4) {
         const int c = i / 4, s = i % 4;
+        const double* src = partials + (int64_t)(c * C_SLOTS + s) * pld;
         double acc = 0.0;
-        for (int b = 0; b < nblocks; b++) acc += partials[(int64_t)b * stride + c * C_SLOTS + s];
-        if (cent) cent[i] = acc;
+#pragma unroll 4
+        for (int b = lane; b < nblocks; b += 32) acc += src[b];
+        acc = warp_sum(acc);
+        if (cent && lane == 0) cent[i] = acc;
     } else if (i < Ac * 5) {
         const int c = i - Ac * 4;
+        const double* sv = partials + (int64_t)(c * C_SLOTS + 4) * pld;
+        const long long* si = reinterpret_cast<const long long*>(partials) + (int64_t)(c * C_SLOTS + 5) * pld;
         ArgMax best{0.0, -1};
-        for (int b = 0; b < nblocks; b++)
-            best = argmax_combine(best, ArgMax{partials[(int64_t)b * stride + c * C_SLOTS + 4],
-                                               reinterpret_cast<const long long*>(partials)[(int64_t)b * stride + c * C_SLOTS + 5]},
-                                  amax_tol);
-        if (amax_val) amax_val[c] = best.v;
-        if (amax_idx) amax_idx[c] = best.i;
+#pragma unroll 4
+        for (int b = lane; b < nblocks; b += 32) best = argmax_combine(best, ArgMax{sv[b], si[b]}, amax_tol);
+        best = argmax_warp(best, amax_tol);
+        if (lane == 0) {
+            if (amax_val) amax_val[c] = best.v;
+            if (amax_idx) amax_idx[c] = best.i;
+        }
     } else if (i < Ac * 5 + Ap * 2) {
         const int j = i - Ac * 5;
+        const double* src = partials + (int64_t)(Ac * C_SLOTS + j) * pld;
         double acc = 0.0;
-        for (int b = 0; b < nblocks; b++) acc += partials[(int64_t)b * stride + Ac * C_SLOTS + j];
-        if (lossp) lossp[j] = acc;
+#pragma unroll 4
+        for (int b = lane; b < nblocks; b += 32) acc += src[b];
+        acc = warp_sum(acc);
+        if (lossp && lane == 0) lossp[j] = acc;
     }
+}
+
+constexpr int COV_BUCKETS_MAX = 128;
+// bucket grid side: about eight buckets per mean cell spacing, so most buckets lie inside ONE cell
+inline int cov_bucket_side(int64_t A) {
+    int nb = 16;
+    while (nb < COV_BUCKETS_MAX && (int64_t)nb * nb < 64 * A) nb *= 2;
+    return nb;
+}
+
+// number of CTAs of the assignment kernel: every warp gets at least one whole chunk
+inline int cov_chunk_blocks(int64_t G) {
+    const int64_t nrows = (G + 31) / 32;
+    int64_t b = (nrows + 4 * CA_WARPS - 1) / (4 * CA_WARPS);     // at least ~4 rows per warp
+    const int64_t cap = 148 * CA_BLOCKS_PER_SM;      // one resident wave; warps grid-stride over the chunks
+    if (b > cap) b = cap;
+    if (b < 1) b = 1;
+    return (int)b;
 }
 
 }  // namespace mfgp
@@ -262,9 +505,10 @@ using namespace mfgp;
 
 extern "C" int64_t cov_workspace_bytes(int64_t G, int64_t Ac, int64_t Ap) {
     const int64_t stride = Ac * C_SLOTS + Ap * P_SLOTS;
-    int64_t a = (int64_t)cov_blocks(G) * stride * 8;
-    int64_t b = (int64_t)cov_blocks(G) * 16;
-    return (a > b ? a : b) + 256;
+    const int64_t nb = cov_blocks(G) > cov_chunk_blocks(G) ? cov_blocks(G) : cov_chunk_blocks(G);
+    int64_t a = nb * stride * 8;
+    int64_t b = nb * 16;
+    return (a > b ? a : b) + 256 + 2 * ((int64_t)COV_BUCKETS_MAX * COV_BUCKETS_MAX * 16 + 64);
 }
 
 extern "C" int cov_assign_reduce(const double* xy, const double* w, const double* var, const double* f, int64_t G,
@@ -286,14 +530,36 @@ extern "C" int cov_assign_reduce(const double* xy, const double* w, const double
     a.P = {seeds_p, (int)Ap, poly_xy_p, poly_off_p};
     a.tie_tol = tie_tol; a.amax_tol = TieRule{amax_k0, amax_rel > 0.0 ? amax_rel : 0.0}; a.member_c = member_c; a.partials = static_cast<double*>(work);
     const int stride = (int)(Ac * C_SLOTS + Ap * P_SLOTS);
-    const size_t smem = sizeof(double) * (2 * Ac + 2 * Ap + 2 * (size_t)nvc + 2 * (size_t)nvp + (size_t)COV_WARPS * stride) +
+    {   // candidate bucket tables live behind the block partials in the workspace
+        const int64_t nbmax = cov_blocks(G) > cov_chunk_blocks(G) ? cov_blocks(G) : cov_chunk_blocks(G);
+        const int64_t pa = nbmax * stride * 8, pb = nbmax * 16;
+        char* base = static_cast<char*>(work) + (((pa > pb ? pa : pb) + 255) / 256) * 256;
+        const int64_t tbytes = (int64_t)COV_BUCKETS_MAX * COV_BUCKETS_MAX * 16;
+        a.buckets_c = reinterpret_cast<const uint4*>(base);
+        a.geom_c = reinterpret_cast<const double*>(base + tbytes);
+        a.buckets_p = reinterpret_cast<const uint4*>(base + tbytes + 64);
+        a.geom_p = reinterpret_cast<const double*>(base + 2 * tbytes + 64);
+        a.nb_c = cov_bucket_side(Ac);
+        a.nb_p = cov_bucket_side(Ap);
+        if (Ac) {
+            cov_build_buckets_kernel<<<(a.nb_c * a.nb_c + 127) / 128, 128, (2 * Ac + 16) * sizeof(double), st>>>(seeds_c, (int)Ac, poly_xy_c, (int)nvc, a.nb_c, tie_tol,
+                                                                             const_cast<uint4*>(a.buckets_c), const_cast<double*>(a.geom_c));
+            MFGP_LAUNCH_CHECK();
+        }
+        if (Ap) {
+            cov_build_buckets_kernel<<<(a.nb_p * a.nb_p + 127) / 128, 128, (2 * Ap + 16) * sizeof(double), st>>>(seeds_p, (int)Ap, poly_xy_p, (int)nvp, a.nb_p, tie_tol,
+                                                                             const_cast<uint4*>(a.buckets_p), const_cast<double*>(a.geom_p));
+            MFGP_LAUNCH_CHECK();
+        }
+    }
+    const size_t smem = sizeof(double) * (2 * Ac + 2 * Ap + 2 * (size_t)nvc + 2 * (size_t)nvp + (size_t)CA_WARPS * stride) +
                         sizeof(int) * (Ac + Ap + 2);
     if (smem > 200 * 1024) return MFGP_ERR_INVALID;
-    const int nblocks = cov_blocks(G);
+    const int nblocks = cov_chunk_blocks(G);
     const int words = (int)((Ac > Ap ? Ac : Ap) + 63) / 64;
     auto launch = [&](auto kern) -> int {
         MFGP_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<nblocks, COV_THREADS, smem, st>>>(a);
+        kern<<<nblocks, CA_THREADS, smem, st>>>(a);
         MFGP_LAUNCH_CHECK();
         return MFGP_OK;
     };
@@ -303,7 +569,7 @@ extern "C" int cov_assign_reduce(const double* xy, const double* w, const double
     else rc = launch(cov_assign_reduce_kernel<4>);
     if (rc) return rc;
     const int nfin = (int)(Ac * 5 + Ap * 2);
-    cov_finalize_kernel<<<(nfin + 127) / 128, 128, 0, st>>>(a.partials, nblocks, (int)Ac, (int)Ap, a.amax_tol, cent, amax_val, amax_idx, lossp);
+    cov_finalize_kernel<<<(nfin + 7) / 8, 256, 0, st>>>(a.partials, nblocks, (int)Ac, (int)Ap, a.amax_tol, cent, amax_val, amax_idx, lossp);
     MFGP_LAUNCH_CHECK();
     return MFGP_OK;
 }

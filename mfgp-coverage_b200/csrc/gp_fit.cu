@@ -50,67 +50,89 @@ __global__ void build_train_cov_kernel(const double* __restrict__ Xt, int NL, in
 }
 
 // ---- 64x64 diagonal block: Cholesky + inverse in one CTA --------------------------------------------------------------
-// Shared-memory resident, 256 threads, rolled loops (a fully unrolled register version is instruction-fetch bound).
-// Factor: right-looking with ONE barrier per column and no divide / sqrt on the critical path -- column j is left
-// UNSCALED (u = L sqrt(p_j)), every thread takes r = rsqrt(p_j), the trailing update is a[i][c] -= u_i u_c r^2, and
-// L = u r is applied to all columns in one pass at the end (r_j is also 1 / L[j][j], so the inverse needs no divide).
+// 256 threads as a 16x16 grid; thread (ti, tc) keeps the 4x4 cyclic sub-block S[ti+16a][tc+16b] in REGISTERS.
+// Factor: right-looking, ONE barrier per column and no divide / sqrt on the critical path -- column j is left
+// UNSCALED (u = L sqrt(p_j)); its owners publish it to a double-buffered shared column, every thread takes
+// r = rsqrt(p_j) and applies a[i][c] -= u_i u_c r^2 to its 16 registers; L = u r is applied once at the end (r_j is also
+// 1 / L[j][j], so the inverse needs no divide).  The j loop is 4 (unrolled: static register index) x 16 (rolled).
 // Inverse: block doubling inside the CTA, X21 = -X22 (L21 X11) for block sizes 8 -> 16 -> 32, all pairs of a level in
 // parallel, the product L21 X11 parked in the (finally zero) upper-right block of X.
 constexpr int PB = 64;
 constexpr int PLD = PB + 1;
 
-__global__ void __launch_bounds__(256) potrf_diag_kernel(double* __restrict__ A, int64_t ld, double* __restrict__ Winv,
+__global__ void __launch_bounds__(256, 1) potrf_diag_kernel(double* __restrict__ A, int64_t ld, double* __restrict__ Winv,
                                                          int64_t ldw, int32_t* __restrict__ info, int jblk) {
     extern __shared__ __align__(16) double potrf_smem[];   // 2 x 64x65 doubles: above the 48 KB static limit
     double* S = potrf_smem;
     double* X = potrf_smem + PB * PLD;
     __shared__ double rs[PB];        // 1/sqrt(pivot) == 1/L[j][j]
+    __shared__ double colbuf[2][PB];
     __shared__ int bad;
     const int tid = threadIdx.x;
-    const int ti = tid >> 4, tc = tid & 15;      // 16 x 16 thread grid for the trailing update
+    const int ti = tid >> 4, tc = tid & 15;
     if (tid == 0) bad = 0;
-    for (int e = tid; e < PB * PB; e += 256) {
-        const int r = e >> 6, c = e & 63;
-        S[r * PLD + c] = (c <= r) ? A[(int64_t)r * ld + c] : 0.0;
-        X[r * PLD + c] = 0.0;
-    }
-    for (int j = 0; j < PB; j++) {
-        __syncthreads();
-        double piv = S[j * PLD + j];
-        if (!(piv > 0.0)) {     // uniform: np.linalg.cholesky raises here (gaussian_process.py:254 / :529)
-            if (tid == 0 && !bad) {
-                bad = 1;
-                atomicCAS(info, 0, jblk * PB + j + 1);
+    double s[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; a++)
+#pragma unroll
+        for (int b = 0; b < 4; b++) {
+            const int r = ti + 16 * a, c = tc + 16 * b;
+            s[a][b] = (c <= r) ? A[(int64_t)r * ld + c] : 0.0;
+        }
+    for (int e = tid; e < PB * PB; e += 256) X[(e >> 6) * PLD + (e & 63)] = 0.0;
+    __syncthreads();
+#pragma unroll
+    for (int jb = 0; jb < 4; jb++) {
+#pragma unroll 1
+        for (int jj = 0; jj < 16; jj++) {
+            const int j = jb * 16 + jj;
+            double* col = colbuf[j & 1];
+            if (tc == jj) {          // owners of column j publish it (rows above j are never read)
+#pragma unroll
+                for (int a = 0; a < 4; a++) col[ti + 16 * a] = s[a][jb];
             }
-            piv = 1.0;
-        }
-        const double r = rsqrt(piv);
-        const double ip = r * r;
-        if (tid == 0) rs[j] = r;
-        // trailing update over rows i > j, columns j < c <= i (16x16 threads tile the block)
-        for (int i = j + 1 + ti; i < PB; i += 16) {
-            const double f = S[i * PLD + j] * ip;
-            for (int c = j + 1 + tc; c <= i; c += 16) S[i * PLD + c] = fma(-f, S[c * PLD + j], S[i * PLD + c]);
+            __syncthreads();
+            double piv = col[j];
+            if (!(piv > 0.0)) {     // uniform: np.linalg.cholesky raises here (gaussian_process.py:254 / :529)
+                if (tid == 0 && !bad) {
+                    bad = 1;
+                    atomicCAS(info, 0, jblk * PB + j + 1);
+                }
+                piv = 1.0;
+            }
+            const double r = rsqrt(piv);
+            const double ip = r * r;
+            if (tid == 0) rs[j] = r;
+            double ui[4], uc[4];
+#pragma unroll
+            for (int a = 0; a < 4; a++) ui[a] = col[ti + 16 * a] * ip;
+#pragma unroll
+            for (int b = 0; b < 4; b++) uc[b] = col[tc + 16 * b];
+#pragma unroll
+            for (int b = 0; b < 4; b++) {
+                if (b < jb) continue;                       // columns of earlier 16-groups are final
+                const bool live = tc + 16 * b > j;          // only columns right of j change
+#pragma unroll
+                for (int a = 0; a < 4; a++)
+                    if (live) s[a][b] = fma(-ui[a], uc[b], s[a][b]);
+            }
         }
     }
     __syncthreads();
-    if (bad) {   // leave a harmless identity so later kernels stay finite; the host raises on `info`
-        for (int e = tid; e < PB * PB; e += 256) {
-            const int r = e >> 6, c = e & 63;
-            S[r * PLD + c] = (r == c) ? 1.0 : 0.0;
+    const bool failed = bad != 0;
+#pragma unroll
+    for (int a = 0; a < 4; a++)
+#pragma unroll
+        for (int b = 0; b < 4; b++) {
+            const int r = ti + 16 * a, c = tc + 16 * b;
+            // on failure leave a harmless identity so later kernels stay finite; the host raises on `info`
+            const double v = failed ? ((r == c) ? 1.0 : 0.0) : ((c <= r) ? s[a][b] * rs[c] : 0.0);
+            S[r * PLD + c] = v;
+            if (c <= r) A[(int64_t)r * ld + c] = v;
         }
-        if (tid < PB) rs[tid] = 1.0;
-    } else {
-        for (int e = tid; e < PB * PB; e += 256) {
-            const int r = e >> 6, c = e & 63;
-            if (c <= r) S[r * PLD + c] *= rs[c];
-        }
-    }
     __syncthreads();
-    for (int e = tid; e < PB * PB; e += 256) {
-        const int r = e >> 6, c = e & 63;
-        if (c <= r) A[(int64_t)r * ld + c] = S[r * PLD + c];
-    }
+    if (failed && tid < PB) rs[tid] = 1.0;
+    __syncthreads();
     if (Winv == nullptr) return;
     // level 0: the eight 8x8 diagonal blocks, one warp each, lane c < 8 solves column c by forward substitution
     {
