@@ -73,6 +73,17 @@ int mfgp_tri_inverse(const double* L, int64_t npad, int64_t ld, double* W, int64
 int mfgp_whiten(const double* W, int64_t npad, int64_t ldw, const double* y, int64_t NL, int64_t NH,
                 const mfgp_params* p_host, double* z, void* stream);
 
+/* Bordered (append-only) factor update: replaces the refit inside SFGP.updt gaussian_process.py:257-268 and
+ * MFGP.updt_hifi :531-542 when samples were only APPENDED.  The reference appends new points at the END of [X_L; X_H]
+ * and refactors from scratch (:266-268, :540-542); the leading block of L is unchanged, so only the 64-row blocks that
+ * hold rows [NL+NH_old, NL+NH_new) of L, W = L^-1 and z are recomputed (left-looking, split-K DMMA tile products).
+ * Xt / y must already hold all NL+NH_new points; K, W, Tt, z must be the buffers of the standing factorisation, with
+ * leading dimensions >= mfgp_npad(NL+NH_new).  `work`: mfgp_append_workspace_bytes(npad) bytes. */
+int mfgp_cholesky_append(const double* Xt, int64_t NL, int64_t NH_old, int64_t NH_new, const mfgp_params* p_host,
+                         double* K, int64_t ld, double* W, int64_t ldw, const double* y, double* z, double* Tt,
+                         int32_t* info, void* work, int64_t work_bytes, void* stream);
+int64_t mfgp_append_workspace_bytes(int64_t npad);
+
 /* ---- GP posterior: replaces SFGP.predict gaussian_process.py:121-148 and MFGP.predict :401-438 ------------------ */
 
 /* mu[G] = mean_H + psi^T K^-1 (y-m), var[G] = k(0) - |W psi|^2 for the G points Xs[G,2].  Fused: psi tiles are
@@ -96,6 +107,18 @@ int mfgp_posterior_grid(int64_t ny, int64_t g_lo, int64_t G, const double* TLx, 
                         const double* THy, int64_t ldt, int64_t NL, int64_t NH, const double* W, int64_t npad,
                         int64_t ldw, const double* z, const mfgp_params* p_host, double* mu, double* var, double* qred,
                         double* Vc, int64_t ldv, void* stream);
+
+/* Incremental posterior after mfgp_cholesky_append: rows [row_lo, NL+NH) of V = W psi are new since mu / var / qred
+ * were last computed; only their contributions are formed and ADDED (mu += v_new . z_new, var -= |v_new|^2,
+ * qred += |v_new|^2).  Equal to a from-scratch mfgp_posterior up to rounding (~1e-13 k(0)); cost ~ G (N - row_lo) N
+ * instead of G N^2 / 2.  0 < row_lo < NL+NH. */
+int mfgp_posterior_update(const double* Xs, int64_t G, const double* Tt, int64_t NL, int64_t NH,
+                          const double* W, int64_t npad, int64_t ldw, const double* z, const mfgp_params* p_host,
+                          int64_t row_lo, double* mu, double* var, double* qred, double* Vc, int64_t ldv, void* stream);
+int mfgp_posterior_grid_update(int64_t ny, int64_t g_lo, int64_t G, const double* TLx, const double* TLy,
+                               const double* THx, const double* THy, int64_t ldt, int64_t NL, int64_t NH, const double* W,
+                               int64_t npad, int64_t ldw, const double* z, const mfgp_params* p_host, int64_t row_lo,
+                               double* mu, double* var, double* qred, double* Vc, int64_t ldv, void* stream);
 
 /* ---- coverage step: replaces simulator.py in_polygon :105-124, compute_loss :194-228, compute_centroids :231-283,
  *      compute_max_var :286-323, compute_sample_clusters :377-412 ------------------------------------------------ */

@@ -58,24 +58,38 @@ class DeviceGP:
         self.params = None
         self.pstruct = None
         self.fitted = False
-        self.fit_id = 0               # bumped by every refactor: grid tables are rebuilt lazily when stale
+        self.fit_id = 0               # bumped by every refactor / append: grid tables are rebuilt lazily when stale
         self._tab = None              # (axes key, fit_id, TLx, TLy, THx, THy, ldt)
+        # incremental mode: appended samples border the standing factor instead of a from-scratch
+        # refit, and a posterior that was computed into the same (mu, var) buffers is updated with the new rows only
+        self.incremental = False
+        self.epoch = 0                # bumped by every FULL refactor: standing posteriors become stale
+        self._post = None             # (buffer key, epoch, N covered)
 
     # -- memory -------------------------------------------------------------------------------------------------------
-    def _reserve(self, n):
+    def _reserve(self, n, keep_factor=False):
         need = nat.npad(n)
         if need <= self.cap:
             return
         cap = max(need, nat.npad(int(self.cap * 1.5)))
         f64 = dict(dtype=torch.float64, device=self.device)
+        old = (self.K, self.W, self.Tt, self.z, self.npad) if (keep_factor and self.K is not None) else None
         self.K = torch.empty((cap, cap), **f64)
         self.W = torch.empty((cap, cap), **f64)
         self.Tt = torch.empty((cap, 4), **f64)
         self.z = torch.empty(cap, **f64)
         self.Xt = torch.empty((cap, 2), **f64)
         self.y = torch.empty(cap, **f64)
-        self.work = torch.empty(int(nat.lib().mfgp_workspace_bytes(cap)) // 8 + 8, **f64)
+        lib = nat.lib()
+        self.work = torch.empty(max(int(lib.mfgp_workspace_bytes(cap)), int(lib.mfgp_append_workspace_bytes(cap))) // 8 + 8,
+                                **f64)
         self.cap = cap
+        if old is not None:           # the standing factorisation moves into the larger buffers
+            K0, W0, T0, z0, n0 = old
+            self.K[:n0, :n0].copy_(K0[:n0, :n0])
+            self.W[:n0, :n0].copy_(W0[:n0, :n0])
+            self.Tt[:n0].copy_(T0[:n0])
+            self.z[:n0].copy_(z0[:n0])
 
     @property
     def N(self):
@@ -122,6 +136,19 @@ class DeviceGP:
         nat.check(lib.mfgp_whiten(nat.ptr(self.W), npad, ld, nat.ptr(self.y), self.NL, self.NH, pp, nat.ptr(self.z),
                                   st), "mfgp_whiten")
         self.fit_id += 1
+        self.epoch += 1
+        if check:
+            self.check_factor()
+
+    def _append_factor(self, NH_old, check=True):
+        """Bordered update of L, W, z for the rows appended since NH_old (mfgp_cholesky_append)."""
+        lib = nat.lib()
+        self.npad = nat.npad(self.N)
+        nat.check(lib.mfgp_cholesky_append(nat.ptr(self.Xt), self.NL, int(NH_old), self.NH, ctypes.byref(self.pstruct),
+                                           nat.ptr(self.K), self.cap, nat.ptr(self.W), self.cap, nat.ptr(self.y),
+                                           nat.ptr(self.z), nat.ptr(self.Tt), nat.ptr(self.info), nat.ptr(self.work),
+                                           self.work.numel() * 8, nat.stream_ptr()), "mfgp_cholesky_append")
+        self.fit_id += 1
         if check:
             self.check_factor()
 
@@ -154,18 +181,25 @@ class DeviceGP:
         """updt / updt_hifi (gaussian_process.py:257-268, :531-542): new points go to the END of [X_L; X_H]; the factor
         is rebuilt from scratch, as in the reference (which does so even when nothing was added)."""
         k = 0 if X_new_host is None else int(np.asarray(X_new_host).reshape(-1, 2).shape[0])
+        border = self.incremental and self.fitted and self.N > 0 and self.npad == nat.npad(self.N)
+        NH_old = self.NH
         if k:
             N = self.N
             if N + k > self.cap:
                 old_x, old_y = self.Xt, self.y
-                self._reserve(N + k)
+                self._reserve(N + k, keep_factor=border)
                 if N:
                     self.Xt[:N].copy_(old_x[:N])
                     self.y[:N].copy_(old_y[:N])
             self.Xt[N:N + k].copy_(torch.from_numpy(np.ascontiguousarray(X_new_host, dtype=np.float64).reshape(k, 2)))
             self.y[N:N + k].copy_(torch.from_numpy(np.ascontiguousarray(y_new_host, dtype=np.float64).reshape(k)))
             self.NH += k
-        if self.N:
+        if not self.N:
+            return
+        if border:
+            if k:
+                self._append_factor(NH_old, check=check)      # nothing appended: the standing factor is still exact
+        else:
             self.refactor(check=check)
 
     # -- posterior ----------------------------------------------------------------------------------------------------
@@ -180,6 +214,32 @@ class DeviceGP:
         var = torch.empty(G, **f64) if var_out is None else var_out
         lib = nat.lib()
         ldv = 0 if vcache is None else int(vcache.shape[1])
+        # incremental mode: the caller's (mu, var) buffers still hold the posterior of the first `covered` rows of the
+        # standing factorisation -> add the appended rows only
+        key = (mu.data_ptr(), var.data_ptr(), xs_dev.data_ptr(), G, 0 if q_out is None else q_out.data_ptr(), int(g_lo))
+        row_lo = 0
+        eligible = self.incremental and vcache is None and mu_out is not None and var_out is not None
+        if eligible:
+            if self._post is not None and self._post[0] == key and self._post[1] == self.epoch \
+                    and 0 < self._post[2] <= self.N:
+                row_lo = self._post[2]
+            self._post = (key, self.epoch, self.N) if self.N > 0 else None
+        if row_lo == self.N and row_lo > 0:
+            return mu, var                       # nothing was appended since the standing posterior was computed
+        if row_lo > 0:
+            if axes is not None:
+                TLx, TLy, THx, THy, ldt, _ = self.grid_tables(axes)
+                nat.check(lib.mfgp_posterior_grid_update(axes.ny, int(g_lo), G, nat.ptr(TLx), nat.ptr(TLy), nat.ptr(THx),
+                                                         nat.ptr(THy), ldt, self.NL, self.NH, nat.ptr(self.W), self.npad,
+                                                         self.cap, nat.ptr(self.z), ctypes.byref(self.pstruct), row_lo,
+                                                         nat.ptr(mu), nat.ptr(var), nat.ptr(q_out), None, 0,
+                                                         nat.stream_ptr()), "mfgp_posterior_grid_update")
+            else:
+                nat.check(lib.mfgp_posterior_update(nat.ptr(xs_dev), G, nat.ptr(self.Tt), self.NL, self.NH, nat.ptr(self.W),
+                                                    self.npad, self.cap, nat.ptr(self.z), ctypes.byref(self.pstruct),
+                                                    row_lo, nat.ptr(mu), nat.ptr(var), nat.ptr(q_out), None, 0,
+                                                    nat.stream_ptr()), "mfgp_posterior_update")
+            return mu, var
         if axes is not None and self.N > 0:
             TLx, TLy, THx, THy, ldt, _ = self.grid_tables(axes)
             nat.check(lib.mfgp_posterior_grid(axes.ny, int(g_lo), G, nat.ptr(TLx), nat.ptr(TLy), nat.ptr(THx),
@@ -205,4 +265,6 @@ class DeviceGP:
             setattr(other, name, None if t is None else t.clone())
         other.info = self.info.clone()
         other.fit_id = self.fit_id
+        other.incremental = self.incremental
+        other.epoch = self.epoch
         return other

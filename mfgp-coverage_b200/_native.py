@@ -44,6 +44,16 @@ SIGNATURES = {
     "mfgp_posterior_grid": (c_int, [c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64,
                                     c_int64, c_void_p, c_int64, c_int64, c_void_p, POINTER(MfgpParams), c_void_p,
                                     c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+    "mfgp_cholesky_append": (c_int, [c_void_p, c_int64, c_int64, c_int64, POINTER(MfgpParams), c_void_p, c_int64,
+                                     c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
+                                     c_void_p]),
+    "mfgp_append_workspace_bytes": (c_int64, [c_int64]),
+    "mfgp_posterior_update": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64,
+                                      c_void_p, POINTER(MfgpParams), c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
+                                      c_int64, c_void_p]),
+    "mfgp_posterior_grid_update": (c_int, [c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
+                                           c_int64, c_int64, c_void_p, c_int64, c_int64, c_void_p, POINTER(MfgpParams),
+                                           c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "cov_assign_reduce": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64,
                                   c_void_p, c_int64, c_void_p, c_void_p, c_int64,
                                   c_void_p, c_int64, c_void_p, c_void_p, c_int64,

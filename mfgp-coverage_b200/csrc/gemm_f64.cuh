@@ -11,7 +11,8 @@ enum GemmMode : int {
     GEMM_GENERAL = 0,
     GEMM_SYRK_LOWER = 1,   // only C tiles with row-tile >= col-tile are computed (B must be A, B_TRANS)
     GEMM_A_LOWER = 2,      // A[M,K=M] lower triangular: k < m0 + 64
-    GEMM_B_LOWER = 3       // B[K=N,N] (not transposed) lower triangular: k >= n0
+    GEMM_B_LOWER = 3,      // B[K=N,N] (not transposed) lower triangular: k >= n0
+    GEMM_BT_LOWER = 4      // B[N,K=N] (transposed operand) lower triangular: k < n0 + 64
 };
 
 struct GemmArgs {
@@ -21,6 +22,8 @@ struct GemmArgs {
     int M, N, K;
     double alpha, beta;
     int mode;
+    int kchunk;            // > 0: split-K -- blockIdx.z selects the k range [z*kchunk, (z+1)*kchunk) (A, B not strided),
+                           //      partial products go to C + z*strideC; reduce with splitk_reduce_kernel
 };
 
 constexpr int GT = 64;        // C tile
@@ -32,8 +35,9 @@ template <bool B_TRANS>
 __global__ void __launch_bounds__(128) gemm_f64_kernel(GemmArgs g) {
     const int m0 = blockIdx.y * GT, n0 = blockIdx.x * GT;
     if (g.mode == GEMM_SYRK_LOWER && n0 > m0) return;
-    const double* A = g.A + (int64_t)blockIdx.z * g.strideA;
-    const double* B = g.B + (int64_t)blockIdx.z * g.strideB;
+    const bool splitk = g.kchunk > 0;
+    const double* A = g.A + (splitk ? 0 : (int64_t)blockIdx.z * g.strideA);
+    const double* B = g.B + (splitk ? 0 : (int64_t)blockIdx.z * g.strideB);
     double* C = g.C + (int64_t)blockIdx.z * g.strideC;
 
     __shared__ __align__(16) double As[2][GT * GLD];
@@ -46,6 +50,11 @@ __global__ void __launch_bounds__(128) gemm_f64_kernel(GemmArgs g) {
     int kbeg = 0, kend = g.K;
     if (g.mode == GEMM_A_LOWER) kend = min(g.K, m0 + GT);
     if (g.mode == GEMM_B_LOWER) kbeg = n0;
+    if (g.mode == GEMM_BT_LOWER) kend = min(g.K, n0 + GT);
+    if (splitk) {
+        kbeg = max(kbeg, (int)blockIdx.z * g.kchunk);
+        kend = min(kend, ((int)blockIdx.z + 1) * g.kchunk);
+    }
 
     double acc[4][4][2];
 #pragma unroll
@@ -121,6 +130,17 @@ __global__ void __launch_bounds__(128) gemm_f64_kernel(GemmArgs g) {
             *p = out;
         }
     }
+}
+
+// out[r][c] = beta * out[r][c] + alpha * sum_z part[z][r][c]  (z in fixed order: deterministic)
+static __global__ void splitk_reduce_kernel(const double* __restrict__ part, int nsplit, int64_t stride, int ldp, double* __restrict__ out,
+                                            int64_t ldo, int rows, int cols, double alpha, double beta) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y;
+    if (c >= cols || r >= rows) return;
+    double s = 0.0;
+    for (int z = 0; z < nsplit; z++) s += part[(int64_t)z * stride + (int64_t)r * ldp + c];
+    double* o = out + (int64_t)r * ldo + c;
+    *o = (beta != 0.0 ? beta * *o : 0.0) + alpha * s;
 }
 
 inline int launch_gemm(const GemmArgs& g, bool b_trans, int batch, cudaStream_t st) {

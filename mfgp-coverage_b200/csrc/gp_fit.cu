@@ -9,9 +9,9 @@ namespace mfgp {
 // K_LL = k_L + noise_L I, K_LH = rho k_L, K_HH = rho^2 k_L + k_H + noise_H I, then + jitter I (gaussian_process.py:
 // 523-529); SF: k + noise I + jitter I (:253-254).  Padding rows/cols [N, npad) carry the identity.
 __global__ void build_train_cov_kernel(const double* __restrict__ Xt, int NL, int NH, DevParams p, double* __restrict__ K,
-                                       int npad, int64_t ld, double* __restrict__ Tt) {
+                                       int npad, int64_t ld, double* __restrict__ Tt, int row_begin) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    const int i = blockIdx.y * blockDim.y + threadIdx.y;
+    const int i = row_begin + blockIdx.y * blockDim.y + threadIdx.y;
     const int N = NL + NH;
     if (i >= npad || j >= npad) return;
     double v;
@@ -183,10 +183,12 @@ __global__ void zero_offdiag_blocks_kernel(double* __restrict__ W, int npad, int
     if ((i >> 6) != (j >> 6)) W[(int64_t)i * ldw + j] = 0.0;
 }
 
+__global__ void zero_cols_kernel(double* __restrict__ Wcol, int64_t ldw) { Wcol[(int64_t)blockIdx.y * ldw + threadIdx.x] = 0.0; }
+
 // z = W (y - mean): one warp per row; W is lower triangular so only k <= row contributes
 __global__ void whiten_kernel(const double* __restrict__ W, int npad, int64_t ldw, const double* __restrict__ y, int NL,
-                              int NH, double mean_L, double mean_H, double* __restrict__ z) {
-    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+                              int NH, double mean_L, double mean_H, double* __restrict__ z, int row_begin) {
+    const int row = row_begin + blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= npad) return;
     const int N = NL + NH;
@@ -221,7 +223,7 @@ extern "C" int mfgp_build_train_cov(const double* Xt, int64_t NL, int64_t NH, co
     if (!p_host->multi && NL != 0) return MFGP_ERR_INVALID;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     dim3 block(32, 8), grid((unsigned)((npad + 31) / 32), (unsigned)((npad + 7) / 8));
-    build_train_cov_kernel<<<grid, block, 0, st>>>(Xt, (int)NL, (int)NH, make_dev_params(*p_host), K, (int)npad, ld, Tt);
+    build_train_cov_kernel<<<grid, block, 0, st>>>(Xt, (int)NL, (int)NH, make_dev_params(*p_host), K, (int)npad, ld, Tt, 0);
     MFGP_LAUNCH_CHECK();
     return MFGP_OK;
 }
@@ -305,7 +307,103 @@ extern "C" int mfgp_whiten(const double* W, int64_t npad, int64_t ldw, const dou
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int wpb = 8;
     whiten_kernel<<<(unsigned)((npad + wpb - 1) / wpb), wpb * 32, 0, st>>>(W, (int)npad, ldw, y, (int)NL, (int)NH,
-                                                                          p_host->mean_L, p_host->mean_H, z);
+                                                                          p_host->mean_L, p_host->mean_H, z, 0);
     MFGP_LAUNCH_CHECK();
     return MFGP_OK;
 }
+
+// Bordered (append-only) update of the factor: the reference appends new samples at the END of [X_L; X_H]
+// (gaussian_process.py:266-268, :540-542) and refactors from scratch; algebraically the leading block of L is unchanged,
+// so only the block rows that hold new points are recomputed, one 64-row block at a time (left-looking):
+//   K_b   = covariance rows of the block                       (build_train_cov_kernel, rows [rb, rb+64))
+//   L_b,left = K_b[:, 0:rb] W11^T                              (W11 = inverse of the already-factored leading block)
+//   S     = K_b[:, rb:rb+64] - L_b,left L_b,left^T ;  L_bb = chol(S), W_bb = L_bb^-1      (potrf_diag_kernel)
+//   W_b,left = -W_bb (L_b,left W11)
+//   z_b   = W_b,: (y - mean)
+// The skinny products (64 rows, K up to N) are split over K so they fill the GPU; partial tiles are added in fixed order.
+extern "C" int mfgp_cholesky_append(const double* Xt, int64_t NL, int64_t NH_old, int64_t NH_new, const mfgp_params* p_host,
+                                    double* K, int64_t ld, double* W, int64_t ldw, const double* y, double* z, double* Tt,
+                                    int32_t* info, void* work, int64_t work_bytes, void* stream) {
+    if (!Xt || !p_host || !K || !W || !y || !z || !info || !work || NL < 0 || NH_old < 0 || NH_new < NH_old) return MFGP_ERR_INVALID;
+    const int64_t N_old = NL + NH_old, N_new = NL + NH_new;
+    if (N_new == N_old) return MFGP_OK;
+    const int64_t npad = mfgp_npad(N_new);
+    if (ld < npad || ldw < npad) return MFGP_ERR_INVALID;
+    if (!p_host->multi && NL != 0) return MFGP_ERR_INVALID;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const DevParams dp = make_dev_params(*p_host);
+    MFGP_CUDA_CHECK(cudaMemsetAsync(info, 0, sizeof(int32_t), st));
+    constexpr int POTRF_SMEM = 2 * PB * PLD * sizeof(double);
+    MFGP_CUDA_CHECK(cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, POTRF_SMEM));
+    double* part = static_cast<double*>(work);
+    for (int64_t rb = N_old / PB * PB; rb < npad; rb += PB) {
+        {   // covariance rows of the block: columns [0, rb+64) are used, the rest of the row is rewritten too (harmless)
+            dim3 block(32, 8), grid((unsigned)((rb + PB + 31) / 32), PB / 8);
+            build_train_cov_kernel<<<grid, block, 0, st>>>(Xt, (int)NL, (int)NH_new, dp, K, (int)(rb + PB), ld, Tt, (int)rb);
+            MFGP_LAUNCH_CHECK();
+        }
+        if (rb > 0) {     // the column block above the new diagonal block of W must read as zero (upper triangle)
+            dim3 zgrid(1, (unsigned)rb);
+            zero_cols_kernel<<<zgrid, PB, 0, st>>>(W + rb, ldw);
+            MFGP_LAUNCH_CHECK();
+        }
+        double* Kb = K + rb * ld;              // block rows of K / L
+        double* Wb = W + rb * ldw;
+        double* Kbb = Kb + rb;
+        double* Wbb = Wb + rb;
+        if (rb > 0) {
+            int nsplit = (int)(rb / 256);
+            if (nsplit < 1) nsplit = 1;
+            if (nsplit > 16) nsplit = 16;
+            int kchunk = (int)((rb / PB + nsplit - 1) / nsplit) * PB;
+            nsplit = (int)((rb + kchunk - 1) / kchunk);
+            const int64_t pstride = (int64_t)PB * rb;
+            if (work_bytes < (int64_t)nsplit * pstride * 8) return MFGP_ERR_INVALID;
+            dim3 rgrid((unsigned)((rb + 127) / 128), PB);
+            GemmArgs g1{};      // part[z] = K_b[:, 0:rb] * W11^T over the z-th k range (W11 lower: k < n0 + 64)
+            g1.A = Kb; g1.lda = ld; g1.B = W; g1.ldb = ldw; g1.C = part; g1.ldc = rb; g1.strideC = pstride;
+            g1.M = PB; g1.N = (int)rb; g1.K = (int)rb; g1.alpha = 1.0; g1.beta = 0.0; g1.mode = GEMM_BT_LOWER; g1.kchunk = kchunk;
+            int rc = launch_gemm(g1, true, nsplit, st);
+            if (rc) return rc;
+            splitk_reduce_kernel<<<rgrid, 128, 0, st>>>(part, nsplit, pstride, (int)rb, Kb, ld, PB, (int)rb, 1.0, 0.0);   // L_b,left
+            MFGP_LAUNCH_CHECK();
+            GemmArgs g2{};      // part[z] = L_b,left L_b,left^T over the z-th k range
+            g2.A = Kb; g2.lda = ld; g2.B = Kb; g2.ldb = ld; g2.C = part; g2.ldc = PB; g2.strideC = PB * PB;
+            g2.M = PB; g2.N = PB; g2.K = (int)rb; g2.alpha = 1.0; g2.beta = 0.0; g2.mode = GEMM_GENERAL; g2.kchunk = kchunk;
+            rc = launch_gemm(g2, true, nsplit, st);
+            if (rc) return rc;
+            splitk_reduce_kernel<<<dim3(1, PB), 64, 0, st>>>(part, nsplit, PB * PB, PB, Kbb, ld, PB, PB, -1.0, 1.0);        // S
+            MFGP_LAUNCH_CHECK();
+        }
+        potrf_diag_kernel<<<1, 256, POTRF_SMEM, st>>>(Kbb, ld, Wbb, ldw, info, (int)(rb / PB));
+        MFGP_LAUNCH_CHECK();
+        if (rb > 0) {
+            int nsplit = (int)(rb / 256);
+            if (nsplit < 1) nsplit = 1;
+            if (nsplit > 16) nsplit = 16;
+            int kchunk = (int)((rb / PB + nsplit - 1) / nsplit) * PB;
+            nsplit = (int)((rb + kchunk - 1) / kchunk);
+            const int64_t pstride = (int64_t)PB * rb;
+            double* T2 = part + (int64_t)nsplit * pstride;      // reduced L_b,left W11 lives behind the partials
+            if (work_bytes < ((int64_t)nsplit + 1) * pstride * 8) return MFGP_ERR_INVALID;
+            GemmArgs g3{};      // part[z] = L_b,left * W11 over the z-th k range (W11 lower: k >= n0)
+            g3.A = Kb; g3.lda = ld; g3.B = W; g3.ldb = ldw; g3.C = part; g3.ldc = rb; g3.strideC = pstride;
+            g3.M = PB; g3.N = (int)rb; g3.K = (int)rb; g3.alpha = 1.0; g3.beta = 0.0; g3.mode = GEMM_B_LOWER; g3.kchunk = kchunk;
+            int rc = launch_gemm(g3, false, nsplit, st);
+            if (rc) return rc;
+            dim3 rgrid((unsigned)((rb + 127) / 128), PB);
+            splitk_reduce_kernel<<<rgrid, 128, 0, st>>>(part, nsplit, pstride, (int)rb, T2, rb, PB, (int)rb, 1.0, 0.0);
+            MFGP_LAUNCH_CHECK();
+            GemmArgs g4{};      // W_b,left = -W_bb * T2
+            g4.A = Wbb; g4.lda = ldw; g4.B = T2; g4.ldb = rb; g4.C = Wb; g4.ldc = ldw;
+            g4.M = PB; g4.N = (int)rb; g4.K = PB; g4.alpha = -1.0; g4.beta = 0.0; g4.mode = GEMM_GENERAL;
+            rc = launch_gemm(g4, false, 1, st);
+            if (rc) return rc;
+        }
+        whiten_kernel<<<PB / 8, 256, 0, st>>>(W, (int)(rb + PB), ldw, y, (int)NL, (int)NH_new, p_host->mean_L, p_host->mean_H, z, (int)rb);
+        MFGP_LAUNCH_CHECK();
+    }
+    return MFGP_OK;
+}
+
+extern "C" int64_t mfgp_append_workspace_bytes(int64_t npad) { return (int64_t)17 * PB * npad * 8 + 256; }

@@ -54,6 +54,7 @@ struct PostArgs {
     const double* z;
     double* mu; double* var; double* qout;   // qout (optional): sum of v^2, the variance reduction
     double* Vc; int64_t ldv;
+    int row_lo;          // > 0: incremental update -- only rows >= row_lo of V are formed and ADDED to mu / var / qout
     DevParams p;
 };
 
@@ -132,6 +133,7 @@ posterior_kernel(const __grid_constant__ CUtensorMap wmap, PostArgs a) {
     __syncthreads();
 
     const int nrb = (a.npad + P_BM - 1) / P_BM;
+    const int rb_begin = a.row_lo / P_BM;      // incremental update: row blocks below the first new row are not visited
 
     if (warp >= P_CONSUMER_WARPS) {
         // =============================== PRODUCERS ===============================
@@ -152,7 +154,7 @@ posterior_kernel(const __grid_constant__ CUtensorMap wmap, PostArgs a) {
             }
         }
         int it = 0;
-        for (int rb = 0; rb < nrb; rb++) {
+        for (int rb = rb_begin; rb < nrb; rb++) {
             const int row0 = rb * P_BM;
             const int nslab = min(a.npad, row0 + P_BM) / P_BK;
             for (int s = 0; s < nslab; s++, it++) {
@@ -216,7 +218,7 @@ posterior_kernel(const __grid_constant__ CUtensorMap wmap, PostArgs a) {
 #pragma unroll
         for (int j = 0; j < 4; j++) aoff[j] = pr * 128 + ((((j * 4 + tq) >> 1) ^ pr) << 4) + ((tq & 1) << 3);
         int it = 0;
-        for (int rb = 0; rb < nrb; rb++) {
+        for (int rb = rb_begin; rb < nrb; rb++) {
             const int row0 = rb * P_BM;
             const int nslab = min(a.npad, row0 + P_BM) / P_BK;
 
@@ -231,7 +233,7 @@ posterior_kernel(const __grid_constant__ CUtensorMap wmap, PostArgs a) {
 #pragma unroll
             for (int i = 0; i < P_MI; i++) {
                 const int r = row0 + (i * P_CONSUMER_WARPS + warp) * 8;
-                klim[i] = (r < a.npad) ? r + 7 : -1;
+                klim[i] = (r < a.npad && r + 7 >= a.row_lo) ? r + 7 : -1;
             }
 
             for (int s = 0; s < nslab; s++, it++) {
@@ -241,7 +243,7 @@ posterior_kernel(const __grid_constant__ CUtensorMap wmap, PostArgs a) {
                 mbar_wait(full0 + 8 * stage, parity);
                 const uint8_t* wsrc = Wst + stage * P_W_STAGE_BYTES + warp * 8 * 128;     // tile i adds i*8 warps*8 rows
                 const double* psrc = Pst + stage * P_BN * P_PLD;
-                const bool full = (k0 + P_BK <= row0) && (row0 + P_BM <= a.npad);
+                const bool full = (k0 + P_BK <= row0) && (row0 + P_BM <= a.npad) && (row0 >= a.row_lo);
                 if (full) {
                     double af[2][P_MI], bf[2][P_NI];
 #pragma unroll
@@ -292,7 +294,7 @@ posterior_kernel(const __grid_constant__ CUtensorMap wmap, PostArgs a) {
 #pragma unroll
             for (int i = 0; i < P_MI; i++) {
                 const int row = row0 + (i * P_CONSUMER_WARPS + warp) * 8 + pr;
-                if (row < a.npad) {
+                if (row < a.npad && row >= a.row_lo) {
                     const double zr = a.z[row];
 #pragma unroll
                     for (int j = 0; j < P_NI; j++) {
@@ -346,9 +348,15 @@ posterior_kernel(const __grid_constant__ CUtensorMap wmap, PostArgs a) {
                     s += colacc[(w * P_BN + tid) * 2 + 0];
                     d += colacc[(w * P_BN + tid) * 2 + 1];
                 }
-                a.var[g] = p.k0 - s;
-                a.mu[g] = p.mean_H + d;
-                if (a.qout) a.qout[g] = s;
+                if (a.row_lo > 0) {      // incremental: the new rows' contributions are added to the standing posterior
+                    a.var[g] -= s;
+                    a.mu[g] += d;
+                    if (a.qout) a.qout[g] += s;
+                } else {
+                    a.var[g] = p.k0 - s;
+                    a.mu[g] = p.mean_H + d;
+                    if (a.qout) a.qout[g] = s;
+                }
             }
         }
     }
@@ -437,6 +445,7 @@ static int posterior_common(PostArgs& a, bool grid, const double* W, int64_t npa
     if ((reinterpret_cast<uintptr_t>(W) & 15) || (ldw & 1)) return MFGP_ERR_INVALID;     // TMA: 16-byte aligned rows
     if (!p_host->multi && a.NL != 0) return MFGP_ERR_INVALID;
     if (a.Vc && a.ldv < a.G) return MFGP_ERR_INVALID;
+    if (a.row_lo < 0 || a.row_lo >= N) return MFGP_ERR_INVALID;
     CUtensorMap wmap;
     int rc = make_w_tensor_map(&wmap, W, npad, ldw);
     if (rc) return rc;
@@ -490,5 +499,35 @@ extern "C" int mfgp_posterior_grid(int64_t ny, int64_t g_lo, int64_t G, const do
     PostArgs a{};
     a.G = G; a.TLx = TLx; a.TLy = TLy; a.THx = THx; a.THy = THy; a.ldt = ldt; a.g_lo = g_lo; a.ny = (int)ny;
     a.NL = (int)NL; a.NH = (int)NH; a.z = z; a.mu = mu; a.var = var; a.qout = qred; a.Vc = Vc; a.ldv = ldv;
+    return posterior_common(a, true, W, npad, ldw, p_host, static_cast<cudaStream_t>(stream));
+}
+
+// Incremental forms: rows [row_lo, N) of V = W psi are new since mu / var (/ qred) were last computed -- samples appended
+// by mfgp_cholesky_append -- and only their contributions are formed and added:  mu += v_new . z_new,  var -= |v_new|^2.
+extern "C" int mfgp_posterior_update(const double* Xs, int64_t G, const double* Tt, int64_t NL, int64_t NH, const double* W,
+                                     int64_t npad, int64_t ldw, const double* z, const mfgp_params* p_host, int64_t row_lo,
+                                     double* mu, double* var, double* qred, double* Vc, int64_t ldv, void* stream) {
+    if (!p_host || !mu || !var || G < 0 || NL < 0 || NH < 0 || row_lo <= 0 || row_lo >= NL + NH) return MFGP_ERR_INVALID;
+    if (G == 0) return MFGP_OK;
+    if (!Xs || !Tt) return MFGP_ERR_INVALID;
+    PostArgs a{};
+    a.Xs = Xs; a.G = G; a.Tt = Tt; a.NL = (int)NL; a.NH = (int)NH; a.z = z; a.mu = mu; a.var = var; a.qout = qred; a.Vc = Vc; a.ldv = ldv;
+    a.row_lo = (int)row_lo;
+    return posterior_common(a, false, W, npad, ldw, p_host, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int mfgp_posterior_grid_update(int64_t ny, int64_t g_lo, int64_t G, const double* TLx, const double* TLy,
+                                          const double* THx, const double* THy, int64_t ldt, int64_t NL, int64_t NH,
+                                          const double* W, int64_t npad, int64_t ldw, const double* z, const mfgp_params* p_host,
+                                          int64_t row_lo, double* mu, double* var, double* qred, double* Vc, int64_t ldv,
+                                          void* stream) {
+    if (!p_host || !mu || !var || G < 0 || NL < 0 || NH < 0 || ny <= 0 || g_lo < 0 || row_lo <= 0 || row_lo >= NL + NH)
+        return MFGP_ERR_INVALID;
+    if (G == 0) return MFGP_OK;
+    if (!TLx || !TLy || !THx || !THy || ldt < npad) return MFGP_ERR_INVALID;
+    PostArgs a{};
+    a.G = G; a.TLx = TLx; a.TLy = TLy; a.THx = THx; a.THy = THy; a.ldt = ldt; a.g_lo = g_lo; a.ny = (int)ny;
+    a.NL = (int)NL; a.NH = (int)NH; a.z = z; a.mu = mu; a.var = var; a.qout = qred; a.Vc = Vc; a.ldv = ldv;
+    a.row_lo = (int)row_lo;
     return posterior_common(a, true, W, npad, ldw, p_host, static_cast<cudaStream_t>(stream));
 }

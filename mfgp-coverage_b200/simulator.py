@@ -21,6 +21,7 @@ Deliberate differences from the reference (documented in DESIGN.md):
     third-party host routine outside the hot path).
 """
 import copy
+import os
 import random
 import sys
 
@@ -327,6 +328,11 @@ def _fidelity_of(hyp):
     raise TypeError("Hyperparameters must be of length 4 (single-fidelity) or 9 (multi-fidelity)")
 
 
+# MFGP_INCREMENTAL=1 (or simulator.INCREMENTAL = True): bordered factor updates + incremental posterior in the algorithm
+# loops instead of the reference's refit-from-scratch every iteration (gaussian_process.py:266-268, :540-542).
+INCREMENTAL = os.environ.get("MFGP_INCREMENTAL", "0") == "1"
+
+
 def _init_models(fidelity, hyp, prior):
     """reference simulator.py:656-681 / :826-851 / :998-1024: max_var_0 from the EMPTY model (== k(0), evaluated on the
     device through the N = 0 posterior), then the model conditioned on the prior with a forced update."""
@@ -338,6 +344,7 @@ def _init_models(fidelity, hyp, prior):
     else:
         model = init_MFGP(hyp, prior=prior)
         model.updt_info(model.X_L, model.y_L, model.X_H, model.y_H)
+    model.incremental = INCREMENTAL
     return model, max_var_0
 
 
