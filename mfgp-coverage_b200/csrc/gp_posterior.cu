@@ -362,6 +362,247 @@ posterior_kernel(const __grid_constant__ CUtensorMap wmap, PostArgs a) {
     }
 }
 
+// ---- skinny incremental update ------------------------------------------------------------------------------------------
+// After mfgp_cholesky_append only a few rows of V = W psi are new.  posterior_kernel's tile (512 rows x 32 points) would
+// regenerate every psi element for 64 useful rows; here the CTA tile is 64 ROWS x 256 GRID POINTS instead: all eight
+// consumer warps share the same 64 x 16 slab of W (one TMA box) and each owns 32 of the 256 points, so a psi element is
+// still generated once per CTA and the register tile (8 x 4 DMMA tiles per warp) is the same.  Rows are processed in
+// 64-row blocks [rb, rb+64) from the block that holds row_lo; each warp folds its own points -- no cross-warp reduction.
+constexpr int U_BM = 64;
+constexpr int U_BN = 256;
+constexpr int U_W_STAGE_BYTES = U_BM * P_BK * 8;            // 8192
+constexpr int U_PSI_STAGE_BYTES = U_BN * P_PLD * 8;         // 40960
+constexpr int U_SMEM_BYTES = P_STAGES * (U_W_STAGE_BYTES + U_PSI_STAGE_BYTES) + U_BN * 4 * 8 + 2 * P_STAGES * 8 + 1024;
+
+template <bool GRID>
+__global__ void __launch_bounds__(P_THREADS, 1)
+posterior_update_kernel(const __grid_constant__ CUtensorMap wmap, PostArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* Wst = smem;                                                        // [S][64][16] doubles, swizzled
+    double* Pst = reinterpret_cast<double*>(smem + P_STAGES * U_W_STAGE_BYTES); // [S][256][20]
+    double* xs = Pst + P_STAGES * U_BN * P_PLD;                                 // [256][4] scaled coordinates (general mode)
+    int* offs = reinterpret_cast<int*>(xs);                                     // [256][2] table row offsets (grid mode)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(xs + U_BN * 4);
+    const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + P_STAGES);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t g0 = (int64_t)blockIdx.x * U_BN;
+    const int N = a.NL + a.NH;
+    const DevParams& p = a.p;
+
+    if (tid == 0) {
+        for (int s = 0; s < P_STAGES; s++) {
+            mbar_init(full0 + 8 * s, P_PRODUCER_WARPS * 32);
+            mbar_init(empty0 + 8 * s, P_CONSUMER_WARPS);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    for (int e = tid; e < U_BN; e += P_THREADS) {
+        int64_t g = g0 + e;
+        if (g >= a.G) g = a.G - 1;
+        if (GRID) {
+            g += a.g_lo;
+            offs[2 * e] = (int)((g / a.ny) * a.ldt);
+            offs[2 * e + 1] = (int)((g % a.ny) * a.ldt);
+        } else {
+            const double x = a.Xs[2 * g], y = a.Xs[2 * g + 1];
+            xs[e * 4 + 0] = x / p.l_L;
+            xs[e * 4 + 1] = y / p.l_L;
+            xs[e * 4 + 2] = x / p.l_H;
+            xs[e * 4 + 3] = y / p.l_H;
+        }
+    }
+    __syncthreads();
+
+    const int rb0 = a.row_lo / U_BM * U_BM;
+
+    if (warp >= P_CONSUMER_WARPS) {
+        // =============================== PRODUCERS ===============================
+        reg_dealloc<72>();
+        const int pt = tid - P_CONSUMER_WARPS * 32;       // 0..127
+        const int k = pt & 15;                            // column of the slab this thread generates
+        const int gbase = pt >> 4;                        // points gbase + 8 i, i = 0..31
+        // grid mode: the 256 consecutive x-major points of a CTA lie in at most two grid columns when ny >= 255; the
+        // x-axis factors are then two values per training column (loaded once per slab) and only the y-axis factors
+        // are fetched per element.  `second` marks this thread's points that lie in the second column.
+        const int offx0 = GRID ? offs[0] : 0, offx1 = GRID ? offs[2 * (U_BN - 1)] : 0;
+        bool two_col = GRID;
+        unsigned second = 0;
+        if (GRID) {
+#pragma unroll 1
+            for (int i = 0; i < U_BN / 8; i++) {
+                const int ox = offs[2 * (gbase + 8 * i)];
+                if (ox == offx1 && offx1 != offx0) second |= 1u << i;
+                else if (ox != offx0) two_col = false;
+            }
+            two_col = __all_sync(0xffffffffu, two_col);      // (every producer thread reaches the same verdict per CTA
+        }                                                     //  only if all see it: threads cover disjoint points)
+        __shared__ int s_two_col;
+        if (GRID) {
+            if (pt == 0) s_two_col = 1;
+            asm volatile("bar.sync 2, %0;\n" ::"n"(P_PRODUCER_WARPS * 32) : "memory");
+            if (!two_col) s_two_col = 0;
+            asm volatile("bar.sync 2, %0;\n" ::"n"(P_PRODUCER_WARPS * 32) : "memory");
+            two_col = s_two_col != 0;
+        }
+        int it = 0;
+        for (int rb = rb0; rb < a.npad; rb += U_BM) {
+            const int nslab = (rb + U_BM) / P_BK;
+            for (int s = 0; s < nslab; s++, it++) {
+                const int stage = it % P_STAGES;
+                const uint32_t parity = (it / P_STAGES) & 1;
+                const int n = s * P_BK + k;
+                double4 t = make_double4(0.0, 0.0, 0.0, 0.0);
+                double lx0 = 0.0, hx0 = 0.0, lx1 = 0.0, hx1 = 0.0;
+                if (GRID) {
+                    if (two_col) {
+                        lx0 = __ldg(a.TLx + offx0 + n); hx0 = __ldg(a.THx + offx0 + n);
+                        lx1 = __ldg(a.TLx + offx1 + n); hx1 = __ldg(a.THx + offx1 + n);
+                    }
+                } else if (n < N) {
+                    t = reinterpret_cast<const double4*>(a.Tt)[n];
+                }
+                mbar_wait(empty0 + 8 * stage, parity ^ 1);
+                if (pt == 0) {
+                    mbar_expect_tx(full0 + 8 * stage, U_W_STAGE_BYTES);
+                    tma_load_2d(smem_u32(Wst + stage * U_W_STAGE_BYTES), &wmap, s * P_BK, rb, full0 + 8 * stage);
+                }
+                double* pdst = Pst + stage * U_BN * P_PLD;
+                if (GRID && two_col) {
+#pragma unroll 1
+                    for (int i0 = 0; i0 < U_BN / 8; i0 += 8) {
+                        double ly[8], hy[8];
+#pragma unroll
+                        for (int u = 0; u < 8; u++) {        // all loads of the batch first: their latencies overlap
+                            const int oy = offs[2 * (gbase + 8 * (i0 + u)) + 1] + n;
+                            ly[u] = __ldg(a.TLy + oy);
+                            hy[u] = __ldg(a.THy + oy);
+                        }
+#pragma unroll
+                        for (int u = 0; u < 8; u++) {
+                            const bool sec = (second >> (i0 + u)) & 1u;
+                            pdst[(gbase + 8 * (i0 + u)) * P_PLD + k] = fma(sec ? hx1 : hx0, hy[u], (sec ? lx1 : lx0) * ly[u]);
+                        }
+                    }
+                } else {
+#pragma unroll 2
+                    for (int i = 0; i < U_BN / 8; i++) {
+                        const int gi = gbase + 8 * i;
+                        double v = 0.0;
+                        if (GRID) {
+                            const int ox = offs[2 * gi] + n, oy = offs[2 * gi + 1] + n;
+                            v = fma(__ldg(a.THx + ox), __ldg(a.THy + oy), __ldg(a.TLx + ox) * __ldg(a.TLy + oy));
+                        } else if (n < N) {
+                            if (p.multi) {
+                                const double kL = rbf_scaled(xs[gi * 4 + 0], xs[gi * 4 + 1], t.x, t.y, p.s_L);
+                                if (n < a.NL) {
+                                    v = p.rho * kL;
+                                } else {
+                                    const double kH = rbf_scaled(xs[gi * 4 + 2], xs[gi * 4 + 3], t.z, t.w, p.s_H);
+                                    v = __dadd_rn(__dmul_rn(p.rho2, kL), kH);
+                                }
+                            } else {
+                                v = rbf_scaled(xs[gi * 4 + 2], xs[gi * 4 + 3], t.z, t.w, p.s_H);
+                            }
+                        }
+                        pdst[gi * P_PLD + k] = v;
+                    }
+                }
+                mbar_arrive(full0 + 8 * stage);
+            }
+        }
+    } else {
+        // =============================== CONSUMERS ===============================
+        reg_alloc<216>();
+        const int gq = lane >> 2, tq = lane & 3;
+        const int pr = row_perm(gq);
+        int aoff[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) aoff[j] = pr * 128 + ((((j * 4 + tq) >> 1) ^ pr) << 4) + ((tq & 1) << 3);
+        double sq[P_NI][2], dt[P_NI][2];
+#pragma unroll
+        for (int j = 0; j < P_NI; j++) sq[j][0] = sq[j][1] = dt[j][0] = dt[j][1] = 0.0;
+        int it = 0;
+        for (int rb = rb0; rb < a.npad; rb += U_BM) {
+            const int nslab = (rb + U_BM) / P_BK;
+            double acc[P_MI][P_NI][2];
+#pragma unroll
+            for (int i = 0; i < P_MI; i++)
+#pragma unroll
+                for (int j = 0; j < P_NI; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+            for (int s = 0; s < nslab; s++, it++) {
+                const int stage = it % P_STAGES;
+                const uint32_t parity = (it / P_STAGES) & 1;
+                mbar_wait(full0 + 8 * stage, parity);
+                const uint8_t* wsrc = Wst + stage * U_W_STAGE_BYTES;                     // tile i: rows 8 i .. 8 i + 7
+                const double* psrc = Pst + stage * U_BN * P_PLD + warp * 32 * P_PLD;     // this warp's 32 points
+                double af[2][P_MI], bf[2][P_NI];
+#pragma unroll
+                for (int i = 0; i < P_MI; i++) af[0][i] = *reinterpret_cast<const double*>(wsrc + i * (8 * 128) + aoff[0]);
+#pragma unroll
+                for (int j = 0; j < P_NI; j++) bf[0][j] = psrc[(j * 8 + gq) * P_PLD + tq];
+#pragma unroll
+                for (int ks = 0; ks < 4; ks++) {
+                    const int cur = ks & 1, nxt = cur ^ 1;
+                    if (ks < 3) {
+#pragma unroll
+                        for (int i = 0; i < P_MI; i++)
+                            af[nxt][i] = *reinterpret_cast<const double*>(wsrc + i * (8 * 128) + aoff[ks + 1]);
+#pragma unroll
+                        for (int j = 0; j < P_NI; j++) bf[nxt][j] = psrc[(j * 8 + gq) * P_PLD + (ks + 1) * 4 + tq];
+                    }
+#pragma unroll
+                    for (int i = 0; i < P_MI; i++)
+#pragma unroll
+                        for (int j = 0; j < P_NI; j++) dmma884(acc[i][j][0], acc[i][j][1], af[cur][i], bf[cur][j]);
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(empty0 + 8 * stage);
+            }
+            // fold the new rows of this block into the per-point sums
+#pragma unroll
+            for (int i = 0; i < P_MI; i++) {
+                const int row = rb + i * 8 + pr;
+                if (row >= a.row_lo && row < a.npad) {
+                    const double zr = a.z[row];
+#pragma unroll
+                    for (int j = 0; j < P_NI; j++) {
+                        const double v0 = acc[i][j][0], v1 = acc[i][j][1];
+                        sq[j][0] += v0 * v0;
+                        sq[j][1] += v1 * v1;
+                        dt[j][0] += v0 * zr;
+                        dt[j][1] += v1 * zr;
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < P_NI; j++)
+#pragma unroll
+            for (int c = 0; c < 2; c++) {
+#pragma unroll
+                for (int o = 4; o < 32; o <<= 1) {
+                    sq[j][c] += __shfl_xor_sync(0xffffffffu, sq[j][c], o);
+                    dt[j][c] += __shfl_xor_sync(0xffffffffu, dt[j][c], o);
+                }
+            }
+        if (gq == 0) {
+#pragma unroll
+            for (int j = 0; j < P_NI; j++)
+#pragma unroll
+                for (int c = 0; c < 2; c++) {
+                    const int64_t g = g0 + warp * 32 + j * 8 + tq * 2 + c;
+                    if (g < a.G) {
+                        a.var[g] -= sq[j][c];
+                        a.mu[g] += dt[j][c];
+                        if (a.qout) a.qout[g] += sq[j][c];
+                    }
+                }
+        }
+    }
+}
+
 __global__ void posterior_prior_kernel(int64_t G, double mean, double k0, double* __restrict__ mu, double* __restrict__ var,
                                        double* __restrict__ q) {
     const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -401,7 +642,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-static int make_w_tensor_map(CUtensorMap* map, const double* W, int64_t npad, int64_t ldw) {
+static int make_w_tensor_map(CUtensorMap* map, const double* W, int64_t npad, int64_t ldw, int box_rows = P_BM / 2) {
     static EncodeTiledFn encode = nullptr;
     if (!encode) {
         void* fn = nullptr;
@@ -415,7 +656,7 @@ static int make_w_tensor_map(CUtensorMap* map, const double* W, int64_t npad, in
     }
     const cuuint64_t gdim[2] = {(cuuint64_t)npad, (cuuint64_t)npad};       // {columns (contiguous), rows}
     const cuuint64_t gstride[1] = {(cuuint64_t)ldw * sizeof(double)};      // row pitch in bytes
-    const cuuint32_t box[2] = {(cuuint32_t)P_BK, (cuuint32_t)(P_BM / 2)};  // 16 doubles (128 B) x 256 rows
+    const cuuint32_t box[2] = {(cuuint32_t)P_BK, (cuuint32_t)box_rows};    // 16 doubles (128 B) x 256 (or 64) rows
     const cuuint32_t estr[2] = {1, 1};
     const CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(W), gdim, gstride, box, estr,
                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -447,9 +688,24 @@ static int posterior_common(PostArgs& a, bool grid, const double* W, int64_t npa
     if (a.Vc && a.ldv < a.G) return MFGP_ERR_INVALID;
     if (a.row_lo < 0 || a.row_lo >= N) return MFGP_ERR_INVALID;
     CUtensorMap wmap;
+    a.npad = (int)npad;
+    if (a.row_lo > 0 && a.Vc == nullptr && npad - a.row_lo / U_BM * U_BM <= 4 * U_BM) {
+        // few new rows: the 64-row x 256-point tiling keeps the psi regeneration amortised
+        int rcu = make_w_tensor_map(&wmap, W, npad, ldw, U_BM);
+        if (rcu) return rcu;
+        const unsigned nb = (unsigned)((a.G + U_BN - 1) / U_BN);
+        if (grid) {
+            MFGP_CUDA_CHECK(cudaFuncSetAttribute(posterior_update_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, U_SMEM_BYTES));
+            posterior_update_kernel<true><<<nb, P_THREADS, U_SMEM_BYTES, st>>>(wmap, a);
+        } else {
+            MFGP_CUDA_CHECK(cudaFuncSetAttribute(posterior_update_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, U_SMEM_BYTES));
+            posterior_update_kernel<false><<<nb, P_THREADS, U_SMEM_BYTES, st>>>(wmap, a);
+        }
+        MFGP_LAUNCH_CHECK();
+        return MFGP_OK;
+    }
     int rc = make_w_tensor_map(&wmap, W, npad, ldw);
     if (rc) return rc;
-    a.npad = (int)npad;
     const unsigned nblk = (unsigned)((a.G + P_BN - 1) / P_BN);
     if (grid) {
         MFGP_CUDA_CHECK(cudaFuncSetAttribute(posterior_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_BYTES));
