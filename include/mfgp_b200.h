@@ -148,6 +148,23 @@ int cov_assign_reduce(const double* xy, const double* w, const double* var, cons
                       uint64_t* member_c, void* work, int64_t work_bytes, void* stream);
 int64_t cov_workspace_bytes(int64_t G, int64_t Ac, int64_t Ap);
 
+/* Bounded Voronoi cells on the device (replaces voronoi_bounded simulator.py:154-191 + poly_area :127-136 where host Qhull
+ * is the bottleneck -- replicate sweeps, device-resident loops): cell i = the box [xmin-eps/2, xmax+eps/2] x
+ * [ymin-eps/2, ymax+eps/2] clipped by the bisectors with all other seeds, which IS the reference's mirrored-seed diagram
+ * restricted to its first A cells.  Output in cov_assign_reduce's layout: poly_xy[<= cap_vertices, 2], poly_off[A+1],
+ * plus areas[A] (shoelace).  Vertices agree with Qhull's to ~1e-13; only grid points exactly on a bisector can be
+ * classified differently, so parity runs keep Qhull.  flag[0] = 1 (and NaN areas) if a polygon outgrew the capacity. */
+int cov_voronoi_clip(const double* seeds, int64_t A, double xmin, double xmax, double ymin, double ymax, double eps,
+                     double* poly_xy, int32_t* poly_off, int64_t cap_vertices, double* areas, int32_t* flag, void* stream);
+
+/* O(A) finishing of cov_assign_reduce's partial sums with the reference's arithmetic (simulator.py:215-219, :256-271):
+ * out[0] = loss, out[1+2i], out[2+2i] = centroid i clamped to [xmin,xmax] x [ymin,ymax], out[1+2Ac+i] = max variance of
+ * cell i, out[1+3Ac+i] = its arg-max grid index as a double (-1: empty cell).  One D2H copy brings a whole iteration's
+ * result back. */
+int cov_finish(const double* cent, const double* areas_c, int64_t Ac, const double* lossp, const double* areas_p, int64_t Ap,
+               const double* amax_val, const int64_t* amax_idx, double xmin, double xmax, double ymin, double ymax,
+               double* out, void* stream);
+
 /* Global first-index argmax of v[G] (np.argmax at simulator.py:352): out_val[1], out_idx[1]. */
 int cov_argmax(const double* v, int64_t G, int64_t base_index, double k0, double rel, double* out_val, int64_t* out_idx,
                void* work, int64_t work_bytes, void* stream);

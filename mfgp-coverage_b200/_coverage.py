@@ -59,13 +59,15 @@ class BoundedVoronoi:
         return self.vertices[self.filtered_regions[i], :]
 
     def areas(self):
-        """Shoelace area per cell (simulator.py:127-136)."""
-        out = np.empty(len(self))
-        for i in range(len(self)):
-            v = self.cell_vertices(i)
-            x, y = v[:, 0], v[:, 1]
-            out[i] = 0.5 * np.abs(np.dot(x, np.roll(y, 1)) - np.dot(y, np.roll(x, 1)))
-        return out
+        """Shoelace area per cell (simulator.py:127-136): 0.5 |x . roll(y,1) - y . roll(x,1)|, cached."""
+        if getattr(self, "_areas", None) is None:
+            out = np.empty(len(self))
+            for i in range(len(self)):
+                v = self.vertices[self.filtered_regions[i]]
+                x, y = v[:, 0], v[:, 1]
+                out[i] = 0.5 * abs(float(np.dot(x[1:], y[:-1]) + x[0] * y[-1]) - float(np.dot(y[1:], x[:-1]) + y[0] * x[-1]))
+            self._areas = out
+        return self._areas
 
     def flat(self):
         """(seeds[A,2], poly_xy[nvert,2], poly_off[A+1]) as contiguous host arrays."""
@@ -79,6 +81,63 @@ class BoundedVoronoi:
             poly = np.ascontiguousarray(np.concatenate(chunks, axis=0), dtype=np.float64) if chunks else np.empty((0, 2))
             self._flat = (np.ascontiguousarray(self.filtered_points, dtype=np.float64), poly, off)
         return self._flat
+
+
+class ClippedVoronoi:
+    """Bounded Voronoi partition built ON THE DEVICE by half-plane clipping (cov_voronoi_clip): same cells as
+    BoundedVoronoi up to ~1e-13 in the vertices, no host Qhull call and nothing to upload but the seeds.  Host views
+    (`vertices`, `filtered_regions`, `areas()`) are fetched lazily, only if somebody asks."""
+
+    def __init__(self, points, bounding_box, device=None):
+        nat.require_cuda()
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        points = np.asarray(points, dtype=np.float64)
+        bb = np.asarray(bounding_box, dtype=np.float64)
+        c = np.ascontiguousarray(points[in_box(points, bb), :])
+        self.filtered_points = c
+        self.bounding_box = bb
+        self.A = int(c.shape[0])
+        self.seeds_inside = bool(np.all((c[:, 0] >= bb[0]) & (c[:, 0] <= bb[1]) & (c[:, 1] >= bb[2]) & (c[:, 1] <= bb[3])))
+        self.nvert = 7 * self.A + 16                       # capacity (planar bound ~6A + corners); actual count = off[A]
+        f64 = dict(dtype=torch.float64, device=self.device)
+        self.seeds = torch.from_numpy(c.reshape(-1)).to(self.device)
+        self.poly = torch.empty(2 * self.nvert, **f64)
+        self.off = torch.empty(self.A + 2, dtype=torch.int32, device=self.device)
+        self.dev_areas = torch.empty(max(self.A, 1), **f64)
+        self.flag = torch.empty(1, dtype=torch.int32, device=self.device)
+        if self.A:
+            nat.check(nat.lib().cov_voronoi_clip(nat.ptr(self.seeds), self.A, bb[0], bb[1], bb[2], bb[3], EPS,
+                                                 nat.ptr(self.poly), nat.ptr(self.off), self.nvert, nat.ptr(self.dev_areas),
+                                                 nat.ptr(self.flag), nat.stream_ptr()), "cov_voronoi_clip")
+        self._host = None
+
+    def __len__(self):
+        return self.A
+
+    def _fetch(self):
+        if self._host is None:
+            if int(self.flag.item()):
+                raise RuntimeError("cov_voronoi_clip: polygon capacity exceeded")
+            off = self.off[:self.A + 1].cpu().numpy()
+            poly = self.poly.cpu().numpy().reshape(-1, 2)[:off[-1]]
+            self._host = (poly, off, self.dev_areas[:self.A].cpu().numpy())
+        return self._host
+
+    @property
+    def vertices(self):
+        return self._fetch()[0]
+
+    @property
+    def filtered_regions(self):
+        off = self._fetch()[1]
+        return [list(range(off[i], off[i + 1])) for i in range(self.A)]
+
+    def cell_vertices(self, i):
+        poly, off, _ = self._fetch()
+        return poly[off[i]:off[i + 1]]
+
+    def areas(self):
+        return self._fetch()[2]
 
 
 def polygon_partition(seeds, polygons):
@@ -99,6 +158,9 @@ def polygon_partition(seeds, polygons):
 
 class _DevPartition:
     """Seeds, polygon vertices and polygon offsets of one partition on the device (ONE packed upload)."""
+
+    def __len__(self):
+        return self.A
 
     def __init__(self, vor, device):
         seeds, poly, off = vor.flat()
@@ -146,8 +208,8 @@ class CoverageGrid:
 
     def upload(self, vor):
         """Device copy of a partition (BoundedVoronoi / polygon_partition); pass the result to assign_reduce to reuse it."""
-        if vor is None or isinstance(vor, _DevPartition):
-            return vor
+        if vor is None or isinstance(vor, (_DevPartition, ClippedVoronoi)):
+            return vor if (vor is None or len(vor)) else None
         if not len(vor):
             return None
         d = _DevPartition(vor, self.device)
@@ -195,6 +257,20 @@ class CoverageGrid:
         nat.check(rc, "cov_assign_reduce")
         out.update(cent=cent, amax_val=amax_val, amax_idx=amax_idx, lossp=lossp, members=members)
         return out
+
+    def finish(self, res, lloyd_vor, loss_vor, bbox):
+        """Device finishing of an assign_reduce result for DEVICE-resident partitions (ClippedVoronoi): returns
+        (loss, centroids[Ac,2], max_var[Ac], argmax_idx[Ac]) with ONE device->host copy (cov_finish)."""
+        Ac = len(lloyd_vor) if lloyd_vor is not None else 0
+        Ap = len(loss_vor) if loss_vor is not None else 0
+        out = torch.empty(1 + 4 * max(Ac, 1), dtype=torch.float64, device=self.device)
+        nat.check(nat.lib().cov_finish(nat.ptr(res["cent"]), nat.ptr(lloyd_vor.dev_areas) if Ac else None, Ac,
+                                       nat.ptr(res["lossp"]), nat.ptr(loss_vor.dev_areas) if Ap else None, Ap,
+                                       nat.ptr(res["amax_val"]), nat.ptr(res["amax_idx"]), bbox[0], bbox[1], bbox[2], bbox[3],
+                                       nat.ptr(out), nat.stream_ptr()), "cov_finish")
+        h = out.cpu().numpy()
+        return float(h[0]), h[1:1 + 2 * Ac].reshape(Ac, 2).copy(), h[1 + 2 * Ac:1 + 3 * Ac].copy(), \
+            h[1 + 3 * Ac:1 + 4 * Ac].astype(np.int64)
 
     def argmax(self, v_dev, k0=0.0, rel=0.0):
         """First-index argmax of a device vector (np.argmax semantics): returns (value, index) device tensors."""

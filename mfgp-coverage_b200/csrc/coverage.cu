@@ -85,7 +85,8 @@ struct BucketGrid {
 };
 
 __global__ void __launch_bounds__(128) cov_build_buckets_kernel(const double* __restrict__ seeds, int A,
-                                                                const double* __restrict__ poly_xy, int nvert, int nb,
+                                                                const double* __restrict__ poly_xy,
+                                                                const int32_t* __restrict__ poly_off, int nb,
                                                                 double tie_tol, uint4* __restrict__ table,
                                                                 double* __restrict__ geom /* x0, y0, inv_h */) {
     extern __shared__ __align__(16) double bsm[];      // [2*A] seeds + [4*4] bbox partials
@@ -93,6 +94,7 @@ __global__ void __launch_bounds__(128) cov_build_buckets_kernel(const double* __
     double* s_box = bsm + 2 * A;
     const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
     for (int i = tid; i < 2 * A; i += 128) s_seeds[i] = seeds[i];
+    const int nvert = poly_off[A];
     // bounding box of the polygon vertices (every CTA recomputes it: nvert is a few hundred)
     double x0 = DBL_MAX, x1 = -DBL_MAX, y0 = DBL_MAX, y1 = -DBL_MAX;
     for (int i = tid; i < nvert; i += 128) {
@@ -542,12 +544,12 @@ extern "C" int cov_assign_reduce(const double* xy, const double* w, const double
         a.nb_c = cov_bucket_side(Ac);
         a.nb_p = cov_bucket_side(Ap);
         if (Ac) {
-            cov_build_buckets_kernel<<<(a.nb_c * a.nb_c + 127) / 128, 128, (2 * Ac + 16) * sizeof(double), st>>>(seeds_c, (int)Ac, poly_xy_c, (int)nvc, a.nb_c, tie_tol,
+            cov_build_buckets_kernel<<<(a.nb_c * a.nb_c + 127) / 128, 128, (2 * Ac + 16) * sizeof(double), st>>>(seeds_c, (int)Ac, poly_xy_c, poly_off_c, a.nb_c, tie_tol,
                                                                              const_cast<uint4*>(a.buckets_c), const_cast<double*>(a.geom_c));
             MFGP_LAUNCH_CHECK();
         }
         if (Ap) {
-            cov_build_buckets_kernel<<<(a.nb_p * a.nb_p + 127) / 128, 128, (2 * Ap + 16) * sizeof(double), st>>>(seeds_p, (int)Ap, poly_xy_p, (int)nvp, a.nb_p, tie_tol,
+            cov_build_buckets_kernel<<<(a.nb_p * a.nb_p + 127) / 128, 128, (2 * Ap + 16) * sizeof(double), st>>>(seeds_p, (int)Ap, poly_xy_p, poly_off_p, a.nb_p, tie_tol,
                                                                              const_cast<uint4*>(a.buckets_p), const_cast<double*>(a.geom_p));
             MFGP_LAUNCH_CHECK();
         }
@@ -586,6 +588,140 @@ extern "C" int cov_argmax(const double* v, int64_t G, int64_t base_index, double
     argmax_partial_kernel<<<nblocks, 256, 0, st>>>(v, G, base_index, tol, pv, pi);
     MFGP_LAUNCH_CHECK();
     argmax_final_kernel<<<1, 32, 0, st>>>(pv, pi, nblocks, tol, out_val, out_idx);
+    MFGP_LAUNCH_CHECK();
+    return MFGP_OK;
+}
+
+// ---- bounded Voronoi cells by half-plane clipping -----------------------------------------
+// The reference mirrors the seeds across the four sides of the box cushioned by eps and asks Qhull for the diagram of
+// the 5A points (simulator.py:154-191).  The first A cells of that diagram are exactly the cells of the A seeds clipped
+// to the box inflated by eps/2 (the bisector of a seed and its own mirror image; mirror images of OTHER seeds never cut
+// closer than the seeds themselves), so each cell is the inflated box clipped by the A-1 bisector half-planes
+// (Sutherland-Hodgman).  Agrees with Qhull's vertices to ~1e-13 (areas to ~1e-12); only grid points lying EXACTLY on a
+// bisector can be classified differently, which is why the Qhull path stays the default for parity runs.
+// One thread per cell; polygons are packed into poly_xy / poly_off in cell order; areas by the shoelace formula
+// (simulator.py:127-136).  flag[0] != 0: a polygon outgrew VC_MAXV or the packed capacity.
+namespace mfgp {
+constexpr int VC_MAXV = 48;
+
+__global__ void __launch_bounds__(256) cov_voronoi_clip_kernel(const double* __restrict__ seeds, int A, double x0, double x1, double y0,
+                                                               double y1, double* __restrict__ poly_xy, int32_t* __restrict__ poly_off,
+                                                               int cap_vertices, double* __restrict__ areas, int32_t* __restrict__ flag) {
+    __shared__ int counts[COV_MAX_CELLS + 1];
+    __shared__ double s_seeds[2 * COV_MAX_CELLS];
+    const int i = threadIdx.x;
+    for (int e = i; e < 2 * A; e += blockDim.x) s_seeds[e] = seeds[e];
+    __syncthreads();
+    double px[VC_MAXV], py[VC_MAXV], qx[VC_MAXV], qy[VC_MAXV];
+    int n = 0;
+    bool overflow = false;
+    if (i < A) {
+        px[0] = x0; py[0] = y0; px[1] = x1; py[1] = y0; px[2] = x1; py[2] = y1; px[3] = x0; py[3] = y1;
+        n = 4;
+        const double sx = s_seeds[2 * i], sy = s_seeds[2 * i + 1];
+        for (int j = 0; j < A && n > 0; j++) {
+            if (j == i) continue;
+            const double tx = s_seeds[2 * j], ty = s_seeds[2 * j + 1];
+            const double nx = tx - sx, ny = ty - sy;
+            if (nx == 0.0 && ny == 0.0) continue;                      // coincident seeds share one cell
+            const double c = 0.5 * ((tx * tx + ty * ty) - (sx * sx + sy * sy));
+            // quick reject: the whole polygon on the near side
+            int m = 0;
+            double da = nx * px[n - 1] + ny * py[n - 1] - c;
+            for (int v = 0; v < n; v++) {
+                const double ax = px[(v + n - 1) % n], ay = py[(v + n - 1) % n];
+                const double bx = px[v], by = py[v];
+                const double db = nx * bx + ny * by - c;
+                if ((da <= 0.0) != (db <= 0.0)) {                      // edge crosses the bisector
+                    const double t = da / (da - db);
+                    if (m < VC_MAXV) { qx[m] = ax + (bx - ax) * t; qy[m] = ay + (by - ay) * t; }
+                    m++;
+                }
+                if (db <= 0.0) {
+                    if (m < VC_MAXV) { qx[m] = bx; qy[m] = by; }
+                    m++;
+                }
+                da = db;
+            }
+            if (m > VC_MAXV) { overflow = true; m = VC_MAXV; }
+            n = m;
+            for (int v = 0; v < n; v++) { px[v] = qx[v]; py[v] = qy[v]; }
+        }
+        counts[i + 1] = n;
+    }
+    if (i == 0) counts[0] = 0;
+    __syncthreads();
+    if (i == 0)
+        for (int c = 1; c <= A; c++) counts[c] += counts[c - 1];
+    __syncthreads();
+    if (i <= A) poly_off[i] = counts[i];
+    if (i < A) {
+        const int o = counts[i];
+        if (o + n > cap_vertices) overflow = true;
+        else
+            for (int v = 0; v < n; v++) { poly_xy[2 * (o + v)] = px[v]; poly_xy[2 * (o + v) + 1] = py[v]; }
+        // shoelace: 0.5 |x . roll(y,1) - y . roll(x,1)|
+        double s1 = 0.0, s2 = 0.0;
+        for (int v = 0; v < n; v++) {
+            const int u = (v + n - 1) % n;
+            s1 += px[v] * py[u];
+            s2 += py[v] * px[u];
+        }
+        areas[i] = overflow ? __longlong_as_double(0x7ff8000000000000LL) : 0.5 * fabs(s1 - s2);   // NaN poisons loss / centroid
+        if (overflow) atomicExch(flag, 1);
+    }
+}
+
+// O(A) finishing of the per-cell partial sums with the reference's arithmetic (simulator.py:215-219, :256-271):
+// out[0] = loss, out[1 + 2i], out[2 + 2i] = centroid i (clamped to the grid's extent), out[1 + 2A + i] = max variance of
+// cell i, out[1 + 3A + i] = its arg-max grid index (as a double; exact below 2^53, -1 = empty cell).
+__global__ void cov_finish_kernel(const double* __restrict__ cent, const double* __restrict__ areas_c, int Ac,
+                                  const double* __restrict__ lossp, const double* __restrict__ areas_p, int Ap,
+                                  const double* __restrict__ amax_val, const int64_t* __restrict__ amax_idx, double xmin,
+                                  double xmax, double ymin, double ymax, double* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) {
+        double loss = 0.0;
+        for (int c = 0; c < Ap; c++) loss += (lossp[2 * c] / lossp[2 * c + 1]) * areas_p[c];     // cell order, like :215-219
+        out[0] = Ap ? loss : 0.0;
+    }
+    if (i < Ac) {
+        const double n = cent[4 * i + 3], a = areas_c[i];
+        const double f_int = (cent[4 * i] / n) * a;
+        double cx = ((cent[4 * i + 1] / n) * a) / f_int, cy = ((cent[4 * i + 2] / n) * a) / f_int;
+        if (cx < xmin) cx = xmin;
+        if (cx > xmax) cx = xmax;
+        if (cy < ymin) cy = ymin;
+        if (cy > ymax) cy = ymax;
+        out[1 + 2 * i] = cx;
+        out[2 + 2 * i] = cy;
+        out[1 + 2 * Ac + i] = amax_val ? amax_val[i] : 0.0;
+        out[1 + 3 * Ac + i] = amax_idx ? (double)amax_idx[i] : -1.0;
+    }
+}
+}  // namespace mfgp
+
+extern "C" int cov_voronoi_clip(const double* seeds, int64_t A, double xmin, double xmax, double ymin, double ymax, double eps,
+                                double* poly_xy, int32_t* poly_off, int64_t cap_vertices, double* areas, int32_t* flag,
+                                void* stream) {
+    if (!seeds || A <= 0 || A > COV_MAX_CELLS || !poly_xy || !poly_off || !areas || !flag || cap_vertices < 4) return MFGP_ERR_INVALID;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    MFGP_CUDA_CHECK(cudaMemsetAsync(flag, 0, sizeof(int32_t), st));
+    const double h = 0.5 * eps;
+    cov_voronoi_clip_kernel<<<1, 256, 0, st>>>(seeds, (int)A, xmin - h, xmax + h, ymin - h, ymax + h, poly_xy, poly_off,
+                                               (int)cap_vertices, areas, flag);
+    MFGP_LAUNCH_CHECK();
+    return MFGP_OK;
+}
+
+extern "C" int cov_finish(const double* cent, const double* areas_c, int64_t Ac, const double* lossp, const double* areas_p,
+                          int64_t Ap, const double* amax_val, const int64_t* amax_idx, double xmin, double xmax, double ymin,
+                          double ymax, double* out, void* stream) {
+    if (!out || Ac < 0 || Ap < 0 || (Ac && (!cent || !areas_c)) || (Ap && (!lossp || !areas_p))) return MFGP_ERR_INVALID;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int n = (int)(Ac > 1 ? Ac : 1);
+    cov_finish_kernel<<<(n + 127) / 128, 128, 0, st>>>(cent, areas_c, (int)Ac, lossp, areas_p, (int)Ap, amax_val, amax_idx, xmin, xmax,
+                                                      ymin, ymax, out);
     MFGP_LAUNCH_CHECK();
     return MFGP_OK;
 }

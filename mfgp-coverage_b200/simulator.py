@@ -112,8 +112,16 @@ def poly_area(x, y):
 in_box = cv.in_box
 
 
+# MFGP_VORONOI=clip (or simulator.VORONOI = "clip"): bounded Voronoi cells by half-plane clipping ON THE DEVICE
+# (cov_voronoi_clip) instead of scipy/Qhull on the host.  Same cells to ~1e-13; grid points lying EXACTLY on a bisector
+# may be classified differently, so the default stays "qhull" (tie parity is defined by live Qhull).
+VORONOI = os.environ.get("MFGP_VORONOI", "qhull")
+
+
 def voronoi_bounded(points, bounding_box):
     """reference simulator.py:154-191."""
+    if VORONOI == "clip":
+        return cv.ClippedVoronoi(points, bounding_box)
     return BoundedVoronoi(points, bounding_box)
 
 
@@ -291,6 +299,13 @@ class _Sim:
                                           amax_k0=prior_variance(model.params()), amax_rel=cv.AMAX_REL)
         else:
             res = self.grid.assign_reduce(lloyd_vor, loss_vor, w=weights)
+        if isinstance(lloyd_vor, cv.ClippedVoronoi) and isinstance(loss_vor, cv.ClippedVoronoi) and len(loss_vor) and len(lloyd_vor):
+            loss_t, centroids, max_var, idx = self.grid.finish(res, lloyd_vor, loss_vor, bb)     # one D2H per iteration
+            if model is None:
+                return loss_t, centroids, None, None, loss_vor, lloyd_vor
+            if np.any(idx < 0):
+                raise ValueError("zero-size array to reduction operation maximum which has no identity")   # np.amax([])
+            return loss_t, centroids, self.truth_arr[idx][:, [0, 1]], max_var.reshape(-1, 1), loss_vor, lloyd_vor
         loss_t = cv.loss_from_partials(res["lossp"].cpu().numpy(), loss_vor.areas())
         centroids = cv.centroids_from_partials(res["cent"].cpu().numpy(), lloyd_vor.areas(), bb[0], bb[1], bb[2], bb[3])
         if model is None:

@@ -81,3 +81,47 @@ def test_empty_cell_raises_like_numpy():
     with pytest.raises(ValueError):
         sim.compute_max_var(vor, truth, np.ones(25))
     assert np.isnan(sim.compute_loss(vor, truth)) == np.isnan(ocov.compute_loss(ovor, truth))
+
+
+@pytest.mark.parametrize("A,seed", [(4, 0), (8, 1), (16, 2), (64, 3), (200, 4)])
+def test_device_voronoi_clip_matches_qhull(A, seed):
+    """cov_voronoi_clip (half-plane clipping on the device) vs the reference's mirrored-seed Qhull diagram
+    (simulator.py:154-191): same cells -- vertex sets to 1e-12, shoelace areas to 1e-11 relative."""
+    from mfgp_coverage_b200 import _coverage as cv
+    seeds = synth.agents(A, seed)
+    bbox = np.array([0.0, 1.0, 0.0, 1.0])
+    q = ocov.voronoi_bounded(seeds, bbox)
+    c = cv.ClippedVoronoi(seeds, bbox)
+    assert len(c) == len(q.filtered_regions) == A
+    qa = np.array([ocov.poly_area(q.cell_vertices(i)[:, 0], q.cell_vertices(i)[:, 1]) for i in range(A)])
+    assert np.max(np.abs(c.areas() - qa) / qa) <= 1e-11
+    assert abs(c.areas().sum() - 1.1 ** 2) <= 1e-12                   # the cells tile the box inflated by eps/2
+    for i in range(A):
+        vq, vc = q.cell_vertices(i), c.cell_vertices(i)
+        assert vq.shape == vc.shape, i
+        d = np.sqrt(((vq[:, None, :] - vc[None, :, :]) ** 2).sum(axis=2))
+        assert d.min(axis=1).max() <= 1e-12 and d.min(axis=0).max() <= 1e-12
+
+
+def test_coverage_step_with_device_voronoi(monkeypatch):
+    """One fused coverage pass on device-built cells + device finishing (cov_finish) vs the oracle on Qhull cells."""
+    from mfgp_coverage_b200 import simulator as sim
+    monkeypatch.setattr(sim, "VORONOI", "clip")
+    xy, f, truth, _ = _setup(96, 16, 5, False)
+    rng = np.random.default_rng(8)
+    mu = f + 0.1 * rng.standard_normal(f.size)
+    var = rng.random(f.size)
+    pos, cen = synth.agents(16, 31), synth.agents(16, 32)
+    bbox = ocov.bounding_box_of(xy)
+    state = sim._Sim(truth)
+    import torch
+    state.mu.copy_(torch.from_numpy(mu))
+    state.var.copy_(torch.from_numpy(var))
+    lv, pv = sim.voronoi_bounded(cen, bbox), sim.voronoi_bounded(pos, bbox)
+    res = state.grid.assign_reduce(lv, pv, w=state.mu, var=state.var)
+    loss, cent, mv, idx = state.grid.finish(res, lv, pv, bbox)
+    olv, opv = ocov.voronoi_bounded(cen, bbox), ocov.voronoi_bounded(pos, bbox)
+    assert abs(loss - ocov.compute_loss(opv, truth)) <= 1e-9 * abs(loss)
+    assert np.max(np.abs(cent - ocov.compute_centroids(olv, xy, mu.reshape(-1, 1)))) <= 1e-9
+    _, mv_o, idx_o = ocov.compute_max_var(olv, truth, var)
+    assert np.array_equal(idx, idx_o) and np.array_equal(mv, mv_o.reshape(-1))

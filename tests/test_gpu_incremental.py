@@ -150,3 +150,28 @@ def test_incremental_runs_vs_oracle_loops(algo, n, A, T, multi, monkeypatch):
                                for r in s]).reshape(-1, 5)
     _compare(np.array([r["Loss"] for r in lg]), _agent_array(ag, len(lg), A), to_s(sg),
              np.array([r["Loss"] for r in lo]), _agent_array(ao, len(lo), A), to_s(so), truth_arr)
+
+
+@pytest.mark.parametrize("algo,n,A,T,multi", [("todescato", 40, 6, 12, True), ("periodic", 32, 5, 12, False)])
+def test_throughput_mode_runs_vs_oracle_loops(algo, n, A, T, multi, monkeypatch):
+    """Throughput mode (config c5): incremental factor + posterior AND device-built Voronoi cells + device finishing --
+    no host Qhull, one D2H per iteration -- still reproduces the oracle loops on tie-free inputs."""
+    from mfgp_coverage_b200 import simulator as sim
+    monkeypatch.setattr(sim, "INCREMENTAL", True)
+    monkeypatch.setattr(sim, "VORONOI", "clip")
+    xy = synth.grid(n)
+    truth_arr = np.column_stack((xy, synth.truth_function(xy)))
+    hyp = synth.MF_HYP if multi else synth.SF_HYP
+    lat_xy = np.random.default_rng(99).random((9, 2))
+    near = np.argmin(((xy[None, :, :] - lat_xy[:, None, :]) ** 2).sum(axis=2), axis=1)
+    prior_arr = np.column_stack((lat_xy, 0.8 * truth_arr[near, 2] + 0.02))
+    seed = 21
+    pos0 = synth.agents(A, seed)
+    lo, ao, so = getattr(oalg, algo)(0, T, A, pos0.copy(), truth_arr, 0.1, prior_arr, hyp, random.Random(seed),
+                                     np.random.default_rng(seed))
+    lg, ag, sg = getattr(sim, algo)(algo, 0, T, A, pos0.copy(), truth_arr, 0.1, prior_arr, hyp, False, None, True,
+                                    rng=random.Random(seed), noise_rng=np.random.default_rng(seed))
+    to_s = lambda s: np.array([[float(r["Iteration"]), float(r["Agent"]), float(r["X"]), float(r["Y"]), float(r["Sample"])]
+                               for r in s]).reshape(-1, 5)
+    _compare(np.array([r["Loss"] for r in lg]), _agent_array(ag, len(lg), A), to_s(sg),
+             np.array([r["Loss"] for r in lo]), _agent_array(ao, len(lo), A), to_s(so), truth_arr)
