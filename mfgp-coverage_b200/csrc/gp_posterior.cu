@@ -54,6 +54,9 @@ struct PostArgs {
     const double* z;
     double* mu; double* var; double* qout;   // qout (optional): sum of v^2, the variance reduction
     double* Vc; int64_t ldv;
+    int remap_cols;      // > 0 (grid mode, whole columns): CTA b -> column b % remap_cols, y-band b / remap_cols, so the CTAs
+                         // in flight share ONE band of the y-axis tables; the L2-resident set is W + a few MB instead of
+                         // W + all y tables (which together exceed the 126 MB L2 at N = 4096)
     int row_lo;          // > 0: incremental update -- only rows >= row_lo of V are formed and ADDED to mu / var / qout
     DevParams p;
 };
@@ -107,7 +110,9 @@ posterior_kernel(const __grid_constant__ CUtensorMap wmap, PostArgs a) {
     const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + P_STAGES);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int64_t g0 = (int64_t)blockIdx.x * P_BN;
+    const int64_t g0 = (GRID && a.remap_cols > 0)
+                           ? (int64_t)(blockIdx.x % a.remap_cols) * a.ny + (int64_t)(blockIdx.x / a.remap_cols) * P_BN
+                           : (int64_t)blockIdx.x * P_BN;
     const int N = a.NL + a.NH;
     const DevParams& p = a.p;
 
@@ -387,7 +392,9 @@ posterior_update_kernel(const __grid_constant__ CUtensorMap wmap, PostArgs a) {
     const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + P_STAGES);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int64_t g0 = (int64_t)blockIdx.x * U_BN;
+    const int64_t g0 = (GRID && a.remap_cols > 0)
+                           ? (int64_t)(blockIdx.x % a.remap_cols) * a.ny + (int64_t)(blockIdx.x / a.remap_cols) * U_BN
+                           : (int64_t)blockIdx.x * U_BN;
     const int N = a.NL + a.NH;
     const DevParams& p = a.p;
 
@@ -689,7 +696,9 @@ static int posterior_common(PostArgs& a, bool grid, const double* W, int64_t npa
     if (a.row_lo < 0 || a.row_lo >= N) return MFGP_ERR_INVALID;
     CUtensorMap wmap;
     a.npad = (int)npad;
+    const bool whole_cols = grid && a.ny > 0 && a.g_lo % a.ny == 0 && a.G % a.ny == 0;
     if (a.row_lo > 0 && a.Vc == nullptr && npad - a.row_lo / U_BM * U_BM <= 4 * U_BM) {
+        a.remap_cols = (whole_cols && a.ny % U_BN == 0) ? (int)(a.G / a.ny) : 0;
         // few new rows: the 64-row x 256-point tiling keeps the psi regeneration amortised
         int rcu = make_w_tensor_map(&wmap, W, npad, ldw, U_BM);
         if (rcu) return rcu;
@@ -706,6 +715,7 @@ static int posterior_common(PostArgs& a, bool grid, const double* W, int64_t npa
     }
     int rc = make_w_tensor_map(&wmap, W, npad, ldw);
     if (rc) return rc;
+    a.remap_cols = (whole_cols && a.ny % P_BN == 0) ? (int)(a.G / a.ny) : 0;
     const unsigned nblk = (unsigned)((a.G + P_BN - 1) / P_BN);
     if (grid) {
         MFGP_CUDA_CHECK(cudaFuncSetAttribute(posterior_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_BYTES));

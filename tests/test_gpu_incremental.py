@@ -174,4 +174,4 @@ def test_throughput_mode_runs_vs_oracle_loops(algo, n, A, T, multi, monkeypatch)
     to_s = lambda s: np.array([[float(r["Iteration"]), float(r["Agent"]), float(r["X"]), float(r["Y"]), float(r["Sample"])]
                                for r in s]).reshape(-1, 5)
     _compare(np.array([r["Loss"] for r in lg]), _agent_array(ag, len(lg), A), to_s(sg),
-             np.array([r["Loss"] for r in lo]), _agent_array(ao, len(lo), A), to_s(so), truth_arr)
+             np.array([r["Loss"] for r in lo]), _agent_array(ao, len(lo), A), to_s(so), truth_arr, replay_ties=False)
