@@ -16,15 +16,27 @@ namespace mfgp {
 constexpr int CH_THREADS = 128;
 constexpr int CH_COLS = CH_THREADS * 2;
 
+// Device-resident loop state: the host launches a BATCH of (append, arg-max) pairs without synchronising; each pair
+// checks `done` / the threshold on the device, so the greedy loop costs one host round trip per batch, not per pick.
+struct ChoiState {
+    long long n;          // valid rows of the V cache
+    long long picks;      // picks recorded so far (all batches)
+    long long done;       // 1: max var <= threshold or a limit was reached -> remaining launches of the batch are no-ops
+    long long pick;       // grid index to append next (the current first-index arg-max)
+    double val;           // its variance
+};
+
 struct ChoiArgs {
     const double* Xs; int64_t G;
-    double* Vc; int64_t ldv; int n;          // rows [0,n) valid; row n is written
+    double* Vc; int64_t ldv;                 // rows [0, state->n) valid; row state->n is written
     double* var;
-    const long long* pick;                   // device: grid index of the point being appended
+    ChoiState* state;
     DevParams p;
     TieRule tol;                             // arg-max tie rule
     double* q;                               // running sum of v^2 per grid point (variance reduction)
     double* pv; long long* pi;               // per-block argmax candidates of the updated variance
+    double threshold; long long cap; long long max_picks;
+    long long* picks_dev;                    // [max_picks] grid indices in selection order
 };
 
 __global__ void __launch_bounds__(CH_THREADS) choi_append_kernel(ChoiArgs a) {
@@ -33,9 +45,11 @@ __global__ void __launch_bounds__(CH_THREADS) choi_append_kernel(ChoiArgs a) {
     __shared__ double sv[CH_THREADS / 32];
     __shared__ long long si[CH_THREADS / 32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int64_t j = *a.pick;
+    if (a.state->done) return;                    // uniform for the whole grid
+    const int an = (int)a.state->n;
+    const int64_t j = a.state->pick;
     double part = 0.0;
-    for (int n = tid; n < a.n; n += CH_THREADS) {
+    for (int n = tid; n < an; n += CH_THREADS) {
         const double v = a.Vc[(int64_t)n * a.ldv + j];
         l[n] = v;
         part += v * v;
@@ -59,19 +73,19 @@ __global__ void __launch_bounds__(CH_THREADS) choi_append_kernel(ChoiArgs a) {
         if (pair) {
             const double* col = a.Vc + g;
             int n = 0;
-            for (; n + 8 <= a.n; n += 8) {
-                double2 v[8];
+            for (; n + 16 <= an; n += 16) {       // 16 x 16 B in flight per thread: the pass over V is HBM-bound
+                double2 v[16];
 #pragma unroll
-                for (int u = 0; u < 8; u++) v[u] = *reinterpret_cast<const double2*>(col + (int64_t)(n + u) * a.ldv);
+                for (int u = 0; u < 16; u++) v[u] = __ldcs(reinterpret_cast<const double2*>(col + (int64_t)(n + u) * a.ldv));
 #pragma unroll
-                for (int u = 0; u < 8; u++) { s0 += l[n + u] * v[u].x; s1 += l[n + u] * v[u].y; }
+                for (int u = 0; u < 16; u++) { s0 += l[n + u] * v[u].x; s1 += l[n + u] * v[u].y; }
             }
-            for (; n < a.n; n++) {
+            for (; n < an; n++) {
                 const double2 v = *reinterpret_cast<const double2*>(col + (int64_t)n * a.ldv);
                 s0 += l[n] * v.x; s1 += l[n] * v.y;
             }
         } else {
-            for (int n = 0; n < a.n; n++) {
+            for (int n = 0; n < an; n++) {
                 s0 += l[n] * a.Vc[(int64_t)n * a.ldv + g];
                 if (g + 1 < a.G) s1 += l[n] * a.Vc[(int64_t)n * a.ldv + g + 1];
             }
@@ -90,7 +104,7 @@ __global__ void __launch_bounds__(CH_THREADS) choi_append_kernel(ChoiArgs a) {
                     k = kH;
                 }
                 const double v = (k - (c ? s1 : s0)) / d;
-                a.Vc[(int64_t)a.n * a.ldv + gg] = v;
+                a.Vc[(int64_t)an * a.ldv + gg] = v;
                 const double nq = a.q[gg] + v * v;         // var is recomputed from the accumulated reduction, as the
                 a.q[gg] = nq;                              // reference's full predict does (k** - psi beta), never decremented
                 const double nv = p.k0 - nq;
@@ -108,6 +122,27 @@ __global__ void __launch_bounds__(CH_THREADS) choi_append_kernel(ChoiArgs a) {
     }
 }
 
+// One warp: the row just written becomes valid, the block candidates give the next arg-max, and the loop condition of
+// simulator.py:345 (`while max_var > threshold`) is evaluated on the device.
+__global__ void choi_advance_kernel(ChoiArgs a, int nblocks, int first) {
+    ChoiState* st = a.state;
+    if (st->done) return;
+    ArgMax best{0.0, -1};
+    if (first) {            // the arg-max of the incoming variance was computed by cov_argmax into (val, pick)
+        best = ArgMax{st->val, st->pick};
+    } else {
+        for (int i = threadIdx.x; i < nblocks; i += 32) best = argmax_combine(best, ArgMax{a.pv[i], a.pi[i]}, a.tol);
+        best = argmax_warp(best, a.tol);
+    }
+    if (threadIdx.x == 0) {
+        if (!first) st->n += 1;
+        st->val = best.v;
+        st->pick = best.i;
+        if (!(best.v > a.threshold) || st->picks >= a.max_picks || st->n >= a.cap) st->done = 1;
+        else a.picks_dev[st->picks++] = best.i;
+    }
+}
+
 }  // namespace mfgp
 
 using namespace mfgp;
@@ -117,41 +152,49 @@ extern "C" int64_t choi_greedy(const double* Xs, int64_t G, double* Vc, int64_t 
                                int64_t* picks_host,
                                void* work, int64_t work_bytes, void* stream) {
     if (!Xs || !Vc || !var || !q || !p_host || !picks_host || !work || G <= 0 || ldv < G || n0 < 0 || cap < n0) return MFGP_ERR_INVALID;
+    if (max_picks > cap - n0) max_picks = cap - n0;           // the V cache holds cap rows: the caller grows it and resumes
     const int nblocks = (int)((G + CH_COLS - 1) / CH_COLS);
-    const int64_t need = (int64_t)nblocks * 16 + 64 + cov_workspace_bytes(G, 1, 0);
+    const int64_t need = (int64_t)nblocks * 16 + 128 + (max_picks + 1) * 8 + cov_workspace_bytes(G, 1, 0);
     if (work_bytes < need) return MFGP_ERR_INVALID;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     double* pv = static_cast<double*>(work);
     long long* pi = reinterpret_cast<long long*>(pv + nblocks);
-    double* d_val = reinterpret_cast<double*>(pi + nblocks);
-    int64_t* d_idx = reinterpret_cast<int64_t*>(d_val + 1);
-    void* awork = d_idx + 7;
+    ChoiState* state = reinterpret_cast<ChoiState*>(pi + nblocks);
+    long long* picks_dev = reinterpret_cast<long long*>(state + 2);
+    void* awork = picks_dev + max_picks + 1;
     const int64_t awork_bytes = work_bytes - ((char*)awork - (char*)work);
-    const DevParams dp0 = make_dev_params(*p_host);
-    const TieRule tol{dp0.k0, tie_rel > 0.0 ? tie_rel : 0.0};
-    int rc = cov_argmax(var, G, 0, tol.k0, tol.rel, d_val, d_idx, awork, awork_bytes, st);
-    if (rc) return rc;
-    struct { double val; int64_t idx; } h;
     const DevParams dp = make_dev_params(*p_host);
-    int64_t n = n0, picks = 0;
-    static_assert(sizeof(h) == 16, "layout");
+    const TieRule tol{dp.k0, tie_rel > 0.0 ? tie_rel : 0.0};
+    ChoiState h{n0, 0, 0, -1, 0.0};
+    MFGP_CUDA_CHECK(cudaMemcpyAsync(state, &h, sizeof(h), cudaMemcpyHostToDevice, st));
+    int rc = cov_argmax(var, G, 0, tol.k0, tol.rel, &state->val, reinterpret_cast<int64_t*>(&state->pick), awork, awork_bytes, st);
+    if (rc) return rc;
+    ChoiArgs a;
+    a.Xs = Xs; a.G = G; a.Vc = Vc; a.ldv = ldv; a.var = var; a.state = state; a.p = dp; a.tol = tol; a.q = q; a.pv = pv; a.pi = pi;
+    a.threshold = threshold; a.cap = cap; a.max_picks = max_picks; a.picks_dev = picks_dev;
+    choi_advance_kernel<<<1, 32, 0, st>>>(a, nblocks, 1);
+    MFGP_LAUNCH_CHECK();
+    constexpr int BATCH = 16;
+    int64_t n_hi = n0;                // upper bound of state->n known to the host (sizes the shared-memory column)
     while (true) {
-        MFGP_CUDA_CHECK(cudaMemcpyAsync(&h, d_val, 16, cudaMemcpyDeviceToHost, st));
+        for (int b = 0; b < BATCH; b++) {
+            n_hi++;
+            const size_t smem = sizeof(double) * (size_t)n_hi;
+            if (smem > 48 * 1024)
+                MFGP_CUDA_CHECK(cudaFuncSetAttribute(choi_append_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            choi_append_kernel<<<nblocks, CH_THREADS, smem, st>>>(a);
+            MFGP_LAUNCH_CHECK();
+            choi_advance_kernel<<<1, 32, 0, st>>>(a, nblocks, 0);
+            MFGP_LAUNCH_CHECK();
+        }
+        MFGP_CUDA_CHECK(cudaMemcpyAsync(&h, state, sizeof(h), cudaMemcpyDeviceToHost, st));
         MFGP_CUDA_CHECK(cudaStreamSynchronize(st));
-        if (!(h.val > threshold) || picks >= max_picks) break;    // simulator.py:345 `while max_var > threshold`
-        if (n >= cap) return MFGP_ERR_INVALID;                    // V cache exhausted
-        picks_host[picks++] = h.idx;
-        ChoiArgs a;
-        a.Xs = Xs; a.G = G; a.Vc = Vc; a.ldv = ldv; a.n = (int)n; a.var = var;
-        a.pick = reinterpret_cast<const long long*>(d_idx); a.p = dp; a.tol = tol; a.q = q; a.pv = pv; a.pi = pi;
-        const size_t smem = sizeof(double) * (size_t)(n > 0 ? n : 1);
-        if (smem > 48 * 1024)
-            MFGP_CUDA_CHECK(cudaFuncSetAttribute(choi_append_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        choi_append_kernel<<<nblocks, CH_THREADS, smem, st>>>(a);
-        MFGP_LAUNCH_CHECK();
-        argmax_final_kernel<<<1, 32, 0, st>>>(pv, pi, nblocks, tol, d_val, d_idx);
-        MFGP_LAUNCH_CHECK();
-        n++;
+        if (h.done) break;
+        n_hi = h.n;
     }
-    return picks;
+    if (h.picks > 0) {
+        MFGP_CUDA_CHECK(cudaMemcpyAsync(picks_host, picks_dev, sizeof(long long) * h.picks, cudaMemcpyDeviceToHost, st));
+        MFGP_CUDA_CHECK(cudaStreamSynchronize(st));
+    }
+    return h.picks;
 }

@@ -187,7 +187,7 @@ def compute_sample_points(model, x_star, threshold, console=False, return_indice
     q = torch.empty(G, dtype=torch.float64, device=dev)
     _, var = model.predict_device(grid.xy, vcache=Vc if n else None, grid=grid, q_out=q)
     lib = cv.nat.lib()
-    work = torch.empty(int(lib.cov_workspace_bytes(G, 1, 0)) // 8 + (G // 256 + 2) * 2 + 64, dtype=torch.float64,
+    work = torch.empty(int(lib.cov_workspace_bytes(G, 1, 0)) // 8 + (G // 256 + 2) * 2 + 64 + (1 << 15), dtype=torch.float64,
                        device=dev)
     picks = []
     import ctypes
