@@ -35,6 +35,10 @@ WORKLOADS = {
     "c3": (256, 1024, 16, "c3: synthetic 256x256 grid, 1024 MF samples, 16 agents"),
     "c2": (51, 309, 8, "c2-like: 51x51 grid, 309 MF samples, 8 agents"),
 }
+# DRAM bytes (read + write) of ONE posterior_kernel launch on the full c4 grid, from the ncu --set full capture in
+# profiles/r01_posterior_v3_ncu_summary.txt (18.883 GB read + 0.040 GB written); algorithmic minimum 32 G + 8 N^2 = 0.17 GB:
+# W (67 MB used) is re-read from L2 by every CTA and only partly stays resident next to the factor tables.
+POSTERIOR_TRAFFIC_C4_1GPU = 18.883344e9 + 39.72864e6
 DGEMM_PEAK_TFLOPS = 35.41   # cuBLAS DGEMM 8192^3 measured on this pool's B200 (profiles/r01_dgemm_peak.json);
 #                             MEASURED_PEAKS.json carries no FP64 figure.  DMMA issue peak: 37.15 (r01_fp64_pipes.log)
 
@@ -320,7 +324,10 @@ def run_ours(args):
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e},
             "roofline": {"bound": "tensor", "kernel": "posterior_kernel (DMMA fp64)", "achieved": achieved,
                          "peak": DGEMM_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": achieved / DGEMM_PEAK_TFLOPS,
-                         "traffic": None, "kernel_ms": pm, "kernel_share_of_step": pm / ms_dev,
+                         "traffic": POSTERIOR_TRAFFIC_C4_1GPU if (w["name"] == "c4" and world == 1) else None,
+                         "traffic_unit": "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum; the kernel "
+                                         "is FP64-compute bound, algorithmic minimum 0.17 GB)",
+                         "kernel_ms": pm, "kernel_share_of_step": pm / ms_dev,
                          "peak_source": "cuBLAS DGEMM 8192^3 measured on this pool (profiles/r01_dgemm_peak.json); "
                                         "MEASURED_PEAKS.json has no FP64 figure; DMMA issue peak 37.15"},
             "breakdown_ms": {"fit(K+chol+inverse+whiten+tables)": float(np.mean(fit_ms)), "posterior": pm,

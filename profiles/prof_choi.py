@@ -19,6 +19,7 @@ m.updt_info(X_L, y_L, X_H, y_H)
 mu, var = m.predict(xy)
 thr = frac * var.max()
 sim.compute_sample_points(m, xy, thr)          # warm-up (uploads the grid, sizes the caches)
+sim.compute_sample_points(m, xy, 0.8 * thr)    # ... including the allocator blocks of the grown V cache
 torch.cuda.synchronize()
 
 
