@@ -148,6 +148,19 @@ int cov_assign_reduce(const double* xy, const double* w, const double* var, cons
                       uint64_t* member_c, void* work, int64_t work_bytes, void* stream);
 int64_t cov_workspace_bytes(int64_t G, int64_t Ac, int64_t Ap);
 
+/* The same pass for a tensor-product grid stored x-major (point g = ix*ny + iy; every grid of the reference:
+ * distribution.py:337-339) or a whole-column slice of one (grid sharding): G must be a multiple of ny.  Uses the
+ * column-sweep kernel -- a warp owns 32 consecutive iy and walks the columns, each lane accumulates privately for the
+ * cell it is in, no shuffles in the loop -- and returns exactly what cov_assign_reduce returns (sums in a different,
+ * equally fixed order).  No membership output; tie_tol must be finite (nearest-seed cells). */
+int cov_assign_reduce_grid(const double* xy, const double* w, const double* var, const double* f, int64_t G, int64_t ny,
+                           int64_t base_index,
+                           const double* seeds_c, int64_t Ac, const double* poly_xy_c, const int32_t* poly_off_c, int64_t nvert_c,
+                           const double* seeds_p, int64_t Ap, const double* poly_xy_p, const int32_t* poly_off_p, int64_t nvert_p,
+                           double tie_tol, double amax_k0, double amax_rel,
+                           double* cent, double* amax_val, int64_t* amax_idx, double* lossp,
+                           void* work, int64_t work_bytes, void* stream);
+
 /* Bounded Voronoi cells on the device (replaces voronoi_bounded simulator.py:154-191 + poly_area :127-136 where host Qhull
  * is the bottleneck -- replicate sweeps, device-resident loops): cell i = the box [xmin-eps/2, xmax+eps/2] x
  * [ymin-eps/2, ymax+eps/2] clipped by the bisectors with all other seeds, which IS the reference's mirrored-seed diagram

@@ -194,6 +194,7 @@ class CoverageGrid:
             np.ascontiguousarray(f_host, dtype=np.float64).reshape(-1)).to(self.device)
         self._work = None
         self._work_key = None
+        self.use_sweep = True        # tensor-product grids: column-sweep kernel (cov_assign_reduce_grid)
         if axes is None and base_index == 0:
             from ._engine import TensorAxes, detect_tensor_grid
             t = detect_tensor_grid(xy)
@@ -246,6 +247,20 @@ class CoverageGrid:
         words = 1 if words <= 1 else (2 if words == 2 else 4)
         members = torch.zeros((self.G, words), dtype=torch.int64, device=dev) if (want_members and Ac) else None
         work = self._workspace(Ac, Ap)
+        ny = self.axes.ny if self.axes is not None else 0
+        if self.use_sweep and ny and members is None and math.isfinite(tie_tol) and self.G % ny == 0 \
+                and self.base_index % ny == 0:
+            rc = nat.lib().cov_assign_reduce_grid(          # tensor-product grid (or a whole-column shard): column sweep
+                nat.ptr(self.xy), nat.ptr(w), nat.ptr(var), nat.ptr(self.f), self.G, ny, self.base_index,
+                nat.ptr(C.seeds) if C else None, Ac, nat.ptr(C.poly) if C else None, nat.ptr(C.off) if C else None,
+                C.nvert if C else 0,
+                nat.ptr(P.seeds) if P else None, Ap, nat.ptr(P.poly) if P else None, nat.ptr(P.off) if P else None,
+                P.nvert if P else 0,
+                ctypes.c_double(tie_tol), ctypes.c_double(amax_k0), ctypes.c_double(amax_rel), nat.ptr(cent),
+                nat.ptr(amax_val), nat.ptr(amax_idx), nat.ptr(lossp), nat.ptr(work), work.numel() * 8, nat.stream_ptr())
+            nat.check(rc, "cov_assign_reduce_grid")
+            out.update(cent=cent, amax_val=amax_val, amax_idx=amax_idx, lossp=lossp, members=None)
+            return out
         rc = nat.lib().cov_assign_reduce(
             nat.ptr(self.xy), nat.ptr(w), nat.ptr(var), nat.ptr(self.f), self.G, self.base_index,
             nat.ptr(C.seeds) if C else None, Ac, nat.ptr(C.poly) if C else None, nat.ptr(C.off) if C else None,

@@ -84,21 +84,23 @@ struct BucketGrid {
     const uint4* table; int nb; double x0, y0, inv_h;   // bucket (ix, iy) = floor((p - origin) * inv_h), clamped
 };
 
-__global__ void __launch_bounds__(128) cov_build_buckets_kernel(const double* __restrict__ seeds, int A,
-                                                                const double* __restrict__ poly_xy,
-                                                                const int32_t* __restrict__ poly_off, int nb,
-                                                                double tie_tol, uint4* __restrict__ table,
-                                                                double* __restrict__ geom /* x0, y0, inv_h */) {
-    extern __shared__ __align__(16) double bsm[];      // [2*A] seeds + [4*4] bbox partials
-    double* s_seeds = bsm;
-    double* s_box = bsm + 2 * A;
+struct BucketBuild {
+    const double* seeds; int A; const double* poly_xy; const int32_t* poly_off; int nb; uint4* table; double* geom;
+};
+
+// one warp per bucket (lanes stride the seeds); blockIdx.y selects the partition
+__global__ void __launch_bounds__(256) cov_build_buckets_kernel(BucketBuild b0, BucketBuild b1, double tie_tol) {
+    const BucketBuild& b = blockIdx.y == 0 ? b0 : b1;
+    __shared__ unsigned char ids[8][16];
+    __shared__ double s_box[8][4];
     const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
-    for (int i = tid; i < 2 * A; i += 128) s_seeds[i] = seeds[i];
-    const int nvert = poly_off[A];
-    // bounding box of the polygon vertices (every CTA recomputes it: nvert is a few hundred)
+    const int A = b.A, nb = b.nb;
+    if (A == 0 || blockIdx.x * 8 >= nb * nb) return;
+    // bounding box of the polygon vertices (every CTA recomputes it: a few hundred vertices)
+    const int nvert = b.poly_off[A];
     double x0 = DBL_MAX, x1 = -DBL_MAX, y0 = DBL_MAX, y1 = -DBL_MAX;
-    for (int i = tid; i < nvert; i += 128) {
-        const double2 v = reinterpret_cast<const double2*>(poly_xy)[i];
+    for (int i = tid; i < nvert; i += 256) {
+        const double2 v = reinterpret_cast<const double2*>(b.poly_xy)[i];
         x0 = fmin(x0, v.x); x1 = fmax(x1, v.x); y0 = fmin(y0, v.y); y1 = fmax(y1, v.y);
     }
 #pragma unroll
@@ -106,46 +108,61 @@ __global__ void __launch_bounds__(128) cov_build_buckets_kernel(const double* __
         x0 = fmin(x0, __shfl_xor_sync(0xffffffffu, x0, o)); x1 = fmax(x1, __shfl_xor_sync(0xffffffffu, x1, o));
         y0 = fmin(y0, __shfl_xor_sync(0xffffffffu, y0, o)); y1 = fmax(y1, __shfl_xor_sync(0xffffffffu, y1, o));
     }
-    if (lane == 0) { s_box[wib * 4] = x0; s_box[wib * 4 + 1] = x1; s_box[wib * 4 + 2] = y0; s_box[wib * 4 + 3] = y1; }
+    if (lane == 0) { s_box[wib][0] = x0; s_box[wib][1] = x1; s_box[wib][2] = y0; s_box[wib][3] = y1; }
     __syncthreads();
 #pragma unroll
-    for (int w = 0; w < 4; w++) {
-        x0 = fmin(x0, s_box[w * 4]); x1 = fmax(x1, s_box[w * 4 + 1]);
-        y0 = fmin(y0, s_box[w * 4 + 2]); y1 = fmax(y1, s_box[w * 4 + 3]);
+    for (int w = 0; w < 8; w++) {
+        x0 = fmin(x0, s_box[w][0]); x1 = fmax(x1, s_box[w][1]);
+        y0 = fmin(y0, s_box[w][2]); y1 = fmax(y1, s_box[w][3]);
     }
     const double h = fmax(x1 - x0, y1 - y0) / nb;
-    const int bucket = blockIdx.x * 128 + tid;
-    if (bucket == 0) { geom[0] = x0; geom[1] = y0; geom[2] = 1.0 / h; }
+    const int bucket = blockIdx.x * 8 + wib;
+    if (bucket == 0 && lane == 0) { b.geom[0] = x0; b.geom[1] = y0; b.geom[2] = 1.0 / h; }
     if (bucket >= nb * nb) return;
     const int ix = bucket % nb, iy = bucket / nb;
-    unsigned e[4] = {BK_OVERFLOW, 0u, 0u, 0u};
+    uint4 e = make_uint4(BK_OVERFLOW, 0, 0, 0);
     const bool border = ix == 0 || iy == 0 || ix == nb - 1 || iy == nb - 1;
     if (!border && tie_tol < 1e300) {
         const double pad = 1e-6 * h;
         const double bx0 = x0 + ix * h - pad, bx1 = x0 + (ix + 1) * h + pad;
         const double by0 = y0 + iy * h - pad, by1 = y0 + (iy + 1) * h + pad;
         double M = DBL_MAX;
-        for (int c = 0; c < A; c++) {
-            const double sx = s_seeds[2 * c], sy = s_seeds[2 * c + 1];
+        for (int c = lane; c < A; c += 32) {
+            const double sx = b.seeds[2 * c], sy = b.seeds[2 * c + 1];
             const double dxm = fmax(sx - bx0, bx1 - sx), dym = fmax(sy - by0, by1 - sy);
             M = fmin(M, dxm * dxm + dym * dym);
         }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) M = fmin(M, __shfl_xor_sync(0xffffffffu, M, o));
         const double T = M * (1.0 + 1e-9) + tie_tol + 1e-300;
-        unsigned w0 = 0, w1 = 0, w2 = 0, w3 = 0;
         int count = 0;
-        for (int c = 0; c < A; c++) {      // ascending seed order, as the brute-force scan
-            const double sx = s_seeds[2 * c], sy = s_seeds[2 * c + 1];
-            const double dxn = fmax(fmax(bx0 - sx, sx - bx1), 0.0), dyn = fmax(fmax(by0 - sy, sy - by1), 0.0);
-            if (dxn * dxn + dyn * dyn <= T) {
-                const int k = count + 1;                   // byte position in the 16-byte entry
-                const unsigned v = (unsigned)c << (8 * (k & 3));
-                if (k < 4) w0 |= v; else if (k < 8) w1 |= v; else if (k < 12) w2 |= v; else if (k < 16) w3 |= v;
-                count++;
+        for (int c0 = 0; c0 < A; c0 += 32) {      // ascending seed order, as the brute-force scan
+            const int c = c0 + lane;
+            bool is = false;
+            if (c < A) {
+                const double sx = b.seeds[2 * c], sy = b.seeds[2 * c + 1];
+                const double dxn = fmax(fmax(bx0 - sx, sx - bx1), 0.0), dyn = fmax(fmax(by0 - sy, sy - by1), 0.0);
+                is = dxn * dxn + dyn * dyn <= T;
             }
+            const unsigned bal = __ballot_sync(0xffffffffu, is);
+            const int posn = count + __popc(bal & ((1u << lane) - 1u));
+            if (is && posn < BK_MAX) ids[wib][1 + posn] = (unsigned char)c;
+            count += __popc(bal);
         }
-        if (count <= BK_MAX) { e[0] = w0 | (unsigned)count; e[1] = w1; e[2] = w2; e[3] = w3; }
+        __syncwarp();
+        if (count <= BK_MAX) {
+            if (lane == 0) ids[wib][0] = (unsigned char)count;
+            __syncwarp();
+            const unsigned* w = reinterpret_cast<const unsigned*>(ids[wib]);
+            const unsigned keep = count >= 15 ? 0xffffffffu : 0u;
+            (void)keep;
+            // bytes beyond the count are stale: mask them so equal candidate sets give equal entries
+            unsigned ww[4] = {w[0], w[1], w[2], w[3]};
+            for (int k = count + 1; k < 16; k++) ww[k >> 2] &= ~(0xffu << (8 * (k & 3)));
+            e = make_uint4(ww[0], ww[1], ww[2], ww[3]);
+        }
     }
-    table[bucket] = make_uint4(e[0], e[1], e[2], e[3]);
+    if (lane == 0) b.table[bucket] = e;
 }
 
 // nearest-seed cell of one point: CELL_TIE when the runner-up is within tie_tol (the crossings test decides later)
@@ -445,6 +462,279 @@ __global__ void __launch_bounds__(CA_THREADS, CA_BLOCKS_PER_SM) cov_assign_reduc
     }
 }
 
+// ---- column-sweep variant for tensor-product grids --------------------------------------------------------------------
+// Every grid of the reference is `[[x, y] for x in gx for y in gy]` (distribution.py:337-339): point g = ix*ny + iy.  Here a
+// warp owns a BAND of 32 consecutive iy and walks a range of columns ix: lane l always looks at (ix, iy0 + l), so from one
+// iteration to the next a lane moves by one grid step in x and stays inside the same Voronoi cell for ~100 iterations.
+// Each lane therefore accumulates privately in registers, keyed by ITS OWN current cell, with no shuffles at all; when a
+// lane's cell changes it parks its sums as one entry of a per-warp shared-memory queue (slot order: iteration, then lane
+// -- deterministic), and lane 0 later adds the entries to the warp's per-cell slots in queue order.  Points within
+// tie_tol of a bisector go to a second queue and are classified with the reference's crossings test, cooperatively.
+// Loads are 32 consecutive points per warp per iteration (full sectors), the next column's in flight.
+constexpr int SW_THREADS = 256, SW_WARPS = SW_THREADS / 32;
+constexpr int SW_QCAP = 64;          // queue entries per warp and partition
+constexpr int SW_DEPTH = 1;          // columns of loads in flight per lane
+constexpr int SW_CW = 7;             // words per C entry: cell, s0, s1, s2, cnt, max var, arg-max index
+constexpr int SW_PW = 3;             // words per P entry: cell, s0, cnt
+
+struct SweepShape { int ny, ncols, nbands, nseg, cols_per_seg; };
+
+__device__ __forceinline__ void sweep_drain_c(const double* __restrict__ q, int n, double* __restrict__ wacc, bool with_var,
+                                              TieRule tol, int lane) {
+    __syncwarp();
+    if (lane == 0)
+        for (int e = 0; e < n; e++) {
+            const double* r = q + e * SW_CW;
+            const int c = (int)__double_as_longlong(r[0]);
+            slot_add_c(wacc + c * C_SLOTS, r[1], r[2], r[3], (int)__double_as_longlong(r[4]),
+                       ArgMax{r[5], __double_as_longlong(r[6])}, with_var, tol);
+        }
+    __syncwarp();
+}
+__device__ __forceinline__ void sweep_drain_p(const double* __restrict__ q, int n, double* __restrict__ wacc_p, int lane) {
+    __syncwarp();
+    if (lane == 0)
+        for (int e = 0; e < n; e++) {
+            const double* r = q + e * SW_PW;
+            const int c = (int)__double_as_longlong(r[0]);
+            wacc_p[c * P_SLOTS] += r[1];
+            wacc_p[c * P_SLOTS + 1] += (double)__double_as_longlong(r[2]);
+        }
+    __syncwarp();
+}
+
+// tie points of the queue, one at a time, all lanes cooperating: lane tests cells lane, lane+32, ... with the crossings test
+__device__ __noinline__ void sweep_ties(const CovArgs& a, const long long* __restrict__ tq, int n, double* __restrict__ wacc,
+                                        bool is_c, int lane) {
+    const CovPartition& part = is_c ? a.C : a.P;
+    const bool with_var = a.var != nullptr;
+    for (int e = 0; e < n; e++) {
+        const long long g = tq[e];
+        const double2 p = reinterpret_cast<const double2*>(a.xy)[g];
+        for (int c0 = 0; c0 < part.A; c0 += 32) {
+            const int c = c0 + lane;
+            bool in = false;
+            if (c < part.A) {
+                const int o = part.poly_off[c];
+                in = crossings_inside(part.poly_xy + 2 * o, part.poly_off[c + 1] - o, p.x, p.y);
+            }
+            unsigned m = __ballot_sync(0xffffffffu, in);
+            if (lane == 0)
+                while (m) {
+                    const int cc = c0 + __ffs(m) - 1;
+                    m &= m - 1;
+                    if (is_c) {
+                        const double wv = a.w ? a.w[g] : 0.0;
+                        slot_add_c(wacc + cc * C_SLOTS, wv, wv * p.x, wv * p.y, 1,
+                                   ArgMax{with_var ? a.var[g] : 0.0, (long long)(a.base_index + g)}, with_var, a.amax_tol);
+                    } else {
+                        const double dx = p.x - part.seeds[2 * cc], dy = p.y - part.seeds[2 * cc + 1];
+                        wacc[cc * P_SLOTS] += __dmul_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), a.f[g]);
+                        wacc[cc * P_SLOTS + 1] += 1.0;
+                    }
+                }
+        }
+    }
+    __syncwarp();
+}
+
+__global__ void __launch_bounds__(SW_THREADS, 2) cov_sweep_kernel(CovArgs a, SweepShape sh) {
+    extern __shared__ __align__(16) double sm[];
+    const int Ac = a.C.A, Ap = a.P.A;
+    const int stride = Ac * C_SLOTS + Ap * P_SLOTS;
+    double* s_seed_c = sm;                                   // [2 Ac]
+    double* s_seed_p = s_seed_c + 2 * Ac;                    // [2 Ap]
+    double* s_acc = s_seed_p + 2 * Ap;                       // [SW_WARPS][stride]
+    double* s_qc = s_acc + SW_WARPS * stride;                // [SW_WARPS][SW_QCAP][SW_CW]
+    double* s_qp = s_qc + SW_WARPS * SW_QCAP * SW_CW;        // [SW_WARPS][SW_QCAP][SW_PW]
+    long long* s_tq = reinterpret_cast<long long*>(s_qp + SW_WARPS * SW_QCAP * SW_PW);   // [SW_WARPS][2][SW_QCAP]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < 2 * Ac; i += SW_THREADS) s_seed_c[i] = a.C.seeds[i];
+    for (int i = tid; i < 2 * Ap; i += SW_THREADS) s_seed_p[i] = a.P.seeds[i];
+    for (int i = tid; i < SW_WARPS * stride; i += SW_THREADS) s_acc[i] = 0.0;
+    __syncthreads();
+    double* wacc = s_acc + warp * stride;
+    double* wacc_p = wacc + Ac * C_SLOTS;
+    for (int c = lane; c < Ac; c += 32) {
+        wacc[c * C_SLOTS + 4] = -DBL_MAX;
+        reinterpret_cast<long long*>(wacc)[c * C_SLOTS + 5] = -1;
+    }
+    __syncwarp();
+    double* qc = s_qc + warp * SW_QCAP * SW_CW;
+    double* qp = s_qp + warp * SW_QCAP * SW_PW;
+    long long* tqc = s_tq + warp * 2 * SW_QCAP;
+    long long* tqp = tqc + SW_QCAP;
+    const bool with_var = a.var != nullptr;
+    const TieRule tol = a.amax_tol;
+    const double tie_tol = a.tie_tol;
+    BucketGrid bgc{a.buckets_c, a.nb_c, 0.0, 0.0, 0.0}, bgp{a.buckets_p, a.nb_p, 0.0, 0.0, 0.0};
+    if (Ac) { bgc.x0 = a.geom_c[0]; bgc.y0 = a.geom_c[1]; bgc.inv_h = a.geom_c[2]; }
+    if (Ap) { bgp.x0 = a.geom_p[0]; bgp.y0 = a.geom_p[1]; bgp.inv_h = a.geom_p[2]; }
+
+    const int gw = blockIdx.x * SW_WARPS + warp;
+    const int band = gw % sh.nbands, seg = gw / sh.nbands;
+    const int iy = band * 32 + lane;
+    const bool lane_ok = iy < sh.ny && seg < sh.nseg;
+    const int col0 = seg * sh.cols_per_seg, col1 = min(sh.ncols, col0 + sh.cols_per_seg);
+    const unsigned lt_mask = (1u << lane) - 1u;
+
+    int cur_c = CELL_NONE, cur_p = CELL_NONE, c_cnt = 0, p_cnt = 0, qn_c = 0, qn_p = 0, tn_c = 0, tn_p = 0;
+    double c_s0 = 0.0, c_s1 = 0.0, c_s2 = 0.0, p_s0 = 0.0, c_tol = 0.0;
+    ArgMax c_am{0.0, -1};
+
+    // software pipeline: the loads of the next SW_DEPTH columns are in flight while one column is processed
+    // (16 warps x 32 lanes x 40 B x SW_DEPTH ~ 80 KB per SM outstanding: enough to cover the HBM latency)
+    double2 nxy[SW_DEPTH];
+    double nw[SW_DEPTH], nv[SW_DEPTH], nf[SW_DEPTH];
+#pragma unroll
+    for (int d = 0; d < SW_DEPTH; d++) { nxy[d] = make_double2(0.0, 0.0); nw[d] = nv[d] = nf[d] = 0.0; }
+    auto fetch = [&](int col, double2& fxy, double& fw, double& fvv, double& ff) {
+        if (lane_ok && col < col1) {
+            const int64_t g = (int64_t)col * sh.ny + iy;
+            fxy = __ldg(reinterpret_cast<const double2*>(a.xy) + g);
+            if (a.w) fw = __ldg(a.w + g);
+            if (with_var) fvv = __ldg(a.var + g);
+            if (a.f) ff = __ldg(a.f + g);
+        }
+    };
+#pragma unroll
+    for (int d = 0; d < SW_DEPTH; d++) fetch(col0 + d, nxy[d], nw[d], nv[d], nf[d]);
+#pragma unroll 1
+    for (int colb = col0; colb < col1; colb += SW_DEPTH) {        // warp-uniform trip count (seg is uniform per warp)
+#pragma unroll
+      for (int d = 0; d < SW_DEPTH; d++) {
+        const int col = colb + d;
+        if (col >= col1) break;
+        const int64_t g = (int64_t)col * sh.ny + iy;
+        const double x = nxy[d].x, y = nxy[d].y, wv = nw[d], vv = nv[d], fv = nf[d];
+        fetch(col + SW_DEPTH, nxy[d], nw[d], nv[d], nf[d]);
+        if (Ac) {
+            const int cell = lane_ok ? classify_point(bgc, s_seed_c, Ac, x, y, tie_tol) : CELL_NONE;
+            const bool tie = cell == CELL_TIE;
+            const int ncell = tie ? CELL_NONE : cell;
+            const bool chg = ncell != cur_c;
+            const bool psh = chg && cur_c >= 0;
+            const unsigned pm = __ballot_sync(0xffffffffu, psh);
+            if (pm) {
+                if (qn_c + __popc(pm) > SW_QCAP) { sweep_drain_c(qc, qn_c, wacc, with_var, tol, lane); qn_c = 0; }
+                if (psh) {
+                    double* r = qc + (qn_c + __popc(pm & lt_mask)) * SW_CW;
+                    r[0] = __longlong_as_double((long long)cur_c); r[1] = c_s0; r[2] = c_s1; r[3] = c_s2;
+                    r[4] = __longlong_as_double((long long)c_cnt); r[5] = c_am.v; r[6] = __longlong_as_double(c_am.i);
+                }
+                qn_c += __popc(pm);
+            }
+            if (chg) { c_s0 = c_s1 = c_s2 = 0.0; c_cnt = 0; c_am = ArgMax{0.0, -1}; cur_c = ncell; }
+            if (ncell >= 0) {
+                c_s0 += wv; c_s1 += wv * x; c_s2 += wv * y; c_cnt++;
+                if (with_var) {      // == argmax_combine(c_am, {vv, idx}) for an index above c_am.i
+                    if (c_am.i < 0 || vv - c_am.v > c_tol) {
+                        c_am = ArgMax{vv, (long long)(a.base_index + g)};
+                        c_tol = tol.rel > 0.0 ? fmax(tol.rel * (tol.k0 - vv), 0.0) : 0.0;
+                    } else if (vv > c_am.v) {
+                        c_am.v = vv;
+                    }
+                }
+            }
+            const unsigned tm = __ballot_sync(0xffffffffu, tie);
+            if (tm) {
+                if (tn_c + __popc(tm) > SW_QCAP) {
+                    sweep_drain_c(qc, qn_c, wacc, with_var, tol, lane); qn_c = 0;      // keep slot order: queue first
+                    sweep_ties(a, tqc, tn_c, wacc, true, lane); tn_c = 0;
+                }
+                if (tie) tqc[tn_c + __popc(tm & lt_mask)] = g;
+                tn_c += __popc(tm);
+            }
+        }
+        if (Ap) {
+            const int cell = lane_ok ? classify_point(bgp, s_seed_p, Ap, x, y, tie_tol) : CELL_NONE;
+            const bool tie = cell == CELL_TIE;
+            const int ncell = tie ? CELL_NONE : cell;
+            const bool chg = ncell != cur_p;
+            const bool psh = chg && cur_p >= 0;
+            const unsigned pm = __ballot_sync(0xffffffffu, psh);
+            if (pm) {
+                if (qn_p + __popc(pm) > SW_QCAP) { sweep_drain_p(qp, qn_p, wacc_p, lane); qn_p = 0; }
+                if (psh) {
+                    double* r = qp + (qn_p + __popc(pm & lt_mask)) * SW_PW;
+                    r[0] = __longlong_as_double((long long)cur_p); r[1] = p_s0; r[2] = __longlong_as_double((long long)p_cnt);
+                }
+                qn_p += __popc(pm);
+            }
+            if (chg) { p_s0 = 0.0; p_cnt = 0; cur_p = ncell; }
+            if (ncell >= 0) {
+                const double dx = x - s_seed_p[2 * ncell], dy = y - s_seed_p[2 * ncell + 1];
+                p_s0 += __dmul_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), fv);     // simulator.py:215-216
+                p_cnt++;
+            }
+            const unsigned tm = __ballot_sync(0xffffffffu, tie);
+            if (tm) {
+                if (tn_p + __popc(tm) > SW_QCAP) {
+                    sweep_drain_p(qp, qn_p, wacc_p, lane); qn_p = 0;
+                    sweep_ties(a, tqp, tn_p, wacc_p, false, lane); tn_p = 0;
+                }
+                if (tie) tqp[tn_p + __popc(tm & lt_mask)] = g;
+                tn_p += __popc(tm);
+            }
+        }
+      }
+    }
+    // end of the warp's range: parked entries first (queue order), then the lanes' live sums grouped by cell with fixed
+    // butterflies, then the tie points
+    if (Ac) {
+        sweep_drain_c(qc, qn_c, wacc, with_var, tol, lane);
+        unsigned pending = __ballot_sync(0xffffffffu, cur_c >= 0);
+        while (pending) {
+            const int c = __shfl_sync(0xffffffffu, cur_c, __ffs(pending) - 1);
+            const bool mine = cur_c == c;
+            const unsigned who = __ballot_sync(0xffffffffu, mine);
+            const double s0 = warp_sum(mine ? c_s0 : 0.0), s1 = warp_sum(mine ? c_s1 : 0.0), s2 = warp_sum(mine ? c_s2 : 0.0);
+            const int cnt = __reduce_add_sync(0xffffffffu, mine ? c_cnt : 0);
+            ArgMax am = mine ? c_am : ArgMax{0.0, -1};
+            if (with_var) am = argmax_warp_band(am, tol);
+            if (lane == 0) slot_add_c(wacc + c * C_SLOTS, s0, s1, s2, cnt, am, with_var, tol);
+            pending &= ~who;
+        }
+        if (tn_c) sweep_ties(a, tqc, tn_c, wacc, true, lane);
+    }
+    if (Ap) {
+        sweep_drain_p(qp, qn_p, wacc_p, lane);
+        unsigned pending = __ballot_sync(0xffffffffu, cur_p >= 0);
+        while (pending) {
+            const int c = __shfl_sync(0xffffffffu, cur_p, __ffs(pending) - 1);
+            const bool mine = cur_p == c;
+            const unsigned who = __ballot_sync(0xffffffffu, mine);
+            const double s0 = warp_sum(mine ? p_s0 : 0.0);
+            const int cnt = __reduce_add_sync(0xffffffffu, mine ? p_cnt : 0);
+            if (lane == 0) { wacc_p[c * P_SLOTS] += s0; wacc_p[c * P_SLOTS + 1] += (double)cnt; }
+            pending &= ~who;
+        }
+        if (tn_p) sweep_ties(a, tqp, tn_p, wacc_p, false, lane);
+    }
+    __syncthreads();
+    double* out = a.partials + blockIdx.x;       // [slot][block], as cov_assign_reduce_kernel
+    const int64_t pld = gridDim.x;
+    for (int i = tid; i < Ac * C_SLOTS; i += SW_THREADS) {
+        const int slot = i % C_SLOTS;
+        if (slot < 4) {
+            double s = 0.0;
+            for (int w = 0; w < SW_WARPS; w++) s += s_acc[w * stride + i];
+            out[i * pld] = s;
+        } else if (slot == 4) {
+            ArgMax best{0.0, -1};
+            for (int w = 0; w < SW_WARPS; w++)
+                best = argmax_combine(best, ArgMax{s_acc[w * stride + i], reinterpret_cast<const long long*>(s_acc)[w * stride + i + 1]}, tol);
+            out[i * pld] = best.v;
+            reinterpret_cast<long long*>(out)[(i + 1) * pld] = best.i;
+        }
+    }
+    for (int i = tid; i < Ap * P_SLOTS; i += SW_THREADS) {
+        double s = 0.0;
+        for (int w = 0; w < SW_WARPS; w++) s += s_acc[w * stride + Ac * C_SLOTS + i];
+        out[(Ac * C_SLOTS + i) * pld] = s;
+    }
+}
+
 // One warp per output: lanes stride over the block partials in block order, then a fixed butterfly.
 __global__ void __launch_bounds__(256) cov_finalize_kernel(const double* __restrict__ partials, int nblocks, int Ac, int Ap,
                                                            TieRule amax_tol, double* __restrict__ cent, double* __restrict__ amax_val,
@@ -484,6 +774,7 @@ __global__ void __launch_bounds__(256) cov_finalize_kernel(const double* __restr
 }
 
 constexpr int COV_BUCKETS_MAX = 128;
+constexpr int COV_MAX_BLOCKS = 148 * 6;     // upper bound of the CTA count of any assignment kernel (sizes the partials)
 // bucket grid side: about eight buckets per mean cell spacing, so most buckets lie inside ONE cell
 inline int cov_bucket_side(int64_t A) {
     int nb = 16;
@@ -507,18 +798,18 @@ using namespace mfgp;
 
 extern "C" int64_t cov_workspace_bytes(int64_t G, int64_t Ac, int64_t Ap) {
     const int64_t stride = Ac * C_SLOTS + Ap * P_SLOTS;
-    const int64_t nb = cov_blocks(G) > cov_chunk_blocks(G) ? cov_blocks(G) : cov_chunk_blocks(G);
+    const int64_t nb = COV_MAX_BLOCKS;
     int64_t a = nb * stride * 8;
     int64_t b = nb * 16;
     return (a > b ? a : b) + 256 + 2 * ((int64_t)COV_BUCKETS_MAX * COV_BUCKETS_MAX * 16 + 64);
 }
 
-extern "C" int cov_assign_reduce(const double* xy, const double* w, const double* var, const double* f, int64_t G,
+static int cov_assign_reduce_impl(const double* xy, const double* w, const double* var, const double* f, int64_t G,
                                  int64_t base_index, const double* seeds_c, int64_t Ac, const double* poly_xy_c,
                                  const int32_t* poly_off_c, int64_t nvert_c, const double* seeds_p, int64_t Ap,
                                  const double* poly_xy_p, const int32_t* poly_off_p, int64_t nvert_p, double tie_tol, double amax_k0, double amax_rel, double* cent, double* amax_val,
                                  int64_t* amax_idx, double* lossp, uint64_t* member_c, void* work, int64_t work_bytes,
-                                 void* stream) {
+                                 void* stream, int64_t ny) {
     if (!xy || G <= 0 || Ac < 0 || Ap < 0 || Ac + Ap == 0 || Ac > COV_MAX_CELLS || Ap > COV_MAX_CELLS) return MFGP_ERR_INVALID;
     if (Ac && (!seeds_c || !poly_xy_c || !poly_off_c)) return MFGP_ERR_INVALID;
     if (Ap && (!seeds_p || !poly_xy_p || !poly_off_p || !f)) return MFGP_ERR_INVALID;
@@ -533,7 +824,7 @@ extern "C" int cov_assign_reduce(const double* xy, const double* w, const double
     a.tie_tol = tie_tol; a.amax_tol = TieRule{amax_k0, amax_rel > 0.0 ? amax_rel : 0.0}; a.member_c = member_c; a.partials = static_cast<double*>(work);
     const int stride = (int)(Ac * C_SLOTS + Ap * P_SLOTS);
     {   // candidate bucket tables live behind the block partials in the workspace
-        const int64_t nbmax = cov_blocks(G) > cov_chunk_blocks(G) ? cov_blocks(G) : cov_chunk_blocks(G);
+        const int64_t nbmax = COV_MAX_BLOCKS;
         const int64_t pa = nbmax * stride * 8, pb = nbmax * 16;
         char* base = static_cast<char*>(work) + (((pa > pb ? pa : pb) + 255) / 256) * 256;
         const int64_t tbytes = (int64_t)COV_BUCKETS_MAX * COV_BUCKETS_MAX * 16;
@@ -543,15 +834,32 @@ extern "C" int cov_assign_reduce(const double* xy, const double* w, const double
         a.geom_p = reinterpret_cast<const double*>(base + 2 * tbytes + 64);
         a.nb_c = cov_bucket_side(Ac);
         a.nb_p = cov_bucket_side(Ap);
-        if (Ac) {
-            cov_build_buckets_kernel<<<(a.nb_c * a.nb_c + 127) / 128, 128, (2 * Ac + 16) * sizeof(double), st>>>(seeds_c, (int)Ac, poly_xy_c, poly_off_c, a.nb_c, tie_tol,
-                                                                             const_cast<uint4*>(a.buckets_c), const_cast<double*>(a.geom_c));
+        BucketBuild bc{seeds_c, (int)Ac, poly_xy_c, poly_off_c, a.nb_c, const_cast<uint4*>(a.buckets_c), const_cast<double*>(a.geom_c)};
+        BucketBuild bp{seeds_p, (int)Ap, poly_xy_p, poly_off_p, a.nb_p, const_cast<uint4*>(a.buckets_p), const_cast<double*>(a.geom_p)};
+        const int nbm = a.nb_c > a.nb_p ? a.nb_c : a.nb_p;
+        cov_build_buckets_kernel<<<dim3((unsigned)((nbm * nbm + 7) / 8), 2), 256, 0, st>>>(bc, bp, tie_tol);
+        MFGP_LAUNCH_CHECK();
+    }
+    const int nfin = (int)(Ac * 5 + Ap * 2);
+    if (ny > 0 && G % ny == 0 && member_c == nullptr && tie_tol < 1e300 && G / ny < (1 << 30)) {
+        // tensor-product grid, nearest-seed cells: column sweep (lane-private accumulation, no shuffles in the loop)
+        SweepShape sh;
+        sh.ny = (int)ny; sh.ncols = (int)(G / ny); sh.nbands = (int)((ny + 31) / 32);
+        int nseg = (148 * 16 + sh.nbands - 1) / sh.nbands;                  // ~16 warps per SM: one resident wave
+        if (nseg > sh.ncols) nseg = sh.ncols;
+        sh.cols_per_seg = (sh.ncols + nseg - 1) / nseg;
+        sh.nseg = (sh.ncols + sh.cols_per_seg - 1) / sh.cols_per_seg;
+        const int64_t nwarps = (int64_t)sh.nbands * sh.nseg;
+        const int sblocks = (int)((nwarps + SW_WARPS - 1) / SW_WARPS);
+        const size_t ssmem = sizeof(double) * (2 * Ac + 2 * Ap + (size_t)SW_WARPS * stride + (size_t)SW_WARPS * SW_QCAP * (SW_CW + SW_PW)) +
+                             sizeof(long long) * SW_WARPS * 2 * SW_QCAP;
+        if (ssmem <= 200 * 1024 && sblocks <= COV_MAX_BLOCKS && sh.nbands <= 148 * 16) {
+            MFGP_CUDA_CHECK(cudaFuncSetAttribute(cov_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssmem));
+            cov_sweep_kernel<<<sblocks, SW_THREADS, ssmem, st>>>(a, sh);
             MFGP_LAUNCH_CHECK();
-        }
-        if (Ap) {
-            cov_build_buckets_kernel<<<(a.nb_p * a.nb_p + 127) / 128, 128, (2 * Ap + 16) * sizeof(double), st>>>(seeds_p, (int)Ap, poly_xy_p, poly_off_p, a.nb_p, tie_tol,
-                                                                             const_cast<uint4*>(a.buckets_p), const_cast<double*>(a.geom_p));
+            cov_finalize_kernel<<<(nfin + 7) / 8, 256, 0, st>>>(a.partials, sblocks, (int)Ac, (int)Ap, a.amax_tol, cent, amax_val, amax_idx, lossp);
             MFGP_LAUNCH_CHECK();
+            return MFGP_OK;
         }
     }
     const size_t smem = sizeof(double) * (2 * Ac + 2 * Ap + 2 * (size_t)nvc + 2 * (size_t)nvp + (size_t)CA_WARPS * stride) +
@@ -570,10 +878,32 @@ extern "C" int cov_assign_reduce(const double* xy, const double* w, const double
     else if (words == 2) rc = launch(cov_assign_reduce_kernel<2>);
     else rc = launch(cov_assign_reduce_kernel<4>);
     if (rc) return rc;
-    const int nfin = (int)(Ac * 5 + Ap * 2);
     cov_finalize_kernel<<<(nfin + 7) / 8, 256, 0, st>>>(a.partials, nblocks, (int)Ac, (int)Ap, a.amax_tol, cent, amax_val, amax_idx, lossp);
     MFGP_LAUNCH_CHECK();
     return MFGP_OK;
+}
+
+extern "C" int cov_assign_reduce(const double* xy, const double* w, const double* var, const double* f, int64_t G,
+                                 int64_t base_index, const double* seeds_c, int64_t Ac, const double* poly_xy_c,
+                                 const int32_t* poly_off_c, int64_t nvert_c, const double* seeds_p, int64_t Ap,
+                                 const double* poly_xy_p, const int32_t* poly_off_p, int64_t nvert_p, double tie_tol, double amax_k0,
+                                 double amax_rel, double* cent, double* amax_val, int64_t* amax_idx, double* lossp,
+                                 uint64_t* member_c, void* work, int64_t work_bytes, void* stream) {
+    return cov_assign_reduce_impl(xy, w, var, f, G, base_index, seeds_c, Ac, poly_xy_c, poly_off_c, nvert_c, seeds_p, Ap, poly_xy_p,
+                                  poly_off_p, nvert_p, tie_tol, amax_k0, amax_rel, cent, amax_val, amax_idx, lossp, member_c, work,
+                                  work_bytes, stream, 0);
+}
+
+extern "C" int cov_assign_reduce_grid(const double* xy, const double* w, const double* var, const double* f, int64_t G, int64_t ny,
+                                      int64_t base_index, const double* seeds_c, int64_t Ac, const double* poly_xy_c,
+                                      const int32_t* poly_off_c, int64_t nvert_c, const double* seeds_p, int64_t Ap,
+                                      const double* poly_xy_p, const int32_t* poly_off_p, int64_t nvert_p, double tie_tol,
+                                      double amax_k0, double amax_rel, double* cent, double* amax_val, int64_t* amax_idx,
+                                      double* lossp, void* work, int64_t work_bytes, void* stream) {
+    if (ny <= 0 || G % ny) return MFGP_ERR_INVALID;
+    return cov_assign_reduce_impl(xy, w, var, f, G, base_index, seeds_c, Ac, poly_xy_c, poly_off_c, nvert_c, seeds_p, Ap, poly_xy_p,
+                                  poly_off_p, nvert_p, tie_tol, amax_k0, amax_rel, cent, amax_val, amax_idx, lossp, nullptr, work,
+                                  work_bytes, stream, ny);
 }
 
 extern "C" int cov_argmax(const double* v, int64_t G, int64_t base_index, double k0, double rel, double* out_val,

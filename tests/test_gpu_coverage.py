@@ -125,3 +125,38 @@ def test_coverage_step_with_device_voronoi(monkeypatch):
     assert np.max(np.abs(cent - ocov.compute_centroids(olv, xy, mu.reshape(-1, 1)))) <= 1e-9
     _, mv_o, idx_o = ocov.compute_max_var(olv, truth, var)
     assert np.array_equal(idx, idx_o) and np.array_equal(mv, mv_o.reshape(-1))
+
+
+@pytest.mark.parametrize("n,A,seed,on_grid", [(51, 8, 2, True), (101, 64, 5, False), (64, 16, 6, True), (130, 200, 9, False),
+                                              (33, 5, 10, True)])
+def test_sweep_and_generic_kernels_agree(n, A, seed, on_grid):
+    """Tensor-product grids take the column-sweep kernel (cov_assign_reduce_grid), arbitrary point lists the generic one
+    (cov_assign_reduce): both must give the oracle's per-cell sums (1e-9) and the same arg-max indices / counts exactly."""
+    import torch
+    from mfgp_coverage_b200 import _coverage as cv
+    from mfgp_coverage_b200 import simulator as sim
+    xy, f, truth, seeds = _setup(n, A, seed, on_grid)
+    rng = np.random.default_rng(seed)
+    mu = f + 0.1 * rng.standard_normal(f.size)
+    var = rng.random(f.size)
+    pos = seeds
+    cen = synth.agents(A, seed + 50)
+    bbox = ocov.bounding_box_of(xy)
+    lv, pv = sim.voronoi_bounded(cen, bbox), sim.voronoi_bounded(pos, bbox)
+    res = {}
+    for sweep in (True, False):
+        g = cv.CoverageGrid(xy, f)
+        assert g.axes is not None
+        g.use_sweep = sweep
+        r = g.assign_reduce(lv, pv, w=torch.from_numpy(mu).cuda(), var=torch.from_numpy(var).cuda())
+        res[sweep] = {k: v.cpu().numpy() for k, v in r.items() if v is not None}
+    a, b = res[True], res[False]
+    assert np.array_equal(a["amax_idx"], b["amax_idx"]) and np.array_equal(a["amax_val"], b["amax_val"])
+    assert np.array_equal(a["cent"][:, 3], b["cent"][:, 3]) and np.array_equal(a["lossp"][:, 1], b["lossp"][:, 1])   # counts
+    assert np.max(np.abs(a["cent"] - b["cent"])) <= 1e-9 * max(1.0, np.max(np.abs(b["cent"])))
+    assert np.max(np.abs(a["lossp"] - b["lossp"])) <= 1e-9 * max(1.0, np.max(np.abs(b["lossp"])))
+    olv, opv = ocov.voronoi_bounded(cen, bbox), ocov.voronoi_bounded(pos, bbox)
+    loss = cv.loss_from_partials(a["lossp"], pv.areas())
+    assert abs(loss - ocov.compute_loss(opv, truth)) <= 1e-9 * abs(loss)
+    _, mv_o, idx_o = ocov.compute_max_var(olv, truth, var)
+    assert np.array_equal(a["amax_idx"], idx_o)
