@@ -172,11 +172,12 @@ int cov_voronoi_clip(const double* seeds, int64_t A, double xmin, double xmax, d
 
 /* O(A) finishing of cov_assign_reduce's partial sums with the reference's arithmetic (simulator.py:215-219, :256-271):
  * out[0] = loss, out[1+2i], out[2+2i] = centroid i clamped to [xmin,xmax] x [ymin,ymax], out[1+2Ac+i] = max variance of
- * cell i, out[1+3Ac+i] = its arg-max grid index as a double (-1: empty cell).  One D2H copy brings a whole iteration's
- * result back. */
+ * cell i, out[1+3Ac+i] = its arg-max grid index as a double (-1: empty cell), out[1+4Ac .. 3+4Ac] = the values of up
+ * to three device int32 flags (may be NULL: e.g. mfgp_cholesky's `info`, cov_voronoi_clip's `flag`), so ONE D2H copy of
+ * 4 + 4 Ac doubles brings a whole iteration's result and its error state back. */
 int cov_finish(const double* cent, const double* areas_c, int64_t Ac, const double* lossp, const double* areas_p, int64_t Ap,
                const double* amax_val, const int64_t* amax_idx, double xmin, double xmax, double ymin, double ymax,
-               double* out, void* stream);
+               const int32_t* flag0, const int32_t* flag1, const int32_t* flag2, double* out, void* stream);
 
 /* Global first-index argmax of v[G] (np.argmax at simulator.py:352): out_val[1], out_idx[1]. */
 int cov_argmax(const double* v, int64_t G, int64_t base_index, double k0, double rel, double* out_val, int64_t* out_idx,

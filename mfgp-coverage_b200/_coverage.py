@@ -88,9 +88,13 @@ class ClippedVoronoi:
     BoundedVoronoi up to ~1e-13 in the vertices, no host Qhull call and nothing to upload but the seeds.  Host views
     (`vertices`, `filtered_regions`, `areas()`) are fetched lazily, only if somebody asks."""
 
-    def __init__(self, points, bounding_box, device=None):
-        nat.require_cuda()
-        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    def __init__(self, points, bounding_box, device=None, reuse=None):
+        """`reuse`: a ClippedVoronoi of an earlier iteration whose device buffers may be overwritten (same cell count)."""
+        if reuse is not None:
+            self.device = reuse.device
+        else:
+            nat.require_cuda()
+            self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         points = np.asarray(points, dtype=np.float64)
         bb = np.asarray(bounding_box, dtype=np.float64)
         c = np.ascontiguousarray(points[in_box(points, bb), :])
@@ -100,11 +104,16 @@ class ClippedVoronoi:
         self.seeds_inside = bool(np.all((c[:, 0] >= bb[0]) & (c[:, 0] <= bb[1]) & (c[:, 1] >= bb[2]) & (c[:, 1] <= bb[3])))
         self.nvert = 7 * self.A + 16                       # capacity (planar bound ~6A + corners); actual count = off[A]
         f64 = dict(dtype=torch.float64, device=self.device)
-        self.seeds = torch.from_numpy(c.reshape(-1)).to(self.device)
-        self.poly = torch.empty(2 * self.nvert, **f64)
-        self.off = torch.empty(self.A + 2, dtype=torch.int32, device=self.device)
-        self.dev_areas = torch.empty(max(self.A, 1), **f64)
-        self.flag = torch.empty(1, dtype=torch.int32, device=self.device)
+        if reuse is not None and reuse.A == self.A:
+            self.seeds, self.poly, self.off, self.dev_areas, self.flag = \
+                reuse.seeds, reuse.poly, reuse.off, reuse.dev_areas, reuse.flag
+            self.seeds.copy_(torch.from_numpy(c.reshape(-1)))
+        else:
+            self.seeds = torch.from_numpy(c.reshape(-1)).to(self.device)
+            self.poly = torch.empty(2 * self.nvert, **f64)
+            self.off = torch.empty(self.A + 2, dtype=torch.int32, device=self.device)
+            self.dev_areas = torch.empty(max(self.A, 1), **f64)
+            self.flag = torch.empty(1, dtype=torch.int32, device=self.device)
         if self.A:
             nat.check(nat.lib().cov_voronoi_clip(nat.ptr(self.seeds), self.A, bb[0], bb[1], bb[2], bb[3], EPS,
                                                  nat.ptr(self.poly), nat.ptr(self.off), self.nvert, nat.ptr(self.dev_areas),
@@ -273,17 +282,23 @@ class CoverageGrid:
         out.update(cent=cent, amax_val=amax_val, amax_idx=amax_idx, lossp=lossp, members=members)
         return out
 
-    def finish(self, res, lloyd_vor, loss_vor, bbox):
+    def finish(self, res, lloyd_vor, loss_vor, bbox, info=None):
         """Device finishing of an assign_reduce result for DEVICE-resident partitions (ClippedVoronoi): returns
-        (loss, centroids[Ac,2], max_var[Ac], argmax_idx[Ac]) with ONE device->host copy (cov_finish)."""
+        (loss, centroids[Ac,2], max_var[Ac], argmax_idx[Ac]) with ONE device->host copy (cov_finish), which also carries
+        the clip-capacity flags and (`info`: device int32, e.g. the Cholesky status) the caller's error state."""
         Ac = len(lloyd_vor) if lloyd_vor is not None else 0
         Ap = len(loss_vor) if loss_vor is not None else 0
-        out = torch.empty(1 + 4 * max(Ac, 1), dtype=torch.float64, device=self.device)
+        out = torch.empty(4 + 4 * max(Ac, 1), dtype=torch.float64, device=self.device)
         nat.check(nat.lib().cov_finish(nat.ptr(res["cent"]), nat.ptr(lloyd_vor.dev_areas) if Ac else None, Ac,
                                        nat.ptr(res["lossp"]), nat.ptr(loss_vor.dev_areas) if Ap else None, Ap,
                                        nat.ptr(res["amax_val"]), nat.ptr(res["amax_idx"]), bbox[0], bbox[1], bbox[2], bbox[3],
-                                       nat.ptr(out), nat.stream_ptr()), "cov_finish")
+                                       nat.ptr(info), nat.ptr(lloyd_vor.flag) if Ac else None,
+                                       nat.ptr(loss_vor.flag) if Ap else None, nat.ptr(out), nat.stream_ptr()), "cov_finish")
         h = out.cpu().numpy()
+        if h[1 + 4 * Ac] != 0:
+            raise np.linalg.LinAlgError(f"Matrix is not positive definite (pivot {int(h[1 + 4 * Ac]) - 1})")
+        if h[2 + 4 * Ac] != 0 or h[3 + 4 * Ac] != 0:
+            raise RuntimeError("cov_voronoi_clip: polygon capacity exceeded")
         return float(h[0]), h[1:1 + 2 * Ac].reshape(Ac, 2).copy(), h[1 + 2 * Ac:1 + 3 * Ac].copy(), \
             h[1 + 3 * Ac:1 + 4 * Ac].astype(np.int64)
 

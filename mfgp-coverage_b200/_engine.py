@@ -63,6 +63,7 @@ class DeviceGP:
         # incremental mode: appended samples border the standing factor instead of a from-scratch
         # refit, and a posterior that was computed into the same (mu, var) buffers is updated with the new rows only
         self.incremental = False
+        self.lazy_check = False       # True: the caller reads `info` itself (cov_finish carries it home): no sync per fit
         self.epoch = 0                # bumped by every FULL refactor: standing posteriors become stale
         self._post = None             # (buffer key, epoch, N covered)
 
@@ -172,7 +173,9 @@ class DeviceGP:
         self._tab = (axes, self.fit_id, TLx, TLy, THx, THy, ldt, buf)
         return self._tab[2:]
 
-    def check_factor(self):
+    def check_factor(self, force=False):
+        if self.lazy_check and not force:
+            return
         info = int(self.info.item())
         if info != 0:
             raise np.linalg.LinAlgError(f"Matrix is not positive definite (pivot {info - 1})")
@@ -266,5 +269,6 @@ class DeviceGP:
         other.info = self.info.clone()
         other.fit_id = self.fit_id
         other.incremental = self.incremental
+        other.lazy_check = self.lazy_check
         other.epoch = self.epoch
         return other

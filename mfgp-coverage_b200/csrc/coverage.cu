@@ -154,8 +154,6 @@ __global__ void __launch_bounds__(256) cov_build_buckets_kernel(BucketBuild b0, 
             if (lane == 0) ids[wib][0] = (unsigned char)count;
             __syncwarp();
             const unsigned* w = reinterpret_cast<const unsigned*>(ids[wib]);
-            const unsigned keep = count >= 15 ? 0xffffffffu : 0u;
-            (void)keep;
             // bytes beyond the count are stale: mask them so equal candidate sets give equal entries
             unsigned ww[4] = {w[0], w[1], w[2], w[3]};
             for (int k = count + 1; k < 16; k++) ww[k >> 2] &= ~(0xffu << (8 * (k & 3)));
@@ -1008,9 +1006,13 @@ __global__ void __launch_bounds__(256) cov_voronoi_clip_kernel(const double* __r
 __global__ void cov_finish_kernel(const double* __restrict__ cent, const double* __restrict__ areas_c, int Ac,
                                   const double* __restrict__ lossp, const double* __restrict__ areas_p, int Ap,
                                   const double* __restrict__ amax_val, const int64_t* __restrict__ amax_idx, double xmin,
-                                  double xmax, double ymin, double ymax, double* __restrict__ out) {
+                                  double xmax, double ymin, double ymax, const int32_t* __restrict__ flag0,
+                                  const int32_t* __restrict__ flag1, const int32_t* __restrict__ flag2, double* __restrict__ out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i == 0) {
+        out[1 + 4 * Ac] = flag0 ? (double)*flag0 : 0.0;      // e.g. the Cholesky `info` and the clip-capacity flags: the
+        out[2 + 4 * Ac] = flag1 ? (double)*flag1 : 0.0;      // host learns about a failure without an extra sync
+        out[3 + 4 * Ac] = flag2 ? (double)*flag2 : 0.0;
         double loss = 0.0;
         for (int c = 0; c < Ap; c++) loss += (lossp[2 * c] / lossp[2 * c + 1]) * areas_p[c];     // cell order, like :215-219
         out[0] = Ap ? loss : 0.0;
@@ -1046,12 +1048,13 @@ extern "C" int cov_voronoi_clip(const double* seeds, int64_t A, double xmin, dou
 
 extern "C" int cov_finish(const double* cent, const double* areas_c, int64_t Ac, const double* lossp, const double* areas_p,
                           int64_t Ap, const double* amax_val, const int64_t* amax_idx, double xmin, double xmax, double ymin,
-                          double ymax, double* out, void* stream) {
+                          double ymax, const int32_t* flag0, const int32_t* flag1, const int32_t* flag2, double* out,
+                          void* stream) {
     if (!out || Ac < 0 || Ap < 0 || (Ac && (!cent || !areas_c)) || (Ap && (!lossp || !areas_p))) return MFGP_ERR_INVALID;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int n = (int)(Ac > 1 ? Ac : 1);
     cov_finish_kernel<<<(n + 127) / 128, 128, 0, st>>>(cent, areas_c, (int)Ac, lossp, areas_p, (int)Ap, amax_val, amax_idx, xmin, xmax,
-                                                      ymin, ymax, out);
+                                                      ymin, ymax, flag0, flag1, flag2, out);
     MFGP_LAUNCH_CHECK();
     return MFGP_OK;
 }

@@ -286,13 +286,27 @@ class _Sim:
         f64 = dict(dtype=torch.float64, device=self.grid.device)
         self.mu = torch.empty(self.grid.G, **f64)
         self.var = torch.empty(self.grid.G, **f64)
+        self._clip = [None, None]
+        self._index_of = None
+
+    def index_of(self):
+        if self._index_of is None:
+            self._index_of = _coordinate_index(self.truth_arr) or {}
+        return self._index_of or None
 
     def step(self, model, positions, centroids_t, weights=None):
         """One hot-path iteration: posterior over the grid, then both partitions in one fused pass.
         Returns (loss_t, centroids_t, argmax_var_t, max_var_t, loss_vor, lloyd_vor)."""
         bb = self.bounding_box
-        loss_vor = voronoi_bounded(positions, bb)
-        lloyd_vor = voronoi_bounded(centroids_t, bb)
+        if VORONOI == "clip":        # device-built cells, the two buffer sets of the previous iteration are recycled
+            loss_vor = cv.ClippedVoronoi(positions, bb, reuse=self._clip[0])
+            lloyd_vor = cv.ClippedVoronoi(centroids_t, bb, reuse=self._clip[1])
+            self._clip = [loss_vor, lloyd_vor]
+            if model is not None:
+                model.engine.lazy_check = True       # cov_finish brings the Cholesky status home with the results
+        else:
+            loss_vor = voronoi_bounded(positions, bb)
+            lloyd_vor = voronoi_bounded(centroids_t, bb)
         if model is not None:
             model.predict_device(self.grid.xy, self.mu, self.var, grid=self.grid)
             res = self.grid.assign_reduce(lloyd_vor, loss_vor, w=self.mu, var=self.var,
@@ -300,7 +314,8 @@ class _Sim:
         else:
             res = self.grid.assign_reduce(lloyd_vor, loss_vor, w=weights)
         if isinstance(lloyd_vor, cv.ClippedVoronoi) and isinstance(loss_vor, cv.ClippedVoronoi) and len(loss_vor) and len(lloyd_vor):
-            loss_t, centroids, max_var, idx = self.grid.finish(res, lloyd_vor, loss_vor, bb)     # one D2H per iteration
+            loss_t, centroids, max_var, idx = self.grid.finish(res, lloyd_vor, loss_vor, bb,
+                                                               info=model.engine.info if model is not None else None)
             if model is None:
                 return loss_t, centroids, None, None, loss_vor, lloyd_vor
             if np.any(idx < 0):
@@ -314,7 +329,18 @@ class _Sim:
         return loss_t, centroids, argmax_xy, max_var, loss_vor, lloyd_vor
 
 
-def _take_samples(agents, positions, explore_t, truth_arr, sigma_n, noise_rng, console, centroids_t, iteration):
+def _coordinate_index(truth_arr):
+    """{(x, y): row} for grids without repeated points (else None): the exact-equality lookup of simulator.py:875 in O(1)."""
+    idx = {}
+    for r, (x, y) in enumerate(zip(truth_arr[:, 0].tolist(), truth_arr[:, 1].tolist())):
+        if (x, y) in idx:
+            return None
+        idx[(x, y)] = r
+    return idx
+
+
+def _take_samples(agents, positions, explore_t, truth_arr, sigma_n, noise_rng, console, centroids_t, iteration,
+                  index_of=None):
     """reference simulator.py:698-713 / :868-883 / :1060-1075: exact-coordinate lookup of the truth + N(0, sigma_n)."""
     x_new = np.empty([0, 2])
     y_new = np.empty([0, 1])
@@ -322,7 +348,11 @@ def _take_samples(agents, positions, explore_t, truth_arr, sigma_n, noise_rng, c
     for i in range(agents):
         if explore_t[i] == 1:
             x_sample = positions[i, :]
-            sample_idx = np.logical_and(truth_arr[:, 0] == x_sample[0], truth_arr[:, 1] == x_sample[1])
+            row = index_of.get((float(x_sample[0]), float(x_sample[1]))) if index_of is not None else None
+            if row is not None:
+                sample_idx = [row]
+            else:
+                sample_idx = np.logical_and(truth_arr[:, 0] == x_sample[0], truth_arr[:, 1] == x_sample[1])
             gen = noise_rng if noise_rng is not None else np.random.default_rng()
             y_sample = truth_arr[sample_idx, 2] + gen.normal(loc=0, scale=sigma_n)
             print(f"Robot {i} explored {x_sample} and sampled {y_sample}") if console else None
@@ -452,7 +482,7 @@ def _explore_exploit(kind, title, sim_num, iterations, agents, positions, truth,
     for iteration in range(iterations):
         print(f"\nBegin Iteration {iteration} of Simulation {sim_num} of {title}") if console else None
         x_new, y_new, id_new = _take_samples(agents, positions, explore_t, truth_arr, sigma_n, noise_rng, console,
-                                             centroids_t, iteration)
+                                             centroids_t, iteration, sim.index_of())
         distance = np.sqrt(np.sum((positions - prev_positions) ** 2, axis=1)).reshape(-1, 1)
         if fidelity == "S":
             model.updt(x_new, y_new)

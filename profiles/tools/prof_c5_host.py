@@ -5,6 +5,7 @@ import bench
 from tests import synth
 from mfgp_coverage_b200 import simulator as sim
 sim.INCREMENTAL = True
+sim.VORONOI = 'clip'
 truth_arr, prior_arr = bench.c5_inputs()
 def one(k):
     with contextlib.redirect_stdout(io.StringIO()):
