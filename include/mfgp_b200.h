@@ -120,6 +120,23 @@ int mfgp_posterior_grid_update(int64_t ny, int64_t g_lo, int64_t G, const double
                                int64_t npad, int64_t ldw, const double* z, const mfgp_params* p_host, int64_t row_lo,
                                double* mu, double* var, double* qred, double* Vc, int64_t ldv, void* stream);
 
+/* Factored posterior for whole columns [ix0, ix0+ncols) of a tensor-product grid ux[nx] x uy[ny] (x-major).  Each axis
+ * factor of the separable RBF cross-covariance is an entire function of the grid coordinate; its Chebyshev interpolant of
+ * order rx / ry (per kernel part: L = lofi, H = hifi) on [xlo,xhi] / [ylo,yhi] reproduces the factor tables to rounding
+ * (~5e-15 entrywise at the orders chosen by the host), which turns the G triangular products v = W psi of mfgp_posterior
+ * into ONE product W B with R = ryL*rxL' + ryH*rxH' (~2.5k) columns plus per-column 64x64 Gram matrices: ~4e10 MAC
+ * instead of 8.8e12 at 1 M points / N = 4096, same mean and variance to ~2e-14 k(0).  Nothing of the training covariance
+ * is approximated.  Outputs are flat over the requested columns: mu / var / qred[(ix-ix0)*ny + iy].  ryL, ryH multiples
+ * of 4, ryL + ryH <= 64, every order <= 64; single fidelity: rxL = ryL = 0.  `chunk_cols` columns are processed per
+ * pass (bounds the workspace).  No V cache: callers that need V (choi_greedy) use mfgp_posterior_grid. */
+int mfgp_posterior_grid_factored(const double* ux, int64_t nx, const double* uy, int64_t ny, int64_t ix0, int64_t ncols,
+                                 const double* Xt, int64_t NL, int64_t NH, const double* W, int64_t npad, int64_t ldw,
+                                 const double* z, const mfgp_params* p_host, int64_t rxL, int64_t ryL, int64_t rxH, int64_t ryH,
+                                 double xlo, double xhi, double ylo, double yhi, int64_t chunk_cols,
+                                 double* mu, double* var, double* qred, void* work, int64_t work_bytes, void* stream);
+int64_t mfgp_factored_workspace_bytes(int64_t npad, int64_t ncols, int64_t ny, int64_t rxL, int64_t ryL, int64_t rxH,
+                                      int64_t ryH, int64_t chunk_cols);
+
 /* ---- coverage step: replaces simulator.py in_polygon :105-124, compute_loss :194-228, compute_centroids :231-283,
  *      compute_max_var :286-323, compute_sample_clusters :377-412 ------------------------------------------------ */
 

@@ -13,10 +13,31 @@ import torch
 from . import _native as nat
 
 
+def chebyshev_order(length_scale, lo, hi, centre_lo, centre_hi, tol=5e-15, rmax=64):
+    """Smallest Chebyshev order r (multiple of 4) whose interpolant of u -> exp(-0.5 ((u - c) / l)^2) on [lo, hi] has
+    converged to `tol` (relative size of the last three coefficients) for every centre c in [centre_lo, centre_hi]
+    -- the training coordinates along this axis.  None if rmax does not suffice (short length scale: use the dense path)."""
+    half, mid = 0.5 * (hi - lo), 0.5 * (hi + lo)
+    if not (half > 0.0) or not (length_scale > 0.0):
+        return None
+    centres = np.linspace(min(centre_lo, lo), max(centre_hi, hi), 17)
+    for r in range(8, rmax + 1, 4):
+        j = np.arange(r)
+        nodes = mid + half * np.cos(np.pi * (j + 0.5) / r)
+        f = np.exp(-0.5 * ((nodes[:, None] - centres[None, :]) / length_scale) ** 2)
+        c = (np.cos(np.pi * np.outer(np.arange(r), j + 0.5) / r) @ f) * (2.0 / r)
+        scale = max(float(np.abs(c).max()), 1e-300)
+        if float(np.abs(c[-3:]).max()) <= tol * scale:
+            return r
+    return None
+
+
 class TensorAxes:
     """Axis values of a tensor-product grid `[[x, y] for x in ux for y in uy]` (x-major, distribution.py:337-339)."""
 
     def __init__(self, ux_host, uy_host, device):
+        self.ux_host = np.ascontiguousarray(ux_host, dtype=np.float64)
+        self.uy_host = np.ascontiguousarray(uy_host, dtype=np.float64)
         self.nx, self.ny = int(len(ux_host)), int(len(uy_host))
         self.ux = torch.from_numpy(np.ascontiguousarray(ux_host, dtype=np.float64)).to(device)
         self.uy = torch.from_numpy(np.ascontiguousarray(uy_host, dtype=np.float64)).to(device)
@@ -62,6 +83,11 @@ class DeviceGP:
         self._tab = None              # (axes key, fit_id, TLx, TLy, THx, THy, ldt)
         # incremental mode: appended samples border the standing factor instead of a from-scratch
         # refit, and a posterior that was computed into the same (mu, var) buffers is updated with the new rows only
+        self.use_factored = True      # tensor-product grids: Chebyshev-factored posterior when it is cheaper (gp_factored.cu)
+        self.factored_min_gain = 2.0  # ... i.e. when its MAC count is at least this factor below the dense kernel's
+        self._fplan = None            # (key, plan) of the last factored-posterior plan
+        self._fwork = None
+        self._xrange = None           # (xmin, xmax, ymin, ymax) of the training points, refreshed by fit / append
         self.incremental = False
         self.lazy_check = False       # True: the caller reads `info` itself (cov_finish carries it home): no sync per fit
         self.epoch = 0                # bumped by every FULL refactor: standing posteriors become stale
@@ -243,6 +269,11 @@ class DeviceGP:
                                                     row_lo, nat.ptr(mu), nat.ptr(var), nat.ptr(q_out), None, 0,
                                                     nat.stream_ptr()), "mfgp_posterior_update")
             return mu, var
+        if axes is not None and self.N > 0 and vcache is None and self.use_factored:
+            plan = self._factored_plan(axes, int(g_lo), G)
+            if plan is not None:
+                self._posterior_factored(axes, plan, mu, var, q_out)
+                return mu, var
         if axes is not None and self.N > 0:
             TLx, TLy, THx, THy, ldt, _ = self.grid_tables(axes)
             nat.check(lib.mfgp_posterior_grid(axes.ny, int(g_lo), G, nat.ptr(TLx), nat.ptr(TLy), nat.ptr(THx),
@@ -257,6 +288,63 @@ class DeviceGP:
                   "mfgp_posterior")
         return mu, var
 
+    # -- factored posterior on tensor-product grids (gp_factored.cu) ---------------------------------------------------------
+    def _training_range(self):
+        if self._xrange is None or self._xrange[0] != self.N:
+            xt = self.Xt[:self.N]
+            lo, hi = xt.min(dim=0).values.tolist(), xt.max(dim=0).values.tolist()        # one small D2H per (re)fit
+            self._xrange = (self.N, lo[0], hi[0], lo[1], hi[1])
+        return self._xrange[1:]
+
+    def _factored_plan(self, axes, g_lo, G):
+        """Chebyshev orders + cost model.  None: keep the dense kernel (range is not whole columns, orders too large for
+        the 64-term budget, or the dense triangular products are cheaper -- small grids)."""
+        ny = axes.ny
+        if ny < 2 or axes.nx < 2 or g_lo % ny or G % ny:
+            return None
+        p = self.params
+        key = (id(axes), g_lo, G, self.npad, self.N, p["l_L"], p["l_H"], p["multi"], self.factored_min_gain)
+        if self._fplan is not None and self._fplan[0] == key:
+            return self._fplan[1]
+        xlo, xhi = float(axes.ux_host.min()), float(axes.ux_host.max())
+        ylo, yhi = float(axes.uy_host.min()), float(axes.uy_host.max())
+        txlo, txhi, tylo, tyhi = self._training_range()
+        plan = None
+        rxH = chebyshev_order(p["l_H"], xlo, xhi, txlo, txhi)
+        ryH = chebyshev_order(p["l_H"], ylo, yhi, tylo, tyhi)
+        rxL = ryL = 0
+        ok = rxH is not None and ryH is not None
+        if ok and p["multi"]:
+            rxL = chebyshev_order(p["l_L"], xlo, xhi, txlo, txhi)
+            ryL = chebyshev_order(p["l_L"], ylo, yhi, tylo, tyhi)
+            ok = rxL is not None and ryL is not None
+        if ok and ryL + ryH <= 64:
+            ncols = G // ny
+            kL, kH = -(-rxL // 16) * 16, -(-rxH // 16) * 16
+            R = ryL * kL + ryH * kH
+            N = self.npad
+            dense = 0.5 * G * N * N
+            fact = 0.5 * N * N * R + ncols * N * R + ncols * N * 64 * 64 + G * 64 * 64
+            if fact * self.factored_min_gain < dense:
+                chunk = max(64, min(-(-ncols // 64) * 64, ((1 << 28) // max(N * (ryL + ryH), 1)) // 64 * 64))   # <= 2 GiB of Y'
+                plan = dict(rxL=rxL, ryL=ryL, rxH=rxH, ryH=ryH, xlo=xlo, xhi=xhi, ylo=ylo, yhi=yhi, ix0=g_lo // ny,
+                            ncols=ncols, chunk=chunk, macs=fact, dense_macs=dense)
+        self._fplan = (key, plan)
+        return plan
+
+    def _posterior_factored(self, axes, plan, mu, var, q_out):
+        lib = nat.lib()
+        need = int(lib.mfgp_factored_workspace_bytes(self.npad, plan["ncols"], axes.ny, plan["rxL"], plan["ryL"], plan["rxH"],
+                                                     plan["ryH"], plan["chunk"]))
+        if self._fwork is None or self._fwork.numel() * 8 < need:
+            self._fwork = torch.empty(need // 8 + 8, dtype=torch.float64, device=self.device)
+        nat.check(lib.mfgp_posterior_grid_factored(
+            nat.ptr(axes.ux), axes.nx, nat.ptr(axes.uy), axes.ny, plan["ix0"], plan["ncols"], nat.ptr(self.Xt), self.NL, self.NH,
+            nat.ptr(self.W), self.npad, self.cap, nat.ptr(self.z), ctypes.byref(self.pstruct), plan["rxL"], plan["ryL"],
+            plan["rxH"], plan["ryH"], ctypes.c_double(plan["xlo"]), ctypes.c_double(plan["xhi"]), ctypes.c_double(plan["ylo"]),
+            ctypes.c_double(plan["yhi"]), plan["chunk"], nat.ptr(mu), nat.ptr(var), nat.ptr(q_out), nat.ptr(self._fwork),
+            self._fwork.numel() * 8, nat.stream_ptr()), "mfgp_posterior_grid_factored")
+
     def clone(self):
         other = DeviceGP(self.device)
         other.NL, other.NH, other.npad, other.cap = self.NL, self.NH, self.npad, self.cap
@@ -269,6 +357,8 @@ class DeviceGP:
         other.info = self.info.clone()
         other.fit_id = self.fit_id
         other.incremental = self.incremental
+        other.use_factored = self.use_factored
+        other.factored_min_gain = self.factored_min_gain
         other.lazy_check = self.lazy_check
         other.epoch = self.epoch
         return other

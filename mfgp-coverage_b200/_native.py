@@ -54,6 +54,11 @@ SIGNATURES = {
     "mfgp_posterior_grid_update": (c_int, [c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
                                            c_int64, c_int64, c_void_p, c_int64, c_int64, c_void_p, POINTER(MfgpParams),
                                            c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+    "mfgp_posterior_grid_factored": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64,
+                                             c_int64, c_void_p, c_int64, c_int64, c_void_p, POINTER(MfgpParams), c_int64,
+                                             c_int64, c_int64, c_int64, c_double, c_double, c_double, c_double, c_int64,
+                                             c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+    "mfgp_factored_workspace_bytes": (c_int64, [c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64]),
     "cov_assign_reduce": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64,
                                   c_void_p, c_int64, c_void_p, c_void_p, c_int64,
                                   c_void_p, c_int64, c_void_p, c_void_p, c_int64,

@@ -1,0 +1,312 @@
+// Factored GP posterior on tensor-product grids (replaces SFGP.predict gaussian_process.py:121-148 / MFGP.predict :401-438,
+// diagonal only, for the grids the reference actually uses: `[[x, y] for x in gx for y in gy]`, distribution.py:337-339).
+//
+// The cross-covariance of grid point (ix, iy) with training point n is separable per kernel part P in {lofi, hifi}:
+//     psi[n] = sum_P coef_P[n] * ex_P(x_ix, X_n) * ey_P(y_iy, Y_n),      e(u, U) = exp(-0.5 ((u - U) / l_P)^2).
+// As a function of the grid coordinate each factor is an entire function, so its Chebyshev interpolant on the grid's
+// interval converges super-exponentially: with r ~ 20 (l = 0.58) / 36 (l = 0.2) terms the factor tables are reproduced to
+// ~5e-15 ENTRYWISE (not a low-rank approximation of the training covariance -- nothing about K is truncated):
+//     ex_P(x, X_n) = sum_k T_k(tx) Cx_P[k][n],    ey_P(y, Y_n) = sum_l T_l(ty) Cy_P[l][n].
+// Then  v(ix, iy) = W psi = sum_{P,l} T_l(ty) * [ sum_k T_k(tx) * Y_P[:, l, k] ],   Y_P = W B_P,
+//     B_P[n][l][k] = coef_P[n] Cy_P[l][n] Cx_P[k][n]                      (N x R_P, R_P = ry_P * kpad_P)
+// and the whole grid costs ONE product W B (N^2 R / 2 MACs, R ~ 2.5k) instead of N^2 / 2 MACs PER GRID POINT:
+//   step 1  Chebyshev coefficient tables of the training points, basis tables of the grid axes        (tiny)
+//   step 2  B_P                                                                                         (84 MB at c4)
+//   step 3  Y_P = W B_P                      DMMA tile GEMM, W lower triangular                         (2.1e10 MAC at c4)
+//   step 4  Y'_P[ix][n][l] = sum_k Ux_P[ix][k] Y_P[n][l][k]      DMMA tile GEMM, per chunk of columns   (1.1e10 MAC)
+//   step 5  G'(ix) = Y'(ix)^T Y'(ix)  (64 x 64),  h'(ix) = Y'(ix)^T z       one CTA per column, DMMA    (1.7e10 MAC)
+//   step 6  var(ix, iy) = k0 - uy^T G'(ix) uy,  mu = mean + h'(ix) . uy      same CTA, G' in shared memory
+// against 8.8e12 MAC for the dense path at c4 (1 M points, N = 4096).  Agreement with the dense path / the oracle:
+// ~2e-14 k(0) (tests/test_gpu_factored.py).  Arbitrary point lists keep the dense path (gp_posterior.cu).
+#include "common.cuh"
+#include "gemm_f64.cuh"
+
+namespace mfgp {
+
+constexpr int F_LW = 64;             // padded number of y-expansion terms of both parts together (ryL + ryH <= 64)
+constexpr int F_MAXR = 64;           // largest supported Chebyshev order per axis and part
+
+struct FPart {                       // one kernel part (lofi / hifi) of the factored expansion
+    int rx, ry, kpad;                // x terms, y terms (multiple of 4), x terms padded to a multiple of 16
+    int loff;                        // first column of this part inside the 64-wide y-term vector
+    double inv_l;                    // 1 / length scale
+    double* Cx; double* Cy;          // [r][npad] Chebyshev coefficients of the training points' axis factors
+    double* B;  double* Y;           // [npad][ry * kpad]
+    double* Ux;                      // [ncols_pad][kpad]  T_k(tx) of the grid columns
+    double* Yp;                      // [chunk][npad][ry]  step-4 output of one chunk of columns
+};
+
+// ---- step 1a: Chebyshev coefficients c_k(n) of u -> exp(-0.5 ((u - U_n)/l)^2) on [lo, hi], one warp per (n, axis) ----------
+__global__ void __launch_bounds__(256) cheb_coef_kernel(const double* __restrict__ Xt, int N, int npad, int axis, double lo, double hi,
+                                                        double inv_l, int r, double* __restrict__ C) {
+    __shared__ double fv[8][F_MAXR];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int n = blockIdx.x * 8 + wib;
+    if (n >= npad) return;
+    if (n >= N) {                    // padding columns carry zeros
+        for (int k = lane; k < r; k += 32) C[(int64_t)k * npad + n] = 0.0;
+        return;
+    }
+    const double U = Xt[2 * n + axis];
+    const double mid = 0.5 * (lo + hi), half = 0.5 * (hi - lo);
+    for (int j = lane; j < r; j += 32) {
+        const double node = mid + half * cospi((j + 0.5) / r);
+        const double d = (node - U) * inv_l;
+        fv[wib][j] = exp(-0.5 * d * d);
+    }
+    __syncwarp();
+    for (int k = lane; k < r; k += 32) {
+        double s = 0.0;
+        for (int j = 0; j < r; j++) s += fv[wib][j] * cospi(k * (j + 0.5) / r);
+        C[(int64_t)k * npad + n] = s * (k == 0 ? 1.0 : 2.0) / r;
+    }
+}
+
+// ---- step 1b: T_k(t(u)) for the grid axis values u[i], rows padded with zeros ------------------------------------------------
+__global__ void cheb_basis_kernel(const double* __restrict__ u, int i0, int count, int rows_pad, double lo, double hi, int r, int ld,
+                                  int col0, double* __restrict__ T) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows_pad) return;
+    double* row = T + (int64_t)i * ld + col0;
+    if (i >= count) {
+        for (int k = 0; k < r; k++) row[k] = 0.0;
+        return;
+    }
+    const double t = (2.0 * u[i0 + i] - (lo + hi)) / (hi - lo);
+    double t0 = 1.0, t1 = t;
+    for (int k = 0; k < r; k++) {
+        row[k] = t0;
+        const double t2 = 2.0 * t * t1 - t0;
+        t0 = t1; t1 = t2;
+    }
+}
+
+// ---- step 2: B[n][l][k] = coef[n] Cy[l][n] Cx[k][n] ------------------------------------------------------------------------
+__global__ void build_B_kernel(const double* __restrict__ Cx, const double* __restrict__ Cy, int npad, int N, int NL, int rx, int ry,
+                               int kpad, double coef_lo, double coef_hi, double* __restrict__ B) {
+    const int n = blockIdx.y;
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;       // (l, k)
+    if (e >= ry * kpad) return;
+    const int l = e / kpad, k = e % kpad;
+    double v = 0.0;
+    if (n < N && k < rx) v = (n < NL ? coef_lo : coef_hi) * Cy[(int64_t)l * npad + n] * Cx[(int64_t)k * npad + n];
+    B[(int64_t)n * ry * kpad + e] = v;
+}
+
+// ---- steps 5 + 6: one CTA per grid column --------------------------------------------------------------------------------
+constexpr int G_LD = F_LW + 4;       // padded shared-memory row (doubles): conflict-free DMMA fragment reads
+constexpr int G_ROWS = 64;           // training rows per chunk
+
+struct GramArgs {
+    const double* YpL; const double* YpH; int ryL, ryH;        // step-4 outputs [cols][npad][ry]
+    int npad; const double* z;
+    const double* Uy;                                          // [ny][F_LW]
+    int ny; int col_begin;                                     // first grid column (relative) of this launch
+    double mean, k0;
+    double* mu; double* var; double* qred;                     // flat outputs, index = col * ny + iy
+};
+
+__global__ void __launch_bounds__(128) gram_eval_kernel(GramArgs a) {
+    extern __shared__ __align__(16) double gsm[];
+    double* Ts = gsm;                               // [2][G_ROWS][G_LD]  double-buffered chunk of Y'(ix)
+    double* Gs = gsm + 2 * G_ROWS * G_LD;           // [F_LW][F_LW + 1]
+    double* hs = Gs + F_LW * (F_LW + 1);            // [2][F_LW]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int col = blockIdx.x;
+    const int wm = (warp >> 1) * 32, wn = (warp & 1) * 32;
+    const int gq = lane >> 2, tq = lane & 3;
+    const double* srcL = a.YpL ? a.YpL + (int64_t)col * a.npad * a.ryL : nullptr;
+    const double* srcH = a.YpH + (int64_t)col * a.npad * a.ryH;
+    const int nw = a.ryL + a.ryH;
+
+    for (int e = tid; e < 2 * G_ROWS * G_LD; e += 128) Ts[e] = 0.0;      // the pad columns stay zero
+    __syncthreads();
+    auto stage = [&](int buf, int n0) {
+        double* dst = Ts + buf * G_ROWS * G_LD;
+        const int cL = a.ryL / 2, cH = a.ryH / 2;                       // 16-byte chunks per row
+        for (int c = tid; c < G_ROWS * (cL + cH); c += 128) {
+            const int r = c / (cL + cH), q = c % (cL + cH);
+            if (q < cL) cp_async16(dst + r * G_LD + 2 * q, srcL + (int64_t)(n0 + r) * a.ryL + 2 * q, true);
+            else cp_async16(dst + r * G_LD + a.ryL + 2 * (q - cL), srcH + (int64_t)(n0 + r) * a.ryH + 2 * (q - cL), true);
+        }
+        cp_async_commit();
+    };
+    double acc[4][4][2];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+    double hacc = 0.0;                              // thread (c = tid % 64, half = tid / 64): sum over its rows of z[n] T[n][c]
+    const int hc = tid & 63, hh = tid >> 6;
+    const int nchunk = a.npad / G_ROWS;
+    stage(0, 0);
+    for (int ch = 0; ch < nchunk; ch++) {
+        const int buf = ch & 1;
+        if (ch + 1 < nchunk) { stage(buf ^ 1, (ch + 1) * G_ROWS); cp_async_wait<1>(); }
+        else cp_async_wait<0>();
+        __syncthreads();
+        const double* T = Ts + buf * G_ROWS * G_LD;
+#pragma unroll 4
+        for (int kk = 0; kk < G_ROWS; kk += 4) {
+            double af[4], bf[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) af[i] = T[(kk + tq) * G_LD + wm + i * 8 + gq];      // A[m][k] = T[k][m]
+#pragma unroll
+            for (int j = 0; j < 4; j++) bf[j] = T[(kk + tq) * G_LD + wn + j * 8 + gq];      // B[k][n] = T[k][n]
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+        }
+        for (int r = hh; r < G_ROWS; r += 2) hacc += a.z[ch * G_ROWS + r] * T[r * G_LD + hc];
+        __syncthreads();
+    }
+    // G' and h' to shared memory
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int r = wm + i * 8 + gq, c = wn + j * 8 + tq * 2;
+            Gs[r * (F_LW + 1) + c] = acc[i][j][0];
+            Gs[r * (F_LW + 1) + c + 1] = acc[i][j][1];
+        }
+    hs[hh * F_LW + hc] = hacc;
+    __syncthreads();
+    if (tid < F_LW) hs[tid] += hs[F_LW + tid];
+    __syncthreads();
+    // step 6: every grid point of the column
+    for (int iy = tid; iy < a.ny; iy += 128) {
+        const double* up = a.Uy + (int64_t)iy * F_LW;
+        double u[F_LW];
+#pragma unroll
+        for (int l = 0; l < F_LW; l += 2) {
+            const double2 t = __ldg(reinterpret_cast<const double2*>(up + l));
+            u[l] = t.x; u[l + 1] = t.y;
+        }
+        double q = 0.0, m = 0.0;
+        for (int l = 0; l < nw; l++) {
+            const double* g = Gs + l * (F_LW + 1);
+            double s = 0.0;
+#pragma unroll
+            for (int c = 0; c < F_LW; c++) s = fma(g[c], u[c], s);
+            // u[] is indexed dynamically below only through this select chain-free form:
+            q = fma(s, up[l], q);
+            m = fma(hs[l], up[l], m);
+        }
+        const int64_t gidx = (int64_t)(a.col_begin + col) * a.ny + iy;
+        a.var[gidx] = a.k0 - q;
+        a.mu[gidx] = a.mean + m;
+        if (a.qred) a.qred[gidx] = q;
+    }
+}
+
+}  // namespace mfgp
+
+using namespace mfgp;
+
+// plan sizes (host helper, also used by the Python side to size the workspace)
+static inline int64_t round_up(int64_t v, int64_t m) { return (v + m - 1) / m * m; }
+
+extern "C" int64_t mfgp_factored_workspace_bytes(int64_t npad, int64_t ncols, int64_t ny, int64_t rxL, int64_t ryL, int64_t rxH,
+                                                 int64_t ryH, int64_t chunk_cols) {
+    const int64_t kL = round_up(rxL, 16), kH = round_up(rxH, 16);
+    const int64_t ncp = round_up(ncols, 64), ch = round_up(chunk_cols, 64);
+    int64_t d = 0;
+    d += (rxL + ryL + rxH + ryH) * npad;                       // coefficient tables
+    d += 2 * npad * (ryL * kL + ryH * kH);                     // B and Y
+    d += ncp * (kL + kH);                                      // Ux
+    d += ny * 64;                                              // Uy
+    d += ch * npad * (ryL + ryH);                              // Y' of one chunk
+    return d * 8 + 4096;
+}
+
+// Factored posterior for the whole columns [ix0, ix0 + ncols) of the tensor-product grid ux[nx] x uy[ny] (x-major); outputs
+// are flat over those columns: index (ix - ix0) * ny + iy.  rx*/ry*: Chebyshev orders per axis and part (ryL, ryH multiples
+// of 4, ryL + ryH <= 64, all <= 64; rxL = ryL = 0 for a single-fidelity model) -- chosen by the caller so that the factor
+// tables are reproduced to rounding (mfgp_coverage_b200/_engine.py: chebyshev_orders).
+extern "C" int mfgp_posterior_grid_factored(const double* ux, int64_t nx, const double* uy, int64_t ny, int64_t ix0, int64_t ncols,
+                                            const double* Xt, int64_t NL, int64_t NH, const double* W, int64_t npad, int64_t ldw,
+                                            const double* z, const mfgp_params* p_host, int64_t rxL, int64_t ryL, int64_t rxH,
+                                            int64_t ryH, double xlo, double xhi, double ylo, double yhi, int64_t chunk_cols,
+                                            double* mu, double* var, double* qred, void* work, int64_t work_bytes, void* stream) {
+    if (!ux || !uy || !Xt || !W || !z || !p_host || !mu || !var || !work) return MFGP_ERR_INVALID;
+    const int64_t N = NL + NH;
+    if (N <= 0 || npad < N || npad % MFGP_TILE || ldw < npad || ncols <= 0 || ix0 < 0 || ix0 + ncols > nx || ny <= 0) return MFGP_ERR_INVALID;
+    const bool multi = p_host->multi != 0;
+    if (!multi && (rxL || ryL || NL)) return MFGP_ERR_INVALID;
+    if (rxH <= 0 || ryH <= 0 || rxH > F_MAXR || ryH > F_MAXR || rxL > F_MAXR || ryL > F_MAXR || (ryL % 4) || (ryH % 4) || ryL + ryH > F_LW)
+        return MFGP_ERR_INVALID;
+    if (multi && (rxL <= 0 || ryL <= 0)) return MFGP_ERR_INVALID;
+    if (!(xhi > xlo) || !(yhi > ylo) || chunk_cols <= 0) return MFGP_ERR_INVALID;
+    if (work_bytes < mfgp_factored_workspace_bytes(npad, ncols, ny, rxL, ryL, rxH, ryH, chunk_cols)) return MFGP_ERR_INVALID;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const DevParams dp = make_dev_params(*p_host);
+    const int64_t ncp = round_up(ncols, 64), chunk = round_up(chunk_cols, 64);
+
+    FPart parts[2];
+    int nparts = 0;
+    double* wp = static_cast<double*>(work);
+    auto carve = [&](int64_t n) { double* r = wp; wp += n; return r; };
+    double* Uy = carve(ny * 64);
+    auto add_part = [&](int rx, int ry, double l, int loff) {
+        FPart& f = parts[nparts++];
+        f.rx = rx; f.ry = ry; f.kpad = (int)round_up(rx, 16); f.loff = loff; f.inv_l = 1.0 / l;
+        f.Cx = carve((int64_t)rx * npad); f.Cy = carve((int64_t)ry * npad);
+        f.B = carve(npad * (int64_t)ry * f.kpad); f.Y = carve(npad * (int64_t)ry * f.kpad);
+        f.Ux = carve(ncp * f.kpad);
+        f.Yp = carve(chunk * npad * ry);
+    };
+    if (multi) add_part((int)rxL, (int)ryL, p_host->l_L, 0);
+    add_part((int)rxH, (int)ryH, p_host->l_H, multi ? (int)ryL : 0);
+
+    MFGP_CUDA_CHECK(cudaMemsetAsync(Uy, 0, sizeof(double) * ny * 64, st));
+    for (int pi = 0; pi < nparts; pi++) {
+        FPart& f = parts[pi];
+        const bool lofi_part = multi && pi == 0;
+        // step 1: coefficient tables of the training points, basis tables of the grid axes
+        cheb_coef_kernel<<<(unsigned)((npad + 7) / 8), 256, 0, st>>>(Xt, (int)N, (int)npad, 0, xlo, xhi, f.inv_l, f.rx, f.Cx);
+        MFGP_LAUNCH_CHECK();
+        cheb_coef_kernel<<<(unsigned)((npad + 7) / 8), 256, 0, st>>>(Xt, (int)N, (int)npad, 1, ylo, yhi, f.inv_l, f.ry, f.Cy);
+        MFGP_LAUNCH_CHECK();
+        MFGP_CUDA_CHECK(cudaMemsetAsync(f.Ux, 0, sizeof(double) * ncp * f.kpad, st));
+        cheb_basis_kernel<<<(unsigned)((ncp + 127) / 128), 128, 0, st>>>(ux, (int)ix0, (int)ncols, (int)ncp, xlo, xhi, f.rx, f.kpad, 0, f.Ux);
+        MFGP_LAUNCH_CHECK();
+        cheb_basis_kernel<<<(unsigned)((ny + 127) / 128), 128, 0, st>>>(uy, 0, (int)ny, (int)ny, ylo, yhi, f.ry, 64, f.loff, Uy);
+        MFGP_LAUNCH_CHECK();
+        // step 2: B.  lofi part: rho s_L (lofi columns) / rho^2 s_L (hifi columns); hifi part: 0 / s_H  (gaussian_process.py:426-429)
+        const double c_lo = lofi_part ? dp.rho * dp.s_L : 0.0;
+        const double c_hi = lofi_part ? dp.rho2 * dp.s_L : dp.s_H;
+        dim3 bgrid((unsigned)((f.ry * f.kpad + 127) / 128), (unsigned)npad);
+        build_B_kernel<<<bgrid, 128, 0, st>>>(f.Cx, f.Cy, (int)npad, (int)N, (int)NL, f.rx, f.ry, f.kpad, c_lo, c_hi, f.B);
+        MFGP_LAUNCH_CHECK();
+        // step 3: Y = W B  (W lower triangular: k < m0 + 64)
+        GemmArgs g{};
+        g.A = W; g.lda = ldw; g.B = f.B; g.ldb = (int64_t)f.ry * f.kpad; g.C = f.Y; g.ldc = (int64_t)f.ry * f.kpad;
+        g.M = (int)npad; g.N = f.ry * f.kpad; g.K = (int)npad; g.alpha = 1.0; g.beta = 0.0; g.mode = GEMM_A_LOWER;
+        int rc = launch_gemm(g, false, 1, st);
+        if (rc) return rc;
+    }
+    const size_t gsmem = sizeof(double) * (2 * G_ROWS * G_LD + F_LW * (F_LW + 1) + 2 * F_LW);
+    MFGP_CUDA_CHECK(cudaFuncSetAttribute(gram_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));
+    for (int64_t c0 = 0; c0 < ncols; c0 += chunk) {
+        const int64_t cc = (ncols - c0 < chunk) ? ncols - c0 : chunk;
+        const int64_t ccp = round_up(cc, 64);
+        for (int pi = 0; pi < nparts; pi++) {
+            FPart& f = parts[pi];
+            // step 4: Y'[col][(n, l)] = sum_k Ux[col][k] Y[(n, l)][k]
+            GemmArgs g{};
+            g.A = f.Ux + c0 * f.kpad; g.lda = f.kpad; g.B = f.Y; g.ldb = f.kpad; g.C = f.Yp; g.ldc = npad * (int64_t)f.ry;
+            g.M = (int)ccp; g.N = (int)(npad * f.ry); g.K = f.kpad; g.alpha = 1.0; g.beta = 0.0; g.mode = GEMM_GENERAL;
+            int rc = launch_gemm(g, true, 1, st);
+            if (rc) return rc;
+        }
+        GramArgs ga;
+        ga.YpL = multi ? parts[0].Yp : nullptr; ga.YpH = parts[nparts - 1].Yp;
+        ga.ryL = multi ? parts[0].ry : 0; ga.ryH = parts[nparts - 1].ry;
+        ga.npad = (int)npad; ga.z = z; ga.Uy = Uy; ga.ny = (int)ny; ga.col_begin = (int)c0;
+        ga.mean = dp.mean_H; ga.k0 = dp.k0; ga.mu = mu; ga.var = var; ga.qred = qred;
+        gram_eval_kernel<<<(unsigned)cc, 128, gsmem, st>>>(ga);
+        MFGP_LAUNCH_CHECK();
+    }
+    return MFGP_OK;
+}

@@ -1,0 +1,115 @@
+"""GPU parity of the Chebyshev-factored posterior on tensor-product grids (csrc/gp_factored.cu) against the oracle and
+against the dense DMMA kernel: same mean / variance to 1e-9 (observed ~1e-13), for MF and SF models, non-square grids,
+whole-column shards of a grid and training points outside the grid's extent."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import gp as ogp
+from tests import synth
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-9
+
+
+def _tensor_grid(nx, ny, x0=0.0, x1=1.0, y0=0.0, y1=1.0):
+    gx, gy = np.linspace(x0, x1, nx), np.linspace(y0, y1, ny)
+    return np.stack(np.meshgrid(gx, gy, indexing="ij"), axis=-1).reshape(-1, 2)
+
+
+def _model(hyp, X_L, y_L, X_H, y_H, multi):
+    from mfgp_coverage_b200 import simulator as sim
+    if multi:
+        m = sim.init_MFGP(hyp, np.column_stack((X_L, y_L)))
+        m.updt_info(X_L, y_L, X_H, y_H)
+    else:
+        m = sim.init_SFGP(hyp, np.empty((0, 3)))
+        m.updt_info(X_H, y_H)
+    return m
+
+
+@pytest.mark.parametrize("nx,ny,N,multi", [(64, 64, 300, True), (96, 96, 700, True), (80, 48, 260, True), (72, 72, 200, False),
+                                           (128, 40, 1100, True)])
+def test_factored_posterior_matches_oracle_and_dense(nx, ny, N, multi):
+    from mfgp_coverage_b200._coverage import CoverageGrid
+    xy = _tensor_grid(nx, ny)
+    f = synth.truth_function(xy)
+    X_L, y_L, X_H, y_H = synth.training_set(xy, f, N, multi=multi)
+    hyp = synth.MF_HYP if multi else synth.SF_HYP
+    p = ogp.GPParams.from_hyp(hyp)
+    om = ogp.Model(p, X_L, y_L, X_H, y_H)
+    om.updt_info()
+    mu_o, var_o = om.predict(xy)
+    m = _model(hyp, X_L, y_L, X_H, y_H, multi)
+    grid = CoverageGrid(xy)
+    assert grid.axes is not None
+    out = {}
+    for mode in ("factored", "dense"):
+        m.engine.use_factored = mode == "factored"
+        m.engine.factored_min_gain = 0.0                 # force the factored path whatever the cost model says
+        mu = torch.empty(grid.G, dtype=torch.float64, device=grid.device)
+        var = torch.empty(grid.G, dtype=torch.float64, device=grid.device)
+        q = torch.empty(grid.G, dtype=torch.float64, device=grid.device)
+        m.predict_device(grid.xy, mu, var, grid=grid, q_out=q)
+        if mode == "factored":
+            assert m.engine._fplan is not None and m.engine._fplan[1] is not None, "factored plan was not taken"
+        out[mode] = (mu.cpu().numpy(), var.cpu().numpy(), q.cpu().numpy())
+    for mode, (mu, var, q) in out.items():
+        assert np.max(np.abs(var - var_o)) <= TOL * p.k0, mode
+        assert np.max(np.abs(mu - mu_o)) <= TOL * max(1.0, np.max(np.abs(mu_o))), mode
+        assert np.max(np.abs((p.k0 - q) - var)) <= 1e-15 * p.k0 + 1e-18, mode
+    assert np.max(np.abs(out["factored"][1] - out["dense"][1])) <= 1e-11 * p.k0
+    assert np.max(np.abs(out["factored"][0] - out["dense"][0])) <= 1e-11 * max(1.0, np.max(np.abs(mu_o)))
+
+
+def test_factored_posterior_on_column_shards_and_offset_domain():
+    """Grid sharding hands every rank a whole-column slice; the domain need not be the unit square and training points
+    may lie outside the grid's extent (lofi points are not grid points)."""
+    from mfgp_coverage_b200._coverage import CoverageGrid
+    from mfgp_coverage_b200._engine import TensorAxes
+    nx, ny = 90, 70
+    xy = _tensor_grid(nx, ny, -0.3, 1.4, 2.0, 2.9)
+    rng = np.random.default_rng(5)
+    f = np.sin(3 * xy[:, 0]) * np.cos(2 * xy[:, 1])
+    X_L = np.column_stack((rng.uniform(-0.6, 1.7, 60), rng.uniform(1.8, 3.1, 60)))          # partly outside the grid
+    y_L = (0.8 * np.sin(3 * X_L[:, 0]) * np.cos(2 * X_L[:, 1]) + rng.normal(0, 0.01, 60)).reshape(-1, 1)
+    idx = rng.choice(xy.shape[0], 240, replace=False)
+    X_H, y_H = xy[idx], (f[idx] + rng.normal(0, 0.1, 240)).reshape(-1, 1)
+    p = ogp.GPParams.from_hyp(synth.MF_HYP)
+    om = ogp.Model(p, X_L, y_L, X_H, y_H)
+    om.updt_info()
+    mu_o, var_o = om.predict(xy)
+    m = _model(synth.MF_HYP, X_L, y_L, X_H, y_H, True)
+    m.engine.factored_min_gain = 0.0
+    gx, gy = np.unique(xy[:, 0]), np.unique(xy[:, 1])
+    axes = TensorAxes(np.linspace(-0.3, 1.4, nx), np.linspace(2.0, 2.9, ny), torch.device("cuda", torch.cuda.current_device()))
+    for lo_col, hi_col in ((0, 30), (30, 61), (61, 90)):
+        lo, hi = lo_col * ny, hi_col * ny
+        grid = CoverageGrid(xy[lo:hi], base_index=lo, axes=axes)
+        mu = torch.empty(hi - lo, dtype=torch.float64, device=grid.device)
+        var = torch.empty(hi - lo, dtype=torch.float64, device=grid.device)
+        m.predict_device(grid.xy, mu, var, grid=grid)
+        assert m.engine._fplan[1] is not None
+        assert np.max(np.abs(var.cpu().numpy() - var_o[lo:hi])) <= TOL * p.k0
+        assert np.max(np.abs(mu.cpu().numpy() - mu_o[lo:hi])) <= TOL * max(1.0, np.max(np.abs(mu_o)))
+
+
+def test_short_length_scale_keeps_the_dense_kernel():
+    """Orders beyond the 64-term budget (length scale << grid extent): the planner must decline, results stay right."""
+    from mfgp_coverage_b200._coverage import CoverageGrid
+    hyp = synth.SF_HYP.copy()
+    hyp[2] = np.log(0.01)
+    xy = _tensor_grid(64, 64)
+    f = synth.truth_function(xy)
+    _, _, X_H, y_H = synth.training_set(xy, f, 150, multi=False)
+    p = ogp.GPParams.from_hyp(hyp)
+    om = ogp.Model(p, np.empty((0, 2)), np.empty((0, 1)), X_H, y_H)
+    om.updt_info()
+    mu_o, var_o = om.predict(xy)
+    m = _model(hyp, None, None, X_H, y_H, False)
+    m.engine.factored_min_gain = 0.0
+    grid = CoverageGrid(xy)
+    mu, var = m.predict_device(grid.xy, grid=grid)
+    assert m.engine._fplan is not None and m.engine._fplan[1] is None
+    assert np.max(np.abs(var.cpu().numpy() - var_o)) <= TOL * p.k0
+    assert np.max(np.abs(mu.cpu().numpy() - mu_o)) <= TOL * max(1.0, np.max(np.abs(mu_o)))
