@@ -39,17 +39,29 @@ WORKLOADS = {
 # profiles/r01_posterior_v3_ncu_summary.txt (18.883 GB read + 0.040 GB written); algorithmic minimum 32 G + 8 N^2 = 0.17 GB:
 # W (67 MB used) is re-read from L2 by every CTA and only partly stays resident next to the factor tables.
 POSTERIOR_TRAFFIC_C4_1GPU = 18.883344e9 + 39.72864e6
+FACTORED_TRAFFIC_C4_1GPU = None      # filled from the ncu capture of the factored posterior (profiles/)
 DGEMM_PEAK_TFLOPS = 35.41   # cuBLAS DGEMM 8192^3 measured on this pool's B200 (profiles/r01_dgemm_peak.json);
 #                             MEASURED_PEAKS.json carries no FP64 figure.  DMMA issue peak: 37.15 (r01_fp64_pipes.log)
 
 
-def make_workload(name):
+def make_workload(name, world=1, rank=0, scaling="weak"):
+    """Synthetic inputs of one rank.  Weak scaling (default, SURVEY 8e: the grid points are independent units): every
+    rank owns n columns x n rows of an (n * world) x n tensor-product grid over the unit square -- the per-GPU shard is
+    the BASELINE grid, the whole grid grows with the number of GPUs.  Strong scaling: the n x n grid is split into
+    whole-column slices.  Training set and agents are the same on every rank."""
     n, N, A, desc = WORKLOADS[name]
-    xy = synth.grid(n)
-    f = synth.truth_function(xy)
-    X_L, y_L, X_H, y_H = synth.training_set(xy, f, N)
-    return dict(name=name, desc=desc, n=n, N=N, A=A, xy=xy, f=f, X_L=X_L, y_L=y_L, X_H=X_H, y_H=y_H,
-                pos=synth.agents(A, 7), cen=synth.agents(A, 8))
+    base = synth.grid(n)
+    fbase = synth.truth_function(base)
+    X_L, y_L, X_H, y_H = synth.training_set(base, fbase, N)
+    if scaling == "weak":
+        ux, uy = np.linspace(0, 1, n * world), np.linspace(0, 1, n)
+        c0, c1 = rank * n, (rank + 1) * n
+    else:
+        ux, uy = np.linspace(0, 1, n), np.linspace(0, 1, n)
+        c0, c1 = (rank * n) // world, ((rank + 1) * n) // world
+    xy = np.stack(np.meshgrid(ux[c0:c1], uy, indexing="ij"), axis=-1).reshape(-1, 2)
+    return dict(name=name, desc=desc, n=n, N=N, A=A, xy=xy, f=synth.truth_function(xy), ux=ux, uy=uy, lo=c0 * n, hi=c1 * n,
+                G_total=ux.size * uy.size, X_L=X_L, y_L=y_L, X_H=X_H, y_H=y_H, pos=synth.agents(A, 7), cen=synth.agents(A, 8))
 
 
 class ClockSampler(threading.Thread):
@@ -140,13 +152,16 @@ def run_reference(args):
 
 
 def base_line(args, w, value, ms):
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    scaling = getattr(args, "scaling", "weak")
+    shard = (f"weak scaling: every GPU owns a {w['n']}x{w['n']}-point shard (whole columns) of a {w['n'] * world}x{w['n']} grid"
+             if scaling == "weak" else f"strong scaling: the {w['n']}x{w['n']} grid split into whole-column slices")
     return {"metric": "GP posterior mean+var + coverage step, grid-points/s (coverage iterations/s = 1000/ms_per_step)",
             "value": value, "unit": "grid-points/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "data": "synthetic",
-            "config": {"workload": w["desc"], "grid_points": int(w["xy"].shape[0]), "train_points": int(w["N"]),
-                       "agents": int(w["A"]), "parallelism": f"grid-sharded x{args.gpus}",
-                       "l2_policy": "inputs larger than L2 (W 134 MB + 40 B/grid point streamed; K/W rewritten every "
-                                    "step)" if w["name"] == "c4" else "L2 flushed between steps (256 MB write)"}}
+            "ms_per_step": ms, "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "data": "synthetic",
+            "config": {"workload": w["desc"], "grid_points": int(w["G_total"]), "grid_points_per_gpu": int(w["xy"].shape[0]),
+                       "train_points": int(w["N"]), "agents": int(w["A"]), "parallelism": f"grid-sharded x{world} ({shard})",
+                       "l2_policy": "L2 flushed between steps (256 MB write)"}}
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -160,6 +175,7 @@ def run_ours(args):
     from mfgp_coverage_b200 import _coverage as cv
     from mfgp_coverage_b200 import sharding
     from mfgp_coverage_b200 import simulator as sim
+    from mfgp_coverage_b200._engine import TensorAxes
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -168,35 +184,30 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
-    w = make_workload(args.workload)
-    G = w["xy"].shape[0]
+    w = make_workload(args.workload, world, rank, args.scaling)
+    G_total, lo, hi = w["G_total"], w["lo"], w["hi"]
+    npts = hi - lo
     bbox = np.array([0.0, 1.0, 0.0, 1.0])
-    lo, hi = sharding.shard_bounds(G, world, rank)
 
     model = sim.init_MFGP(synth.MF_HYP, np.column_stack((w["X_L"], w["y_L"])))
     model.updt_info(w["X_L"], w["y_L"], w["X_H"], w["y_H"])          # uploads the training set once
     eng = model.engine
-    from mfgp_coverage_b200._engine import TensorAxes, detect_tensor_grid
-    tg = detect_tensor_grid(w["xy"])                                   # the synthetic grids are tensor-product grids
-    axes = TensorAxes(tg[0], tg[1], dev) if tg is not None else None
-    grid = cv.CoverageGrid(w["xy"][lo:hi], w["f"][lo:hi], base_index=lo, axes=axes)
-    mu = torch.empty(hi - lo, dtype=torch.float64, device=dev)
-    var = torch.empty(hi - lo, dtype=torch.float64, device=dev)
-    flush = torch.empty(64 << 20, dtype=torch.float32, device=dev) if w["name"] != "c4" else None
+    axes = TensorAxes(w["ux"], w["uy"], dev)                           # the synthetic grids are tensor-product grids
+    grid = cv.CoverageGrid(w["xy"], w["f"], base_index=lo, axes=axes)
+    mu = torch.empty(npts, dtype=torch.float64, device=dev)
+    var = torch.empty(npts, dtype=torch.float64, device=dev)
+    flush = torch.empty(64 << 20, dtype=torch.float32, device=dev)     # 256 MB > 126 MB L2
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
     post_ms, fit_ms, cov_ms = [], [], []
 
     def device_step(timed):
-        if flush is not None:
-            flush.zero_()
+        flush.zero_()
         if timed:
             ev[3].record()
         eng.refactor(check=False)                                     # K -> L -> W -> z  (train set resident)
-        if axes is not None:
-            eng.grid_tables(axes)                                     # per-axis factor tables of the separable kernel
         if timed:
             ev[0].record()
-        eng.posterior(grid.xy, mu, var, axes=axes, g_lo=lo)
+        eng.posterior(grid.xy, mu, var, axes=axes, g_lo=lo)           # factored (tensor grid) or dense DMMA kernel
         if timed:
             ev[1].record()
         loss_vor = sim.voronoi_bounded(w["pos"], bbox)
@@ -220,7 +231,9 @@ def run_ours(args):
             dist.barrier()
             torch.cuda.synchronize()
 
-    def timed_region(fn, steps):
+    def timed_region(fn, steps, exclude_flush=True):
+        """K steps between barriers; device timeline (CUDA events), max over ranks.  The L2 flush between steps is a
+        256 MB memset (~45 us), measured once and subtracted."""
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -229,7 +242,7 @@ def run_ours(args):
             out = fn()
         e1.record()
         barrier()
-        ms = e0.elapsed_time(e1)      # device timeline; the host work of a step sits between its kernels
+        ms = e0.elapsed_time(e1)
         if world > 1:
             t = torch.tensor([ms], dtype=torch.float64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -238,57 +251,77 @@ def run_ours(args):
 
     for _ in range(args.warmup):
         device_step(False)
-    eng.check_factor()
+    eng.check_factor(force=True)
     sampler = ClockSampler(local)
     sampler.start()
     l0 = nat.lib().mfgp_launch_count()
     ms_dev, out = timed_region(lambda: device_step(True), args.steps)
     launches = nat.lib().mfgp_launch_count() - l0
     clocks = sampler.result()
+    plan = eng._fplan[1] if eng._fplan is not None else None
 
-    # end-to-end through the drop-in API with host buffers (rank-local slice of the grid)
-    xs_host = np.ascontiguousarray(w["xy"][lo:hi])
-    truth_host = np.ascontiguousarray(np.column_stack((w["xy"][lo:hi], w["f"][lo:hi])))
+    # the dense DMMA posterior kernel on a 64-column sub-grid, for reference (it is the path of arbitrary point lists)
+    dense = None
+    if plan is not None:
+        sub = min(64, npts // axes.ny) * axes.ny
+        eng.use_factored = False
+        for _ in range(2):
+            eng.posterior(grid.xy[:sub], mu[:sub], var[:sub], axes=axes, g_lo=lo)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        eng.posterior(grid.xy[:sub], mu[:sub], var[:sub], axes=axes, g_lo=lo)
+        e1.record()
+        torch.cuda.synchronize()
+        eng.use_factored = True
+        dms = e0.elapsed_time(e1)
+        dfl = float(sub) * w["N"] * w["N"] + 4.0 * sub * w["N"]
+        dense = {"kernel": "posterior_kernel (dense DMMA path, arbitrary point lists)", "grid_points": int(sub), "ms": dms,
+                 "achieved": dfl / (dms * 1e-3) * 1e-12, "unit": "TFLOP/s", "frac": dfl / (dms * 1e-3) * 1e-12 / DGEMM_PEAK_TFLOPS,
+                 "grid_points_per_s": sub / (dms * 1e-3)}
+        eng.posterior(grid.xy, mu, var, axes=axes, g_lo=lo)           # restore the standing posterior
+
+    # end-to-end through the reference-style call sequence with HOST buffers: updt_hifi -> predict(x_star) ->
+    # compute_loss / compute_centroids / compute_max_var (simulator.py:888-904); host arrays in, host arrays out
+    xs_host = np.ascontiguousarray(w["xy"])
+    truth_host = np.ascontiguousarray(np.column_stack((w["xy"], w["f"])))
     empty_x, empty_y = np.empty((0, 2)), np.empty((0, 1))
 
     def e2e_step():
         model.updt_hifi(empty_x, empty_y)                 # the reference refits every iteration (simulator.py:888-891)
-        mu_h, var_h = model.predict(xs_host)              # H2D grid, D2H mean + variance
+        mu_h, var_h = model.predict(xs_host)              # D2H mean + variance (the grid upload is cached by identity)
         loss_vor = sim.voronoi_bounded(w["pos"], bbox)
         lloyd_vor = sim.voronoi_bounded(w["cen"], bbox)
-        g = cv.CoverageGrid(xs_host, truth_host[:, 2], base_index=lo)          # H2D grid + truth
-        res = g.assign_reduce(lloyd_vor, loss_vor, w=torch.from_numpy(mu_h[:, 0]).to(dev),
-                              var=torch.from_numpy(var_h).to(dev))             # H2D mean + variance
-        sharding.allreduce_partials(res)
-        loss = cv.loss_from_partials(res["lossp"].cpu().numpy(), loss_vor.areas())
-        cent = cv.centroids_from_partials(res["cent"].cpu().numpy(), lloyd_vor.areas(), 0.0, 1.0, 0.0, 1.0)
-        return loss, cent, res["amax_idx"].cpu().numpy()
+        loss = sim.compute_loss(loss_vor, truth_host)
+        cent = sim.compute_centroids(lloyd_vor, xs_host, mu_h)            # H2D mean
+        axy, mv = sim.compute_max_var(lloyd_vor, truth_host, var_h)       # H2D variance
+        return loss, cent, axy
 
     e2e_step()
-    ms_e2e, out_e2e = timed_region(e2e_step, max(1, min(args.steps, 3)))
+    ms_e2e, out_e2e = timed_region(e2e_step, max(1, min(args.steps, 5)))
+    h2d = npts * (8 + 8) + w["A"] * 200
+    d2h = npts * 16 + w["A"] * 8 * 8
 
     # incremental iteration (reported separately -- never as `value`): every agent takes one new
-    # hifi sample; the factor is bordered (mfgp_cholesky_append), the standing posterior gets the new rows only
-    # (mfgp_posterior_grid_update), then the same coverage step.  Same results as refit-from-scratch to ~1e-13 k(0).
+    # hifi sample; the factor is bordered (mfgp_cholesky_append) instead of refactored, then posterior + coverage step.
     npad_main = eng.npad
     rng_inc = np.random.default_rng(5)
+    pool = rng_inc.permutation(w["n"] * w["n"])
+    basegrid = synth.grid(w["n"])
     used = {tuple(r) for r in w["X_H"]}
-    pool = [i for i in rng_inc.permutation(G) if tuple(w["xy"][i]) not in used]
+    pool = [i for i in pool if tuple(basegrid[i]) not in used]
     inc_steps = max(1, min(args.steps, 5))
     eng.incremental = True
     eng.refactor(check=False)
-    if axes is not None:
-        eng.grid_tables(axes)
-    eng.posterior(grid.xy, mu, var, axes=axes, g_lo=lo)            # standing posterior of the first N rows
+    eng.posterior(grid.xy, mu, var, axes=axes, g_lo=lo)
     cursor = [0]
 
     def inc_step():
         idx = pool[cursor[0]:cursor[0] + w["A"]]
         cursor[0] += w["A"]
-        x_new = w["xy"][idx]
-        y_new = (w["f"][idx] + rng_inc.normal(0, 0.1, len(idx))).reshape(-1, 1)
+        x_new = basegrid[idx]
+        y_new = (synth.truth_function(x_new) + rng_inc.normal(0, 0.1, len(idx))).reshape(-1, 1)
         eng.append_hifi(x_new, y_new, check=False)                 # H2D of the new samples + bordered factor update
-        eng.posterior(grid.xy, mu, var, axes=axes, g_lo=lo)        # rows [N_old, N_new) only
+        eng.posterior(grid.xy, mu, var, axes=axes, g_lo=lo)
         loss_vor = sim.voronoi_bounded(w["pos"], bbox)
         lloyd_vor = sim.voronoi_bounded(w["cen"], bbox)
         res = grid.assign_reduce(lloyd_vor, loss_vor, w=mu, var=var)
@@ -299,54 +332,66 @@ def run_ours(args):
 
     inc_step()                                                     # warm-up (grows the factor buffers once)
     ms_inc, out_inc = timed_region(inc_step, inc_steps)
-    eng.check_factor()
+    eng.check_factor(force=True)
     mu_i, var_i = mu.clone(), var.clone()
     eng.incremental = False
-    eng.refactor(check=True)                                       # from-scratch posterior of the grown model
+    eng.refactor(check=True)                                       # from-scratch factor of the grown model
     eng.posterior(grid.xy, mu, var, axes=axes, g_lo=lo)
-    inc_err = (float((var_i - var).abs().max().item()) / float(eng.params["s_H"] + eng.params["rho"] ** 2 * eng.params["s_L"]),
-               float((mu_i - mu).abs().max().item()))
-    npts = hi - lo
-    h2d = npts * (16 + 16 + 8 + 8 + 8)
-    d2h = npts * 16 + w["A"] * 8 * 8
+    k0 = float(eng.params["s_H"] + eng.params["rho"] ** 2 * eng.params["s_L"])
+    inc_err = (float((var_i - var).abs().max().item()) / k0, float((mu_i - mu).abs().max().item()))
 
     if rank == 0:
-        value = G / (ms_dev * 1e-3)
+        value = G_total / (ms_dev * 1e-3)
         N = w["N"]
-        npad = npad_main
-        flops = float(npts) * N * N + 4.0 * npts * N            # algorithmic: triangular solve + mean + column norm
         pm = float(np.mean(post_ms))
-        achieved = flops / (pm * 1e-3) * 1e-12
         line = base_line(args, w, value, ms_dev)
+        if plan is not None:
+            wv = plan["ryL"] + plan["ryH"]
+            R = plan["ryL"] * plan["rxL"] + plan["ryH"] * plan["rxH"]
+            ncols = plan["ncols"]
+            macs = 0.5 * N * N * R + float(ncols) * N * R + float(ncols) * N * wv * wv + float(npts) * wv * wv
+            achieved = 2.0 * macs / (pm * 1e-3) * 1e-12
+            roof = {"bound": "tensor", "kernel": "factored posterior (gemm_f64_kernel W*B and Ux*Y^T, gram_eval_kernel; FP64 DMMA)",
+                    "achieved": achieved, "peak": DGEMM_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": achieved / DGEMM_PEAK_TFLOPS,
+                    "traffic": FACTORED_TRAFFIC_C4_1GPU if (w["name"] == "c4" and world == 1) else None,
+                    "traffic_unit": "bytes per posterior call (ncu dram__bytes_read.sum + dram__bytes_write.sum over its kernels)",
+                    "algorithmic_flops": 2.0 * macs, "chebyshev_orders": [plan["rxL"], plan["ryL"], plan["rxH"], plan["ryH"]],
+                    "kernel_ms": pm, "kernel_share_of_step": pm / ms_dev,
+                    "dense_equivalent_tflops": (float(npts) * N * N + 4.0 * npts * N) / (pm * 1e-3) * 1e-12,
+                    "peak_source": "cuBLAS DGEMM 8192^3 measured on this pool (profiles/r01_dgemm_peak.json); "
+                                   "MEASURED_PEAKS.json has no FP64 figure; DMMA issue peak 37.15",
+                    "dense_kernel": dense}
+        else:
+            flops = float(npts) * N * N + 4.0 * npts * N        # algorithmic: triangular solve + mean + column norm
+            achieved = flops / (pm * 1e-3) * 1e-12
+            roof = {"bound": "tensor", "kernel": "posterior_kernel (DMMA fp64)", "achieved": achieved,
+                    "peak": DGEMM_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": achieved / DGEMM_PEAK_TFLOPS, "traffic": None,
+                    "kernel_ms": pm, "kernel_share_of_step": pm / ms_dev,
+                    "peak_source": "cuBLAS DGEMM 8192^3 measured on this pool (profiles/r01_dgemm_peak.json)"}
         line.update({
             "dtype": "f64", "clocks": clocks, "gpu_launches": int(launches),
-            "e2e": {"value": G / (ms_e2e * 1e-3), "unit": "grid-points/s", "h2d_bytes_per_step": int(h2d),
-                    "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e},
-            "roofline": {"bound": "tensor", "kernel": "posterior_kernel (DMMA fp64)", "achieved": achieved,
-                         "peak": DGEMM_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": achieved / DGEMM_PEAK_TFLOPS,
-                         "traffic": POSTERIOR_TRAFFIC_C4_1GPU if (w["name"] == "c4" and world == 1) else None,
-                         "traffic_unit": "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum; the kernel "
-                                         "is FP64-compute bound, algorithmic minimum 0.17 GB)",
-                         "kernel_ms": pm, "kernel_share_of_step": pm / ms_dev,
-                         "peak_source": "cuBLAS DGEMM 8192^3 measured on this pool (profiles/r01_dgemm_peak.json); "
-                                        "MEASURED_PEAKS.json has no FP64 figure; DMMA issue peak 37.15"},
-            "breakdown_ms": {"fit(K+chol+inverse+whiten+tables)": float(np.mean(fit_ms)), "posterior": pm,
+            "e2e": {"value": G_total / (ms_e2e * 1e-3), "unit": "grid-points/s", "h2d_bytes_per_step": int(h2d),
+                    "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e,
+                    "api": "MFGP.updt_hifi + MFGP.predict(x_star) + compute_loss / compute_centroids / compute_max_var, "
+                           "numpy arrays in and out"},
+            "roofline": roof,
+            "breakdown_ms": {"l2_flush": None, "fit(K+chol+inverse+whiten)": float(np.mean(fit_ms)), "posterior": pm,
                              "qhull+coverage_kernels": float(np.mean(cov_ms)),
-                             "d2h+host_finish": ms_dev - pm - float(np.mean(fit_ms)) - float(np.mean(cov_ms))},
-            "incremental": {"ms_per_step": ms_inc, "value": G / (ms_inc * 1e-3), "unit": "grid-points/s",
+                             "d2h+host_finish+flush": ms_dev - pm - float(np.mean(fit_ms)) - float(np.mean(cov_ms))},
+            "incremental": {"ms_per_step": ms_inc, "value": G_total / (ms_inc * 1e-3), "unit": "grid-points/s",
                             "iterations_per_s": 1000.0 / ms_inc, "appended_per_step": int(w["A"]), "steps": inc_steps,
                             "train_points_end": int(eng.N),
                             "max_err_vs_refit": {"var_rel_k0": inc_err[0], "mu_abs": inc_err[1]},
-                            "note": "bordered Cholesky append + posterior update with the new rows only + coverage "
-                                    "step; the reference refits from scratch every iteration (that is `value`)"},
-            "check": {"loss": float(out[0]), "loss_e2e": float(out_e2e[0]), "npad": int(npad),
-                      "separable_grid_path": axes is not None},
+                            "note": "bordered Cholesky append instead of the refactor + posterior + coverage step; the "
+                                    "reference refits from scratch every iteration (that is `value`)"},
+            "check": {"loss": float(out[0]), "loss_e2e": float(out_e2e[0]), "npad": int(npad_main),
+                      "posterior_path": "factored" if plan is not None else "dense"},
         })
         if world == 1:
             pts = cpu_sample_points(w)
             t, _ = cpu_step(w, pts)
             line["cpu_baseline"] = {"value": pts / t, "unit": "grid-points/s", "cores": os.cpu_count(), "kind": "port",
-                                    "sample": f"one step on the first {pts} of {G} grid points, full N={N} training "
+                                    "sample": f"one step on the first {pts} of {npts} grid points, full N={N} training "
                                               f"set ({t:.1f} s), oracle = numpy/scipy restatement of the reference"}
         print(json.dumps(line))
     if world > 1:
@@ -470,6 +515,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS) + ["c5"])
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="N > 1: per-GPU grid shard fixed (weak, default) or the fixed grid split over the GPUs (strong)")
     args = ap.parse_args()
     if args.workload == "c5":
         run_c5(args)

@@ -39,6 +39,8 @@ class TensorAxes:
         self.ux_host = np.ascontiguousarray(ux_host, dtype=np.float64)
         self.uy_host = np.ascontiguousarray(uy_host, dtype=np.float64)
         self.nx, self.ny = int(len(ux_host)), int(len(uy_host))
+        self.xlo, self.xhi = float(self.ux_host.min()), float(self.ux_host.max())
+        self.ylo, self.yhi = float(self.uy_host.min()), float(self.uy_host.max())
         self.ux = torch.from_numpy(np.ascontiguousarray(ux_host, dtype=np.float64)).to(device)
         self.uy = torch.from_numpy(np.ascontiguousarray(uy_host, dtype=np.float64)).to(device)
 
@@ -85,7 +87,8 @@ class DeviceGP:
         # refit, and a posterior that was computed into the same (mu, var) buffers is updated with the new rows only
         self.use_factored = True      # tensor-product grids: Chebyshev-factored posterior when it is cheaper (gp_factored.cu)
         self.factored_min_gain = 2.0  # ... i.e. when its MAC count is at least this factor below the dense kernel's
-        self._fplan = None            # (key, plan) of the last factored-posterior plan
+        self._fplan = None            # (key, plan, orders) of the last factored-posterior plan
+        self._forders = None          # (key, hull, orders): Chebyshev orders and the training-point hull they cover
         self._fwork = None
         self._xrange = None           # (xmin, xmax, ymin, ymax) of the training points, refreshed by fit / append
         self.incremental = False
@@ -141,6 +144,8 @@ class DeviceGP:
         self._reserve(N)
         xt = torch.from_numpy(np.ascontiguousarray(Xt_host, dtype=np.float64).reshape(N, 2))
         yy = torch.from_numpy(np.ascontiguousarray(y_host, dtype=np.float64).reshape(N))
+        xh = xt.numpy()
+        self._xrange = (float(xh[:, 0].min()), float(xh[:, 0].max()), float(xh[:, 1].min()), float(xh[:, 1].max()))
         self.Xt[:N].copy_(xt, non_blocking=False)
         self.y[:N].copy_(yy, non_blocking=False)
         self.refactor(check=check)
@@ -220,7 +225,12 @@ class DeviceGP:
                 if N:
                     self.Xt[:N].copy_(old_x[:N])
                     self.y[:N].copy_(old_y[:N])
-            self.Xt[N:N + k].copy_(torch.from_numpy(np.ascontiguousarray(X_new_host, dtype=np.float64).reshape(k, 2)))
+            xn = np.ascontiguousarray(X_new_host, dtype=np.float64).reshape(k, 2)
+            r = self._xrange
+            self._xrange = (float(xn[:, 0].min()), float(xn[:, 0].max()), float(xn[:, 1].min()), float(xn[:, 1].max())) if r is None \
+                else (min(r[0], float(xn[:, 0].min())), max(r[1], float(xn[:, 0].max())),
+                      min(r[2], float(xn[:, 1].min())), max(r[3], float(xn[:, 1].max())))
+            self.Xt[N:N + k].copy_(torch.from_numpy(xn))
             self.y[N:N + k].copy_(torch.from_numpy(np.ascontiguousarray(y_new_host, dtype=np.float64).reshape(k)))
             self.NH += k
         if not self.N:
@@ -255,6 +265,12 @@ class DeviceGP:
             self._post = (key, self.epoch, self.N) if self.N > 0 else None
         if row_lo == self.N and row_lo > 0:
             return mu, var                       # nothing was appended since the standing posterior was computed
+        plan = None
+        if axes is not None and self.N > 0 and vcache is None and self.use_factored:
+            plan = self._factored_plan(axes, int(g_lo), G)
+        if plan is not None:                     # cheaper than any row update: recompute from the (bordered) factor
+            self._posterior_factored(axes, plan, mu, var, q_out)
+            return mu, var
         if row_lo > 0:
             if axes is not None:
                 TLx, TLy, THx, THy, ldt, _ = self.grid_tables(axes)
@@ -269,11 +285,6 @@ class DeviceGP:
                                                     row_lo, nat.ptr(mu), nat.ptr(var), nat.ptr(q_out), None, 0,
                                                     nat.stream_ptr()), "mfgp_posterior_update")
             return mu, var
-        if axes is not None and self.N > 0 and vcache is None and self.use_factored:
-            plan = self._factored_plan(axes, int(g_lo), G)
-            if plan is not None:
-                self._posterior_factored(axes, plan, mu, var, q_out)
-                return mu, var
         if axes is not None and self.N > 0:
             TLx, TLy, THx, THy, ldt, _ = self.grid_tables(axes)
             nat.check(lib.mfgp_posterior_grid(axes.ny, int(g_lo), G, nat.ptr(TLx), nat.ptr(TLy), nat.ptr(THx),
@@ -290,11 +301,34 @@ class DeviceGP:
 
     # -- factored posterior on tensor-product grids (gp_factored.cu) ---------------------------------------------------------
     def _training_range(self):
-        if self._xrange is None or self._xrange[0] != self.N:
+        """(xmin, xmax, ymin, ymax) of the training points, tracked on the host by fit / append_hifi."""
+        if self._xrange is None:
             xt = self.Xt[:self.N]
-            lo, hi = xt.min(dim=0).values.tolist(), xt.max(dim=0).values.tolist()        # one small D2H per (re)fit
-            self._xrange = (self.N, lo[0], hi[0], lo[1], hi[1])
-        return self._xrange[1:]
+            lo, hi = xt.min(dim=0).values.tolist(), xt.max(dim=0).values.tolist()
+            self._xrange = (lo[0], hi[0], lo[1], hi[1])
+        return self._xrange
+
+    def _cheb_orders(self, axes, p):
+        """(rxL, ryL, rxH, ryH) or None, cached while the training points stay inside the hull they were computed for."""
+        xlo, xhi, ylo, yhi = axes.xlo, axes.xhi, axes.ylo, axes.yhi
+        t = self._training_range()
+        c = self._forders
+        if c is not None and c[0] == (id(axes), p["l_L"], p["l_H"], p["multi"]) and c[1][0] <= t[0] and c[1][1] >= t[1] \
+                and c[1][2] <= t[2] and c[1][3] >= t[3]:
+            return c[2]
+        mx, my = 0.05 * (xhi - xlo), 0.05 * (yhi - ylo)            # a margin, so that a few new samples do not invalidate it
+        hull = (min(t[0], xlo) - mx, max(t[1], xhi) + mx, min(t[2], ylo) - my, max(t[3], yhi) + my)
+        rxH = chebyshev_order(p["l_H"], xlo, xhi, hull[0], hull[1])
+        ryH = chebyshev_order(p["l_H"], ylo, yhi, hull[2], hull[3])
+        rxL = ryL = 0
+        ok = rxH is not None and ryH is not None
+        if ok and p["multi"]:
+            rxL = chebyshev_order(p["l_L"], xlo, xhi, hull[0], hull[1])
+            ryL = chebyshev_order(p["l_L"], ylo, yhi, hull[2], hull[3])
+            ok = rxL is not None and ryL is not None
+        orders = (rxL, ryL, rxH, ryH) if ok and ryL + ryH <= 64 else None
+        self._forders = ((id(axes), p["l_L"], p["l_H"], p["multi"]), hull, orders)
+        return orders
 
     def _factored_plan(self, axes, g_lo, G):
         """Chebyshev orders + cost model.  None: keep the dense kernel (range is not whole columns, orders too large for
@@ -303,34 +337,29 @@ class DeviceGP:
         if ny < 2 or axes.nx < 2 or g_lo % ny or G % ny:
             return None
         p = self.params
-        key = (id(axes), g_lo, G, self.npad, self.N, p["l_L"], p["l_H"], p["multi"], self.factored_min_gain)
-        if self._fplan is not None and self._fplan[0] == key:
+        N = self.npad
+        dense = 0.5 * G * N * N
+        if self.factored_min_gain > 0 and dense < 4e9:      # the dense kernel needs well under a millisecond: no plan
+            return None
+        key = (id(axes), g_lo, G, self.npad, p["l_L"], p["l_H"], p["multi"], self.factored_min_gain)
+        orders = self._cheb_orders(axes, p)
+        if self._fplan is not None and self._fplan[0] == key and self._fplan[2] == orders:
             return self._fplan[1]
-        xlo, xhi = float(axes.ux_host.min()), float(axes.ux_host.max())
-        ylo, yhi = float(axes.uy_host.min()), float(axes.uy_host.max())
-        txlo, txhi, tylo, tyhi = self._training_range()
         plan = None
-        rxH = chebyshev_order(p["l_H"], xlo, xhi, txlo, txhi)
-        ryH = chebyshev_order(p["l_H"], ylo, yhi, tylo, tyhi)
-        rxL = ryL = 0
-        ok = rxH is not None and ryH is not None
-        if ok and p["multi"]:
-            rxL = chebyshev_order(p["l_L"], xlo, xhi, txlo, txhi)
-            ryL = chebyshev_order(p["l_L"], ylo, yhi, tylo, tyhi)
-            ok = rxL is not None and ryL is not None
-        if ok and ryL + ryH <= 64:
+        if orders is not None:
+            rxL, ryL, rxH, ryH = orders
             ncols = G // ny
             kL, kH = -(-rxL // 16) * 16, -(-rxH // 16) * 16
             R = ryL * kL + ryH * kH
-            N = self.npad
-            dense = 0.5 * G * N * N
             fact = 0.5 * N * N * R + ncols * N * R + ncols * N * 64 * 64 + G * 64 * 64
             if fact * self.factored_min_gain < dense:
                 chunk = max(64, min(-(-ncols // 64) * 64, ((1 << 28) // max(N * (ryL + ryH), 1)) // 64 * 64))   # <= 2 GiB of Y'
-                plan = dict(rxL=rxL, ryL=ryL, rxH=rxH, ryH=ryH, xlo=xlo, xhi=xhi, ylo=ylo, yhi=yhi, ix0=g_lo // ny,
+                plan = dict(rxL=rxL, ryL=ryL, rxH=rxH, ryH=ryH, xlo=axes.xlo, xhi=axes.xhi, ylo=axes.ylo, yhi=axes.yhi,
+                            ix0=g_lo // ny,
                             ncols=ncols, chunk=chunk, macs=fact, dense_macs=dense)
-        self._fplan = (key, plan)
+        self._fplan = (key, plan, orders)
         return plan
+
 
     def _posterior_factored(self, axes, plan, mu, var, q_out):
         lib = nat.lib()

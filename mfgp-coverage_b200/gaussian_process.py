@@ -99,11 +99,20 @@ class _GPBase:
     def predict(self, X_star):
         """Posterior mean [G,1] and variance [G] at X_star[G,2] (host arrays in, host arrays out)."""
         from ._engine import TensorAxes, detect_tensor_grid
-        xs_dev = self._upload_grid(X_star)
-        axes = None
-        if self.use_separable:
+        # the reference's loops pass the SAME x_star array every iteration (simulator.py:892): its device copy and its
+        # tensor-grid analysis are cached on the array's identity (the host array is kept alive by the cache)
+        X_star = np.asarray(X_star)
+        key = (X_star.__array_interface__["data"][0], X_star.shape, X_star.strides)
+        if self._grid_key == key:
+            xs_dev, axes, _ = self._grid_dev
+        else:
+            xs_dev = self._upload_grid(X_star)
+            axes = None
             t = detect_tensor_grid(X_star)
             axes = TensorAxes(t[0], t[1], self._dev.device) if t is not None else None
+            self._grid_key, self._grid_dev = key, (xs_dev, axes, X_star)
+        if not self.use_separable:
+            axes = None
         if not self._dev.fitted:
             self._refit(check=True)
         mu, var = self._dev.posterior(xs_dev, axes=axes)
