@@ -106,15 +106,20 @@ struct GramArgs {
     double* mu; double* var; double* qred;                     // flat outputs, index = col * ny + iy
 };
 
+// G' is symmetric: only the 36 lower 8x8 tiles (of 64) are formed.  Warp 0: lower half of block (0,0) -- 10 tiles; warp 1:
+// lower half of block (1,1) -- 10 tiles; warps 2, 3: block (1,0), column tiles {0,1} / {2,3} -- 8 tiles each.
 __global__ void __launch_bounds__(128) gram_eval_kernel(GramArgs a) {
     extern __shared__ __align__(16) double gsm[];
     double* Ts = gsm;                               // [2][G_ROWS][G_LD]  double-buffered chunk of Y'(ix)
-    double* Gs = gsm + 2 * G_ROWS * G_LD;           // [F_LW][F_LW + 1]
-    double* hs = Gs + F_LW * (F_LW + 1);            // [2][F_LW]
+    double* Gs = gsm + 2 * G_ROWS * G_LD;           // [F_LW][F_LW + 2]   (row pitch even: 16-byte loads)
+    double* hs = Gs + F_LW * (F_LW + 2);            // [2][F_LW]
+    constexpr int GP = F_LW + 2;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int col = blockIdx.x;
-    const int wm = (warp >> 1) * 32, wn = (warp & 1) * 32;
     const int gq = lane >> 2, tq = lane & 3;
+    const bool diag = warp < 2;
+    const int wm = (warp == 0) ? 0 : 32;                         // first row of the warp's tiles
+    const int wn = (warp == 0) ? 0 : (warp == 1 ? 32 : (warp == 2 ? 0 : 16));   // first column
     const double* srcL = a.YpL ? a.YpL + (int64_t)col * a.npad * a.ryL : nullptr;
     const double* srcH = a.YpH + (int64_t)col * a.npad * a.ryH;
     const int nw = a.ryL + a.ryH;
@@ -131,6 +136,7 @@ __global__ void __launch_bounds__(128) gram_eval_kernel(GramArgs a) {
         }
         cp_async_commit();
     };
+    // diag warps: acc[i][j] for j <= i (4x4 lower, 10 tiles); off-diagonal warps: acc[i][j], i < 4 row tiles, j < 2 column tiles
     double acc[4][4][2];
 #pragma unroll
     for (int i = 0; i < 4; i++)
@@ -146,35 +152,53 @@ __global__ void __launch_bounds__(128) gram_eval_kernel(GramArgs a) {
         else cp_async_wait<0>();
         __syncthreads();
         const double* T = Ts + buf * G_ROWS * G_LD;
+        if (diag) {
 #pragma unroll 4
-        for (int kk = 0; kk < G_ROWS; kk += 4) {
-            double af[4], bf[4];
+            for (int kk = 0; kk < G_ROWS; kk += 4) {
+                double af[4];
 #pragma unroll
-            for (int i = 0; i < 4; i++) af[i] = T[(kk + tq) * G_LD + wm + i * 8 + gq];      // A[m][k] = T[k][m]
+                for (int i = 0; i < 4; i++) af[i] = T[(kk + tq) * G_LD + wm + i * 8 + gq];      // A[m][k] = T[k][m]; B[k][n] = T[k][n]
 #pragma unroll
-            for (int j = 0; j < 4; j++) bf[j] = T[(kk + tq) * G_LD + wn + j * 8 + gq];      // B[k][n] = T[k][n]
+                for (int i = 0; i < 4; i++)
 #pragma unroll
-            for (int i = 0; i < 4; i++)
+                    for (int j = 0; j <= i; j++) dmma884(acc[i][j][0], acc[i][j][1], af[i], af[j]);
+            }
+        } else {
+#pragma unroll 4
+            for (int kk = 0; kk < G_ROWS; kk += 4) {
+                double af[4], bf[2];
 #pragma unroll
-                for (int j = 0; j < 4; j++) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+                for (int i = 0; i < 4; i++) af[i] = T[(kk + tq) * G_LD + wm + i * 8 + gq];
+#pragma unroll
+                for (int j = 0; j < 2; j++) bf[j] = T[(kk + tq) * G_LD + wn + j * 8 + gq];
+#pragma unroll
+                for (int i = 0; i < 4; i++)
+#pragma unroll
+                    for (int j = 0; j < 2; j++) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+            }
         }
         for (int r = hh; r < G_ROWS; r += 2) hacc += a.z[ch * G_ROWS + r] * T[r * G_LD + hc];
         __syncthreads();
     }
-    // G' and h' to shared memory
+    // G' (both triangles) and h' to shared memory
 #pragma unroll
     for (int i = 0; i < 4; i++)
 #pragma unroll
         for (int j = 0; j < 4; j++) {
+            if (diag ? (j > i) : (j >= 2)) continue;
             const int r = wm + i * 8 + gq, c = wn + j * 8 + tq * 2;
-            Gs[r * (F_LW + 1) + c] = acc[i][j][0];
-            Gs[r * (F_LW + 1) + c + 1] = acc[i][j][1];
+            Gs[r * GP + c] = acc[i][j][0];
+            Gs[r * GP + c + 1] = acc[i][j][1];
+            if (!(diag && i == j)) {                 // mirror (diagonal tiles already hold both triangles)
+                Gs[c * GP + r] = acc[i][j][0];
+                Gs[(c + 1) * GP + r] = acc[i][j][1];
+            }
         }
     hs[hh * F_LW + hc] = hacc;
     __syncthreads();
     if (tid < F_LW) hs[tid] += hs[F_LW + tid];
     __syncthreads();
-    // step 6: every grid point of the column
+    // step 6: every grid point of the column;  q = sum_l u_l (G_ll u_l + 2 sum_{c<l} G_lc u_c)
     for (int iy = tid; iy < a.ny; iy += 128) {
         const double* up = a.Uy + (int64_t)iy * F_LW;
         double u[F_LW];
@@ -184,14 +208,25 @@ __global__ void __launch_bounds__(128) gram_eval_kernel(GramArgs a) {
             u[l] = t.x; u[l + 1] = t.y;
         }
         double q = 0.0, m = 0.0;
-        for (int l = 0; l < nw; l++) {
-            const double* g = Gs + l * (F_LW + 1);
-            double s = 0.0;
 #pragma unroll
-            for (int c = 0; c < F_LW; c++) s = fma(g[c], u[c], s);
-            // u[] is indexed dynamically below only through this select chain-free form:
-            q = fma(s, up[l], q);
-            m = fma(hs[l], up[l], m);
+        for (int l = 0; l < F_LW; l += 2) {          // rows l, l+1 together: 16-byte loads of G
+            const double* g0 = Gs + l * GP;
+            const double* g1 = g0 + GP;
+            double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+            for (int c = 0; c < l; c += 2) {
+                const double2 a0 = *reinterpret_cast<const double2*>(g0 + c);
+                const double2 a1 = *reinterpret_cast<const double2*>(g1 + c);
+                s0 = fma(a0.x, u[c], s0); s0 = fma(a0.y, u[c + 1], s0);
+                s1 = fma(a1.x, u[c], s1); s1 = fma(a1.y, u[c + 1], s1);
+            }
+            const double2 d0 = *reinterpret_cast<const double2*>(g0 + l);
+            const double2 d1 = *reinterpret_cast<const double2*>(g1 + l);
+            s1 = fma(d1.x, u[l], s1);                                  // G[l+1][l] is below the diagonal of row l+1
+            q = fma(u[l], fma(2.0, s0, d0.x * u[l]), q);
+            q = fma(u[l + 1], fma(2.0, s1, d1.y * u[l + 1]), q);
+            m = fma(hs[l], u[l], m);
+            m = fma(hs[l + 1], u[l + 1], m);
         }
         const int64_t gidx = (int64_t)(a.col_begin + col) * a.ny + iy;
         a.var[gidx] = a.k0 - q;
@@ -286,7 +321,7 @@ extern "C" int mfgp_posterior_grid_factored(const double* ux, int64_t nx, const 
         int rc = launch_gemm(g, false, 1, st);
         if (rc) return rc;
     }
-    const size_t gsmem = sizeof(double) * (2 * G_ROWS * G_LD + F_LW * (F_LW + 1) + 2 * F_LW);
+    const size_t gsmem = sizeof(double) * (2 * G_ROWS * G_LD + F_LW * (F_LW + 2) + 2 * F_LW);
     MFGP_CUDA_CHECK(cudaFuncSetAttribute(gram_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));
     for (int64_t c0 = 0; c0 < ncols; c0 += chunk) {
         const int64_t cc = (ncols - c0 < chunk) ? ncols - c0 : chunk;
