@@ -39,7 +39,9 @@ WORKLOADS = {
 # profiles/r01_posterior_v3_ncu_summary.txt (18.883 GB read + 0.040 GB written); algorithmic minimum 32 G + 8 N^2 = 0.17 GB:
 # W (67 MB used) is re-read from L2 by every CTA and only partly stays resident next to the factor tables.
 POSTERIOR_TRAFFIC_C4_1GPU = 18.883344e9 + 39.72864e6
-FACTORED_TRAFFIC_C4_1GPU = None      # filled from the ncu capture of the factored posterior (profiles/)
+# DRAM bytes (read + write) of ONE factored posterior call on the c4 grid, summed over its 14 kernels
+# (profiles/r01_factored_posterior_launches.csv); ~4 GB of it is the Y' intermediate written once and read once.
+FACTORED_TRAFFIC_C4_1GPU = 5.216e9
 DGEMM_PEAK_TFLOPS = 35.41   # cuBLAS DGEMM 8192^3 measured on this pool's B200 (profiles/r01_dgemm_peak.json);
 #                             MEASURED_PEAKS.json carries no FP64 figure.  DMMA issue peak: 37.15 (r01_fp64_pipes.log)
 
