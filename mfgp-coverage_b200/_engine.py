@@ -353,7 +353,7 @@ class DeviceGP:
             R = ryL * kL + ryH * kH
             fact = 0.5 * N * N * R + ncols * N * R + ncols * N * 64 * 64 + G * 64 * 64
             if fact * self.factored_min_gain < dense:
-                chunk = max(64, min(-(-ncols // 64) * 64, ((1 << 28) // max(N * (ryL + ryH), 1)) // 64 * 64))   # <= 2 GiB of Y'
+                chunk = max(64, min(-(-ncols // 64) * 64, ((1 << 28) // max(self.cap * (ryL + ryH), 1)) // 64 * 64))   # <= 2 GiB of Y'
                 plan = dict(rxL=rxL, ryL=ryL, rxH=rxH, ryH=ryH, xlo=axes.xlo, xhi=axes.xhi, ylo=axes.ylo, yhi=axes.yhi,
                             ix0=g_lo // ny,
                             ncols=ncols, chunk=chunk, macs=fact, dense_macs=dense)
@@ -363,7 +363,8 @@ class DeviceGP:
 
     def _posterior_factored(self, axes, plan, mu, var, q_out):
         lib = nat.lib()
-        need = int(lib.mfgp_factored_workspace_bytes(self.npad, plan["ncols"], axes.ny, plan["rxL"], plan["ryL"], plan["rxH"],
+        # sized for the CAPACITY of the factor buffers, so appended samples do not reallocate gigabytes every iteration
+        need = int(lib.mfgp_factored_workspace_bytes(self.cap, plan["ncols"], axes.ny, plan["rxL"], plan["ryL"], plan["rxH"],
                                                      plan["ryH"], plan["chunk"]))
         if self._fwork is None or self._fwork.numel() * 8 < need:
             self._fwork = torch.empty(need // 8 + 8, dtype=torch.float64, device=self.device)

@@ -88,6 +88,8 @@ def _grid_for(arr):
     if len(_grid_cache) > 8:
         _grid_cache.clear()
     g = CoverageGrid(arr[:, [0, 1]], arr[:, 2] if arr.shape[1] >= 3 else None)
+    # extent of the grid (simulator.py:264-271 clamps the centroids to it), computed once per grid, not per call
+    g.extent = (np.amin(arr[:, 0]), np.amax(arr[:, 0]), np.amin(arr[:, 1]), np.amax(arr[:, 1]))
     _grid_cache[key] = (g, arr)
     return g
 
@@ -139,8 +141,7 @@ def compute_centroids(vor, x_star, mu_star):
     w = mu_star if torch.is_tensor(mu_star) else torch.from_numpy(
         np.ascontiguousarray(mu_star, dtype=np.float64).reshape(-1)).to(grid.device)
     res = grid.assign_reduce(lloyd_vor=vor, w=w)
-    return cv.centroids_from_partials(res["cent"].cpu().numpy(), vor.areas(), np.amin(x_star[:, 0]),
-                                      np.amax(x_star[:, 0]), np.amin(x_star[:, 1]), np.amax(x_star[:, 1]))
+    return cv.centroids_from_partials(res["cent"].cpu().numpy(), vor.areas(), *grid.extent)
 
 
 def _as_var_vector(var_star, device):
