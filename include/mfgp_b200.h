@@ -137,6 +137,27 @@ int mfgp_posterior_grid_factored(const double* ux, int64_t nx, const double* uy,
 int64_t mfgp_factored_workspace_bytes(int64_t npad, int64_t ncols, int64_t ny, int64_t rxL, int64_t ryL, int64_t rxH,
                                       int64_t ryH, int64_t chunk_cols);
 
+/* Fused fit + factored posterior (the from-scratch iteration of the reference, simulator.py:888-892, on a tensor grid):
+ *   mfgp_build_train_cov  ->  mfgp_factored_prepare (B = [B_L | B_H | y - mean], mfgp_factored_rhs_cols columns)
+ *   ->  mfgp_cholesky_solve (K -> L in place, diagonal-block inverses into W, Ball -> L^-1 Ball; the right-hand-side tile
+ *       GEMMs run on an internal side stream behind the latency-bound panel chain)
+ *   ->  mfgp_posterior_grid_factored_solved (steps 4-6; z_out receives the whitened observations).
+ * Neither the explicit inverse (mfgp_tri_inverse) nor the product W B is formed; run mfgp_tri_inverse afterwards only if W
+ * is needed (dense posterior, mfgp_cholesky_append, choi_greedy).  Same geometry / order arguments and the same `work`
+ * buffer for prepare and solved. */
+int64_t mfgp_factored_rhs_cols(int64_t rxL, int64_t ryL, int64_t rxH, int64_t ryH);
+int mfgp_factored_prepare(const double* ux, int64_t nx, const double* uy, int64_t ny, int64_t ix0, int64_t ncols,
+                          const double* Xt, const double* y, int64_t NL, int64_t NH, int64_t npad, const mfgp_params* p_host,
+                          int64_t rxL, int64_t ryL, int64_t rxH, int64_t ryH, double xlo, double xhi, double ylo, double yhi,
+                          int64_t chunk_cols, double* Ball, int64_t ldB, void* work, int64_t work_bytes, void* stream);
+int mfgp_cholesky_solve(double* K, int64_t npad, int64_t ld, double* W, int64_t ldw, int32_t* info, double* Bm, int64_t ldb,
+                        int64_t R, void* stream);
+int mfgp_posterior_grid_factored_solved(const double* ux, int64_t nx, const double* uy, int64_t ny, int64_t ix0, int64_t ncols,
+                                        const double* Xt, int64_t NL, int64_t NH, int64_t npad, const mfgp_params* p_host,
+                                        int64_t rxL, int64_t ryL, int64_t rxH, int64_t ryH, double xlo, double xhi, double ylo,
+                                        double yhi, int64_t chunk_cols, const double* Yall, int64_t ldY, double* z_out,
+                                        double* mu, double* var, double* qred, void* work, int64_t work_bytes, void* stream);
+
 /* ---- coverage step: replaces simulator.py in_polygon :105-124, compute_loss :194-228, compute_centroids :231-283,
  *      compute_max_var :286-323, compute_sample_clusters :377-412 ------------------------------------------------ */
 

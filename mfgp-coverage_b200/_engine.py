@@ -91,6 +91,10 @@ class DeviceGP:
         self._forders = None          # (key, hull, orders): Chebyshev orders and the training-point hull they cover
         self._fwork = None
         self._xrange = None           # (xmin, xmax, ymin, ymax) of the training points, refreshed by fit / append
+        self.defer_fit = False        # True: refactor(check=False) only marks the factor stale; the first consumer factorises --
+        self._dirty = False           #   a factored posterior then fuses fit + forward substitution (mfgp_cholesky_solve)
+        self._w_partial = False       # True: W holds only the diagonal-block inverses (mfgp_tri_inverse still to run)
+        self._fB = None               # right-hand-side matrix of the fused fit
         self.incremental = False
         self.lazy_check = False       # True: the caller reads `info` itself (cov_finish carries it home): no sync per fit
         self.epoch = 0                # bumped by every FULL refactor: standing posteriors become stale
@@ -152,6 +156,15 @@ class DeviceGP:
 
     def refactor(self, check=True):
         """K assembly -> Cholesky -> inverse -> whitening for the data already resident in Xt / y."""
+        if self.defer_fit and not check:
+            self.npad = nat.npad(self.N)
+            self._dirty = True
+            self._w_partial = False
+            self.fit_id += 1
+            self.epoch += 1
+            return
+        self._dirty = False
+        self._w_partial = False
         N = self.N
         lib = nat.lib()
         st = nat.stream_ptr()
@@ -172,6 +185,21 @@ class DeviceGP:
         if check:
             self.check_factor()
 
+    def ensure_factor(self, need_inverse=True):
+        """Bring a deferred / partially finished factorisation up to date (no-op otherwise)."""
+        if self._dirty:
+            self.defer_fit, keep = False, self.defer_fit
+            try:
+                self.fit_id -= 1
+                self.epoch -= 1
+                self.refactor(check=False)
+            finally:
+                self.defer_fit = keep
+        if need_inverse and self._w_partial:
+            nat.check(nat.lib().mfgp_tri_inverse(nat.ptr(self.K), self.npad, self.cap, nat.ptr(self.W), self.cap,
+                                                 nat.ptr(self.work), nat.stream_ptr()), "mfgp_tri_inverse")
+            self._w_partial = False
+
     def _append_factor(self, NH_old, check=True):
         """Bordered update of L, W, z for the rows appended since NH_old (mfgp_cholesky_append)."""
         lib = nat.lib()
@@ -187,6 +215,7 @@ class DeviceGP:
     def grid_tables(self, axes):
         """Per-axis factor tables of the separable kernel for a tensor-product grid (`axes` = TensorAxes), rebuilt
         after every refit (mfgp_grid_tables)."""
+        self.ensure_factor(need_inverse=False)
         if self._tab is not None and self._tab[0] is axes and self._tab[1] == self.fit_id:
             return self._tab[2:]
         ldt = self.cap
@@ -207,6 +236,7 @@ class DeviceGP:
     def check_factor(self, force=False):
         if self.lazy_check and not force:
             return
+        self.ensure_factor(need_inverse=False)
         info = int(self.info.item())
         if info != 0:
             raise np.linalg.LinAlgError(f"Matrix is not positive definite (pivot {info - 1})")
@@ -216,6 +246,8 @@ class DeviceGP:
         is rebuilt from scratch, as in the reference (which does so even when nothing was added)."""
         k = 0 if X_new_host is None else int(np.asarray(X_new_host).reshape(-1, 2).shape[0])
         border = self.incremental and self.fitted and self.N > 0 and self.npad == nat.npad(self.N)
+        if border:
+            self.ensure_factor()
         NH_old = self.NH
         if k:
             N = self.N
@@ -269,8 +301,13 @@ class DeviceGP:
         if axes is not None and self.N > 0 and vcache is None and self.use_factored:
             plan = self._factored_plan(axes, int(g_lo), G)
         if plan is not None:                     # cheaper than any row update: recompute from the (bordered) factor
-            self._posterior_factored(axes, plan, mu, var, q_out)
+            if self._dirty:
+                self._fit_and_posterior_fused(axes, plan, mu, var, q_out)
+            else:
+                self.ensure_factor()
+                self._posterior_factored(axes, plan, mu, var, q_out)
             return mu, var
+        self.ensure_factor()
         if row_lo > 0:
             if axes is not None:
                 TLx, TLy, THx, THy, ldt, _ = self.grid_tables(axes)
@@ -361,13 +398,46 @@ class DeviceGP:
         return plan
 
 
-    def _posterior_factored(self, axes, plan, mu, var, q_out):
-        lib = nat.lib()
+    def _factored_work(self, axes, plan):
         # sized for the CAPACITY of the factor buffers, so appended samples do not reallocate gigabytes every iteration
-        need = int(lib.mfgp_factored_workspace_bytes(self.cap, plan["ncols"], axes.ny, plan["rxL"], plan["ryL"], plan["rxH"],
-                                                     plan["ryH"], plan["chunk"]))
+        need = int(nat.lib().mfgp_factored_workspace_bytes(self.cap, plan["ncols"], axes.ny, plan["rxL"], plan["ryL"],
+                                                           plan["rxH"], plan["ryH"], plan["chunk"]))
         if self._fwork is None or self._fwork.numel() * 8 < need:
             self._fwork = torch.empty(need // 8 + 8, dtype=torch.float64, device=self.device)
+        return self._fwork
+
+    def _fit_and_posterior_fused(self, axes, plan, mu, var, q_out):
+        """From-scratch iteration on a tensor grid in one pass: K -> (L, diagonal-block inverses) with the right-hand sides
+        [B_L | B_H | y - mean] forward-substituted on the side stream -> steps 4-6 (see include/mfgp_b200.h)."""
+        lib = nat.lib()
+        st = nat.stream_ptr()
+        pp = ctypes.byref(self.pstruct)
+        npad, ld = self.npad, self.cap
+        o = (plan["rxL"], plan["ryL"], plan["rxH"], plan["ryH"])
+        R = int(lib.mfgp_factored_rhs_cols(*o))
+        if self._fB is None or self._fB.numel() < self.cap * R:
+            self._fB = torch.empty(self.cap * R, dtype=torch.float64, device=self.device)
+        work = self._factored_work(axes, plan)
+        geom = (ctypes.c_double(plan["xlo"]), ctypes.c_double(plan["xhi"]), ctypes.c_double(plan["ylo"]),
+                ctypes.c_double(plan["yhi"]), plan["chunk"])
+        nat.check(lib.mfgp_build_train_cov(nat.ptr(self.Xt), self.NL, self.NH, pp, nat.ptr(self.K), npad, ld,
+                                           nat.ptr(self.Tt), st), "mfgp_build_train_cov")
+        nat.check(lib.mfgp_factored_prepare(nat.ptr(axes.ux), axes.nx, nat.ptr(axes.uy), axes.ny, plan["ix0"], plan["ncols"],
+                                            nat.ptr(self.Xt), nat.ptr(self.y), self.NL, self.NH, npad, pp, *o, *geom,
+                                            nat.ptr(self._fB), R, nat.ptr(work), work.numel() * 8, st),
+                  "mfgp_factored_prepare")
+        nat.check(lib.mfgp_cholesky_solve(nat.ptr(self.K), npad, ld, nat.ptr(self.W), ld, nat.ptr(self.info),
+                                          nat.ptr(self._fB), R, R, st), "mfgp_cholesky_solve")
+        nat.check(lib.mfgp_posterior_grid_factored_solved(
+            nat.ptr(axes.ux), axes.nx, nat.ptr(axes.uy), axes.ny, plan["ix0"], plan["ncols"], nat.ptr(self.Xt), self.NL,
+            self.NH, npad, pp, *o, *geom, nat.ptr(self._fB), R, nat.ptr(self.z), nat.ptr(mu), nat.ptr(var), nat.ptr(q_out),
+            nat.ptr(work), work.numel() * 8, st), "mfgp_posterior_grid_factored_solved")
+        self._dirty = False
+        self._w_partial = True
+
+    def _posterior_factored(self, axes, plan, mu, var, q_out):
+        lib = nat.lib()
+        self._factored_work(axes, plan)
         nat.check(lib.mfgp_posterior_grid_factored(
             nat.ptr(axes.ux), axes.nx, nat.ptr(axes.uy), axes.ny, plan["ix0"], plan["ncols"], nat.ptr(self.Xt), self.NL, self.NH,
             nat.ptr(self.W), self.npad, self.cap, nat.ptr(self.z), ctypes.byref(self.pstruct), plan["rxL"], plan["ryL"],
@@ -376,6 +446,7 @@ class DeviceGP:
             self._fwork.numel() * 8, nat.stream_ptr()), "mfgp_posterior_grid_factored")
 
     def clone(self):
+        self.ensure_factor()
         other = DeviceGP(self.device)
         other.NL, other.NH, other.npad, other.cap = self.NL, self.NH, self.npad, self.cap
         other.params = None if self.params is None else dict(self.params)
@@ -390,5 +461,6 @@ class DeviceGP:
         other.use_factored = self.use_factored
         other.factored_min_gain = self.factored_min_gain
         other.lazy_check = self.lazy_check
+        other.defer_fit = self.defer_fit
         other.epoch = self.epoch
         return other

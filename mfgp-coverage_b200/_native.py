@@ -59,6 +59,17 @@ SIGNATURES = {
                                              c_int64, c_int64, c_int64, c_double, c_double, c_double, c_double, c_int64,
                                              c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "mfgp_factored_workspace_bytes": (c_int64, [c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64]),
+    "mfgp_factored_rhs_cols": (c_int64, [c_int64, c_int64, c_int64, c_int64]),
+    "mfgp_factored_prepare": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_int64,
+                                      c_int64, c_int64, POINTER(MfgpParams), c_int64, c_int64, c_int64, c_int64, c_double,
+                                      c_double, c_double, c_double, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p]),
+    "mfgp_cholesky_solve": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int64,
+                                    c_void_p]),
+    "mfgp_posterior_grid_factored_solved": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64,
+                                                    c_int64, c_int64, POINTER(MfgpParams), c_int64, c_int64, c_int64,
+                                                    c_int64, c_double, c_double, c_double, c_double, c_int64, c_void_p,
+                                                    c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
+                                                    c_void_p]),
     "cov_assign_reduce": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64,
                                   c_void_p, c_int64, c_void_p, c_void_p, c_int64,
                                   c_void_p, c_int64, c_void_p, c_void_p, c_int64,

@@ -83,14 +83,34 @@ __global__ void cheb_basis_kernel(const double* __restrict__ u, int i0, int coun
 
 // ---- step 2: B[n][l][k] = coef[n] Cy[l][n] Cx[k][n] ------------------------------------------------------------------------
 __global__ void build_B_kernel(const double* __restrict__ Cx, const double* __restrict__ Cy, int npad, int N, int NL, int rx, int ry,
-                               int kpad, double coef_lo, double coef_hi, double* __restrict__ B) {
+                               int kpad, double coef_lo, double coef_hi, double* __restrict__ B, int64_t ldB) {
     const int n = blockIdx.y;
     const int e = blockIdx.x * blockDim.x + threadIdx.x;       // (l, k)
     if (e >= ry * kpad) return;
     const int l = e / kpad, k = e % kpad;
     double v = 0.0;
     if (n < N && k < rx) v = (n < NL ? coef_lo : coef_hi) * Cy[(int64_t)l * npad + n] * Cx[(int64_t)k * npad + n];
-    B[(int64_t)n * ry * kpad + e] = v;
+    B[(int64_t)n * ldB + e] = v;
+}
+
+// centred observations as one more 64-wide block of right-hand sides: column 0 = y - mean (gaussian_process.py:133, :419-424)
+__global__ void build_z_block_kernel(const double* __restrict__ y, int npad, int N, int NL, double mean_L, double mean_H,
+                                     double* __restrict__ B, int64_t ldB) {
+    const int n = blockIdx.x, c = threadIdx.x;
+    double v = 0.0;
+    if (c == 0 && n < N) v = y[n] - (n < NL ? mean_L : mean_H);
+    B[(int64_t)n * ldB + c] = v;
+}
+
+// Y_all[n][off + e] -> contiguous Y_P[n][e] (step 4 views Y_P as a [(n, l)] x [k] matrix), and the solved z column
+__global__ void unpack_Y_kernel(const double* __restrict__ Yall, int64_t ldY, int off, int cols, double* __restrict__ Yp) {
+    const int n = blockIdx.y;
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < cols) Yp[(int64_t)n * cols + e] = Yall[(int64_t)n * ldY + off + e];
+}
+__global__ void unpack_z_kernel(const double* __restrict__ Yall, int64_t ldY, int off, int npad, double* __restrict__ z) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n < npad) z[n] = Yall[(int64_t)n * ldY + off];
 }
 
 // ---- steps 5 + 6: one CTA per grid column --------------------------------------------------------------------------------
@@ -239,7 +259,7 @@ __global__ void __launch_bounds__(128) gram_eval_kernel(GramArgs a) {
 
 using namespace mfgp;
 
-// plan sizes (host helper, also used by the Python side to size the workspace)
+// ---- host side -------------------------------------------------------------------------------------------------------------
 static inline int64_t round_up(int64_t v, int64_t m) { return (v + m - 1) / m * m; }
 
 extern "C" int64_t mfgp_factored_workspace_bytes(int64_t npad, int64_t ncols, int64_t ny, int64_t rxL, int64_t ryL, int64_t rxH,
@@ -247,101 +267,205 @@ extern "C" int64_t mfgp_factored_workspace_bytes(int64_t npad, int64_t ncols, in
     const int64_t kL = round_up(rxL, 16), kH = round_up(rxH, 16);
     const int64_t ncp = round_up(ncols, 64), ch = round_up(chunk_cols, 64);
     int64_t d = 0;
+    d += ny * 64 + npad;                                       // Uy, solved z
     d += (rxL + ryL + rxH + ryH) * npad;                       // coefficient tables
     d += 2 * npad * (ryL * kL + ryH * kH);                     // B and Y
     d += ncp * (kL + kH);                                      // Ux
-    d += ny * 64;                                              // Uy
     d += ch * npad * (ryL + ryH);                              // Y' of one chunk
     return d * 8 + 4096;
 }
 
-// Factored posterior for the whole columns [ix0, ix0 + ncols) of the tensor-product grid ux[nx] x uy[ny] (x-major); outputs
-// are flat over those columns: index (ix - ix0) * ny + iy.  rx*/ry*: Chebyshev orders per axis and part (ryL, ryH multiples
-// of 4, ryL + ryH <= 64, all <= 64; rxL = ryL = 0 for a single-fidelity model) -- chosen by the caller so that the factor
-// tables are reproduced to rounding (mfgp_coverage_b200/_engine.py: chebyshev_orders).
-extern "C" int mfgp_posterior_grid_factored(const double* ux, int64_t nx, const double* uy, int64_t ny, int64_t ix0, int64_t ncols,
-                                            const double* Xt, int64_t NL, int64_t NH, const double* W, int64_t npad, int64_t ldw,
-                                            const double* z, const mfgp_params* p_host, int64_t rxL, int64_t ryL, int64_t rxH,
-                                            int64_t ryH, double xlo, double xhi, double ylo, double yhi, int64_t chunk_cols,
-                                            double* mu, double* var, double* qred, void* work, int64_t work_bytes, void* stream) {
-    if (!ux || !uy || !Xt || !W || !z || !p_host || !mu || !var || !work) return MFGP_ERR_INVALID;
-    const int64_t N = NL + NH;
-    if (N <= 0 || npad < N || npad % MFGP_TILE || ldw < npad || ncols <= 0 || ix0 < 0 || ix0 + ncols > nx || ny <= 0) return MFGP_ERR_INVALID;
-    const bool multi = p_host->multi != 0;
-    if (!multi && (rxL || ryL || NL)) return MFGP_ERR_INVALID;
-    if (rxH <= 0 || ryH <= 0 || rxH > F_MAXR || ryH > F_MAXR || rxL > F_MAXR || ryL > F_MAXR || (ryL % 4) || (ryH % 4) || ryL + ryH > F_LW)
-        return MFGP_ERR_INVALID;
-    if (multi && (rxL <= 0 || ryL <= 0)) return MFGP_ERR_INVALID;
-    if (!(xhi > xlo) || !(yhi > ylo) || chunk_cols <= 0) return MFGP_ERR_INVALID;
-    if (work_bytes < mfgp_factored_workspace_bytes(npad, ncols, ny, rxL, ryL, rxH, ryH, chunk_cols)) return MFGP_ERR_INVALID;
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const DevParams dp = make_dev_params(*p_host);
-    const int64_t ncp = round_up(ncols, 64), chunk = round_up(chunk_cols, 64);
+// number of right-hand-side columns of the fused fit (mfgp_cholesky_solve): [B_L | B_H | z block]
+extern "C" int64_t mfgp_factored_rhs_cols(int64_t rxL, int64_t ryL, int64_t rxH, int64_t ryH) {
+    return ryL * round_up(rxL, 16) + ryH * round_up(rxH, 16) + 64;
+}
 
-    FPart parts[2];
-    int nparts = 0;
+namespace {
+struct FGeom {
+    const double* ux; int64_t nx; const double* uy; int64_t ny; int64_t ix0, ncols;
+    const double* Xt; int64_t NL, NH, npad;
+    const mfgp_params* p;
+    int64_t rxL, ryL, rxH, ryH;
+    double xlo, xhi, ylo, yhi;
+    int64_t chunk;
+};
+struct FLayout {
+    FPart parts[2]; int nparts; double* Uy; double* zbuf; int64_t ncp, chunk; bool multi;
+};
+
+int f_validate(const FGeom& g, void* work, int64_t work_bytes) {
+    if (!g.ux || !g.uy || !g.Xt || !g.p || !work) return MFGP_ERR_INVALID;
+    const int64_t N = g.NL + g.NH;
+    if (N <= 0 || g.npad < N || g.npad % MFGP_TILE || g.ncols <= 0 || g.ix0 < 0 || g.ix0 + g.ncols > g.nx || g.ny <= 0) return MFGP_ERR_INVALID;
+    const bool multi = g.p->multi != 0;
+    if (!multi && (g.rxL || g.ryL || g.NL)) return MFGP_ERR_INVALID;
+    if (g.rxH <= 0 || g.ryH <= 0 || g.rxH > F_MAXR || g.ryH > F_MAXR || g.rxL > F_MAXR || g.ryL > F_MAXR || (g.ryL % 4) || (g.ryH % 4) ||
+        g.ryL + g.ryH > F_LW)
+        return MFGP_ERR_INVALID;
+    if (multi && (g.rxL <= 0 || g.ryL <= 0)) return MFGP_ERR_INVALID;
+    if (!(g.xhi > g.xlo) || !(g.yhi > g.ylo) || g.chunk <= 0) return MFGP_ERR_INVALID;
+    if (work_bytes < mfgp_factored_workspace_bytes(g.npad, g.ncols, g.ny, g.rxL, g.ryL, g.rxH, g.ryH, g.chunk)) return MFGP_ERR_INVALID;
+    return MFGP_OK;
+}
+
+void f_carve(const FGeom& g, void* work, FLayout& L) {
+    L.multi = g.p->multi != 0;
+    L.ncp = round_up(g.ncols, 64); L.chunk = round_up(g.chunk, 64);
+    L.nparts = 0;
     double* wp = static_cast<double*>(work);
     auto carve = [&](int64_t n) { double* r = wp; wp += n; return r; };
-    double* Uy = carve(ny * 64);
+    L.Uy = carve(g.ny * 64);
+    L.zbuf = carve(g.npad);
     auto add_part = [&](int rx, int ry, double l, int loff) {
-        FPart& f = parts[nparts++];
+        FPart& f = L.parts[L.nparts++];
         f.rx = rx; f.ry = ry; f.kpad = (int)round_up(rx, 16); f.loff = loff; f.inv_l = 1.0 / l;
-        f.Cx = carve((int64_t)rx * npad); f.Cy = carve((int64_t)ry * npad);
-        f.B = carve(npad * (int64_t)ry * f.kpad); f.Y = carve(npad * (int64_t)ry * f.kpad);
-        f.Ux = carve(ncp * f.kpad);
-        f.Yp = carve(chunk * npad * ry);
+        f.Cx = carve((int64_t)rx * g.npad); f.Cy = carve((int64_t)ry * g.npad);
+        f.B = carve(g.npad * (int64_t)ry * f.kpad); f.Y = carve(g.npad * (int64_t)ry * f.kpad);
+        f.Ux = carve(L.ncp * f.kpad);
+        f.Yp = carve(L.chunk * g.npad * ry);
     };
-    if (multi) add_part((int)rxL, (int)ryL, p_host->l_L, 0);
-    add_part((int)rxH, (int)ryH, p_host->l_H, multi ? (int)ryL : 0);
+    if (L.multi) add_part((int)g.rxL, (int)g.ryL, g.p->l_L, 0);
+    add_part((int)g.rxH, (int)g.ryH, g.p->l_H, L.multi ? (int)g.ryL : 0);
+}
 
-    MFGP_CUDA_CHECK(cudaMemsetAsync(Uy, 0, sizeof(double) * ny * 64, st));
-    for (int pi = 0; pi < nparts; pi++) {
-        FPart& f = parts[pi];
-        const bool lofi_part = multi && pi == 0;
-        // step 1: coefficient tables of the training points, basis tables of the grid axes
-        cheb_coef_kernel<<<(unsigned)((npad + 7) / 8), 256, 0, st>>>(Xt, (int)N, (int)npad, 0, xlo, xhi, f.inv_l, f.rx, f.Cx);
+// steps 1 + 2: tables, then B_P either into the part's own buffer (Ball == nullptr) or into the column range of Ball
+int f_tables_and_B(const FGeom& g, FLayout& L, double* Ball, int64_t ldB, cudaStream_t st) {
+    const DevParams dp = make_dev_params(*g.p);
+    const int64_t N = g.NL + g.NH, npad = g.npad;
+    MFGP_CUDA_CHECK(cudaMemsetAsync(L.Uy, 0, sizeof(double) * g.ny * 64, st));
+    int64_t off = 0;
+    for (int pi = 0; pi < L.nparts; pi++) {
+        FPart& f = L.parts[pi];
+        const bool lofi_part = L.multi && pi == 0;
+        cheb_coef_kernel<<<(unsigned)((npad + 7) / 8), 256, 0, st>>>(g.Xt, (int)N, (int)npad, 0, g.xlo, g.xhi, f.inv_l, f.rx, f.Cx);
         MFGP_LAUNCH_CHECK();
-        cheb_coef_kernel<<<(unsigned)((npad + 7) / 8), 256, 0, st>>>(Xt, (int)N, (int)npad, 1, ylo, yhi, f.inv_l, f.ry, f.Cy);
+        cheb_coef_kernel<<<(unsigned)((npad + 7) / 8), 256, 0, st>>>(g.Xt, (int)N, (int)npad, 1, g.ylo, g.yhi, f.inv_l, f.ry, f.Cy);
         MFGP_LAUNCH_CHECK();
-        MFGP_CUDA_CHECK(cudaMemsetAsync(f.Ux, 0, sizeof(double) * ncp * f.kpad, st));
-        cheb_basis_kernel<<<(unsigned)((ncp + 127) / 128), 128, 0, st>>>(ux, (int)ix0, (int)ncols, (int)ncp, xlo, xhi, f.rx, f.kpad, 0, f.Ux);
+        MFGP_CUDA_CHECK(cudaMemsetAsync(f.Ux, 0, sizeof(double) * L.ncp * f.kpad, st));
+        cheb_basis_kernel<<<(unsigned)((L.ncp + 127) / 128), 128, 0, st>>>(g.ux, (int)g.ix0, (int)g.ncols, (int)L.ncp, g.xlo, g.xhi, f.rx,
+                                                                        f.kpad, 0, f.Ux);
         MFGP_LAUNCH_CHECK();
-        cheb_basis_kernel<<<(unsigned)((ny + 127) / 128), 128, 0, st>>>(uy, 0, (int)ny, (int)ny, ylo, yhi, f.ry, 64, f.loff, Uy);
+        cheb_basis_kernel<<<(unsigned)((g.ny + 127) / 128), 128, 0, st>>>(g.uy, 0, (int)g.ny, (int)g.ny, g.ylo, g.yhi, f.ry, 64, f.loff, L.Uy);
         MFGP_LAUNCH_CHECK();
-        // step 2: B.  lofi part: rho s_L (lofi columns) / rho^2 s_L (hifi columns); hifi part: 0 / s_H  (gaussian_process.py:426-429)
+        // lofi part: rho s_L (lofi columns) / rho^2 s_L (hifi columns); hifi part: 0 / s_H  (gaussian_process.py:426-429)
         const double c_lo = lofi_part ? dp.rho * dp.s_L : 0.0;
         const double c_hi = lofi_part ? dp.rho2 * dp.s_L : dp.s_H;
-        dim3 bgrid((unsigned)((f.ry * f.kpad + 127) / 128), (unsigned)npad);
-        build_B_kernel<<<bgrid, 128, 0, st>>>(f.Cx, f.Cy, (int)npad, (int)N, (int)NL, f.rx, f.ry, f.kpad, c_lo, c_hi, f.B);
+        const int cols = f.ry * f.kpad;
+        dim3 bgrid((unsigned)((cols + 127) / 128), (unsigned)npad);
+        build_B_kernel<<<bgrid, 128, 0, st>>>(f.Cx, f.Cy, (int)npad, (int)N, (int)g.NL, f.rx, f.ry, f.kpad, c_lo, c_hi,
+                                             Ball ? Ball + off : f.B, Ball ? ldB : (int64_t)cols);
         MFGP_LAUNCH_CHECK();
-        // step 3: Y = W B  (W lower triangular: k < m0 + 64)
-        GemmArgs g{};
-        g.A = W; g.lda = ldw; g.B = f.B; g.ldb = (int64_t)f.ry * f.kpad; g.C = f.Y; g.ldc = (int64_t)f.ry * f.kpad;
-        g.M = (int)npad; g.N = f.ry * f.kpad; g.K = (int)npad; g.alpha = 1.0; g.beta = 0.0; g.mode = GEMM_A_LOWER;
-        int rc = launch_gemm(g, false, 1, st);
-        if (rc) return rc;
+        off += cols;
     }
+    return MFGP_OK;
+}
+
+// steps 4 - 6 from Y_P (parts[].Y) and the whitened observations z
+int f_tail(const FGeom& g, FLayout& L, const double* z, double* mu, double* var, double* qred, cudaStream_t st) {
+    const DevParams dp = make_dev_params(*g.p);
+    const int64_t npad = g.npad;
     const size_t gsmem = sizeof(double) * (2 * G_ROWS * G_LD + F_LW * (F_LW + 2) + 2 * F_LW);
     MFGP_CUDA_CHECK(cudaFuncSetAttribute(gram_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));
-    for (int64_t c0 = 0; c0 < ncols; c0 += chunk) {
-        const int64_t cc = (ncols - c0 < chunk) ? ncols - c0 : chunk;
+    for (int64_t c0 = 0; c0 < g.ncols; c0 += L.chunk) {
+        const int64_t cc = (g.ncols - c0 < L.chunk) ? g.ncols - c0 : L.chunk;
         const int64_t ccp = round_up(cc, 64);
-        for (int pi = 0; pi < nparts; pi++) {
-            FPart& f = parts[pi];
-            // step 4: Y'[col][(n, l)] = sum_k Ux[col][k] Y[(n, l)][k]
-            GemmArgs g{};
-            g.A = f.Ux + c0 * f.kpad; g.lda = f.kpad; g.B = f.Y; g.ldb = f.kpad; g.C = f.Yp; g.ldc = npad * (int64_t)f.ry;
-            g.M = (int)ccp; g.N = (int)(npad * f.ry); g.K = f.kpad; g.alpha = 1.0; g.beta = 0.0; g.mode = GEMM_GENERAL;
-            int rc = launch_gemm(g, true, 1, st);
+        for (int pi = 0; pi < L.nparts; pi++) {
+            FPart& f = L.parts[pi];
+            GemmArgs gm{};          // step 4: Y'[col][(n, l)] = sum_k Ux[col][k] Y[(n, l)][k]
+            gm.A = f.Ux + c0 * f.kpad; gm.lda = f.kpad; gm.B = f.Y; gm.ldb = f.kpad; gm.C = f.Yp; gm.ldc = npad * (int64_t)f.ry;
+            gm.M = (int)ccp; gm.N = (int)(npad * f.ry); gm.K = f.kpad; gm.alpha = 1.0; gm.beta = 0.0; gm.mode = GEMM_GENERAL;
+            int rc = launch_gemm(gm, true, 1, st);
             if (rc) return rc;
         }
         GramArgs ga;
-        ga.YpL = multi ? parts[0].Yp : nullptr; ga.YpH = parts[nparts - 1].Yp;
-        ga.ryL = multi ? parts[0].ry : 0; ga.ryH = parts[nparts - 1].ry;
-        ga.npad = (int)npad; ga.z = z; ga.Uy = Uy; ga.ny = (int)ny; ga.col_begin = (int)c0;
+        ga.YpL = L.multi ? L.parts[0].Yp : nullptr; ga.YpH = L.parts[L.nparts - 1].Yp;
+        ga.ryL = L.multi ? L.parts[0].ry : 0; ga.ryH = L.parts[L.nparts - 1].ry;
+        ga.npad = (int)npad; ga.z = z; ga.Uy = L.Uy; ga.ny = (int)g.ny; ga.col_begin = (int)c0;
         ga.mean = dp.mean_H; ga.k0 = dp.k0; ga.mu = mu; ga.var = var; ga.qred = qred;
         gram_eval_kernel<<<(unsigned)cc, 128, gsmem, st>>>(ga);
         MFGP_LAUNCH_CHECK();
     }
     return MFGP_OK;
+}
+}  // namespace
+
+// Factored posterior for the whole columns [ix0, ix0 + ncols) of the tensor-product grid ux[nx] x uy[ny] (x-major); outputs
+// are flat over those columns: index (ix - ix0) * ny + iy.  rx*/ry*: Chebyshev orders per axis and part (ryL, ryH multiples
+// of 4, ryL + ryH <= 64, all <= 64; rxL = ryL = 0 for a single-fidelity model) -- chosen by the caller so that the factor
+// tables are reproduced to rounding (mfgp_coverage_b200/_engine.py: chebyshev_order).
+extern "C" int mfgp_posterior_grid_factored(const double* ux, int64_t nx, const double* uy, int64_t ny, int64_t ix0, int64_t ncols,
+                                            const double* Xt, int64_t NL, int64_t NH, const double* W, int64_t npad, int64_t ldw,
+                                            const double* z, const mfgp_params* p_host, int64_t rxL, int64_t ryL, int64_t rxH,
+                                            int64_t ryH, double xlo, double xhi, double ylo, double yhi, int64_t chunk_cols,
+                                            double* mu, double* var, double* qred, void* work, int64_t work_bytes, void* stream) {
+    if (!W || !z || !mu || !var || ldw < npad) return MFGP_ERR_INVALID;
+    FGeom g{ux, nx, uy, ny, ix0, ncols, Xt, NL, NH, npad, p_host, rxL, ryL, rxH, ryH, xlo, xhi, ylo, yhi, chunk_cols};
+    int rc = f_validate(g, work, work_bytes);
+    if (rc) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    FLayout L;
+    f_carve(g, work, L);
+    rc = f_tables_and_B(g, L, nullptr, 0, st);
+    if (rc) return rc;
+    for (int pi = 0; pi < L.nparts; pi++) {       // step 3: Y = W B  (W lower triangular: k < m0 + 64)
+        FPart& f = L.parts[pi];
+        GemmArgs gm{};
+        gm.A = W; gm.lda = ldw; gm.B = f.B; gm.ldb = (int64_t)f.ry * f.kpad; gm.C = f.Y; gm.ldc = (int64_t)f.ry * f.kpad;
+        gm.M = (int)npad; gm.N = f.ry * f.kpad; gm.K = (int)npad; gm.alpha = 1.0; gm.beta = 0.0; gm.mode = GEMM_A_LOWER;
+        rc = launch_gemm(gm, false, 1, st);
+        if (rc) return rc;
+    }
+    return f_tail(g, L, z, mu, var, qred, st);
+}
+
+// Fused-fit form, part 1: steps 1 + 2 straight into the right-hand-side matrix of mfgp_cholesky_solve,
+// Ball[npad, ldB] = [B_L | B_H | (y - mean), 0 ...] with mfgp_factored_rhs_cols(...) columns.
+extern "C" int mfgp_factored_prepare(const double* ux, int64_t nx, const double* uy, int64_t ny, int64_t ix0, int64_t ncols,
+                                     const double* Xt, const double* y, int64_t NL, int64_t NH, int64_t npad,
+                                     const mfgp_params* p_host, int64_t rxL, int64_t ryL, int64_t rxH, int64_t ryH, double xlo,
+                                     double xhi, double ylo, double yhi, int64_t chunk_cols, double* Ball, int64_t ldB, void* work,
+                                     int64_t work_bytes, void* stream) {
+    if (!y || !Ball || ldB < mfgp_factored_rhs_cols(rxL, ryL, rxH, ryH)) return MFGP_ERR_INVALID;
+    FGeom g{ux, nx, uy, ny, ix0, ncols, Xt, NL, NH, npad, p_host, rxL, ryL, rxH, ryH, xlo, xhi, ylo, yhi, chunk_cols};
+    int rc = f_validate(g, work, work_bytes);
+    if (rc) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    FLayout L;
+    f_carve(g, work, L);
+    rc = f_tables_and_B(g, L, Ball, ldB, st);
+    if (rc) return rc;
+    const int64_t zoff = mfgp_factored_rhs_cols(rxL, ryL, rxH, ryH) - 64;
+    build_z_block_kernel<<<(unsigned)npad, 64, 0, st>>>(y, (int)npad, (int)(NL + NH), (int)NL, p_host->mean_L, p_host->mean_H, Ball + zoff, ldB);
+    MFGP_LAUNCH_CHECK();
+    return MFGP_OK;
+}
+
+// Fused-fit form, part 2: Yall = L^-1 Ball (mfgp_cholesky_solve) -> steps 4 - 6.  `work` must be the workspace that
+// mfgp_factored_prepare filled (it holds the basis tables); z_out (optional) receives the whitened observations z[npad].
+extern "C" int mfgp_posterior_grid_factored_solved(const double* ux, int64_t nx, const double* uy, int64_t ny, int64_t ix0,
+                                                   int64_t ncols, const double* Xt, int64_t NL, int64_t NH, int64_t npad,
+                                                   const mfgp_params* p_host, int64_t rxL, int64_t ryL, int64_t rxH, int64_t ryH,
+                                                   double xlo, double xhi, double ylo, double yhi, int64_t chunk_cols,
+                                                   const double* Yall, int64_t ldY, double* z_out, double* mu, double* var,
+                                                   double* qred, void* work, int64_t work_bytes, void* stream) {
+    if (!Yall || !mu || !var || ldY < mfgp_factored_rhs_cols(rxL, ryL, rxH, ryH)) return MFGP_ERR_INVALID;
+    FGeom g{ux, nx, uy, ny, ix0, ncols, Xt, NL, NH, npad, p_host, rxL, ryL, rxH, ryH, xlo, xhi, ylo, yhi, chunk_cols};
+    int rc = f_validate(g, work, work_bytes);
+    if (rc) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    FLayout L;
+    f_carve(g, work, L);
+    int64_t off = 0;
+    for (int pi = 0; pi < L.nparts; pi++) {
+        FPart& f = L.parts[pi];
+        const int cols = f.ry * f.kpad;
+        dim3 ug((unsigned)((cols + 255) / 256), (unsigned)npad);
+        unpack_Y_kernel<<<ug, 256, 0, st>>>(Yall, ldY, (int)off, cols, f.Y);
+        MFGP_LAUNCH_CHECK();
+        off += cols;
+    }
+    unpack_z_kernel<<<(unsigned)((npad + 255) / 256), 256, 0, st>>>(Yall, ldY, (int)off, (int)npad, L.zbuf);
+    MFGP_LAUNCH_CHECK();
+    if (z_out) MFGP_CUDA_CHECK(cudaMemcpyAsync(z_out, L.zbuf, sizeof(double) * npad, cudaMemcpyDeviceToDevice, st));
+    return f_tail(g, L, L.zbuf, mu, var, qred, st);
 }

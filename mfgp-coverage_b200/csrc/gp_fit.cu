@@ -261,6 +261,98 @@ extern "C" int mfgp_cholesky(double* K, int64_t npad, int64_t ld, double* W, int
     return MFGP_OK;
 }
 
+// Cholesky of K fused with the forward substitution of R right-hand sides: on return K holds L (lower), the diagonal
+// blocks of W hold the inverses of L's diagonal blocks, and Bm[npad, R] holds L^-1 Bm.  The panel chain (potrf -> panel solve
+// -> trailing update: three small dependent kernels per 64 columns) leaves most of the GPU idle, so the right-hand-side
+// work -- Y_j = W_jj B_j and B_{>j} -= L_{>j,j} Y_j, one pair of tile GEMMs per panel, N^2 R / 2 MACs in total -- runs on
+// an internal side stream and hides behind it: the explicit inverse (mfgp_tri_inverse) and the product W B are not needed
+// by the factored posterior.  Cross-stream order: Y_j waits for potrf(j), the update waits for the panel solve of panel j;
+// the caller's stream waits for the side stream before the call returns control of Bm.
+namespace {
+struct SideStream {
+    cudaStream_t st = nullptr;
+    cudaEvent_t ev_potrf[2] = {nullptr, nullptr}, ev_trsm[2] = {nullptr, nullptr}, ev_begin = nullptr, ev_end = nullptr;
+    int device = -1;
+};
+SideStream g_side[16];
+
+int side_for_current_device(SideStream** out) {
+    int dev = 0;
+    MFGP_CUDA_CHECK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 16) return MFGP_ERR_INVALID;
+    SideStream& s = g_side[dev];
+    if (!s.st) {
+        MFGP_CUDA_CHECK(cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; i++) {
+            MFGP_CUDA_CHECK(cudaEventCreateWithFlags(&s.ev_potrf[i], cudaEventDisableTiming));
+            MFGP_CUDA_CHECK(cudaEventCreateWithFlags(&s.ev_trsm[i], cudaEventDisableTiming));
+        }
+        MFGP_CUDA_CHECK(cudaEventCreateWithFlags(&s.ev_begin, cudaEventDisableTiming));
+        MFGP_CUDA_CHECK(cudaEventCreateWithFlags(&s.ev_end, cudaEventDisableTiming));
+        s.device = dev;
+    }
+    *out = &s;
+    return MFGP_OK;
+}
+}  // namespace
+
+extern "C" int mfgp_cholesky_solve(double* K, int64_t npad, int64_t ld, double* W, int64_t ldw, int32_t* info, double* Bm,
+                                   int64_t ldb, int64_t R, void* stream) {
+    if (!K || !W || !info || !Bm || npad <= 0 || npad % MFGP_TILE || ld < npad || ldw < npad || R <= 0 || R % GT || ldb < R)
+        return MFGP_ERR_INVALID;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    SideStream* side = nullptr;
+    int rcs = side_for_current_device(&side);
+    if (rcs) return rcs;
+    cudaStream_t sb = side->st;
+    MFGP_CUDA_CHECK(cudaMemsetAsync(info, 0, sizeof(int32_t), st));
+    MFGP_CUDA_CHECK(cudaEventRecord(side->ev_begin, st));             // Bm and K were produced on the caller's stream
+    MFGP_CUDA_CHECK(cudaStreamWaitEvent(sb, side->ev_begin, 0));
+    const int nb = (int)(npad / PB);
+    constexpr int POTRF_SMEM = 2 * PB * PLD * sizeof(double);
+    MFGP_CUDA_CHECK(cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, POTRF_SMEM));
+    for (int j = 0; j < nb; j++) {
+        double* Ajj = K + (int64_t)j * PB * (ld + 1);
+        double* Wjj = W + (int64_t)j * PB * (ldw + 1);
+        potrf_diag_kernel<<<1, 256, POTRF_SMEM, st>>>(Ajj, ld, Wjj, ldw, info, j);
+        MFGP_LAUNCH_CHECK();
+        MFGP_CUDA_CHECK(cudaEventRecord(side->ev_potrf[j & 1], st));
+        const int rem = (int)(npad - (int64_t)(j + 1) * PB);
+        double* A21 = K + (int64_t)(j + 1) * PB * ld + (int64_t)j * PB;
+        if (rem > 0) {
+            GemmArgs t{};   // L21 = A21 * inv(L11)^T, in place
+            t.A = A21; t.lda = ld; t.B = Wjj; t.ldb = ldw; t.C = A21; t.ldc = ld;
+            t.M = rem; t.N = PB; t.K = PB; t.alpha = 1.0; t.beta = 0.0; t.mode = GEMM_GENERAL;
+            int rc = launch_gemm(t, true, 1, st);
+            if (rc) return rc;
+            MFGP_CUDA_CHECK(cudaEventRecord(side->ev_trsm[j & 1], st));
+        }
+        // side stream: Y_j = W_jj B_j (in place: every CTA reads only the column tile it writes)
+        double* Bj = Bm + (int64_t)j * PB * ldb;
+        MFGP_CUDA_CHECK(cudaStreamWaitEvent(sb, side->ev_potrf[j & 1], 0));
+        GemmArgs y{};
+        y.A = Wjj; y.lda = ldw; y.B = Bj; y.ldb = ldb; y.C = Bj; y.ldc = ldb;
+        y.M = PB; y.N = (int)R; y.K = PB; y.alpha = 1.0; y.beta = 0.0; y.mode = GEMM_GENERAL;
+        int rc = launch_gemm(y, false, 1, sb);
+        if (rc) return rc;
+        if (rem <= 0) break;
+        MFGP_CUDA_CHECK(cudaStreamWaitEvent(sb, side->ev_trsm[j & 1], 0));
+        GemmArgs u{};       // B_{>j} -= L_{>j,j} Y_j
+        u.A = A21; u.lda = ld; u.B = Bj; u.ldb = ldb; u.C = Bm + (int64_t)(j + 1) * PB * ldb; u.ldc = ldb;
+        u.M = rem; u.N = (int)R; u.K = PB; u.alpha = -1.0; u.beta = 1.0; u.mode = GEMM_GENERAL;
+        rc = launch_gemm(u, false, 1, sb);
+        if (rc) return rc;
+        GemmArgs s2{};  // A22 -= L21 L21^T (lower tiles)
+        s2.A = A21; s2.lda = ld; s2.B = A21; s2.ldb = ld; s2.C = K + (int64_t)(j + 1) * PB * (ld + 1); s2.ldc = ld;
+        s2.M = rem; s2.N = rem; s2.K = PB; s2.alpha = -1.0; s2.beta = 1.0; s2.mode = GEMM_SYRK_LOWER;
+        rc = launch_gemm(s2, true, 1, st);
+        if (rc) return rc;
+    }
+    MFGP_CUDA_CHECK(cudaEventRecord(side->ev_end, sb));
+    MFGP_CUDA_CHECK(cudaStreamWaitEvent(st, side->ev_end, 0));
+    return MFGP_OK;
+}
+
 extern "C" int mfgp_tri_inverse(const double* L, int64_t npad, int64_t ld, double* W, int64_t ldw, void* work,
                                 void* stream) {
     if (!L || !W || !work || npad <= 0 || npad % MFGP_TILE || ld < npad || ldw < npad) return MFGP_ERR_INVALID;

@@ -123,6 +123,7 @@ class _GPBase:
         d = self._dev
         if d.N == 0:
             return np.empty([0, 0])
+        d.ensure_factor(need_inverse=False)
         return torch.tril(d.K[:d.N, :d.N]).cpu().numpy()
 
     def __deepcopy__(self, memo):

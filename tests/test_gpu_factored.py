@@ -113,3 +113,46 @@ def test_short_length_scale_keeps_the_dense_kernel():
     assert m.engine._fplan is not None and m.engine._fplan[1] is None
     assert np.max(np.abs(var.cpu().numpy() - var_o)) <= TOL * p.k0
     assert np.max(np.abs(mu.cpu().numpy() - mu_o)) <= TOL * max(1.0, np.max(np.abs(mu_o)))
+
+
+@pytest.mark.parametrize("nx,ny,N,multi", [(64, 64, 300, True), (96, 80, 700, True), (72, 72, 200, False)])
+def test_fused_fit_and_factored_posterior(nx, ny, N, multi):
+    """Deferred fit: refactor(check=False) only marks the factor stale, the factored posterior then runs
+    mfgp_cholesky_solve (right-hand sides forward-substituted on the side stream) -- no explicit inverse, no W B product.
+    Same results as the oracle; L and the lazily completed inverse W are right as well."""
+    from mfgp_coverage_b200._coverage import CoverageGrid
+    xy = _tensor_grid(nx, ny)
+    f = synth.truth_function(xy)
+    X_L, y_L, X_H, y_H = synth.training_set(xy, f, N, multi=multi)
+    hyp = synth.MF_HYP if multi else synth.SF_HYP
+    p = ogp.GPParams.from_hyp(hyp)
+    om = ogp.Model(p, X_L, y_L, X_H, y_H)
+    om.updt_info()
+    mu_o, var_o = om.predict(xy)
+    m = _model(hyp, X_L, y_L, X_H, y_H, multi)
+    e = m.engine
+    e.factored_min_gain = 0.0
+    e.defer_fit = True
+    grid = CoverageGrid(xy)
+    mu = torch.empty(grid.G, dtype=torch.float64, device=grid.device)
+    var = torch.empty(grid.G, dtype=torch.float64, device=grid.device)
+    for rep in range(2):                                   # twice: the side stream / events are reused
+        e.K.fill_(float("nan")); e.W.fill_(float("nan")); e.z.fill_(float("nan"))      # nothing may survive from the first fit
+        e.refactor(check=False)
+        assert e._dirty
+        m.predict_device(grid.xy, mu, var, grid=grid)
+        assert not e._dirty and e._w_partial
+        assert np.max(np.abs(var.cpu().numpy() - var_o)) <= TOL * p.k0
+        assert np.max(np.abs(mu.cpu().numpy() - mu_o)) <= TOL * max(1.0, np.max(np.abs(mu_o)))
+    e.check_factor(force=True)
+    L = m.factor()
+    assert np.max(np.abs(L - om.L)) <= 1e-10 * np.max(np.abs(om.L))
+    # a consumer of W (the dense kernel on an arbitrary point list) completes the inverse on demand
+    pts = np.random.default_rng(1).random((500, 2))
+    mu_p, var_p = m.predict(pts)
+    assert not e._w_partial
+    mu_q, var_q = om.predict(pts)
+    assert np.max(np.abs(var_p - var_q)) <= TOL * p.k0 and np.max(np.abs(mu_p[:, 0] - mu_q)) <= TOL * max(1.0, np.max(np.abs(mu_q)))
+    Nn = om.L.shape[0]
+    Wd = torch.tril(e.W[:Nn, :Nn]).cpu().numpy()
+    assert np.max(np.abs(Wd @ om.L - np.eye(Nn))) <= 1e-9
