@@ -34,6 +34,7 @@ struct FPart {                       // one kernel part (lofi / hifi) of the fac
     double* B;  double* Y;           // [npad][ry * kpad]
     double* Ux;                      // [ncols_pad][kpad]  T_k(tx) of the grid columns
     double* Yp;                      // [chunk][npad][ry]  step-4 output of one chunk of columns
+    double* Hz;                      // [ry][kpad]  z^T Y
 };
 
 // ---- step 1a: Chebyshev coefficients c_k(n) of u -> exp(-0.5 ((u - U_n)/l)^2) on [lo, hi], one warp per (n, axis) ----------
@@ -113,26 +114,71 @@ __global__ void unpack_z_kernel(const double* __restrict__ Yall, int64_t ldY, in
     if (n < npad) z[n] = Yall[(int64_t)n * ldY + off];
 }
 
+// Hz[e] = sum_n z[n] Y[n][e]: the mean needs z^T Y only contracted with T_k(tx) per column (h'(ix) = Ux(ix) . Hz)
+__global__ void __launch_bounds__(256) hz_kernel(const double* __restrict__ Y, const double* __restrict__ z, int npad, int cols,
+                                                 double* __restrict__ Hz) {
+    __shared__ double part[8][32];
+    const int e = blockIdx.x * 32 + (threadIdx.x & 31), w = threadIdx.x >> 5;
+    double s = 0.0;
+    if (e < cols)
+        for (int n = w; n < npad; n += 8) s = fma(z[n], Y[(int64_t)n * cols + e], s);
+    part[w][threadIdx.x & 31] = s;
+    __syncthreads();
+    if (w == 0 && e < cols) {
+        double t = 0.0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) t += part[k][threadIdx.x & 31];
+        Hz[e] = t;
+    }
+}
+
 // ---- steps 5 + 6: one CTA per grid column --------------------------------------------------------------------------------
 constexpr int G_LD = F_LW + 4;       // padded shared-memory row (doubles): conflict-free DMMA fragment reads
 constexpr int G_ROWS = 64;           // training rows per chunk
 
 struct GramArgs {
     const double* YpL; const double* YpH; int ryL, ryH;        // step-4 outputs [cols][npad][ry]
-    int npad; const double* z;
+    int npad;
+    const double* HzL; const double* HzH;                      // z^T Y_P, [ry][kpad]  (h'(ix) = Ux(ix) . Hz)
+    const double* UxL; const double* UxH; int kL, kH;          // T_k(tx) of this launch's columns, [cols][kpad]
     const double* Uy;                                          // [ny][F_LW]
     int ny; int col_begin;                                     // first grid column (relative) of this launch
     double mean, k0;
     double* mu; double* var; double* qred;                     // flat outputs, index = col * ny + iy
 };
 
+// mbarrier / bulk-copy primitives (same PTX as gp_posterior.cu)
+__device__ __forceinline__ uint32_t f_smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void f_mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void f_mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void f_mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+            : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void f_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(dst), "l"(src),
+                 "r"(bytes), "r"(bar) : "memory");
+}
+
 // G' is symmetric: only the 36 lower 8x8 tiles (of 64) are formed.  Warp 0: lower half of block (0,0) -- 10 tiles; warp 1:
 // lower half of block (1,1) -- 10 tiles; warps 2, 3: block (1,0), column tiles {0,1} / {2,3} -- 8 tiles each.
+// Staging: every thread issues ONE bulk copy per chunk (thread t: training row t % 64 of part t / 64; each row of Y'_P(ix)
+// is a contiguous run of ry doubles) straight into the padded shared tile, completion on an mbarrier -- no per-element
+// address arithmetic in the loop.
 __global__ void __launch_bounds__(128) gram_eval_kernel(GramArgs a) {
     extern __shared__ __align__(16) double gsm[];
     double* Ts = gsm;                               // [2][G_ROWS][G_LD]  double-buffered chunk of Y'(ix)
     double* Gs = gsm + 2 * G_ROWS * G_LD;           // [F_LW][F_LW + 2]   (row pitch even: 16-byte loads)
-    double* hs = Gs + F_LW * (F_LW + 2);            // [2][F_LW]
+    double* hs = Gs + F_LW * (F_LW + 2);            // [F_LW]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(hs + 2 * F_LW);    // [2] "chunk landed"
     constexpr int GP = F_LW + 2;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int col = blockIdx.x;
@@ -142,19 +188,27 @@ __global__ void __launch_bounds__(128) gram_eval_kernel(GramArgs a) {
     const int wn = (warp == 0) ? 0 : (warp == 1 ? 32 : (warp == 2 ? 0 : 16));   // first column
     const double* srcL = a.YpL ? a.YpL + (int64_t)col * a.npad * a.ryL : nullptr;
     const double* srcH = a.YpH + (int64_t)col * a.npad * a.ryH;
-    const int nw = a.ryL + a.ryH;
+    const uint32_t bar0 = f_smem_u32(bars);
 
     for (int e = tid; e < 2 * G_ROWS * G_LD; e += 128) Ts[e] = 0.0;      // the pad columns stay zero
+    if (tid == 0) {
+        f_mbar_init(bar0, 1);
+        f_mbar_init(bar0 + 8, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
     __syncthreads();
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");        // generic-proxy zero fill before the async-proxy copies
+    const int srow = tid & 63, spart = tid >> 6;                          // this thread's staging job
+    const uint32_t chunk_bytes = (uint32_t)(G_ROWS * (a.ryL + a.ryH) * 8);
     auto stage = [&](int buf, int n0) {
-        double* dst = Ts + buf * G_ROWS * G_LD;
-        const int cL = a.ryL / 2, cH = a.ryH / 2;                       // 16-byte chunks per row
-        for (int c = tid; c < G_ROWS * (cL + cH); c += 128) {
-            const int r = c / (cL + cH), q = c % (cL + cH);
-            if (q < cL) cp_async16(dst + r * G_LD + 2 * q, srcL + (int64_t)(n0 + r) * a.ryL + 2 * q, true);
-            else cp_async16(dst + r * G_LD + a.ryL + 2 * (q - cL), srcH + (int64_t)(n0 + r) * a.ryH + 2 * (q - cL), true);
+        if (tid == 0) f_mbar_arrive_expect_tx(bar0 + 8 * buf, chunk_bytes);
+        __syncwarp();
+        double* dst = Ts + buf * G_ROWS * G_LD + srow * G_LD;
+        if (spart == 0) {
+            if (a.ryL) f_bulk_g2s(f_smem_u32(dst), srcL + (int64_t)(n0 + srow) * a.ryL, (uint32_t)(a.ryL * 8), bar0 + 8 * buf);
+        } else {
+            f_bulk_g2s(f_smem_u32(dst + a.ryL), srcH + (int64_t)(n0 + srow) * a.ryH, (uint32_t)(a.ryH * 8), bar0 + 8 * buf);
         }
-        cp_async_commit();
     };
     // diag warps: acc[i][j] for j <= i (4x4 lower, 10 tiles); off-diagonal warps: acc[i][j], i < 4 row tiles, j < 2 column tiles
     double acc[4][4][2];
@@ -162,15 +216,12 @@ __global__ void __launch_bounds__(128) gram_eval_kernel(GramArgs a) {
     for (int i = 0; i < 4; i++)
 #pragma unroll
         for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
-    double hacc = 0.0;                              // thread (c = tid % 64, half = tid / 64): sum over its rows of z[n] T[n][c]
-    const int hc = tid & 63, hh = tid >> 6;
     const int nchunk = a.npad / G_ROWS;
     stage(0, 0);
     for (int ch = 0; ch < nchunk; ch++) {
         const int buf = ch & 1;
-        if (ch + 1 < nchunk) { stage(buf ^ 1, (ch + 1) * G_ROWS); cp_async_wait<1>(); }
-        else cp_async_wait<0>();
-        __syncthreads();
+        if (ch + 1 < nchunk) stage(buf ^ 1, (ch + 1) * G_ROWS);          // buf ^ 1 was released by the barrier below
+        f_mbar_wait(bar0 + 8 * buf, (ch >> 1) & 1);
         const double* T = Ts + buf * G_ROWS * G_LD;
         if (diag) {
 #pragma unroll 4
@@ -197,8 +248,7 @@ __global__ void __launch_bounds__(128) gram_eval_kernel(GramArgs a) {
                     for (int j = 0; j < 2; j++) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
             }
         }
-        for (int r = hh; r < G_ROWS; r += 2) hacc += a.z[ch * G_ROWS + r] * T[r * G_LD + hc];
-        __syncthreads();
+        __syncthreads();                                                  // everybody is done reading `buf`
     }
     // G' (both triangles) and h' to shared memory
 #pragma unroll
@@ -214,9 +264,20 @@ __global__ void __launch_bounds__(128) gram_eval_kernel(GramArgs a) {
                 Gs[(c + 1) * GP + r] = acc[i][j][1];
             }
         }
-    hs[hh * F_LW + hc] = hacc;
-    __syncthreads();
-    if (tid < F_LW) hs[tid] += hs[F_LW + tid];
+    // h'(ix)[l] = sum_k Ux(ix)[k] Hz_P[l][k]     (Hz = z^T Y, computed once per posterior by hz_kernel)
+    if (tid < F_LW) {
+        double h = 0.0;
+        if (tid < a.ryL) {
+            const double* ux = a.UxL + (int64_t)col * a.kL;
+            const double* hz = a.HzL + (int64_t)tid * a.kL;
+            for (int k = 0; k < a.kL; k++) h = fma(ux[k], hz[k], h);
+        } else if (tid < a.ryL + a.ryH) {
+            const double* ux = a.UxH + (int64_t)col * a.kH;
+            const double* hz = a.HzH + (int64_t)(tid - a.ryL) * a.kH;
+            for (int k = 0; k < a.kH; k++) h = fma(ux[k], hz[k], h);
+        }
+        hs[tid] = h;
+    }
     __syncthreads();
     // step 6: every grid point of the column;  q = sum_l u_l (G_ll u_l + 2 sum_{c<l} G_lc u_c)
     for (int iy = tid; iy < a.ny; iy += 128) {
@@ -267,7 +328,7 @@ extern "C" int64_t mfgp_factored_workspace_bytes(int64_t npad, int64_t ncols, in
     const int64_t kL = round_up(rxL, 16), kH = round_up(rxH, 16);
     const int64_t ncp = round_up(ncols, 64), ch = round_up(chunk_cols, 64);
     int64_t d = 0;
-    d += ny * 64 + npad;                                       // Uy, solved z
+    d += ny * 64 + npad + (ryL * kL + ryH * kH);               // Uy, solved z, Hz
     d += (rxL + ryL + rxH + ryH) * npad;                       // coefficient tables
     d += 2 * npad * (ryL * kL + ryH * kH);                     // B and Y
     d += ncp * (kL + kH);                                      // Ux
@@ -323,6 +384,7 @@ void f_carve(const FGeom& g, void* work, FLayout& L) {
         f.B = carve(g.npad * (int64_t)ry * f.kpad); f.Y = carve(g.npad * (int64_t)ry * f.kpad);
         f.Ux = carve(L.ncp * f.kpad);
         f.Yp = carve(L.chunk * g.npad * ry);
+        f.Hz = carve((int64_t)ry * f.kpad);
     };
     if (L.multi) add_part((int)g.rxL, (int)g.ryL, g.p->l_L, 0);
     add_part((int)g.rxH, (int)g.ryH, g.p->l_H, L.multi ? (int)g.ryL : 0);
@@ -364,8 +426,14 @@ int f_tables_and_B(const FGeom& g, FLayout& L, double* Ball, int64_t ldB, cudaSt
 int f_tail(const FGeom& g, FLayout& L, const double* z, double* mu, double* var, double* qred, cudaStream_t st) {
     const DevParams dp = make_dev_params(*g.p);
     const int64_t npad = g.npad;
-    const size_t gsmem = sizeof(double) * (2 * G_ROWS * G_LD + F_LW * (F_LW + 2) + 2 * F_LW);
+    const size_t gsmem = sizeof(double) * (2 * G_ROWS * G_LD + F_LW * (F_LW + 2) + 2 * F_LW) + 64;
     MFGP_CUDA_CHECK(cudaFuncSetAttribute(gram_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));
+    for (int pi = 0; pi < L.nparts; pi++) {
+        FPart& f = L.parts[pi];
+        const int cols = f.ry * f.kpad;
+        hz_kernel<<<(cols + 31) / 32, 256, 0, st>>>(f.Y, z, (int)npad, cols, f.Hz);
+        MFGP_LAUNCH_CHECK();
+    }
     for (int64_t c0 = 0; c0 < g.ncols; c0 += L.chunk) {
         const int64_t cc = (g.ncols - c0 < L.chunk) ? g.ncols - c0 : L.chunk;
         const int64_t ccp = round_up(cc, 64);
@@ -380,7 +448,11 @@ int f_tail(const FGeom& g, FLayout& L, const double* z, double* mu, double* var,
         GramArgs ga;
         ga.YpL = L.multi ? L.parts[0].Yp : nullptr; ga.YpH = L.parts[L.nparts - 1].Yp;
         ga.ryL = L.multi ? L.parts[0].ry : 0; ga.ryH = L.parts[L.nparts - 1].ry;
-        ga.npad = (int)npad; ga.z = z; ga.Uy = L.Uy; ga.ny = (int)g.ny; ga.col_begin = (int)c0;
+        ga.npad = (int)npad; ga.Uy = L.Uy; ga.ny = (int)g.ny; ga.col_begin = (int)c0;
+        ga.HzL = L.multi ? L.parts[0].Hz : nullptr; ga.HzH = L.parts[L.nparts - 1].Hz;
+        ga.UxL = L.multi ? L.parts[0].Ux + c0 * L.parts[0].kpad : nullptr;
+        ga.UxH = L.parts[L.nparts - 1].Ux + c0 * L.parts[L.nparts - 1].kpad;
+        ga.kL = L.multi ? L.parts[0].kpad : 0; ga.kH = L.parts[L.nparts - 1].kpad;
         ga.mean = dp.mean_H; ga.k0 = dp.k0; ga.mu = mu; ga.var = var; ga.qred = qred;
         gram_eval_kernel<<<(unsigned)cc, 128, gsmem, st>>>(ga);
         MFGP_LAUNCH_CHECK();

@@ -265,7 +265,7 @@ extern "C" int mfgp_cholesky(double* K, int64_t npad, int64_t ld, double* W, int
 // blocks of W hold the inverses of L's diagonal blocks, and Bm[npad, R] holds L^-1 Bm.  The panel chain (potrf -> panel solve
 // -> trailing update: three small dependent kernels per 64 columns) leaves most of the GPU idle, so the right-hand-side
 // work -- Y_j = W_jj B_j and B_{>j} -= L_{>j,j} Y_j, one pair of tile GEMMs per panel, N^2 R / 2 MACs in total -- runs on
-// an internal side stream and hides behind it: the explicit inverse (mfgp_tri_inverse) and the product W B are not needed
+// the caller's stream while the chain itself runs on an internal high-priority stream, and hides behind it: the explicit inverse (mfgp_tri_inverse) and the product W B are not needed
 // by the factored posterior.  Cross-stream order: Y_j waits for potrf(j), the update waits for the panel solve of panel j;
 // the caller's stream waits for the side stream before the call returns control of Bm.
 namespace {
@@ -282,7 +282,11 @@ int side_for_current_device(SideStream** out) {
     if (dev < 0 || dev >= 16) return MFGP_ERR_INVALID;
     SideStream& s = g_side[dev];
     if (!s.st) {
-        MFGP_CUDA_CHECK(cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking));
+        // the latency-bound panel chain runs on this stream at the HIGHEST priority, so that its small kernels are placed
+        // ahead of the pending CTAs of the bulk right-hand-side GEMMs (which stay on the caller's stream)
+        int least = 0, greatest = 0;
+        MFGP_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+        MFGP_CUDA_CHECK(cudaStreamCreateWithPriority(&s.st, cudaStreamNonBlocking, greatest));
         for (int i = 0; i < 2; i++) {
             MFGP_CUDA_CHECK(cudaEventCreateWithFlags(&s.ev_potrf[i], cudaEventDisableTiming));
             MFGP_CUDA_CHECK(cudaEventCreateWithFlags(&s.ev_trsm[i], cudaEventDisableTiming));
@@ -300,14 +304,15 @@ extern "C" int mfgp_cholesky_solve(double* K, int64_t npad, int64_t ld, double* 
                                    int64_t ldb, int64_t R, void* stream) {
     if (!K || !W || !info || !Bm || npad <= 0 || npad % MFGP_TILE || ld < npad || ldw < npad || R <= 0 || R % GT || ldb < R)
         return MFGP_ERR_INVALID;
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    cudaStream_t caller = static_cast<cudaStream_t>(stream);
     SideStream* side = nullptr;
     int rcs = side_for_current_device(&side);
     if (rcs) return rcs;
-    cudaStream_t sb = side->st;
+    cudaStream_t st = side->st;        // panel chain: internal high-priority stream
+    cudaStream_t sb = caller;          // right-hand-side GEMMs: the caller's stream
+    MFGP_CUDA_CHECK(cudaEventRecord(side->ev_begin, caller));         // Bm and K were produced on the caller's stream
+    MFGP_CUDA_CHECK(cudaStreamWaitEvent(st, side->ev_begin, 0));
     MFGP_CUDA_CHECK(cudaMemsetAsync(info, 0, sizeof(int32_t), st));
-    MFGP_CUDA_CHECK(cudaEventRecord(side->ev_begin, st));             // Bm and K were produced on the caller's stream
-    MFGP_CUDA_CHECK(cudaStreamWaitEvent(sb, side->ev_begin, 0));
     const int nb = (int)(npad / PB);
     constexpr int POTRF_SMEM = 2 * PB * PLD * sizeof(double);
     MFGP_CUDA_CHECK(cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, POTRF_SMEM));
@@ -348,8 +353,8 @@ extern "C" int mfgp_cholesky_solve(double* K, int64_t npad, int64_t ld, double* 
         rc = launch_gemm(s2, true, 1, st);
         if (rc) return rc;
     }
-    MFGP_CUDA_CHECK(cudaEventRecord(side->ev_end, sb));
-    MFGP_CUDA_CHECK(cudaStreamWaitEvent(st, side->ev_end, 0));
+    MFGP_CUDA_CHECK(cudaEventRecord(side->ev_end, st));               // the caller's stream resumes when the chain is done too
+    MFGP_CUDA_CHECK(cudaStreamWaitEvent(caller, side->ev_end, 0));
     return MFGP_OK;
 }
 
