@@ -156,7 +156,7 @@ class DeviceGP:
 
     def refactor(self, check=True):
         """K assembly -> Cholesky -> inverse -> whitening for the data already resident in Xt / y."""
-        if self.defer_fit and not check:
+        if self.defer_fit and (not check or self.lazy_check):
             self.npad = nat.npad(self.N)
             self._dirty = True
             self._w_partial = False

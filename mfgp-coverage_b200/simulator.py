@@ -305,6 +305,7 @@ class _Sim:
             self._clip = [loss_vor, lloyd_vor]
             if model is not None:
                 model.engine.lazy_check = True       # cov_finish brings the Cholesky status home with the results
+                model.engine.defer_fit = True        # ... so a refit may fuse with the factored posterior (large tensor grids)
         else:
             loss_vor = voronoi_bounded(positions, bb)
             lloyd_vor = voronoi_bounded(centroids_t, bb)

@@ -156,3 +156,39 @@ def test_fused_fit_and_factored_posterior(nx, ny, N, multi):
     Nn = om.L.shape[0]
     Wd = torch.tril(e.W[:Nn, :Nn]).cpu().numpy()
     assert np.max(np.abs(Wd @ om.L - np.eye(Nn))) <= 1e-9
+
+
+@pytest.mark.parametrize("incremental,voronoi", [(False, "qhull"), (True, "clip"), (False, "clip")])
+def test_algorithm_loop_on_the_factored_path(incremental, voronoi, monkeypatch):
+    """A whole todescato run with the factored (and, in throughput mode, fused-fit) posterior forced on a small tensor grid
+    reproduces the oracle loop: the factored path changes nothing a caller can see."""
+    import random
+    from mfgp_coverage_b200 import _engine, simulator as sim
+    from oracle import algorithms as oalg
+    from tests.test_gpu_algorithms import _agent_array, _compare
+    orig = _engine.DeviceGP.__init__
+
+    def forced(self, *a, **k):
+        orig(self, *a, **k)
+        self.factored_min_gain = 0.0
+
+    monkeypatch.setattr(_engine.DeviceGP, "__init__", forced)
+    monkeypatch.setattr(sim, "INCREMENTAL", incremental)
+    monkeypatch.setattr(sim, "VORONOI", voronoi)
+    n, A, T = 40, 6, 12
+    xy = synth.grid(n)
+    truth_arr = np.column_stack((xy, synth.truth_function(xy)))
+    lat_xy = np.random.default_rng(99).random((9, 2))
+    near = np.argmin(((xy[None, :, :] - lat_xy[:, None, :]) ** 2).sum(axis=2), axis=1)
+    prior_arr = np.column_stack((lat_xy, 0.8 * truth_arr[near, 2] + 0.02))
+    seed = 21
+    pos0 = synth.agents(A, seed)
+    lo, ao, so = oalg.todescato(0, T, A, pos0.copy(), truth_arr, 0.1, prior_arr, synth.MF_HYP, random.Random(seed),
+                                np.random.default_rng(seed))
+    lg, ag, sg = sim.todescato("todescato", 0, T, A, pos0.copy(), truth_arr, 0.1, prior_arr, synth.MF_HYP, False, None, True,
+                               rng=random.Random(seed), noise_rng=np.random.default_rng(seed))
+    to_s = lambda s: np.array([[float(r["Iteration"]), float(r["Agent"]), float(r["X"]), float(r["Y"]), float(r["Sample"])]
+                               for r in s]).reshape(-1, 5)
+    _compare(np.array([r["Loss"] for r in lg]), _agent_array(ag, len(lg), A), to_s(sg),
+             np.array([r["Loss"] for r in lo]), _agent_array(ao, len(lo), A), to_s(so), truth_arr,
+             replay_ties=voronoi == "qhull")
