@@ -95,6 +95,9 @@ class DeviceGP:
         self._dirty = False           #   a factored posterior then fuses fit + forward substitution (mfgp_cholesky_solve)
         self._w_partial = False       # True: W holds only the diagonal-block inverses (mfgp_tri_inverse still to run)
         self._fB = None               # right-hand-side matrix of the fused fit
+        self._fG = None               # per-column Gram matrices G'(ix) [ncols, 64, 64] and z^T Y: state of the incremental
+        self._fHz = None              #   factored update (mfgp_posterior_grid_factored_update)
+        self._fstate = None           # (plan key, epoch, rows covered, output buffer key) the stores are valid for
         self.incremental = False
         self.lazy_check = False       # True: the caller reads `info` itself (cov_finish carries it home): no sync per fit
         self.epoch = 0                # bumped by every FULL refactor: standing posteriors become stale
@@ -300,12 +303,17 @@ class DeviceGP:
         plan = None
         if axes is not None and self.N > 0 and vcache is None and self.use_factored:
             plan = self._factored_plan(axes, int(g_lo), G)
-        if plan is not None:                     # cheaper than any row update: recompute from the (bordered) factor
+        if plan is not None:
+            # state key of the stored G'(ix): same geometry / orders / buffers, only appended rows since
+            skey = (id(axes), int(g_lo), G, plan["rxL"], plan["ryL"], plan["rxH"], plan["ryH"], key)
             if self._dirty:
                 self._fit_and_posterior_fused(axes, plan, mu, var, q_out)
             else:
                 self.ensure_factor()
-                self._posterior_factored(axes, plan, mu, var, q_out)
+                upd = row_lo if (row_lo > 0 and self._fstate is not None and self._fstate[0] == skey
+                                 and self._fstate[1] == self.epoch and self._fstate[2] == row_lo) else 0
+                self._posterior_factored(axes, plan, mu, var, q_out, row_lo=upd)
+            self._fstate = (skey, self.epoch, self.N) if self.incremental else None
             return mu, var
         self.ensure_factor()
         if row_lo > 0:
@@ -406,6 +414,19 @@ class DeviceGP:
             self._fwork = torch.empty(need // 8 + 8, dtype=torch.float64, device=self.device)
         return self._fwork
 
+    def _factored_stores(self, plan):
+        """Persistent G'(ix) / z^T Y buffers of the incremental factored update (only kept in incremental mode)."""
+        if not self.incremental:
+            return None, None
+        lib = nat.lib()
+        nG = plan["ncols"] * 64 * 64
+        nH = int(lib.mfgp_factored_rhs_cols(plan["rxL"], plan["ryL"], plan["rxH"], plan["ryH"])) - 64
+        if self._fG is None or self._fG.numel() < nG:
+            self._fG = torch.empty(nG, dtype=torch.float64, device=self.device)
+        if self._fHz is None or self._fHz.numel() < nH:
+            self._fHz = torch.empty(nH, dtype=torch.float64, device=self.device)
+        return self._fG, self._fHz
+
     def _fit_and_posterior_fused(self, axes, plan, mu, var, q_out):
         """From-scratch iteration on a tensor grid in one pass: K -> (L, diagonal-block inverses) with the right-hand sides
         [B_L | B_H | y - mean] forward-substituted on the side stream -> steps 4-6 (see include/mfgp_b200.h)."""
@@ -428,22 +449,34 @@ class DeviceGP:
                   "mfgp_factored_prepare")
         nat.check(lib.mfgp_cholesky_solve(nat.ptr(self.K), npad, ld, nat.ptr(self.W), ld, nat.ptr(self.info),
                                           nat.ptr(self._fB), R, R, st), "mfgp_cholesky_solve")
+        Gs, Hs = self._factored_stores(plan)
         nat.check(lib.mfgp_posterior_grid_factored_solved(
             nat.ptr(axes.ux), axes.nx, nat.ptr(axes.uy), axes.ny, plan["ix0"], plan["ncols"], nat.ptr(self.Xt), self.NL,
             self.NH, npad, pp, *o, *geom, nat.ptr(self._fB), R, nat.ptr(self.z), nat.ptr(mu), nat.ptr(var), nat.ptr(q_out),
-            nat.ptr(work), work.numel() * 8, st), "mfgp_posterior_grid_factored_solved")
+            nat.ptr(Gs), nat.ptr(Hs), nat.ptr(work), work.numel() * 8, st), "mfgp_posterior_grid_factored_solved")
         self._dirty = False
         self._w_partial = True
 
-    def _posterior_factored(self, axes, plan, mu, var, q_out):
+    def _posterior_factored(self, axes, plan, mu, var, q_out, row_lo=0):
+        """Full factored posterior from W, or (row_lo > 0, stores valid) the incremental update with the appended rows."""
         lib = nat.lib()
-        self._factored_work(axes, plan)
+        work = self._factored_work(axes, plan)
+        Gs, Hs = self._factored_stores(plan)
+        geom = (ctypes.c_double(plan["xlo"]), ctypes.c_double(plan["xhi"]), ctypes.c_double(plan["ylo"]),
+                ctypes.c_double(plan["yhi"]), plan["chunk"])
+        o = (plan["rxL"], plan["ryL"], plan["rxH"], plan["ryH"])
+        if row_lo > 0 and Gs is not None:
+            nat.check(lib.mfgp_posterior_grid_factored_update(
+                nat.ptr(axes.ux), axes.nx, nat.ptr(axes.uy), axes.ny, plan["ix0"], plan["ncols"], nat.ptr(self.Xt), self.NL,
+                self.NH, int(row_lo), nat.ptr(self.W), self.npad, self.cap, nat.ptr(self.z), ctypes.byref(self.pstruct), *o, *geom,
+                nat.ptr(mu), nat.ptr(var), nat.ptr(q_out), nat.ptr(Gs), nat.ptr(Hs), nat.ptr(work), work.numel() * 8,
+                nat.stream_ptr()), "mfgp_posterior_grid_factored_update")
+            return
         nat.check(lib.mfgp_posterior_grid_factored(
             nat.ptr(axes.ux), axes.nx, nat.ptr(axes.uy), axes.ny, plan["ix0"], plan["ncols"], nat.ptr(self.Xt), self.NL, self.NH,
-            nat.ptr(self.W), self.npad, self.cap, nat.ptr(self.z), ctypes.byref(self.pstruct), plan["rxL"], plan["ryL"],
-            plan["rxH"], plan["ryH"], ctypes.c_double(plan["xlo"]), ctypes.c_double(plan["xhi"]), ctypes.c_double(plan["ylo"]),
-            ctypes.c_double(plan["yhi"]), plan["chunk"], nat.ptr(mu), nat.ptr(var), nat.ptr(q_out), nat.ptr(self._fwork),
-            self._fwork.numel() * 8, nat.stream_ptr()), "mfgp_posterior_grid_factored")
+            nat.ptr(self.W), self.npad, self.cap, nat.ptr(self.z), ctypes.byref(self.pstruct), *o, *geom, nat.ptr(mu), nat.ptr(var),
+            nat.ptr(q_out), nat.ptr(Gs), nat.ptr(Hs), nat.ptr(work), work.numel() * 8, nat.stream_ptr()),
+            "mfgp_posterior_grid_factored")
 
     def clone(self):
         self.ensure_factor()

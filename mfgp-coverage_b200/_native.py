@@ -57,7 +57,12 @@ SIGNATURES = {
     "mfgp_posterior_grid_factored": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64,
                                              c_int64, c_void_p, c_int64, c_int64, c_void_p, POINTER(MfgpParams), c_int64,
                                              c_int64, c_int64, c_int64, c_double, c_double, c_double, c_double, c_int64,
-                                             c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+                                             c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+    "mfgp_posterior_grid_factored_update": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64,
+                                                    c_int64, c_int64, c_void_p, c_int64, c_int64, c_void_p, POINTER(MfgpParams),
+                                                    c_int64, c_int64, c_int64, c_int64, c_double, c_double, c_double, c_double,
+                                                    c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
+                                                    c_void_p]),
     "mfgp_factored_workspace_bytes": (c_int64, [c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64]),
     "mfgp_factored_rhs_cols": (c_int64, [c_int64, c_int64, c_int64, c_int64]),
     "mfgp_factored_prepare": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_int64,
@@ -68,8 +73,8 @@ SIGNATURES = {
     "mfgp_posterior_grid_factored_solved": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64,
                                                     c_int64, c_int64, POINTER(MfgpParams), c_int64, c_int64, c_int64,
                                                     c_int64, c_double, c_double, c_double, c_double, c_int64, c_void_p,
-                                                    c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
-                                                    c_void_p]),
+                                                    c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                                    c_void_p, c_int64, c_void_p]),
     "cov_assign_reduce": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64,
                                   c_void_p, c_int64, c_void_p, c_void_p, c_int64,
                                   c_void_p, c_int64, c_void_p, c_void_p, c_int64,

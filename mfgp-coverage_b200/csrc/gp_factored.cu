@@ -116,7 +116,7 @@ __global__ void unpack_z_kernel(const double* __restrict__ Yall, int64_t ldY, in
 
 // Hz[e] = sum_n z[n] Y[n][e]: the mean needs z^T Y only contracted with T_k(tx) per column (h'(ix) = Ux(ix) . Hz)
 __global__ void __launch_bounds__(256) hz_kernel(const double* __restrict__ Y, const double* __restrict__ z, int npad, int cols,
-                                                 double* __restrict__ Hz) {
+                                                 double* __restrict__ Hz, int accumulate) {
     __shared__ double part[8][32];
     const int e = blockIdx.x * 32 + (threadIdx.x & 31), w = threadIdx.x >> 5;
     double s = 0.0;
@@ -128,8 +128,13 @@ __global__ void __launch_bounds__(256) hz_kernel(const double* __restrict__ Y, c
         double t = 0.0;
 #pragma unroll
         for (int k = 0; k < 8; k++) t += part[k][threadIdx.x & 31];
-        Hz[e] = t;
+        Hz[e] = accumulate ? Hz[e] + t : t;
     }
+}
+
+__global__ void zero_rows_kernel(double* __restrict__ Y, int64_t cols, int nrows) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < cols * nrows) Y[e] = 0.0;
 }
 
 // ---- steps 5 + 6: one CTA per grid column --------------------------------------------------------------------------------
@@ -138,7 +143,9 @@ constexpr int G_ROWS = 64;           // training rows per chunk
 
 struct GramArgs {
     const double* YpL; const double* YpH; int ryL, ryH;        // step-4 outputs [cols][npad][ry]
-    int npad;
+    int npad;                                                  // rows of Y' held per column (all rows, or only the new ones)
+    double* Gstore;                                            // optional [cols_total][F_LW][F_LW]: G'(ix) kept across calls
+    int accumulate;                                            // 1: G' = Gstore + (the rows given); the store is updated
     const double* HzL; const double* HzH;                      // z^T Y_P, [ry][kpad]  (h'(ix) = Ux(ix) . Hz)
     const double* UxL; const double* UxH; int kL, kH;          // T_k(tx) of this launch's columns, [cols][kpad]
     const double* Uy;                                          // [ny][F_LW]
@@ -264,6 +271,16 @@ __global__ void __launch_bounds__(128) gram_eval_kernel(GramArgs a) {
                 Gs[(c + 1) * GP + r] = acc[i][j][1];
             }
         }
+    if (a.Gstore) {          // keep / extend the column's Gram matrix for later row updates (incremental path)
+        __syncthreads();
+        double* gst = a.Gstore + (int64_t)(a.col_begin + col) * F_LW * F_LW;
+        for (int e = tid; e < F_LW * F_LW; e += 128) {
+            const int r = e >> 6, c = e & 63;
+            double v = Gs[r * GP + c];
+            if (a.accumulate) { v += gst[e]; Gs[r * GP + c] = v; }
+            gst[e] = v;
+        }
+    }
     // h'(ix)[l] = sum_k Ux(ix)[k] Hz_P[l][k]     (Hz = z^T Y, computed once per posterior by hz_kernel)
     if (tid < F_LW) {
         double h = 0.0;
@@ -422,17 +439,22 @@ int f_tables_and_B(const FGeom& g, FLayout& L, double* Ball, int64_t ldB, cudaSt
     return MFGP_OK;
 }
 
-// steps 4 - 6 from Y_P (parts[].Y) and the whitened observations z
-int f_tail(const FGeom& g, FLayout& L, const double* z, double* mu, double* var, double* qred, cudaStream_t st) {
+// steps 4 - 6 from `rows` rows of Y_P (parts[].Y; all npad rows, or only the appended block) and their whitened
+// observations z.  Gstore / Hz_store (optional) keep G'(ix) and z^T Y across calls; accumulate = 1 adds to them.
+int f_tail(const FGeom& g, FLayout& L, const double* z, int64_t rows, double* Gstore, double* Hz_store, int accumulate,
+           double* mu, double* var, double* qred, cudaStream_t st) {
     const DevParams dp = make_dev_params(*g.p);
-    const int64_t npad = g.npad;
+    const int64_t npad = rows;
     const size_t gsmem = sizeof(double) * (2 * G_ROWS * G_LD + F_LW * (F_LW + 2) + 2 * F_LW) + 64;
     MFGP_CUDA_CHECK(cudaFuncSetAttribute(gram_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));
+    int64_t hoff = 0;
     for (int pi = 0; pi < L.nparts; pi++) {
         FPart& f = L.parts[pi];
         const int cols = f.ry * f.kpad;
-        hz_kernel<<<(cols + 31) / 32, 256, 0, st>>>(f.Y, z, (int)npad, cols, f.Hz);
+        if (Hz_store) f.Hz = Hz_store + hoff;          // persistent across calls (incremental path)
+        hz_kernel<<<(cols + 31) / 32, 256, 0, st>>>(f.Y, z, (int)npad, cols, f.Hz, accumulate);
         MFGP_LAUNCH_CHECK();
+        hoff += cols;
     }
     for (int64_t c0 = 0; c0 < g.ncols; c0 += L.chunk) {
         const int64_t cc = (g.ncols - c0 < L.chunk) ? g.ncols - c0 : L.chunk;
@@ -449,6 +471,7 @@ int f_tail(const FGeom& g, FLayout& L, const double* z, double* mu, double* var,
         ga.YpL = L.multi ? L.parts[0].Yp : nullptr; ga.YpH = L.parts[L.nparts - 1].Yp;
         ga.ryL = L.multi ? L.parts[0].ry : 0; ga.ryH = L.parts[L.nparts - 1].ry;
         ga.npad = (int)npad; ga.Uy = L.Uy; ga.ny = (int)g.ny; ga.col_begin = (int)c0;
+        ga.Gstore = Gstore; ga.accumulate = accumulate;
         ga.HzL = L.multi ? L.parts[0].Hz : nullptr; ga.HzH = L.parts[L.nparts - 1].Hz;
         ga.UxL = L.multi ? L.parts[0].Ux + c0 * L.parts[0].kpad : nullptr;
         ga.UxH = L.parts[L.nparts - 1].Ux + c0 * L.parts[L.nparts - 1].kpad;
@@ -469,7 +492,8 @@ extern "C" int mfgp_posterior_grid_factored(const double* ux, int64_t nx, const 
                                             const double* Xt, int64_t NL, int64_t NH, const double* W, int64_t npad, int64_t ldw,
                                             const double* z, const mfgp_params* p_host, int64_t rxL, int64_t ryL, int64_t rxH,
                                             int64_t ryH, double xlo, double xhi, double ylo, double yhi, int64_t chunk_cols,
-                                            double* mu, double* var, double* qred, void* work, int64_t work_bytes, void* stream) {
+                                            double* mu, double* var, double* qred, double* Gstore, double* Hz_store, void* work,
+                                            int64_t work_bytes, void* stream) {
     if (!W || !z || !mu || !var || ldw < npad) return MFGP_ERR_INVALID;
     FGeom g{ux, nx, uy, ny, ix0, ncols, Xt, NL, NH, npad, p_host, rxL, ryL, rxH, ryH, xlo, xhi, ylo, yhi, chunk_cols};
     int rc = f_validate(g, work, work_bytes);
@@ -487,7 +511,7 @@ extern "C" int mfgp_posterior_grid_factored(const double* ux, int64_t nx, const 
         rc = launch_gemm(gm, false, 1, st);
         if (rc) return rc;
     }
-    return f_tail(g, L, z, mu, var, qred, st);
+    return f_tail(g, L, z, npad, Gstore, Hz_store, 0, mu, var, qred, st);
 }
 
 // Fused-fit form, part 1: steps 1 + 2 straight into the right-hand-side matrix of mfgp_cholesky_solve,
@@ -519,7 +543,8 @@ extern "C" int mfgp_posterior_grid_factored_solved(const double* ux, int64_t nx,
                                                    const mfgp_params* p_host, int64_t rxL, int64_t ryL, int64_t rxH, int64_t ryH,
                                                    double xlo, double xhi, double ylo, double yhi, int64_t chunk_cols,
                                                    const double* Yall, int64_t ldY, double* z_out, double* mu, double* var,
-                                                   double* qred, void* work, int64_t work_bytes, void* stream) {
+                                                   double* qred, double* Gstore, double* Hz_store, void* work,
+                                                   int64_t work_bytes, void* stream) {
     if (!Yall || !mu || !var || ldY < mfgp_factored_rhs_cols(rxL, ryL, rxH, ryH)) return MFGP_ERR_INVALID;
     FGeom g{ux, nx, uy, ny, ix0, ncols, Xt, NL, NH, npad, p_host, rxL, ryL, rxH, ryH, xlo, xhi, ylo, yhi, chunk_cols};
     int rc = f_validate(g, work, work_bytes);
@@ -539,5 +564,67 @@ extern "C" int mfgp_posterior_grid_factored_solved(const double* ux, int64_t nx,
     unpack_z_kernel<<<(unsigned)((npad + 255) / 256), 256, 0, st>>>(Yall, ldY, (int)off, (int)npad, L.zbuf);
     MFGP_LAUNCH_CHECK();
     if (z_out) MFGP_CUDA_CHECK(cudaMemcpyAsync(z_out, L.zbuf, sizeof(double) * npad, cudaMemcpyDeviceToDevice, st));
-    return f_tail(g, L, L.zbuf, mu, var, qred, st);
+    return f_tail(g, L, L.zbuf, npad, Gstore, Hz_store, 0, mu, var, qred, st);
+}
+
+// Incremental form (after mfgp_cholesky_append): rows [row_lo, NL+NH) of the training set are new since Gstore / Hz_store
+// (and mu / var) were last brought up to date by one of the full forms above with the same geometry and orders.  Only the
+// new rows of Y = W B are formed (one split-K tile product over the 64-row blocks that hold them), contracted with T_k(tx),
+// and added to the stored per-column Gram matrices; then every grid point is re-evaluated from G'(ix):
+//   G'(ix) += Y'_new(ix)^T Y'_new(ix),   z^T Y += z_new^T Y_new,   var = k0 - uy^T G' uy,   mu = mean + (Ux(ix) . z^T Y) . uy.
+// Cost at c4 with 64 new samples: ~7e8 MAC + the evaluation pass, against 4.2e10 MAC for the full factored form.
+extern "C" int mfgp_posterior_grid_factored_update(const double* ux, int64_t nx, const double* uy, int64_t ny, int64_t ix0,
+                                                   int64_t ncols, const double* Xt, int64_t NL, int64_t NH, int64_t row_lo,
+                                                   const double* W, int64_t npad, int64_t ldw, const double* z,
+                                                   const mfgp_params* p_host, int64_t rxL, int64_t ryL, int64_t rxH, int64_t ryH,
+                                                   double xlo, double xhi, double ylo, double yhi, int64_t chunk_cols, double* mu,
+                                                   double* var, double* qred, double* Gstore, double* Hz_store, void* work,
+                                                   int64_t work_bytes, void* stream) {
+    if (!W || !z || !mu || !var || !Gstore || !Hz_store || ldw < npad || row_lo <= 0 || row_lo >= NL + NH) return MFGP_ERR_INVALID;
+    FGeom g{ux, nx, uy, ny, ix0, ncols, Xt, NL, NH, npad, p_host, rxL, ryL, rxH, ryH, xlo, xhi, ylo, yhi, chunk_cols};
+    int rc = f_validate(g, work, work_bytes);
+    if (rc) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    FLayout L;
+    f_carve(g, work, L);
+    rc = f_tables_and_B(g, L, nullptr, 0, st);            // all rows of B: the new rows of Y contract over every training point
+    if (rc) return rc;
+    const int64_t rb = row_lo / 64 * 64;                  // first 64-row block that holds a new row
+    const int64_t M = npad - rb;
+    for (int pi = 0; pi < L.nparts; pi++) {
+        FPart& f = L.parts[pi];
+        const int64_t cols = (int64_t)f.ry * f.kpad;
+        // Y_new = W[rb:npad, :] B, split over K; partial products parked in the (unused) tail of the part's Y buffer
+        int nsplit = (int)(npad / 512);
+        if (nsplit < 1) nsplit = 1;
+        if (nsplit > 16) nsplit = 16;
+        while (nsplit > 1 && (int64_t)(nsplit + 1) * M * cols > npad * cols) nsplit--;       // must fit behind Y_new in f.Y
+        const int kchunk = (int)((npad / 64 + nsplit - 1) / nsplit) * 64;
+        nsplit = (int)((npad + kchunk - 1) / kchunk);
+        double* Ynew = f.Y;
+        double* part = f.Y + M * cols;
+        if (nsplit > 1) {
+            GemmArgs gm{};
+            gm.A = W + rb * ldw; gm.lda = ldw; gm.B = f.B; gm.ldb = cols; gm.C = part; gm.ldc = cols; gm.strideC = M * cols;
+            gm.M = (int)M; gm.N = (int)cols; gm.K = (int)npad; gm.alpha = 1.0; gm.beta = 0.0; gm.mode = GEMM_GENERAL; gm.kchunk = kchunk;
+            rc = launch_gemm(gm, false, nsplit, st);
+            if (rc) return rc;
+            dim3 rgrid((unsigned)((cols + 127) / 128), (unsigned)M);
+            splitk_reduce_kernel<<<rgrid, 128, 0, st>>>(part, nsplit, M * cols, (int)cols, Ynew, cols, (int)M, (int)cols, 1.0, 0.0);
+            MFGP_LAUNCH_CHECK();
+        } else {
+            GemmArgs gm{};
+            gm.A = W + rb * ldw; gm.lda = ldw; gm.B = f.B; gm.ldb = cols; gm.C = Ynew; gm.ldc = cols;
+            gm.M = (int)M; gm.N = (int)cols; gm.K = (int)npad; gm.alpha = 1.0; gm.beta = 0.0; gm.mode = GEMM_GENERAL;
+            rc = launch_gemm(gm, false, 1, st);
+            if (rc) return rc;
+        }
+        if (row_lo > rb) {        // rows [rb, row_lo) of the first block are old: already inside the stored G' and z^T Y
+            const int64_t nz = (row_lo - rb) * cols;
+            zero_rows_kernel<<<(unsigned)((nz + 255) / 256), 256, 0, st>>>(Ynew, cols, (int)(row_lo - rb));
+            MFGP_LAUNCH_CHECK();
+        }
+    }
+    // steps 4 - 6 on the M new rows only (g.npad stays the full size for the table shapes; f_tail takes the row count)
+    return f_tail(g, L, z + rb, M, Gstore, Hz_store, 1, mu, var, qred, st);
 }

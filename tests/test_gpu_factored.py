@@ -192,3 +192,48 @@ def test_algorithm_loop_on_the_factored_path(incremental, voronoi, monkeypatch):
     _compare(np.array([r["Loss"] for r in lg]), _agent_array(ag, len(lg), A), to_s(sg),
              np.array([r["Loss"] for r in lo]), _agent_array(ao, len(lo), A), to_s(so), truth_arr,
              replay_ties=voronoi == "qhull")
+
+
+@pytest.mark.parametrize("nx,ny,N0,adds,multi", [(64, 64, 200, [5, 0, 60, 1, 130], True), (80, 48, 128, [64, 64, 3], True),
+                                                 (72, 72, 90, [8, 70], False)])
+def test_factored_incremental_update(nx, ny, N0, adds, multi):
+    """Incremental factored path: after a bordered append only the new rows of Y = W B are formed and added to the stored
+    per-column Gram matrices (mfgp_posterior_grid_factored_update); results equal the oracle's refit-from-scratch."""
+    from mfgp_coverage_b200._coverage import CoverageGrid
+    from mfgp_coverage_b200 import _native as nat
+    xy = _tensor_grid(nx, ny)
+    f = synth.truth_function(xy)
+    total = N0 + sum(adds)
+    X_L, y_L, X_H, y_H = synth.training_set(xy, f, total + (total // 3 if multi else 0), multi=multi)
+    nl = X_L.shape[0]
+    X_H, y_H = X_H[:total - nl], y_H[:total - nl]
+    hyp = synth.MF_HYP if multi else synth.SF_HYP
+    p = ogp.GPParams.from_hyp(hyp)
+    nh = N0 - nl
+    assert nh > 0
+    m = _model(hyp, X_L, y_L, X_H[:nh], y_H[:nh], multi)
+    m.incremental = True
+    e = m.engine
+    e.factored_min_gain = 0.0
+    grid = CoverageGrid(xy)
+    mu = torch.empty(grid.G, dtype=torch.float64, device=grid.device)
+    var = torch.empty(grid.G, dtype=torch.float64, device=grid.device)
+    m.predict_device(grid.xy, mu, var, grid=grid)
+    assert e._fstate is not None
+    for k in adds:
+        l0 = nat.lib().mfgp_launch_count()
+        (m.updt_hifi if multi else m.updt)(X_H[nh:nh + k], y_H[nh:nh + k])
+        nh += k
+        m.predict_device(grid.xy, mu, var, grid=grid)
+        if k == 0:
+            assert nat.lib().mfgp_launch_count() == l0           # nothing appended: nothing to do
+        om = ogp.Model(p, X_L, y_L, X_H[:nh], y_H[:nh])
+        om.updt_info()
+        mu_o, var_o = om.predict(xy)
+        assert np.max(np.abs(var.cpu().numpy() - var_o)) <= TOL * p.k0
+        assert np.max(np.abs(mu.cpu().numpy() - mu_o)) <= TOL * max(1.0, np.max(np.abs(mu_o)))
+    # the stored Gram matrices are what a fresh full pass would produce
+    mu2 = torch.empty_like(mu); var2 = torch.empty_like(var)
+    e.incremental = False
+    m.predict_device(grid.xy, mu2, var2, grid=grid)
+    assert float((var2 - var).abs().max()) <= 1e-11 * p.k0 and float((mu2 - mu).abs().max()) <= 1e-11 * max(1.0, float(mu2.abs().max()))
