@@ -371,7 +371,7 @@ class DeviceGP:
             rxL = chebyshev_order(p["l_L"], xlo, xhi, hull[0], hull[1])
             ryL = chebyshev_order(p["l_L"], ylo, yhi, hull[2], hull[3])
             ok = rxL is not None and ryL is not None
-        orders = (rxL, ryL, rxH, ryH) if ok and ryL + ryH <= 64 else None
+        orders = (rxL, ryL, rxH, ryH) if ok else None
         self._forders = ((id(axes), p["l_L"], p["l_H"], p["multi"]), hull, orders)
         return orders
 
@@ -394,11 +394,11 @@ class DeviceGP:
         if orders is not None:
             rxL, ryL, rxH, ryH = orders
             ncols = G // ny
-            kL, kH = -(-rxL // 16) * 16, -(-rxH // 16) * 16
-            R = ryL * kL + ryH * kH
+            ry, kp = max(ryL, ryH), -(-max(rxL, rxH) // 16) * 16       # both kernel parts share one Chebyshev basis
+            R = ry * kp
             fact = 0.5 * N * N * R + ncols * N * R + ncols * N * 64 * 64 + G * 64 * 64
             if fact * self.factored_min_gain < dense:
-                chunk = max(64, min(-(-ncols // 64) * 64, ((1 << 28) // max(self.cap * (ryL + ryH), 1)) // 64 * 64))   # <= 2 GiB of Y'
+                chunk = max(64, min(-(-ncols // 64) * 64, ((1 << 28) // max(self.cap * max(ryL, ryH), 1)) // 64 * 64))   # <= 2 GiB of Y'
                 plan = dict(rxL=rxL, ryL=ryL, rxH=rxH, ryH=ryH, xlo=axes.xlo, xhi=axes.xhi, ylo=axes.ylo, yhi=axes.yhi,
                             ix0=g_lo // ny,
                             ncols=ncols, chunk=chunk, macs=fact, dense_macs=dense)

@@ -94,6 +94,25 @@ __global__ void build_B_kernel(const double* __restrict__ Cx, const double* __re
     B[(int64_t)n * ldB + e] = v;
 }
 
+// Both kernel parts expand in the SAME Chebyshev basis T_l(ty) T_k(tx), so their coefficient tensors simply add: one B with
+// rx = max(rxL, rxH), ry = max(ryL, ryH) instead of two (the lofi part's terms beyond its own orders are zero):
+//   B[n][l][k] = cL[n] CyL[l][n] CxL[k][n] [l < ryL, k < rxL]  +  cH[n] CyH[l][n] CxH[k][n] [l < ryH, k < rxH]
+struct BTab { const double* Cx; const double* Cy; int rx, ry; double coef_lo, coef_hi; };
+__global__ void build_B_merged_kernel(BTab t0, BTab t1, int ntab, int npad, int N, int NL, int ry, int kpad, double* __restrict__ B,
+                                      int64_t ldB) {
+    const int n = blockIdx.y;
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;       // (l, k)
+    if (e >= ry * kpad) return;
+    const int l = e / kpad, k = e % kpad;
+    double v = 0.0;
+    if (n < N) {
+        if (l < t0.ry && k < t0.rx) v = (n < NL ? t0.coef_lo : t0.coef_hi) * t0.Cy[(int64_t)l * npad + n] * t0.Cx[(int64_t)k * npad + n];
+        if (ntab > 1 && l < t1.ry && k < t1.rx)
+            v += (n < NL ? t1.coef_lo : t1.coef_hi) * t1.Cy[(int64_t)l * npad + n] * t1.Cx[(int64_t)k * npad + n];
+    }
+    B[(int64_t)n * ldB + e] = v;
+}
+
 // centred observations as one more 64-wide block of right-hand sides: column 0 = y - mean (gaussian_process.py:133, :419-424)
 __global__ void build_z_block_kernel(const double* __restrict__ y, int npad, int N, int NL, double mean_L, double mean_H,
                                      double* __restrict__ B, int64_t ldB) {
@@ -340,22 +359,24 @@ using namespace mfgp;
 // ---- host side -------------------------------------------------------------------------------------------------------------
 static inline int64_t round_up(int64_t v, int64_t m) { return (v + m - 1) / m * m; }
 
+static inline int64_t imax(int64_t a, int64_t b) { return a > b ? a : b; }
+
 extern "C" int64_t mfgp_factored_workspace_bytes(int64_t npad, int64_t ncols, int64_t ny, int64_t rxL, int64_t ryL, int64_t rxH,
                                                  int64_t ryH, int64_t chunk_cols) {
-    const int64_t kL = round_up(rxL, 16), kH = round_up(rxH, 16);
+    const int64_t rx = imax(rxL, rxH), ry = imax(ryL, ryH), kp = round_up(rx, 16);
     const int64_t ncp = round_up(ncols, 64), ch = round_up(chunk_cols, 64);
     int64_t d = 0;
-    d += ny * 64 + npad + (ryL * kL + ryH * kH);               // Uy, solved z, Hz
-    d += (rxL + ryL + rxH + ryH) * npad;                       // coefficient tables
-    d += 2 * npad * (ryL * kL + ryH * kH);                     // B and Y
-    d += ncp * (kL + kH);                                      // Ux
-    d += ch * npad * (ryL + ryH);                              // Y' of one chunk
+    d += ny * 64 + npad + ry * kp;                             // Uy, solved z, Hz
+    d += (rxL + ryL + rxH + ryH) * npad;                       // coefficient tables of both kernel parts
+    d += 2 * npad * ry * kp;                                   // B and Y (merged over the parts)
+    d += ncp * kp;                                             // Ux
+    d += ch * npad * ry;                                       // Y' of one chunk
     return d * 8 + 4096;
 }
 
-// number of right-hand-side columns of the fused fit (mfgp_cholesky_solve): [B_L | B_H | z block]
+// number of right-hand-side columns of the fused fit (mfgp_cholesky_solve): [B | z block]
 extern "C" int64_t mfgp_factored_rhs_cols(int64_t rxL, int64_t ryL, int64_t rxH, int64_t ryH) {
-    return ryL * round_up(rxL, 16) + ryH * round_up(rxH, 16) + 64;
+    return imax(ryL, ryH) * round_up(imax(rxL, rxH), 16) + 64;
 }
 
 namespace {
@@ -367,8 +388,11 @@ struct FGeom {
     double xlo, xhi, ylo, yhi;
     int64_t chunk;
 };
+struct FTab { int rx, ry; double inv_l; double* Cx; double* Cy; bool lofi; };
 struct FLayout {
-    FPart parts[2]; int nparts; double* Uy; double* zbuf; int64_t ncp, chunk; bool multi;
+    FTab tabs[2]; int ntabs;         // coefficient tables per kernel part
+    FPart parts[1]; int nparts;      // ONE merged expansion (rx = max, ry = max)
+    double* Uy; double* zbuf; int64_t ncp, chunk; bool multi;
 };
 
 int f_validate(const FGeom& g, void* work, int64_t work_bytes) {
@@ -377,8 +401,7 @@ int f_validate(const FGeom& g, void* work, int64_t work_bytes) {
     if (N <= 0 || g.npad < N || g.npad % MFGP_TILE || g.ncols <= 0 || g.ix0 < 0 || g.ix0 + g.ncols > g.nx || g.ny <= 0) return MFGP_ERR_INVALID;
     const bool multi = g.p->multi != 0;
     if (!multi && (g.rxL || g.ryL || g.NL)) return MFGP_ERR_INVALID;
-    if (g.rxH <= 0 || g.ryH <= 0 || g.rxH > F_MAXR || g.ryH > F_MAXR || g.rxL > F_MAXR || g.ryL > F_MAXR || (g.ryL % 4) || (g.ryH % 4) ||
-        g.ryL + g.ryH > F_LW)
+    if (g.rxH <= 0 || g.ryH <= 0 || g.rxH > F_MAXR || g.ryH > F_MAXR || g.rxL > F_MAXR || g.ryL > F_MAXR || (g.ryL % 4) || (g.ryH % 4))
         return MFGP_ERR_INVALID;
     if (multi && (g.rxL <= 0 || g.ryL <= 0)) return MFGP_ERR_INVALID;
     if (!(g.xhi > g.xlo) || !(g.yhi > g.ylo) || g.chunk <= 0) return MFGP_ERR_INVALID;
@@ -389,53 +412,56 @@ int f_validate(const FGeom& g, void* work, int64_t work_bytes) {
 void f_carve(const FGeom& g, void* work, FLayout& L) {
     L.multi = g.p->multi != 0;
     L.ncp = round_up(g.ncols, 64); L.chunk = round_up(g.chunk, 64);
-    L.nparts = 0;
     double* wp = static_cast<double*>(work);
     auto carve = [&](int64_t n) { double* r = wp; wp += n; return r; };
     L.Uy = carve(g.ny * 64);
     L.zbuf = carve(g.npad);
-    auto add_part = [&](int rx, int ry, double l, int loff) {
-        FPart& f = L.parts[L.nparts++];
-        f.rx = rx; f.ry = ry; f.kpad = (int)round_up(rx, 16); f.loff = loff; f.inv_l = 1.0 / l;
-        f.Cx = carve((int64_t)rx * g.npad); f.Cy = carve((int64_t)ry * g.npad);
-        f.B = carve(g.npad * (int64_t)ry * f.kpad); f.Y = carve(g.npad * (int64_t)ry * f.kpad);
-        f.Ux = carve(L.ncp * f.kpad);
-        f.Yp = carve(L.chunk * g.npad * ry);
-        f.Hz = carve((int64_t)ry * f.kpad);
+    L.ntabs = 0;
+    auto add_tab = [&](int rx, int ry, double l, bool lofi) {
+        FTab& t = L.tabs[L.ntabs++];
+        t.rx = rx; t.ry = ry; t.inv_l = 1.0 / l; t.lofi = lofi;
+        t.Cx = carve((int64_t)rx * g.npad); t.Cy = carve((int64_t)ry * g.npad);
     };
-    if (L.multi) add_part((int)g.rxL, (int)g.ryL, g.p->l_L, 0);
-    add_part((int)g.rxH, (int)g.ryH, g.p->l_H, L.multi ? (int)g.ryL : 0);
+    if (L.multi) add_tab((int)g.rxL, (int)g.ryL, g.p->l_L, true);
+    add_tab((int)g.rxH, (int)g.ryH, g.p->l_H, false);
+    FPart& f = L.parts[0];
+    L.nparts = 1;
+    f.rx = (int)imax(g.rxL, g.rxH); f.ry = (int)imax(g.ryL, g.ryH); f.kpad = (int)round_up(f.rx, 16); f.loff = 0; f.inv_l = 0.0;
+    f.Cx = f.Cy = nullptr;
+    f.B = carve(g.npad * (int64_t)f.ry * f.kpad); f.Y = carve(g.npad * (int64_t)f.ry * f.kpad);
+    f.Ux = carve(L.ncp * f.kpad);
+    f.Yp = carve(L.chunk * g.npad * f.ry);
+    f.Hz = carve((int64_t)f.ry * f.kpad);
 }
 
-// steps 1 + 2: tables, then B_P either into the part's own buffer (Ball == nullptr) or into the column range of Ball
+// steps 1 + 2: tables of both kernel parts, basis tables, then the merged B either into the part's own buffer
+// (Ball == nullptr) or into the leading columns of Ball
 int f_tables_and_B(const FGeom& g, FLayout& L, double* Ball, int64_t ldB, cudaStream_t st) {
     const DevParams dp = make_dev_params(*g.p);
     const int64_t N = g.NL + g.NH, npad = g.npad;
+    FPart& f = L.parts[0];
     MFGP_CUDA_CHECK(cudaMemsetAsync(L.Uy, 0, sizeof(double) * g.ny * 64, st));
-    int64_t off = 0;
-    for (int pi = 0; pi < L.nparts; pi++) {
-        FPart& f = L.parts[pi];
-        const bool lofi_part = L.multi && pi == 0;
-        cheb_coef_kernel<<<(unsigned)((npad + 7) / 8), 256, 0, st>>>(g.Xt, (int)N, (int)npad, 0, g.xlo, g.xhi, f.inv_l, f.rx, f.Cx);
+    MFGP_CUDA_CHECK(cudaMemsetAsync(f.Ux, 0, sizeof(double) * L.ncp * f.kpad, st));
+    cheb_basis_kernel<<<(unsigned)((L.ncp + 127) / 128), 128, 0, st>>>(g.ux, (int)g.ix0, (int)g.ncols, (int)L.ncp, g.xlo, g.xhi, f.rx, f.kpad,
+                                                                    0, f.Ux);
+    MFGP_LAUNCH_CHECK();
+    cheb_basis_kernel<<<(unsigned)((g.ny + 127) / 128), 128, 0, st>>>(g.uy, 0, (int)g.ny, (int)g.ny, g.ylo, g.yhi, f.ry, 64, 0, L.Uy);
+    MFGP_LAUNCH_CHECK();
+    BTab bt[2] = {};
+    for (int ti = 0; ti < L.ntabs; ti++) {
+        FTab& t = L.tabs[ti];
+        cheb_coef_kernel<<<(unsigned)((npad + 7) / 8), 256, 0, st>>>(g.Xt, (int)N, (int)npad, 0, g.xlo, g.xhi, t.inv_l, t.rx, t.Cx);
         MFGP_LAUNCH_CHECK();
-        cheb_coef_kernel<<<(unsigned)((npad + 7) / 8), 256, 0, st>>>(g.Xt, (int)N, (int)npad, 1, g.ylo, g.yhi, f.inv_l, f.ry, f.Cy);
-        MFGP_LAUNCH_CHECK();
-        MFGP_CUDA_CHECK(cudaMemsetAsync(f.Ux, 0, sizeof(double) * L.ncp * f.kpad, st));
-        cheb_basis_kernel<<<(unsigned)((L.ncp + 127) / 128), 128, 0, st>>>(g.ux, (int)g.ix0, (int)g.ncols, (int)L.ncp, g.xlo, g.xhi, f.rx,
-                                                                        f.kpad, 0, f.Ux);
-        MFGP_LAUNCH_CHECK();
-        cheb_basis_kernel<<<(unsigned)((g.ny + 127) / 128), 128, 0, st>>>(g.uy, 0, (int)g.ny, (int)g.ny, g.ylo, g.yhi, f.ry, 64, f.loff, L.Uy);
+        cheb_coef_kernel<<<(unsigned)((npad + 7) / 8), 256, 0, st>>>(g.Xt, (int)N, (int)npad, 1, g.ylo, g.yhi, t.inv_l, t.ry, t.Cy);
         MFGP_LAUNCH_CHECK();
         // lofi part: rho s_L (lofi columns) / rho^2 s_L (hifi columns); hifi part: 0 / s_H  (gaussian_process.py:426-429)
-        const double c_lo = lofi_part ? dp.rho * dp.s_L : 0.0;
-        const double c_hi = lofi_part ? dp.rho2 * dp.s_L : dp.s_H;
-        const int cols = f.ry * f.kpad;
-        dim3 bgrid((unsigned)((cols + 127) / 128), (unsigned)npad);
-        build_B_kernel<<<bgrid, 128, 0, st>>>(f.Cx, f.Cy, (int)npad, (int)N, (int)g.NL, f.rx, f.ry, f.kpad, c_lo, c_hi,
-                                             Ball ? Ball + off : f.B, Ball ? ldB : (int64_t)cols);
-        MFGP_LAUNCH_CHECK();
-        off += cols;
+        bt[ti] = BTab{t.Cx, t.Cy, t.rx, t.ry, t.lofi ? dp.rho * dp.s_L : 0.0, t.lofi ? dp.rho2 * dp.s_L : dp.s_H};
     }
+    const int cols = f.ry * f.kpad;
+    dim3 bgrid((unsigned)((cols + 127) / 128), (unsigned)npad);
+    build_B_merged_kernel<<<bgrid, 128, 0, st>>>(bt[0], bt[1], L.ntabs, (int)npad, (int)N, (int)g.NL, f.ry, f.kpad, Ball ? Ball : f.B,
+                                                Ball ? ldB : (int64_t)cols);
+    MFGP_LAUNCH_CHECK();
     return MFGP_OK;
 }
 
@@ -468,14 +494,13 @@ int f_tail(const FGeom& g, FLayout& L, const double* z, int64_t rows, double* Gs
             if (rc) return rc;
         }
         GramArgs ga;
-        ga.YpL = L.multi ? L.parts[0].Yp : nullptr; ga.YpH = L.parts[L.nparts - 1].Yp;
-        ga.ryL = L.multi ? L.parts[0].ry : 0; ga.ryH = L.parts[L.nparts - 1].ry;
+        ga.YpL = nullptr; ga.YpH = L.parts[0].Yp;          // one merged expansion: the "L" slot of the kernel stays empty
+        ga.ryL = 0; ga.ryH = L.parts[0].ry;
         ga.npad = (int)npad; ga.Uy = L.Uy; ga.ny = (int)g.ny; ga.col_begin = (int)c0;
         ga.Gstore = Gstore; ga.accumulate = accumulate;
-        ga.HzL = L.multi ? L.parts[0].Hz : nullptr; ga.HzH = L.parts[L.nparts - 1].Hz;
-        ga.UxL = L.multi ? L.parts[0].Ux + c0 * L.parts[0].kpad : nullptr;
-        ga.UxH = L.parts[L.nparts - 1].Ux + c0 * L.parts[L.nparts - 1].kpad;
-        ga.kL = L.multi ? L.parts[0].kpad : 0; ga.kH = L.parts[L.nparts - 1].kpad;
+        ga.HzL = nullptr; ga.HzH = L.parts[0].Hz;
+        ga.UxL = nullptr; ga.UxH = L.parts[0].Ux + c0 * L.parts[0].kpad;
+        ga.kL = 0; ga.kH = L.parts[0].kpad;
         ga.mean = dp.mean_H; ga.k0 = dp.k0; ga.mu = mu; ga.var = var; ga.qred = qred;
         gram_eval_kernel<<<(unsigned)cc, 128, gsmem, st>>>(ga);
         MFGP_LAUNCH_CHECK();
