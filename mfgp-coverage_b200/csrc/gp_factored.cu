@@ -194,27 +194,39 @@ __device__ __forceinline__ void f_bulk_g2s(uint32_t dst, const void* src, uint32
                  "r"(bytes), "r"(bar) : "memory");
 }
 
-// G' is symmetric: only the 36 lower 8x8 tiles (of 64) are formed.  Warp 0: lower half of block (0,0) -- 10 tiles; warp 1:
-// lower half of block (1,1) -- 10 tiles; warps 2, 3: block (1,0), column tiles {0,1} / {2,3} -- 8 tiles each.
+// G' is symmetric: only the lower 8x8 tiles are formed -- NT (NT + 1) / 2 of them for a padded width WM = 8 NT (15 for the
+// usual WM = 40, 36 for WM = 64), dealt round-robin to the four warps.
 // Staging: every thread issues ONE bulk copy per chunk (thread t: training row t % 64 of part t / 64; each row of Y'_P(ix)
 // is a contiguous run of ry doubles) straight into the padded shared tile, completion on an mbarrier -- no per-element
 // address arithmetic in the loop.
+template <int WM>
 __global__ void __launch_bounds__(128) gram_eval_kernel(GramArgs a) {
+    constexpr int NT = WM / 8, NTILES = NT * (NT + 1) / 2, MAXT = (NTILES + 3) / 4;
+    constexpr int GP = WM + 2;
     extern __shared__ __align__(16) double gsm[];
     double* Ts = gsm;                               // [2][G_ROWS][G_LD]  double-buffered chunk of Y'(ix)
-    double* Gs = gsm + 2 * G_ROWS * G_LD;           // [F_LW][F_LW + 2]   (row pitch even: 16-byte loads)
-    double* hs = Gs + F_LW * (F_LW + 2);            // [F_LW]
+    double* Gs = gsm + 2 * G_ROWS * G_LD;           // [WM][WM + 2]   (row pitch even: 16-byte loads)
+    double* hs = Gs + WM * GP;                      // [F_LW]
     uint64_t* bars = reinterpret_cast<uint64_t*>(hs + 2 * F_LW);    // [2] "chunk landed"
-    constexpr int GP = F_LW + 2;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int col = blockIdx.x;
     const int gq = lane >> 2, tq = lane & 3;
-    const bool diag = warp < 2;
-    const int wm = (warp == 0) ? 0 : 32;                         // first row of the warp's tiles
-    const int wn = (warp == 0) ? 0 : (warp == 1 ? 32 : (warp == 2 ? 0 : 16));   // first column
     const double* srcL = a.YpL ? a.YpL + (int64_t)col * a.npad * a.ryL : nullptr;
     const double* srcH = a.YpH + (int64_t)col * a.npad * a.ryH;
     const uint32_t bar0 = f_smem_u32(bars);
+    // this warp's tiles: t = warp + 4 s  ->  (row tile ti, column tile tj <= ti), element offsets inside a shared row
+    int ta[MAXT], tb[MAXT];
+    bool tv[MAXT];
+#pragma unroll
+    for (int s = 0; s < MAXT; s++) {
+        const int t = warp + 4 * s;
+        tv[s] = t < NTILES;
+        int i = 0;
+        while ((i + 1) * (i + 2) / 2 <= t) i++;
+        const int j = t - i * (i + 1) / 2;
+        ta[s] = i * 8 + gq;
+        tb[s] = j * 8 + gq;
+    }
 
     for (int e = tid; e < 2 * G_ROWS * G_LD; e += 128) Ts[e] = 0.0;      // the pad columns stay zero
     if (tid == 0) {
@@ -236,12 +248,9 @@ __global__ void __launch_bounds__(128) gram_eval_kernel(GramArgs a) {
             f_bulk_g2s(f_smem_u32(dst + a.ryL), srcH + (int64_t)(n0 + srow) * a.ryH, (uint32_t)(a.ryH * 8), bar0 + 8 * buf);
         }
     };
-    // diag warps: acc[i][j] for j <= i (4x4 lower, 10 tiles); off-diagonal warps: acc[i][j], i < 4 row tiles, j < 2 column tiles
-    double acc[4][4][2];
+    double acc[MAXT][2];
 #pragma unroll
-    for (int i = 0; i < 4; i++)
-#pragma unroll
-        for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+    for (int s = 0; s < MAXT; s++) acc[s][0] = acc[s][1] = 0.0;
     const int nchunk = a.npad / G_ROWS;
     stage(0, 0);
     for (int ch = 0; ch < nchunk; ch++) {
@@ -249,55 +258,38 @@ __global__ void __launch_bounds__(128) gram_eval_kernel(GramArgs a) {
         if (ch + 1 < nchunk) stage(buf ^ 1, (ch + 1) * G_ROWS);          // buf ^ 1 was released by the barrier below
         f_mbar_wait(bar0 + 8 * buf, (ch >> 1) & 1);
         const double* T = Ts + buf * G_ROWS * G_LD;
-        if (diag) {
 #pragma unroll 4
-            for (int kk = 0; kk < G_ROWS; kk += 4) {
-                double af[4];
+        for (int kk = 0; kk < G_ROWS; kk += 4) {
+            const double* row = T + (kk + tq) * G_LD;                   // A[m][k] = T[k][m]; B[k][n] = T[k][n]
+            double af[MAXT], bf[MAXT];
 #pragma unroll
-                for (int i = 0; i < 4; i++) af[i] = T[(kk + tq) * G_LD + wm + i * 8 + gq];      // A[m][k] = T[k][m]; B[k][n] = T[k][n]
+            for (int s = 0; s < MAXT; s++) { af[s] = row[ta[s]]; bf[s] = row[tb[s]]; }
 #pragma unroll
-                for (int i = 0; i < 4; i++)
-#pragma unroll
-                    for (int j = 0; j <= i; j++) dmma884(acc[i][j][0], acc[i][j][1], af[i], af[j]);
-            }
-        } else {
-#pragma unroll 4
-            for (int kk = 0; kk < G_ROWS; kk += 4) {
-                double af[4], bf[2];
-#pragma unroll
-                for (int i = 0; i < 4; i++) af[i] = T[(kk + tq) * G_LD + wm + i * 8 + gq];
-#pragma unroll
-                for (int j = 0; j < 2; j++) bf[j] = T[(kk + tq) * G_LD + wn + j * 8 + gq];
-#pragma unroll
-                for (int i = 0; i < 4; i++)
-#pragma unroll
-                    for (int j = 0; j < 2; j++) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
-            }
+            for (int s = 0; s < MAXT; s++)
+                if (tv[s]) dmma884(acc[s][0], acc[s][1], af[s], bf[s]);
         }
         __syncthreads();                                                  // everybody is done reading `buf`
     }
-    // G' (both triangles) and h' to shared memory
+    // G' (both triangles) to shared memory
 #pragma unroll
-    for (int i = 0; i < 4; i++)
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            if (diag ? (j > i) : (j >= 2)) continue;
-            const int r = wm + i * 8 + gq, c = wn + j * 8 + tq * 2;
-            Gs[r * GP + c] = acc[i][j][0];
-            Gs[r * GP + c + 1] = acc[i][j][1];
-            if (!(diag && i == j)) {                 // mirror (diagonal tiles already hold both triangles)
-                Gs[c * GP + r] = acc[i][j][0];
-                Gs[(c + 1) * GP + r] = acc[i][j][1];
-            }
+    for (int s = 0; s < MAXT; s++) {
+        if (!tv[s]) continue;
+        const int r = ta[s], c = tb[s] - gq + tq * 2;                   // C fragment: row gq, columns 2 tq, 2 tq + 1
+        Gs[r * GP + c] = acc[s][0];
+        Gs[r * GP + c + 1] = acc[s][1];
+        if (ta[s] - gq != tb[s] - gq) {                                  // mirror (diagonal tiles already hold both triangles)
+            Gs[c * GP + r] = acc[s][0];
+            Gs[(c + 1) * GP + r] = acc[s][1];
         }
+    }
     if (a.Gstore) {          // keep / extend the column's Gram matrix for later row updates (incremental path)
         __syncthreads();
         double* gst = a.Gstore + (int64_t)(a.col_begin + col) * F_LW * F_LW;
-        for (int e = tid; e < F_LW * F_LW; e += 128) {
-            const int r = e >> 6, c = e & 63;
+        for (int e = tid; e < WM * WM; e += 128) {
+            const int r = e / WM, c = e % WM;
             double v = Gs[r * GP + c];
-            if (a.accumulate) { v += gst[e]; Gs[r * GP + c] = v; }
-            gst[e] = v;
+            if (a.accumulate) { v += gst[r * F_LW + c]; Gs[r * GP + c] = v; }
+            gst[r * F_LW + c] = v;
         }
     }
     // h'(ix)[l] = sum_k Ux(ix)[k] Hz_P[l][k]     (Hz = z^T Y, computed once per posterior by hz_kernel)
@@ -318,15 +310,15 @@ __global__ void __launch_bounds__(128) gram_eval_kernel(GramArgs a) {
     // step 6: every grid point of the column;  q = sum_l u_l (G_ll u_l + 2 sum_{c<l} G_lc u_c)
     for (int iy = tid; iy < a.ny; iy += 128) {
         const double* up = a.Uy + (int64_t)iy * F_LW;
-        double u[F_LW];
+        double u[WM];
 #pragma unroll
-        for (int l = 0; l < F_LW; l += 2) {
+        for (int l = 0; l < WM; l += 2) {
             const double2 t = __ldg(reinterpret_cast<const double2*>(up + l));
             u[l] = t.x; u[l + 1] = t.y;
         }
         double q = 0.0, m = 0.0;
 #pragma unroll
-        for (int l = 0; l < F_LW; l += 2) {          // rows l, l+1 together: 16-byte loads of G
+        for (int l = 0; l < WM; l += 2) {          // rows l, l+1 together: 16-byte loads of G
             const double* g0 = Gs + l * GP;
             const double* g1 = g0 + GP;
             double s0 = 0.0, s1 = 0.0;
@@ -471,8 +463,11 @@ int f_tail(const FGeom& g, FLayout& L, const double* z, int64_t rows, double* Gs
            double* mu, double* var, double* qred, cudaStream_t st) {
     const DevParams dp = make_dev_params(*g.p);
     const int64_t npad = rows;
-    const size_t gsmem = sizeof(double) * (2 * G_ROWS * G_LD + F_LW * (F_LW + 2) + 2 * F_LW) + 64;
-    MFGP_CUDA_CHECK(cudaFuncSetAttribute(gram_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));
+    const bool narrow = L.parts[0].ry <= 40;          // padded width of the y expansion: 40 (15 Gram tiles) or 64 (36)
+    const int wm = narrow ? 40 : 64;
+    const size_t gsmem = sizeof(double) * (2 * G_ROWS * G_LD + wm * (wm + 2) + 2 * F_LW) + 64;
+    MFGP_CUDA_CHECK(cudaFuncSetAttribute(gram_eval_kernel<40>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));
+    MFGP_CUDA_CHECK(cudaFuncSetAttribute(gram_eval_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));
     int64_t hoff = 0;
     for (int pi = 0; pi < L.nparts; pi++) {
         FPart& f = L.parts[pi];
@@ -502,7 +497,8 @@ int f_tail(const FGeom& g, FLayout& L, const double* z, int64_t rows, double* Gs
         ga.UxL = nullptr; ga.UxH = L.parts[0].Ux + c0 * L.parts[0].kpad;
         ga.kL = 0; ga.kH = L.parts[0].kpad;
         ga.mean = dp.mean_H; ga.k0 = dp.k0; ga.mu = mu; ga.var = var; ga.qred = qred;
-        gram_eval_kernel<<<(unsigned)cc, 128, gsmem, st>>>(ga);
+        if (narrow) gram_eval_kernel<40><<<(unsigned)cc, 128, gsmem, st>>>(ga);
+        else gram_eval_kernel<64><<<(unsigned)cc, 128, gsmem, st>>>(ga);
         MFGP_LAUNCH_CHECK();
     }
     return MFGP_OK;
