@@ -241,6 +241,8 @@ class DeviceGP:
             return
         self.ensure_factor(need_inverse=False)
         info = int(self.info.item())
+        if info < 0:
+            raise RuntimeError("libmfgp_b200: the tiled Cholesky kernel gave up waiting for a tile (internal error)")
         if info != 0:
             raise np.linalg.LinAlgError(f"Matrix is not positive definite (pivot {info - 1})")
 

@@ -2,6 +2,8 @@
 // Replaces SFGP.updt_info (reference gaussian_process.py:229-255) and MFGP.updt_info (:493-529).
 #include "common.cuh"
 #include "gemm_f64.cuh"
+#include <cstdlib>
+#include <cstring>
 
 namespace mfgp {
 
@@ -50,36 +52,35 @@ __global__ void build_train_cov_kernel(const double* __restrict__ Xt, int NL, in
 }
 
 // ---- 64x64 diagonal block: Cholesky + inverse in one CTA --------------------------------------------------------------
-// 256 threads as a 16x16 grid; thread (ti, tc) keeps the 4x4 cyclic sub-block S[ti+16a][tc+16b] in REGISTERS.
-// Factor: right-looking, ONE barrier per column and no divide / sqrt on the critical path -- column j is left
-// UNSCALED (u = L sqrt(p_j)); its owners publish it to a double-buffered shared column, every thread takes
-// r = rsqrt(p_j) and applies a[i][c] -= u_i u_c r^2 to its 16 registers; L = u r is applied once at the end (r_j is also
-// 1 / L[j][j], so the inverse needs no divide).  The j loop is 4 (unrolled: static register index) x 16 (rolled).
-// Inverse: block doubling inside the CTA, X21 = -X22 (L21 X11) for block sizes 8 -> 16 -> 32, all pairs of a level in
-// parallel, the product L21 X11 parked in the (finally zero) upper-right block of X.
+// 256 threads as a 16x16 grid; thread (ti, tc) keeps the 4x4 cyclic sub-blocks S[ti+16a][tc+16b] and M[ti+16a][tc+16b]
+// in REGISTERS.  Factor: right-looking, ONE barrier per column and no divide / sqrt on the critical path -- column j is
+// left UNSCALED (u = L sqrt(p_j)); its owners publish it to a double-buffered shared column, every thread takes
+// r = rsqrt(p_j) and applies a[i][c] -= u_i u_c r^2 to its 16 registers; L = u r is applied once at the end.
+// Inverse: carried along in the same sweep instead of a second (serial) phase -- M starts as the identity, and with
+// row j of M published next to column j, rows below take M_i -= (u_i r^2) M_j; at the end W = L^-1 = diag(r) M
+// (r_j = 1 / L[j][j], so no divide either).  M stays lower triangular exactly; groups of 16 columns right of j are skipped.
+// The j loop is 4 (unrolled: static register index) x 16 (rolled).
 constexpr int PB = 64;
 constexpr int PLD = PB + 1;
 
-__global__ void __launch_bounds__(256, 1) potrf_diag_kernel(double* __restrict__ A, int64_t ld, double* __restrict__ Winv,
-                                                         int64_t ldw, int32_t* __restrict__ info, int jblk) {
-    extern __shared__ __align__(16) double potrf_smem[];   // 2 x 64x65 doubles: above the 48 KB static limit
-    double* S = potrf_smem;
-    double* X = potrf_smem + PB * PLD;
+__device__ __forceinline__ void potrf_diag_body(double* __restrict__ A, int64_t ld, double* __restrict__ Winv, int64_t ldw,
+                                                int32_t* __restrict__ info, int jblk) {
     __shared__ double rs[PB];        // 1/sqrt(pivot) == 1/L[j][j]
     __shared__ double colbuf[2][PB];
+    __shared__ double rowbuf[2][PB];
     __shared__ int bad;
     const int tid = threadIdx.x;
     const int ti = tid >> 4, tc = tid & 15;
     if (tid == 0) bad = 0;
-    double s[4][4];
+    double s[4][4], m[4][4];
 #pragma unroll
     for (int a = 0; a < 4; a++)
 #pragma unroll
         for (int b = 0; b < 4; b++) {
             const int r = ti + 16 * a, c = tc + 16 * b;
             s[a][b] = (c <= r) ? A[(int64_t)r * ld + c] : 0.0;
+            m[a][b] = (r == c) ? 1.0 : 0.0;
         }
-    for (int e = tid; e < PB * PB; e += 256) X[(e >> 6) * PLD + (e & 63)] = 0.0;
     __syncthreads();
 #pragma unroll
     for (int jb = 0; jb < 4; jb++) {
@@ -87,9 +88,14 @@ __global__ void __launch_bounds__(256, 1) potrf_diag_kernel(double* __restrict__
         for (int jj = 0; jj < 16; jj++) {
             const int j = jb * 16 + jj;
             double* col = colbuf[j & 1];
+            double* row = rowbuf[j & 1];
             if (tc == jj) {          // owners of column j publish it (rows above j are never read)
 #pragma unroll
                 for (int a = 0; a < 4; a++) col[ti + 16 * a] = s[a][jb];
+            }
+            if (ti == jj) {          // owners of row j of M
+#pragma unroll
+                for (int b = 0; b < 4; b++) row[tc + 16 * b] = m[jb][b];
             }
             __syncthreads();
             double piv = col[j];
@@ -103,11 +109,13 @@ __global__ void __launch_bounds__(256, 1) potrf_diag_kernel(double* __restrict__
             const double r = rsqrt(piv);
             const double ip = r * r;
             if (tid == 0) rs[j] = r;
-            double ui[4], uc[4];
+            double ui[4], uc[4], mj[4];
 #pragma unroll
             for (int a = 0; a < 4; a++) ui[a] = col[ti + 16 * a] * ip;
 #pragma unroll
             for (int b = 0; b < 4; b++) uc[b] = col[tc + 16 * b];
+#pragma unroll
+            for (int b = 0; b < 4; b++) mj[b] = row[tc + 16 * b];
 #pragma unroll
             for (int b = 0; b < 4; b++) {
                 if (b < jb) continue;                       // columns of earlier 16-groups are final
@@ -115,6 +123,16 @@ __global__ void __launch_bounds__(256, 1) potrf_diag_kernel(double* __restrict__
 #pragma unroll
                 for (int a = 0; a < 4; a++)
                     if (live) s[a][b] = fma(-ui[a], uc[b], s[a][b]);
+            }
+#pragma unroll
+            for (int a = 0; a < 4; a++) {
+                if (a < jb) continue;                       // rows of earlier 16-groups are final
+                const bool live = ti + 16 * a > j;          // only rows below j change
+#pragma unroll
+                for (int b = 0; b < 4; b++) {
+                    if (b > jb) continue;                   // M_j is zero right of column j
+                    if (live) m[a][b] = fma(-ui[a], mj[b], m[a][b]);
+                }
             }
         }
     }
@@ -126,53 +144,246 @@ __global__ void __launch_bounds__(256, 1) potrf_diag_kernel(double* __restrict__
         for (int b = 0; b < 4; b++) {
             const int r = ti + 16 * a, c = tc + 16 * b;
             // on failure leave a harmless identity so later kernels stay finite; the host raises on `info`
-            const double v = failed ? ((r == c) ? 1.0 : 0.0) : ((c <= r) ? s[a][b] * rs[c] : 0.0);
-            S[r * PLD + c] = v;
-            if (c <= r) A[(int64_t)r * ld + c] = v;
+            if (c <= r) A[(int64_t)r * ld + c] = failed ? ((r == c) ? 1.0 : 0.0) : s[a][b] * rs[c];
+            if (Winv != nullptr)
+                Winv[(int64_t)r * ldw + c] = failed ? ((r == c) ? 1.0 : 0.0) : ((c <= r) ? m[a][b] * rs[r] : 0.0);
         }
-    __syncthreads();
-    if (failed && tid < PB) rs[tid] = 1.0;
-    __syncthreads();
-    if (Winv == nullptr) return;
-    // level 0: the eight 8x8 diagonal blocks, one warp each, lane c < 8 solves column c by forward substitution
-    {
-        const int b0 = (tid >> 5) * 8, c = tid & 31;
-        if (c < 8) {
-            for (int i = c; i < 8; i++) {
-                double s = (i == c) ? 1.0 : 0.0;
-                for (int k = c; k < i; k++) s = fma(-S[(b0 + i) * PLD + b0 + k], X[(b0 + k) * PLD + b0 + c], s);
-                X[(b0 + i) * PLD + b0 + c] = s * rs[b0 + i];
+}
+
+__global__ void __launch_bounds__(256, 1) potrf_diag_kernel(double* __restrict__ A, int64_t ld, double* __restrict__ Winv,
+                                                         int64_t ldw, int32_t* __restrict__ info, int jblk) {
+    potrf_diag_body(A, ld, Winv, ldw, info, jblk);
+}
+
+// ---- tiled Cholesky + forward substitution as ONE persistent dataflow kernel -----------------------------------------
+// The launch-per-panel chain (potrf -> panel solve -> trailing update, three dependent kernels per 64 columns) is bound
+// by launch and drain latency, not by flops.  Here every 64x64 tile of L (and of Y = L^-1 B) is one task; CTAs draw
+// tasks from a ticket counter in column-major order (diagonal tile, the tiles below it, then the row of right-hand-side
+// tiles of the same block row) and synchronise through per-tile ready flags in global memory:
+//   L tile (i, c), i > c:  acc = sum_{k<c} L_ik L_ck^T  (left-looking: accumulated in registers as the L_*k tiles become
+//                          ready, so when column c's diagonal block is factored only X = (A_ic - acc) W_cc^T remains)
+//   diagonal tile (c, c):  S = A_cc - sum_{k<c} L_ck L_ck^T, then the in-CTA factor + inverse (potrf_diag_body)
+//   Y tile (c, r):         Y_cr = W_cc (B_cr - sum_{k<c} L_ck Y_kr)
+// A task waits only on tasks with a SMALLER ticket, and a CTA holds a ticket only while it is resident, so the scheme
+// cannot deadlock whatever the number of resident CTAs; a bounded spin (abort flag) guards against bugs all the same.
+constexpr int DF_K = 32;                 // K slab
+constexpr int DF_LDA = DF_K + 4;         // [m][k] / [n][k] slabs: rows land on distinct 8-bank groups
+constexpr int DF_LDT = PB + 4;           // [k][n] slabs and the 64x64 epilogue tiles
+constexpr int DF_STAGE = PB * DF_LDA;    // doubles per operand per stage (64 x 36 = 2304 >= 32 x 68 = 2176)
+constexpr int DF_SMEM_DOUBLES = 4 * DF_STAGE;     // 2 stages x (A, B) = 9216 doubles; the epilogue needs 8704
+constexpr int DF_THREADS = 256;
+
+struct DfArgs {
+    double* K; int64_t ld;
+    double* W; int64_t ldw;
+    double* Bm; int64_t ldb;
+    int nb, nr;
+    int32_t* info;
+    int* flagsL;        // [nb][nb]: tile (i, c) of L is final (diagonal: L_cc and W_cc)
+    int* flagsY;        // [nb][nr]
+    int* ctrl;          // [0] ticket counter, [1] abort
+    int total;
+    long long spin_limit;
+};
+
+__device__ __forceinline__ int df_ld_acquire(const int* p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void df_st_release(int* p, int v) {
+    asm volatile("st.release.gpu.global.s32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
+}
+// lane 0 of the calling warp spins until *f != 0 (or the abort flag is raised); every lane gets the verdict
+__device__ __forceinline__ bool df_wait(const int* f, int* ctrl, int32_t* info, long long limit) {
+    int ok = 1;
+    if ((threadIdx.x & 31) == 0) {
+        if (!df_ld_acquire(f)) {
+            const long long t0 = clock64();
+            while (!df_ld_acquire(f)) {
+                __nanosleep(32);
+                if (clock64() - t0 > limit) { atomicExch(ctrl + 1, 1); atomicExch(info, -1); }
+                if (*reinterpret_cast<volatile int*>(ctrl + 1)) { ok = 0; break; }
             }
         }
     }
-    for (int bs = 8, sh = 3; bs < PB; bs <<= 1, sh++) {
-        const int total = 32 * bs;                  // (64 / 2bs) pairs x bs^2 elements
-        __syncthreads();
-        for (int e = tid; e < total; e += 256) {    // T = L21 X11 (X11 lower triangular: k >= c)
-            const int t = e >> (2 * sh), rem = e & (bs * bs - 1), i = rem >> sh, c = rem & (bs - 1);
-            const int top = 2 * bs * t;
-            double s = 0.0;
-            for (int k = c; k < bs; k++) s = fma(S[(top + bs + i) * PLD + top + k], X[(top + k) * PLD + top + c], s);
-            X[(top + i) * PLD + top + bs + c] = s;
+    ok = __shfl_sync(0xffffffffu, ok, 0);
+    return ok != 0;
+}
+
+__global__ void __launch_bounds__(DF_THREADS, 2) chol_dataflow_kernel(DfArgs g) {
+    extern __shared__ __align__(16) double df_smem[];
+    __shared__ int task[4];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = (warp >> 1) * 16, wn = (warp & 1) * 32;       // 8 warps: 4 x 2, warp tile 16 x 32
+    const int gq = lane >> 2, tq = lane & 3;
+    double* As0 = df_smem;
+    double* Bs0 = df_smem + 2 * DF_STAGE;
+
+    for (;;) {
+        __syncthreads();                      // the previous task is done with shared memory and task[]
+        if (tid == 0) {
+            int t = atomicAdd(g.ctrl, 1);
+            int c = 0, kind = -1, idx = 0;
+            if (t < g.total) {
+                for (;;) {
+                    const int n = (g.nb - c) + g.nr;
+                    if (t < n) break;
+                    t -= n; c++;
+                }
+                if (t < g.nb - c) { kind = 0; idx = c + t; } else { kind = 1; idx = t - (g.nb - c); }
+            }
+            task[0] = kind; task[1] = c; task[2] = idx;
         }
         __syncthreads();
-        for (int e = tid; e < total; e += 256) {    // X21 = -X22 T (X22 lower triangular: k <= i)
-            const int t = e >> (2 * sh), rem = e & (bs * bs - 1), i = rem >> sh, c = rem & (bs - 1);
-            const int top = 2 * bs * t;
-            double s = 0.0;
-            for (int k = 0; k <= i; k++) s = fma(X[(top + bs + i) * PLD + top + bs + k], X[(top + k) * PLD + top + bs + c], s);
-            X[(top + bs + i) * PLD + top + c] = -s;
+        const int kind = task[0], c = task[1], idx = task[2];
+        if (kind < 0) return;
+        const bool rhs = kind == 1;
+        const int i = rhs ? c : idx;                 // block row of the output tile (and of the A operand L_i*)
+        // operands of the k loop: A = L_i,k ([m][k]);  B = L_c,k ([n][k], transposed product) or Y_k,r ([k][n])
+        const double* Ag = g.K + (int64_t)i * PB * g.ld;
+        const double* Bg = rhs ? g.Bm + (int64_t)idx * PB : g.K + (int64_t)c * PB * g.ld;
+        const int* fa = g.flagsL + (int64_t)i * g.nb;                      // L_i,k ready
+        const int* fb = rhs ? g.flagsY + idx : g.flagsL + (int64_t)c * g.nb;   // Y_k,r (stride nr) or L_c,k ready
+        const int fbs = rhs ? g.nr : 1;
+
+        double acc[2][4][2];
+#pragma unroll
+        for (int a = 0; a < 2; a++)
+#pragma unroll
+            for (int b = 0; b < 4; b++) acc[a][b][0] = acc[a][b][1] = 0.0;
+
+        bool ok = true;
+        auto stage = [&](int buf, int s) {
+            const int k0 = s * DF_K;
+            if ((s & 1) == 0) {                       // first slab of a 64-wide k tile: its producers must be done
+                const int kt = s >> 1;
+                ok = df_wait(fa + kt, g.ctrl, g.info, g.spin_limit) && ok;
+                if (rhs || i != c) ok = df_wait(fb + (int64_t)kt * fbs, g.ctrl, g.info, g.spin_limit) && ok;
+            }
+            double* As = As0 + buf * DF_STAGE;
+            double* Bs = Bs0 + buf * DF_STAGE;
+#pragma unroll
+            for (int e = tid; e < PB * (DF_K / 2); e += DF_THREADS) {     // 64 rows x 16 chunks of 16 bytes
+                const int r = e >> 4, q = e & 15;
+                cp_async16(&As[r * DF_LDA + q * 2], Ag + (int64_t)r * g.ld + k0 + q * 2, true);
+            }
+            if (!rhs) {
+#pragma unroll
+                for (int e = tid; e < PB * (DF_K / 2); e += DF_THREADS) {
+                    const int r = e >> 4, q = e & 15;
+                    cp_async16(&Bs[r * DF_LDA + q * 2], Bg + (int64_t)r * g.ld + k0 + q * 2, true);
+                }
+            } else {
+#pragma unroll
+                for (int e = tid; e < DF_K * (PB / 2); e += DF_THREADS) { // 32 rows x 32 chunks
+                    const int r = e >> 5, q = e & 31;
+                    cp_async16(&Bs[r * DF_LDT + q * 2], Bg + (int64_t)(k0 + r) * g.ldb + q * 2, true);
+                }
+            }
+            cp_async_commit();
+        };
+
+        const int nslab = c * (PB / DF_K);
+        if (nslab > 0) stage(0, 0);
+        for (int s = 0; s < nslab; s++) {
+            const int buf = s & 1;
+            if (s + 1 < nslab) {
+                stage(buf ^ 1, s + 1);
+                cp_async_wait<1>();
+            } else {
+                cp_async_wait<0>();
+            }
+            if (__syncthreads_or(!ok)) return;        // abort raised: every thread of the CTA leaves together
+            const double* As = As0 + buf * DF_STAGE;
+            const double* Bs = Bs0 + buf * DF_STAGE;
+#pragma unroll
+            for (int kk = 0; kk < DF_K; kk += 4) {
+                double a[2], b[4];
+#pragma unroll
+                for (int x = 0; x < 2; x++) a[x] = As[(wm + x * 8 + gq) * DF_LDA + kk + tq];
+#pragma unroll
+                for (int y = 0; y < 4; y++)
+                    b[y] = rhs ? Bs[(kk + tq) * DF_LDT + wn + y * 8 + gq] : Bs[(wn + y * 8 + gq) * DF_LDA + kk + tq];
+#pragma unroll
+                for (int x = 0; x < 2; x++)
+#pragma unroll
+                    for (int y = 0; y < 4; y++) dmma884(acc[x][y][0], acc[x][y][1], a[x], b[y]);
+            }
+            __syncthreads();
         }
+
+        // ---- epilogue ----
+        double* Ct = rhs ? g.Bm + (int64_t)c * PB * g.ldb + (int64_t)idx * PB : g.K + (int64_t)i * PB * g.ld + (int64_t)c * PB;
+        const int64_t ldc = rhs ? g.ldb : g.ld;
+        double* Wcc = g.W + (int64_t)c * PB * (g.ldw + 1);
+        int* myflag = rhs ? g.flagsY + (int64_t)c * g.nr + idx : g.flagsL + (int64_t)i * g.nb + c;
+        if (!rhs && i == c) {
+            // diagonal tile: S = A_cc - acc back to global, then factor + invert inside this CTA
+#pragma unroll
+            for (int x = 0; x < 2; x++)
+#pragma unroll
+                for (int y = 0; y < 4; y++) {
+                    double2* p = reinterpret_cast<double2*>(Ct + (int64_t)(wm + x * 8 + gq) * ldc + wn + y * 8 + tq * 2);
+                    double2 v = *p;
+                    v.x -= acc[x][y][0]; v.y -= acc[x][y][1];
+                    *p = v;
+                }
+            __syncthreads();
+            potrf_diag_body(Ct, ldc, Wcc, g.ldw, g.info, c);
+        } else {
+            double* Xs = df_smem;                 // [64][68]  X = C - acc
+            double* Ws = df_smem + PB * DF_LDT;   // [64][68]  W_cc
+#pragma unroll
+            for (int x = 0; x < 2; x++)
+#pragma unroll
+                for (int y = 0; y < 4; y++) {
+                    const int r = wm + x * 8 + gq, cc = wn + y * 8 + tq * 2;
+                    const double2 v = *reinterpret_cast<const double2*>(Ct + (int64_t)r * ldc + cc);
+                    Xs[r * DF_LDT + cc] = v.x - acc[x][y][0];
+                    Xs[r * DF_LDT + cc + 1] = v.y - acc[x][y][1];
+                    acc[x][y][0] = acc[x][y][1] = 0.0;
+                }
+            const bool okd = df_wait(g.flagsL + (int64_t)c * g.nb + c, g.ctrl, g.info, g.spin_limit);
+#pragma unroll
+            for (int e = tid; e < PB * (PB / 2); e += DF_THREADS) {
+                const int r = e >> 5, q = e & 31;
+                cp_async16(&Ws[r * DF_LDT + q * 2], Wcc + (int64_t)r * g.ldw + q * 2, okd);
+            }
+            cp_async_commit();
+            cp_async_wait<0>();
+            if (__syncthreads_or(!okd)) return;
+#pragma unroll 4
+            for (int kk = 0; kk < PB; kk += 4) {
+                double a[2], b[4];
+                if (!rhs) {       // L_ic = X W_cc^T :  A = X [m][k],  B = W_cc [n][k]
+#pragma unroll
+                    for (int x = 0; x < 2; x++) a[x] = Xs[(wm + x * 8 + gq) * DF_LDT + kk + tq];
+#pragma unroll
+                    for (int y = 0; y < 4; y++) b[y] = Ws[(wn + y * 8 + gq) * DF_LDT + kk + tq];
+                } else {          // Y_cr = W_cc X :    A = W_cc [m][k],  B = X [k][n]
+#pragma unroll
+                    for (int x = 0; x < 2; x++) a[x] = Ws[(wm + x * 8 + gq) * DF_LDT + kk + tq];
+#pragma unroll
+                    for (int y = 0; y < 4; y++) b[y] = Xs[(kk + tq) * DF_LDT + wn + y * 8 + gq];
+                }
+#pragma unroll
+                for (int x = 0; x < 2; x++)
+#pragma unroll
+                    for (int y = 0; y < 4; y++) dmma884(acc[x][y][0], acc[x][y][1], a[x], b[y]);
+            }
+#pragma unroll
+            for (int x = 0; x < 2; x++)
+#pragma unroll
+                for (int y = 0; y < 4; y++) {
+                    double2 v;
+                    v.x = acc[x][y][0]; v.y = acc[x][y][1];
+                    *reinterpret_cast<double2*>(Ct + (int64_t)(wm + x * 8 + gq) * ldc + wn + y * 8 + tq * 2) = v;
+                }
+        }
+        __threadfence();
         __syncthreads();
-        for (int e = tid; e < total; e += 256) {    // clear the parked product
-            const int t = e >> (2 * sh), rem = e & (bs * bs - 1), i = rem >> sh, c = rem & (bs - 1);
-            X[(2 * bs * t + i) * PLD + 2 * bs * t + bs + c] = 0.0;
-        }
-    }
-    __syncthreads();
-    for (int e = tid; e < PB * PB; e += 256) {
-        const int r = e >> 6, c = e & 63;
-        Winv[(int64_t)r * ldw + c] = X[r * PLD + c];
+        if (tid == 0) df_st_release(myflag, 1);
     }
 }
 
@@ -228,15 +439,71 @@ extern "C" int mfgp_build_train_cov(const double* Xt, int64_t NL, int64_t NH, co
     return MFGP_OK;
 }
 
+namespace {
+struct DfScratch {
+    int* buf = nullptr;
+    int64_t ints = 0;
+    int sms = 0;
+};
+DfScratch g_df[16];
+
+bool use_panel_chain() {
+    static const int v = [] {
+        const char* e = getenv("MFGP_CHOL");
+        return (e && std::strcmp(e, "chain") == 0) ? 1 : 0;
+    }();
+    return v != 0;
+}
+
+// One launch: K -> L (lower, in place), diagonal blocks of W -> inverses of L's diagonal blocks, Bm[npad, R] -> L^-1 Bm
+// (R may be 0).  The ready flags live in a per-device scratch buffer: calls on one device must not overlap in time.
+int chol_dataflow(double* K, int64_t npad, int64_t ld, double* W, int64_t ldw, int32_t* info, double* Bm, int64_t ldb, int64_t R,
+                  cudaStream_t st) {
+    int dev = 0;
+    MFGP_CUDA_CHECK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 16) return MFGP_ERR_INVALID;
+    DfScratch& sc = g_df[dev];
+    const int nb = (int)(npad / PB), nr = (int)(R / PB);
+    const int64_t need = 2 + (int64_t)nb * nb + (int64_t)nb * nr;
+    if (need > sc.ints) {
+        if (sc.buf) {
+            MFGP_CUDA_CHECK(cudaDeviceSynchronize());
+            MFGP_CUDA_CHECK(cudaFree(sc.buf));
+            sc.buf = nullptr;
+        }
+        int64_t n = need > (1 << 18) ? need : (1 << 18);
+        MFGP_CUDA_CHECK(cudaMalloc(&sc.buf, n * sizeof(int)));
+        sc.ints = n;
+        MFGP_CUDA_CHECK(cudaDeviceGetAttribute(&sc.sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    MFGP_CUDA_CHECK(cudaMemsetAsync(sc.buf, 0, need * sizeof(int), st));
+    MFGP_CUDA_CHECK(cudaMemsetAsync(info, 0, sizeof(int32_t), st));
+    DfArgs a{};
+    a.K = K; a.ld = ld; a.W = W; a.ldw = ldw; a.Bm = Bm; a.ldb = ldb; a.nb = nb; a.nr = nr; a.info = info;
+    a.ctrl = sc.buf; a.flagsL = sc.buf + 2; a.flagsY = sc.buf + 2 + (int64_t)nb * nb;
+    a.total = nb * (nb + 1) / 2 + nb * nr;
+    a.spin_limit = 4000000000LL;      // ~2 s of SM clocks: only a bug can get there
+    constexpr int smem = DF_SMEM_DOUBLES * sizeof(double);
+    MFGP_CUDA_CHECK(cudaFuncSetAttribute(chol_dataflow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    static const int occ = [] { const char* e = getenv("MFGP_DF_OCC"); return e ? atoi(e) : 2; }();
+    int grid = (occ < 1 ? 1 : occ) * sc.sms;
+    if (grid > a.total) grid = a.total;
+    chol_dataflow_kernel<<<grid, DF_THREADS, smem, st>>>(a);
+    MFGP_LAUNCH_CHECK();
+    return MFGP_OK;
+}
+}  // namespace
+
 extern "C" int mfgp_cholesky(double* K, int64_t npad, int64_t ld, double* W, int64_t ldw, int32_t* info, void* work,
                              void* stream) {
     if (!K || !info || npad <= 0 || npad % MFGP_TILE || ld < npad) return MFGP_ERR_INVALID;
     if (!W && !work) return MFGP_ERR_INVALID;
     if (W && ldw < npad) return MFGP_ERR_INVALID;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (W && !use_panel_chain()) return chol_dataflow(K, npad, ld, W, ldw, info, nullptr, 0, 0, st);
     MFGP_CUDA_CHECK(cudaMemsetAsync(info, 0, sizeof(int32_t), st));
     const int nb = (int)(npad / PB);
-    constexpr int POTRF_SMEM = 2 * PB * PLD * sizeof(double);
+    constexpr int POTRF_SMEM = 0;   // the factor + inverse sweep lives in registers and static shared memory
     MFGP_CUDA_CHECK(cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, POTRF_SMEM));
     for (int j = 0; j < nb; j++) {
         double* Ajj = K + (int64_t)j * PB * (ld + 1);
@@ -305,6 +572,7 @@ extern "C" int mfgp_cholesky_solve(double* K, int64_t npad, int64_t ld, double* 
     if (!K || !W || !info || !Bm || npad <= 0 || npad % MFGP_TILE || ld < npad || ldw < npad || R <= 0 || R % GT || ldb < R)
         return MFGP_ERR_INVALID;
     cudaStream_t caller = static_cast<cudaStream_t>(stream);
+    if (!use_panel_chain()) return chol_dataflow(K, npad, ld, W, ldw, info, Bm, ldb, R, caller);
     SideStream* side = nullptr;
     int rcs = side_for_current_device(&side);
     if (rcs) return rcs;
@@ -314,7 +582,7 @@ extern "C" int mfgp_cholesky_solve(double* K, int64_t npad, int64_t ld, double* 
     MFGP_CUDA_CHECK(cudaStreamWaitEvent(st, side->ev_begin, 0));
     MFGP_CUDA_CHECK(cudaMemsetAsync(info, 0, sizeof(int32_t), st));
     const int nb = (int)(npad / PB);
-    constexpr int POTRF_SMEM = 2 * PB * PLD * sizeof(double);
+    constexpr int POTRF_SMEM = 0;   // the factor + inverse sweep lives in registers and static shared memory
     MFGP_CUDA_CHECK(cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, POTRF_SMEM));
     for (int j = 0; j < nb; j++) {
         double* Ajj = K + (int64_t)j * PB * (ld + 1);
@@ -430,7 +698,7 @@ extern "C" int mfgp_cholesky_append(const double* Xt, int64_t NL, int64_t NH_old
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const DevParams dp = make_dev_params(*p_host);
     MFGP_CUDA_CHECK(cudaMemsetAsync(info, 0, sizeof(int32_t), st));
-    constexpr int POTRF_SMEM = 2 * PB * PLD * sizeof(double);
+    constexpr int POTRF_SMEM = 0;   // the factor + inverse sweep lives in registers and static shared memory
     MFGP_CUDA_CHECK(cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, POTRF_SMEM));
     double* part = static_cast<double*>(work);
     for (int64_t rb = N_old / PB * PB; rb < npad; rb += PB) {
