@@ -63,8 +63,8 @@ __global__ void build_train_cov_kernel(const double* __restrict__ Xt, int NL, in
 constexpr int PB = 64;
 constexpr int PLD = PB + 1;
 
-__device__ __forceinline__ void potrf_diag_body(double* __restrict__ A, int64_t ld, double* __restrict__ Winv, int64_t ldw,
-                                                int32_t* __restrict__ info, int jblk) {
+__device__ __forceinline__ void potrf_diag_body(const double* src, int64_t lds, double* A, int64_t ld,
+                                                double* __restrict__ Winv, int64_t ldw, int32_t* __restrict__ info, int jblk) {
     __shared__ double rs[PB];        // 1/sqrt(pivot) == 1/L[j][j]
     __shared__ double colbuf[2][PB];
     __shared__ double rowbuf[2][PB];
@@ -78,7 +78,7 @@ __device__ __forceinline__ void potrf_diag_body(double* __restrict__ A, int64_t 
 #pragma unroll
         for (int b = 0; b < 4; b++) {
             const int r = ti + 16 * a, c = tc + 16 * b;
-            s[a][b] = (c <= r) ? A[(int64_t)r * ld + c] : 0.0;
+            s[a][b] = (c <= r) ? src[(int64_t)r * lds + c] : 0.0;
             m[a][b] = (r == c) ? 1.0 : 0.0;
         }
     __syncthreads();
@@ -152,25 +152,32 @@ __device__ __forceinline__ void potrf_diag_body(double* __restrict__ A, int64_t 
 
 __global__ void __launch_bounds__(256, 1) potrf_diag_kernel(double* __restrict__ A, int64_t ld, double* __restrict__ Winv,
                                                          int64_t ldw, int32_t* __restrict__ info, int jblk) {
-    potrf_diag_body(A, ld, Winv, ldw, info, jblk);
+    potrf_diag_body(A, ld, A, ld, Winv, ldw, info, jblk);
 }
 
 // ---- tiled Cholesky + forward substitution as ONE persistent dataflow kernel -----------------------------------------
 // The launch-per-panel chain (potrf -> panel solve -> trailing update, three dependent kernels per 64 columns) is bound
 // by launch and drain latency, not by flops.  Here every 64x64 tile of L (and of Y = L^-1 B) is one task; CTAs draw
-// tasks from a ticket counter in column-major order (diagonal tile, the tiles below it, then the row of right-hand-side
-// tiles of the same block row) and synchronise through per-tile ready flags in global memory:
-//   L tile (i, c), i > c:  acc = sum_{k<c} L_ik L_ck^T  (left-looking: accumulated in registers as the L_*k tiles become
-//                          ready, so when column c's diagonal block is factored only X = (A_ic - acc) W_cc^T remains)
-//   diagonal tile (c, c):  S = A_cc - sum_{k<c} L_ck L_ck^T, then the in-CTA factor + inverse (potrf_diag_body)
-//   Y tile (c, r):         Y_cr = W_cc (B_cr - sum_{k<c} L_ck Y_kr)
+// tasks from a ticket counter and synchronise through per-tile ready flags in global memory.  Left-looking: a task
+// accumulates its sum over the earlier block columns k in registers AS the tiles L_*k become ready, so that when the
+// diagonal block of its own column is finally factored only one 64^3 product remains:
+//   L tile (i, c), i >= c+2:  L_ic = (A_ic - sum_{k<c} L_ik L_ck^T) W_cc^T
+//   Y tile (c, r):            Y_cr = W_cc (B_cr - sum_{k<c} L_ck Y_kr)
+//   chain task d (the critical path, ONE hop per block column): accumulates BOTH the sub-diagonal tile (d, d-1) and the
+//                             diagonal tile (d, d) over k < d-1 (they share the A operand L_dk); when W_{d-1,d-1} is
+//                             flagged it forms L_{d,d-1} = X W^T, subtracts L_{d,d-1} L_{d,d-1}^T from the diagonal tile
+//                             out of shared memory, and factors + inverts it in place (potrf_diag_body) -> W_dd.
+// Ticket order: chain 0; then per block column c: chain c+1, the tiles (i, c) below it, the Y tiles of block row c.
 // A task waits only on tasks with a SMALLER ticket, and a CTA holds a ticket only while it is resident, so the scheme
 // cannot deadlock whatever the number of resident CTAs; a bounded spin (abort flag) guards against bugs all the same.
+// Two CTAs share an SM; while one of them runs the latency-bound tail of a chain task it raises a per-SM pause flag and
+// the other one idles between its k slabs (its DMMA traffic would otherwise stretch the chain by ~25%).
 constexpr int DF_K = 32;                 // K slab
 constexpr int DF_LDA = DF_K + 4;         // [m][k] / [n][k] slabs: rows land on distinct 8-bank groups
 constexpr int DF_LDT = PB + 4;           // [k][n] slabs and the 64x64 epilogue tiles
 constexpr int DF_STAGE = PB * DF_LDA;    // doubles per operand per stage (64 x 36 = 2304 >= 32 x 68 = 2176)
-constexpr int DF_SMEM_DOUBLES = 4 * DF_STAGE;     // 2 stages x (A, B) = 9216 doubles; the epilogue needs 8704
+constexpr int DF_TILE = PB * DF_LDT;     // one padded 64x64 tile
+constexpr int DF_SMEM_DOUBLES = 3 * DF_TILE;      // epilogue: X, W, L tiles (13056) >= 2 stages x (A, B) = 9216
 constexpr int DF_THREADS = 256;
 
 struct DfArgs {
@@ -182,6 +189,7 @@ struct DfArgs {
     int* flagsL;        // [nb][nb]: tile (i, c) of L is final (diagonal: L_cc and W_cc)
     int* flagsY;        // [nb][nr]
     int* ctrl;          // [0] ticket counter, [1] abort
+    int* pause;         // [number of SMs]
     int total;
     long long spin_limit;
 };
@@ -191,8 +199,16 @@ __device__ __forceinline__ int df_ld_acquire(const int* p) {
     asm volatile("ld.acquire.gpu.global.s32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+__device__ __forceinline__ int df_ld_relaxed(const int* p) {
+    int v;
+    asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
 __device__ __forceinline__ void df_st_release(int* p, int v) {
     asm volatile("st.release.gpu.global.s32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void df_st_relaxed(int* p, int v) {
+    asm volatile("st.relaxed.gpu.global.s32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
 }
 // lane 0 of the calling warp spins until *f != 0 (or the abort flag is raised); every lane gets the verdict
 __device__ __forceinline__ bool df_wait(const int* f, int* ctrl, int32_t* info, long long limit) {
@@ -219,39 +235,54 @@ __global__ void __launch_bounds__(DF_THREADS, 2) chol_dataflow_kernel(DfArgs g) 
     const int gq = lane >> 2, tq = lane & 3;
     double* As0 = df_smem;
     double* Bs0 = df_smem + 2 * DF_STAGE;
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;\n" : "=r"(smid));
+    int* my_pause = g.pause + smid;
 
     for (;;) {
         __syncthreads();                      // the previous task is done with shared memory and task[]
         if (tid == 0) {
             int t = atomicAdd(g.ctrl, 1);
             int c = 0, kind = -1, idx = 0;
-            if (t < g.total) {
+            if (t == 0) {
+                kind = 2; idx = 0;            // chain task 0: the first diagonal block
+            } else if (t < g.total) {
+                t -= 1;
                 for (;;) {
-                    const int n = (g.nb - c) + g.nr;
-                    if (t < n) break;
+                    const int nchain = (c + 1 < g.nb) ? 1 : 0;
+                    const int ntile = g.nb - c - 2 > 0 ? g.nb - c - 2 : 0;
+                    const int n = nchain + ntile + g.nr;
+                    if (t < n) {
+                        if (t < nchain) { kind = 2; idx = c + 1; }
+                        else if (t < nchain + ntile) { kind = 0; idx = c + 2 + (t - nchain); }
+                        else { kind = 1; idx = t - nchain - ntile; }
+                        break;
+                    }
                     t -= n; c++;
                 }
-                if (t < g.nb - c) { kind = 0; idx = c + t; } else { kind = 1; idx = t - (g.nb - c); }
             }
             task[0] = kind; task[1] = c; task[2] = idx;
         }
         __syncthreads();
-        const int kind = task[0], c = task[1], idx = task[2];
+        const int kind = task[0], idx = task[2];
         if (kind < 0) return;
-        const bool rhs = kind == 1;
-        const int i = rhs ? c : idx;                 // block row of the output tile (and of the A operand L_i*)
+        const bool rhs = kind == 1, chain = kind == 2;
+        // c = block column whose diagonal inverse finishes the task; i = block row of the A operand / output tile
+        const int c = chain ? idx - 1 : task[1];
+        const int i = rhs ? c : idx;
+        const int nk = chain ? (idx > 0 ? idx - 1 : 0) : c;             // k tiles accumulated before the epilogue
         // operands of the k loop: A = L_i,k ([m][k]);  B = L_c,k ([n][k], transposed product) or Y_k,r ([k][n])
         const double* Ag = g.K + (int64_t)i * PB * g.ld;
-        const double* Bg = rhs ? g.Bm + (int64_t)idx * PB : g.K + (int64_t)c * PB * g.ld;
-        const int* fa = g.flagsL + (int64_t)i * g.nb;                      // L_i,k ready
-        const int* fb = rhs ? g.flagsY + idx : g.flagsL + (int64_t)c * g.nb;   // Y_k,r (stride nr) or L_c,k ready
+        const double* Bg = rhs ? g.Bm + (int64_t)idx * PB : g.K + (int64_t)(c > 0 ? c : 0) * PB * g.ld;
+        const int* fa = g.flagsL + (int64_t)i * g.nb;                                           // L_i,k ready
+        const int* fb = rhs ? g.flagsY + idx : g.flagsL + (int64_t)(c > 0 ? c : 0) * g.nb;      // Y_k,r (stride nr) or L_c,k
         const int fbs = rhs ? g.nr : 1;
 
-        double acc[2][4][2];
+        double acc[2][4][2], acc2[2][4][2];
 #pragma unroll
         for (int a = 0; a < 2; a++)
 #pragma unroll
-            for (int b = 0; b < 4; b++) acc[a][b][0] = acc[a][b][1] = 0.0;
+            for (int b = 0; b < 4; b++) acc[a][b][0] = acc[a][b][1] = acc2[a][b][0] = acc2[a][b][1] = 0.0;
 
         bool ok = true;
         auto stage = [&](int buf, int s) {
@@ -259,7 +290,7 @@ __global__ void __launch_bounds__(DF_THREADS, 2) chol_dataflow_kernel(DfArgs g) 
             if ((s & 1) == 0) {                       // first slab of a 64-wide k tile: its producers must be done
                 const int kt = s >> 1;
                 ok = df_wait(fa + kt, g.ctrl, g.info, g.spin_limit) && ok;
-                if (rhs || i != c) ok = df_wait(fb + (int64_t)kt * fbs, g.ctrl, g.info, g.spin_limit) && ok;
+                ok = df_wait(fb + (int64_t)kt * fbs, g.ctrl, g.info, g.spin_limit) && ok;
             }
             double* As = As0 + buf * DF_STAGE;
             double* Bs = Bs0 + buf * DF_STAGE;
@@ -284,8 +315,9 @@ __global__ void __launch_bounds__(DF_THREADS, 2) chol_dataflow_kernel(DfArgs g) 
             cp_async_commit();
         };
 
-        const int nslab = c * (PB / DF_K);
+        const int nslab = nk * (PB / DF_K);
         if (nslab > 0) stage(0, 0);
+        int paused = 0;
         for (int s = 0; s < nslab; s++) {
             const int buf = s & 1;
             if (s + 1 < nslab) {
@@ -293,6 +325,10 @@ __global__ void __launch_bounds__(DF_THREADS, 2) chol_dataflow_kernel(DfArgs g) 
                 cp_async_wait<1>();
             } else {
                 cp_async_wait<0>();
+            }
+            if (lane == 0) {                          // the SM's other CTA is in the tail of a chain task: stand back
+                while (paused && df_ld_relaxed(my_pause)) __nanosleep(200);
+                paused = df_ld_relaxed(my_pause);     // (sampled one slab ahead: the load is off the critical path)
             }
             if (__syncthreads_or(!ok)) return;        // abort raised: every thread of the CTA leaves together
             const double* As = As0 + buf * DF_STAGE;
@@ -309,31 +345,28 @@ __global__ void __launch_bounds__(DF_THREADS, 2) chol_dataflow_kernel(DfArgs g) 
                 for (int x = 0; x < 2; x++)
 #pragma unroll
                     for (int y = 0; y < 4; y++) dmma884(acc[x][y][0], acc[x][y][1], a[x], b[y]);
+                if (chain) {                          // diagonal tile (i, i): L_ik L_ik^T out of the same A slab
+#pragma unroll
+                    for (int y = 0; y < 4; y++) b[y] = As[(wn + y * 8 + gq) * DF_LDA + kk + tq];
+#pragma unroll
+                    for (int x = 0; x < 2; x++)
+#pragma unroll
+                        for (int y = 0; y < 4; y++) dmma884(acc2[x][y][0], acc2[x][y][1], a[x], b[y]);
+                }
             }
             __syncthreads();
         }
 
         // ---- epilogue ----
-        double* Ct = rhs ? g.Bm + (int64_t)c * PB * g.ldb + (int64_t)idx * PB : g.K + (int64_t)i * PB * g.ld + (int64_t)c * PB;
+        double* Xs = df_smem;                 // [64][68]  X = C - acc   (later: the diagonal tile S)
+        double* Ws = df_smem + DF_TILE;       // [64][68]  W_cc
+        double* Ls = df_smem + 2 * DF_TILE;   // [64][68]  L_{i,c} of a chain task
+        double* Wcc = g.W + (int64_t)(c > 0 ? c : 0) * PB * (g.ldw + 1);
+        double* Ct = rhs ? g.Bm + (int64_t)c * PB * g.ldb + (int64_t)idx * PB
+                         : g.K + (int64_t)i * PB * g.ld + (int64_t)(c > 0 ? c : 0) * PB;
         const int64_t ldc = rhs ? g.ldb : g.ld;
-        double* Wcc = g.W + (int64_t)c * PB * (g.ldw + 1);
-        int* myflag = rhs ? g.flagsY + (int64_t)c * g.nr + idx : g.flagsL + (int64_t)i * g.nb + c;
-        if (!rhs && i == c) {
-            // diagonal tile: S = A_cc - acc back to global, then factor + invert inside this CTA
-#pragma unroll
-            for (int x = 0; x < 2; x++)
-#pragma unroll
-                for (int y = 0; y < 4; y++) {
-                    double2* p = reinterpret_cast<double2*>(Ct + (int64_t)(wm + x * 8 + gq) * ldc + wn + y * 8 + tq * 2);
-                    double2 v = *p;
-                    v.x -= acc[x][y][0]; v.y -= acc[x][y][1];
-                    *p = v;
-                }
-            __syncthreads();
-            potrf_diag_body(Ct, ldc, Wcc, g.ldw, g.info, c);
-        } else {
-            double* Xs = df_smem;                 // [64][68]  X = C - acc
-            double* Ws = df_smem + PB * DF_LDT;   // [64][68]  W_cc
+        int* myflag = rhs ? g.flagsY + (int64_t)c * g.nr + idx : g.flagsL + (int64_t)i * g.nb + (c > 0 ? c : 0);
+        if (!(chain && idx == 0)) {
 #pragma unroll
             for (int x = 0; x < 2; x++)
 #pragma unroll
@@ -345,6 +378,7 @@ __global__ void __launch_bounds__(DF_THREADS, 2) chol_dataflow_kernel(DfArgs g) 
                     acc[x][y][0] = acc[x][y][1] = 0.0;
                 }
             const bool okd = df_wait(g.flagsL + (int64_t)c * g.nb + c, g.ctrl, g.info, g.spin_limit);
+            if (chain && tid == 0) df_st_relaxed(my_pause, 1);
 #pragma unroll
             for (int e = tid; e < PB * (PB / 2); e += DF_THREADS) {
                 const int r = e >> 5, q = e & 31;
@@ -352,7 +386,10 @@ __global__ void __launch_bounds__(DF_THREADS, 2) chol_dataflow_kernel(DfArgs g) 
             }
             cp_async_commit();
             cp_async_wait<0>();
-            if (__syncthreads_or(!okd)) return;
+            if (__syncthreads_or(!okd)) {
+                if (chain && tid == 0) df_st_relaxed(my_pause, 0);
+                return;
+            }
 #pragma unroll 4
             for (int kk = 0; kk < PB; kk += 4) {
                 double a[2], b[4];
@@ -376,14 +413,56 @@ __global__ void __launch_bounds__(DF_THREADS, 2) chol_dataflow_kernel(DfArgs g) 
             for (int x = 0; x < 2; x++)
 #pragma unroll
                 for (int y = 0; y < 4; y++) {
+                    const int r = wm + x * 8 + gq, cc = wn + y * 8 + tq * 2;
                     double2 v;
                     v.x = acc[x][y][0]; v.y = acc[x][y][1];
-                    *reinterpret_cast<double2*>(Ct + (int64_t)(wm + x * 8 + gq) * ldc + wn + y * 8 + tq * 2) = v;
+                    *reinterpret_cast<double2*>(Ct + (int64_t)r * ldc + cc) = v;
+                    if (chain) { Ls[r * DF_LDT + cc] = v.x; Ls[r * DF_LDT + cc + 1] = v.y; }
                 }
+        }
+        if (chain) {
+            double* Cd = g.K + (int64_t)idx * PB * (g.ld + 1);          // diagonal tile (idx, idx)
+            double* Wd = g.W + (int64_t)idx * PB * (g.ldw + 1);
+            if (idx > 0) {
+                __syncthreads();                      // L_{i,c} complete in shared memory; X is free
+#pragma unroll 4
+                for (int kk = 0; kk < PB; kk += 4) {  // acc2 += L_ic L_ic^T
+                    double a[2], b[4];
+#pragma unroll
+                    for (int x = 0; x < 2; x++) a[x] = Ls[(wm + x * 8 + gq) * DF_LDT + kk + tq];
+#pragma unroll
+                    for (int y = 0; y < 4; y++) b[y] = Ls[(wn + y * 8 + gq) * DF_LDT + kk + tq];
+#pragma unroll
+                    for (int x = 0; x < 2; x++)
+#pragma unroll
+                        for (int y = 0; y < 4; y++) dmma884(acc2[x][y][0], acc2[x][y][1], a[x], b[y]);
+                }
+            }
+#pragma unroll
+            for (int x = 0; x < 2; x++)
+#pragma unroll
+                for (int y = 0; y < 4; y++) {
+                    const int r = wm + x * 8 + gq, cc = wn + y * 8 + tq * 2;
+                    const double2 v = *reinterpret_cast<const double2*>(Cd + (int64_t)r * g.ld + cc);
+                    Xs[r * DF_LDT + cc] = v.x - acc2[x][y][0];
+                    Xs[r * DF_LDT + cc + 1] = v.y - acc2[x][y][1];
+                }
+            if (idx > 0) {                            // publish the sub-diagonal tile before the long factor step
+                __threadfence();
+                __syncthreads();
+                if (tid == 0) df_st_release(myflag, 1);
+            } else {
+                __syncthreads();
+            }
+            potrf_diag_body(Xs, DF_LDT, Cd, g.ld, Wd, g.ldw, g.info, idx);
+            myflag = g.flagsL + (int64_t)idx * g.nb + idx;
         }
         __threadfence();
         __syncthreads();
-        if (tid == 0) df_st_release(myflag, 1);
+        if (tid == 0) {
+            df_st_release(myflag, 1);
+            if (chain) df_st_relaxed(my_pause, 0);
+        }
     }
 }
 
@@ -464,7 +543,7 @@ int chol_dataflow(double* K, int64_t npad, int64_t ld, double* W, int64_t ldw, i
     if (dev < 0 || dev >= 16) return MFGP_ERR_INVALID;
     DfScratch& sc = g_df[dev];
     const int nb = (int)(npad / PB), nr = (int)(R / PB);
-    const int64_t need = 2 + (int64_t)nb * nb + (int64_t)nb * nr;
+    const int64_t need = 2 + 1024 + (int64_t)nb * nb + (int64_t)nb * nr;      // ctrl, per-SM pause flags, tile flags
     if (need > sc.ints) {
         if (sc.buf) {
             MFGP_CUDA_CHECK(cudaDeviceSynchronize());
@@ -480,8 +559,8 @@ int chol_dataflow(double* K, int64_t npad, int64_t ld, double* W, int64_t ldw, i
     MFGP_CUDA_CHECK(cudaMemsetAsync(info, 0, sizeof(int32_t), st));
     DfArgs a{};
     a.K = K; a.ld = ld; a.W = W; a.ldw = ldw; a.Bm = Bm; a.ldb = ldb; a.nb = nb; a.nr = nr; a.info = info;
-    a.ctrl = sc.buf; a.flagsL = sc.buf + 2; a.flagsY = sc.buf + 2 + (int64_t)nb * nb;
-    a.total = nb * (nb + 1) / 2 + nb * nr;
+    a.ctrl = sc.buf; a.pause = sc.buf + 2; a.flagsL = sc.buf + 1026; a.flagsY = sc.buf + 1026 + (int64_t)nb * nb;
+    a.total = nb + (nb - 1) * (nb - 2) / 2 + nb * nr;     // nb chain tasks, the tiles two or more below the diagonal, Y tiles
     a.spin_limit = 4000000000LL;      // ~2 s of SM clocks: only a bug can get there
     constexpr int smem = DF_SMEM_DOUBLES * sizeof(double);
     MFGP_CUDA_CHECK(cudaFuncSetAttribute(chol_dataflow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
