@@ -46,6 +46,7 @@ typedef struct mfgp_params {
 
 const char* mfgp_version(void);
 const char* mfgp_last_error(void);          /* text of the last CUDA error seen by this thread */
+int64_t mfgp_debug_chol_trace(int64_t* out, int64_t max_tasks);   /* diagnostics: per-chain-task time stamps of the tiled Cholesky (MFGP_DF_TRACE=1) */
 int64_t mfgp_launch_count(void);            /* kernels launched by this library since load (bench.py's gpu_launches) */
 int64_t mfgp_npad(int64_t n);               /* n rounded up to MFGP_TILE (at least MFGP_TILE)  */
 int64_t mfgp_workspace_bytes(int64_t npad); /* scratch needed by mfgp_cholesky / mfgp_tri_inverse */

@@ -29,6 +29,7 @@ SIGNATURES = {
     "mfgp_version": (c_char_p, []),
     "mfgp_last_error": (c_char_p, []),
     "mfgp_launch_count": (c_int64, []),
+    "mfgp_debug_chol_trace": (c_int64, [c_void_p, c_int64]),
     "mfgp_npad": (c_int64, [c_int64]),
     "mfgp_workspace_bytes": (c_int64, [c_int64]),
     "mfgp_build_train_cov": (c_int, [c_void_p, c_int64, c_int64, POINTER(MfgpParams), c_void_p, c_int64, c_int64,

@@ -53,21 +53,27 @@ __global__ void build_train_cov_kernel(const double* __restrict__ Xt, int NL, in
 
 // ---- 64x64 diagonal block: Cholesky + inverse in one CTA --------------------------------------------------------------
 // 256 threads as a 16x16 grid; thread (ti, tc) keeps the 4x4 cyclic sub-blocks S[ti+16a][tc+16b] and M[ti+16a][tc+16b]
-// in REGISTERS.  Factor: right-looking, ONE barrier per column and no divide / sqrt on the critical path -- column j is
-// left UNSCALED (u = L sqrt(p_j)); its owners publish it to a double-buffered shared column, every thread takes
-// r = rsqrt(p_j) and applies a[i][c] -= u_i u_c r^2 to its 16 registers; L = u r is applied once at the end.
-// Inverse: carried along in the same sweep instead of a second (serial) phase -- M starts as the identity, and with
-// row j of M published next to column j, rows below take M_i -= (u_i r^2) M_j; at the end W = L^-1 = diag(r) M
-// (r_j = 1 / L[j][j], so no divide either).  M stays lower triangular exactly; groups of 16 columns right of j are skipped.
-// The j loop is 4 (unrolled: static register index) x 16 (rolled).
+// in REGISTERS.  The sweep is bound by one serial chain per step (barrier -> read pivot -> reciprocal -> scale -> FMA ->
+// publish, ~20-cycle FP64 latencies: profiles/r01_fp64_latency.log), so it eliminates TWO columns per step and keeps
+// square roots off the chain altogether:
+//   step k (columns j0 = 2k, j1 = j0+1): the owners publish the two UNSCALED columns U = [u1 u2] (as they stand after the
+//   earlier steps); P = [[a, b], [b, c]] is their 2x2 pivot block; every thread forms P^-1 from ONE reciprocal
+//   (1 / (ac - b^2)) and applies the rank-2 update S -= (U P^-1) U^T to its registers.
+// Inverse: carried along in the same sweep -- M starts as the identity and, with rows j0, j1 of M published next to the
+// columns, the rows below take M_i -= (U_i P^-1) [M_j0; M_j1].
+// Afterwards, with C = chol(P) per pair (32 independent 2x2 factors, computed in parallel),
+//   L[:, pair] = U C^-T     and     W[pair, :] = C^-1 M[pair, :]         (W = L^-1),
+// i.e. even columns / rows are scaled by 1/sqrt(a), odd ones take (x_odd - (b/a) x_even) / sqrt(c - b^2/a); the even
+// partner sits in the neighbouring lane (columns) or 16 lanes away (rows).  No divide or sqrt other than these.
+// Pivot test as in LAPACK potrf (np.linalg.cholesky raises, gaussian_process.py:254 / :529): a > 0, then c - b^2/a > 0.
 constexpr int PB = 64;
 constexpr int PLD = PB + 1;
 
 __device__ __forceinline__ void potrf_diag_body(const double* src, int64_t lds, double* A, int64_t ld,
                                                 double* __restrict__ Winv, int64_t ldw, int32_t* __restrict__ info, int jblk) {
-    __shared__ double rs[PB];        // 1/sqrt(pivot) == 1/L[j][j]
-    __shared__ double colbuf[2][PB];
-    __shared__ double rowbuf[2][PB];
+    __shared__ double colA[2][PB], colB[2][PB], rowA[2][PB], rowB[2][PB];
+    __shared__ double piv[3][PB / 2];     // a, b, c of every pivot block
+    __shared__ double fin[3][PB / 2];     // 1/sqrt(a), 1/sqrt(c - b^2/a), b/a
     __shared__ int bad;
     const int tid = threadIdx.x;
     const int ti = tid >> 4, tc = tid & 15;
@@ -81,60 +87,74 @@ __device__ __forceinline__ void potrf_diag_body(const double* src, int64_t lds, 
             s[a][b] = (c <= r) ? src[(int64_t)r * lds + c] : 0.0;
             m[a][b] = (r == c) ? 1.0 : 0.0;
         }
-    __syncthreads();
 #pragma unroll
     for (int jb = 0; jb < 4; jb++) {
 #pragma unroll 1
-        for (int jj = 0; jj < 16; jj++) {
-            const int j = jb * 16 + jj;
-            double* col = colbuf[j & 1];
-            double* row = rowbuf[j & 1];
-            if (tc == jj) {          // owners of column j publish it (rows above j are never read)
+        for (int jp = 0; jp < 8; jp++) {
+            const int k = jb * 8 + jp, j0 = 2 * k, j1 = j0 + 1, jj0 = 2 * jp, buf = k & 1;
+            if ((tc & 14) == jj0) {          // owners of columns j0 (tc even) and j1 (tc odd); rows above are never read
+                double* dst = (tc & 1) ? colB[buf] : colA[buf];
 #pragma unroll
-                for (int a = 0; a < 4; a++) col[ti + 16 * a] = s[a][jb];
+                for (int a = 0; a < 4; a++) dst[ti + 16 * a] = s[a][jb];
             }
-            if (ti == jj) {          // owners of row j of M
+            if ((ti & 14) == jj0) {          // owners of rows j0, j1 of M
+                double* dst = (ti & 1) ? rowB[buf] : rowA[buf];
 #pragma unroll
-                for (int b = 0; b < 4; b++) row[tc + 16 * b] = m[jb][b];
+                for (int b = 0; b < 4; b++) dst[tc + 16 * b] = m[jb][b];
             }
             __syncthreads();
-            double piv = col[j];
-            if (!(piv > 0.0)) {     // uniform: np.linalg.cholesky raises here (gaussian_process.py:254 / :529)
+            double pa = colA[buf][j0], pb = colA[buf][j1], pc = colB[buf][j1];
+            double det = fma(pa, pc, -(pb * pb));
+            if (!(pa > 0.0) || !(det > 0.0)) {          // uniform
                 if (tid == 0 && !bad) {
                     bad = 1;
-                    atomicCAS(info, 0, jblk * PB + j + 1);
+                    atomicCAS(info, 0, jblk * PB + ((pa > 0.0) ? j1 : j0) + 1);
                 }
-                piv = 1.0;
+                pa = 1.0; pb = 0.0; pc = 1.0; det = 1.0;
             }
-            const double r = rsqrt(piv);
-            const double ip = r * r;
-            if (tid == 0) rs[j] = r;
-            double ui[4], uc[4], mj[4];
-#pragma unroll
-            for (int a = 0; a < 4; a++) ui[a] = col[ti + 16 * a] * ip;
-#pragma unroll
-            for (int b = 0; b < 4; b++) uc[b] = col[tc + 16 * b];
-#pragma unroll
-            for (int b = 0; b < 4; b++) mj[b] = row[tc + 16 * b];
-#pragma unroll
-            for (int b = 0; b < 4; b++) {
-                if (b < jb) continue;                       // columns of earlier 16-groups are final
-                const bool live = tc + 16 * b > j;          // only columns right of j change
-#pragma unroll
-                for (int a = 0; a < 4; a++)
-                    if (live) s[a][b] = fma(-ui[a], uc[b], s[a][b]);
-            }
+            if (tid == 0) { piv[0][k] = pa; piv[1][k] = pb; piv[2][k] = pc; }
+            const double idet = 1.0 / det;
+            const double qa = pc * idet, qb = -pb * idet, qc = pa * idet;      // P^-1
+            double t1[4], t2[4];
 #pragma unroll
             for (int a = 0; a < 4; a++) {
                 if (a < jb) continue;                       // rows of earlier 16-groups are final
-                const bool live = ti + 16 * a > j;          // only rows below j change
+                const double x1 = colA[buf][ti + 16 * a], x2 = colB[buf][ti + 16 * a];
+                t1[a] = fma(qa, x1, qb * x2);
+                t2[a] = fma(qb, x1, qc * x2);
+            }
 #pragma unroll
-                for (int b = 0; b < 4; b++) {
-                    if (b > jb) continue;                   // M_j is zero right of column j
-                    if (live) m[a][b] = fma(-ui[a], mj[b], m[a][b]);
+            for (int b = 0; b < 4; b++) {
+                if (b < jb) continue;                       // columns of earlier 16-groups are final
+                const double y1 = colA[buf][tc + 16 * b], y2 = colB[buf][tc + 16 * b];
+                const bool live = tc + 16 * b > j1;         // only columns right of the pair change
+#pragma unroll
+                for (int a = 0; a < 4; a++) {
+                    if (a < b) continue;                    // register groups strictly above the diagonal are never read
+                    if (live) s[a][b] = fma(-t1[a], y1, fma(-t2[a], y2, s[a][b]));
+                }
+            }
+#pragma unroll
+            for (int b = 0; b < 4; b++) {
+                if (b > jb) continue;                       // rows j0, j1 of M are zero right of column j1
+                const double z1 = rowA[buf][tc + 16 * b], z2 = rowB[buf][tc + 16 * b];
+#pragma unroll
+                for (int a = 0; a < 4; a++) {
+                    if (a < jb) continue;                   // rows of earlier 16-groups are final
+                    const bool live = ti + 16 * a > j1;     // only rows below the pair change
+                    if (live) m[a][b] = fma(-t1[a], z1, fma(-t2[a], z2, m[a][b]));
                 }
             }
         }
+    }
+    __syncthreads();
+    if (tid < PB / 2) {          // C = chol(P) of every pair
+        const double a = piv[0][tid], b = piv[1][tid], c = piv[2][tid];
+        const double r1 = rsqrt(a);
+        const double g = b * r1 * r1;
+        fin[0][tid] = r1;
+        fin[1][tid] = rsqrt(fma(-g, b, c));
+        fin[2][tid] = g;
     }
     __syncthreads();
     const bool failed = bad != 0;
@@ -143,10 +163,15 @@ __device__ __forceinline__ void potrf_diag_body(const double* src, int64_t lds, 
 #pragma unroll
         for (int b = 0; b < 4; b++) {
             const int r = ti + 16 * a, c = tc + 16 * b;
+            const double v = s[a][b], w = m[a][b];
+            const double vp = __shfl_up_sync(0xffffffffu, v, 1);       // same row, column c-1
+            const double wp = __shfl_up_sync(0xffffffffu, w, 16);      // row r-1, same column
+            const int kc = c >> 1, kr = r >> 1;
+            const double lv = (c & 1) ? (v - fin[2][kc] * vp) * fin[1][kc] : v * fin[0][kc];
+            const double wv = (r & 1) ? (w - fin[2][kr] * wp) * fin[1][kr] : w * fin[0][kr];
             // on failure leave a harmless identity so later kernels stay finite; the host raises on `info`
-            if (c <= r) A[(int64_t)r * ld + c] = failed ? ((r == c) ? 1.0 : 0.0) : s[a][b] * rs[c];
-            if (Winv != nullptr)
-                Winv[(int64_t)r * ldw + c] = failed ? ((r == c) ? 1.0 : 0.0) : ((c <= r) ? m[a][b] * rs[r] : 0.0);
+            if (c <= r) A[(int64_t)r * ld + c] = failed ? ((r == c) ? 1.0 : 0.0) : lv;
+            if (Winv != nullptr) Winv[(int64_t)r * ldw + c] = failed ? ((r == c) ? 1.0 : 0.0) : ((c <= r) ? wv : 0.0);
         }
 }
 
@@ -192,7 +217,17 @@ struct DfArgs {
     int* pause;         // [number of SMs]
     int total;
     long long spin_limit;
+    long long* trace;   // diagnostics (MFGP_DF_TRACE=1): 8 timestamps per chain task, else nullptr
 };
+
+__device__ __forceinline__ void df_stamp(long long* trace, int task, int k) {
+    if (trace != nullptr && threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(t));
+        trace[task * 16 + k] = (long long)t;
+        trace[task * 16 + 8 + k] = clock64();
+    }
+}
 
 __device__ __forceinline__ int df_ld_acquire(const int* p) {
     int v;
@@ -358,6 +393,7 @@ __global__ void __launch_bounds__(DF_THREADS, 2) chol_dataflow_kernel(DfArgs g) 
         }
 
         // ---- epilogue ----
+        if (chain) df_stamp(g.trace, idx, 0);
         double* Xs = df_smem;                 // [64][68]  X = C - acc   (later: the diagonal tile S)
         double* Ws = df_smem + DF_TILE;       // [64][68]  W_cc
         double* Ls = df_smem + 2 * DF_TILE;   // [64][68]  L_{i,c} of a chain task
@@ -379,6 +415,7 @@ __global__ void __launch_bounds__(DF_THREADS, 2) chol_dataflow_kernel(DfArgs g) 
                 }
             const bool okd = df_wait(g.flagsL + (int64_t)c * g.nb + c, g.ctrl, g.info, g.spin_limit);
             if (chain && tid == 0) df_st_relaxed(my_pause, 1);
+            if (chain) df_stamp(g.trace, idx, 1);
 #pragma unroll
             for (int e = tid; e < PB * (PB / 2); e += DF_THREADS) {
                 const int r = e >> 5, q = e & 31;
@@ -390,6 +427,7 @@ __global__ void __launch_bounds__(DF_THREADS, 2) chol_dataflow_kernel(DfArgs g) 
                 if (chain && tid == 0) df_st_relaxed(my_pause, 0);
                 return;
             }
+            if (chain) df_stamp(g.trace, idx, 2);
 #pragma unroll 4
             for (int kk = 0; kk < PB; kk += 4) {
                 double a[2], b[4];
@@ -423,6 +461,7 @@ __global__ void __launch_bounds__(DF_THREADS, 2) chol_dataflow_kernel(DfArgs g) 
         if (chain) {
             double* Cd = g.K + (int64_t)idx * PB * (g.ld + 1);          // diagonal tile (idx, idx)
             double* Wd = g.W + (int64_t)idx * PB * (g.ldw + 1);
+            df_stamp(g.trace, idx, 3);
             if (idx > 0) {
                 __syncthreads();                      // L_{i,c} complete in shared memory; X is free
 #pragma unroll 4
@@ -454,8 +493,10 @@ __global__ void __launch_bounds__(DF_THREADS, 2) chol_dataflow_kernel(DfArgs g) 
             } else {
                 __syncthreads();
             }
+            df_stamp(g.trace, idx, 4);
             potrf_diag_body(Xs, DF_LDT, Cd, g.ld, Wd, g.ldw, g.info, idx);
             myflag = g.flagsL + (int64_t)idx * g.nb + idx;
+            df_stamp(g.trace, idx, 5);
         }
         __threadfence();
         __syncthreads();
@@ -463,6 +504,7 @@ __global__ void __launch_bounds__(DF_THREADS, 2) chol_dataflow_kernel(DfArgs g) 
             df_st_release(myflag, 1);
             if (chain) df_st_relaxed(my_pause, 0);
         }
+        if (chain) df_stamp(g.trace, idx, 6);
     }
 }
 
@@ -520,6 +562,8 @@ extern "C" int mfgp_build_train_cov(const double* Xt, int64_t NL, int64_t NH, co
 
 namespace {
 struct DfScratch {
+    long long* trace = nullptr;
+    int trace_nb = 0;
     int* buf = nullptr;
     int64_t ints = 0;
     int sms = 0;
@@ -561,6 +605,13 @@ int chol_dataflow(double* K, int64_t npad, int64_t ld, double* W, int64_t ldw, i
     a.K = K; a.ld = ld; a.W = W; a.ldw = ldw; a.Bm = Bm; a.ldb = ldb; a.nb = nb; a.nr = nr; a.info = info;
     a.ctrl = sc.buf; a.pause = sc.buf + 2; a.flagsL = sc.buf + 1026; a.flagsY = sc.buf + 1026 + (int64_t)nb * nb;
     a.total = nb + (nb - 1) * (nb - 2) / 2 + nb * nr;     // nb chain tasks, the tiles two or more below the diagonal, Y tiles
+    static const bool want_trace = [] { const char* e = getenv("MFGP_DF_TRACE"); return e && atoi(e) != 0; }();
+    if (want_trace) {
+        if (!sc.trace) MFGP_CUDA_CHECK(cudaMalloc(&sc.trace, 1024 * 16 * sizeof(long long)));
+        MFGP_CUDA_CHECK(cudaMemsetAsync(sc.trace, 0, 1024 * 16 * sizeof(long long), st));
+        a.trace = nb <= 1024 ? sc.trace : nullptr;
+        sc.trace_nb = nb;
+    }
     a.spin_limit = 4000000000LL;      // ~2 s of SM clocks: only a bug can get there
     constexpr int smem = DF_SMEM_DOUBLES * sizeof(double);
     MFGP_CUDA_CHECK(cudaFuncSetAttribute(chol_dataflow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -572,6 +623,18 @@ int chol_dataflow(double* K, int64_t npad, int64_t ld, double* W, int64_t ldw, i
     return MFGP_OK;
 }
 }  // namespace
+
+// Diagnostics: with MFGP_DF_TRACE=1 in the environment the tiled Cholesky records 7 (globaltimer ns, SM clock) stamps per
+// chain task; this copies them out ([task][16] int64).  Returns the number of chain tasks of the last call, or 0.
+extern "C" int64_t mfgp_debug_chol_trace(int64_t* out, int64_t max_tasks) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return 0;
+    DfScratch& sc = g_df[dev];
+    if (!sc.trace || !out) return 0;
+    int64_t n = sc.trace_nb < max_tasks ? sc.trace_nb : max_tasks;
+    if (cudaMemcpy(out, sc.trace, n * 16 * sizeof(long long), cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
+    return n;
+}
 
 extern "C" int mfgp_cholesky(double* K, int64_t npad, int64_t ld, double* W, int64_t ldw, int32_t* info, void* work,
                              void* stream) {

@@ -39,3 +39,16 @@ for R in (0, 64, 1792):
     W = e.W.view(ld, ld)[:npad, :npad].cpu().numpy()
     d = max(np.max(np.abs(W[j:j+64, j:j+64] @ Lref[j:j+64, j:j+64] - np.eye(64))) for j in range(0, npad, 64))
     print(msg + f" errWdiag={d:.2e}", flush=True)
+if os.environ.get("MFGP_DF_TRACE"):
+    nbk = npad // 64
+    buf = np.zeros((nbk, 16), dtype=np.int64)
+    n = lib.mfgp_debug_chol_trace(buf.ctypes.data_as(ctypes.c_void_p), nbk)
+    gt, ck = buf[:n, :7].astype(float), buf[:n, 8:15].astype(float)
+    names = ["k-loop end -> diag flag seen", "flag -> W loaded", "panel solve (X W^T) + stores", "diag update (L L^T) + S + publish",
+             "potrf_diag_body", "fence + flag"]
+    sel = slice(2, n)
+    print("chain-task phases, median over tasks 2.. (SM clocks | globaltimer ns):")
+    for k, nm in enumerate(names):
+        print(f"  {nm:38s} {np.median(ck[sel, k + 1] - ck[sel, k]):9.0f} clk | {np.median(gt[sel, k + 1] - gt[sel, k]):8.0f} ns")
+    print(f"  flag(d) set -> task d+1 sees it        {np.median(gt[3:n, 1] - gt[2:n - 1, 6]):8.0f} ns   (hop)")
+    print(f"  per block column (flag seen -> next flag seen) {np.median(gt[3:n, 1] - gt[2:n - 1, 1]):8.0f} ns")
