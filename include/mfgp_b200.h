@@ -53,7 +53,8 @@ int64_t mfgp_workspace_bytes(int64_t npad); /* scratch needed by mfgp_cholesky /
 
 /* ---- GP fit: replaces SFGP.updt_info gaussian_process.py:229-255 and MFGP.updt_info :493-529 ------------------- */
 
-/* K[npad,ld] = full symmetric training covariance + (noise + jitter) I; padding = identity.  Also writes the scaled
+/* K[npad,ld] = training covariance + (noise + jitter) I; padding = identity.  Only the 64x64 tiles on or below the
+ * diagonal are written (K is symmetric and mfgp_cholesky* read the lower triangle).  Also writes the scaled
  * training coordinates Tt[npad,4] = (x/l_L, y/l_L, x/l_H, y/l_H) used by mfgp_posterior (:77-78 divides before
  * differencing).  Replaces the K assembly at gaussian_process.py:253 / :523-528. */
 int mfgp_build_train_cov(const double* Xt, int64_t NL, int64_t NH, const mfgp_params* p_host,

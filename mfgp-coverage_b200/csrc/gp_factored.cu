@@ -37,29 +37,45 @@ struct FPart {                       // one kernel part (lofi / hifi) of the fac
     double* Hz;                      // [ry][kpad]  z^T Y
 };
 
-// ---- step 1a: Chebyshev coefficients c_k(n) of u -> exp(-0.5 ((u - U_n)/l)^2) on [lo, hi], one warp per (n, axis) ----------
-__global__ void __launch_bounds__(256) cheb_coef_kernel(const double* __restrict__ Xt, int N, int npad, int axis, double lo, double hi,
-                                                        double inv_l, int r, double* __restrict__ C) {
+// ---- step 1a: Chebyshev coefficients c_k(n) of u -> exp(-0.5 ((u - U_n)/l)^2) on [lo, hi] --------------------------------------
+// One launch for every (kernel part, axis) job (blockIdx.y); a CTA tabulates the job's r x r DCT matrix once in shared memory
+// and then serves 32 training points, one warp per point at a time.
+struct ChebJob { int axis, r; double lo, hi, inv_l; double* C; };
+struct ChebJobs { ChebJob j[4]; };
+constexpr int CHEB_PTS = 32;         // training points per CTA
+__global__ void __launch_bounds__(256) cheb_coef_kernel(const double* __restrict__ Xt, int N, int npad, ChebJobs jobs) {
+    __shared__ double D[F_MAXR * (F_MAXR + 1)];     // D[k][j] = w_k cos(pi k (j + 1/2) / r), odd pitch: conflict-free over k
+    __shared__ double node[F_MAXR];
     __shared__ double fv[8][F_MAXR];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int n = blockIdx.x * 8 + wib;
-    if (n >= npad) return;
-    if (n >= N) {                    // padding columns carry zeros
-        for (int k = lane; k < r; k += 32) C[(int64_t)k * npad + n] = 0.0;
-        return;
+    const ChebJob jb = jobs.j[blockIdx.y];
+    const int r = jb.r, lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    double* __restrict__ C = jb.C;
+    const double mid = 0.5 * (jb.lo + jb.hi), half = 0.5 * (jb.hi - jb.lo);
+    for (int e = threadIdx.x; e < r * r; e += 256) {
+        const int k = e / r, j = e % r;
+        D[k * (F_MAXR + 1) + j] = cospi(k * (j + 0.5) / r) * (k == 0 ? 1.0 : 2.0) / r;
     }
-    const double U = Xt[2 * n + axis];
-    const double mid = 0.5 * (lo + hi), half = 0.5 * (hi - lo);
-    for (int j = lane; j < r; j += 32) {
-        const double node = mid + half * cospi((j + 0.5) / r);
-        const double d = (node - U) * inv_l;
-        fv[wib][j] = exp(-0.5 * d * d);
-    }
-    __syncwarp();
-    for (int k = lane; k < r; k += 32) {
-        double s = 0.0;
-        for (int j = 0; j < r; j++) s += fv[wib][j] * cospi(k * (j + 0.5) / r);
-        C[(int64_t)k * npad + n] = s * (k == 0 ? 1.0 : 2.0) / r;
+    for (int j = threadIdx.x; j < r; j += 256) node[j] = mid + half * cospi((j + 0.5) / r);
+    __syncthreads();
+    for (int i = wib; i < CHEB_PTS; i += 8) {
+        const int n = blockIdx.x * CHEB_PTS + i;
+        if (n >= npad) break;
+        if (n >= N) {                    // padding columns carry zeros
+            for (int k = lane; k < r; k += 32) C[(int64_t)k * npad + n] = 0.0;
+            continue;
+        }
+        const double U = Xt[2 * n + jb.axis];
+        __syncwarp();
+        for (int j = lane; j < r; j += 32) {
+            const double d = (node[j] - U) * jb.inv_l;
+            fv[wib][j] = exp(-0.5 * d * d);
+        }
+        __syncwarp();
+        for (int k = lane; k < r; k += 32) {
+            double s0 = 0.0;
+            for (int j = 0; j < r; j++) s0 = fma(fv[wib][j], D[k * (F_MAXR + 1) + j], s0);
+            C[(int64_t)k * npad + n] = s0;
+        }
     }
 }
 
@@ -133,22 +149,36 @@ __global__ void unpack_z_kernel(const double* __restrict__ Yall, int64_t ldY, in
     if (n < npad) z[n] = Yall[(int64_t)n * ldY + off];
 }
 
-// Hz[e] = sum_n z[n] Y[n][e]: the mean needs z^T Y only contracted with T_k(tx) per column (h'(ix) = Ux(ix) . Hz)
-__global__ void __launch_bounds__(256) hz_kernel(const double* __restrict__ Y, const double* __restrict__ z, int npad, int cols,
-                                                 double* __restrict__ Hz, int accumulate) {
-    __shared__ double part[8][32];
+// Hz[e] = sum_n z[n] Y[n][e]: the mean needs z^T Y only contracted with T_k(tx) per column (h'(ix) = Ux(ix) . Hz).
+// Two passes (fixed summation order): HZ_SPLIT row ranges per 32 columns, then one thread per column adds the partials.
+constexpr int HZ_SPLIT = 16;
+__global__ void __launch_bounds__(256) hz_partial_kernel(const double* __restrict__ Y, const double* __restrict__ z, int npad, int cols,
+                                                         double* __restrict__ part) {
+    __shared__ double red[8][32];
     const int e = blockIdx.x * 32 + (threadIdx.x & 31), w = threadIdx.x >> 5;
+    const int rows = (npad + HZ_SPLIT - 1) / HZ_SPLIT;
+    const int n0 = blockIdx.y * rows, n1 = min(npad, n0 + rows);
     double s = 0.0;
-    if (e < cols)
-        for (int n = w; n < npad; n += 8) s = fma(z[n], Y[(int64_t)n * cols + e], s);
-    part[w][threadIdx.x & 31] = s;
+    if (e < cols) {
+#pragma unroll 4
+        for (int n = n0 + w; n < n1; n += 8) s = fma(z[n], Y[(int64_t)n * cols + e], s);
+    }
+    red[w][threadIdx.x & 31] = s;
     __syncthreads();
     if (w == 0 && e < cols) {
         double t = 0.0;
 #pragma unroll
-        for (int k = 0; k < 8; k++) t += part[k][threadIdx.x & 31];
-        Hz[e] = accumulate ? Hz[e] + t : t;
+        for (int k = 0; k < 8; k++) t += red[k][threadIdx.x & 31];
+        part[(int64_t)blockIdx.y * cols + e] = t;
     }
+}
+__global__ void hz_reduce_kernel(const double* __restrict__ part, int cols, double* __restrict__ Hz, int accumulate) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= cols) return;
+    double t = 0.0;
+#pragma unroll
+    for (int k = 0; k < HZ_SPLIT; k++) t += part[(int64_t)k * cols + e];
+    Hz[e] = accumulate ? Hz[e] + t : t;
 }
 
 __global__ void zero_rows_kernel(double* __restrict__ Y, int64_t cols, int nrows) {
@@ -195,13 +225,15 @@ __device__ __forceinline__ void f_bulk_g2s(uint32_t dst, const void* src, uint32
 }
 
 // G' is symmetric: only the lower 8x8 tiles are formed -- NT (NT + 1) / 2 of them for a padded width WM = 8 NT (15 for the
-// usual WM = 40, 36 for WM = 64), dealt round-robin to the four warps.
+// usual WM = 40, 36 for WM = 64).  The four warps split the TRAINING ROWS of a chunk (warp w takes k-steps w, w+4, ...) and each
+// accumulates ALL the tiles: A and B fragments of a tile pair are the same shared-memory words (A[m][k] = B[k][m] = Y'[k][m]),
+// so a k-step costs NT fragment loads for NT (NT + 1) / 2 DMMAs; the four partial Gram matrices are added in fixed order.
 // Staging: every thread issues ONE bulk copy per chunk (thread t: training row t % 64 of part t / 64; each row of Y'_P(ix)
 // is a contiguous run of ry doubles) straight into the padded shared tile, completion on an mbarrier -- no per-element
 // address arithmetic in the loop.
 template <int WM>
 __global__ void __launch_bounds__(128) gram_eval_kernel(GramArgs a) {
-    constexpr int NT = WM / 8, NTILES = NT * (NT + 1) / 2, MAXT = (NTILES + 3) / 4;
+    constexpr int NT = WM / 8, NTILES = NT * (NT + 1) / 2;
     constexpr int GP = WM + 2;
     extern __shared__ __align__(16) double gsm[];
     double* Ts = gsm;                               // [2][G_ROWS][G_LD]  double-buffered chunk of Y'(ix)
@@ -214,20 +246,6 @@ __global__ void __launch_bounds__(128) gram_eval_kernel(GramArgs a) {
     const double* srcL = a.YpL ? a.YpL + (int64_t)col * a.npad * a.ryL : nullptr;
     const double* srcH = a.YpH + (int64_t)col * a.npad * a.ryH;
     const uint32_t bar0 = f_smem_u32(bars);
-    // this warp's tiles: t = warp + 4 s  ->  (row tile ti, column tile tj <= ti), element offsets inside a shared row
-    int ta[MAXT], tb[MAXT];
-    bool tv[MAXT];
-#pragma unroll
-    for (int s = 0; s < MAXT; s++) {
-        const int t = warp + 4 * s;
-        tv[s] = t < NTILES;
-        int i = 0;
-        while ((i + 1) * (i + 2) / 2 <= t) i++;
-        const int j = t - i * (i + 1) / 2;
-        ta[s] = i * 8 + gq;
-        tb[s] = j * 8 + gq;
-    }
-
     for (int e = tid; e < 2 * G_ROWS * G_LD; e += 128) Ts[e] = 0.0;      // the pad columns stay zero
     if (tid == 0) {
         f_mbar_init(bar0, 1);
@@ -248,9 +266,9 @@ __global__ void __launch_bounds__(128) gram_eval_kernel(GramArgs a) {
             f_bulk_g2s(f_smem_u32(dst + a.ryL), srcH + (int64_t)(n0 + srow) * a.ryH, (uint32_t)(a.ryH * 8), bar0 + 8 * buf);
         }
     };
-    double acc[MAXT][2];
+    double acc[NTILES][2];
 #pragma unroll
-    for (int s = 0; s < MAXT; s++) acc[s][0] = acc[s][1] = 0.0;
+    for (int t = 0; t < NTILES; t++) acc[t][0] = acc[t][1] = 0.0;
     const int nchunk = a.npad / G_ROWS;
     stage(0, 0);
     for (int ch = 0; ch < nchunk; ch++) {
@@ -258,32 +276,42 @@ __global__ void __launch_bounds__(128) gram_eval_kernel(GramArgs a) {
         if (ch + 1 < nchunk) stage(buf ^ 1, (ch + 1) * G_ROWS);          // buf ^ 1 was released by the barrier below
         f_mbar_wait(bar0 + 8 * buf, (ch >> 1) & 1);
         const double* T = Ts + buf * G_ROWS * G_LD;
-#pragma unroll 4
-        for (int kk = 0; kk < G_ROWS; kk += 4) {
-            const double* row = T + (kk + tq) * G_LD;                   // A[m][k] = T[k][m]; B[k][n] = T[k][n]
-            double af[MAXT], bf[MAXT];
 #pragma unroll
-            for (int s = 0; s < MAXT; s++) { af[s] = row[ta[s]]; bf[s] = row[tb[s]]; }
+        for (int ks = 0; ks < G_ROWS / 16; ks++) {
+            const double* row = T + (4 * (warp + 4 * ks) + tq) * G_LD + gq;   // fragment word of tile index i: row[8 i]
+            double f[NT];
 #pragma unroll
-            for (int s = 0; s < MAXT; s++)
-                if (tv[s]) dmma884(acc[s][0], acc[s][1], af[s], bf[s]);
+            for (int i = 0; i < NT; i++) f[i] = row[8 * i];
+#pragma unroll
+            for (int i = 0; i < NT; i++)
+#pragma unroll
+                for (int j = 0; j <= i; j++) dmma884(acc[i * (i + 1) / 2 + j][0], acc[i * (i + 1) / 2 + j][1], f[i], f[j]);
         }
         __syncthreads();                                                  // everybody is done reading `buf`
     }
-    // G' (both triangles) to shared memory
+    // G' (both triangles) to shared memory: the warps add their partial sums one after the other
+#pragma unroll 1
+    for (int w = 0; w < 4; w++) {
+        if (warp == w) {
 #pragma unroll
-    for (int s = 0; s < MAXT; s++) {
-        if (!tv[s]) continue;
-        const int r = ta[s], c = tb[s] - gq + tq * 2;                   // C fragment: row gq, columns 2 tq, 2 tq + 1
-        Gs[r * GP + c] = acc[s][0];
-        Gs[r * GP + c + 1] = acc[s][1];
-        if (ta[s] - gq != tb[s] - gq) {                                  // mirror (diagonal tiles already hold both triangles)
-            Gs[c * GP + r] = acc[s][0];
-            Gs[(c + 1) * GP + r] = acc[s][1];
+            for (int i = 0; i < NT; i++)
+#pragma unroll
+                for (int j = 0; j <= i; j++) {
+                    const int t = i * (i + 1) / 2 + j;
+                    const int r = i * 8 + gq, c = j * 8 + tq * 2;           // C fragment: row gq, columns 2 tq, 2 tq + 1
+                    double v0 = acc[t][0], v1 = acc[t][1];
+                    if (w > 0) { v0 += Gs[r * GP + c]; v1 += Gs[r * GP + c + 1]; }
+                    Gs[r * GP + c] = v0;
+                    Gs[r * GP + c + 1] = v1;
+                    if (i != j) {                                          // mirror (diagonal tiles hold both triangles)
+                        Gs[c * GP + r] = v0;
+                        Gs[(c + 1) * GP + r] = v1;
+                    }
+                }
         }
+        __syncthreads();
     }
     if (a.Gstore) {          // keep / extend the column's Gram matrix for later row updates (incremental path)
-        __syncthreads();
         double* gst = a.Gstore + (int64_t)(a.col_begin + col) * F_LW * F_LW;
         for (int e = tid; e < WM * WM; e += 128) {
             const int r = e / WM, c = e % WM;
@@ -440,14 +468,18 @@ int f_tables_and_B(const FGeom& g, FLayout& L, double* Ball, int64_t ldB, cudaSt
     cheb_basis_kernel<<<(unsigned)((g.ny + 127) / 128), 128, 0, st>>>(g.uy, 0, (int)g.ny, (int)g.ny, g.ylo, g.yhi, f.ry, 64, 0, L.Uy);
     MFGP_LAUNCH_CHECK();
     BTab bt[2] = {};
+    ChebJobs jobs = {};
     for (int ti = 0; ti < L.ntabs; ti++) {
         FTab& t = L.tabs[ti];
-        cheb_coef_kernel<<<(unsigned)((npad + 7) / 8), 256, 0, st>>>(g.Xt, (int)N, (int)npad, 0, g.xlo, g.xhi, t.inv_l, t.rx, t.Cx);
-        MFGP_LAUNCH_CHECK();
-        cheb_coef_kernel<<<(unsigned)((npad + 7) / 8), 256, 0, st>>>(g.Xt, (int)N, (int)npad, 1, g.ylo, g.yhi, t.inv_l, t.ry, t.Cy);
-        MFGP_LAUNCH_CHECK();
+        jobs.j[2 * ti] = ChebJob{0, t.rx, g.xlo, g.xhi, t.inv_l, t.Cx};
+        jobs.j[2 * ti + 1] = ChebJob{1, t.ry, g.ylo, g.yhi, t.inv_l, t.Cy};
         // lofi part: rho s_L (lofi columns) / rho^2 s_L (hifi columns); hifi part: 0 / s_H  (gaussian_process.py:426-429)
         bt[ti] = BTab{t.Cx, t.Cy, t.rx, t.ry, t.lofi ? dp.rho * dp.s_L : 0.0, t.lofi ? dp.rho2 * dp.s_L : dp.s_H};
+    }
+    {
+        dim3 cgrid((unsigned)((npad + CHEB_PTS - 1) / CHEB_PTS), (unsigned)(2 * L.ntabs));
+        cheb_coef_kernel<<<cgrid, 256, 0, st>>>(g.Xt, (int)N, (int)npad, jobs);
+        MFGP_LAUNCH_CHECK();
     }
     const int cols = f.ry * f.kpad;
     dim3 bgrid((unsigned)((cols + 127) / 128), (unsigned)npad);
@@ -473,7 +505,10 @@ int f_tail(const FGeom& g, FLayout& L, const double* z, int64_t rows, double* Gs
         FPart& f = L.parts[pi];
         const int cols = f.ry * f.kpad;
         if (Hz_store) f.Hz = Hz_store + hoff;          // persistent across calls (incremental path)
-        hz_kernel<<<(cols + 31) / 32, 256, 0, st>>>(f.Y, z, (int)npad, cols, f.Hz, accumulate);
+        // partials go to the (not yet written) step-4 buffer: HZ_SPLIT x cols doubles << one column of Y'
+        hz_partial_kernel<<<dim3((unsigned)((cols + 31) / 32), HZ_SPLIT), 256, 0, st>>>(f.Y, z, (int)npad, cols, f.Yp);
+        MFGP_LAUNCH_CHECK();
+        hz_reduce_kernel<<<(cols + 127) / 128, 128, 0, st>>>(f.Yp, cols, f.Hz, accumulate);
         MFGP_LAUNCH_CHECK();
         hoff += cols;
     }

@@ -9,13 +9,15 @@ namespace mfgp {
 
 // ---- K assembly ------------------------------------------------------------------------------------------------------
 // K_LL = k_L + noise_L I, K_LH = rho k_L, K_HH = rho^2 k_L + k_H + noise_H I, then + jitter I (gaussian_process.py:
-// 523-529); SF: k + noise I + jitter I (:253-254).  Padding rows/cols [N, npad) carry the identity.
+// 523-529); SF: k + noise I + jitter I (:253-254).  Padding rows/cols [N, npad) carry the identity.  K is symmetric and
+// the factorisation reads its lower triangle only, so tiles strictly above the diagonal are left untouched.
 __global__ void build_train_cov_kernel(const double* __restrict__ Xt, int NL, int NH, DevParams p, double* __restrict__ K,
                                        int npad, int64_t ld, double* __restrict__ Tt, int row_begin) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     const int i = row_begin + blockIdx.y * blockDim.y + threadIdx.y;
     const int N = NL + NH;
     if (i >= npad || j >= npad) return;
+    if (j >= ((i >> 6) + 1) * 64) return;      // only the 64x64 tiles on or below the diagonal are ever read
     double v;
     if (i >= N || j >= N) {
         v = (i == j) ? 1.0 : 0.0;
@@ -266,7 +268,10 @@ __global__ void __launch_bounds__(DF_THREADS, 2) chol_dataflow_kernel(DfArgs g) 
     extern __shared__ __align__(16) double df_smem[];
     __shared__ int task[4];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int wm = (warp >> 1) * 16, wn = (warp & 1) * 32;       // 8 warps: 4 x 2, warp tile 16 x 32
+    // 8 warps as 4 x 2; a warp owns the 8x8 tiles (row tile (warp>>1) + 4x, column tile (warp&1) + 2y), x < 2, y < 4 --
+    // interleaved, so that the triangular products of the chain task (W_cc lower, S symmetric) skip about the same share
+    // of DMMAs in every warp
+    const int wm = (warp >> 1) * 8, wn = (warp & 1) * 8;
     const int gq = lane >> 2, tq = lane & 3;
     double* As0 = df_smem;
     double* Bs0 = df_smem + 2 * DF_STAGE;
@@ -372,21 +377,22 @@ __global__ void __launch_bounds__(DF_THREADS, 2) chol_dataflow_kernel(DfArgs g) 
             for (int kk = 0; kk < DF_K; kk += 4) {
                 double a[2], b[4];
 #pragma unroll
-                for (int x = 0; x < 2; x++) a[x] = As[(wm + x * 8 + gq) * DF_LDA + kk + tq];
+                for (int x = 0; x < 2; x++) a[x] = As[(wm + x * 32 + gq) * DF_LDA + kk + tq];
 #pragma unroll
                 for (int y = 0; y < 4; y++)
-                    b[y] = rhs ? Bs[(kk + tq) * DF_LDT + wn + y * 8 + gq] : Bs[(wn + y * 8 + gq) * DF_LDA + kk + tq];
+                    b[y] = rhs ? Bs[(kk + tq) * DF_LDT + wn + y * 16 + gq] : Bs[(wn + y * 16 + gq) * DF_LDA + kk + tq];
 #pragma unroll
                 for (int x = 0; x < 2; x++)
 #pragma unroll
                     for (int y = 0; y < 4; y++) dmma884(acc[x][y][0], acc[x][y][1], a[x], b[y]);
-                if (chain) {                          // diagonal tile (i, i): L_ik L_ik^T out of the same A slab
+                if (chain) {                          // diagonal tile (i, i): L_ik L_ik^T out of the same A slab, lower tiles only
 #pragma unroll
-                    for (int y = 0; y < 4; y++) b[y] = As[(wn + y * 8 + gq) * DF_LDA + kk + tq];
+                    for (int y = 0; y < 4; y++) b[y] = As[(wn + y * 16 + gq) * DF_LDA + kk + tq];
 #pragma unroll
                     for (int x = 0; x < 2; x++)
 #pragma unroll
-                        for (int y = 0; y < 4; y++) dmma884(acc2[x][y][0], acc2[x][y][1], a[x], b[y]);
+                        for (int y = 0; y < 4; y++)
+                            if (wn + y * 16 < wm + x * 32 + 8) dmma884(acc2[x][y][0], acc2[x][y][1], a[x], b[y]);
                 }
             }
             __syncthreads();
@@ -407,7 +413,7 @@ __global__ void __launch_bounds__(DF_THREADS, 2) chol_dataflow_kernel(DfArgs g) 
             for (int x = 0; x < 2; x++)
 #pragma unroll
                 for (int y = 0; y < 4; y++) {
-                    const int r = wm + x * 8 + gq, cc = wn + y * 8 + tq * 2;
+                    const int r = wm + x * 32 + gq, cc = wn + y * 16 + tq * 2;
                     const double2 v = *reinterpret_cast<const double2*>(Ct + (int64_t)r * ldc + cc);
                     Xs[r * DF_LDT + cc] = v.x - acc[x][y][0];
                     Xs[r * DF_LDT + cc + 1] = v.y - acc[x][y][1];
@@ -431,16 +437,22 @@ __global__ void __launch_bounds__(DF_THREADS, 2) chol_dataflow_kernel(DfArgs g) 
 #pragma unroll 4
             for (int kk = 0; kk < PB; kk += 4) {
                 double a[2], b[4];
-                if (!rhs) {       // L_ic = X W_cc^T :  A = X [m][k],  B = W_cc [n][k]
+                if (!rhs) {       // L_ic = X W_cc^T :  A = X [m][k],  B = W_cc [n][k] (lower triangular: k < n0 + 8)
 #pragma unroll
-                    for (int x = 0; x < 2; x++) a[x] = Xs[(wm + x * 8 + gq) * DF_LDT + kk + tq];
+                    for (int x = 0; x < 2; x++) a[x] = Xs[(wm + x * 32 + gq) * DF_LDT + kk + tq];
 #pragma unroll
-                    for (int y = 0; y < 4; y++) b[y] = Ws[(wn + y * 8 + gq) * DF_LDT + kk + tq];
+                    for (int y = 0; y < 4; y++) b[y] = (kk < wn + y * 16 + 8) ? Ws[(wn + y * 16 + gq) * DF_LDT + kk + tq] : 0.0;
+#pragma unroll
+                    for (int x = 0; x < 2; x++)
+#pragma unroll
+                        for (int y = 0; y < 4; y++)
+                            if (kk < wn + y * 16 + 8) dmma884(acc[x][y][0], acc[x][y][1], a[x], b[y]);
+                    continue;
                 } else {          // Y_cr = W_cc X :    A = W_cc [m][k],  B = X [k][n]
 #pragma unroll
-                    for (int x = 0; x < 2; x++) a[x] = Ws[(wm + x * 8 + gq) * DF_LDT + kk + tq];
+                    for (int x = 0; x < 2; x++) a[x] = Ws[(wm + x * 32 + gq) * DF_LDT + kk + tq];
 #pragma unroll
-                    for (int y = 0; y < 4; y++) b[y] = Xs[(kk + tq) * DF_LDT + wn + y * 8 + gq];
+                    for (int y = 0; y < 4; y++) b[y] = Xs[(kk + tq) * DF_LDT + wn + y * 16 + gq];
                 }
 #pragma unroll
                 for (int x = 0; x < 2; x++)
@@ -451,7 +463,7 @@ __global__ void __launch_bounds__(DF_THREADS, 2) chol_dataflow_kernel(DfArgs g) 
             for (int x = 0; x < 2; x++)
 #pragma unroll
                 for (int y = 0; y < 4; y++) {
-                    const int r = wm + x * 8 + gq, cc = wn + y * 8 + tq * 2;
+                    const int r = wm + x * 32 + gq, cc = wn + y * 16 + tq * 2;
                     double2 v;
                     v.x = acc[x][y][0]; v.y = acc[x][y][1];
                     *reinterpret_cast<double2*>(Ct + (int64_t)r * ldc + cc) = v;
@@ -468,20 +480,21 @@ __global__ void __launch_bounds__(DF_THREADS, 2) chol_dataflow_kernel(DfArgs g) 
                 for (int kk = 0; kk < PB; kk += 4) {  // acc2 += L_ic L_ic^T
                     double a[2], b[4];
 #pragma unroll
-                    for (int x = 0; x < 2; x++) a[x] = Ls[(wm + x * 8 + gq) * DF_LDT + kk + tq];
+                    for (int x = 0; x < 2; x++) a[x] = Ls[(wm + x * 32 + gq) * DF_LDT + kk + tq];
 #pragma unroll
-                    for (int y = 0; y < 4; y++) b[y] = Ls[(wn + y * 8 + gq) * DF_LDT + kk + tq];
+                    for (int y = 0; y < 4; y++) b[y] = Ls[(wn + y * 16 + gq) * DF_LDT + kk + tq];
 #pragma unroll
                     for (int x = 0; x < 2; x++)
 #pragma unroll
-                        for (int y = 0; y < 4; y++) dmma884(acc2[x][y][0], acc2[x][y][1], a[x], b[y]);
+                        for (int y = 0; y < 4; y++)
+                            if (wn + y * 16 < wm + x * 32 + 8) dmma884(acc2[x][y][0], acc2[x][y][1], a[x], b[y]);
                 }
             }
 #pragma unroll
             for (int x = 0; x < 2; x++)
 #pragma unroll
                 for (int y = 0; y < 4; y++) {
-                    const int r = wm + x * 8 + gq, cc = wn + y * 8 + tq * 2;
+                    const int r = wm + x * 32 + gq, cc = wn + y * 16 + tq * 2;
                     const double2 v = *reinterpret_cast<const double2*>(Cd + (int64_t)r * g.ld + cc);
                     Xs[r * DF_LDT + cc] = v.x - acc2[x][y][0];
                     Xs[r * DF_LDT + cc + 1] = v.y - acc2[x][y][1];

@@ -18,7 +18,8 @@ def build():
 build(); torch.cuda.synchronize()
 Kh = e.K.view(ld, ld)[:npad, :npad].cpu().numpy().copy()
 Lref = np.linalg.cholesky(Kh)
-for R in (0, 64, 1792):
+RS = tuple(int(x) for x in sys.argv[2].split(",")) if len(sys.argv) > 2 else (0, 64, 1792)
+for R in RS:
     B0 = torch.randn(npad, max(R, 64), dtype=torch.float64, device="cuda")
     ts = []
     for rep in range(4):
