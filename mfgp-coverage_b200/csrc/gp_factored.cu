@@ -201,7 +201,9 @@ struct GramArgs {
     int ny; int col_begin;                                     // first grid column (relative) of this launch
     double mean, k0;
     double* mu; double* var; double* qred;                     // flat outputs, index = col * ny + iy
+    int pitch, nstage;                                         // shared-memory row pitch of a staged chunk (doubles), pipeline depth
 };
+constexpr int G_MAXSTAGE = 6;
 
 // mbarrier / bulk-copy primitives (same PTX as gp_posterior.cu)
 __device__ __forceinline__ uint32_t f_smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -228,57 +230,59 @@ __device__ __forceinline__ void f_bulk_g2s(uint32_t dst, const void* src, uint32
 // usual WM = 40, 36 for WM = 64).  The four warps split the TRAINING ROWS of a chunk (warp w takes k-steps w, w+4, ...) and each
 // accumulates ALL the tiles: A and B fragments of a tile pair are the same shared-memory words (A[m][k] = B[k][m] = Y'[k][m]),
 // so a k-step costs NT fragment loads for NT (NT + 1) / 2 DMMAs; the four partial Gram matrices are added in fixed order.
-// Staging: every thread issues ONE bulk copy per chunk (thread t: training row t % 64 of part t / 64; each row of Y'_P(ix)
-// is a contiguous run of ry doubles) straight into the padded shared tile, completion on an mbarrier -- no per-element
-// address arithmetic in the loop.
+// Staging: chunks of 64 training rows of Y'(ix) ride an nstage-deep ring of bulk copies (completion on mbarriers).  The
+// shared row pitch is ry when ry = 4 (mod 8) -- fragment reads are then bank-conflict-free as they stand and the whole chunk is
+// ONE contiguous 64 ry x 8-byte copy -- else ry + 4 with one copy per row.  Columns [ry, WM) of a staged row alias the next row
+// (finite data, or the zero fill); they only ever meet the zero-padded entries of Uy.
 template <int WM>
 __global__ void __launch_bounds__(128) gram_eval_kernel(GramArgs a) {
     constexpr int NT = WM / 8, NTILES = NT * (NT + 1) / 2;
     constexpr int GP = WM + 2;
     extern __shared__ __align__(16) double gsm[];
-    double* Ts = gsm;                               // [2][G_ROWS][G_LD]  double-buffered chunk of Y'(ix)
-    double* Gs = gsm + 2 * G_ROWS * G_LD;           // [WM][WM + 2]   (row pitch even: 16-byte loads)
+    const int P = a.pitch, NST = a.nstage, ry = a.ryH;
+    const int ring = NST * G_ROWS * P + 8;          // + 8: the last row's aliased columns stay inside the (zeroed) buffer
+    double* Ts = gsm;                               // [NST][G_ROWS][P]  ring of chunks of Y'(ix)
+    double* Gs = gsm + ring;                        // [WM][WM + 2]   (row pitch even: 16-byte loads)
     double* hs = Gs + WM * GP;                      // [F_LW]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(hs + 2 * F_LW);    // [2] "chunk landed"
+    uint64_t* bars = reinterpret_cast<uint64_t*>(hs + 2 * F_LW);    // [NST] "chunk landed"
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int col = blockIdx.x;
     const int gq = lane >> 2, tq = lane & 3;
-    const double* srcL = a.YpL ? a.YpL + (int64_t)col * a.npad * a.ryL : nullptr;
-    const double* srcH = a.YpH + (int64_t)col * a.npad * a.ryH;
+    const double* src = a.YpH + (int64_t)col * a.npad * ry;
     const uint32_t bar0 = f_smem_u32(bars);
-    for (int e = tid; e < 2 * G_ROWS * G_LD; e += 128) Ts[e] = 0.0;      // the pad columns stay zero
+    for (int e = tid; e < ring; e += 128) Ts[e] = 0.0;
     if (tid == 0) {
-        f_mbar_init(bar0, 1);
-        f_mbar_init(bar0 + 8, 1);
+        for (int i = 0; i < NST; i++) f_mbar_init(bar0 + 8 * i, 1);
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     __syncthreads();
     asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");        // generic-proxy zero fill before the async-proxy copies
-    const int srow = tid & 63, spart = tid >> 6;                          // this thread's staging job
-    const uint32_t chunk_bytes = (uint32_t)(G_ROWS * (a.ryL + a.ryH) * 8);
+    const uint32_t chunk_bytes = (uint32_t)(G_ROWS * ry * 8);
+    const bool whole = P == ry;
     auto stage = [&](int buf, int n0) {
         if (tid == 0) f_mbar_arrive_expect_tx(bar0 + 8 * buf, chunk_bytes);
-        __syncwarp();
-        double* dst = Ts + buf * G_ROWS * G_LD + srow * G_LD;
-        if (spart == 0) {
-            if (a.ryL) f_bulk_g2s(f_smem_u32(dst), srcL + (int64_t)(n0 + srow) * a.ryL, (uint32_t)(a.ryL * 8), bar0 + 8 * buf);
+        double* dst = Ts + buf * G_ROWS * P;
+        if (whole) {
+            if (tid == 0) f_bulk_g2s(f_smem_u32(dst), src + (int64_t)n0 * ry, chunk_bytes, bar0 + 8 * buf);
         } else {
-            f_bulk_g2s(f_smem_u32(dst + a.ryL), srcH + (int64_t)(n0 + srow) * a.ryH, (uint32_t)(a.ryH * 8), bar0 + 8 * buf);
+            __syncwarp();
+            if (tid < G_ROWS) f_bulk_g2s(f_smem_u32(dst + tid * P), src + (int64_t)(n0 + tid) * ry, (uint32_t)(ry * 8), bar0 + 8 * buf);
         }
     };
     double acc[NTILES][2];
 #pragma unroll
     for (int t = 0; t < NTILES; t++) acc[t][0] = acc[t][1] = 0.0;
     const int nchunk = a.npad / G_ROWS;
-    stage(0, 0);
+    for (int i = 0; i < NST - 1 && i < nchunk; i++) stage(i, i * G_ROWS);
+    int buf = 0, par = 0;
     for (int ch = 0; ch < nchunk; ch++) {
-        const int buf = ch & 1;
-        if (ch + 1 < nchunk) stage(buf ^ 1, (ch + 1) * G_ROWS);          // buf ^ 1 was released by the barrier below
-        f_mbar_wait(bar0 + 8 * buf, (ch >> 1) & 1);
-        const double* T = Ts + buf * G_ROWS * G_LD;
+        const int nx = ch + NST - 1;                                      // its buffer was released by the barrier of chunk ch - 1
+        if (nx < nchunk) stage(nx % NST, nx * G_ROWS);
+        f_mbar_wait(bar0 + 8 * buf, par);
+        const double* T = Ts + buf * G_ROWS * P;
 #pragma unroll
         for (int ks = 0; ks < G_ROWS / 16; ks++) {
-            const double* row = T + (4 * (warp + 4 * ks) + tq) * G_LD + gq;   // fragment word of tile index i: row[8 i]
+            const double* row = T + (4 * (warp + 4 * ks) + tq) * P + gq;      // fragment word of tile index i: row[8 i]
             double f[NT];
 #pragma unroll
             for (int i = 0; i < NT; i++) f[i] = row[8 * i];
@@ -288,6 +292,7 @@ __global__ void __launch_bounds__(128) gram_eval_kernel(GramArgs a) {
                 for (int j = 0; j <= i; j++) dmma884(acc[i * (i + 1) / 2 + j][0], acc[i * (i + 1) / 2 + j][1], f[i], f[j]);
         }
         __syncthreads();                                                  // everybody is done reading `buf`
+        if (++buf == NST) { buf = 0; par ^= 1; }
     }
     // G' (both triangles) to shared memory: the warps add their partial sums one after the other
 #pragma unroll 1
@@ -495,9 +500,13 @@ int f_tail(const FGeom& g, FLayout& L, const double* z, int64_t rows, double* Gs
            double* mu, double* var, double* qred, cudaStream_t st) {
     const DevParams dp = make_dev_params(*g.p);
     const int64_t npad = rows;
-    const bool narrow = L.parts[0].ry <= 40;          // padded width of the y expansion: 40 (15 Gram tiles) or 64 (36)
+    const int ry0 = L.parts[0].ry;
+    const bool narrow = ry0 <= 40;          // padded width of the y expansion: 40 (15 Gram tiles) or 64 (36)
     const int wm = narrow ? 40 : 64;
-    const size_t gsmem = sizeof(double) * (2 * G_ROWS * G_LD + wm * (wm + 2) + 2 * F_LW) + 64;
+    const int pitch = (ry0 % 8 == 4) ? ry0 : ry0 + 4;
+    int nstage = (int)(73728 / (G_ROWS * pitch * 8));
+    nstage = nstage < 2 ? 2 : (nstage > G_MAXSTAGE ? G_MAXSTAGE : nstage);
+    const size_t gsmem = sizeof(double) * ((size_t)nstage * G_ROWS * pitch + 8 + wm * (wm + 2) + 2 * F_LW) + 8 * G_MAXSTAGE + 64;
     MFGP_CUDA_CHECK(cudaFuncSetAttribute(gram_eval_kernel<40>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));
     MFGP_CUDA_CHECK(cudaFuncSetAttribute(gram_eval_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));
     int64_t hoff = 0;
@@ -532,6 +541,7 @@ int f_tail(const FGeom& g, FLayout& L, const double* z, int64_t rows, double* Gs
         ga.UxL = nullptr; ga.UxH = L.parts[0].Ux + c0 * L.parts[0].kpad;
         ga.kL = 0; ga.kH = L.parts[0].kpad;
         ga.mean = dp.mean_H; ga.k0 = dp.k0; ga.mu = mu; ga.var = var; ga.qred = qred;
+        ga.pitch = pitch; ga.nstage = nstage;
         if (narrow) gram_eval_kernel<40><<<(unsigned)cc, 128, gsmem, st>>>(ga);
         else gram_eval_kernel<64><<<(unsigned)cc, 128, gsmem, st>>>(ga);
         MFGP_LAUNCH_CHECK();

@@ -325,12 +325,19 @@ __global__ void __launch_bounds__(DF_THREADS, 2) chol_dataflow_kernel(DfArgs g) 
             for (int b = 0; b < 4; b++) acc[a][b][0] = acc[a][b][1] = acc2[a][b][0] = acc2[a][b][1] = 0.0;
 
         bool ok = true;
+        int pre = 0;                                  // lane 0: both flags of the NEXT k tile, sampled one slab early
         auto stage = [&](int buf, int s) {
             const int k0 = s * DF_K;
+            const int kt = s >> 1;
             if ((s & 1) == 0) {                       // first slab of a 64-wide k tile: its producers must be done
-                const int kt = s >> 1;
-                ok = df_wait(fa + kt, g.ctrl, g.info, g.spin_limit) && ok;
-                ok = df_wait(fb + (int64_t)kt * fbs, g.ctrl, g.info, g.spin_limit) && ok;
+                int ready = (lane == 0) ? pre : 0;    // (the early sample hides the L2 round trip of the common, ready case)
+                ready = __shfl_sync(0xffffffffu, ready, 0);
+                if (!ready) {
+                    ok = df_wait(fa + kt, g.ctrl, g.info, g.spin_limit) && ok;
+                    ok = df_wait(fb + (int64_t)kt * fbs, g.ctrl, g.info, g.spin_limit) && ok;
+                }
+            } else if (lane == 0) {
+                pre = (kt + 1 < nk) ? (df_ld_acquire(fa + kt + 1) & df_ld_acquire(fb + (int64_t)(kt + 1) * fbs)) : 0;
             }
             double* As = As0 + buf * DF_STAGE;
             double* Bs = Bs0 + buf * DF_STAGE;
