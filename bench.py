@@ -39,9 +39,10 @@ WORKLOADS = {
 # profiles/r01_posterior_v3_ncu_summary.txt (18.883 GB read + 0.040 GB written); algorithmic minimum 32 G + 8 N^2 = 0.17 GB:
 # W (67 MB used) is re-read from L2 by every CTA and only partly stays resident next to the factor tables.
 POSTERIOR_TRAFFIC_C4_1GPU = 18.883344e9 + 39.72864e6
-# DRAM bytes (read + write) of ONE factored posterior call on the c4 grid, summed over its 14 kernels
-# (profiles/r01_factored_posterior_launches.csv); ~4 GB of it is the Y' intermediate written once and read once.
-FACTORED_TRAFFIC_C4_1GPU = 5.216e9
+# DRAM bytes (read + write) of ONE chol_dataflow_kernel launch at c4 (N = 4096, 1792 right-hand-side columns), from the
+# ncu --set full capture in profiles/r01_chol_dataflow_ncu_summary.txt (214.9 MB read + 109.0 MB written); algorithmic:
+# lower triangle of K in and L out (2 x 67 MB) + B in and Y out (2 x 58.7 MB) = 252 MB.
+CHOL_TRAFFIC_C4_1GPU = 214.939136e6 + 108.998912e6
 DGEMM_PEAK_TFLOPS = 35.41   # cuBLAS DGEMM 8192^3 measured on this pool's B200 (profiles/r01_dgemm_peak.json);
 #                             MEASURED_PEAKS.json carries no FP64 figure.  DMMA issue peak: 37.15 (r01_fp64_pipes.log)
 
@@ -201,7 +202,8 @@ def run_ours(args):
     var = torch.empty(npts, dtype=torch.float64, device=dev)
     flush = torch.empty(64 << 20, dtype=torch.float32, device=dev)     # 256 MB > 126 MB L2
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
-    post_ms, fit_ms, cov_ms = [], [], []
+    post_ms, fit_ms, cov_ms, chol_ms = [], [], [], []
+    eng.profile_events = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
 
     def device_step(timed):
         flush.zero_()
@@ -226,6 +228,11 @@ def run_ours(args):
             post_ms.append(ev[0].elapsed_time(ev[1]))                 # .cpu() above synchronised the stream
             fit_ms.append(ev[3].elapsed_time(ev[0]))
             cov_ms.append(ev[1].elapsed_time(ev[2]))                  # includes the host Qhull calls before the launch
+            if eng.profile_events[1].query():                         # recorded by the fused fit (mfgp_cholesky_solve)
+                try:
+                    chol_ms.append(eng.profile_events[0].elapsed_time(eng.profile_events[1]))
+                except Exception:                                     # never recorded (non-fused path)
+                    pass
         return loss, cent, idx
 
     def barrier():
@@ -362,22 +369,37 @@ def run_ours(args):
             fused = eng.defer_fit                       # the Cholesky runs inside the same call (mfgp_cholesky_solve)
             flops = 2.0 * macs + (N ** 3 / 3.0 if fused else 0.0)
             pm_roof = pm + (float(np.mean(fit_ms)) if fused else 0.0)
-            achieved = flops / (pm_roof * 1e-3) * 1e-12
-            roof = {"bound": "tensor",
-                    "kernel": ("fused fit + factored posterior (potrf_diag / gemm_f64 panel chain with the right-hand sides on a "
-                               "side stream, gemm_f64 Ux*Y^T, gram_eval; FP64 DMMA)") if fused else
-                              "factored posterior (gemm_f64_kernel W*B and Ux*Y^T, gram_eval_kernel; FP64 DMMA)",
-                    "achieved": achieved, "peak": DGEMM_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": achieved / DGEMM_PEAK_TFLOPS,
-                    "traffic": FACTORED_TRAFFIC_C4_1GPU if (w["name"] == "c4" and world == 1) else None,
-                    "traffic_unit": "bytes per posterior call (ncu dram__bytes_read.sum + dram__bytes_write.sum over its kernels)",
-                    "algorithmic_flops": flops, "algorithmic_flops_note": "N^3/3 (Cholesky) + 2 (N^2 R / 2 + n_col N R + n_col N w^2 "
-                                                                            "+ G w^2), R = max rx * max ry, w = max ry",
-                    "chebyshev_orders": [plan["rxL"], plan["ryL"], plan["rxH"], plan["ryH"]],
-                    "kernel_ms": pm_roof, "kernel_share_of_step": pm_roof / ms_dev,
-                    "dense_equivalent_tflops": (float(npts) * N * N + 4.0 * npts * N) / (pm * 1e-3) * 1e-12,
-                    "peak_source": "cuBLAS DGEMM 8192^3 measured on this pool (profiles/r01_dgemm_peak.json); "
-                                   "MEASURED_PEAKS.json has no FP64 figure; DMMA issue peak 37.15",
-                    "dense_kernel": dense}
+            call = {"what": "whole posterior call: covariance + Chebyshev tables + tiled Cholesky/substitution + Ux*Y^T + gram_eval",
+                    "ms": pm_roof, "share_of_step": pm_roof / ms_dev, "algorithmic_flops": flops,
+                    "achieved": flops / (pm_roof * 1e-3) * 1e-12, "unit": "TFLOP/s",
+                    "frac": flops / (pm_roof * 1e-3) * 1e-12 / DGEMM_PEAK_TFLOPS,
+                    "algorithmic_flops_note": "N^3/3 (Cholesky) + 2 (N^2 R / 2 + n_col N R + n_col N w^2 + G w^2), "
+                                              "R = max rx * max ry, w = max ry",
+                    "dense_equivalent_tflops": (float(npts) * N * N + 4.0 * npts * N) / (pm * 1e-3) * 1e-12}
+            if fused and chol_ms:
+                # the dominant kernel of the step: ONE launch factors K and forward-substitutes [B | y - m] (R + 1 columns)
+                km = float(np.mean(chol_ms))
+                kfl = N ** 3 / 3.0 + float(N) * N * (R + 1)
+                roof = {"bound": "tensor",
+                        "kernel": "chol_dataflow_kernel (tiled Cholesky of K fused with the forward substitution of the R + 1 "
+                                  "right-hand sides of the factored posterior; persistent tile-dataflow kernel, FP64 DMMA)",
+                        "achieved": kfl / (km * 1e-3) * 1e-12, "peak": DGEMM_PEAK_TFLOPS, "unit": "TFLOP/s",
+                        "frac": kfl / (km * 1e-3) * 1e-12 / DGEMM_PEAK_TFLOPS,
+                        "traffic": CHOL_TRAFFIC_C4_1GPU if (w["name"] == "c4" and N == 4096) else None,
+                        "traffic_unit": "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)",
+                        "algorithmic_flops": kfl, "algorithmic_flops_note": "N^3/3 + N^2 (R + 1), R = max rx * max ry",
+                        "algorithmic_bytes": 8.0 * (N * (N + 64.0) + 2.0 * N * (R + 64)),
+                        "kernel_ms": km, "kernel_share_of_step": km / ms_dev}
+            else:
+                roof = {"bound": "tensor",
+                        "kernel": "factored posterior (gemm_f64_kernel W*B and Ux*Y^T, gram_eval_kernel; FP64 DMMA)",
+                        "achieved": call["achieved"], "peak": DGEMM_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": call["frac"],
+                        "traffic": None, "algorithmic_flops": flops, "kernel_ms": pm_roof,
+                        "kernel_share_of_step": pm_roof / ms_dev}
+            roof.update({"chebyshev_orders": [plan["rxL"], plan["ryL"], plan["rxH"], plan["ryH"]], "posterior_call": call,
+                         "peak_source": "cuBLAS DGEMM 8192^3 measured on this pool (profiles/r01_dgemm_peak.json); "
+                                        "MEASURED_PEAKS.json has no FP64 figure; DMMA issue peak 37.15",
+                         "dense_kernel": dense})
         else:
             flops = float(npts) * N * N + 4.0 * npts * N        # algorithmic: triangular solve + mean + column norm
             achieved = flops / (pm * 1e-3) * 1e-12

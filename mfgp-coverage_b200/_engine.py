@@ -99,6 +99,7 @@ class DeviceGP:
         self._fHz = None              #   factored update (mfgp_posterior_grid_factored_update)
         self._fstate = None           # (plan key, epoch, rows covered, output buffer key) the stores are valid for
         self.incremental = False
+        self.profile_events = None    # optional (start, stop) torch.cuda.Event pair recorded around mfgp_cholesky_solve
         self.lazy_check = False       # True: the caller reads `info` itself (cov_finish carries it home): no sync per fit
         self.epoch = 0                # bumped by every FULL refactor: standing posteriors become stale
         self._post = None             # (buffer key, epoch, N covered)
@@ -449,8 +450,13 @@ class DeviceGP:
                                             nat.ptr(self.Xt), nat.ptr(self.y), self.NL, self.NH, npad, pp, *o, *geom,
                                             nat.ptr(self._fB), R, nat.ptr(work), work.numel() * 8, st),
                   "mfgp_factored_prepare")
+        ev = self.profile_events          # bench.py: (start, stop) CUDA events around the dominant kernel
+        if ev is not None:
+            ev[0].record()
         nat.check(lib.mfgp_cholesky_solve(nat.ptr(self.K), npad, ld, nat.ptr(self.W), ld, nat.ptr(self.info),
                                           nat.ptr(self._fB), R, R, st), "mfgp_cholesky_solve")
+        if ev is not None:
+            ev[1].record()
         Gs, Hs = self._factored_stores(plan)
         nat.check(lib.mfgp_posterior_grid_factored_solved(
             nat.ptr(axes.ux), axes.nx, nat.ptr(axes.uy), axes.ny, plan["ix0"], plan["ncols"], nat.ptr(self.Xt), self.NL,

@@ -54,6 +54,16 @@ def prior_variance(params):
     return params["s_H"]
 
 
+
+def _to_host_pinned(t):
+    """Device tensor -> host tensor in page-locked memory (asynchronous DMA at PCIe speed instead of a staged pageable
+    copy).  The block comes from torch's caching host allocator and goes back to it when the numpy array that wraps it is
+    garbage collected, so a loop that calls predict() every iteration reuses the same pages; and because the memory is
+    page-locked, handing the array back to compute_centroids / compute_max_var uploads it by DMA as well."""
+    h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+    h.copy_(t, non_blocking=True)
+    return h
+
 class _GPBase:
     raw_means = False     # set True to reproduce runs logged with the pre-exp() mean convention
     use_separable = True  # tensor-product grids: per-axis factor tables instead of one exp per (point, sample) pair
@@ -116,7 +126,9 @@ class _GPBase:
         if not self._dev.fitted:
             self._refit(check=True)
         mu, var = self._dev.posterior(xs_dev, axes=axes)
-        return mu.cpu().numpy().reshape(-1, 1), var.cpu().numpy()
+        mu_h, var_h = _to_host_pinned(mu), _to_host_pinned(var)
+        torch.cuda.current_stream(mu.device).synchronize()
+        return mu_h.numpy().reshape(-1, 1), var_h.numpy()
 
     def factor(self):
         """Lower Cholesky factor L[N,N] as a host array (the reference keeps it in `self.L`)."""
