@@ -137,7 +137,7 @@ int mfgp_posterior_grid_factored(const double* ux, int64_t nx, const double* uy,
                                  double xlo, double xhi, double ylo, double yhi, int64_t chunk_cols,
                                  double* mu, double* var, double* qred, double* Gstore, double* Hz_store, void* work,
                                  int64_t work_bytes, void* stream);
-/* Gstore[ncols, 64, 64] / Hz_store[mfgp_factored_rhs_cols - 64] (both optional in the full forms) keep the per-column Gram
+/* Gstore[ncols, 64, 64] / Hz_store[mfgp_factored_rhs_cols] (both optional in the full forms) keep the per-column Gram
  * matrices G'(ix) and z^T Y, so that after mfgp_cholesky_append only the NEW rows [row_lo, NL+NH) of Y = W B have to be
  * formed: G'(ix) += Y'_new^T Y'_new, then every grid point is re-evaluated (a 64 x 64 quadratic form per point).  Same
  * results as the full form to rounding; ~7e8 MAC + the evaluation pass instead of 4e10 MAC at c4 with 64 new samples. */

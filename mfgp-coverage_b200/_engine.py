@@ -397,7 +397,7 @@ class DeviceGP:
         if orders is not None:
             rxL, ryL, rxH, ryH = orders
             ncols = G // ny
-            ry, kp = max(ryL, ryH), -(-max(rxL, rxH) // 16) * 16       # both kernel parts share one Chebyshev basis
+            ry, kp = max(ryL, ryH), -(-max(rxL, rxH) // 4) * 4         # both kernel parts share one Chebyshev basis
             R = ry * kp
             fact = 0.5 * N * N * R + ncols * N * R + ncols * N * 64 * 64 + G * 64 * 64
             if fact * self.factored_min_gain < dense:
@@ -423,7 +423,7 @@ class DeviceGP:
             return None, None
         lib = nat.lib()
         nG = plan["ncols"] * 64 * 64
-        nH = int(lib.mfgp_factored_rhs_cols(plan["rxL"], plan["ryL"], plan["rxH"], plan["ryH"])) - 64
+        nH = int(lib.mfgp_factored_rhs_cols(plan["rxL"], plan["ryL"], plan["rxH"], plan["ryH"]))     # >= ry * kpad
         if self._fG is None or self._fG.numel() < nG:
             self._fG = torch.empty(nG, dtype=torch.float64, device=self.device)
         if self._fHz is None or self._fHz.numel() < nH:

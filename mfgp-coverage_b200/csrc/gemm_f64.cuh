@@ -1,6 +1,7 @@
 // Batched fp64 tile GEMM on DMMA for the factorisation kernels (Cholesky panel solve, SYRK trailing update,
-// block-doubling triangular inverse).  All dimensions are multiples of 64 (buffers are padded to MFGP_TILE), so there
-// is no edge handling.  C[M,N] = alpha * A[M,K] * op(B) + beta * C, row-major, one 64x64 C tile per 128-thread CTA
+// block-doubling triangular inverse) and the products of the factored posterior.  M is a multiple of 64 (buffers are padded
+// to MFGP_TILE); N may end inside a tile (multiple of 2: loads zero-filled, stores predicated) and K inside a slab (multiple
+// of 2: zero-filled).  C[M,N] = alpha * A[M,K] * op(B) + beta * C, row-major, one 64x64 C tile per 128-thread CTA
 // (2x2 warps, 32x32 per warp = 4x4 DMMA 8x8 tiles), K streamed in 16-wide cp.async double-buffered slabs.
 #pragma once
 #include "common.cuh"
@@ -63,29 +64,29 @@ __global__ void __launch_bounds__(128) gemm_f64_kernel(GemmArgs g) {
         for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
 
     auto stage = [&](int buf, int k0) {
-        // A slab: 64 rows x 16 doubles = 512 16-byte chunks
+        // A slab: 64 rows x 16 doubles = 512 16-byte chunks (chunks at or beyond kend / N are zero-filled, never read)
 #pragma unroll
         for (int c = tid; c < GT * (GK / 2); c += 128) {
             int r = c >> 3, q = c & 7;
-            cp_async16(&As[buf][r * GLD + q * 2], A + (int64_t)(m0 + r) * g.lda + k0 + q * 2, true);
+            cp_async16(&As[buf][r * GLD + q * 2], A + (int64_t)(m0 + r) * g.lda + k0 + q * 2, k0 + q * 2 < kend);
         }
         if (B_TRANS) {
 #pragma unroll
             for (int c = tid; c < GT * (GK / 2); c += 128) {
                 int r = c >> 3, q = c & 7;
-                cp_async16(&Bs[buf][r * GLD + q * 2], B + (int64_t)(n0 + r) * g.ldb + k0 + q * 2, true);
+                cp_async16(&Bs[buf][r * GLD + q * 2], B + (int64_t)(n0 + r) * g.ldb + k0 + q * 2, k0 + q * 2 < kend && n0 + r < g.N);
             }
         } else {
 #pragma unroll
             for (int c = tid; c < GK * (GT / 2); c += 128) {
                 int r = c >> 5, q = c & 31;
-                cp_async16(&Bs[buf][r * GLDB + q * 2], B + (int64_t)(k0 + r) * g.ldb + n0 + q * 2, true);
+                cp_async16(&Bs[buf][r * GLDB + q * 2], B + (int64_t)(k0 + r) * g.ldb + n0 + q * 2, k0 + r < kend && n0 + q * 2 < g.N);
             }
         }
         cp_async_commit();
     };
 
-    const int nslab = (kend - kbeg) / GK;
+    const int nslab = (kend - kbeg + GK - 1) / GK;
     if (nslab > 0) stage(0, kbeg);
     for (int s = 0; s < nslab; s++) {
         const int buf = s & 1;
@@ -117,6 +118,7 @@ __global__ void __launch_bounds__(128) gemm_f64_kernel(GemmArgs g) {
         const int64_t row = m0 + wm + i * 8 + gq;
 #pragma unroll
         for (int j = 0; j < 4; j++) {
+            if (n0 + wn + j * 8 + tq * 2 >= g.N) continue;
             double2* p = reinterpret_cast<double2*>(C + row * g.ldc + n0 + wn + j * 8 + tq * 2);
             double2 out;
             if (g.beta != 0.0) {
@@ -145,7 +147,7 @@ static __global__ void splitk_reduce_kernel(const double* __restrict__ part, int
 
 inline int launch_gemm(const GemmArgs& g, bool b_trans, int batch, cudaStream_t st) {
     if (g.M <= 0 || g.N <= 0 || batch <= 0) return MFGP_OK;
-    dim3 grid(g.N / GT, g.M / GT, batch);
+    dim3 grid((g.N + GT - 1) / GT, g.M / GT, batch);
     if (b_trans)
         gemm_f64_kernel<true><<<grid, 128, 0, st>>>(g);
     else

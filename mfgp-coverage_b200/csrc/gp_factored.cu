@@ -27,7 +27,7 @@ constexpr int F_LW = 64;             // padded number of y-expansion terms of bo
 constexpr int F_MAXR = 64;           // largest supported Chebyshev order per axis and part
 
 struct FPart {                       // one kernel part (lofi / hifi) of the factored expansion
-    int rx, ry, kpad;                // x terms, y terms (multiple of 4), x terms padded to a multiple of 16
+    int rx, ry, kpad;                // x terms, y terms (multiple of 4), x terms padded to a multiple of 4
     int loff;                        // first column of this part inside the 64-wide y-term vector
     double inv_l;                    // 1 / length scale
     double* Cx; double* Cy;          // [r][npad] Chebyshev coefficients of the training points' axis factors
@@ -129,7 +129,7 @@ __global__ void build_B_merged_kernel(BTab t0, BTab t1, int ntab, int npad, int 
     B[(int64_t)n * ldB + e] = v;
 }
 
-// centred observations as one more 64-wide block of right-hand sides: column 0 = y - mean (gaussian_process.py:133, :419-424)
+// centred observations behind B: column 0 of the block = y - mean (gaussian_process.py:133, :419-424), the padding columns zero
 __global__ void build_z_block_kernel(const double* __restrict__ y, int npad, int N, int NL, double mean_L, double mean_H,
                                      double* __restrict__ B, int64_t ldB) {
     const int n = blockIdx.x, c = threadIdx.x;
@@ -388,7 +388,7 @@ static inline int64_t imax(int64_t a, int64_t b) { return a > b ? a : b; }
 
 extern "C" int64_t mfgp_factored_workspace_bytes(int64_t npad, int64_t ncols, int64_t ny, int64_t rxL, int64_t ryL, int64_t rxH,
                                                  int64_t ryH, int64_t chunk_cols) {
-    const int64_t rx = imax(rxL, rxH), ry = imax(ryL, ryH), kp = round_up(rx, 16);
+    const int64_t rx = imax(rxL, rxH), ry = imax(ryL, ryH), kp = round_up(rx, 4);
     const int64_t ncp = round_up(ncols, 64), ch = round_up(chunk_cols, 64);
     int64_t d = 0;
     d += ny * 64 + npad + ry * kp;                             // Uy, solved z, Hz
@@ -399,9 +399,10 @@ extern "C" int64_t mfgp_factored_workspace_bytes(int64_t npad, int64_t ncols, in
     return d * 8 + 4096;
 }
 
-// number of right-hand-side columns of the fused fit (mfgp_cholesky_solve): [B | z block]
+// number of right-hand-side columns of the fused fit (mfgp_cholesky_solve): [B (ry * kpad columns) | y - mean | zero padding
+// up to the next multiple of 64]
 extern "C" int64_t mfgp_factored_rhs_cols(int64_t rxL, int64_t ryL, int64_t rxH, int64_t ryH) {
-    return imax(ryL, ryH) * round_up(imax(rxL, rxH), 16) + 64;
+    return round_up(imax(ryL, ryH) * round_up(imax(rxL, rxH), 4) + 1, 64);
 }
 
 namespace {
@@ -451,7 +452,7 @@ void f_carve(const FGeom& g, void* work, FLayout& L) {
     add_tab((int)g.rxH, (int)g.ryH, g.p->l_H, false);
     FPart& f = L.parts[0];
     L.nparts = 1;
-    f.rx = (int)imax(g.rxL, g.rxH); f.ry = (int)imax(g.ryL, g.ryH); f.kpad = (int)round_up(f.rx, 16); f.loff = 0; f.inv_l = 0.0;
+    f.rx = (int)imax(g.rxL, g.rxH); f.ry = (int)imax(g.ryL, g.ryH); f.kpad = (int)round_up(f.rx, 4); f.loff = 0; f.inv_l = 0.0;
     f.Cx = f.Cy = nullptr;
     f.B = carve(g.npad * (int64_t)f.ry * f.kpad); f.Y = carve(g.npad * (int64_t)f.ry * f.kpad);
     f.Ux = carve(L.ncp * f.kpad);
@@ -596,8 +597,9 @@ extern "C" int mfgp_factored_prepare(const double* ux, int64_t nx, const double*
     f_carve(g, work, L);
     rc = f_tables_and_B(g, L, Ball, ldB, st);
     if (rc) return rc;
-    const int64_t zoff = mfgp_factored_rhs_cols(rxL, ryL, rxH, ryH) - 64;
-    build_z_block_kernel<<<(unsigned)npad, 64, 0, st>>>(y, (int)npad, (int)(NL + NH), (int)NL, p_host->mean_L, p_host->mean_H, Ball + zoff, ldB);
+    const int64_t zoff = (int64_t)L.parts[0].ry * L.parts[0].kpad;           // the column right behind B; the rest is zero padding
+    const int zw = (int)(mfgp_factored_rhs_cols(rxL, ryL, rxH, ryH) - zoff);
+    build_z_block_kernel<<<(unsigned)npad, zw, 0, st>>>(y, (int)npad, (int)(NL + NH), (int)NL, p_host->mean_L, p_host->mean_H, Ball + zoff, ldB);
     MFGP_LAUNCH_CHECK();
     return MFGP_OK;
 }
