@@ -215,15 +215,17 @@ def run_ours(args):
         eng.posterior(grid.xy, mu, var, axes=axes, g_lo=lo)           # factored (tensor grid) or dense DMMA kernel
         if timed:
             ev[1].record()
-        loss_vor = sim.voronoi_bounded(w["pos"], bbox)
+        loss_vor = sim.voronoi_bounded(w["pos"], bbox)                # host Qhull while the GPU works on the posterior
         lloyd_vor = sim.voronoi_bounded(w["cen"], bbox)
+        loss_vor.areas(), lloyd_vor.areas()
         res = grid.assign_reduce(lloyd_vor, loss_vor, w=mu, var=var)
         if timed:
             ev[2].record()
         sharding.allreduce_partials(res)
-        loss = cv.loss_from_partials(res["lossp"].cpu().numpy(), loss_vor.areas())
-        cent = cv.centroids_from_partials(res["cent"].cpu().numpy(), lloyd_vor.areas(), 0.0, 1.0, 0.0, 1.0)
-        idx = res["amax_idx"].cpu().numpy()
+        host = cv.CoverageGrid.results_to_host(res)                   # one packed device->host copy
+        loss = cv.loss_from_partials(host["lossp"], loss_vor.areas())
+        cent = cv.centroids_from_partials(host["cent"], lloyd_vor.areas(), 0.0, 1.0, 0.0, 1.0)
+        idx = host["amax_idx"]
         if timed:
             post_ms.append(ev[0].elapsed_time(ev[1]))                 # .cpu() above synchronised the stream
             fit_ms.append(ev[3].elapsed_time(ev[0]))

@@ -5,6 +5,7 @@ output / workspace buffers of `cov_assign_reduce`; `BoundedVoronoi` is the host-
 from scipy/Qhull (simulator.py:154-191), flattened for the device.
 """
 import ctypes
+import itertools
 import math
 
 import numpy as np
@@ -59,26 +60,32 @@ class BoundedVoronoi:
         return self.vertices[self.filtered_regions[i], :]
 
     def areas(self):
-        """Shoelace area per cell (simulator.py:127-136): 0.5 |x . roll(y,1) - y . roll(x,1)|, cached."""
+        """Shoelace area per cell (simulator.py:127-136): 0.5 |x . roll(y,1) - y . roll(x,1)|, cached.  All cells at once
+        on the flat vertex list (two segmented dot products, then the difference -- the reference's order of operations)."""
         if getattr(self, "_areas", None) is None:
-            out = np.empty(len(self))
-            for i in range(len(self)):
-                v = self.vertices[self.filtered_regions[i]]
-                x, y = v[:, 0], v[:, 1]
-                out[i] = 0.5 * abs(float(np.dot(x[1:], y[:-1]) + x[0] * y[-1]) - float(np.dot(y[1:], x[:-1]) + y[0] * x[-1]))
-            self._areas = out
+            _, poly, off = self.flat()
+            A = len(self)
+            if A == 0 or poly.shape[0] == 0:
+                self._areas = np.zeros(A)
+            else:
+                x, y = poly[:, 0], poly[:, 1]
+                prev = np.arange(poly.shape[0]) - 1
+                prev[off[:-1]] = off[1:] - 1                      # roll(., 1) inside every cell
+                a = np.add.reduceat(x * y[prev], off[:-1])
+                b = np.add.reduceat(y * x[prev], off[:-1])
+                self._areas = 0.5 * np.abs(a - b)
         return self._areas
 
     def flat(self):
         """(seeds[A,2], poly_xy[nvert,2], poly_off[A+1]) as contiguous host arrays."""
         if self._flat is None:
-            off = np.zeros(len(self) + 1, dtype=np.int32)
-            chunks = []
-            for i in range(len(self)):
-                v = self.cell_vertices(i)
-                chunks.append(v)
-                off[i + 1] = off[i] + v.shape[0]
-            poly = np.ascontiguousarray(np.concatenate(chunks, axis=0), dtype=np.float64) if chunks else np.empty((0, 2))
+            regs = self.filtered_regions
+            A = len(regs)
+            lens = np.fromiter((len(r) for r in regs), dtype=np.int64, count=A)
+            off = np.zeros(A + 1, dtype=np.int32)
+            np.cumsum(lens, out=off[1:])
+            idx = np.fromiter(itertools.chain.from_iterable(regs), dtype=np.intp, count=int(off[-1]))
+            poly = np.ascontiguousarray(self.vertices[idx], dtype=np.float64) if A else np.empty((0, 2))
             self._flat = (np.ascontiguousarray(self.filtered_points, dtype=np.float64), poly, off)
         return self._flat
 
@@ -176,12 +183,15 @@ class _DevPartition:
         self.A = int(seeds.shape[0])
         self.nvert = int(off[-1])
         nb_s, nb_p = self.A * 16, max(self.nvert, 1) * 16
-        host = np.zeros(nb_s + nb_p + (self.A + 2) // 2 * 8, dtype=np.uint8)
+        # staged in page-locked memory (torch's caching host allocator) and copied asynchronously: a pageable upload
+        # would make the host wait for everything queued on the stream before it (the posterior kernels)
+        stage = torch.zeros(nb_s + nb_p + (self.A + 2) // 2 * 8, dtype=torch.uint8, pin_memory=True)
+        host = stage.numpy()
         host[:nb_s] = seeds.reshape(-1).view(np.uint8)
         if self.nvert:
             host[nb_s:nb_s + self.nvert * 16] = poly.reshape(-1).view(np.uint8)
         host[nb_s + nb_p:nb_s + nb_p + (self.A + 1) * 4] = off.view(np.uint8)
-        buf = torch.from_numpy(host).to(device)
+        buf = stage.to(device, non_blocking=True)
         self.seeds = buf[:nb_s].view(torch.float64)
         self.poly = buf[nb_s:nb_s + nb_p].view(torch.float64)
         self.off = buf[nb_s + nb_p:].view(torch.int32)
@@ -247,11 +257,14 @@ class CoverageGrid:
         if reuse:
             cent, amax_val, amax_idx, lossp = out["cent"], out["amax_val"], out["amax_idx"], out["lossp"]
         else:
-            out = {}
-            cent = torch.empty((Ac, 4), **f64) if Ac else None
-            amax_val = torch.empty(Ac, **f64) if Ac else None
-            amax_idx = torch.empty(Ac, dtype=torch.int64, device=dev) if Ac else None
-            lossp = torch.empty((Ap, 2), **f64) if Ap else None
+            # one packed buffer [cent 4 Ac | amax_val Ac | amax_idx Ac (int64 bits) | lossp 2 Ap]: results_to_host()
+            # brings everything home with ONE device->host copy
+            pack = torch.empty(6 * Ac + 2 * Ap, **f64)
+            out = {"pack": pack, "pack_shape": (Ac, Ap)}
+            cent = pack[:4 * Ac].view(Ac, 4) if Ac else None
+            amax_val = pack[4 * Ac:5 * Ac] if Ac else None
+            amax_idx = pack[5 * Ac:6 * Ac].view(torch.int64) if Ac else None
+            lossp = pack[6 * Ac:].view(Ap, 2) if Ap else None
         words = (max(Ac, Ap) + 63) // 64
         words = 1 if words <= 1 else (2 if words == 2 else 4)
         members = torch.zeros((self.G, words), dtype=torch.int64, device=dev) if (want_members and Ac) else None
@@ -281,6 +294,21 @@ class CoverageGrid:
         nat.check(rc, "cov_assign_reduce")
         out.update(cent=cent, amax_val=amax_val, amax_idx=amax_idx, lossp=lossp, members=members)
         return out
+
+    @staticmethod
+    def results_to_host(res):
+        """Host copy of an assign_reduce result as a dict of numpy arrays (cent, amax_val, amax_idx, lossp): ONE
+        device->host copy of the packed buffer into page-locked memory, one synchronisation."""
+        Ac, Ap = res["pack_shape"]
+        pack = res["pack"]
+        h = torch.empty(pack.shape, dtype=pack.dtype, pin_memory=True)
+        h.copy_(pack, non_blocking=True)
+        torch.cuda.current_stream(pack.device).synchronize()
+        a = h.numpy()
+        return {"cent": a[:4 * Ac].reshape(Ac, 4) if Ac else None,
+                "amax_val": a[4 * Ac:5 * Ac] if Ac else None,
+                "amax_idx": a[5 * Ac:6 * Ac].view(np.int64) if Ac else None,
+                "lossp": a[6 * Ac:].reshape(Ap, 2) if Ap else None}
 
     def finish(self, res, lloyd_vor, loss_vor, bbox, info=None):
         """Device finishing of an assign_reduce result for DEVICE-resident partitions (ClippedVoronoi): returns

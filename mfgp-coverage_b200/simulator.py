@@ -131,7 +131,7 @@ def compute_loss(vor, truth_arr):
     """reference simulator.py:194-228."""
     grid = _grid_for(truth_arr)
     res = grid.assign_reduce(loss_vor=vor)
-    return cv.loss_from_partials(res["lossp"].cpu().numpy(), vor.areas())
+    return cv.loss_from_partials(cv.CoverageGrid.results_to_host(res)["lossp"], vor.areas())
 
 
 def compute_centroids(vor, x_star, mu_star):
@@ -141,7 +141,7 @@ def compute_centroids(vor, x_star, mu_star):
     w = mu_star if torch.is_tensor(mu_star) else torch.from_numpy(
         np.ascontiguousarray(mu_star, dtype=np.float64).reshape(-1)).to(grid.device)
     res = grid.assign_reduce(lloyd_vor=vor, w=w)
-    return cv.centroids_from_partials(res["cent"].cpu().numpy(), vor.areas(), *grid.extent)
+    return cv.centroids_from_partials(cv.CoverageGrid.results_to_host(res)["cent"], vor.areas(), *grid.extent)
 
 
 def _as_var_vector(var_star, device):
@@ -154,10 +154,13 @@ def _as_var_vector(var_star, device):
 
 
 def _max_var_from(res, truth_arr):
-    idx = res["amax_idx"].cpu().numpy()
+    """`res`: an assign_reduce result (device tensors) or its host copy (CoverageGrid.results_to_host)."""
+    if torch.is_tensor(res["amax_idx"]):
+        res = cv.CoverageGrid.results_to_host(res)
+    idx = res["amax_idx"]
     if np.any(idx < 0):
         raise ValueError("zero-size array to reduction operation maximum which has no identity")   # np.amax([])
-    return truth_arr[idx][:, [0, 1]], res["amax_val"].cpu().numpy().reshape(-1, 1), idx
+    return truth_arr[idx][:, [0, 1]], np.array(res["amax_val"]).reshape(-1, 1), idx
 
 
 def compute_max_var(vor, truth_arr, var_star):
@@ -299,18 +302,22 @@ class _Sim:
         """One hot-path iteration: posterior over the grid, then both partitions in one fused pass.
         Returns (loss_t, centroids_t, argmax_var_t, max_var_t, loss_vor, lloyd_vor)."""
         bb = self.bounding_box
-        if VORONOI == "clip":        # device-built cells, the two buffer sets of the previous iteration are recycled
+        clip = VORONOI == "clip"
+        if clip and model is not None:
+            model.engine.lazy_check = True       # cov_finish brings the Cholesky status home with the results
+            model.engine.defer_fit = True        # ... so a refit may fuse with the factored posterior (large tensor grids)
+        if model is not None:                    # queued first: the host builds the partitions while the GPU works
+            model.predict_device(self.grid.xy, self.mu, self.var, grid=self.grid)
+        if clip:                     # device-built cells, the two buffer sets of the previous iteration are recycled
             loss_vor = cv.ClippedVoronoi(positions, bb, reuse=self._clip[0])
             lloyd_vor = cv.ClippedVoronoi(centroids_t, bb, reuse=self._clip[1])
             self._clip = [loss_vor, lloyd_vor]
-            if model is not None:
-                model.engine.lazy_check = True       # cov_finish brings the Cholesky status home with the results
-                model.engine.defer_fit = True        # ... so a refit may fuse with the factored posterior (large tensor grids)
         else:
             loss_vor = voronoi_bounded(positions, bb)
             lloyd_vor = voronoi_bounded(centroids_t, bb)
+            loss_vor.areas()                     # host work that does not depend on the GPU goes before the launch
+            lloyd_vor.areas()
         if model is not None:
-            model.predict_device(self.grid.xy, self.mu, self.var, grid=self.grid)
             res = self.grid.assign_reduce(lloyd_vor, loss_vor, w=self.mu, var=self.var,
                                           amax_k0=prior_variance(model.params()), amax_rel=cv.AMAX_REL)
         else:
@@ -323,11 +330,12 @@ class _Sim:
             if np.any(idx < 0):
                 raise ValueError("zero-size array to reduction operation maximum which has no identity")   # np.amax([])
             return loss_t, centroids, self.truth_arr[idx][:, [0, 1]], max_var.reshape(-1, 1), loss_vor, lloyd_vor
-        loss_t = cv.loss_from_partials(res["lossp"].cpu().numpy(), loss_vor.areas())
-        centroids = cv.centroids_from_partials(res["cent"].cpu().numpy(), lloyd_vor.areas(), bb[0], bb[1], bb[2], bb[3])
+        host = cv.CoverageGrid.results_to_host(res)      # one device->host copy for all the per-cell results
+        loss_t = cv.loss_from_partials(host["lossp"], loss_vor.areas())
+        centroids = cv.centroids_from_partials(host["cent"], lloyd_vor.areas(), bb[0], bb[1], bb[2], bb[3])
         if model is None:
             return loss_t, centroids, None, None, loss_vor, lloyd_vor
-        argmax_xy, max_var, _ = _max_var_from(res, self.truth_arr)
+        argmax_xy, max_var, _ = _max_var_from(host, self.truth_arr)
         return loss_t, centroids, argmax_xy, max_var, loss_vor, lloyd_vor
 
 
