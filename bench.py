@@ -221,8 +221,7 @@ def run_ours(args):
         res = grid.assign_reduce(lloyd_vor, loss_vor, w=mu, var=var)
         if timed:
             ev[2].record()
-        sharding.allreduce_partials(res)
-        host = cv.CoverageGrid.results_to_host(res)                   # one packed device->host copy
+        host = sharding.gather_results_to_host(res)                   # N > 1: one all-gather; one packed device->host copy
         loss = cv.loss_from_partials(host["lossp"], loss_vor.areas())
         cent = cv.centroids_from_partials(host["cent"], lloyd_vor.areas(), 0.0, 1.0, 0.0, 1.0)
         idx = host["amax_idx"]

@@ -152,8 +152,10 @@ int64_t mfgp_factored_workspace_bytes(int64_t npad, int64_t ncols, int64_t ny, i
 
 /* Fused fit + factored posterior (the from-scratch iteration of the reference, simulator.py:888-892, on a tensor grid):
  *   mfgp_build_train_cov  ->  mfgp_factored_prepare (B = [B_L | B_H | y - mean], mfgp_factored_rhs_cols columns)
- *   ->  mfgp_cholesky_solve (K -> L in place, diagonal-block inverses into W, Ball -> L^-1 Ball; the right-hand-side tile
- *       GEMMs run on an internal side stream behind the latency-bound panel chain)
+ *   ->  mfgp_cholesky_solve (K -> L in place, diagonal-block inverses into W, Ball -> L^-1 Ball: ONE persistent
+ *       tile-dataflow kernel, chol_dataflow_kernel in csrc/gp_fit.cu; its ready flags live in a per-device scratch buffer,
+ *       so calls on one device must not overlap in time.  MFGP_CHOL=chain in the environment selects the older
+ *       launch-per-panel implementation)
  *   ->  mfgp_posterior_grid_factored_solved (steps 4-6; z_out receives the whitened observations).
  * Neither the explicit inverse (mfgp_tri_inverse) nor the product W B is formed; run mfgp_tri_inverse afterwards only if W
  * is needed (dense posterior, mfgp_cholesky_append, choi_greedy).  Same geometry / order arguments and the same `work`

@@ -59,6 +59,57 @@ def allreduce_partials(res, group=None):
     return res
 
 
+def merge_argmax_host(vals, idxs):
+    """numpy twin of merge_argmax for host-side merging: vals[R, A], idxs[R, A] (int64, -1 = empty)."""
+    vals = np.array(vals, dtype=np.float64)
+    idxs = np.asarray(idxs, dtype=np.int64)
+    big = np.iinfo(np.int64).max
+    empty = idxs < 0
+    vals[empty] = -np.inf
+    best = vals.max(axis=0)
+    cand = np.where((vals == best[None, :]) & ~empty, idxs, big)
+    bidx = cand.min(axis=0)
+    bidx[bidx == big] = -1
+    return best, bidx
+
+
+def gather_results_to_host(res, group=None):
+    """Global per-cell results of CoverageGrid.assign_reduce on the host with ONE collective and ONE device->host copy:
+    the packed result buffers of all ranks are all-gathered, copied home, and combined there -- partial sums added in rank
+    order (deterministic), arg-max pairs merged with the lowest-global-index rule.  Every rank gets the same dict of numpy
+    arrays (cent, amax_val, amax_idx, lossp).  Cheaper than allreduce_partials (two all-reduces, two all-gathers and a
+    handful of small kernels) when the results go to the host anyway, as in the coverage loops."""
+    from ._coverage import CoverageGrid
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return CoverageGrid.results_to_host(res)
+    world = dist.get_world_size(group)
+    Ac, Ap = res["pack_shape"]
+    pack = res["pack"]
+    parts = [torch.empty_like(pack) for _ in range(world)]
+    dist.all_gather(parts, pack, group=group)
+    allp = torch.stack(parts)
+    if allp.is_cuda:
+        h = torch.empty(allp.shape, dtype=allp.dtype, pin_memory=True)
+        h.copy_(allp, non_blocking=True)
+        torch.cuda.current_stream(allp.device).synchronize()
+        a = h.numpy()
+    else:
+        a = allp.numpy()
+    out = {"cent": None, "amax_val": None, "amax_idx": None, "lossp": None}
+    if Ac:
+        cent = np.zeros((Ac, 4))
+        for r in range(world):                                   # rank order: the same sum on every rank, every run
+            cent += a[r, :4 * Ac].reshape(Ac, 4)
+        out["cent"] = cent
+        out["amax_val"], out["amax_idx"] = merge_argmax_host(a[:, 4 * Ac:5 * Ac], a[:, 5 * Ac:6 * Ac].copy().view(np.int64))
+    if Ap:
+        lossp = np.zeros((Ap, 2))
+        for r in range(world):
+            lossp += a[r, 6 * Ac:].reshape(Ap, 2)
+        out["lossp"] = lossp
+    return out
+
+
 def broadcast_factor(engine, src=0, group=None):
     """Broadcast the fitted factor state (W, z, Tt) of `engine` (a DeviceGP) from rank `src` to all ranks."""
     if not dist.is_initialized() or dist.get_world_size(group) == 1:

@@ -43,9 +43,14 @@ def _worker(rank, world, port, out):
     cent, lossp, aval, aidx = _local_partials(xy, f, mu, var, vor, lo, hi)
     res = dict(cent=torch.from_numpy(cent), lossp=torch.from_numpy(lossp), amax_val=torch.from_numpy(aval),
                amax_idx=torch.from_numpy(aidx))
+    # the packed form the coverage kernels write: [cent | amax_val | amax_idx bits | lossp], merged on the host
+    A = cent.shape[0]
+    pack = torch.cat([res["cent"].reshape(-1), res["amax_val"], res["amax_idx"].view(torch.float64), res["lossp"].reshape(-1)])
+    hosted = sharding.gather_results_to_host({"pack": pack, "pack_shape": (A, A)})
     sharding.allreduce_partials(res)
     if rank == 0:
         torch.save({k: v.clone() for k, v in res.items()}, out)
+        torch.save({k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in hosted.items()}, out + ".host")
     dist.destroy_process_group()
 
 
@@ -65,6 +70,10 @@ def test_grid_sharded_reductions_match_unsharded(tmp_path):
     assert np.array_equal(res["amax_idx"].numpy(), aidx) and np.array_equal(res["amax_val"].numpy(), aval)
     _, _, idx_o = ocov.compute_max_var(vor, np.column_stack((xy, f)), var)
     assert np.array_equal(res["amax_idx"].numpy(), idx_o)
+    hosted = torch.load(out + ".host")            # the one-collective host merge gives the same global results
+    assert np.allclose(hosted["cent"].numpy(), cent, rtol=1e-13, atol=1e-13)
+    assert np.allclose(hosted["lossp"].numpy(), lossp, rtol=1e-13, atol=1e-13)
+    assert np.array_equal(hosted["amax_idx"].numpy(), aidx) and np.array_equal(hosted["amax_val"].numpy(), aval)
 
 
 def test_shard_bounds_cover_the_grid():
