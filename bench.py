@@ -205,7 +205,7 @@ def run_ours(args):
     post_ms, fit_ms, cov_ms, chol_ms = [], [], [], []
     eng.profile_events = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
 
-    def device_step(timed):
+    def device_step(timed, shared_partitions=True):
         flush.zero_()
         if timed:
             ev[3].record()
@@ -215,9 +215,12 @@ def run_ours(args):
         eng.posterior(grid.xy, mu, var, axes=axes, g_lo=lo)           # factored (tensor grid) or dense DMMA kernel
         if timed:
             ev[1].record()
-        loss_vor = sim.voronoi_bounded(w["pos"], bbox)                # host Qhull while the GPU works on the posterior
-        lloyd_vor = sim.voronoi_bounded(w["cen"], bbox)
-        loss_vor.areas(), lloyd_vor.areas()
+        if world == 1 or not shared_partitions:
+            loss_vor = sim.voronoi_bounded(w["pos"], bbox)            # host Qhull while the GPU works on the posterior
+            lloyd_vor = sim.voronoi_bounded(w["cen"], bbox)
+            loss_vor.areas(), lloyd_vor.areas()
+        else:       # the partitions are global: rank 0 builds them (host Qhull), everybody else receives the packed cells
+            loss_vor, lloyd_vor = sharding.broadcast_partitions([w["pos"], w["cen"]], bbox, dev)
         res = grid.assign_reduce(lloyd_vor, loss_vor, w=mu, var=var)
         if timed:
             ev[2].record()
@@ -263,6 +266,9 @@ def run_ours(args):
     for _ in range(args.warmup):
         device_step(False)
     eng.check_factor(force=True)
+    if world > 1:      # the broadcast partitions give what every rank's own Qhull run gives
+        a, b = device_step(False), device_step(False, shared_partitions=False)
+        assert abs(a[0] - b[0]) <= 1e-12 * abs(b[0]) and np.allclose(a[1], b[1], rtol=1e-12, atol=1e-14) and np.array_equal(a[2], b[2])
     sampler = ClockSampler(local)
     sampler.start()
     l0 = nat.lib().mfgp_launch_count()

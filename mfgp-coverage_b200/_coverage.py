@@ -197,6 +197,68 @@ class _DevPartition:
         self.off = buf[nb_s + nb_p:].view(torch.int32)
 
 
+def seeds_summary(points, bounding_box):
+    """(number of cells, seeds_inside) of the partition BoundedVoronoi would build from `points` -- without building it
+    (the seeds kept are those inside the cushioned box, simulator.py:139-151)."""
+    points = np.asarray(points, dtype=np.float64).reshape(-1, 2)
+    bb = bounding_box
+    c = points[in_box(points, bb), :]
+    inside = bool(np.all((c[:, 0] >= bb[0]) & (c[:, 0] <= bb[1]) & (c[:, 1] >= bb[2]) & (c[:, 1] <= bb[3])))
+    return int(c.shape[0]), inside
+
+
+def partition_capacity(A):
+    """Vertex capacity of a packed partition buffer (planar bound ~6A + the box corners, with slack)."""
+    return 8 * A + 32
+
+
+def partition_doubles(A):
+    """Size of one packed partition: seeds 2A | areas A (+pad) | offsets (A+1 int32, padded) | vertices 2 cap."""
+    return 2 * A + (A + 1) // 2 * 2 + (A + 2) // 2 * 2 + 2 * partition_capacity(A)
+
+
+def pack_partition(vor, out):
+    """Write a BoundedVoronoi into `out` (numpy float64 view of partition_doubles(A) entries)."""
+    seeds, poly, off = vor.flat()
+    A = seeds.shape[0]
+    cap = partition_capacity(A)
+    if int(off[-1]) > cap:
+        raise RuntimeError("pack_partition: polygon capacity exceeded")
+    o_ar = 2 * A
+    o_off = o_ar + (A + 1) // 2 * 2
+    o_poly = o_off + (A + 2) // 2 * 2
+    out[:] = 0.0
+    out[:2 * A] = seeds.reshape(-1)
+    out[o_ar:o_ar + A] = vor.areas()
+    out[o_off:o_poly].view(np.int32)[:A + 1] = off
+    out[o_poly:o_poly + 2 * int(off[-1])] = poly.reshape(-1)
+
+
+class PackedPartition:
+    """A partition that lives in a packed device buffer (pack_partition layout): what CoverageGrid.assign_reduce needs
+    (seeds, polygons, offsets) plus the cell areas, without any host geometry -- e.g. received through a broadcast."""
+
+    def __init__(self, buf, A, seeds_inside):
+        cap = partition_capacity(A)
+        o_ar = 2 * A
+        o_off = o_ar + (A + 1) // 2 * 2
+        o_poly = o_off + (A + 2) // 2 * 2
+        self.A, self.nvert, self.seeds_inside = int(A), cap, bool(seeds_inside)      # nvert: capacity, the count is off[A]
+        self.seeds = buf[:2 * A]
+        self.dev_areas = buf[o_ar:o_ar + A]
+        self.off = buf[o_off:o_poly].view(torch.int32)
+        self.poly = buf[o_poly:o_poly + 2 * cap]
+
+    def __len__(self):
+        return self.A
+
+    def areas(self):
+        """Host copy of the cell areas (one small device->host copy, cached)."""
+        if getattr(self, "_areas", None) is None:
+            self._areas = self.dev_areas.cpu().numpy()
+        return self._areas
+
+
 class CoverageGrid:
     """Grid points xy[G,2] (+ optional truth f[G]) resident on the device, with reusable output buffers."""
 
@@ -228,7 +290,7 @@ class CoverageGrid:
 
     def upload(self, vor):
         """Device copy of a partition (BoundedVoronoi / polygon_partition); pass the result to assign_reduce to reuse it."""
-        if vor is None or isinstance(vor, (_DevPartition, ClippedVoronoi)):
+        if vor is None or isinstance(vor, (_DevPartition, ClippedVoronoi, PackedPartition)):
             return vor if (vor is None or len(vor)) else None
         if not len(vor):
             return None

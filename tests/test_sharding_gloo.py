@@ -76,6 +76,36 @@ def test_grid_sharded_reductions_match_unsharded(tmp_path):
     assert np.array_equal(hosted["amax_idx"].numpy(), aidx) and np.array_equal(hosted["amax_val"].numpy(), aval)
 
 
+def _bcast_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from mfgp_coverage_b200 import sharding
+    bb = np.array([0.0, 1.0, 0.0, 1.0])
+    sets = [synth.agents(7, 3), synth.agents(12, 4)]
+    parts = sharding.broadcast_partitions(sets, bb, "cpu")
+    torch.save([{"seeds": p.seeds.clone(), "off": p.off.clone(), "poly": p.poly.clone(), "areas": torch.from_numpy(p.areas()),
+                 "A": p.A, "inside": p.seeds_inside} for p in parts], out + f".{rank}")
+    dist.destroy_process_group()
+
+
+def test_partitions_built_once_and_broadcast(tmp_path):
+    """N > 1: rank 0 runs Qhull, every rank ends up with the same packed cells as a locally built partition."""
+    from mfgp_coverage_b200 import _coverage as cv
+    out = str(tmp_path / "parts.pt")
+    mp.spawn(_bcast_worker, args=(2, 29533, out), nprocs=2, join=True)
+    bb = np.array([0.0, 1.0, 0.0, 1.0])
+    for rank in range(2):
+        got = torch.load(out + f".{rank}")
+        for g, pts in zip(got, [synth.agents(7, 3), synth.agents(12, 4)]):
+            v = cv.BoundedVoronoi(pts, bb)
+            seeds, poly, off = v.flat()
+            assert g["A"] == len(v) and g["inside"] == v.seeds_inside
+            assert np.array_equal(g["seeds"].numpy(), seeds.reshape(-1))
+            assert np.array_equal(g["off"].numpy()[:len(v) + 1], off)
+            assert np.array_equal(g["poly"].numpy()[:2 * off[-1]], poly.reshape(-1))
+            assert np.array_equal(g["areas"].numpy(), v.areas())
+
+
 def test_shard_bounds_cover_the_grid():
     from mfgp_coverage_b200 import sharding
     for G in (1, 7, 2601, 1 << 20):
