@@ -98,18 +98,7 @@ __global__ void cheb_basis_kernel(const double* __restrict__ u, int i0, int coun
     }
 }
 
-// ---- step 2: B[n][l][k] = coef[n] Cy[l][n] Cx[k][n] ------------------------------------------------------------------------
-__global__ void build_B_kernel(const double* __restrict__ Cx, const double* __restrict__ Cy, int npad, int N, int NL, int rx, int ry,
-                               int kpad, double coef_lo, double coef_hi, double* __restrict__ B, int64_t ldB) {
-    const int n = blockIdx.y;
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;       // (l, k)
-    if (e >= ry * kpad) return;
-    const int l = e / kpad, k = e % kpad;
-    double v = 0.0;
-    if (n < N && k < rx) v = (n < NL ? coef_lo : coef_hi) * Cy[(int64_t)l * npad + n] * Cx[(int64_t)k * npad + n];
-    B[(int64_t)n * ldB + e] = v;
-}
-
+// ---- step 2: B[n][l][k] = sum_P coef_P[n] Cy_P[l][n] Cx_P[k][n] ---------------------------------------------------------------
 // Both kernel parts expand in the SAME Chebyshev basis T_l(ty) T_k(tx), so their coefficient tensors simply add: one B with
 // rx = max(rxL, rxH), ry = max(ryL, ryH) instead of two (the lofi part's terms beyond its own orders are zero):
 //   B[n][l][k] = cL[n] CyL[l][n] CxL[k][n] [l < ryL, k < rxL]  +  cH[n] CyH[l][n] CxH[k][n] [l < ryH, k < rxH]
@@ -187,7 +176,6 @@ __global__ void zero_rows_kernel(double* __restrict__ Y, int64_t cols, int nrows
 }
 
 // ---- steps 5 + 6: one CTA per grid column --------------------------------------------------------------------------------
-constexpr int G_LD = F_LW + 4;       // padded shared-memory row (doubles): conflict-free DMMA fragment reads
 constexpr int G_ROWS = 64;           // training rows per chunk
 
 struct GramArgs {

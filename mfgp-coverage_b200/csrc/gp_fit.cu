@@ -318,11 +318,25 @@ __global__ void __launch_bounds__(DF_THREADS, 2) chol_dataflow_kernel(DfArgs g) 
         const int* fb = rhs ? g.flagsY + idx : g.flagsL + (int64_t)(c > 0 ? c : 0) * g.nb;      // Y_k,r (stride nr) or L_c,k
         const int fbs = rhs ? g.nr : 1;
 
+        // The accumulators START at minus the tile they will be subtracted from (A_ic or B_cr; chain tasks: also A_dd), so the
+        // global reads of those tiles happen here, at the head of the task, instead of on the critical tail behind the flag.
+        double* Ct = rhs ? g.Bm + (int64_t)c * PB * g.ldb + (int64_t)idx * PB
+                         : g.K + (int64_t)i * PB * g.ld + (int64_t)(c > 0 ? c : 0) * PB;
+        const int64_t ldc = rhs ? g.ldb : g.ld;
+        double* Cd = g.K + (int64_t)(chain ? idx : 0) * PB * (g.ld + 1);        // diagonal tile (idx, idx) of a chain task
+        const bool has_tile = !(chain && idx == 0);
         double acc[2][4][2], acc2[2][4][2];
 #pragma unroll
-        for (int a = 0; a < 2; a++)
+        for (int x = 0; x < 2; x++)
 #pragma unroll
-            for (int b = 0; b < 4; b++) acc[a][b][0] = acc[a][b][1] = acc2[a][b][0] = acc2[a][b][1] = 0.0;
+            for (int y = 0; y < 4; y++) {
+                const int r = wm + x * 32 + gq, cc = wn + y * 16 + tq * 2;
+                double2 v = make_double2(0.0, 0.0), d = make_double2(0.0, 0.0);
+                if (has_tile) v = *reinterpret_cast<const double2*>(Ct + (int64_t)r * ldc + cc);
+                if (chain) d = *reinterpret_cast<const double2*>(Cd + (int64_t)r * g.ld + cc);
+                acc[x][y][0] = -v.x; acc[x][y][1] = -v.y;
+                acc2[x][y][0] = -d.x; acc2[x][y][1] = -d.y;
+            }
 
         bool ok = true;
         int pre = 0;                                  // lane 0: both flags of the NEXT k tile, sampled one slab early
@@ -411,9 +425,6 @@ __global__ void __launch_bounds__(DF_THREADS, 2) chol_dataflow_kernel(DfArgs g) 
         double* Ws = df_smem + DF_TILE;       // [64][68]  W_cc
         double* Ls = df_smem + 2 * DF_TILE;   // [64][68]  L_{i,c} of a chain task
         double* Wcc = g.W + (int64_t)(c > 0 ? c : 0) * PB * (g.ldw + 1);
-        double* Ct = rhs ? g.Bm + (int64_t)c * PB * g.ldb + (int64_t)idx * PB
-                         : g.K + (int64_t)i * PB * g.ld + (int64_t)(c > 0 ? c : 0) * PB;
-        const int64_t ldc = rhs ? g.ldb : g.ld;
         int* myflag = rhs ? g.flagsY + (int64_t)c * g.nr + idx : g.flagsL + (int64_t)i * g.nb + (c > 0 ? c : 0);
         if (!(chain && idx == 0)) {
 #pragma unroll
@@ -421,9 +432,8 @@ __global__ void __launch_bounds__(DF_THREADS, 2) chol_dataflow_kernel(DfArgs g) 
 #pragma unroll
                 for (int y = 0; y < 4; y++) {
                     const int r = wm + x * 32 + gq, cc = wn + y * 16 + tq * 2;
-                    const double2 v = *reinterpret_cast<const double2*>(Ct + (int64_t)r * ldc + cc);
-                    Xs[r * DF_LDT + cc] = v.x - acc[x][y][0];
-                    Xs[r * DF_LDT + cc + 1] = v.y - acc[x][y][1];
+                    Xs[r * DF_LDT + cc] = -acc[x][y][0];              // X = C - sum (the accumulator started at -C)
+                    Xs[r * DF_LDT + cc + 1] = -acc[x][y][1];
                     acc[x][y][0] = acc[x][y][1] = 0.0;
                 }
             const bool okd = df_wait(g.flagsL + (int64_t)c * g.nb + c, g.ctrl, g.info, g.spin_limit);
@@ -478,7 +488,6 @@ __global__ void __launch_bounds__(DF_THREADS, 2) chol_dataflow_kernel(DfArgs g) 
                 }
         }
         if (chain) {
-            double* Cd = g.K + (int64_t)idx * PB * (g.ld + 1);          // diagonal tile (idx, idx)
             double* Wd = g.W + (int64_t)idx * PB * (g.ldw + 1);
             df_stamp(g.trace, idx, 3);
             if (idx > 0) {
@@ -502,9 +511,8 @@ __global__ void __launch_bounds__(DF_THREADS, 2) chol_dataflow_kernel(DfArgs g) 
 #pragma unroll
                 for (int y = 0; y < 4; y++) {
                     const int r = wm + x * 32 + gq, cc = wn + y * 16 + tq * 2;
-                    const double2 v = *reinterpret_cast<const double2*>(Cd + (int64_t)r * g.ld + cc);
-                    Xs[r * DF_LDT + cc] = v.x - acc2[x][y][0];
-                    Xs[r * DF_LDT + cc + 1] = v.y - acc2[x][y][1];
+                    Xs[r * DF_LDT + cc] = -acc2[x][y][0];             // S = A_dd - sum (acc2 started at -A_dd)
+                    Xs[r * DF_LDT + cc + 1] = -acc2[x][y][1];
                 }
             if (idx > 0) {                            // publish the sub-diagonal tile before the long factor step
                 __threadfence();

@@ -160,3 +160,32 @@ def test_sweep_and_generic_kernels_agree(n, A, seed, on_grid):
     assert abs(loss - ocov.compute_loss(opv, truth)) <= 1e-9 * abs(loss)
     _, mv_o, idx_o = ocov.compute_max_var(olv, truth, var)
     assert np.array_equal(a["amax_idx"], idx_o)
+
+
+def test_packed_partitions_and_packed_results_match_the_plain_path():
+    """N > 1 plumbing on one GPU: partitions that arrive as packed device buffers (sharding.broadcast_partitions ->
+    PackedPartition) and results that leave as one packed copy (results_to_host / gather_results_to_host) give exactly
+    what BoundedVoronoi objects and per-tensor copies give."""
+    import torch
+    from mfgp_coverage_b200 import _coverage as cv
+    from mfgp_coverage_b200 import sharding
+    from mfgp_coverage_b200 import simulator as sim
+    xy, f, truth, seeds = _setup(64, 16, 6, True)
+    rng = np.random.default_rng(11)
+    mu = torch.from_numpy(f + 0.1 * rng.standard_normal(f.size)).cuda()
+    var = torch.from_numpy(rng.random(f.size)).cuda()
+    cen = synth.agents(16, 77)
+    bbox = ocov.bounding_box_of(xy)
+    g = cv.CoverageGrid(xy, f)
+    lv, pv = sim.voronoi_bounded(cen, bbox), sim.voronoi_bounded(seeds, bbox)
+    plain = g.assign_reduce(lv, pv, w=mu, var=var)
+    ref = {k: plain[k].cpu().numpy().copy() for k in ("cent", "amax_val", "amax_idx", "lossp")}
+    pk_p, pk_l = sharding.broadcast_partitions([seeds, cen], bbox, g.device)
+    assert isinstance(pk_p, cv.PackedPartition) and len(pk_p) == len(pv) and pk_p.seeds_inside == pv.seeds_inside
+    assert np.array_equal(pk_l.areas(), lv.areas()) and np.array_equal(pk_p.areas(), pv.areas())
+    host = sharding.gather_results_to_host(g.assign_reduce(pk_l, pk_p, w=mu, var=var))
+    for k in ref:
+        assert np.array_equal(host[k], ref[k]), k
+    host2 = cv.CoverageGrid.results_to_host(plain)
+    for k in ref:
+        assert np.array_equal(host2[k], ref[k]), k
