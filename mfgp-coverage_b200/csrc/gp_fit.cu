@@ -73,7 +73,7 @@ constexpr int PLD = PB + 1;
 
 __device__ __forceinline__ void potrf_diag_body(const double* src, int64_t lds, double* A, int64_t ld,
                                                 double* __restrict__ Winv, int64_t ldw, int32_t* __restrict__ info, int jblk) {
-    __shared__ double colA[2][PB], colB[2][PB], rowA[2][PB], rowB[2][PB];
+    __shared__ double2 colAB[2][PB], rowAB[2][PB];     // (.x, .y) = (column j0, column j1) of S / (row j0, row j1) of M
     __shared__ double piv[3][PB / 2];     // a, b, c of every pivot block
     __shared__ double fin[3][PB / 2];     // 1/sqrt(a), 1/sqrt(c - b^2/a), b/a
     __shared__ int bad;
@@ -95,17 +95,21 @@ __device__ __forceinline__ void potrf_diag_body(const double* src, int64_t lds, 
         for (int jp = 0; jp < 8; jp++) {
             const int k = jb * 8 + jp, j0 = 2 * k, j1 = j0 + 1, jj0 = 2 * jp, buf = k & 1;
             if ((tc & 14) == jj0) {          // owners of columns j0 (tc even) and j1 (tc odd); rows above are never read
-                double* dst = (tc & 1) ? colB[buf] : colA[buf];
+                double* dst = reinterpret_cast<double*>(colAB[buf]) + (tc & 1);
 #pragma unroll
-                for (int a = 0; a < 4; a++) dst[ti + 16 * a] = s[a][jb];
+                for (int a = 0; a < 4; a++) dst[2 * (ti + 16 * a)] = s[a][jb];
             }
             if ((ti & 14) == jj0) {          // owners of rows j0, j1 of M
-                double* dst = (ti & 1) ? rowB[buf] : rowA[buf];
+                double* dst = reinterpret_cast<double*>(rowAB[buf]) + (ti & 1);
 #pragma unroll
-                for (int b = 0; b < 4; b++) dst[tc + 16 * b] = m[jb][b];
+                for (int b = 0; b < 4; b++) dst[2 * (tc + 16 * b)] = m[jb][b];
             }
             __syncthreads();
-            double pa = colA[buf][j0], pb = colA[buf][j1], pc = colB[buf][j1];
+            const double2* col = colAB[buf];
+            const double2* row = rowAB[buf];
+            double pa = col[j0].x;
+            const double2 p1 = col[j1];
+            double pb = p1.x, pc = p1.y;
             double det = fma(pa, pc, -(pb * pb));
             if (!(pa > 0.0) || !(det > 0.0)) {          // uniform
                 if (tid == 0 && !bad) {
@@ -121,30 +125,30 @@ __device__ __forceinline__ void potrf_diag_body(const double* src, int64_t lds, 
 #pragma unroll
             for (int a = 0; a < 4; a++) {
                 if (a < jb) continue;                       // rows of earlier 16-groups are final
-                const double x1 = colA[buf][ti + 16 * a], x2 = colB[buf][ti + 16 * a];
-                t1[a] = fma(qa, x1, qb * x2);
-                t2[a] = fma(qb, x1, qc * x2);
+                const double2 x = col[ti + 16 * a];
+                t1[a] = fma(qa, x.x, qb * x.y);
+                t2[a] = fma(qb, x.x, qc * x.y);
             }
 #pragma unroll
             for (int b = 0; b < 4; b++) {
                 if (b < jb) continue;                       // columns of earlier 16-groups are final
-                const double y1 = colA[buf][tc + 16 * b], y2 = colB[buf][tc + 16 * b];
+                const double2 y = col[tc + 16 * b];
                 const bool live = tc + 16 * b > j1;         // only columns right of the pair change
 #pragma unroll
                 for (int a = 0; a < 4; a++) {
                     if (a < b) continue;                    // register groups strictly above the diagonal are never read
-                    if (live) s[a][b] = fma(-t1[a], y1, fma(-t2[a], y2, s[a][b]));
+                    if (live) s[a][b] = fma(-t1[a], y.x, fma(-t2[a], y.y, s[a][b]));
                 }
             }
 #pragma unroll
             for (int b = 0; b < 4; b++) {
                 if (b > jb) continue;                       // rows j0, j1 of M are zero right of column j1
-                const double z1 = rowA[buf][tc + 16 * b], z2 = rowB[buf][tc + 16 * b];
+                const double2 z = row[tc + 16 * b];
 #pragma unroll
                 for (int a = 0; a < 4; a++) {
                     if (a < jb) continue;                   // rows of earlier 16-groups are final
                     const bool live = ti + 16 * a > j1;     // only rows below the pair change
-                    if (live) m[a][b] = fma(-t1[a], z1, fma(-t2[a], z2, m[a][b]));
+                    if (live) m[a][b] = fma(-t1[a], z.x, fma(-t2[a], z.y, m[a][b]));
                 }
             }
         }

@@ -13,6 +13,7 @@ coverage algorithms use: construction from arrays, `hyp` assigned after construc
 Every arithmetic step runs on the GPU through the C-ABI in include/mfgp_b200.h; there is no CPU fallback.
 """
 import copy
+import weakref
 
 import numpy as np
 import torch
@@ -55,14 +56,30 @@ def prior_variance(params):
 
 
 
+_PINNED_BUDGET = 1 << 30        # page-locked bytes that results handed to the caller may hold at any one time
+_pinned_live = [0]
+
+
 def _to_host_pinned(t):
-    """Device tensor -> host tensor in page-locked memory (asynchronous DMA at PCIe speed instead of a staged pageable
+    """Device tensor -> numpy array in page-locked memory (asynchronous DMA at PCIe speed instead of a staged pageable
     copy).  The block comes from torch's caching host allocator and goes back to it when the numpy array that wraps it is
     garbage collected, so a loop that calls predict() every iteration reuses the same pages; and because the memory is
-    page-locked, handing the array back to compute_centroids / compute_max_var uploads it by DMA as well."""
+    page-locked, handing the array back to compute_centroids / compute_max_var uploads it by DMA as well.  A caller that
+    keeps many results alive falls back to ordinary pageable arrays once _PINNED_BUDGET bytes are outstanding."""
+    nbytes = t.numel() * t.element_size()
+    if _pinned_live[0] + nbytes > _PINNED_BUDGET:
+        return t.cpu().numpy()
     h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
     h.copy_(t, non_blocking=True)
-    return h
+    a = h.numpy()                       # shares (and keeps alive) the page-locked block; views of `a` keep `a` alive
+    _pinned_live[0] += nbytes
+    weakref.finalize(a, _release_pinned, nbytes)
+    return a
+
+
+def _release_pinned(nbytes):
+    _pinned_live[0] -= nbytes
+
 
 class _GPBase:
     raw_means = False     # set True to reproduce runs logged with the pre-exp() mean convention
@@ -128,7 +145,7 @@ class _GPBase:
         mu, var = self._dev.posterior(xs_dev, axes=axes)
         mu_h, var_h = _to_host_pinned(mu), _to_host_pinned(var)
         torch.cuda.current_stream(mu.device).synchronize()
-        return mu_h.numpy().reshape(-1, 1), var_h.numpy()
+        return mu_h.reshape(-1, 1), var_h
 
     def factor(self):
         """Lower Cholesky factor L[N,N] as a host array (the reference keeps it in `self.L`)."""
