@@ -70,3 +70,60 @@ def test_runner_rejects_unknown_algorithm():
     from mfgp_coverage_b200 import runner
     with pytest.raises(ValueError):
         runner.run_sim(("x", "nonsense", 0, 1, 2, None, 0.1, None, None, False, None, True))
+
+
+def test_cell_areas_and_flat_layout_match_the_reference_formula():
+    """BoundedVoronoi.areas(): the vectorised shoelace equals simulator.py:127-136 per cell (1e-15 absolute: the two dot
+    products of the reference are summed in a different order); flat() lists every cell's vertices in region order."""
+    from mfgp_coverage_b200 import _coverage as cv
+    bb = np.array([0.0, 1.0, 0.0, 1.0])
+    for A, seed in ((1, 0), (2, 1), (8, 2), (64, 3), (200, 4)):
+        v = cv.BoundedVoronoi(synth.agents(A, seed), bb)
+        seeds, poly, off = v.flat()
+        assert seeds.shape == (A, 2) and off[0] == 0 and off[-1] == poly.shape[0]
+        ref = np.empty(A)
+        for i in range(A):
+            pts = v.vertices[v.filtered_regions[i]]
+            assert np.array_equal(poly[off[i]:off[i + 1]], pts)
+            x, y = pts[:, 0], pts[:, 1]
+            ref[i] = 0.5 * np.abs(np.dot(x, np.roll(y, 1)) - np.dot(y, np.roll(x, 1)))          # poly_area, simulator.py:127-136
+        assert np.max(np.abs(v.areas() - ref)) <= 4e-15
+        assert abs(v.areas().sum() - 1.1 * 1.1) <= 1e-12       # the cells tile the box inflated by eps/2 on every side
+
+
+def test_packed_partition_round_trip_and_seed_summary():
+    """The packed cell buffer that travels between ranks (sharding.broadcast_partitions) carries exactly the partition."""
+    import torch
+    from mfgp_coverage_b200 import _coverage as cv
+    bb = np.array([0.0, 1.0, 0.0, 1.0])
+    for A, seed in ((1, 5), (5, 6), (64, 7)):
+        pts = synth.agents(A, seed)
+        v = cv.BoundedVoronoi(pts, bb)
+        n = cv.partition_doubles(A)
+        assert n % 2 == 0                                      # the next partition in a shared buffer stays 16-byte aligned
+        buf = np.full(n, np.nan)
+        cv.pack_partition(v, buf)
+        assert np.all(np.isfinite(buf))
+        p = cv.PackedPartition(torch.from_numpy(buf), A, v.seeds_inside)
+        seeds, poly, off = v.flat()
+        assert len(p) == A and p.nvert == cv.partition_capacity(A) >= off[-1]
+        assert np.array_equal(p.seeds.numpy(), seeds.reshape(-1)) and np.array_equal(p.off.numpy()[:A + 1], off)
+        assert np.array_equal(p.poly.numpy()[:2 * off[-1]], poly.reshape(-1)) and np.array_equal(p.areas(), v.areas())
+        assert cv.seeds_summary(pts, bb) == (A, v.seeds_inside)
+    outside = np.array([[0.5, 0.5], [1.05, 0.5], [3.0, 3.0]])     # one seed in the cushion, one beyond it (dropped)
+    v = cv.BoundedVoronoi(outside, bb)
+    assert cv.seeds_summary(outside, bb) == (len(v), v.seeds_inside) == (2, False)
+
+
+def test_host_argmax_merge_matches_the_tensor_version():
+    import torch
+    from mfgp_coverage_b200 import sharding
+    rng = np.random.default_rng(8)
+    vals = rng.integers(0, 4, size=(5, 40)).astype(np.float64)          # many ties across ranks
+    idxs = rng.permutation(5 * 40).reshape(5, 40).astype(np.int64)
+    idxs[rng.random((5, 40)) < 0.3] = -1                                # empty cells on some ranks
+    idxs[:, 7] = -1                                                     # ... and one cell empty everywhere
+    bv, bi = sharding.merge_argmax_host(vals, idxs)
+    tv, ti = sharding.merge_argmax(torch.from_numpy(vals), torch.from_numpy(idxs))
+    assert np.array_equal(bv, tv.numpy()) and np.array_equal(bi, ti.numpy())
+    assert bi[7] == -1 and bv[7] == -np.inf
