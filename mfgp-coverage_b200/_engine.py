@@ -432,7 +432,7 @@ class DeviceGP:
 
     def _fit_and_posterior_fused(self, axes, plan, mu, var, q_out):
         """From-scratch iteration on a tensor grid in one pass: K -> (L, diagonal-block inverses) with the right-hand sides
-        [B_L | B_H | y - mean] forward-substituted on the side stream -> steps 4-6 (see include/mfgp_b200.h)."""
+        [B | y - mean] forward-substituted inside the same tile-dataflow kernel -> steps 4-6 (see include/mfgp_b200.h)."""
         lib = nat.lib()
         st = nat.stream_ptr()
         pp = ctypes.byref(self.pstruct)

@@ -703,12 +703,13 @@ extern "C" int mfgp_cholesky(double* K, int64_t npad, int64_t ld, double* W, int
 }
 
 // Cholesky of K fused with the forward substitution of R right-hand sides: on return K holds L (lower), the diagonal
-// blocks of W hold the inverses of L's diagonal blocks, and Bm[npad, R] holds L^-1 Bm.  The panel chain (potrf -> panel solve
-// -> trailing update: three small dependent kernels per 64 columns) leaves most of the GPU idle, so the right-hand-side
-// work -- Y_j = W_jj B_j and B_{>j} -= L_{>j,j} Y_j, one pair of tile GEMMs per panel, N^2 R / 2 MACs in total -- runs on
-// the caller's stream while the chain itself runs on an internal high-priority stream, and hides behind it: the explicit inverse (mfgp_tri_inverse) and the product W B are not needed
-// by the factored posterior.  Cross-stream order: Y_j waits for potrf(j), the update waits for the panel solve of panel j;
-// the caller's stream waits for the side stream before the call returns control of Bm.
+// blocks of W hold the inverses of L's diagonal blocks, and Bm[npad, R] holds L^-1 Bm; the explicit inverse
+// (mfgp_tri_inverse) and the product W B are not needed by the factored posterior.  Default: ONE launch of
+// chol_dataflow_kernel (above).  What follows is the older launch-per-panel implementation, kept behind MFGP_CHOL=chain
+// for A/B timing: the panel chain (potrf -> panel solve -> trailing update: three small dependent kernels per 64 columns)
+// runs on an internal high-priority stream, the right-hand-side work -- Y_j = W_jj B_j and B_{>j} -= L_{>j,j} Y_j, one pair
+// of tile GEMMs per panel -- on the caller's stream; Y_j waits for potrf(j), the update for the panel solve of panel j, and
+// the caller's stream waits for the internal stream before the call returns control of Bm.
 namespace {
 struct SideStream {
     cudaStream_t st = nullptr;
@@ -774,7 +775,7 @@ extern "C" int mfgp_cholesky_solve(double* K, int64_t npad, int64_t ld, double* 
             if (rc) return rc;
             MFGP_CUDA_CHECK(cudaEventRecord(side->ev_trsm[j & 1], st));
         }
-        // side stream: Y_j = W_jj B_j (in place: every CTA reads only the column tile it writes)
+        // caller's stream: Y_j = W_jj B_j (in place: every CTA reads only the column tile it writes)
         double* Bj = Bm + (int64_t)j * PB * ldb;
         MFGP_CUDA_CHECK(cudaStreamWaitEvent(sb, side->ev_potrf[j & 1], 0));
         GemmArgs y{};

@@ -118,7 +118,7 @@ def test_short_length_scale_keeps_the_dense_kernel():
 @pytest.mark.parametrize("nx,ny,N,multi", [(64, 64, 300, True), (96, 80, 700, True), (72, 72, 200, False)])
 def test_fused_fit_and_factored_posterior(nx, ny, N, multi):
     """Deferred fit: refactor(check=False) only marks the factor stale, the factored posterior then runs
-    mfgp_cholesky_solve (right-hand sides forward-substituted on the side stream) -- no explicit inverse, no W B product.
+    mfgp_cholesky_solve (right-hand sides forward-substituted inside the tiled Cholesky kernel) -- no explicit inverse, no W B product.
     Same results as the oracle; L and the lazily completed inverse W are right as well."""
     from mfgp_coverage_b200._coverage import CoverageGrid
     xy = _tensor_grid(nx, ny)
@@ -136,7 +136,7 @@ def test_fused_fit_and_factored_posterior(nx, ny, N, multi):
     grid = CoverageGrid(xy)
     mu = torch.empty(grid.G, dtype=torch.float64, device=grid.device)
     var = torch.empty(grid.G, dtype=torch.float64, device=grid.device)
-    for rep in range(2):                                   # twice: the side stream / events are reused
+    for rep in range(2):                                   # twice: the per-device flag scratch is reused
         e.K.fill_(float("nan")); e.W.fill_(float("nan")); e.z.fill_(float("nan"))      # nothing may survive from the first fit
         e.refactor(check=False)
         assert e._dirty
