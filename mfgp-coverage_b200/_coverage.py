@@ -406,31 +406,28 @@ class CoverageGrid:
 # ---- host finishing of the per-cell partial sums (O(A) scalar work, same arithmetic as the reference) ----------------
 
 def loss_from_partials(lossp, areas):
-    """simulator.py:215-219: sum_i mean(point_loss_i) * area_i, accumulated in cell order."""
-    loss = 0
+    """simulator.py:215-219: sum_i mean(point_loss_i) * area_i, accumulated in cell order (the per-cell terms are formed
+    elementwise, the running sum is sequential: the same IEEE operations in the same order as the reference's loop)."""
     with np.errstate(invalid="ignore", divide="ignore"):
-        for i in range(lossp.shape[0]):
-            loss += (lossp[i, 0] / lossp[i, 1]) * areas[i]
-    return loss
+        terms = (lossp[:, 0] / lossp[:, 1]) * np.asarray(areas, dtype=np.float64)[:lossp.shape[0]]
+    loss = 0.0
+    for t in terms.tolist():
+        loss += t
+    return np.float64(loss) if lossp.shape[0] else 0
 
 
 def centroids_from_partials(cent, areas, xmin, xmax, ymin, ymax):
-    """simulator.py:256-271: c = (mean(w p) area) / (mean(w) area), clamped to the grid's extent."""
+    """simulator.py:256-271: c = (mean(w p) area) / (mean(w) area), clamped to the grid's extent.  Elementwise over the
+    cells: per cell exactly the reference's operations (mean, times area, divide, the two one-sided clamps per coordinate)."""
     A = cent.shape[0]
-    out = np.empty((A, 2))
+    ar = np.asarray(areas, dtype=np.float64)[:A]
     with np.errstate(invalid="ignore", divide="ignore"):
-        for i in range(A):
-            n = cent[i, 3]
-            f_integral = (cent[i, 0] / n) * areas[i]
-            w_integral = np.array([cent[i, 1] / n, cent[i, 2] / n]) * areas[i]
-            c = w_integral / f_integral
-            if c[0] < xmin:
-                c[0] = xmin
-            if c[0] > xmax:
-                c[0] = xmax
-            if c[1] < ymin:
-                c[1] = ymin
-            if c[1] > ymax:
-                c[1] = ymax
-            out[i] = c
-    return out
+        n = cent[:, 3]
+        f_integral = (cent[:, 0] / n) * ar
+        cx = ((cent[:, 1] / n) * ar) / f_integral
+        cy = ((cent[:, 2] / n) * ar) / f_integral
+        cx = np.where(cx < xmin, xmin, cx)           # a NaN centroid (empty cell) fails both tests and stays NaN
+        cx = np.where(cx > xmax, xmax, cx)
+        cy = np.where(cy < ymin, ymin, cy)
+        cy = np.where(cy > ymax, ymax, cy)
+    return np.column_stack((cx, cy))

@@ -127,3 +127,32 @@ def test_host_argmax_merge_matches_the_tensor_version():
     tv, ti = sharding.merge_argmax(torch.from_numpy(vals), torch.from_numpy(idxs))
     assert np.array_equal(bv, tv.numpy()) and np.array_equal(bi, ti.numpy())
     assert bi[7] == -1 and bv[7] == -np.inf
+
+
+def test_vectorised_finishing_is_bitwise_the_reference_loop():
+    """loss_from_partials / centroids_from_partials are elementwise over the cells; they must give bit for bit what the
+    reference's per-cell statements give (simulator.py:215-219, :256-271), empty cells (0/0 -> NaN) included."""
+    from mfgp_coverage_b200 import _coverage as cv
+    rng = np.random.default_rng(0)
+    for _ in range(100):
+        A = int(rng.integers(1, 70))
+        cent = np.column_stack((rng.normal(0.3, 1.0, A), rng.normal(0, 1, A), rng.normal(0, 1, A),
+                                rng.integers(0, 50, A).astype(float)))
+        lossp = np.column_stack((rng.random(A), rng.integers(0, 50, A).astype(float)))
+        areas = rng.random(A)
+        loss = 0
+        ref = np.empty((A, 2))
+        with np.errstate(invalid="ignore", divide="ignore"):
+            for i in range(A):
+                loss += (lossp[i, 0] / lossp[i, 1]) * areas[i]                     # mean(point_loss) * area
+                n = cent[i, 3]
+                f_integral = (cent[i, 0] / n) * areas[i]
+                c = (np.array([cent[i, 1] / n, cent[i, 2] / n]) * areas[i]) / f_integral
+                c[0] = 0.0 if c[0] < 0.0 else c[0]
+                c[0] = 1.0 if c[0] > 1.0 else c[0]
+                c[1] = 0.0 if c[1] < 0.0 else c[1]
+                c[1] = 1.0 if c[1] > 1.0 else c[1]
+                ref[i] = c
+        got = cv.loss_from_partials(lossp, areas)
+        assert (np.isnan(got) and np.isnan(loss)) or got == loss
+        assert np.array_equal(cv.centroids_from_partials(cent, areas, 0.0, 1.0, 0.0, 1.0), ref, equal_nan=True)
