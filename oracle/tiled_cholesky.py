@@ -1,0 +1,109 @@
+"""TEST INFRASTRUCTURE ONLY (see oracle/__init__.py): numpy restatements of the two algorithms behind mfgp_cholesky /
+mfgp_cholesky_solve (mfgp-coverage_b200/csrc/gp_fit.cu), used by tests/ to pin their logic on the CPU.  The reference itself
+calls np.linalg.cholesky (gaussian_process.py:254, :529); these functions describe HOW the device reaches the same factor.
+
+1. pair_step_factor: the 64x64 diagonal-block factorisation of potrf_diag_body -- two columns per step, 2x2 pivot blocks,
+   one reciprocal per step, the inverse carried along, square roots only in the final per-pair scaling.
+2. task_order / task_dependencies: the ticket order of chol_dataflow_kernel and what every task waits for; a task must only
+   depend on smaller tickets (that is the kernel's deadlock-freedom argument).
+"""
+import numpy as np
+
+
+def pair_step_factor(S):
+    """Lower Cholesky factor L and W = L^-1 of the SPD matrix S (even order), and LAPACK's `info` (0, or 1 + index of the
+    first non-positive pivot; on failure L = W = I as the kernel leaves them).  Follows potrf_diag_body step by step:
+    U keeps the UNSCALED columns, M (identity at the start) takes the same eliminations; with P = [[a, b], [b, c]] the pivot
+    block of columns (j0, j1):  S -= (U P^-1) U^T  right of the pair,  M -= (U P^-1) [M_j0; M_j1]  below it; afterwards, with
+    C = chol(P):  L[:, pair] = U C^-T,  W[pair, :] = C^-1 M[pair, :]."""
+    S = np.array(S, dtype=np.float64)
+    n = S.shape[0]
+    assert n % 2 == 0
+    U = np.tril(S)
+    M = np.eye(n)
+    piv = np.empty((n // 2, 3))
+    info = 0
+    for k in range(n // 2):
+        j0, j1 = 2 * k, 2 * k + 1
+        a, b, c = U[j0, j0], U[j1, j0], U[j1, j1]
+        det = a * c - b * b
+        if not (a > 0.0) or not (det > 0.0):
+            if info == 0:
+                info = (j1 if a > 0.0 else j0) + 1
+            a, b, c, det = 1.0, 0.0, 1.0, 1.0
+        piv[k] = a, b, c
+        idet = 1.0 / det
+        qa, qb, qc = c * idet, -b * idet, a * idet                     # P^-1
+        u1, u2 = U[:, j0].copy(), U[:, j1].copy()
+        t1 = qa * u1 + qb * u2                                           # T = U P^-1
+        t2 = qb * u1 + qc * u2
+        rows = np.arange(n) > j1
+        cols = np.arange(n) > j1
+        U[np.ix_(rows, cols)] -= np.outer(t1[rows], u1[cols]) + np.outer(t2[rows], u2[cols])
+        U[:] = np.tril(U)                                                # only the lower triangle is kept
+        M[rows, :] -= np.outer(t1[rows], M[j0, :]) + np.outer(t2[rows], M[j1, :])
+    if info:
+        return np.eye(n), np.eye(n), info
+    L = np.empty_like(U)
+    W = np.empty_like(M)
+    for k in range(n // 2):
+        a, b, c = piv[k]
+        r1 = 1.0 / np.sqrt(a)
+        g = b * r1 * r1
+        r2 = 1.0 / np.sqrt(c - g * b)
+        j0, j1 = 2 * k, 2 * k + 1
+        L[:, j0] = U[:, j0] * r1
+        L[:, j1] = (U[:, j1] - g * U[:, j0]) * r2
+        W[j0, :] = M[j0, :] * r1
+        W[j1, :] = (M[j1, :] - g * M[j0, :]) * r2
+    return np.tril(L), np.tril(W), 0
+
+
+# ---- ticket order of the tile-dataflow kernel ---------------------------------------------------------------------------
+# Task kinds (chol_dataflow_kernel): ("chain", d): sub-diagonal tile (d, d-1) + diagonal tile (d, d) + factor/inverse of block d;
+# ("L", i, c): tile (i, c) of L, i >= c + 2;  ("Y", c, r): tile (c, r) of Y = L^-1 B.
+
+def task_order(nb, nr):
+    """Tasks in ticket order: chain 0; then per block column c: chain c+1, the tiles (i, c) with i >= c+2, the Y tiles of
+    block row c."""
+    order = [("chain", 0)]
+    for c in range(nb):
+        if c + 1 < nb:
+            order.append(("chain", c + 1))
+        order += [("L", i, c) for i in range(c + 2, nb)]
+        order += [("Y", c, r) for r in range(nr)]
+    return order
+
+
+def producer_of(tile):
+    """The task that sets the ready flag of a tile: ("Ltile", i, c) with i > c, ("W", c) (diagonal block c factored and
+    inverted), ("Ytile", k, r)."""
+    if tile[0] == "W":
+        return ("chain", tile[1])
+    if tile[0] == "Ytile":
+        return ("Y", tile[1], tile[2])
+    _, i, c = tile
+    return ("chain", i) if i == c + 1 else ("L", i, c)
+
+
+def task_dependencies(task):
+    """Every flag a task waits for, as tiles (see producer_of)."""
+    if task[0] == "chain":
+        d = task[1]
+        if d == 0:
+            return []
+        deps = [("W", d - 1)]
+        for k in range(d - 1):                                            # accumulates L_dk L_(d-1)k^T and L_dk L_dk^T
+            deps += [("Ltile", d, k), ("Ltile", d - 1, k)]
+        return deps
+    if task[0] == "L":
+        _, i, c = task
+        deps = [("W", c)]
+        for k in range(c):
+            deps += [("Ltile", i, k), ("Ltile", c, k)]
+        return deps
+    _, c, r = task
+    deps = [("W", c)]
+    for k in range(c):
+        deps += [("Ltile", c, k), ("Ytile", k, r)]
+    return deps

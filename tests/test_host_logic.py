@@ -156,3 +156,56 @@ def test_vectorised_finishing_is_bitwise_the_reference_loop():
         got = cv.loss_from_partials(lossp, areas)
         assert (np.isnan(got) and np.isnan(loss)) or got == loss
         assert np.array_equal(cv.centroids_from_partials(cent, areas, 0.0, 1.0, 0.0, 1.0), ref, equal_nan=True)
+
+
+def test_pair_step_factorisation_matches_lapack():
+    """The algorithm of potrf_diag_body (two columns per step, 2x2 pivot blocks, inverse carried along), restated in numpy:
+    same factor and inverse as LAPACK, same failing-pivot index."""
+    import scipy.linalg as sl
+    from oracle import tiled_cholesky as tc
+    rng = np.random.default_rng(4)
+    for n, cond in ((2, 10.0), (8, 1e3), (64, 1e6), (64, 1e10)):
+        q, _ = np.linalg.qr(rng.standard_normal((n, n)))
+        S = (q * np.logspace(0, -np.log10(cond), n)) @ q.T
+        S = 0.5 * (S + S.T)
+        L, W, info = tc.pair_step_factor(S)
+        Lref = np.linalg.cholesky(S)
+        assert info == 0
+        assert np.max(np.abs(L - Lref)) <= 1e-15 * cond * np.max(np.abs(Lref)) + 1e-15
+        assert np.max(np.abs(W @ Lref - np.eye(n))) <= 1e-14 * cond
+    S = (q * np.logspace(0, -3, 64)) @ q.T
+    Lr = np.linalg.cholesky(S)
+    for bad in (0, 5, 38, 63):
+        Sb = S.copy()
+        Sb[bad, bad] = float(np.sum(Lr[bad, :bad] ** 2)) - 0.25
+        _, info_ref = sl.lapack.dpotrf(Sb, lower=1)
+        L, W, info = tc.pair_step_factor(Sb)
+        assert info == info_ref == bad + 1 and np.array_equal(L, np.eye(64)) and np.array_equal(W, np.eye(64))
+
+
+def test_dataflow_ticket_order_is_topological():
+    """chol_dataflow_kernel hands out tasks through a ticket counter and a task spins on the ready flags of other tasks; it
+    cannot deadlock iff every task only waits for tasks with a SMALLER ticket (a CTA holds a ticket only while resident).
+    Checked exhaustively on the restated order for every size up to 20 block columns; the count matches the kernel's."""
+    from oracle import tiled_cholesky as tc
+    for nb in range(1, 21):
+        for nr in (0, 1, 3):
+            order = tc.task_order(nb, nr)
+            assert len(order) == len(set(order)) == nb + (nb - 1) * (nb - 2) // 2 + nb * nr       # a.total in gp_fit.cu
+            ticket = {t: k for k, t in enumerate(order)}
+            produced = set()
+            for t in order:
+                for dep in tc.task_dependencies(t):
+                    assert ticket[tc.producer_of(dep)] < ticket[t], (nb, nr, t, dep)
+                    assert dep in produced, (nb, nr, t, dep)
+                if t[0] == "chain":
+                    produced.add(("W", t[1]))
+                    if t[1] > 0:
+                        produced.add(("Ltile", t[1], t[1] - 1))
+                elif t[0] == "L":
+                    produced.add(("Ltile", t[1], t[2]))
+                else:
+                    produced.add(("Ytile", t[1], t[2]))
+            # every tile of L below the diagonal, every diagonal block and every Y tile is produced exactly once
+            assert produced == {("W", c) for c in range(nb)} | {("Ltile", i, c) for c in range(nb) for i in range(c + 1, nb)} | \
+                {("Ytile", c, r) for c in range(nb) for r in range(nr)}
