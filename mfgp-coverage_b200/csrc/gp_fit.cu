@@ -265,6 +265,7 @@ __device__ __forceinline__ bool df_wait(const int* f, int* ctrl, int32_t* info, 
         }
     }
     ok = __shfl_sync(0xffffffffu, ok, 0);
+    __syncwarp();                 // shuffles carry no memory ordering: order lane 0's acquire before the other lanes' tile loads
     return ok != 0;
 }
 
@@ -350,6 +351,7 @@ __global__ void __launch_bounds__(DF_THREADS, 2) chol_dataflow_kernel(DfArgs g) 
             if ((s & 1) == 0) {                       // first slab of a 64-wide k tile: its producers must be done
                 int ready = (lane == 0) ? pre : 0;    // (the early sample hides the L2 round trip of the common, ready case)
                 ready = __shfl_sync(0xffffffffu, ready, 0);
+                __syncwarp();                         // (memory ordering for the early-sampled acquire, see df_wait)
                 if (!ready) {
                     ok = df_wait(fa + kt, g.ctrl, g.info, g.spin_limit) && ok;
                     ok = df_wait(fb + (int64_t)kt * fbs, g.ctrl, g.info, g.spin_limit) && ok;
