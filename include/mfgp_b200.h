@@ -49,7 +49,7 @@ const char* mfgp_last_error(void);          /* text of the last CUDA error seen 
 int64_t mfgp_debug_chol_trace(int64_t* out, int64_t max_tasks);   /* diagnostics: per-chain-task time stamps of the tiled Cholesky (MFGP_DF_TRACE=1) */
 int64_t mfgp_launch_count(void);            /* kernels launched by this library since load (bench.py's gpu_launches) */
 int64_t mfgp_npad(int64_t n);               /* n rounded up to MFGP_TILE (at least MFGP_TILE)  */
-int64_t mfgp_workspace_bytes(int64_t npad); /* scratch needed by mfgp_cholesky / mfgp_tri_inverse */
+int64_t mfgp_workspace_bytes(int64_t npad); /* scratch needed by mfgp_cholesky / mfgp_tri_inverse (one buffer serves both) */
 
 /* ---- GP fit: replaces SFGP.updt_info gaussian_process.py:229-255 and MFGP.updt_info :493-529 ------------------- */
 
@@ -62,7 +62,10 @@ int mfgp_build_train_cov(const double* Xt, int64_t NL, int64_t NH, const mfgp_pa
 
 /* In-place lower Cholesky of K[npad,ld] (np.linalg.cholesky at gaussian_process.py:254 / :529).  Blocked, trailing
  * updates on FP64 tensor cores (DMMA).  Also writes the inverses of the 64x64 diagonal blocks into the diagonal
- * blocks of W (may be NULL).  `info` (device int32): 0, or 1 + index of the first non-positive pivot. */
+ * blocks of W (may be NULL).  `info` (device int32): 0, 1 + index of the first non-positive pivot, or -1 (internal error:
+ * the tile-dataflow kernel gave up waiting for a tile).  `work`: mfgp_workspace_bytes(npad) bytes; it holds the kernel's
+ * ticket counter and per-tile ready flags, so calls that use DIFFERENT work buffers may overlap freely (other streams,
+ * other host threads); a work buffer must not be shared by calls that can run concurrently. */
 int mfgp_cholesky(double* K, int64_t npad, int64_t ld, double* W, int64_t ldw, int32_t* info, void* work,
                   void* stream);
 
@@ -153,9 +156,9 @@ int64_t mfgp_factored_workspace_bytes(int64_t npad, int64_t ncols, int64_t ny, i
 /* Fused fit + factored posterior (the from-scratch iteration of the reference, simulator.py:888-892, on a tensor grid):
  *   mfgp_build_train_cov  ->  mfgp_factored_prepare (B = [B_L | B_H | y - mean], mfgp_factored_rhs_cols columns)
  *   ->  mfgp_cholesky_solve (K -> L in place, diagonal-block inverses into W, Ball -> L^-1 Ball: ONE persistent
- *       tile-dataflow kernel, chol_dataflow_kernel in csrc/gp_fit.cu; its ready flags live in a per-device scratch buffer,
- *       so calls on one device must not overlap in time.  MFGP_CHOL=chain in the environment selects the older
- *       launch-per-panel implementation)
+ *       tile-dataflow kernel, chol_dataflow_kernel in csrc/gp_fit.cu; its ticket counter and ready flags live in `work`,
+ *       mfgp_cholesky_solve_workspace_bytes(npad, R) bytes of caller memory, so the call is re-entrant per work buffer.
+ *       MFGP_CHOL=chain in the environment selects the older launch-per-panel implementation)
  *   ->  mfgp_posterior_grid_factored_solved (steps 4-6; z_out receives the whitened observations).
  * Neither the explicit inverse (mfgp_tri_inverse) nor the product W B is formed; run mfgp_tri_inverse afterwards only if W
  * is needed (dense posterior, mfgp_cholesky_append, choi_greedy).  Same geometry / order arguments and the same `work`
@@ -165,8 +168,9 @@ int mfgp_factored_prepare(const double* ux, int64_t nx, const double* uy, int64_
                           const double* Xt, const double* y, int64_t NL, int64_t NH, int64_t npad, const mfgp_params* p_host,
                           int64_t rxL, int64_t ryL, int64_t rxH, int64_t ryH, double xlo, double xhi, double ylo, double yhi,
                           int64_t chunk_cols, double* Ball, int64_t ldB, void* work, int64_t work_bytes, void* stream);
+int64_t mfgp_cholesky_solve_workspace_bytes(int64_t npad, int64_t R);
 int mfgp_cholesky_solve(double* K, int64_t npad, int64_t ld, double* W, int64_t ldw, int32_t* info, double* Bm, int64_t ldb,
-                        int64_t R, void* stream);
+                        int64_t R, void* work, int64_t work_bytes, void* stream);
 int mfgp_posterior_grid_factored_solved(const double* ux, int64_t nx, const double* uy, int64_t ny, int64_t ix0, int64_t ncols,
                                         const double* Xt, int64_t NL, int64_t NH, int64_t npad, const mfgp_params* p_host,
                                         int64_t rxL, int64_t ryL, int64_t rxH, int64_t ryH, double xlo, double xhi, double ylo,

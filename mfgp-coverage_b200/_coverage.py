@@ -19,6 +19,18 @@ TIE_TOL = 1e-9       # |d2_second - d2_best| below which the exact crossings tes
 AMAX_REL = 1e-10     # arg-max ties: |dvar| <= AMAX_REL * (k(0) - var) counts as tied, first index wins (argmax.cuh)
 
 
+def host_array_key(arr):
+    """Identity key of a host array for the device-copy caches (predict's x_star, the free coverage functions' truth_arr):
+    address, shape, strides plus a checksum of a strided sample of <= 257 rows, so an in-place edit of the array between
+    two calls is noticed in all but contrived cases (O(1): the reference's loops pass the same million-point array every
+    iteration)."""
+    arr = np.asarray(arr)
+    n = arr.shape[0] if arr.ndim else 0
+    step = max(1, n // 256)
+    sample = arr[::step]
+    return (arr.__array_interface__["data"][0], arr.shape, arr.strides, hash(sample.tobytes()))
+
+
 def in_box(points, bounding_box):
     """simulator.py:139-151."""
     return np.logical_and(np.logical_and(bounding_box[0] - EPS <= points[:, 0], points[:, 0] <= bounding_box[1] + EPS),
@@ -385,6 +397,8 @@ class CoverageGrid:
                                        nat.ptr(info), nat.ptr(lloyd_vor.flag) if Ac else None,
                                        nat.ptr(loss_vor.flag) if Ap else None, nat.ptr(out), nat.stream_ptr()), "cov_finish")
         h = out.cpu().numpy()
+        if h[1 + 4 * Ac] < 0:       # info = -1: the tiled Cholesky gave up waiting for a tile (internal error, not a pivot)
+            raise RuntimeError("libmfgp_b200: the tiled Cholesky kernel gave up waiting for a tile (internal error)")
         if h[1 + 4 * Ac] != 0:
             raise np.linalg.LinAlgError(f"Matrix is not positive definite (pivot {int(h[1 + 4 * Ac]) - 1})")
         if h[2 + 4 * Ac] != 0 or h[3 + 4 * Ac] != 0:

@@ -6,6 +6,7 @@ Cholesky factor K[npad,npad], its inverse W[npad,npad], scaled coordinates Tt[np
 streams only.  Layout notes are in DESIGN.md ("Data layout in HBM").
 """
 import ctypes
+import itertools
 
 import numpy as np
 import torch
@@ -35,7 +36,11 @@ def chebyshev_order(length_scale, lo, hi, centre_lo, centre_hi, tol=5e-15, rmax=
 class TensorAxes:
     """Axis values of a tensor-product grid `[[x, y] for x in ux for y in uy]` (x-major, distribution.py:337-339)."""
 
+    _uids = itertools.count(1)
+
     def __init__(self, ux_host, uy_host, device):
+        # never reused, unlike id(): plan / order caches key on it, so a collected grid cannot alias a new one
+        self.uid = next(TensorAxes._uids)
         self.ux_host = np.ascontiguousarray(ux_host, dtype=np.float64)
         self.uy_host = np.ascontiguousarray(uy_host, dtype=np.float64)
         self.nx, self.ny = int(len(ux_host)), int(len(uy_host))
@@ -95,6 +100,7 @@ class DeviceGP:
         self._dirty = False           #   a factored posterior then fuses fit + forward substitution (mfgp_cholesky_solve)
         self._w_partial = False       # True: W holds only the diagonal-block inverses (mfgp_tri_inverse still to run)
         self._fB = None               # right-hand-side matrix of the fused fit
+        self._cwork = None            # ticket counter + tile flags of mfgp_cholesky_solve (caller-owned, per model)
         self._fG = None               # per-column Gram matrices G'(ix) [ncols, 64, 64] and z^T Y: state of the incremental
         self._fHz = None              #   factored update (mfgp_posterior_grid_factored_update)
         self._fstate = None           # (plan key, epoch, rows covered, output buffer key) the stores are valid for
@@ -308,7 +314,7 @@ class DeviceGP:
             plan = self._factored_plan(axes, int(g_lo), G)
         if plan is not None:
             # state key of the stored G'(ix): same geometry / orders / buffers, only appended rows since
-            skey = (id(axes), int(g_lo), G, plan["rxL"], plan["ryL"], plan["rxH"], plan["ryH"], key)
+            skey = (axes.uid, int(g_lo), G, plan["rxL"], plan["ryL"], plan["rxH"], plan["ryH"], key)
             if self._dirty:
                 self._fit_and_posterior_fused(axes, plan, mu, var, q_out)
             else:
@@ -361,7 +367,7 @@ class DeviceGP:
         xlo, xhi, ylo, yhi = axes.xlo, axes.xhi, axes.ylo, axes.yhi
         t = self._training_range()
         c = self._forders
-        if c is not None and c[0] == (id(axes), p["l_L"], p["l_H"], p["multi"]) and c[1][0] <= t[0] and c[1][1] >= t[1] \
+        if c is not None and c[0] == (axes.uid, p["l_L"], p["l_H"], p["multi"]) and c[1][0] <= t[0] and c[1][1] >= t[1] \
                 and c[1][2] <= t[2] and c[1][3] >= t[3]:
             return c[2]
         mx, my = 0.05 * (xhi - xlo), 0.05 * (yhi - ylo)            # a margin, so that a few new samples do not invalidate it
@@ -375,7 +381,7 @@ class DeviceGP:
             ryL = chebyshev_order(p["l_L"], ylo, yhi, hull[2], hull[3])
             ok = rxL is not None and ryL is not None
         orders = (rxL, ryL, rxH, ryH) if ok else None
-        self._forders = ((id(axes), p["l_L"], p["l_H"], p["multi"]), hull, orders)
+        self._forders = ((axes.uid, p["l_L"], p["l_H"], p["multi"]), hull, orders)
         return orders
 
     def _factored_plan(self, axes, g_lo, G):
@@ -389,7 +395,7 @@ class DeviceGP:
         dense = 0.5 * G * N * N
         if self.factored_min_gain > 0 and dense < 4e9:      # the dense kernel needs well under a millisecond: no plan
             return None
-        key = (id(axes), g_lo, G, self.npad, p["l_L"], p["l_H"], p["multi"], self.factored_min_gain)
+        key = (axes.uid, g_lo, G, self.npad, p["l_L"], p["l_H"], p["multi"], self.factored_min_gain)
         orders = self._cheb_orders(axes, p)
         if self._fplan is not None and self._fplan[0] == key and self._fplan[2] == orders:
             return self._fplan[1]
@@ -453,8 +459,12 @@ class DeviceGP:
         ev = self.profile_events          # bench.py: (start, stop) CUDA events around the dominant kernel
         if ev is not None:
             ev[0].record()
+        cneed = int(lib.mfgp_cholesky_solve_workspace_bytes(self.cap, R))
+        if self._cwork is None or self._cwork.numel() * 8 < cneed:
+            self._cwork = torch.empty(cneed // 8 + 8, dtype=torch.float64, device=self.device)
         nat.check(lib.mfgp_cholesky_solve(nat.ptr(self.K), npad, ld, nat.ptr(self.W), ld, nat.ptr(self.info),
-                                          nat.ptr(self._fB), R, R, st), "mfgp_cholesky_solve")
+                                          nat.ptr(self._fB), R, R, nat.ptr(self._cwork), self._cwork.numel() * 8, st),
+                  "mfgp_cholesky_solve")
         if ev is not None:
             ev[1].record()
         Gs, Hs = self._factored_stores(plan)

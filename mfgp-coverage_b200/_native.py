@@ -69,8 +69,9 @@ SIGNATURES = {
     "mfgp_factored_prepare": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_int64,
                                       c_int64, c_int64, POINTER(MfgpParams), c_int64, c_int64, c_int64, c_int64, c_double,
                                       c_double, c_double, c_double, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p]),
+    "mfgp_cholesky_solve_workspace_bytes": (c_int64, [c_int64, c_int64]),
     "mfgp_cholesky_solve": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int64,
-                                    c_void_p]),
+                                    c_void_p, c_int64, c_void_p]),
     "mfgp_posterior_grid_factored_solved": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64,
                                                     c_int64, c_int64, POINTER(MfgpParams), c_int64, c_int64, c_int64,
                                                     c_int64, c_double, c_double, c_double, c_double, c_int64, c_void_p,

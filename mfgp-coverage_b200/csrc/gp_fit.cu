@@ -578,9 +578,21 @@ extern "C" int64_t mfgp_npad(int64_t n) {
     return (n + MFGP_TILE - 1) / MFGP_TILE * MFGP_TILE;
 }
 
-extern "C" int64_t mfgp_workspace_bytes(int64_t npad) {
-    return npad * npad * 2 + (int64_t)PB * PB * 8 + 256;   // T blocks of the inverse (npad^2/4 doubles) + one 64x64 block
+// Synchronisation scratch of chol_dataflow_kernel: ticket counter + abort flag, per-SM pause flags, one ready flag per
+// 64x64 tile of L and of Y.  It lives in CALLER-provided workspace (so two models may factorise concurrently on different
+// streams of one device, and nothing is allocated inside the library).
+static int64_t df_scratch_ints(int64_t npad, int64_t R) {
+    const int64_t nb = npad / PB, nr = (R + PB - 1) / PB;
+    return 2 + 1024 + nb * nb + nb * nr;
 }
+static int64_t df_scratch_bytes(int64_t npad, int64_t R) { return (df_scratch_ints(npad, R) * 4 + 255) / 256 * 256; }
+
+extern "C" int64_t mfgp_workspace_bytes(int64_t npad) {
+    // T blocks of the inverse (npad^2/4 doubles) + one 64x64 block, then the tile flags of mfgp_cholesky
+    return npad * npad * 2 + (int64_t)PB * PB * 8 + 256 + df_scratch_bytes(npad, 0);
+}
+
+extern "C" int64_t mfgp_cholesky_solve_workspace_bytes(int64_t npad, int64_t R) { return df_scratch_bytes(npad, R); }
 
 extern "C" int mfgp_build_train_cov(const double* Xt, int64_t NL, int64_t NH, const mfgp_params* p_host, double* K,
                                     int64_t npad, int64_t ld, double* Tt, void* stream) {
@@ -595,11 +607,9 @@ extern "C" int mfgp_build_train_cov(const double* Xt, int64_t NL, int64_t NH, co
 }
 
 namespace {
-struct DfScratch {
+struct DfScratch {        // diagnostics (MFGP_DF_TRACE=1) and the cached SM count only; no data-path state
     long long* trace = nullptr;
     int trace_nb = 0;
-    int* buf = nullptr;
-    int64_t ints = 0;
     int sms = 0;
 };
 DfScratch g_df[16];
@@ -613,31 +623,21 @@ bool use_panel_chain() {
 }
 
 // One launch: K -> L (lower, in place), diagonal blocks of W -> inverses of L's diagonal blocks, Bm[npad, R] -> L^-1 Bm
-// (R may be 0).  The ready flags live in a per-device scratch buffer: calls on one device must not overlap in time.
+// (R may be 0).  The ready flags live in `scratch` (df_scratch_bytes(npad, R) bytes of caller workspace), zeroed on `st`.
 int chol_dataflow(double* K, int64_t npad, int64_t ld, double* W, int64_t ldw, int32_t* info, double* Bm, int64_t ldb, int64_t R,
-                  cudaStream_t st) {
+                  int* scratch, cudaStream_t st) {
     int dev = 0;
     MFGP_CUDA_CHECK(cudaGetDevice(&dev));
-    if (dev < 0 || dev >= 16) return MFGP_ERR_INVALID;
+    if (dev < 0 || dev >= 16 || !scratch) return MFGP_ERR_INVALID;
     DfScratch& sc = g_df[dev];
     const int nb = (int)(npad / PB), nr = (int)(R / PB);
-    const int64_t need = 2 + 1024 + (int64_t)nb * nb + (int64_t)nb * nr;      // ctrl, per-SM pause flags, tile flags
-    if (need > sc.ints) {
-        if (sc.buf) {
-            MFGP_CUDA_CHECK(cudaDeviceSynchronize());
-            MFGP_CUDA_CHECK(cudaFree(sc.buf));
-            sc.buf = nullptr;
-        }
-        int64_t n = need > (1 << 18) ? need : (1 << 18);
-        MFGP_CUDA_CHECK(cudaMalloc(&sc.buf, n * sizeof(int)));
-        sc.ints = n;
-        MFGP_CUDA_CHECK(cudaDeviceGetAttribute(&sc.sms, cudaDevAttrMultiProcessorCount, dev));
-    }
-    MFGP_CUDA_CHECK(cudaMemsetAsync(sc.buf, 0, need * sizeof(int), st));
+    const int64_t need = df_scratch_ints(npad, R);                            // ctrl, per-SM pause flags, tile flags
+    if (!sc.sms) MFGP_CUDA_CHECK(cudaDeviceGetAttribute(&sc.sms, cudaDevAttrMultiProcessorCount, dev));
+    MFGP_CUDA_CHECK(cudaMemsetAsync(scratch, 0, need * sizeof(int), st));
     MFGP_CUDA_CHECK(cudaMemsetAsync(info, 0, sizeof(int32_t), st));
     DfArgs a{};
     a.K = K; a.ld = ld; a.W = W; a.ldw = ldw; a.Bm = Bm; a.ldb = ldb; a.nb = nb; a.nr = nr; a.info = info;
-    a.ctrl = sc.buf; a.pause = sc.buf + 2; a.flagsL = sc.buf + 1026; a.flagsY = sc.buf + 1026 + (int64_t)nb * nb;
+    a.ctrl = scratch; a.pause = scratch + 2; a.flagsL = scratch + 1026; a.flagsY = scratch + 1026 + (int64_t)nb * nb;
     a.total = nb + (nb - 1) * (nb - 2) / 2 + nb * nr;     // nb chain tasks, the tiles two or more below the diagonal, Y tiles
     static const bool want_trace = [] { const char* e = getenv("MFGP_DF_TRACE"); return e && atoi(e) != 0; }();
     if (want_trace) {
@@ -676,7 +676,12 @@ extern "C" int mfgp_cholesky(double* K, int64_t npad, int64_t ld, double* W, int
     if (!W && !work) return MFGP_ERR_INVALID;
     if (W && ldw < npad) return MFGP_ERR_INVALID;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (W && !use_panel_chain()) return chol_dataflow(K, npad, ld, W, ldw, info, nullptr, 0, 0, st);
+    if (W && !use_panel_chain()) {
+        if (!work) return MFGP_ERR_INVALID;
+        // the tile flags sit behind the part of `work` that mfgp_tri_inverse uses (see mfgp_workspace_bytes)
+        int* scratch = reinterpret_cast<int*>(static_cast<char*>(work) + npad * npad * 2 + (int64_t)PB * PB * 8 + 256);
+        return chol_dataflow(K, npad, ld, W, ldw, info, nullptr, 0, 0, scratch, st);
+    }
     MFGP_CUDA_CHECK(cudaMemsetAsync(info, 0, sizeof(int32_t), st));
     const int nb = (int)(npad / PB);
     constexpr int POTRF_SMEM = 0;   // the factor + inverse sweep lives in registers and static shared memory
@@ -745,11 +750,14 @@ int side_for_current_device(SideStream** out) {
 }  // namespace
 
 extern "C" int mfgp_cholesky_solve(double* K, int64_t npad, int64_t ld, double* W, int64_t ldw, int32_t* info, double* Bm,
-                                   int64_t ldb, int64_t R, void* stream) {
+                                   int64_t ldb, int64_t R, void* work, int64_t work_bytes, void* stream) {
     if (!K || !W || !info || !Bm || npad <= 0 || npad % MFGP_TILE || ld < npad || ldw < npad || R <= 0 || R % GT || ldb < R)
         return MFGP_ERR_INVALID;
     cudaStream_t caller = static_cast<cudaStream_t>(stream);
-    if (!use_panel_chain()) return chol_dataflow(K, npad, ld, W, ldw, info, Bm, ldb, R, caller);
+    if (!use_panel_chain()) {
+        if (!work || work_bytes < df_scratch_bytes(npad, R)) return MFGP_ERR_INVALID;
+        return chol_dataflow(K, npad, ld, W, ldw, info, Bm, ldb, R, static_cast<int*>(work), caller);
+    }
     SideStream* side = nullptr;
     int rcs = side_for_current_device(&side);
     if (rcs) return rcs;

@@ -48,33 +48,77 @@ def run_sim(args):
     return loss_log_t, agent_log_t, sample_log_t
 
 
-def _worker(rank, world, args, seed, queue):
-    import torch
-    torch.cuda.set_device(rank % max(torch.cuda.device_count(), 1))
-    if seed is not None:
-        random.seed(seed + rank)
-    out = {}
-    for i in range(rank, len(args), world):       # run-sharding: simulation i goes to worker i mod world
-        out[i] = run_sim(args[i])
-    queue.put(out)
+def _worker(rank, world, args, seed, queue, fn=None):
+    """One worker process.  Whatever happens it reports exactly once: ("ok", rank, results) or ("error", rank, exception,
+    traceback text) -- Pool.map in the reference (runner.py:131-141) re-raises worker exceptions in the parent too."""
+    import traceback
+    try:
+        import torch
+        if torch.cuda.is_available():
+            torch.cuda.set_device(rank % max(torch.cuda.device_count(), 1))
+        if seed is not None:
+            random.seed(seed + rank)
+        out = {}
+        for i in range(rank, len(args), world):       # run-sharding: simulation i goes to worker i mod world
+            out[i] = (fn or run_sim)(args[i])
+        queue.put(("ok", rank, out))
+    except BaseException as e:                         # noqa: BLE001 -- everything goes home, the parent re-raises
+        tb = traceback.format_exc()
+        try:
+            queue.put(("error", rank, e, tb))
+        except Exception:                              # the exception itself does not pickle
+            queue.put(("error", rank, RuntimeError(f"{type(e).__name__}: {e}"), tb))
 
 
-def _map_sims(args, n_processors, seed=None):
+class WorkerError(RuntimeError):
+    """A simulation worker died without reporting (killed, segfault, CUDA abort)."""
+
+
+def _map_sims(args, n_processors, seed=None, fn=None):
+    """Pool.map(run_sim, args) of the reference (runner.py:131-141) over `n_processors` spawned workers (one per GPU slot).
+    A worker exception is re-raised here; a worker that dies silently raises WorkerError.  `fn`: stand-in for run_sim
+    (a picklable top-level function), used by the tests."""
     if n_processors <= 1:
         if seed is not None:
             random.seed(seed)
-        return [run_sim(a) for a in args]
+        return [(fn or run_sim)(a) for a in args]
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     queue = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, n_processors, args, seed, queue)) for r in range(n_processors)]
+    procs = [ctx.Process(target=_worker, args=(r, n_processors, args, seed, queue, fn)) for r in range(n_processors)]
     for p in procs:
         p.start()
-    merged = {}
-    for _ in procs:
-        merged.update(queue.get())
+    merged, failure, reported = {}, None, set()
+    import queue as _q
+    while len(reported) < len(procs) and failure is None:
+        try:
+            msg = queue.get(timeout=1.0)
+        except _q.Empty:
+            # liveness: a child that exited without putting its report (hard crash) must not block the parent forever
+            dead = [r for r, p in enumerate(procs) if r not in reported and p.exitcode is not None]
+            if dead:
+                try:
+                    msg = queue.get(timeout=2.0)      # its report may still be in flight through the pipe
+                except _q.Empty:
+                    failure = WorkerError(f"simulation worker {dead[0]} exited with code {procs[dead[0]].exitcode} "
+                                          "without reporting")
+                    break
+            else:
+                continue
+        reported.add(msg[1])
+        if msg[0] == "ok":
+            merged.update(msg[2])
+        else:
+            failure = msg[2]
+            failure.worker_traceback = msg[3]
+    if failure is not None:
+        for p in procs:
+            if p.is_alive():
+                p.terminate()
     for p in procs:
         p.join()
+    if failure is not None:
+        raise failure
     return [merged[i] for i in range(len(args))]
 
 

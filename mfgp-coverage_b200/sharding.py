@@ -25,21 +25,37 @@ def shard_bounds(G, world, rank):
     return lo, lo + base + (1 if rank < extra else 0)
 
 
-def merge_argmax(vals, idxs):
-    """vals[R, A], idxs[R, A] (global indices, -1 = empty) -> per-cell (max value, LOWEST index attaining it)."""
-    vals = vals.clone()
-    big = torch.iinfo(torch.int64).max
-    empty = idxs < 0
-    vals[empty] = -float("inf")
-    best = vals.max(dim=0).values
-    cand = torch.where((vals == best.unsqueeze(0)) & ~empty, idxs, torch.full_like(idxs, big))
-    bidx = cand.min(dim=0).values
-    bidx = torch.where(bidx == big, torch.full_like(bidx, -1), bidx)
-    return best, bidx
+def merge_argmax(vals, idxs, k0=0.0, rel=0.0):
+    """vals[R, A], idxs[R, A] (global indices, -1 = empty) -> per-cell (max value, LOWEST index attaining it).
+
+    Ranks are folded in rank order with the SAME tie rule the kernels apply inside a shard (csrc/argmax.cuh,
+    argmax_combine): two candidates are tied when they differ by at most rel * (k0 - smaller value) -- a tolerance
+    relative to the variance reduction -- and a tie goes to the lower global index, carrying the larger value.  With
+    rel = 0 this is the plain first-index arg-max.  Without it two mirror-image grid points ~1e-16 apart that land on
+    different ranks would be resolved by rounding noise instead of by index (the single-GPU kernel and the reference
+    pick the lower index)."""
+    R = vals.shape[0]
+    bv, bi = vals[0].clone(), idxs[0].clone()
+    for r in range(1, R):
+        v, i = vals[r], idxs[r]
+        a_empty, b_empty = bi < 0, i < 0
+        lo = torch.minimum(bv, v)
+        tol = torch.clamp(rel * (k0 - lo), min=0.0) if rel > 0.0 else torch.zeros_like(lo)
+        d = bv - v
+        take_b = (-d > tol)
+        tie = ~(d > tol) & ~take_b
+        nv = torch.where(take_b, v, torch.where(tie, torch.maximum(bv, v), bv))
+        ni = torch.where(take_b, i, torch.where(tie, torch.minimum(bi, i), bi))
+        nv = torch.where(b_empty, bv, torch.where(a_empty, v, nv))
+        ni = torch.where(b_empty, bi, torch.where(a_empty, i, ni))
+        bv, bi = nv, ni
+    bv = torch.where(bi < 0, torch.full_like(bv, -float("inf")), bv)
+    return bv, bi
 
 
-def allreduce_partials(res, group=None):
-    """In-place combination of the outputs of CoverageGrid.assign_reduce across ranks."""
+def allreduce_partials(res, group=None, amax_k0=0.0, amax_rel=0.0):
+    """In-place combination of the outputs of CoverageGrid.assign_reduce across ranks.  (amax_k0, amax_rel): the arg-max
+    tie rule the kernels were called with (see merge_argmax)."""
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
         return res
     world = dist.get_world_size(group)
@@ -53,27 +69,35 @@ def allreduce_partials(res, group=None):
         idxs = [torch.empty_like(res["amax_idx"]) for _ in range(world)]
         dist.all_gather(vals, res["amax_val"].contiguous(), group=group)
         dist.all_gather(idxs, res["amax_idx"].contiguous(), group=group)
-        v, i = merge_argmax(torch.stack(vals).reshape(world, A), torch.stack(idxs).reshape(world, A))
+        v, i = merge_argmax(torch.stack(vals).reshape(world, A), torch.stack(idxs).reshape(world, A), amax_k0, amax_rel)
         res["amax_val"].copy_(v)
         res["amax_idx"].copy_(i)
     return res
 
 
-def merge_argmax_host(vals, idxs):
+def merge_argmax_host(vals, idxs, k0=0.0, rel=0.0):
     """numpy twin of merge_argmax for host-side merging: vals[R, A], idxs[R, A] (int64, -1 = empty)."""
-    vals = np.array(vals, dtype=np.float64)
+    vals = np.asarray(vals, dtype=np.float64)
     idxs = np.asarray(idxs, dtype=np.int64)
-    big = np.iinfo(np.int64).max
-    empty = idxs < 0
-    vals[empty] = -np.inf
-    best = vals.max(axis=0)
-    cand = np.where((vals == best[None, :]) & ~empty, idxs, big)
-    bidx = cand.min(axis=0)
-    bidx[bidx == big] = -1
-    return best, bidx
+    bv, bi = vals[0].copy(), idxs[0].copy()
+    for r in range(1, vals.shape[0]):
+        v, i = vals[r], idxs[r]
+        a_empty, b_empty = bi < 0, i < 0
+        with np.errstate(invalid="ignore"):
+            lo = np.minimum(bv, v)
+            tol = np.maximum(rel * (k0 - lo), 0.0) if rel > 0.0 else np.zeros_like(lo)
+            d = bv - v
+            take_b = -d > tol
+            tie = ~(d > tol) & ~take_b
+        nv = np.where(take_b, v, np.where(tie, np.maximum(bv, v), bv))
+        ni = np.where(take_b, i, np.where(tie, np.minimum(bi, i), bi))
+        bv = np.where(b_empty, bv, np.where(a_empty, v, nv))
+        bi = np.where(b_empty, bi, np.where(a_empty, i, ni))
+    bv = np.where(bi < 0, -np.inf, bv)
+    return bv, bi
 
 
-def gather_results_to_host(res, group=None):
+def gather_results_to_host(res, group=None, amax_k0=0.0, amax_rel=0.0):
     """Global per-cell results of CoverageGrid.assign_reduce on the host with ONE collective and ONE device->host copy:
     the packed result buffers of all ranks are all-gathered, copied home, and combined there -- partial sums added in rank
     order (deterministic), arg-max pairs merged with the lowest-global-index rule.  Every rank gets the same dict of numpy
@@ -105,7 +129,8 @@ def gather_results_to_host(res, group=None):
         for r in range(world):                                   # rank order: the same sum on every rank, every run
             cent += a[r, :4 * Ac].reshape(Ac, 4)
         out["cent"] = cent
-        out["amax_val"], out["amax_idx"] = merge_argmax_host(a[:, 4 * Ac:5 * Ac], a[:, 5 * Ac:6 * Ac].copy().view(np.int64))
+        out["amax_val"], out["amax_idx"] = merge_argmax_host(a[:, 4 * Ac:5 * Ac], a[:, 5 * Ac:6 * Ac].copy().view(np.int64),
+                                                             amax_k0, amax_rel)
     if Ap:
         lossp = np.zeros((Ap, 2))
         for r in range(world):
@@ -149,6 +174,7 @@ def broadcast_factor(engine, src=0, group=None):
     """Broadcast the fitted factor state (W, z, Tt) of `engine` (a DeviceGP) from rank `src` to all ranks."""
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
         return
+    engine.ensure_factor()        # a fused / deferred fit leaves only the diagonal-block inverses in W: complete it first
     n = engine.npad
     for t in (engine.W[:n], engine.z[:n], engine.Tt[:n]):
         dist.broadcast(t, src=src, group=group)
@@ -172,4 +198,4 @@ class ShardedGrid:
                                   base_index=self.lo, axes=axes)
 
     def assign_reduce(self, *a, **k):
-        return allreduce_partials(self.local.assign_reduce(*a, **k), self.group)
+        return allreduce_partials(self.local.assign_reduce(*a, **k), self.group, k.get("amax_k0", 0.0), k.get("amax_rel", 0.0))

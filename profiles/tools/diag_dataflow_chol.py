@@ -21,6 +21,7 @@ Lref = np.linalg.cholesky(Kh)
 RS = tuple(int(x) for x in sys.argv[2].split(",")) if len(sys.argv) > 2 else (0, 64, 1792)
 for R in RS:
     B0 = torch.randn(npad, max(R, 64), dtype=torch.float64, device="cuda")
+    sw = torch.empty(int(lib.mfgp_cholesky_solve_workspace_bytes(npad, max(R, 64))) // 8 + 8, dtype=torch.float64, device="cuda")
     ts = []
     for rep in range(4):
         build(); B = B0.clone(); torch.cuda.synchronize()
@@ -28,7 +29,7 @@ for R in RS:
         if R == 0:
             rc = lib.mfgp_cholesky(nat.ptr(e.K), npad, ld, nat.ptr(e.W), ld, nat.ptr(e.info), nat.ptr(e.work), st)
         else:
-            rc = lib.mfgp_cholesky_solve(nat.ptr(e.K), npad, ld, nat.ptr(e.W), ld, nat.ptr(e.info), nat.ptr(B), R, R, st)
+            rc = lib.mfgp_cholesky_solve(nat.ptr(e.K), npad, ld, nat.ptr(e.W), ld, nat.ptr(e.info), nat.ptr(B), R, R, nat.ptr(sw), sw.numel() * 8, st)
         b.record(); torch.cuda.synchronize(); ts.append(a.elapsed_time(b))
     L = np.tril(e.K.view(ld, ld)[:npad, :npad].cpu().numpy())
     errL = np.max(np.abs(L - Lref)) / np.max(np.abs(Lref))

@@ -14,6 +14,7 @@ lib = nat.lib(); st = nat.stream_ptr(); pp = ctypes.byref(e.pstruct); npad, ld =
 def ev(): return torch.cuda.Event(enable_timing=True)
 for R in (0, 64, 1024, 2560):
     B = torch.randn(npad * max(R, 64), dtype=torch.float64, device="cuda")
+    sw = torch.empty(int(lib.mfgp_cholesky_solve_workspace_bytes(npad, max(R, 64))) // 8 + 8, dtype=torch.float64, device="cuda")
     for rep in range(3):
         lib.mfgp_build_train_cov(nat.ptr(e.Xt), e.NL, e.NH, pp, nat.ptr(e.K), npad, ld, nat.ptr(e.Tt), st)
         torch.cuda.synchronize()
@@ -22,7 +23,7 @@ for R in (0, 64, 1024, 2560):
         if R == 0:
             lib.mfgp_cholesky(nat.ptr(e.K), npad, ld, nat.ptr(e.W), ld, nat.ptr(e.info), nat.ptr(e.work), st)
         else:
-            lib.mfgp_cholesky_solve(nat.ptr(e.K), npad, ld, nat.ptr(e.W), ld, nat.ptr(e.info), nat.ptr(B), R, R, st)
+            lib.mfgp_cholesky_solve(nat.ptr(e.K), npad, ld, nat.ptr(e.W), ld, nat.ptr(e.info), nat.ptr(B), R, R, nat.ptr(sw), sw.numel() * 8, st)
         b.record(); t1 = time.perf_counter()
         torch.cuda.synchronize()
     print(f"N={N} R={R}: host launch {1e3*(t1-t0):.2f} ms, device {a.elapsed_time(b):.2f} ms")

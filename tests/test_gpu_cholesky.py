@@ -44,8 +44,9 @@ def _run(K_host, R, seed=0):
     if R:
         B0 = np.random.default_rng(seed).standard_normal((npad, R))
         B = torch.from_numpy(B0).cuda()
-        nat.check(lib.mfgp_cholesky_solve(nat.ptr(K), npad, npad, nat.ptr(W), npad, nat.ptr(info), nat.ptr(B), R, R, st),
-                  "mfgp_cholesky_solve")
+        sw = torch.empty(int(lib.mfgp_cholesky_solve_workspace_bytes(npad, R)) // 8 + 8, dtype=torch.float64, device="cuda")
+        nat.check(lib.mfgp_cholesky_solve(nat.ptr(K), npad, npad, nat.ptr(W), npad, nat.ptr(info), nat.ptr(B), R, R,
+                                          nat.ptr(sw), sw.numel() * 8, st), "mfgp_cholesky_solve")
     else:
         B = None
         nat.check(lib.mfgp_cholesky(nat.ptr(K), npad, npad, nat.ptr(W), npad, nat.ptr(info), nat.ptr(work), st), "mfgp_cholesky")

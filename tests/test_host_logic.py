@@ -129,6 +129,41 @@ def test_host_argmax_merge_matches_the_tensor_version():
     assert bi[7] == -1 and bv[7] == -np.inf
 
 
+def test_cross_rank_argmax_merge_applies_the_kernels_tie_rule():
+    """Two mirror-image grid points whose variances differ by rounding noise (~1e-16) and that land on DIFFERENT ranks
+    must resolve to the lower global index, as csrc/argmax.cuh does inside a shard; the 1-ulp plateaus of k0 - q far
+    from all data must NOT be merged (tolerance relative to the variance reduction)."""
+    import torch
+    from mfgp_coverage_b200 import sharding
+    k0, rel = 1.7, 1e-10
+    # (a) symmetric-prior case: rank 1 holds the larger value by one ulp, rank 0 the lower index
+    v0 = 0.9
+    vals = np.array([[v0, 0.5], [np.nextafter(v0, 2.0), 0.7]])
+    idxs = np.array([[10, 11], [900, 901]], dtype=np.int64)
+    bv, bi = sharding.merge_argmax_host(vals, idxs, k0, rel)
+    assert bi.tolist() == [10, 901] and bv[0] == vals[1, 0] and bv[1] == 0.7       # tie -> low index, larger value carried
+    tv, ti = sharding.merge_argmax(torch.from_numpy(vals), torch.from_numpy(idxs), k0, rel)
+    assert np.array_equal(bv, tv.numpy()) and np.array_equal(bi, ti.numpy())
+    assert sharding.merge_argmax_host(vals, idxs)[1].tolist() == [900, 901]            # plain rule: noise decides
+    # (b) plateau case: var = k0 - q with q ~ ulp(k0); one ulp apart is NOT a tie
+    top = k0 - 2.0 ** -52
+    vals = np.array([[np.nextafter(top, 0.0)], [top]])
+    idxs = np.array([[3], [4000]], dtype=np.int64)
+    assert sharding.merge_argmax_host(vals, idxs, k0, rel)[1].tolist() == [4000]
+    # the fold equals the kernel's pairwise rule on random data with many near-ties and empty cells
+    rng = np.random.default_rng(2)
+    base = rng.random(64)
+    vals = base[None, :] + rng.integers(-2, 3, size=(8, 64)) * 1e-16
+    idxs = rng.permutation(8 * 64).reshape(8, 64).astype(np.int64)
+    idxs[rng.random((8, 64)) < 0.25] = -1
+    bv, bi = sharding.merge_argmax_host(vals, idxs, k0, rel)
+    tv, ti = sharding.merge_argmax(torch.from_numpy(vals), torch.from_numpy(idxs), k0, rel)
+    assert np.array_equal(bi, ti.numpy()) and np.array_equal(bv, tv.numpy())
+    for a in range(64):
+        live = idxs[:, a] >= 0
+        assert bi[a] == (idxs[live, a].min() if live.any() else -1)                    # all within tolerance: lowest index
+
+
 def test_vectorised_finishing_is_bitwise_the_reference_loop():
     """loss_from_partials / centroids_from_partials are elementwise over the cells; they must give bit for bit what the
     reference's per-cell statements give (simulator.py:215-219, :256-271), empty cells (0/0 -> NaN) included."""
@@ -209,3 +244,34 @@ def test_dataflow_ticket_order_is_topological():
             # every tile of L below the diagonal, every diagonal block and every Y tile is produced exactly once
             assert produced == {("W", c) for c in range(nb)} | {("Ltile", i, c) for c in range(nb) for i in range(c + 1, nb)} | \
                 {("Ytile", c, r) for c in range(nb) for r in range(nr)}
+
+
+# ---- runner._map_sims: the multi-process run-sharding path (reference runner.py:131-141) ------------------------------
+
+def _sim_ok(a):
+    return ([{"sim": a}], [], [])
+
+
+def _sim_raises(a):
+    if a == 3:
+        raise np.linalg.LinAlgError("Matrix is not positive definite (pivot 7)")
+    return ([{"sim": a}], [], [])
+
+
+def _sim_dies(a):
+    import os
+    if a == 2:
+        os._exit(17)              # hard crash: no report ever reaches the queue
+    return ([{"sim": a}], [], [])
+
+
+def test_map_sims_shards_runs_and_propagates_worker_failures():
+    from mfgp_coverage_b200 import runner
+    out = runner._map_sims(list(range(7)), 3, seed=1, fn=_sim_ok)
+    assert [o[0][0]["sim"] for o in out] == list(range(7))                 # original order, whatever worker ran what
+    with pytest.raises(np.linalg.LinAlgError, match="pivot 7"):            # Pool.map re-raises worker exceptions
+        runner._map_sims(list(range(7)), 3, fn=_sim_raises)
+    with pytest.raises(runner.WorkerError, match="exited with code 17"):   # ... and a dead worker must not hang the parent
+        runner._map_sims(list(range(7)), 3, fn=_sim_dies)
+    with pytest.raises(ValueError, match="Invalid simulation algorithm"):  # the real run_sim, failing before any GPU call
+        runner._map_sims([("o", "nonsense", 0, 1, 2, None, 0.1, None, None, False, None, False)] * 2, 2)
