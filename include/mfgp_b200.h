@@ -253,6 +253,21 @@ int64_t choi_greedy(const double* Xs, int64_t G, double* Vc, int64_t ldv, int64_
                     int64_t* picks_host,
                     void* work, int64_t work_bytes, void* stream);
 
+/* ---- Choi tour planner: replaces compute_sample_tsp simulator.py:415-454 ------------------------------------------ */
+
+/* Visiting order of every agent's sample points.  The reference calls mlrose.TSPOpt + mlrose.genetic_alg(mutation_prob=0.2,
+ * max_attempts=100, random_state=2) per cluster (:435-438); mlrose is an unpinned third-party host routine, so its tour
+ * order is not reproducible.  This entry minimises the same objective (length of the closed tour) deterministically:
+ * nearest-neighbour construction from point 0 of the cluster (ties -> lowest index), then best-improvement 2-opt with
+ * position 0 fixed (ties -> lowest (i, j)) until no segment reversal gains more than 1e-12.  One CTA per cluster, all
+ * clusters in one launch.  pts[n_total,2]: the clusters' points back to back; off[A+1]: cluster c owns points
+ * [off[c], off[c+1]); n_max = size of the largest cluster; order[n_total]: order[off[c] + k] = LOCAL index (within
+ * cluster c) of the k-th point of its tour; moves[A] (optional): 2-opt moves applied.  `work`: only read when
+ * n_max > 4096 (choi_tsp_workspace_bytes(n_total) bytes).  Bit-identical to the CPU statement oracle/tsp.py. */
+int64_t choi_tsp_workspace_bytes(int64_t n_total);
+int choi_tsp_tours(const double* pts, const int32_t* off, int64_t A, int64_t n_total, int64_t n_max, int32_t* order,
+                   int32_t* moves, void* work, int64_t work_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

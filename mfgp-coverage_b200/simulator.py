@@ -17,8 +17,9 @@ Deliberate differences from the reference (documented in DESIGN.md):
     `compute_max_var` accepts either.
   * optional keyword arguments `rng=` (object with .random(), default: the `random` module) and `noise_rng=`
     (numpy Generator, default: a fresh `np.random.default_rng()` per sample as in the reference) make runs replayable.
-  * the Choi TSP tour uses mlrose when it is importable and the cluster's own order otherwise (mlrose's GA is a
-    third-party host routine outside the hot path).
+  * the Choi TSP tour comes from a deterministic device planner (nearest neighbour + 2-opt, csrc/tsp.cu) instead of
+    mlrose's genetic algorithm, whose tours are not reproducible (unpinned third-party routine); MFGP_TSP=mlrose
+    selects mlrose when it is installed.
 """
 import copy
 import os
@@ -230,27 +231,57 @@ def compute_sample_clusters(vor, sample_points):
     return clusters
 
 
+# MFGP_TSP=mlrose (or simulator.TSP = "mlrose"): the reference's mlrose genetic algorithm, if mlrose is installed.
+TSP = os.environ.get("MFGP_TSP", "2opt")
+
+
+def plan_tours(clusters):
+    """Visiting order (index arrays) of every cluster: nearest-neighbour + best-improvement 2-opt on the device
+    (choi_tsp_tours, csrc/tsp.cu), all clusters of a period in one launch."""
+    lens = [int(c.shape[0]) for c in clusters]
+    n_total = sum(lens)
+    if n_total == 0:
+        return [np.empty(0, dtype=np.int64) for _ in clusters]
+    nat = cv.nat
+    nat.require_cuda()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    off = np.zeros(len(clusters) + 1, dtype=np.int32)
+    np.cumsum(lens, out=off[1:])
+    pts = np.ascontiguousarray(np.concatenate([np.asarray(c, dtype=np.float64).reshape(-1, 2) for c in clusters], axis=0))
+    d_pts = torch.from_numpy(pts).to(dev)
+    d_off = torch.from_numpy(off).to(dev)
+    d_ord = torch.empty(n_total, dtype=torch.int32, device=dev)
+    n_max = max(lens)
+    lib = nat.lib()
+    work = None
+    if n_max > 4096:
+        work = torch.empty(int(lib.choi_tsp_workspace_bytes(n_total)) // 8 + 8, dtype=torch.float64, device=dev)
+    nat.check(lib.choi_tsp_tours(nat.ptr(d_pts), nat.ptr(d_off), len(clusters), n_total, n_max, nat.ptr(d_ord), None,
+                                 nat.ptr(work), 0 if work is None else work.numel() * 8, nat.stream_ptr()), "choi_tsp_tours")
+    order = d_ord.cpu().numpy().astype(np.int64)
+    return [order[off[i]:off[i + 1]] for i in range(len(clusters))]
+
+
 def compute_sample_tsp(clusters):
-    """reference simulator.py:415-454.  mlrose's genetic algorithm when importable, the cluster's own order otherwise."""
-    try:
+    """reference simulator.py:415-454.  The reference's mlrose genetic algorithm (an unpinned third-party host routine
+    whose tours are not reproducible) is replaced by a deterministic planner for the same objective -- nearest neighbour
+    + 2-opt on the closed tour, on the device (see plan_tours); TSP = "mlrose" selects mlrose itself when installed."""
+    if TSP == "mlrose":
         import six
         sys.modules['sklearn.externals.six'] = six
         import mlrose
-    except Exception:
-        mlrose = None
-    tours = []
-    for cluster in clusters:
-        tour = np.empty((0, 2))
-        if cluster.shape[0] > 0:
-            if mlrose is not None:
+        tours = []
+        for cluster in clusters:
+            tour = np.empty((0, 2))
+            if cluster.shape[0] > 0:
                 coords_list = [tuple(coord) for coord in cluster]
                 problem = mlrose.TSPOpt(length=len(coords_list), coords=coords_list, maximize=False)
                 solution, _ = mlrose.genetic_alg(problem, mutation_prob=0.2, max_attempts=100, random_state=2)
                 tour = cluster[solution]
-            else:
-                tour = cluster
-        tours.append(tour)
-    return tours
+            tours.append(tour)
+        return tours
+    orders = plan_tours(clusters)
+    return [cluster[o] if cluster.shape[0] > 0 else np.empty((0, 2)) for cluster, o in zip(clusters, orders)]
 
 
 def todescato_prob(max_var_t, max_var_0):

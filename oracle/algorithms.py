@@ -4,12 +4,14 @@ Follows /root/reference/simulator.py: lloyd :508-616, periodic :618-785, todesca
 decision rules :457-500.  Array in / list-of-dict-rows out (same row schemas as the reference's logs, including the
 `YMax` column that logs positions[i,1], :596,:754,:924,:1116).  Randomness is injected: `py_random` stands for the
 `random` module (Bernoulli explore draws, :943) and `noise_rng` for the per-sample `np.random.default_rng()` (:707,
-:877,:1069).  The Choi TSP tour (mlrose GA, out of scope) is the identity order, as in oracle/refshim/mlrose.
+:877,:1069).  The Choi TSP tour (mlrose GA, :415-454: unpinned third-party routine) comes from the deterministic
+planner of oracle/tsp.py, as in oracle/refshim/mlrose and in the product (csrc/tsp.cu).
 """
 import numpy as np
 
 from . import coverage as cov
 from . import gp as ogp
+from . import tsp
 
 
 def _fidelity(hyp):
@@ -158,7 +160,7 @@ def choi(sim_num, iterations, agents, positions, truth_arr, sigma_n, prior_arr, 
         threshold = 0.82 * threshold
         sample_vor = cov.voronoi_bounded(centroids_t, bbox)
         sample_points, _ = planner(model, x_star, threshold)
-        tours = cov.compute_sample_clusters(sample_vor, sample_points)     # identity tour order
+        tours = tsp.compute_sample_tsp(cov.compute_sample_clusters(sample_vor, sample_points))
         for _step in range(8 * 2 ** period):
             x_new, y_new, id_new = _take_samples(positions, explore_t, truth_arr, sigma_n, noise_rng)
             distance = np.sqrt(np.sum((positions - prev_positions) ** 2, axis=1)).reshape(-1, 1)

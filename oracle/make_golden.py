@@ -5,6 +5,7 @@ Runs only in the build container (needs /root/reference); the outputs are commit
 Contents (SURVEY.md section 4.1 says which logged files still pin today's code):
   inputs_australia6.npz      truth grid, 9-point lofi prior, MF/SF hyper-parameters (inputs, config c2)
   inputs_two_corners.npz     same for the two_corners data set (raw-mean convention runs)
+  inputs_australia3.npz      same for australia3 (BASELINE config 1: todescato_nsf, 4 agents, Data/australia3.md:11)
   ref_gp_cases.npz           live reference: SFGP/MFGP .predict mean + diag(cov) for several model states
   ref_coverage_cases.npz     live reference: compute_loss / compute_centroids / compute_max_var + Qhull polygons
   ref_runs.npz               live reference: seeded lloyd / todescato / periodic / choi runs (loss, agent, sample logs)
@@ -12,6 +13,8 @@ Contents (SURVEY.md section 4.1 says which logged files still pin today's code):
   logged_australia6_lloyd.npz  Data/australia6_lloyd_{agent,loss}.csv sims 0,1 (loss + centroid chain, 120 it)
   logged_two_corners_hmf.npz   Data/two_corners_todescato_hmf_* sim 0 (samples, centroids, VarMax; raw means)
   logged_australia6_nsf.npz    Data/australia6_todescato_nsf_* sim 0 (SF, null prior, current convention)
+  logged_australia3_nsf.npz    Data/australia3_todescato_nsf_* sim 0 (config 1; pins the SF VARIANCE path only: the run
+                               predates the exp(mean) convention)
 """
 import os
 import random
@@ -36,7 +39,7 @@ def _save(name, **arrays):
 
 
 def inputs():
-    for ds in ("australia6", "two_corners"):
+    for ds in ("australia6", "two_corners", "australia3"):
         _save(f"inputs_{ds}.npz",
               truth=_csv(f"{ds}_hifi.csv").values.astype(np.float64),
               prior=_csv(f"{ds}_prior.csv").values.astype(np.float64),
@@ -120,7 +123,9 @@ def ref_runs(sim, gp):
                                       ("periodic_hsf", "periodic", "sf", "prior", 8, 14, 14),
                                       ("periodic_hmf", "periodic", "mf", "prior", 8, 14, 15),
                                       ("choi_hmf", "choi", "mf", "prior", 8, 24, 16),
-                                      ("choi_nsf", "choi", "sf", "null", 4, 24, 17))),):
+                                      ("choi_nsf", "choi", "sf", "null", 4, 24, 17))),
+                      ("australia3", (("todescato_nsf", "todescato", "sf", "null", 4, 30, 31),      # BASELINE config 1
+                                      ("choi_nsf", "choi", "sf", "null", 4, 24, 32)))):
         truth = _csv(f"{ds}_hifi.csv")
         hyps = {"mf": _csv(f"{ds}_mf_hyp.csv"), "sf": _csv(f"{ds}_sf_hyp.csv")}
         priors = {"prior": _csv(f"{ds}_prior.csv"), "null": _csv("null_prior.csv")}
@@ -159,7 +164,8 @@ def logged():
     _save("logged_australia6_lloyd.npz", **out)
     # replayable GP runs: logged samples + logged centroids (seeds of the next iteration) + VarMax / XMax
     for fname, stem, T in (("logged_two_corners_hmf.npz", "two_corners_todescato_hmf", 40),
-                           ("logged_australia6_nsf.npz", "australia6_todescato_nsf", 30)):
+                           ("logged_australia6_nsf.npz", "australia6_todescato_nsf", 30),
+                           ("logged_australia3_nsf.npz", "australia3_todescato_nsf", 40)):
         a, smp = _csv(f"{stem}_agent.csv"), _csv(f"{stem}_sample.csv")
         aa = a[(a.SimNum == 0) & (a.Iteration < T)].sort_values(["Iteration", "Agent"])
         A = int(aa.Agent.max() + 1)

@@ -52,17 +52,20 @@ def _compare(loss, agent, samples, g_loss, g_agent, g_samples, truth_arr, replay
         assert np.max(np.abs(samples[:, 4] - g_samples[:, 4])) <= TOL
 
 
-@pytest.mark.parametrize("name,algo,hyp_key,use_prior", [
-    ("lloyd", "lloyd", "sf_hyp", False), ("todescato_hmf", "todescato", "mf_hyp", True),
-    ("todescato_nsf", "todescato", "sf_hyp", False), ("periodic_hsf", "periodic", "sf_hyp", True),
-    ("periodic_hmf", "periodic", "mf_hyp", True), ("choi_hmf", "choi", "mf_hyp", True),
-    ("choi_nsf", "choi", "sf_hyp", False)])
-def test_seeded_reference_runs(golden_dir, name, algo, hyp_key, use_prior):
-    """config c1/c2: australia6 runs of the unmodified reference, same seeds (random + shared default_rng)."""
+@pytest.mark.parametrize("ds,name,algo,hyp_key,use_prior", [
+    ("australia6", "lloyd", "lloyd", "sf_hyp", False), ("australia6", "todescato_hmf", "todescato", "mf_hyp", True),
+    ("australia6", "todescato_nsf", "todescato", "sf_hyp", False), ("australia6", "periodic_hsf", "periodic", "sf_hyp", True),
+    ("australia6", "periodic_hmf", "periodic", "mf_hyp", True), ("australia6", "choi_hmf", "choi", "mf_hyp", True),
+    ("australia6", "choi_nsf", "choi", "sf_hyp", False),
+    ("australia3", "todescato_nsf", "todescato", "sf_hyp", False),        # BASELINE config 1 (4 agents, null prior, SF)
+    ("australia3", "choi_nsf", "choi", "sf_hyp", False)])
+def test_seeded_reference_runs(golden_dir, ds, name, algo, hyp_key, use_prior):
+    """configs c1 / c2: australia3 and australia6 runs of the unmodified reference, same seeds (random + shared
+    default_rng); Choi tours from the deterministic planner on both sides (oracle/refshim/mlrose, csrc/tsp.cu)."""
     from mfgp_coverage_b200 import simulator as sim
     g = np.load(os.path.join(golden_dir, "ref_runs.npz"), allow_pickle=False)
-    inp = np.load(os.path.join(golden_dir, "inputs_australia6.npz"))
-    key = f"australia6_{name}"
+    inp = np.load(os.path.join(golden_dir, f"inputs_{ds}.npz"))
+    key = f"{ds}_{name}"
     A, T, seed = (int(v) for v in g[f"{key}_meta"])
     truth = pd.DataFrame(inp["truth"], columns=["X", "Y", "f_H"])
     prior = pd.DataFrame(inp["prior"] if use_prior else np.empty((0, 3)), columns=["X", "Y", "f_prior"])

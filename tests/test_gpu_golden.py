@@ -101,10 +101,13 @@ def test_logged_australia6_lloyd_chain(golden_dir):
         assert np.max(np.abs(cen - g[f"s{s}_cent"])) <= TOL
 
 
-@pytest.mark.parametrize("fname,ds,hyp_key,raw,use_prior", [("logged_two_corners_hmf.npz", "two_corners", "mf_hyp", True, True),
-                                                            ("logged_australia6_nsf.npz", "australia6", "sf_hyp", False, False)])
-def test_logged_gp_run_replay(golden_dir, fname, ds, hyp_key, raw, use_prior):
-    """Replay of a logged todescato run: logged samples in, logged centroids / VarMax / XMax out."""
+@pytest.mark.parametrize("fname,ds,hyp_key,raw,use_prior,means", [
+    ("logged_two_corners_hmf.npz", "two_corners", "mf_hyp", True, True, True),
+    ("logged_australia6_nsf.npz", "australia6", "sf_hyp", False, False, True),
+    ("logged_australia3_nsf.npz", "australia3", "sf_hyp", False, False, False)])       # BASELINE config 1 inputs
+def test_logged_gp_run_replay(golden_dir, fname, ds, hyp_key, raw, use_prior, means):
+    """Replay of a logged todescato run: logged samples in, logged centroids / VarMax / XMax out.
+    The australia3 run predates the exp(mean) convention: it pins the variance path only (means=False)."""
     from mfgp_coverage_b200 import simulator as sim
     from mfgp_coverage_b200._coverage import CoverageGrid
     from mfgp_coverage_b200.gaussian_process import evaluate_hyp, prior_variance
@@ -137,7 +140,8 @@ def test_logged_gp_run_replay(golden_dir, fname, ds, hyp_key, raw, use_prior):
         cen = centroids_from_partials(res["cent"].cpu().numpy(), vor.areas(), bbox[0], bbox[1], bbox[2], bbox[3])
         vmax = res["amax_val"].cpu().numpy()
         idx = res["amax_idx"].cpu().numpy()
-        assert np.max(np.abs(cen - g["cent"][t])) <= TOL, t
+        if means:
+            assert np.max(np.abs(cen - g["cent"][t])) <= TOL, t
         assert np.max(np.abs(vmax - g["varmax"][t])) <= TOL * k0, t
         # XMax: accept another index only where the variances tie to 1e-12 (symmetric priors)
         bad = xs[idx, 0] != g["xmax"][t]

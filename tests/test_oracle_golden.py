@@ -69,14 +69,18 @@ def test_oracle_lloyd_vs_logged_csv(golden_dir):
     assert np.max(np.abs(cen - g["s0_cent"][:T])) <= 1e-13
 
 
-@pytest.mark.parametrize("name,algo,hyp_key,use_prior", [
-    ("lloyd", "lloyd", None, False), ("todescato_hmf", "todescato", "mf_hyp", True),
-    ("todescato_nsf", "todescato", "sf_hyp", False), ("periodic_hsf", "periodic", "sf_hyp", True),
-    ("choi_hmf", "choi", "mf_hyp", True)])
-def test_oracle_loops_vs_seeded_reference_runs(golden_dir, name, algo, hyp_key, use_prior):
+@pytest.mark.parametrize("ds,name,algo,hyp_key,use_prior", [
+    ("australia6", "lloyd", "lloyd", None, False), ("australia6", "todescato_hmf", "todescato", "mf_hyp", True),
+    ("australia6", "todescato_nsf", "todescato", "sf_hyp", False), ("australia6", "periodic_hsf", "periodic", "sf_hyp", True),
+    ("australia6", "choi_hmf", "choi", "mf_hyp", True),
+    # (australia6 choi_nsf is left to the GPU test: with a null prior the planner's picks hinge on variances that tie
+    #  bit-exactly at mirror-image points only in the reference's own LU arithmetic -- DESIGN "Arg-max ties" case (a); the
+    #  product's tolerance rule reproduces them, the oracle's plain np.argmax on its triangular solves does not)
+    ("australia3", "todescato_nsf", "todescato", "sf_hyp", False), ("australia3", "choi_nsf", "choi", "sf_hyp", False)])
+def test_oracle_loops_vs_seeded_reference_runs(golden_dir, ds, name, algo, hyp_key, use_prior):
     g = _load(golden_dir, "ref_runs.npz")
-    inp = _load(golden_dir, "inputs_australia6.npz")
-    key = f"australia6_{name}"
+    inp = _load(golden_dir, f"inputs_{ds}.npz")
+    key = f"{ds}_{name}"
     A, T, seed = (int(v) for v in g[f"{key}_meta"])
     pos = g[f"{key}_start"].copy()
     if algo == "lloyd":
@@ -98,6 +102,39 @@ def test_oracle_loops_vs_seeded_reference_runs(golden_dir, name, algo, hyp_key, 
             assert abs(loss[t] - g[f"{key}_loss"][t]) <= 1e-12, t
     cen = np.array([[r_["XCentroid"], r_["YCentroid"], r_["VarMax"], r_["Explore"]] for r_ in logs[1]]).reshape(len(loss), A, 4)
     assert np.max(np.abs(cen - g[f"{key}_agent"][:, :, [6, 7, 4, 9]])) <= 1e-12
+
+
+@pytest.mark.parametrize("fname,ds,hyp_key,raw,use_prior,means", [
+    ("logged_two_corners_hmf.npz", "two_corners", "mf_hyp", True, True, True),
+    ("logged_australia6_nsf.npz", "australia6", "sf_hyp", False, False, True),
+    ("logged_australia3_nsf.npz", "australia3", "sf_hyp", False, False, False)])
+def test_oracle_replays_logged_gp_runs(golden_dir, fname, ds, hyp_key, raw, use_prior, means):
+    """Replay of the reference's own logged todescato runs: logged samples in,
+    logged VarMax / XMax (and, where the run used today's mean convention, centroids) out.  australia3_todescato_nsf
+    (BASELINE config 1) predates the exp(mean) convention, so it pins the variance path only."""
+    g = _load(golden_dir, fname)
+    inp = _load(golden_dir, f"inputs_{ds}.npz")
+    truth = inp["truth"]
+    xs = truth[:, :2]
+    bbox = ocov.bounding_box_of(xs)
+    p = ogp.GPParams.from_hyp(inp[hyp_key], raw_means=raw)
+    prior = inp["prior"] if use_prior else None
+    m = ogp.Model.from_prior(p, prior)
+    assert abs(p.k0 - g["var0"][0, 0]) <= 1e-12 * p.k0
+    T = min(g["pos"].shape[0], 12)
+    seeds = g["pos"][0]
+    for t in range(T):
+        smp = g["samples"][g["samples"][:, 0] == t]
+        m.append(smp[:, 2:4], smp[:, 4:5])
+        mu, var = m.predict(xs)
+        vor = ocov.voronoi_bounded(seeds, bbox)
+        axy, mv, _ = ocov.compute_max_var(vor, truth, var)
+        assert np.max(np.abs(mv[:, 0] - g["varmax"][t])) <= 1e-9 * p.k0, t
+        tie = np.abs(mv[:, 0] - g["varmax"][t]) <= 1e-12 * p.k0
+        assert np.all((axy[:, 0] == g["xmax"][t]) | tie), t
+        if means:
+            assert np.max(np.abs(ocov.compute_centroids(vor, xs, mu) - g["cent"][t])) <= 1e-9, t
+        seeds = g["cent"][t]
 
 
 def test_fast_planner_equals_literal_planner():
