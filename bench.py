@@ -21,6 +21,10 @@ import sys
 import threading
 import time
 
+if "reference" in sys.argv:       # --impl reference: the CPU arm uses every host core, also under torchrun (which exports
+    for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):     # OMP_NUM_THREADS=1 to its workers)
+        os.environ[_v] = str(os.cpu_count() or 1)
+
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -108,56 +112,85 @@ class ClockSampler(threading.Thread):
 # reference arm / cpu baseline: the oracle port of the reference path on the host cores
 # ---------------------------------------------------------------------------------------------------------------------
 
-def cpu_step(w, sample_pts):
-    """The same iteration with the oracle (numpy/scipy, all BLAS threads) on a bounded sample of the grid."""
+def cpu_step(w, sample_pts, threads=None):
+    """The same iteration with the oracle (numpy/scipy) on a bounded sample of the grid: the first `sample_pts` points.
+    Returns a dict: seconds of the fit (K assembly + Cholesky, paid once per iteration whatever the grid size), of the
+    posterior over the sample, of the coverage step over the sample; the oracle's mu / var on the sample (bench.py checks
+    the device results against them); BLAS threads in use."""
+    from threadpoolctl import threadpool_info, threadpool_limits
     from oracle import coverage as ocov
     from oracle import gp as ogp
     p = ogp.GPParams.from_hyp(synth.MF_HYP)
     xy = w["xy"][:sample_pts]
     truth = np.column_stack((xy, w["f"][:sample_pts]))
-    t0 = time.perf_counter()
-    L = ogp.cholesky(ogp.train_cov(p, w["X_L"], w["X_H"]))
-    mu, var = ogp.posterior(p, xy, w["X_L"], w["y_L"], w["X_H"], w["y_H"], L=L, chunk=4096)
-    bbox = ocov.bounding_box_of(w["xy"])
-    ocov.compute_loss(ocov.voronoi_bounded(w["pos"], bbox), truth)
-    lv = ocov.voronoi_bounded(w["cen"], bbox)
-    ocov.compute_centroids(lv, xy, mu)
-    mem_ok = True
-    try:
-        ocov.compute_max_var(lv, truth, var)
-    except ValueError:      # a bounded sample can leave cells empty; the reference raises there
-        mem_ok = False
-    return time.perf_counter() - t0, mem_ok
+    with threadpool_limits(limits=threads or (os.cpu_count() or 1)):
+        blas = max([i.get("num_threads", 1) for i in threadpool_info() if i.get("user_api") == "blas"] or [1])
+        t0 = time.perf_counter()
+        L = ogp.cholesky(ogp.train_cov(p, w["X_L"], w["X_H"]))
+        t1 = time.perf_counter()
+        mu, var = ogp.posterior(p, xy, w["X_L"], w["y_L"], w["X_H"], w["y_H"], L=L, chunk=4096)
+        t2 = time.perf_counter()
+        bbox = ocov.bounding_box_of(w["xy"])
+        ocov.compute_loss(ocov.voronoi_bounded(w["pos"], bbox), truth)
+        lv = ocov.voronoi_bounded(w["cen"], bbox)
+        ocov.compute_centroids(lv, xy, mu)
+        try:
+            ocov.compute_max_var(lv, truth, var)
+        except ValueError:      # a bounded sample can leave cells empty; the reference raises there
+            pass
+        t3 = time.perf_counter()
+    return {"fit_s": t1 - t0, "posterior_s": t2 - t1, "coverage_s": t3 - t2, "total_s": t3 - t0, "mu": mu, "var": var,
+            "blas_threads": int(blas), "k0": p.k0}
+
+
+def cpu_rate(w, r, sample_pts):
+    """Whole-grid rate of the CPU arm from a bounded sample: the fit is paid once per iteration, posterior + coverage
+    scale with the number of grid points -> G / (fit + (G / sample) * (posterior + coverage)).  (sample / total would
+    charge the N^3/3 factorisation to every 16 K points and bias the per-point rate low.)"""
+    G = float(w["G_total"])
+    return G / (r["fit_s"] + G / sample_pts * (r["posterior_s"] + r["coverage_s"]))
 
 
 def cpu_sample_points(w):
     return {"c4": 16384, "c3": 16384, "c2": 2601}[w["name"]]
 
 
+def cpu_baseline_entry(w, r, pts, r1=None):
+    e = {"value": cpu_rate(w, r, pts), "unit": "grid-points/s", "cores": os.cpu_count(), "blas_threads": r["blas_threads"],
+         "kind": "port",
+         "sample": f"one step on the first {pts} of {int(w['G_total'])} grid points with the full N={w['N']} training set "
+                   f"(fit {r['fit_s']:.2f} s + posterior {r['posterior_s']:.2f} s + coverage {r['coverage_s']:.2f} s); value = "
+                   "G / (fit + G/sample * (posterior + coverage)); oracle = numpy/scipy restatement of the reference (its own "
+                   "G x G predict cannot run at this size)",
+         "sample_rate_incl_fit": pts / r["total_s"]}
+    if r1 is not None:
+        e["value_1_thread"] = cpu_rate(w, r1, r1["pts"])
+        e["sample_1_thread"] = f"same, BLAS limited to 1 thread, first {r1['pts']} points"
+    return e
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    w = make_workload(args.workload)
+    w = make_workload(args.workload, 1, 0, "strong")
     pts = cpu_sample_points(w)
     for _ in range(min(args.warmup, 1)):
         cpu_step(w, pts)
-    times = [cpu_step(w, pts)[0] for _ in range(args.steps)]
-    t = float(np.mean(times))
-    value = pts / t
-    line = base_line(args, w, value, t * 1e3)
+    runs = [cpu_step(w, pts) for _ in range(args.steps)]
+    mean = {k: float(np.mean([r[k] for r in runs])) for k in ("fit_s", "posterior_s", "coverage_s", "total_s")}
+    mean["blas_threads"] = runs[0]["blas_threads"]
+    value = cpu_rate(w, mean, pts)
+    line = base_line(args, w, value, w["G_total"] / value * 1e3, world=1)
     line.update({"impl": "reference", "dtype": "f64", "gpu_launches": 0,
-                 "cpu_baseline": {"value": value, "unit": "grid-points/s", "cores": os.cpu_count(), "kind": "port",
-                                  "sample": f"first {pts} of {w['xy'].shape[0]} grid points per step, full N={w['N']} "
-                                            "training set, oracle (numpy/scipy restatement of the reference; the "
-                                            "reference's own G x G predict cannot run at this size)"},
+                 "cpu_baseline": cpu_baseline_entry(w, mean, pts),
                  "e2e": {"value": value, "unit": "grid-points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
     print(json.dumps(line))
 
 
-def base_line(args, w, value, ms):
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    scaling = getattr(args, "scaling", "weak")
+def base_line(args, w, value, ms, world=None, scaling=None):
+    world = int(os.environ.get("WORLD_SIZE", "1")) if world is None else world
+    scaling = getattr(args, "scaling", "weak") if scaling is None else scaling
     shard = (f"weak scaling: every GPU owns a {w['n']}x{w['n']}-point shard (whole columns) of a {w['n'] * world}x{w['n']} grid"
              if scaling == "weak" else f"strong scaling: the {w['n']}x{w['n']} grid split into whole-column slices")
     return {"metric": "GP posterior mean+var + coverage step, grid-points/s (coverage iterations/s = 1000/ms_per_step)",
@@ -277,6 +310,8 @@ def run_ours(args):
     l0 = nat.lib().mfgp_launch_count()
     ms_dev, out = timed_region(lambda: device_step(True), args.steps)
     launches = nat.lib().mfgp_launch_count() - l0
+    chk = min(npts, 1 << 16)
+    mu_timed, var_timed = mu[:chk].cpu().numpy(), var[:chk].cpu().numpy()      # results of the last TIMED step
     clocks = sampler.result()
     plan = eng._fplan[1] if eng._fplan is not None else None
 
@@ -439,13 +474,25 @@ def run_ours(args):
                       "broadcast_partitions_match_local_qhull": shared_ok,
                       "posterior_path": "factored" if plan is not None else "dense"},
         })
+        parity_ok = True
         if world == 1:
             pts = cpu_sample_points(w)
-            t, _ = cpu_step(w, pts)
-            line["cpu_baseline"] = {"value": pts / t, "unit": "grid-points/s", "cores": os.cpu_count(), "kind": "port",
-                                    "sample": f"one step on the first {pts} of {npts} grid points, full N={N} training "
-                                              f"set ({t:.1f} s), oracle = numpy/scipy restatement of the reference"}
+            r = cpu_step(w, pts)
+            p1 = max(256, pts // 16)
+            r1 = cpu_step(w, p1, threads=1)
+            r1["pts"] = p1
+            line["cpu_baseline"] = cpu_baseline_entry(w, r, pts, r1)
+            # parity of the exact path that was timed: device mu / var of the timed steps vs the oracle on the CPU sample
+            err_var = float(np.max(np.abs(var_timed[:pts] - r["var"]))) / r["k0"]
+            err_mu = float(np.max(np.abs(mu_timed[:pts] - r["mu"]))) / max(1.0, float(np.max(np.abs(r["mu"]))))
+            parity_ok = err_var <= 1e-9 and err_mu <= 1e-9
+            line["check"]["max_err_vs_oracle"] = {"var_rel_k0": err_var, "mu_rel": err_mu, "points": int(pts), "tolerance": 1e-9,
+                                                  "ok": parity_ok,
+                                                  "what": "posterior of the TIMED device steps (fused fit + factored posterior) vs "
+                                                          "the oracle on the cpu_baseline sample points"}
         print(json.dumps(line))
+        if not parity_ok:
+            raise SystemExit("bench: the timed path disagrees with the oracle beyond 1e-9 -- the line above is INVALID")
     if world > 1:
         dist.destroy_process_group()
 

@@ -9,6 +9,7 @@ Contents (SURVEY.md section 4.1 says which logged files still pin today's code):
   ref_gp_cases.npz           live reference: SFGP/MFGP .predict mean + diag(cov) for several model states
   ref_coverage_cases.npz     live reference: compute_loss / compute_centroids / compute_max_var + Qhull polygons
   ref_runs.npz               live reference: seeded lloyd / todescato / periodic / choi runs (loss, agent, sample logs)
+  csv_headers.json           header + first row of Data/australia6_{todescato_hmf,lloyd}_{loss,agent,sample}.csv
   logged_ex_gp.npz           Data/ex_gp.csv iteration 0 (per-point Mu, Var; raw-mean convention) + its inputs
   logged_australia6_lloyd.npz  Data/australia6_lloyd_{agent,loss}.csv sims 0,1 (loss + centroid chain, 120 it)
   logged_two_corners_hmf.npz   Data/two_corners_todescato_hmf_* sim 0 (samples, centroids, VarMax; raw means)
@@ -175,8 +176,24 @@ def logged():
               samples=ss[["Iteration", "Agent", "X", "Y", "Sample"]].values.astype(np.float64))
 
 
+def csv_headers():
+    """First line + first data row of the reference's logged output CSVs (runner.py:150-156 writes them with pandas'
+    default index column): the column ORDER analysis.py reads; checked against what runner.run() writes."""
+    import json
+    out = {}
+    for stem in ("australia6_todescato_hmf", "australia6_lloyd"):
+        for kind in ("loss", "agent", "sample"):
+            with open(os.path.join(D, f"{stem}_{kind}.csv")) as f:
+                out[f"{stem}_{kind}"] = {"header": f.readline().rstrip("\n"), "first_row": f.readline().rstrip("\n")}
+    path = os.path.join(OUT, "csv_headers.json")
+    with open(path, "w") as f:
+        json.dump(out, f, indent=1, sort_keys=True)
+    print(f"wrote {path}")
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    csv_headers()
     sim, gp = rl.load()
     inputs()
     logged()

@@ -237,3 +237,46 @@ def test_factored_incremental_update(nx, ny, N0, adds, multi):
     e.incremental = False
     m.predict_device(grid.xy, mu2, var2, grid=grid)
     assert float((var2 - var).abs().max()) <= 1e-11 * p.k0 and float((mu2 - mu).abs().max()) <= 1e-11 * max(1.0, float(mu2.abs().max()))
+
+
+@pytest.mark.parametrize("hyp_name", ["two_corners", "ex"])
+@pytest.mark.parametrize("fused", [False, True])
+def test_factored_posterior_with_near_zero_noise(golden_dir, hyp_name, fused):
+    """The reference's own hyper-parameter files with noises of e^-27 ... e^-58 (two_corners_mf_hyp.csv, ex_hyp.csv): the
+    only regularisation left is the 1e-8 jitter, lambda_min(K) = 1e-8 and cond(K) ~ 2e9 at N = 512.  The Chebyshev
+    re-expansion error of the cross-covariances (~5e-15 entrywise) is amplified by |L^-1| ~ 1e4 in the variance, so this is
+    the configuration where the factored path could leave the 1e-9 k(0) band.  256x256 grid (factored-eligible), N = 512.
+    Mean: in this regime even the oracle's two CPU solve orders (triangular substitution vs the reference's general LU on
+    L, gaussian_process.py:431-434) differ by ~1e-8, so the mean tolerance is the larger of 1e-9 and 4x that spread."""
+    import os
+    from mfgp_coverage_b200._coverage import CoverageGrid
+    hyp = {"two_corners": np.load(os.path.join(golden_dir, "inputs_two_corners.npz"))["mf_hyp"],
+           "ex": np.load(os.path.join(golden_dir, "logged_ex_gp.npz"))["hyp"]}[hyp_name]
+    xy = _tensor_grid(256, 256)
+    f = synth.truth_function(xy)
+    X_L, y_L, X_H, y_H = synth.training_set(xy, f, 512)
+    p = ogp.GPParams.from_hyp(hyp, raw_means=True)
+    assert p.noise_H < 1e-11 and p.noise_L < 1e-11
+    om = ogp.Model(p, X_L, y_L, X_H, y_H)
+    om.updt_info()
+    idx = np.sort(np.random.default_rng(0).choice(xy.shape[0], 4000, replace=False))
+    mu_o, var_o = om.predict(xy[idx])
+    mu_lu, var_lu = om.predict(xy[idx], exact_solve=True)
+    spread_mu = float(np.max(np.abs(mu_o - mu_lu)))
+    assert np.max(np.abs(var_o - var_lu)) <= 1e-11 * p.k0            # the variance IS well defined to 1e-9 k(0) here
+    m = _model(hyp, X_L, y_L, X_H, y_H, True)
+    m.raw_means = True
+    m.updt_info(X_L, y_L, X_H, y_H)
+    e = m.engine
+    grid = CoverageGrid(xy)
+    mu = torch.empty(grid.G, dtype=torch.float64, device=grid.device)
+    var = torch.empty(grid.G, dtype=torch.float64, device=grid.device)
+    if fused:
+        e.defer_fit = True
+        e.refactor(check=False)
+    m.predict_device(grid.xy, mu, var, grid=grid)
+    assert e._fplan is not None and e._fplan[1] is not None          # the factored path ran
+    e.check_factor(force=True)
+    assert np.max(np.abs(var.cpu().numpy()[idx] - var_o)) <= TOL * p.k0
+    assert np.max(np.abs(mu.cpu().numpy()[idx] - mu_o)) <= max(TOL * max(1.0, np.max(np.abs(mu_o))), 4.0 * spread_mu)
+    assert float(var.min()) > -1e-12 * p.k0

@@ -41,6 +41,38 @@ def test_oracle_spot_check_full_training_set(workload):
     assert np.max(np.abs(mu - mu_o)) <= TOL * max(1.0, np.max(np.abs(mu_o)))
 
 
+def test_fused_fit_path_oracle_spot_check(workload):
+    """The exact path bench.py times (`value`): deferred fit -> mfgp_build_train_cov + mfgp_factored_prepare +
+    mfgp_cholesky_solve (Cholesky fused with the forward substitution) + mfgp_posterior_grid_factored_solved, at the
+    BASELINE sizes, against the oracle on a random subset of grid points with the FULL training set; and against the
+    non-fused path (explicit inverse + W B product) on every grid point."""
+    w = workload
+    e = w["m"].engine
+    g = w["g"]
+    mu = torch.full((g.G,), float("nan"), dtype=torch.float64, device=g.device)
+    var = torch.full((g.G,), float("nan"), dtype=torch.float64, device=g.device)
+    e.defer_fit = True
+    try:
+        for rep in range(2):
+            e.refactor(check=False)
+            assert e._dirty
+            w["m"].predict_device(g.xy, mu, var, grid=g)
+            assert not e._dirty and e._w_partial and e._fplan[1] is not None        # fused + factored, not the dense kernel
+        e.check_factor(force=True)
+    finally:
+        e.defer_fit = False
+    idx = np.sort(np.random.default_rng(0).choice(w["xy"].shape[0], 3000, replace=False))
+    om = ogp.Model(w["p"], w["X_L"], w["y_L"], w["X_H"], w["y_H"])
+    om.updt_info()
+    mu_o, var_o = om.predict(w["xy"][idx])
+    assert np.max(np.abs(var.cpu().numpy()[idx] - var_o)) <= TOL * w["p"].k0
+    assert np.max(np.abs(mu.cpu().numpy()[idx] - mu_o)) <= TOL * max(1.0, np.max(np.abs(mu_o)))
+    assert float((var - w["var"]).abs().max()) <= 1e-11 * w["p"].k0
+    assert float((mu - w["mu"]).abs().max()) <= 1e-11
+    L = torch.tril(e.K[:w["N"], :w["N"]]).cpu().numpy()
+    assert np.max(np.abs(L - om.L)) <= 1e-10 * np.max(np.abs(om.L))
+
+
 def test_general_kernel_agrees_with_separable_kernel(workload):
     w = workload
     G = w["xy"].shape[0]
@@ -121,3 +153,66 @@ def test_coverage_conservation_and_subset_oracle(workload):
     for c in range(0, A, max(1, A // 8)):
         sel = np.nonzero(cell == c)[0]
         assert res["amax_idx"][c].item() == sel[np.argmax(var[sel])]
+
+
+def test_choi_period_at_c3_size():
+    """BASELINE config 3 (synthetic 256x256 grid, 1024 MF training samples, 16 agents, choi_hmf): one Choi period -- greedy
+    sample planner (compute_sample_points), clustering, tour planner, then the period's 8 coverage iterations -- through the
+    drop-in simulator, against the oracle: identical pick sequence (V-cached CPU twin of the reference's refit-per-pick
+    loop, pinned to the literal loop in tests/test_oracle_golden.py), identical clusters and tours, and the agents visit
+    their tours in order.  With 1024 samples already in the model the maximum variance is 0.2 k(0), far below the first
+    periods' thresholds 0.82^p k(0) (simulator.py:1015,1037), so the period's threshold is set to 0.6 max(var) -- the state
+    a long run reaches after ~11 periods."""
+    import random
+    from mfgp_coverage_b200 import simulator as sim
+    from oracle import tsp as otsp
+    n, N, A = 256, 1024, 16
+    xy = synth.grid(n)
+    f = synth.truth_function(xy)
+    truth_arr = np.column_stack((xy, f))
+    X_L, y_L, X_H, y_H = synth.training_set(xy, f, N)
+    p = ogp.GPParams.from_hyp(synth.MF_HYP)
+    bbox = np.array([0.0, 1.0, 0.0, 1.0])
+    # --- planner + clusters + tours at the period's start state
+    m = sim.init_MFGP(synth.MF_HYP, np.column_stack((X_L, y_L)))
+    m.updt_info(X_L, y_L, X_H, y_H)
+    om = ogp.Model(p, X_L, y_L, X_H, y_H)
+    om.updt_info()
+    g = sim._grid_for(xy)
+    _, var0 = m.predict_device(g.xy, grid=g)
+    thr = 0.6 * float(var0.max())
+    pts_o, idx_o = ocov.compute_sample_points_fast(om, xy, thr)
+    pts_g, idx_g = sim.compute_sample_points(m, xy, thr, False, return_indices=True)
+    assert 16 <= len(idx_o) <= 500
+    assert np.array_equal(idx_g, idx_o) and np.array_equal(pts_g, pts_o)
+    pos = synth.agents(A, 5)
+    vor_g, vor_o = sim.voronoi_bounded(pos, bbox), ocov.voronoi_bounded(pos, bbox)
+    cl_g, cl_o = sim.compute_sample_clusters(vor_g, pts_g), ocov.compute_sample_clusters(vor_o, pts_o)
+    tours_g, tours_o = sim.compute_sample_tsp(cl_g), otsp.compute_sample_tsp(cl_o)
+    assert sum(c.shape[0] for c in cl_g) == len(idx_o)
+    for a, b, c, d in zip(cl_g, cl_o, tours_g, tours_o):
+        assert np.array_equal(a, b) and np.array_equal(c, d)
+    # --- the whole period through simulator.choi, from a model that already holds the c3 training set
+    real_init, real_thr = sim._init_models, sim.choi_threshold
+
+    def init_with_training_set(fidelity, hyp, prior):
+        model, max_var_0 = real_init(fidelity, hyp, prior)
+        model.updt_info(model.X_L, model.y_L, X_H, y_H)
+        return model, max_var_0
+    sim._init_models = init_with_training_set
+    sim.choi_threshold = lambda threshold: thr
+    try:
+        loss_log, agent_log, sample_log = sim.choi("choi_hmf", 0, 8, A, pos.copy(), truth_arr, 0.1, np.column_stack((X_L, y_L)),
+                                                   synth.MF_HYP, False, None, True, rng=random.Random(3),
+                                                   noise_rng=np.random.default_rng(3))
+    finally:
+        sim._init_models, sim.choi_threshold = real_init, real_thr
+    assert len(loss_log) == 8 and all(r["Period"] == 0 for r in loss_log)
+    X = np.array([[r["X"], r["Y"]] for r in agent_log]).reshape(8, A, 2)
+    for i in range(A):                       # agent i visits its tour in order from iteration 1 on
+        k = min(7, tours_o[i].shape[0])
+        assert np.array_equal(X[1:1 + k, i], tours_o[i][:k]), i
+    taken = np.array([[r["X"], r["Y"]] for r in sample_log]).reshape(-1, 2)
+    want = [tours_o[i][t - 1] for t in range(1, 8) for i in range(A) if tours_o[i].shape[0] >= t]
+    assert len(want) >= 16 and np.array_equal(taken, np.array(want).reshape(-1, 2))
+    assert all(np.isfinite(r["Loss"]) and r["Loss"] > 0 for r in loss_log)
