@@ -253,6 +253,23 @@ int64_t choi_greedy(const double* Xs, int64_t G, double* Vc, int64_t ldv, int64_
                     int64_t* picks_host,
                     void* work, int64_t work_bytes, void* stream);
 
+/* ---- hyper-parameter training: replaces SFGP.likelihood / MFGP.likelihood gaussian_process.py:81-105, :344-384 and the
+ *      autograd gradient behind SFGP.train / MFGP.train :107-119, :386-399 ------------------------------------------- */
+
+/* Negative log marginal likelihood and its analytic gradient for the model whose fit is standing in (L, W, z, Tt) --
+ * i.e. after mfgp_build_train_cov -> mfgp_cholesky -> mfgp_tri_inverse -> mfgp_whiten with the hyper-parameters in
+ * question (means under the exp() convention of :89, :356-357):
+ *   out[0] = 1/2 z.z + sum log diag L + 1/2 N log 2 pi            (:102-104, :381-383)
+ *   out[1 + k] = d out[0] / d hyp[k] for the LOG-scaled hyper-parameters in the reference's order --
+ *   [mu_lo, s^2_lo, L_lo, mu_hi, s^2_hi, L_hi, rho, noise_lo, noise_hi] (multi) or [mu, s^2, L, noise] (single; out[5..9] = 0):
+ *   1/2 sum_ij (K^-1 - alpha alpha^T)_ij dK_ij/dh - alpha . dm/dh with alpha = W^T z, K^-1 = W^T W (DMMA tile product) and
+ *   the dK/dh terms re-evaluated on the fly in one sweep over the lower triangle.  out: 10 doubles (device).
+ *   `work`: mfgp_nlml_workspace_bytes(npad) bytes. */
+int64_t mfgp_nlml_workspace_bytes(int64_t npad);
+int mfgp_nlml_grad(const double* L, int64_t npad, int64_t ld, const double* W, int64_t ldw, const double* z, const double* Tt,
+                   int64_t NL, int64_t NH, const mfgp_params* p_host, double* out, void* work, int64_t work_bytes,
+                   void* stream);
+
 /* ---- Choi tour planner: replaces compute_sample_tsp simulator.py:415-454 ------------------------------------------ */
 
 /* Visiting order of every agent's sample points.  The reference calls mlrose.TSPOpt + mlrose.genetic_alg(mutation_prob=0.2,

@@ -100,6 +100,7 @@ class DeviceGP:
         self._dirty = False           #   a factored posterior then fuses fit + forward substitution (mfgp_cholesky_solve)
         self._w_partial = False       # True: W holds only the diagonal-block inverses (mfgp_tri_inverse still to run)
         self._fB = None               # right-hand-side matrix of the fused fit
+        self._twork = None            # workspace of mfgp_nlml_grad (hyper-parameter training)
         self._cwork = None            # ticket counter + tile flags of mfgp_cholesky_solve (caller-owned, per model)
         self._fG = None               # per-column Gram matrices G'(ix) [ncols, 64, 64] and z^T Y: state of the incremental
         self._fHz = None              #   factored update (mfgp_posterior_grid_factored_update)
@@ -495,6 +496,24 @@ class DeviceGP:
             nat.ptr(self.W), self.npad, self.cap, nat.ptr(self.z), ctypes.byref(self.pstruct), *o, *geom, nat.ptr(mu), nat.ptr(var),
             nat.ptr(q_out), nat.ptr(Gs), nat.ptr(Hs), nat.ptr(work), work.numel() * 8, nat.stream_ptr()),
             "mfgp_posterior_grid_factored")
+
+    # -- hyper-parameter training ------------------------------------------------------------------------------------
+    def nlml_grad(self):
+        """(NLML, gradient[10]) of the standing fit (mfgp_nlml_grad; gaussian_process.py:81-105, :344-384 and the autograd
+        gradient behind train :107-119, :386-399).  Host floats / numpy array; one device->host copy."""
+        if self.N == 0:
+            raise ValueError("likelihood of an empty model")
+        self.ensure_factor(need_inverse=True)
+        lib = nat.lib()
+        need = int(lib.mfgp_nlml_workspace_bytes(self.npad))
+        if self._twork is None or self._twork.numel() * 8 < need:
+            self._twork = torch.empty(need // 8 + 8, dtype=torch.float64, device=self.device)
+        out = torch.empty(10, dtype=torch.float64, device=self.device)
+        nat.check(lib.mfgp_nlml_grad(nat.ptr(self.K), self.npad, self.cap, nat.ptr(self.W), self.cap, nat.ptr(self.z),
+                                     nat.ptr(self.Tt), self.NL, self.NH, ctypes.byref(self.pstruct), nat.ptr(out),
+                                     nat.ptr(self._twork), self._twork.numel() * 8, nat.stream_ptr()), "mfgp_nlml_grad")
+        h = out.cpu().numpy()
+        return float(h[0]), h[1:].copy()
 
     def clone(self):
         self.ensure_factor()

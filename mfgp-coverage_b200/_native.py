@@ -97,6 +97,9 @@ SIGNATURES = {
     "choi_greedy": (c_int64, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p,
                               POINTER(MfgpParams), c_double, c_double, c_int64, POINTER(c_int64), c_void_p, c_int64,
                               c_void_p]),
+    "mfgp_nlml_workspace_bytes": (c_int64, [c_int64]),
+    "mfgp_nlml_grad": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int64,
+                               POINTER(MfgpParams), c_void_p, c_void_p, c_int64, c_void_p]),
     "choi_tsp_workspace_bytes": (c_int64, [c_int64]),
     "choi_tsp_tours": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_int64,
                                c_void_p]),

@@ -13,7 +13,8 @@ enum GemmMode : int {
     GEMM_SYRK_LOWER = 1,   // only C tiles with row-tile >= col-tile are computed (B must be A, B_TRANS)
     GEMM_A_LOWER = 2,      // A[M,K=M] lower triangular: k < m0 + 64
     GEMM_B_LOWER = 3,      // B[K=N,N] (not transposed) lower triangular: k >= n0
-    GEMM_BT_LOWER = 4      // B[N,K=N] (transposed operand) lower triangular: k < n0 + 64
+    GEMM_BT_LOWER = 4,     // B[N,K=N] (transposed operand) lower triangular: k < n0 + 64
+    GEMM_SYRK_LOWER_AUPPER = 5   // C = A A^T lower tiles with A[M,K=M] UPPER triangular: k >= m0 (>= n0)
 };
 
 struct GemmArgs {
@@ -35,7 +36,7 @@ constexpr int GLDB = GT + 4;  // padded row for the non-transposed B slab [GK][G
 template <bool B_TRANS>
 __global__ void __launch_bounds__(128) gemm_f64_kernel(GemmArgs g) {
     const int m0 = blockIdx.y * GT, n0 = blockIdx.x * GT;
-    if (g.mode == GEMM_SYRK_LOWER && n0 > m0) return;
+    if ((g.mode == GEMM_SYRK_LOWER || g.mode == GEMM_SYRK_LOWER_AUPPER) && n0 > m0) return;
     const bool splitk = g.kchunk > 0;
     const double* A = g.A + (splitk ? 0 : (int64_t)blockIdx.z * g.strideA);
     const double* B = g.B + (splitk ? 0 : (int64_t)blockIdx.z * g.strideB);
@@ -52,6 +53,7 @@ __global__ void __launch_bounds__(128) gemm_f64_kernel(GemmArgs g) {
     if (g.mode == GEMM_A_LOWER) kend = min(g.K, m0 + GT);
     if (g.mode == GEMM_B_LOWER) kbeg = n0;
     if (g.mode == GEMM_BT_LOWER) kend = min(g.K, n0 + GT);
+    if (g.mode == GEMM_SYRK_LOWER_AUPPER) kbeg = m0;
     if (splitk) {
         kbeg = max(kbeg, (int)blockIdx.z * g.kchunk);
         kend = min(kend, ((int)blockIdx.z + 1) * g.kchunk);

@@ -7,8 +7,9 @@ coverage algorithms use: construction from arrays, `hyp` assigned after construc
   * `predict(X_star)` returns `(mu[G,1], var[G])` -- the posterior VARIANCE VECTOR, not the G x G covariance matrix
     (gaussian_process.py:146, :435-436) of which the reference's callers only ever take `np.diag`
     (simulator.py:301, :341, :685, :855).  A 1M-point grid would need an 8 TB matrix.
-  * hyper-parameter training (`train`, `likelihood`; autograd + L-BFGS, offline) is out of scope; the `*_hyp.csv`
-    files it produces are consumed unchanged.
+  * `likelihood(hyp)` / `train()` (gaussian_process.py:81-119, :344-399) evaluate the negative log marginal likelihood
+    AND its analytic gradient on the device (mfgp_nlml_grad) where the reference differentiates with autograd; the
+    optimiser is the same scipy L-BFGS-B call.
 
 Every arithmetic step runs on the GPU through the C-ABI in include/mfgp_b200.h; there is no CPU fallback.
 """
@@ -147,6 +148,43 @@ class _GPBase:
         mu_h, var_h = _to_host_pinned(mu), _to_host_pinned(var)
         torch.cuda.current_stream(mu.device).synchronize()
         return mu_h.reshape(-1, 1), var_h
+
+    # -- hyper-parameter training (gaussian_process.py:81-119, :344-399) ------------------------------------------------
+    def likelihood_and_grad(self, hyp):
+        """(NLML, d NLML / d hyp) for log-scaled hyper-parameters `hyp` on the model's current data, on the device: refit
+        (K assembly, tiled Cholesky, inverse, whitening) + mfgp_nlml_grad.  Raises np.linalg.LinAlgError where the
+        reference's np.linalg.cholesky does.  The exp() mean convention of the reference's likelihood is used whatever
+        `raw_means` says (:89, :356-357)."""
+        hyp = np.asarray(hyp, dtype=np.float64).reshape(-1)
+        if hyp.size != np.asarray(self.hyp).reshape(-1).size:
+            raise TypeError("Hyperparameters must be of length 4 (single-fidelity) or 9 (multi-fidelity)")
+        keep_hyp, keep_raw = self.hyp, self.raw_means
+        self.hyp, self.raw_means = hyp, False
+        try:
+            self._refit(check=True)
+        finally:
+            self.hyp, self.raw_means = keep_hyp, keep_raw
+        value, grad = self._dev.nlml_grad()
+        return value, grad[:hyp.size]
+
+    def likelihood(self, hyp):
+        """reference gaussian_process.py:81-105 / :344-384: negative log marginal likelihood (scalar)."""
+        return self.likelihood_and_grad(hyp)[0]
+
+    def callback(self, params):
+        """reference gaussian_process.py:219-227 / :483-491."""
+        print("Log likelihood {}".format(self.likelihood(params)))
+
+    def train(self, callback=True, **options):
+        """reference gaussian_process.py:107-119 / :386-399: L-BFGS-B on the NLML from the current `hyp`; the value and the
+        gradient come from ONE device evaluation per optimiser step (the reference: autograd's value_and_grad)."""
+        from scipy.optimize import minimize
+        cb = self.callback if callback is True else (callback or None)
+        result = minimize(self.likelihood_and_grad, np.asarray(self.hyp, dtype=np.float64), jac=True, method="L-BFGS-B",
+                          callback=cb, options=options or None)
+        self.hyp = result.x
+        self._refit(check=True)          # leave the device state on the trained hyper-parameters
+        return result
 
     def factor(self):
         """Lower Cholesky factor L[N,N] as a host array (the reference keeps it in `self.L`)."""

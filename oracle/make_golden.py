@@ -9,6 +9,8 @@ Contents (SURVEY.md section 4.1 says which logged files still pin today's code):
   ref_gp_cases.npz           live reference: SFGP/MFGP .predict mean + diag(cov) for several model states
   ref_coverage_cases.npz     live reference: compute_loss / compute_centroids / compute_max_var + Qhull polygons
   ref_runs.npz               live reference: seeded lloyd / todescato / periodic / choi runs (loss, agent, sample logs)
+  ref_train.npz              live reference: NLML of MFGP / SFGP .likelihood on Data/australia6_{lofi,hifi}_train.csv rows
+                             at three hyper-parameter vectors each + finite-difference gradients of the same function
   csv_headers.json           header + first row of Data/australia6_{todescato_hmf,lloyd}_{loss,agent,sample}.csv
   logged_ex_gp.npz           Data/ex_gp.csv iteration 0 (per-point Mu, Var; raw-mean convention) + its inputs
   logged_australia6_lloyd.npz  Data/australia6_lloyd_{agent,loss}.csv sims 0,1 (loss + centroid chain, 120 it)
@@ -176,6 +178,39 @@ def logged():
               samples=ss[["Iteration", "Agent", "X", "Y", "Sample"]].values.astype(np.float64))
 
 
+def train_cases(sim, gp):
+    """Live reference `MFGP.likelihood` / `SFGP.likelihood` (gaussian_process.py:81-105, :344-384) on the reference's own
+    training files (trainer.py:27, :66-67), at the constructor's initial hyper-parameters (trainer.py:35-36, :76-78), at the
+    shipped trained ones and at a perturbed point; central finite differences of the same function for the gradient
+    (the reference's autograd is not installed)."""
+    lofi = np.loadtxt(os.path.join(D, "australia6_lofi_train.csv"), skiprows=1, delimiter=",")[:150]
+    hifi = np.loadtxt(os.path.join(D, "australia6_hifi_train.csv"), skiprows=1, delimiter=",")[:150]
+    mf = _csv("australia6_mf_hyp.csv").values[0].astype(np.float64)
+    sf = _csv("australia6_sf_hyp.csv").values[0].astype(np.float64)
+    X_L, y_L, X_H, y_H = lofi[:, :2], lofi[:, 2:3], hifi[:, :2], hifi[:, 2:3]
+    out = {"X_L": X_L, "y_L": y_L, "X_H": X_H, "y_H": y_H}
+    rng = np.random.default_rng(9)
+
+    def fd(fn, h):
+        g = np.zeros(h.size)
+        for k in range(h.size):
+            e = np.zeros(h.size)
+            e[k] = 1e-5
+            g[k] = (fn(h + e) - fn(h - e)) / 2e-5
+        return g
+    m = gp.MFGP(X_L, y_L, X_H, y_H, 0.5, 0.1)
+    hyps = [m.hyp.copy(), mf, mf + 0.2 * rng.standard_normal(9)]
+    out["mf_hyps"] = np.array(hyps)
+    out["mf_nlml"] = np.array([m.likelihood(h) for h in hyps])
+    out["mf_grad_fd"] = np.array([fd(m.likelihood, h) for h in hyps])
+    s = gp.SFGP(X_H, y_H, 0.01)
+    hyps = [s.hyp.copy(), sf, sf + 0.2 * rng.standard_normal(4)]
+    out["sf_hyps"] = np.array(hyps)
+    out["sf_nlml"] = np.array([s.likelihood(h) for h in hyps])
+    out["sf_grad_fd"] = np.array([fd(s.likelihood, h) for h in hyps])
+    _save("ref_train.npz", **out)
+
+
 def csv_headers():
     """First line + first data row of the reference's logged output CSVs (runner.py:150-156 writes them with pandas'
     default index column): the column ORDER analysis.py reads; checked against what runner.run() writes."""
@@ -200,6 +235,7 @@ def main():
     gp_cases(sim, gp)
     coverage_cases(sim, gp)
     ref_runs(sim, gp)
+    train_cases(sim, gp)
 
 
 if __name__ == "__main__":

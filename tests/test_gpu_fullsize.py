@@ -59,8 +59,10 @@ def test_fused_fit_path_oracle_spot_check(workload):
             w["m"].predict_device(g.xy, mu, var, grid=g)
             assert not e._dirty and e._w_partial and e._fplan[1] is not None        # fused + factored, not the dense kernel
         e.check_factor(force=True)
+        L = torch.tril(e.K[:w["N"], :w["N"]]).cpu().numpy()
     finally:
         e.defer_fit = False
+        e.refactor(check=True)      # back to the module fixture's state (explicit inverse, z = W (y - m)) for the other tests
     idx = np.sort(np.random.default_rng(0).choice(w["xy"].shape[0], 3000, replace=False))
     om = ogp.Model(w["p"], w["X_L"], w["y_L"], w["X_H"], w["y_H"])
     om.updt_info()
@@ -69,7 +71,6 @@ def test_fused_fit_path_oracle_spot_check(workload):
     assert np.max(np.abs(mu.cpu().numpy()[idx] - mu_o)) <= TOL * max(1.0, np.max(np.abs(mu_o)))
     assert float((var - w["var"]).abs().max()) <= 1e-11 * w["p"].k0
     assert float((mu - w["mu"]).abs().max()) <= 1e-11
-    L = torch.tril(e.K[:w["N"], :w["N"]]).cpu().numpy()
     assert np.max(np.abs(L - om.L)) <= 1e-10 * np.max(np.abs(om.L))
 
 
