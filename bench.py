@@ -9,8 +9,11 @@ One "step" = one coverage iteration of the workload (default: BASELINE.json conf
     -> O(agents) host finishing (Qhull polygons, centroid / loss arithmetic), exactly what simulator.todescato does.
 `value` = grid points / s with everything resident in HBM; `e2e` = the same iteration through the drop-in Python API
 with HOST numpy buffers (grid upload, mu/var download, re-upload into the coverage functions) inside the timed region.
-N > 1 (torchrun, one rank per GPU): the grid is sharded contiguously over ranks (strong scaling), every rank
-factorises the (small) training system redundantly, per-cell partial sums / arg-max are combined with NCCL.
+N > 1 (torchrun, one rank per GPU): the FIXED grid of the named config is split into whole-column slices (strong scaling,
+BASELINE config 4); every rank factorises the (small) training system itself and forward-substitutes only the right-hand
+sides of its own x-interval; per-cell partial sums / arg-max come home through ONE all-gather.  The weak-scaling figure
+(every GPU owns a full 1024x1024 shard of a wider grid) is measured in the same run and reported as `other_scaling`;
+`--scaling weak|strong` forces one mode for `value`.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c4|c3|c2]
 """
@@ -181,22 +184,26 @@ def run_reference(args):
     mean = {k: float(np.mean([r[k] for r in runs])) for k in ("fit_s", "posterior_s", "coverage_s", "total_s")}
     mean["blas_threads"] = runs[0]["blas_threads"]
     value = cpu_rate(w, mean, pts)
-    line = base_line(args, w, value, w["G_total"] / value * 1e3, world=1)
-    line.update({"impl": "reference", "dtype": "f64", "gpu_launches": 0,
+    line = base_line(args, w, value, mean["total_s"] * 1e3)        # ms_per_step: one bounded-sample step as it was timed
+    line.update({"impl": "reference", "extrapolated_full_grid_ms_per_step": w["G_total"] / value * 1e3, "dtype": "f64", "gpu_launches": 0,
                  "cpu_baseline": cpu_baseline_entry(w, mean, pts),
                  "e2e": {"value": value, "unit": "grid-points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
     print(json.dumps(line))
 
 
 def base_line(args, w, value, ms, world=None, scaling=None):
+    """Keys shared by both arms; `config` is a function of (workload, number of GPUs, scaling mode) only, so the reference arm
+    launched with the same flags prints the same config."""
     world = int(os.environ.get("WORLD_SIZE", "1")) if world is None else world
-    scaling = getattr(args, "scaling", "weak") if scaling is None else scaling
-    shard = (f"weak scaling: every GPU owns a {w['n']}x{w['n']}-point shard (whole columns) of a {w['n'] * world}x{w['n']} grid"
-             if scaling == "weak" else f"strong scaling: the {w['n']}x{w['n']} grid split into whole-column slices")
+    scaling = getattr(args, "scaling", "strong") if scaling is None else scaling
+    n = w["n"]
+    G = n * n * (world if scaling == "weak" else 1)
+    shard = (f"weak scaling: every GPU owns a {n}x{n}-point shard (whole columns) of a {n * world}x{n} grid"
+             if scaling == "weak" else f"strong scaling: the fixed {n}x{n} grid split into whole-column slices")
     return {"metric": "GP posterior mean+var + coverage step, grid-points/s (coverage iterations/s = 1000/ms_per_step)",
             "value": value, "unit": "grid-points/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms, "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "data": "synthetic",
-            "config": {"workload": w["desc"], "grid_points": int(w["G_total"]), "grid_points_per_gpu": int(w["xy"].shape[0]),
+            "config": {"workload": w["desc"], "grid_points": int(G), "grid_points_per_gpu": int(G // world),
                        "train_points": int(w["N"]), "agents": int(w["A"]), "parallelism": f"grid-sharded x{world} ({shard})",
                        "l2_policy": "L2 flushed between steps (256 MB write)"}}
 
@@ -221,57 +228,9 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
-    w = make_workload(args.workload, world, rank, args.scaling)
-    G_total, lo, hi = w["G_total"], w["lo"], w["hi"]
-    npts = hi - lo
     bbox = np.array([0.0, 1.0, 0.0, 1.0])
-
-    model = sim.init_MFGP(synth.MF_HYP, np.column_stack((w["X_L"], w["y_L"])))
-    model.updt_info(w["X_L"], w["y_L"], w["X_H"], w["y_H"])          # uploads the training set once
-    eng = model.engine
-    eng.defer_fit = True          # refactor(check=False) + posterior on a tensor grid fuse into mfgp_cholesky_solve
-    axes = TensorAxes(w["ux"], w["uy"], dev)                           # the synthetic grids are tensor-product grids
-    grid = cv.CoverageGrid(w["xy"], w["f"], base_index=lo, axes=axes)
-    mu = torch.empty(npts, dtype=torch.float64, device=dev)
-    var = torch.empty(npts, dtype=torch.float64, device=dev)
     flush = torch.empty(64 << 20, dtype=torch.float32, device=dev)     # 256 MB > 126 MB L2
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
-    post_ms, fit_ms, cov_ms, chol_ms = [], [], [], []
-    eng.profile_events = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-
-    def device_step(timed, shared_partitions=True):
-        flush.zero_()
-        if timed:
-            ev[3].record()
-        eng.refactor(check=False)                                     # K -> L -> W -> z  (train set resident)
-        if timed:
-            ev[0].record()
-        eng.posterior(grid.xy, mu, var, axes=axes, g_lo=lo)           # factored (tensor grid) or dense DMMA kernel
-        if timed:
-            ev[1].record()
-        if world == 1 or not shared_partitions:
-            loss_vor = sim.voronoi_bounded(w["pos"], bbox)            # host Qhull while the GPU works on the posterior
-            lloyd_vor = sim.voronoi_bounded(w["cen"], bbox)
-            loss_vor.areas(), lloyd_vor.areas()
-        else:       # the partitions are global: rank 0 builds them (host Qhull), everybody else receives the packed cells
-            loss_vor, lloyd_vor = sharding.broadcast_partitions([w["pos"], w["cen"]], bbox, dev)
-        res = grid.assign_reduce(lloyd_vor, loss_vor, w=mu, var=var)
-        if timed:
-            ev[2].record()
-        host = sharding.gather_results_to_host(res)                   # N > 1: one all-gather; one packed device->host copy
-        loss = cv.loss_from_partials(host["lossp"], loss_vor.areas())
-        cent = cv.centroids_from_partials(host["cent"], lloyd_vor.areas(), 0.0, 1.0, 0.0, 1.0)
-        idx = host["amax_idx"]
-        if timed:
-            post_ms.append(ev[0].elapsed_time(ev[1]))                 # .cpu() above synchronised the stream
-            fit_ms.append(ev[3].elapsed_time(ev[0]))
-            cov_ms.append(ev[1].elapsed_time(ev[2]))                  # includes the host Qhull calls before the launch
-            if eng.profile_events[1].query():                         # recorded by the fused fit (mfgp_cholesky_solve)
-                try:
-                    chol_ms.append(eng.profile_events[0].elapsed_time(eng.profile_events[1]))
-                except Exception:                                     # never recorded (non-fused path)
-                    pass
-        return loss, cent, idx
+    empty_x, empty_y = np.empty((0, 2)), np.empty((0, 1))
 
     def barrier():
         torch.cuda.synchronize()
@@ -279,9 +238,8 @@ def run_ours(args):
             dist.barrier()
             torch.cuda.synchronize()
 
-    def timed_region(fn, steps, exclude_flush=True):
-        """K steps between barriers; device timeline (CUDA events), max over ranks.  The L2 flush between steps is a
-        256 MB memset (~45 us), measured once and subtracted."""
+    def timed_region(fn, steps):
+        """K steps between barriers; device timeline (CUDA events), max over ranks."""
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -297,34 +255,106 @@ def run_ours(args):
             ms = float(t.item())
         return ms / steps, out
 
+    class Arm:
+        """One workload on this rank: model, device-resident grid (shard), and the step the product runs per iteration:
+        simulator._Sim.step on one GPU, sharding.ShardedSim.step on a grid shard."""
+
+        def __init__(self, scaling):
+            self.w = w = make_workload(args.workload, world, rank, scaling)
+            self.model = sim.init_MFGP(synth.MF_HYP, np.column_stack((w["X_L"], w["y_L"])))
+            self.model.updt_info(w["X_L"], w["y_L"], w["X_H"], w["y_H"])      # uploads the training set once
+            self.eng = self.model.engine
+            self.eng.profile_events = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            self.chol_ms = []
+            if world == 1:
+                self.state = sim._Sim(np.column_stack((w["xy"], w["f"])))
+            else:
+                axes = TensorAxes(w["ux"], w["uy"], dev)
+                self.state = sharding.ShardedSim(w["xy"], w["f"], axes, w["lo"], bbox)
+
+        def step(self, timed=False):
+            w = self.w
+            flush.zero_()
+            self.eng.refactor(check=False)         # the reference refits every iteration (simulator.py:888-891): factor stale
+            if world == 1:
+                loss, cent, axy, mv, _, _ = self.state.step(self.model, w["pos"], w["cen"])
+                out = (loss, cent, axy)
+            else:
+                loss, cent, idx, mv = self.state.step(self.model, w["pos"], w["cen"])
+                out = (loss, cent, idx)
+            if timed and self.eng.profile_events[1].query():
+                try:
+                    self.chol_ms.append(self.eng.profile_events[0].elapsed_time(self.eng.profile_events[1]))
+                except Exception:                  # never recorded (non-fused path)
+                    pass
+            return out
+
+    main_scaling = args.scaling          # default "strong": BASELINE config 4 is the FIXED grid, sharded at 2 / 4 / 8 GPUs
+    arm = Arm(main_scaling)
+    w, eng, model = arm.w, arm.eng, arm.model
+    G_total, npts = w["G_total"], w["hi"] - w["lo"]
     for _ in range(args.warmup):
-        device_step(False)
+        arm.step()
     eng.check_factor(force=True)
-    shared_ok = None
-    if world > 1:      # the broadcast partitions must give what every rank's own Qhull run gives (reported in `check`)
-        a, b = device_step(False), device_step(False, shared_partitions=False)
-        shared_ok = bool(abs(a[0] - b[0]) <= 1e-12 * abs(b[0]) and np.allclose(a[1], b[1], rtol=1e-12, atol=1e-14)
-                         and np.array_equal(a[2], b[2]))
     sampler = ClockSampler(local)
     sampler.start()
     l0 = nat.lib().mfgp_launch_count()
-    ms_dev, out = timed_region(lambda: device_step(True), args.steps)
+    ms_dev, out = timed_region(lambda: arm.step(True), args.steps)
     launches = nat.lib().mfgp_launch_count() - l0
-    chk = min(npts, 1 << 16)
-    mu_timed, var_timed = mu[:chk].cpu().numpy(), var[:chk].cpu().numpy()      # results of the last TIMED step
     clocks = sampler.result()
+    chk = min(npts, 1 << 16)
+    mu_timed, var_timed = arm.state.mu[:chk].cpu().numpy(), arm.state.var[:chk].cpu().numpy()      # results of the last TIMED step
     plan = eng._fplan[1] if eng._fplan is not None else None
+
+    # the other scaling mode at N > 1, reported inside the same line (never as `value`)
+    other = None
+    if world > 1 and not args.scaling_given:
+        arm2 = Arm("weak")
+        for _ in range(args.warmup):
+            arm2.step()
+        ms2, _ = timed_region(lambda: arm2.step(True), args.steps)
+        other = {"scaling": "weak", "grid_points": int(arm2.w["G_total"]), "ms_per_step": ms2,
+                 "value": arm2.w["G_total"] / (ms2 * 1e-3), "unit": "grid-points/s",
+                 "note": f"every GPU owns a {w['n']}x{w['n']}-point shard of a {w['n'] * world}x{w['n']} grid (the per-GPU work of the "
+                         "1-GPU line; the training system is the same)"}
+        del arm2
+
+    # instrumented steps (outside the timed region): where the step's time goes
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    bd = {"posterior (incl. the fused fit)": [], "cells + coverage kernels + finish": [], "host tail (copy home, O(A) finishing)": []}
+    grid, state = arm.state.grid, arm.state
+    k0 = float(eng.params["s_H"] + eng.params["rho"] ** 2 * eng.params["s_L"])
+    for _ in range(3):
+        flush.zero_()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        eng.refactor(check=False)
+        ev[0].record()
+        model.predict_device(grid.xy, state.mu, state.var, grid=grid)
+        ev[1].record()
+        lv, pv = cv.HybridVoronoi(w["cen"], bbox), cv.HybridVoronoi(w["pos"], bbox)
+        res = grid.assign_reduce(lv, pv, w=state.mu, var=state.var, amax_k0=k0, amax_rel=cv.AMAX_REL)
+        if world == 1:
+            grid.finish(res, lv, pv, bbox, info=eng.info, with_ties=True)
+        ev[2].record()
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        bd["posterior (incl. the fused fit)"].append(ev[0].elapsed_time(ev[1]))
+        bd["cells + coverage kernels + finish"].append(ev[1].elapsed_time(ev[2]))
+        bd["host tail (copy home, O(A) finishing)"].append(max(0.0, (t1 - t0) * 1e3 - ev[0].elapsed_time(ev[2])))
+    pm = float(np.mean(bd["posterior (incl. the fused fit)"]))
 
     # the dense DMMA posterior kernel on a 64-column sub-grid, for reference (it is the path of arbitrary point lists)
     dense = None
+    axes = grid.axes
     if plan is not None:
         sub = min(64, npts // axes.ny) * axes.ny
         eng.use_factored = False
         for _ in range(2):
-            eng.posterior(grid.xy[:sub], mu[:sub], var[:sub], axes=axes, g_lo=lo)
+            eng.posterior(grid.xy[:sub], state.mu[:sub], state.var[:sub], axes=axes, g_lo=w["lo"])
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        eng.posterior(grid.xy[:sub], mu[:sub], var[:sub], axes=axes, g_lo=lo)
+        eng.posterior(grid.xy[:sub], state.mu[:sub], state.var[:sub], axes=axes, g_lo=w["lo"])
         e1.record()
         torch.cuda.synchronize()
         eng.use_factored = True
@@ -333,20 +363,18 @@ def run_ours(args):
         dense = {"kernel": "posterior_kernel (dense DMMA path, arbitrary point lists)", "grid_points": int(sub), "ms": dms,
                  "achieved": dfl / (dms * 1e-3) * 1e-12, "unit": "TFLOP/s", "frac": dfl / (dms * 1e-3) * 1e-12 / DGEMM_PEAK_TFLOPS,
                  "grid_points_per_s": sub / (dms * 1e-3)}
-        eng.posterior(grid.xy, mu, var, axes=axes, g_lo=lo)           # restore the standing posterior
 
     # end-to-end through the reference-style call sequence with HOST buffers: updt_hifi -> predict(x_star) ->
-    # compute_loss / compute_centroids / compute_max_var (simulator.py:888-904); host arrays in, host arrays out
+    # voronoi_bounded + compute_loss / compute_centroids / compute_max_var (simulator.py:888-904); host arrays in and out
     xs_host = np.ascontiguousarray(w["xy"])
     truth_host = np.ascontiguousarray(np.column_stack((w["xy"], w["f"])))
-    empty_x, empty_y = np.empty((0, 2)), np.empty((0, 1))
 
     def e2e_step():
         model.updt_hifi(empty_x, empty_y)                 # the reference refits every iteration (simulator.py:888-891)
         mu_h, var_h = model.predict(xs_host)              # D2H mean + variance (the grid upload is cached by identity)
         loss_vor = sim.voronoi_bounded(w["pos"], bbox)
-        lloyd_vor = sim.voronoi_bounded(w["cen"], bbox)
         loss = sim.compute_loss(loss_vor, truth_host)
+        lloyd_vor = sim.voronoi_bounded(w["cen"], bbox)
         cent = sim.compute_centroids(lloyd_vor, xs_host, mu_h)            # H2D mean
         try:
             axy, mv = sim.compute_max_var(lloyd_vor, truth_host, var_h)   # H2D variance
@@ -358,7 +386,7 @@ def run_ours(args):
 
     e2e_step()
     ms_e2e, out_e2e = timed_region(e2e_step, max(1, min(args.steps, 5)))
-    h2d = npts * (8 + 8) + w["A"] * 200
+    h2d = npts * (8 + 8) + w["A"] * 2 * 16
     d2h = npts * 16 + w["A"] * 8 * 8
 
     # incremental iteration (reported separately -- never as `value`): every agent takes one new
@@ -370,58 +398,63 @@ def run_ours(args):
     used = {tuple(r) for r in w["X_H"]}
     pool = [i for i in pool if tuple(basegrid[i]) not in used]
     inc_steps = max(1, min(args.steps, 5))
-    eng.incremental = True
-    eng.refactor(check=False)
-    eng.posterior(grid.xy, mu, var, axes=axes, g_lo=lo)
-    cursor = [0]
-    clip = [None, None]
+    inc = None
+    if world == 1:
+        mu, var = state.mu, state.var
+        eng.incremental = True
+        eng.refactor(check=False)
+        eng.posterior(grid.xy, mu, var, axes=axes, g_lo=w["lo"])
+        cursor = [0]
+        clip = [None, None]
 
-    def inc_step():
-        idx = pool[cursor[0]:cursor[0] + w["A"]]
-        cursor[0] += w["A"]
-        x_new = basegrid[idx]
-        y_new = (synth.truth_function(x_new) + rng_inc.normal(0, 0.1, len(idx))).reshape(-1, 1)
-        eng.append_hifi(x_new, y_new, check=False)                 # H2D of the new samples + bordered factor update
-        eng.posterior(grid.xy, mu, var, axes=axes, g_lo=lo)        # factored: only the new rows of Y = W B
-        # throughput mode: cells built on the device (cov_voronoi_clip), O(A) finishing on the device, ONE D2H per iteration
-        clip[0] = cv.ClippedVoronoi(w["pos"], bbox, reuse=clip[0])
-        clip[1] = cv.ClippedVoronoi(w["cen"], bbox, reuse=clip[1])
-        res = grid.assign_reduce(clip[1], clip[0], w=mu, var=var)
-        sharding.allreduce_partials(res)
-        loss, cent, _, out3 = grid.finish(res, clip[1], clip[0], bbox, info=eng.info)
-        return loss, cent, out3
+        def inc_step():
+            idx = pool[cursor[0]:cursor[0] + w["A"]]
+            cursor[0] += w["A"]
+            x_new = basegrid[idx]
+            y_new = (synth.truth_function(x_new) + rng_inc.normal(0, 0.1, len(idx))).reshape(-1, 1)
+            eng.append_hifi(x_new, y_new, check=False)                 # H2D of the new samples + bordered factor update
+            eng.posterior(grid.xy, mu, var, axes=axes, g_lo=w["lo"])   # factored: only the new rows of Y = W B
+            clip[0] = cv.ClippedVoronoi(w["pos"], bbox, reuse=clip[0])
+            clip[1] = cv.ClippedVoronoi(w["cen"], bbox, reuse=clip[1])
+            res = grid.assign_reduce(clip[1], clip[0], w=mu, var=var)
+            loss, cent, _, out3 = grid.finish(res, clip[1], clip[0], bbox, info=eng.info)
+            return loss, cent, out3
 
-    inc_step()                                                     # warm-up (grows the factor buffers once)
-    ms_inc, out_inc = timed_region(inc_step, inc_steps)
-    eng.check_factor(force=True)
-    mu_i, var_i = mu.clone(), var.clone()
-    eng.incremental = False
-    eng.refactor(check=True)                                       # from-scratch factor of the grown model
-    eng.posterior(grid.xy, mu, var, axes=axes, g_lo=lo)
-    k0 = float(eng.params["s_H"] + eng.params["rho"] ** 2 * eng.params["s_L"])
-    inc_err = (float((var_i - var).abs().max().item()) / k0, float((mu_i - mu).abs().max().item()))
+        inc_step()                                                     # warm-up (grows the factor buffers once)
+        ms_inc, out_inc = timed_region(inc_step, inc_steps)
+        eng.check_factor(force=True)
+        mu_i, var_i = mu.clone(), var.clone()
+        eng.incremental = False
+        eng.defer_fit = False
+        eng.refactor(check=True)                                       # from-scratch factor of the grown model
+        eng.posterior(grid.xy, mu, var, axes=axes, g_lo=w["lo"])
+        inc_err = (float((var_i - var).abs().max().item()) / k0, float((mu_i - mu).abs().max().item()))
+        inc = {"ms_per_step": ms_inc, "value": G_total / (ms_inc * 1e-3), "unit": "grid-points/s",
+               "iterations_per_s": 1000.0 / ms_inc, "appended_per_step": int(w["A"]), "steps": inc_steps,
+               "train_points_end": int(eng.N), "max_err_vs_refit": {"var_rel_k0": inc_err[0], "mu_abs": inc_err[1]},
+               "note": "throughput mode: bordered Cholesky append + incremental (factored) posterior + coverage step on "
+                       "device-built Voronoi cells, one D2H per iteration; the reference refits from scratch every iteration "
+                       "(that is `value`)"}
 
     if rank == 0:
         value = G_total / (ms_dev * 1e-3)
         N = w["N"]
-        pm = float(np.mean(post_ms))
-        line = base_line(args, w, value, ms_dev)
+        line = base_line(args, w, value, ms_dev, world, main_scaling)
+        chol_ms = arm.chol_ms
         if plan is not None:
             wv = max(plan["ryL"], plan["ryH"])                 # both kernel parts share one Chebyshev basis
             R = wv * max(plan["rxL"], plan["rxH"])
             ncols = plan["ncols"]
             macs = 0.5 * N * N * R + float(ncols) * N * R + float(ncols) * N * wv * wv + float(npts) * wv * wv
-            fused = eng.defer_fit                       # the Cholesky runs inside the same call (mfgp_cholesky_solve)
-            flops = 2.0 * macs + (N ** 3 / 3.0 if fused else 0.0)
-            pm_roof = pm + (float(np.mean(fit_ms)) if fused else 0.0)
-            call = {"what": "whole posterior call: covariance + Chebyshev tables + tiled Cholesky/substitution + Ux*Y^T + gram_eval",
-                    "ms": pm_roof, "share_of_step": pm_roof / ms_dev, "algorithmic_flops": flops,
-                    "achieved": flops / (pm_roof * 1e-3) * 1e-12, "unit": "TFLOP/s",
-                    "frac": flops / (pm_roof * 1e-3) * 1e-12 / DGEMM_PEAK_TFLOPS,
+            flops = 2.0 * macs + N ** 3 / 3.0
+            call = {"what": "whole posterior call: covariance + Chebyshev tables + tiled Cholesky/substitution + per-column Gram + evaluation",
+                    "ms": pm, "share_of_step": pm / ms_dev, "algorithmic_flops": flops,
+                    "achieved": flops / (pm * 1e-3) * 1e-12, "unit": "TFLOP/s",
+                    "frac": flops / (pm * 1e-3) * 1e-12 / DGEMM_PEAK_TFLOPS,
                     "algorithmic_flops_note": "N^3/3 (Cholesky) + 2 (N^2 R / 2 + n_col N R + n_col N w^2 + G w^2), "
                                               "R = max rx * max ry, w = max ry",
                     "dense_equivalent_tflops": (float(npts) * N * N + 4.0 * npts * N) / (pm * 1e-3) * 1e-12}
-            if fused and chol_ms:
+            if chol_ms:
                 # the dominant kernel of the step: ONE launch factors K and forward-substitutes [B | y - m] (R + 1 columns)
                 km = float(np.mean(chol_ms))
                 kfl = N ** 3 / 3.0 + float(N) * N * (R + 1)
@@ -430,17 +463,15 @@ def run_ours(args):
                                   "right-hand sides of the factored posterior; persistent tile-dataflow kernel, FP64 DMMA)",
                         "achieved": kfl / (km * 1e-3) * 1e-12, "peak": DGEMM_PEAK_TFLOPS, "unit": "TFLOP/s",
                         "frac": kfl / (km * 1e-3) * 1e-12 / DGEMM_PEAK_TFLOPS,
-                        "traffic": CHOL_TRAFFIC_C4_1GPU if (w["name"] == "c4" and N == 4096) else None,
+                        "traffic": CHOL_TRAFFIC_C4_1GPU if (w["name"] == "c4" and N == 4096 and world == 1) else None,
                         "traffic_unit": "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)",
                         "algorithmic_flops": kfl, "algorithmic_flops_note": "N^3/3 + N^2 (R + 1), R = max rx * max ry",
                         "algorithmic_bytes": 8.0 * (N * (N + 64.0) + 2.0 * N * (R + 64)),
                         "kernel_ms": km, "kernel_share_of_step": km / ms_dev}
             else:
-                roof = {"bound": "tensor",
-                        "kernel": "factored posterior (gemm_f64_kernel W*B and Ux*Y^T, gram_eval_kernel; FP64 DMMA)",
-                        "achieved": call["achieved"], "peak": DGEMM_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": call["frac"],
-                        "traffic": None, "algorithmic_flops": flops, "kernel_ms": pm_roof,
-                        "kernel_share_of_step": pm_roof / ms_dev}
+                roof = {"bound": "tensor", "kernel": "factored posterior (FP64 DMMA)", "achieved": call["achieved"],
+                        "peak": DGEMM_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": call["frac"], "traffic": None,
+                        "algorithmic_flops": flops, "kernel_ms": pm, "kernel_share_of_step": pm / ms_dev}
             roof.update({"chebyshev_orders": [plan["rxL"], plan["ryL"], plan["rxH"], plan["ryH"]], "posterior_call": call,
                          "peak_source": "cuBLAS DGEMM 8192^3 measured on this pool (profiles/r01_dgemm_peak.json); "
                                         "MEASURED_PEAKS.json has no FP64 figure; DMMA issue peak 37.15",
@@ -456,24 +487,23 @@ def run_ours(args):
             "dtype": "f64", "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": G_total / (ms_e2e * 1e-3), "unit": "grid-points/s", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e,
-                    "api": "MFGP.updt_hifi + MFGP.predict(x_star) + compute_loss / compute_centroids / compute_max_var, "
-                           "numpy arrays in and out"},
+                    "api": "MFGP.updt_hifi + MFGP.predict(x_star) + voronoi_bounded + compute_loss / compute_centroids / "
+                           "compute_max_var, numpy arrays in and out"},
             "roofline": roof,
-            "breakdown_ms": {"fit(K+chol+inverse+whiten; ~0 when fused into the posterior call)": float(np.mean(fit_ms)),
-                             "posterior (incl. the fused fit)" if eng.defer_fit else "posterior": pm,
-                             "qhull+coverage_kernels": float(np.mean(cov_ms)),
-                             "d2h+host_finish+flush": ms_dev - pm - float(np.mean(fit_ms)) - float(np.mean(cov_ms))},
-            "incremental": {"ms_per_step": ms_inc, "value": G_total / (ms_inc * 1e-3), "unit": "grid-points/s",
-                            "iterations_per_s": 1000.0 / ms_inc, "appended_per_step": int(w["A"]), "steps": inc_steps,
-                            "train_points_end": int(eng.N),
-                            "max_err_vs_refit": {"var_rel_k0": inc_err[0], "mu_abs": inc_err[1]},
-                            "note": "throughput mode: bordered Cholesky append + incremental (factored) posterior + coverage step "
-                                    "on device-built Voronoi cells, one D2H per iteration; the reference refits from scratch "
-                                    "every iteration (that is `value`, measured with host Qhull cells)"},
+            "breakdown_ms": {k: float(np.mean(v)) for k, v in bd.items()},
             "check": {"loss": float(out[0]), "loss_e2e": float(out_e2e[0]) if world == 1 else None, "npad": int(npad_main),
-                      "broadcast_partitions_match_local_qhull": shared_ok,
-                      "posterior_path": "factored" if plan is not None else "dense"},
+                      "posterior_path": "factored" if plan is not None else "dense",
+                      "step": "simulator._Sim.step" if world == 1 else "sharding.ShardedSim.step"},
         })
+        if inc is not None:
+            line["incremental"] = inc
+        if other is not None:
+            line["other_scaling"] = other
+        if world > 1:
+            line["scaling_note"] = ("strong scaling of the fixed grid: every rank factorises the N x N training covariance itself "
+                                    "(N^3/3 flop, a serial chain of N/64 diagonal blocks that more GPUs cannot shorten) and "
+                                    "forward-substitutes only the right-hand sides of ITS x-interval; Amdahl bound of the step = "
+                                    "t_cholesky / t_step(1 GPU)")
         parity_ok = True
         if world == 1:
             pts = cpu_sample_points(w)
@@ -614,9 +644,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS) + ["c5"])
-    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
-                    help="N > 1: per-GPU grid shard fixed (weak, default) or the fixed grid split over the GPUs (strong)")
+    ap.add_argument("--scaling", default="strong", choices=["weak", "strong"],
+                    help="N > 1: the fixed grid split over the GPUs (strong, default: BASELINE config 4) or a fixed per-GPU shard (weak)")
     args = ap.parse_args()
+    args.scaling_given = any(a.startswith("--scaling") for a in sys.argv[1:])
     if args.workload == "c5":
         run_c5(args)
     elif args.impl == "reference":

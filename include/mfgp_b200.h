@@ -196,14 +196,17 @@ int mfgp_posterior_grid_factored_solved(const double* ux, int64_t nx, const doub
  * a tolerance relative to the variance REDUCTION; ties go to the LOWEST index (np.argmax returns the first index).
  * This reproduces both ways the reference's variances tie: bit-identical values at mirror-image points of a symmetric
  * prior (tolerance >> arithmetic noise) and the 1-ulp plateaus of k0 - q far from all data (tolerance << 1 ulp, exact
- * compare).  amax_rel = 0: plain first-index arg-max.  Callers in simulator.py pass k(0) and 1e-10. */
+ * compare).  amax_rel = 0: plain first-index arg-max.  Callers in simulator.py pass k(0) and 1e-10.
+ * tie_count (optional device int32): receives the number of (point, partition) pairs whose membership the crossings test
+ * decided (nearest-seed gap <= tie_tol).  0 means the result does not depend on the polygon vertices at all -- the
+ * drop-in then never needs host Qhull for that iteration (cells clipped on the device, cov_voronoi_clip). */
 int cov_assign_reduce(const double* xy, const double* w, const double* var, const double* f, int64_t G,
                       int64_t base_index,
                       const double* seeds_c, int64_t Ac, const double* poly_xy_c, const int32_t* poly_off_c, int64_t nvert_c,
                       const double* seeds_p, int64_t Ap, const double* poly_xy_p, const int32_t* poly_off_p, int64_t nvert_p,
                       double tie_tol, double amax_k0, double amax_rel,
                       double* cent, double* amax_val, int64_t* amax_idx, double* lossp,
-                      uint64_t* member_c, void* work, int64_t work_bytes, void* stream);
+                      uint64_t* member_c, int32_t* tie_count, void* work, int64_t work_bytes, void* stream);
 int64_t cov_workspace_bytes(int64_t G, int64_t Ac, int64_t Ap);
 
 /* The same pass for a tensor-product grid stored x-major (point g = ix*ny + iy; every grid of the reference:
@@ -217,7 +220,7 @@ int cov_assign_reduce_grid(const double* xy, const double* w, const double* var,
                            const double* seeds_p, int64_t Ap, const double* poly_xy_p, const int32_t* poly_off_p, int64_t nvert_p,
                            double tie_tol, double amax_k0, double amax_rel,
                            double* cent, double* amax_val, int64_t* amax_idx, double* lossp,
-                           void* work, int64_t work_bytes, void* stream);
+                           int32_t* tie_count, void* work, int64_t work_bytes, void* stream);
 
 /* Bounded Voronoi cells on the device (replaces voronoi_bounded simulator.py:154-191 + poly_area :127-136 where host Qhull
  * is the bottleneck -- replicate sweeps, device-resident loops): cell i = the box [xmin-eps/2, xmax+eps/2] x
@@ -230,12 +233,13 @@ int cov_voronoi_clip(const double* seeds, int64_t A, double xmin, double xmax, d
 
 /* O(A) finishing of cov_assign_reduce's partial sums with the reference's arithmetic (simulator.py:215-219, :256-271):
  * out[0] = loss, out[1+2i], out[2+2i] = centroid i clamped to [xmin,xmax] x [ymin,ymax], out[1+2Ac+i] = max variance of
- * cell i, out[1+3Ac+i] = its arg-max grid index as a double (-1: empty cell), out[1+4Ac .. 3+4Ac] = the values of up
- * to three device int32 flags (may be NULL: e.g. mfgp_cholesky's `info`, cov_voronoi_clip's `flag`), so ONE D2H copy of
- * 4 + 4 Ac doubles brings a whole iteration's result and its error state back. */
+ * cell i, out[1+3Ac+i] = its arg-max grid index as a double (-1: empty cell), out[1+4Ac .. 4+4Ac] = the values of up
+ * to four device int32 flags (may be NULL: e.g. mfgp_cholesky's `info`, cov_voronoi_clip's `flag`, cov_assign_reduce's
+ * tie_count), so ONE D2H copy of 5 + 4 Ac doubles brings a whole iteration's result and its error state back. */
 int cov_finish(const double* cent, const double* areas_c, int64_t Ac, const double* lossp, const double* areas_p, int64_t Ap,
                const double* amax_val, const int64_t* amax_idx, double xmin, double xmax, double ymin, double ymax,
-               const int32_t* flag0, const int32_t* flag1, const int32_t* flag2, double* out, void* stream);
+               const int32_t* flag0, const int32_t* flag1, const int32_t* flag2, const int32_t* flag3, double* out,
+               void* stream);
 
 /* Global first-index argmax of v[G] (np.argmax at simulator.py:352): out_val[1], out_idx[1]. */
 int cov_argmax(const double* v, int64_t G, int64_t base_index, double k0, double rel, double* out_val, int64_t* out_idx,

@@ -123,12 +123,19 @@ class ClippedVoronoi:
         self.seeds_inside = bool(np.all((c[:, 0] >= bb[0]) & (c[:, 0] <= bb[1]) & (c[:, 1] >= bb[2]) & (c[:, 1] <= bb[3])))
         self.nvert = 7 * self.A + 16                       # capacity (planar bound ~6A + corners); actual count = off[A]
         f64 = dict(dtype=torch.float64, device=self.device)
+        self._stale = False
         if reuse is not None and reuse.A == self.A:
-            self.seeds, self.poly, self.off, self.dev_areas, self.flag = \
-                reuse.seeds, reuse.poly, reuse.off, reuse.dev_areas, reuse.flag
-            self.seeds.copy_(torch.from_numpy(c.reshape(-1)))
+            reuse._stale = True      # its device buffers now belong to this object
+            self.seeds, self.poly, self.off, self.dev_areas, self.flag, self._stage = \
+                reuse.seeds, reuse.poly, reuse.off, reuse.dev_areas, reuse.flag, reuse._stage
+            # page-locked staging + asynchronous copy: the host never waits for what is already queued on the stream
+            # (the previous user of the staging buffer is long done: its iteration ended with a synchronising copy home)
+            self._stage.numpy()[:] = c.reshape(-1)
+            self.seeds.copy_(self._stage, non_blocking=True)
         else:
-            self.seeds = torch.from_numpy(c.reshape(-1)).to(self.device)
+            self._stage = torch.empty(max(2 * self.A, 1), dtype=torch.float64, pin_memory=True)
+            self._stage.numpy()[:2 * self.A] = c.reshape(-1)
+            self.seeds = self._stage[:2 * self.A].to(self.device, non_blocking=True)
             self.poly = torch.empty(2 * self.nvert, **f64)
             self.off = torch.empty(self.A + 2, dtype=torch.int32, device=self.device)
             self.dev_areas = torch.empty(max(self.A, 1), **f64)
@@ -138,11 +145,14 @@ class ClippedVoronoi:
                                                  nat.ptr(self.poly), nat.ptr(self.off), self.nvert, nat.ptr(self.dev_areas),
                                                  nat.ptr(self.flag), nat.stream_ptr()), "cov_voronoi_clip")
         self._host = None
+        self._areas_host = None
 
     def __len__(self):
         return self.A
 
     def _fetch(self):
+        if self._host is None and self._stale:
+            raise RuntimeError("this partition's device buffers were recycled by a later iteration (ClippedVoronoi reuse=)")
         if self._host is None:
             if int(self.flag.item()):
                 raise RuntimeError("cov_voronoi_clip: polygon capacity exceeded")
@@ -165,7 +175,58 @@ class ClippedVoronoi:
         return poly[off[i]:off[i + 1]]
 
     def areas(self):
-        return self._fetch()[2]
+        """Host copy of the device shoelace areas (one small copy; the vertices stay on the device)."""
+        if self._host is not None:
+            return self._host[2]
+        if getattr(self, "_areas_host", None) is None and self._stale:
+            raise RuntimeError("this partition's device buffers were recycled by a later iteration (ClippedVoronoi reuse=)")
+        if getattr(self, "_areas_host", None) is None:
+            h = torch.empty(self.A + 1, dtype=torch.float64, pin_memory=True)
+            h[:self.A].copy_(self.dev_areas[:self.A], non_blocking=True)
+            h[self.A:].copy_(self.flag.to(torch.float64), non_blocking=True)
+            torch.cuda.current_stream(self.device).synchronize()
+            if h[self.A] != 0:
+                raise RuntimeError("cov_voronoi_clip: polygon capacity exceeded")
+            self._areas_host = h.numpy()[:self.A]
+        return self._areas_host
+
+
+class HybridVoronoi(ClippedVoronoi):
+    """The default partition object of the drop-in (`simulator.voronoi_bounded`): the cells are clipped on the DEVICE at
+    construction (nothing to wait for, nothing to upload), and scipy/Qhull -- what the reference calls,
+    simulator.py:154-191 -- runs on the host only on demand:
+      * when a coverage pass reports grid points within TIE_TOL of a bisector (cov_assign_reduce's tie counter): their
+        membership is decided by the reference's crossings test against the polygon VERTICES, and tie parity is defined
+        by live Qhull (SURVEY 7.4), so that pass is repeated with Qhull's polygons;
+      * when the host reads `vertices` / `filtered_regions` / `cell_vertices` (plotting, the reference's attribute names).
+    With no tie point the result of a pass depends on the cells only through nearest-seed membership (identical) and the
+    cell areas (device shoelace vs Qhull shoelace: 1e-11 relative, tests/test_gpu_coverage.py)."""
+
+    def __init__(self, points, bounding_box, device=None, reuse=None):
+        super().__init__(points, bounding_box, device=device, reuse=reuse)
+        self._points = np.array(points, dtype=np.float64, copy=True)
+        self._qhull = None
+
+    def qhull(self):
+        if self._qhull is None:
+            self._qhull = BoundedVoronoi(self._points, self.bounding_box)
+        return self._qhull
+
+    @property
+    def vertices(self):
+        return self.qhull().vertices
+
+    @property
+    def filtered_regions(self):
+        return self.qhull().filtered_regions
+
+    def cell_vertices(self, i):
+        return self.qhull().cell_vertices(i)
+
+    def areas(self):
+        if self._qhull is None and self._stale and self._areas_host is None:
+            self.qhull()             # the device buffers went to a later iteration: Qhull rebuilds the cells from the seeds
+        return self._qhull.areas() if self._qhull is not None else super().areas()
 
 
 def polygon_partition(seeds, polygons):
@@ -287,6 +348,7 @@ class CoverageGrid:
             np.ascontiguousarray(f_host, dtype=np.float64).reshape(-1)).to(self.device)
         self._work = None
         self._work_key = None
+        self._fin = None
         self.use_sweep = True        # tensor-product grids: column-sweep kernel (cov_assign_reduce_grid)
         if axes is None and base_index == 0:
             from ._engine import TensorAxes, detect_tensor_grid
@@ -302,6 +364,12 @@ class CoverageGrid:
 
     def upload(self, vor):
         """Device copy of a partition (BoundedVoronoi / polygon_partition); pass the result to assign_reduce to reuse it."""
+        if isinstance(vor, ClippedVoronoi) and vor._stale and not (isinstance(vor, HybridVoronoi)):
+            raise RuntimeError("this partition's device buffers were recycled by a later iteration (ClippedVoronoi reuse=)")
+        if isinstance(vor, HybridVoronoi) and (not vor.seeds_inside or vor._qhull is not None or vor._stale):
+            # Qhull's vertices: once they exist (an earlier pass met tie points / the host asked for them) they are the
+            # cells; and cells with a seed outside the box are not nearest-seed cells (every point takes the crossings test)
+            vor = vor.qhull()
         if vor is None or isinstance(vor, (_DevPartition, ClippedVoronoi, PackedPartition)):
             return vor if (vor is None or len(vor)) else None
         if not len(vor):
@@ -313,8 +381,12 @@ class CoverageGrid:
     def assign_reduce(self, lloyd_vor=None, loss_vor=None, w=None, var=None, want_members=False, tie_tol=None,
                       amax_k0=0.0, amax_rel=0.0, out=None):
         """One fused pass.  Returns a dict of DEVICE tensors: cent[Ac,4], amax_val[Ac], amax_idx[Ac], lossp[Ap,2],
-        members[G,words] (optional).  `out`: a dict returned by an earlier call with the same cell counts, reused."""
+        members[G,words] (optional), ties[1] (int32: points whose membership the crossings test decided).  `out`: a
+        dict returned by an earlier call with the same cell counts, reused."""
         dev = self.device
+        if want_members:         # membership masks are compared bit for bit with the reference's: Qhull's vertices decide ties
+            lloyd_vor = lloyd_vor.qhull() if isinstance(lloyd_vor, HybridVoronoi) else lloyd_vor
+            loss_vor = loss_vor.qhull() if isinstance(loss_vor, HybridVoronoi) else loss_vor
         C = self.upload(lloyd_vor)
         P = self.upload(loss_vor)
         Ac = C.A if C else 0
@@ -331,18 +403,19 @@ class CoverageGrid:
         if reuse:
             cent, amax_val, amax_idx, lossp = out["cent"], out["amax_val"], out["amax_idx"], out["lossp"]
         else:
-            # one packed buffer [cent 4 Ac | amax_val Ac | amax_idx Ac (int64 bits) | lossp 2 Ap]: results_to_host()
-            # brings everything home with ONE device->host copy
-            pack = torch.empty(6 * Ac + 2 * Ap, **f64)
-            out = {"pack": pack, "pack_shape": (Ac, Ap)}
+            # one packed buffer [cent 4 Ac | amax_val Ac | amax_idx Ac (int64 bits) | lossp 2 Ap | tie count (int32)]:
+            # results_to_host() brings everything home with ONE device->host copy
+            pack = torch.empty(6 * Ac + 2 * Ap + 1, **f64)
+            out = {"pack": pack, "pack_shape": (Ac, Ap), "ties": pack[6 * Ac + 2 * Ap:].view(torch.int32)[:1]}
             cent = pack[:4 * Ac].view(Ac, 4) if Ac else None
             amax_val = pack[4 * Ac:5 * Ac] if Ac else None
             amax_idx = pack[5 * Ac:6 * Ac].view(torch.int64) if Ac else None
-            lossp = pack[6 * Ac:].view(Ap, 2) if Ap else None
+            lossp = pack[6 * Ac:6 * Ac + 2 * Ap].view(Ap, 2) if Ap else None
         words = (max(Ac, Ap) + 63) // 64
         words = 1 if words <= 1 else (2 if words == 2 else 4)
         members = torch.zeros((self.G, words), dtype=torch.int64, device=dev) if (want_members and Ac) else None
         work = self._workspace(Ac, Ap)
+        ties = out["ties"]
         ny = self.axes.ny if self.axes is not None else 0
         if self.use_sweep and ny and members is None and math.isfinite(tie_tol) and self.G % ny == 0 \
                 and self.base_index % ny == 0:
@@ -353,7 +426,8 @@ class CoverageGrid:
                 nat.ptr(P.seeds) if P else None, Ap, nat.ptr(P.poly) if P else None, nat.ptr(P.off) if P else None,
                 P.nvert if P else 0,
                 ctypes.c_double(tie_tol), ctypes.c_double(amax_k0), ctypes.c_double(amax_rel), nat.ptr(cent),
-                nat.ptr(amax_val), nat.ptr(amax_idx), nat.ptr(lossp), nat.ptr(work), work.numel() * 8, nat.stream_ptr())
+                nat.ptr(amax_val), nat.ptr(amax_idx), nat.ptr(lossp), nat.ptr(ties), nat.ptr(work), work.numel() * 8,
+                nat.stream_ptr())
             nat.check(rc, "cov_assign_reduce_grid")
             out.update(cent=cent, amax_val=amax_val, amax_idx=amax_idx, lossp=lossp, members=None)
             return out
@@ -364,10 +438,20 @@ class CoverageGrid:
             nat.ptr(P.seeds) if P else None, Ap, nat.ptr(P.poly) if P else None, nat.ptr(P.off) if P else None,
             P.nvert if P else 0,
             ctypes.c_double(tie_tol), ctypes.c_double(amax_k0), ctypes.c_double(amax_rel), nat.ptr(cent), nat.ptr(amax_val), nat.ptr(amax_idx), nat.ptr(lossp),
-            nat.ptr(members), nat.ptr(work), work.numel() * 8, nat.stream_ptr())
+            nat.ptr(members), nat.ptr(ties), nat.ptr(work), work.numel() * 8, nat.stream_ptr())
         nat.check(rc, "cov_assign_reduce")
         out.update(cent=cent, amax_val=amax_val, amax_idx=amax_idx, lossp=lossp, members=members)
         return out
+
+    def reduce_to_host(self, lloyd_vor=None, loss_vor=None, **kw):
+        """assign_reduce + results_to_host with the Qhull fallback of HybridVoronoi partitions: if the pass met tie points
+        (membership decided by polygon vertices), it is repeated with Qhull's polygons -- exactly the reference's cells."""
+        host = self.results_to_host(self.assign_reduce(lloyd_vor, loss_vor, **kw))
+        hybrid = [v for v in (lloyd_vor, loss_vor) if isinstance(v, HybridVoronoi) and v._qhull is None]
+        if host["ties"] and hybrid:
+            q = [v.qhull() if isinstance(v, HybridVoronoi) else v for v in (lloyd_vor, loss_vor)]
+            host = self.results_to_host(self.assign_reduce(q[0], q[1], **kw))
+        return host
 
     @staticmethod
     def results_to_host(res):
@@ -379,32 +463,42 @@ class CoverageGrid:
         h.copy_(pack, non_blocking=True)
         torch.cuda.current_stream(pack.device).synchronize()
         a = h.numpy()
-        return {"cent": a[:4 * Ac].reshape(Ac, 4) if Ac else None,
+        return {"ties": int(a[6 * Ac + 2 * Ap:].view(np.int32)[0]),
+                "cent": a[:4 * Ac].reshape(Ac, 4) if Ac else None,
                 "amax_val": a[4 * Ac:5 * Ac] if Ac else None,
                 "amax_idx": a[5 * Ac:6 * Ac].view(np.int64) if Ac else None,
-                "lossp": a[6 * Ac:].reshape(Ap, 2) if Ap else None}
+                "lossp": a[6 * Ac:6 * Ac + 2 * Ap].reshape(Ap, 2) if Ap else None}
 
-    def finish(self, res, lloyd_vor, loss_vor, bbox, info=None):
-        """Device finishing of an assign_reduce result for DEVICE-resident partitions (ClippedVoronoi): returns
-        (loss, centroids[Ac,2], max_var[Ac], argmax_idx[Ac]) with ONE device->host copy (cov_finish), which also carries
-        the clip-capacity flags and (`info`: device int32, e.g. the Cholesky status) the caller's error state."""
+    def finish(self, res, lloyd_vor, loss_vor, bbox, info=None, with_ties=False):
+        """Device finishing of an assign_reduce result for DEVICE-resident partitions (ClippedVoronoi / HybridVoronoi):
+        returns (loss, centroids[Ac,2], max_var[Ac], argmax_idx[Ac]) -- plus the pass's tie count when `with_ties` -- with
+        ONE device->host copy (cov_finish), which also carries the clip-capacity flags and (`info`: device int32, e.g. the
+        Cholesky status) the caller's error state."""
         Ac = len(lloyd_vor) if lloyd_vor is not None else 0
         Ap = len(loss_vor) if loss_vor is not None else 0
-        out = torch.empty(4 + 4 * max(Ac, 1), dtype=torch.float64, device=self.device)
+        n = 5 + 4 * max(Ac, 1)
+        if self._fin is None or self._fin[0].numel() != n:
+            self._fin = (torch.empty(n, dtype=torch.float64, device=self.device),
+                         torch.empty(n, dtype=torch.float64, pin_memory=True))
+        out, host = self._fin
         nat.check(nat.lib().cov_finish(nat.ptr(res["cent"]), nat.ptr(lloyd_vor.dev_areas) if Ac else None, Ac,
                                        nat.ptr(res["lossp"]), nat.ptr(loss_vor.dev_areas) if Ap else None, Ap,
                                        nat.ptr(res["amax_val"]), nat.ptr(res["amax_idx"]), bbox[0], bbox[1], bbox[2], bbox[3],
                                        nat.ptr(info), nat.ptr(lloyd_vor.flag) if Ac else None,
-                                       nat.ptr(loss_vor.flag) if Ap else None, nat.ptr(out), nat.stream_ptr()), "cov_finish")
-        h = out.cpu().numpy()
+                                       nat.ptr(loss_vor.flag) if Ap else None, nat.ptr(res.get("ties")), nat.ptr(out),
+                                       nat.stream_ptr()), "cov_finish")
+        host.copy_(out, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        h = host.numpy()
         if h[1 + 4 * Ac] < 0:       # info = -1: the tiled Cholesky gave up waiting for a tile (internal error, not a pivot)
             raise RuntimeError("libmfgp_b200: the tiled Cholesky kernel gave up waiting for a tile (internal error)")
         if h[1 + 4 * Ac] != 0:
             raise np.linalg.LinAlgError(f"Matrix is not positive definite (pivot {int(h[1 + 4 * Ac]) - 1})")
         if h[2 + 4 * Ac] != 0 or h[3 + 4 * Ac] != 0:
             raise RuntimeError("cov_voronoi_clip: polygon capacity exceeded")
-        return float(h[0]), h[1:1 + 2 * Ac].reshape(Ac, 2).copy(), h[1 + 2 * Ac:1 + 3 * Ac].copy(), \
-            h[1 + 3 * Ac:1 + 4 * Ac].astype(np.int64)
+        r = (float(h[0]), h[1:1 + 2 * Ac].reshape(Ac, 2).copy(), h[1 + 2 * Ac:1 + 3 * Ac].copy(),
+             h[1 + 3 * Ac:1 + 4 * Ac].astype(np.int64))
+        return r + (int(h[4 + 4 * Ac]),) if with_ties else r
 
     def argmax(self, v_dev, k0=0.0, rel=0.0):
         """First-index argmax of a device vector (np.argmax semantics): returns (value, index) device tensors."""

@@ -363,16 +363,17 @@ class DeviceGP:
             self._xrange = (lo[0], hi[0], lo[1], hi[1])
         return self._xrange
 
-    def _cheb_orders(self, axes, p):
-        """(rxL, ryL, rxH, ryH) or None, cached while the training points stay inside the hull they were computed for."""
-        xlo, xhi, ylo, yhi = axes.xlo, axes.xhi, axes.ylo, axes.yhi
+    def _cheb_orders(self, axes, p, xlo, xhi):
+        """(rxL, ryL, rxH, ryH) or None for the column range whose x values span [xlo, xhi]; cached while the training
+        points stay inside the hull the orders were computed for."""
+        ylo, yhi = axes.ylo, axes.yhi
         t = self._training_range()
         c = self._forders
-        if c is not None and c[0] == (axes.uid, p["l_L"], p["l_H"], p["multi"]) and c[1][0] <= t[0] and c[1][1] >= t[1] \
+        if c is not None and c[0] == (axes.uid, xlo, xhi, p["l_L"], p["l_H"], p["multi"]) and c[1][0] <= t[0] and c[1][1] >= t[1] \
                 and c[1][2] <= t[2] and c[1][3] >= t[3]:
             return c[2]
-        mx, my = 0.05 * (xhi - xlo), 0.05 * (yhi - ylo)            # a margin, so that a few new samples do not invalidate it
-        hull = (min(t[0], xlo) - mx, max(t[1], xhi) + mx, min(t[2], ylo) - my, max(t[3], yhi) + my)
+        mx, my = 0.05 * (axes.xhi - axes.xlo), 0.05 * (yhi - ylo)      # a margin, so that a few new samples do not invalidate it
+        hull = (min(t[0], axes.xlo) - mx, max(t[1], axes.xhi) + mx, min(t[2], ylo) - my, max(t[3], yhi) + my)
         rxH = chebyshev_order(p["l_H"], xlo, xhi, hull[0], hull[1])
         ryH = chebyshev_order(p["l_H"], ylo, yhi, hull[2], hull[3])
         rxL = ryL = 0
@@ -382,12 +383,15 @@ class DeviceGP:
             ryL = chebyshev_order(p["l_L"], ylo, yhi, hull[2], hull[3])
             ok = rxL is not None and ryL is not None
         orders = (rxL, ryL, rxH, ryH) if ok else None
-        self._forders = ((axes.uid, p["l_L"], p["l_H"], p["multi"]), hull, orders)
+        self._forders = ((axes.uid, xlo, xhi, p["l_L"], p["l_H"], p["multi"]), hull, orders)
         return orders
 
     def _factored_plan(self, axes, g_lo, G):
         """Chebyshev orders + cost model.  None: keep the dense kernel (range is not whole columns, orders too large for
-        the 64-term budget, or the dense triangular products are cheaper -- small grids)."""
+        the 64-term budget, or the dense triangular products are cheaper -- small grids).
+        The x expansion covers only the interval of the REQUESTED columns: a grid shard (whole-column slice, grid sharding)
+        needs a lower order in x than the whole grid, so its right-hand-side count R = ry * rx -- and with it the forward
+        substitution, the one part of the fit that is not replicated work -- shrinks with the number of ranks."""
         ny = axes.ny
         if ny < 2 or axes.nx < 2 or g_lo % ny or G % ny:
             return None
@@ -396,22 +400,27 @@ class DeviceGP:
         dense = 0.5 * G * N * N
         if self.factored_min_gain > 0 and dense < 4e9:      # the dense kernel needs well under a millisecond: no plan
             return None
+        ix0, ncols = g_lo // ny, G // ny
+        if ncols < 2:
+            return None
+        xs = axes.ux_host[ix0:ix0 + ncols]
+        xlo, xhi = float(xs.min()), float(xs.max())
+        if not (xhi > xlo):
+            return None
         key = (axes.uid, g_lo, G, self.npad, p["l_L"], p["l_H"], p["multi"], self.factored_min_gain)
-        orders = self._cheb_orders(axes, p)
+        orders = self._cheb_orders(axes, p, xlo, xhi)
         if self._fplan is not None and self._fplan[0] == key and self._fplan[2] == orders:
             return self._fplan[1]
         plan = None
         if orders is not None:
             rxL, ryL, rxH, ryH = orders
-            ncols = G // ny
             ry, kp = max(ryL, ryH), -(-max(rxL, rxH) // 4) * 4         # both kernel parts share one Chebyshev basis
             R = ry * kp
             fact = 0.5 * N * N * R + ncols * N * R + ncols * N * 64 * 64 + G * 64 * 64
             if fact * self.factored_min_gain < dense:
                 chunk = max(64, min(-(-ncols // 64) * 64, ((1 << 28) // max(self.cap * max(ryL, ryH), 1)) // 64 * 64))   # <= 2 GiB of Y'
-                plan = dict(rxL=rxL, ryL=ryL, rxH=rxH, ryH=ryH, xlo=axes.xlo, xhi=axes.xhi, ylo=axes.ylo, yhi=axes.yhi,
-                            ix0=g_lo // ny,
-                            ncols=ncols, chunk=chunk, macs=fact, dense_macs=dense)
+                plan = dict(rxL=rxL, ryL=ryL, rxH=rxH, ryH=ryH, xlo=xlo, xhi=xhi, ylo=axes.ylo, yhi=axes.yhi,
+                            ix0=ix0, ncols=ncols, chunk=chunk, macs=fact, dense_macs=dense)
         self._fplan = (key, plan, orders)
         return plan
 
@@ -504,6 +513,7 @@ class DeviceGP:
         if self.N == 0:
             raise ValueError("likelihood of an empty model")
         self.ensure_factor(need_inverse=True)
+        self.check_factor(force=True)             # LinAlgError where the reference's np.linalg.cholesky raises (:100, :380)
         lib = nat.lib()
         need = int(lib.mfgp_nlml_workspace_bytes(self.npad))
         if self._twork is None or self._twork.numel() * 8 < need:

@@ -80,18 +80,18 @@ SIGNATURES = {
     "cov_assign_reduce": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64,
                                   c_void_p, c_int64, c_void_p, c_void_p, c_int64,
                                   c_void_p, c_int64, c_void_p, c_void_p, c_int64,
-                                  c_double, c_double, c_double, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                  c_double, c_double, c_double, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                   c_void_p, c_int64, c_void_p]),
     "cov_workspace_bytes": (c_int64, [c_int64, c_int64, c_int64]),
     "cov_assign_reduce_grid": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64,
                                        c_void_p, c_int64, c_void_p, c_void_p, c_int64,
                                        c_void_p, c_int64, c_void_p, c_void_p, c_int64,
-                                       c_double, c_double, c_double, c_void_p, c_void_p, c_void_p, c_void_p,
+                                       c_double, c_double, c_double, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                        c_void_p, c_int64, c_void_p]),
     "cov_voronoi_clip": (c_int, [c_void_p, c_int64, c_double, c_double, c_double, c_double, c_double, c_void_p, c_void_p,
                                  c_int64, c_void_p, c_void_p, c_void_p]),
     "cov_finish": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_double,
-                           c_double, c_double, c_double, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+                           c_double, c_double, c_double, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "cov_argmax": (c_int, [c_void_p, c_int64, c_int64, c_double, c_double, c_void_p, c_void_p, c_void_p, c_int64,
                            c_void_p]),
     "choi_greedy": (c_int64, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p,

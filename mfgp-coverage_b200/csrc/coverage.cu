@@ -40,6 +40,7 @@ struct CovArgs {
     const uint4* buckets_c; const uint4* buckets_p;   // candidate tables (cov_build_buckets_kernel)
     const double* geom_c; const double* geom_p;       // {x0, y0, 1/h} of each table
     int nb_c, nb_p;
+    int* tie_count;       // optional: number of (point, partition) pairs whose membership the crossings test decided
 };
 
 // matplotlib _path.h point_in_path_impl, radius 0, no codes (implicitly closed polygon): SURVEY.md Appendix A.1
@@ -67,7 +68,7 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
-constexpr int CELL_NONE = -1, CELL_TIE = -2;
+constexpr int CELL_NONE = -1, CELL_TIE = -2, CELL_TIE_HARD = -3;   // HARD: gap <= tie_tol / 10 (counted in tie_count)
 constexpr int CA_THREADS = 128, CA_WARPS = CA_THREADS / 32, CA_BLOCKS_PER_SM = 6;   // assignment kernel CTA shape
 constexpr int BK_MAX = 15;            // candidate ids per bucket entry (16 bytes: count + 15 ids)
 constexpr unsigned BK_OVERFLOW = 255; // count byte: scan all seeds
@@ -191,7 +192,8 @@ __device__ __forceinline__ int classify_point(const BucketGrid& bg, const double
             else if (d < second) second = d;
         }
     }
-    return (second - best > tie_tol) ? bi : CELL_TIE;
+    const double gap = second - best;
+    return (gap > tie_tol) ? bi : ((gap > 0.1 * tie_tol) ? CELL_TIE : CELL_TIE_HARD);
 }
 
 // membership words of one point (test / in_polygon output): the nearest cell, or the crossings test for tie points
@@ -263,7 +265,7 @@ __device__ __noinline__ void flush_p(double s0, int cnt, double* __restrict__ sl
 // 0, 1 or several cells.
 __device__ __noinline__ void mixed_c(int A, bool with_var, TieRule tol, const double* __restrict__ s_poly,
                                      const int* __restrict__ s_off, double* __restrict__ wacc, int cell, double x, double y,
-                                     double wv, double vv, long long gidx, int lane) {
+                                     double wv, double vv, long long gidx, int lane, int* ties) {
     unsigned pending = __ballot_sync(0xffffffffu, cell >= 0);
     while (pending) {
         const int c = __shfl_sync(0xffffffffu, cell, __ffs(pending) - 1);
@@ -275,7 +277,9 @@ __device__ __noinline__ void mixed_c(int A, bool with_var, TieRule tol, const do
         if (lane == 0) slot_add_c(wacc + c * C_SLOTS, s0, s1, s2, __popc(who), am, with_var, tol);
         pending &= ~who;
     }
-    if (__any_sync(0xffffffffu, cell == CELL_TIE)) {
+    const unsigned tied = __ballot_sync(0xffffffffu, cell == CELL_TIE);
+    if (tied) {
+        if (ties != nullptr && lane == 0) atomicAdd(ties, __popc(tied));
         for (int c = 0; c < A; c++) {
             const bool mine = cell == CELL_TIE && crossings_inside(s_poly + 2 * s_off[c], s_off[c + 1] - s_off[c], x, y);
             const unsigned who = __ballot_sync(0xffffffffu, mine);
@@ -289,7 +293,7 @@ __device__ __noinline__ void mixed_c(int A, bool with_var, TieRule tol, const do
 }
 __device__ __noinline__ void mixed_p(int A, const double* __restrict__ s_seeds, const double* __restrict__ s_poly,
                                      const int* __restrict__ s_off, double* __restrict__ wacc_p, int cell, double x, double y,
-                                     double fv, int lane) {
+                                     double fv, int lane, int* ties) {
     unsigned pending = __ballot_sync(0xffffffffu, cell >= 0);
     while (pending) {
         const int c = __shfl_sync(0xffffffffu, cell, __ffs(pending) - 1);
@@ -301,7 +305,9 @@ __device__ __noinline__ void mixed_p(int A, const double* __restrict__ s_seeds, 
         if (lane == 0) { wacc_p[c * P_SLOTS] += s0; wacc_p[c * P_SLOTS + 1] += (double)__popc(who); }
         pending &= ~who;
     }
-    if (__any_sync(0xffffffffu, cell == CELL_TIE)) {
+    const unsigned tied = __ballot_sync(0xffffffffu, cell == CELL_TIE);
+    if (tied) {
+        if (ties != nullptr && lane == 0) atomicAdd(ties, __popc(tied));
         for (int c = 0; c < A; c++) {
             const bool mine = cell == CELL_TIE && crossings_inside(s_poly + 2 * s_off[c], s_off[c + 1] - s_off[c], x, y);
             const unsigned who = __ballot_sync(0xffffffffu, mine);
@@ -388,7 +394,12 @@ __global__ void __launch_bounds__(CA_THREADS, CA_BLOCKS_PER_SM) cov_assign_reduc
         const double x = nxy.x, y = nxy.y, wv = nw, vv = nv, fv = nf;
         fetch(row + 1);
         if (Ac) {
-            const int cell = !valid ? CELL_NONE : (polygon_mode ? CELL_TIE : classify_point(bgc, s_seed_c, Ac, x, y, tie_tol));
+            int cell = !valid ? CELL_NONE : (polygon_mode ? CELL_TIE : classify_point(bgc, s_seed_c, Ac, x, y, tie_tol));
+            {
+                const unsigned hm = __ballot_sync(0xffffffffu, cell == CELL_TIE_HARD);
+                if (hm && a.tie_count != nullptr && lane == 0) atomicAdd(a.tie_count, __popc(hm));
+                if (cell == CELL_TIE_HARD) cell = CELL_TIE;
+            }
             if (a.member_c && valid) write_members<WORDS>(a.member_c + g * WORDS, cell, s_poly_c, s_off_c, Ac, x, y);
             const int c0 = __shfl_sync(0xffffffffu, cell, 0);       // lane 0 is valid whenever the row holds any point
             if (c0 >= 0 && __all_sync(0xffffffffu, cell == c0 || cell == CELL_NONE)) {
@@ -409,11 +420,16 @@ __global__ void __launch_bounds__(CA_THREADS, CA_BLOCKS_PER_SM) cov_assign_reduc
                     }
                 }
             } else {
-                mixed_c(Ac, with_var, tol, s_poly_c, s_off_c, wacc, cell, x, y, wv, vv, (long long)(base_index + g), lane);
+                mixed_c(Ac, with_var, tol, s_poly_c, s_off_c, wacc, cell, x, y, wv, vv, (long long)(base_index + g), lane, nullptr);
             }
         }
         if (Ap) {
-            const int cell = !valid ? CELL_NONE : (polygon_mode ? CELL_TIE : classify_point(bgp, s_seed_p, Ap, x, y, tie_tol));
+            int cell = !valid ? CELL_NONE : (polygon_mode ? CELL_TIE : classify_point(bgp, s_seed_p, Ap, x, y, tie_tol));
+            {
+                const unsigned hm = __ballot_sync(0xffffffffu, cell == CELL_TIE_HARD);
+                if (hm && a.tie_count != nullptr && lane == 0) atomicAdd(a.tie_count, __popc(hm));
+                if (cell == CELL_TIE_HARD) cell = CELL_TIE;
+            }
             const int c0 = __shfl_sync(0xffffffffu, cell, 0);
             if (c0 >= 0 && __all_sync(0xffffffffu, cell == c0 || cell == CELL_NONE)) {
                 if (c0 != cur_p) {
@@ -427,7 +443,7 @@ __global__ void __launch_bounds__(CA_THREADS, CA_BLOCKS_PER_SM) cov_assign_reduc
                     p_cnt++;
                 }
             } else {
-                mixed_p(Ap, s_seed_p, s_poly_p, s_off_p, wacc + Ac * C_SLOTS, cell, x, y, fv, lane);
+                mixed_p(Ap, s_seed_p, s_poly_p, s_off_p, wacc + Ac * C_SLOTS, cell, x, y, fv, lane, nullptr);
             }
         }
     }
@@ -608,7 +624,8 @@ __global__ void __launch_bounds__(SW_THREADS, 2) cov_sweep_kernel(CovArgs a, Swe
         fetch(col + SW_DEPTH, nxy[d], nw[d], nv[d], nf[d]);
         if (Ac) {
             const int cell = lane_ok ? classify_point(bgc, s_seed_c, Ac, x, y, tie_tol) : CELL_NONE;
-            const bool tie = cell == CELL_TIE;
+            const bool tie = cell == CELL_TIE || cell == CELL_TIE_HARD;
+            const bool hard = cell == CELL_TIE_HARD;
             const int ncell = tie ? CELL_NONE : cell;
             const bool chg = ncell != cur_c;
             const bool psh = chg && cur_c >= 0;
@@ -635,6 +652,10 @@ __global__ void __launch_bounds__(SW_THREADS, 2) cov_sweep_kernel(CovArgs a, Swe
                 }
             }
             const unsigned tm = __ballot_sync(0xffffffffu, tie);
+            if (tm && a.tie_count != nullptr) {
+                const unsigned hm = __ballot_sync(0xffffffffu, hard);
+                if (hm && lane == 0) atomicAdd(a.tie_count, __popc(hm));
+            }
             if (tm) {
                 if (tn_c + __popc(tm) > SW_QCAP) {
                     sweep_drain_c(qc, qn_c, wacc, with_var, tol, lane); qn_c = 0;      // keep slot order: queue first
@@ -646,7 +667,8 @@ __global__ void __launch_bounds__(SW_THREADS, 2) cov_sweep_kernel(CovArgs a, Swe
         }
         if (Ap) {
             const int cell = lane_ok ? classify_point(bgp, s_seed_p, Ap, x, y, tie_tol) : CELL_NONE;
-            const bool tie = cell == CELL_TIE;
+            const bool tie = cell == CELL_TIE || cell == CELL_TIE_HARD;
+            const bool hard = cell == CELL_TIE_HARD;
             const int ncell = tie ? CELL_NONE : cell;
             const bool chg = ncell != cur_p;
             const bool psh = chg && cur_p >= 0;
@@ -666,6 +688,10 @@ __global__ void __launch_bounds__(SW_THREADS, 2) cov_sweep_kernel(CovArgs a, Swe
                 p_cnt++;
             }
             const unsigned tm = __ballot_sync(0xffffffffu, tie);
+            if (tm && a.tie_count != nullptr) {
+                const unsigned hm = __ballot_sync(0xffffffffu, hard);
+                if (hm && lane == 0) atomicAdd(a.tie_count, __popc(hm));
+            }
             if (tm) {
                 if (tn_p + __popc(tm) > SW_QCAP) {
                     sweep_drain_p(qp, qn_p, wacc_p, lane); qn_p = 0;
@@ -806,8 +832,8 @@ static int cov_assign_reduce_impl(const double* xy, const double* w, const doubl
                                  int64_t base_index, const double* seeds_c, int64_t Ac, const double* poly_xy_c,
                                  const int32_t* poly_off_c, int64_t nvert_c, const double* seeds_p, int64_t Ap,
                                  const double* poly_xy_p, const int32_t* poly_off_p, int64_t nvert_p, double tie_tol, double amax_k0, double amax_rel, double* cent, double* amax_val,
-                                 int64_t* amax_idx, double* lossp, uint64_t* member_c, void* work, int64_t work_bytes,
-                                 void* stream, int64_t ny) {
+                                 int64_t* amax_idx, double* lossp, uint64_t* member_c, int32_t* tie_count, void* work,
+                                 int64_t work_bytes, void* stream, int64_t ny) {
     if (!xy || G <= 0 || Ac < 0 || Ap < 0 || Ac + Ap == 0 || Ac > COV_MAX_CELLS || Ap > COV_MAX_CELLS) return MFGP_ERR_INVALID;
     if (Ac && (!seeds_c || !poly_xy_c || !poly_off_c)) return MFGP_ERR_INVALID;
     if (Ap && (!seeds_p || !poly_xy_p || !poly_off_p || !f)) return MFGP_ERR_INVALID;
@@ -820,6 +846,8 @@ static int cov_assign_reduce_impl(const double* xy, const double* w, const doubl
     a.C = {seeds_c, (int)Ac, poly_xy_c, poly_off_c};
     a.P = {seeds_p, (int)Ap, poly_xy_p, poly_off_p};
     a.tie_tol = tie_tol; a.amax_tol = TieRule{amax_k0, amax_rel > 0.0 ? amax_rel : 0.0}; a.member_c = member_c; a.partials = static_cast<double*>(work);
+    a.tie_count = tie_count;
+    if (tie_count) MFGP_CUDA_CHECK(cudaMemsetAsync(tie_count, 0, sizeof(int32_t), st));
     const int stride = (int)(Ac * C_SLOTS + Ap * P_SLOTS);
     {   // candidate bucket tables live behind the block partials in the workspace
         const int64_t nbmax = COV_MAX_BLOCKS;
@@ -886,10 +914,10 @@ extern "C" int cov_assign_reduce(const double* xy, const double* w, const double
                                  const int32_t* poly_off_c, int64_t nvert_c, const double* seeds_p, int64_t Ap,
                                  const double* poly_xy_p, const int32_t* poly_off_p, int64_t nvert_p, double tie_tol, double amax_k0,
                                  double amax_rel, double* cent, double* amax_val, int64_t* amax_idx, double* lossp,
-                                 uint64_t* member_c, void* work, int64_t work_bytes, void* stream) {
+                                 uint64_t* member_c, int32_t* tie_count, void* work, int64_t work_bytes, void* stream) {
     return cov_assign_reduce_impl(xy, w, var, f, G, base_index, seeds_c, Ac, poly_xy_c, poly_off_c, nvert_c, seeds_p, Ap, poly_xy_p,
-                                  poly_off_p, nvert_p, tie_tol, amax_k0, amax_rel, cent, amax_val, amax_idx, lossp, member_c, work,
-                                  work_bytes, stream, 0);
+                                  poly_off_p, nvert_p, tie_tol, amax_k0, amax_rel, cent, amax_val, amax_idx, lossp, member_c,
+                                  tie_count, work, work_bytes, stream, 0);
 }
 
 extern "C" int cov_assign_reduce_grid(const double* xy, const double* w, const double* var, const double* f, int64_t G, int64_t ny,
@@ -897,11 +925,11 @@ extern "C" int cov_assign_reduce_grid(const double* xy, const double* w, const d
                                       const int32_t* poly_off_c, int64_t nvert_c, const double* seeds_p, int64_t Ap,
                                       const double* poly_xy_p, const int32_t* poly_off_p, int64_t nvert_p, double tie_tol,
                                       double amax_k0, double amax_rel, double* cent, double* amax_val, int64_t* amax_idx,
-                                      double* lossp, void* work, int64_t work_bytes, void* stream) {
+                                      double* lossp, int32_t* tie_count, void* work, int64_t work_bytes, void* stream) {
     if (ny <= 0 || G % ny) return MFGP_ERR_INVALID;
     return cov_assign_reduce_impl(xy, w, var, f, G, base_index, seeds_c, Ac, poly_xy_c, poly_off_c, nvert_c, seeds_p, Ap, poly_xy_p,
-                                  poly_off_p, nvert_p, tie_tol, amax_k0, amax_rel, cent, amax_val, amax_idx, lossp, nullptr, work,
-                                  work_bytes, stream, ny);
+                                  poly_off_p, nvert_p, tie_tol, amax_k0, amax_rel, cent, amax_val, amax_idx, lossp, nullptr,
+                                  tie_count, work, work_bytes, stream, ny);
 }
 
 extern "C" int cov_argmax(const double* v, int64_t G, int64_t base_index, double k0, double rel, double* out_val,
@@ -931,72 +959,117 @@ extern "C" int cov_argmax(const double* v, int64_t G, int64_t base_index, double
 // (simulator.py:127-136).  flag[0] != 0: a polygon outgrew VC_MAXV or the packed capacity.
 namespace mfgp {
 constexpr int VC_MAXV = 48;
+constexpr int VC_WARPS = 16;
 
-__global__ void __launch_bounds__(256) cov_voronoi_clip_kernel(const double* __restrict__ seeds, int A, double x0, double x1, double y0,
-                                                               double y1, double* __restrict__ poly_xy, int32_t* __restrict__ poly_off,
-                                                               int cap_vertices, double* __restrict__ areas, int32_t* __restrict__ flag) {
+// One WARP per cell, lane = polygon vertex (two slots per lane: up to 64 >= VC_MAXV vertices).  A clip against one bisector
+// is: signed distances of every vertex and of its predecessor in parallel, two ballots (vertex kept / edge crosses), output
+// slots by prefix popcount -- the same vertices, from the same fp operations, in the same order as the sequential
+// Sutherland-Hodgman sweep (crossing point first, then the kept vertex).  Most bisectors do not touch the cell once its
+// nearest neighbours have been applied: one ballot rejects them.  Pass 1 counts the vertices (-> packed offsets), pass 2
+// clips again and writes vertices + shoelace area (a cell costs a few thousand cycles; a stash would not pay).
+__device__ __forceinline__ int vc_clip_cell(const double* __restrict__ s_seeds, int A, int i, double x0, double x1, double y0,
+                                            double y1, double* __restrict__ buf, int lane, bool& overflow, int& which) {
+    // buf: [2 ping-pong][2 coords][64]
+    double* P = buf;
+    double* Q = buf + 128;
+    if (lane < 4) {
+        P[lane] = (lane == 0 || lane == 3) ? x0 : x1;
+        P[64 + lane] = (lane < 2) ? y0 : y1;
+    }
+    __syncwarp();
+    int n = 4;
+    which = 0;
+    const double sx = s_seeds[2 * i], sy = s_seeds[2 * i + 1];
+    const unsigned lt = (1u << lane) - 1u;
+    for (int j = 0; j < A && n > 0; j++) {
+        if (j == i) continue;
+        const double tx = s_seeds[2 * j], ty = s_seeds[2 * j + 1];
+        const double nx = tx - sx, ny = ty - sy;
+        if (nx == 0.0 && ny == 0.0) continue;                      // coincident seeds share one cell
+        const double c = 0.5 * ((tx * tx + ty * ty) - (sx * sx + sy * sy));
+        double bx[2], by[2], ax[2], ay[2], da[2], db[2];
+        bool valid[2], inb[2], cross[2];
+        bool any_out = false;
+#pragma unroll
+        for (int sl = 0; sl < 2; sl++) {
+            const int v = lane + 32 * sl;
+            valid[sl] = v < n;
+            const int u = valid[sl] ? (v + n - 1) % n : 0, vv = valid[sl] ? v : 0;
+            bx[sl] = P[vv]; by[sl] = P[64 + vv]; ax[sl] = P[u]; ay[sl] = P[64 + u];
+            db[sl] = nx * bx[sl] + ny * by[sl] - c;
+            da[sl] = nx * ax[sl] + ny * ay[sl] - c;
+            inb[sl] = valid[sl] && db[sl] <= 0.0;
+            cross[sl] = valid[sl] && ((da[sl] <= 0.0) != (db[sl] <= 0.0));
+            any_out = any_out || (valid[sl] && !(db[sl] <= 0.0));
+        }
+        if (!__any_sync(0xffffffffu, any_out)) continue;           // the whole polygon lies on the near side: unchanged
+        const unsigned c0 = __ballot_sync(0xffffffffu, cross[0]), i0 = __ballot_sync(0xffffffffu, inb[0]);
+        const unsigned c1 = __ballot_sync(0xffffffffu, cross[1]), i1 = __ballot_sync(0xffffffffu, inb[1]);
+        const int tot0 = __popc(c0) + __popc(i0);
+        const int m = tot0 + __popc(c1) + __popc(i1);
+        int pos[2] = {__popc(c0 & lt) + __popc(i0 & lt), tot0 + __popc(c1 & lt) + __popc(i1 & lt)};
+#pragma unroll
+        for (int sl = 0; sl < 2; sl++) {
+            int o = pos[sl];
+            if (cross[sl]) {
+                const double t = da[sl] / (da[sl] - db[sl]);
+                if (o < VC_MAXV) { Q[o] = ax[sl] + (bx[sl] - ax[sl]) * t; Q[64 + o] = ay[sl] + (by[sl] - ay[sl]) * t; }
+                o++;
+            }
+            if (inb[sl] && o < VC_MAXV) { Q[o] = bx[sl]; Q[64 + o] = by[sl]; }
+        }
+        n = m;
+        if (n > VC_MAXV) { overflow = true; n = VC_MAXV; }
+        double* T = P; P = Q; Q = T;
+        which ^= 1;
+        __syncwarp();
+    }
+    return n;
+}
+
+__global__ void __launch_bounds__(VC_WARPS * 32) cov_voronoi_clip_kernel(const double* __restrict__ seeds, int A, double x0, double x1,
+                                                                         double y0, double y1, double* __restrict__ poly_xy,
+                                                                         int32_t* __restrict__ poly_off, int cap_vertices,
+                                                                         double* __restrict__ areas, int32_t* __restrict__ flag) {
     __shared__ int counts[COV_MAX_CELLS + 1];
     __shared__ double s_seeds[2 * COV_MAX_CELLS];
-    const int i = threadIdx.x;
-    for (int e = i; e < 2 * A; e += blockDim.x) s_seeds[e] = seeds[e];
+    __shared__ double s_buf[VC_WARPS][256];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int e = tid; e < 2 * A; e += blockDim.x) s_seeds[e] = seeds[e];
+    if (tid == 0) counts[0] = 0;
     __syncthreads();
-    double px[VC_MAXV], py[VC_MAXV], qx[VC_MAXV], qy[VC_MAXV];
-    int n = 0;
     bool overflow = false;
-    if (i < A) {
-        px[0] = x0; py[0] = y0; px[1] = x1; py[1] = y0; px[2] = x1; py[2] = y1; px[3] = x0; py[3] = y1;
-        n = 4;
-        const double sx = s_seeds[2 * i], sy = s_seeds[2 * i + 1];
-        for (int j = 0; j < A && n > 0; j++) {
-            if (j == i) continue;
-            const double tx = s_seeds[2 * j], ty = s_seeds[2 * j + 1];
-            const double nx = tx - sx, ny = ty - sy;
-            if (nx == 0.0 && ny == 0.0) continue;                      // coincident seeds share one cell
-            const double c = 0.5 * ((tx * tx + ty * ty) - (sx * sx + sy * sy));
-            // quick reject: the whole polygon on the near side
-            int m = 0;
-            double da = nx * px[n - 1] + ny * py[n - 1] - c;
-            for (int v = 0; v < n; v++) {
-                const double ax = px[(v + n - 1) % n], ay = py[(v + n - 1) % n];
-                const double bx = px[v], by = py[v];
-                const double db = nx * bx + ny * by - c;
-                if ((da <= 0.0) != (db <= 0.0)) {                      // edge crosses the bisector
-                    const double t = da / (da - db);
-                    if (m < VC_MAXV) { qx[m] = ax + (bx - ax) * t; qy[m] = ay + (by - ay) * t; }
-                    m++;
-                }
-                if (db <= 0.0) {
-                    if (m < VC_MAXV) { qx[m] = bx; qy[m] = by; }
-                    m++;
-                }
-                da = db;
-            }
-            if (m > VC_MAXV) { overflow = true; m = VC_MAXV; }
-            n = m;
-            for (int v = 0; v < n; v++) { px[v] = qx[v]; py[v] = qy[v]; }
-        }
-        counts[i + 1] = n;
+    int which = 0;
+    for (int i = warp; i < A; i += VC_WARPS) {                    // pass 1: vertex counts
+        const int n = vc_clip_cell(s_seeds, A, i, x0, x1, y0, y1, s_buf[warp], lane, overflow, which);
+        if (lane == 0) counts[i + 1] = n;
+        __syncwarp();
     }
-    if (i == 0) counts[0] = 0;
     __syncthreads();
-    if (i == 0)
+    if (tid == 0)
         for (int c = 1; c <= A; c++) counts[c] += counts[c - 1];
     __syncthreads();
-    if (i <= A) poly_off[i] = counts[i];
-    if (i < A) {
+    for (int e = tid; e <= A; e += blockDim.x) poly_off[e] = counts[e];
+    for (int i = warp; i < A; i += VC_WARPS) {                    // pass 2: vertices + area
+        const int n = vc_clip_cell(s_seeds, A, i, x0, x1, y0, y1, s_buf[warp], lane, overflow, which);
+        const double* px = s_buf[warp] + 128 * which;
+        const double* py = px + 64;
         const int o = counts[i];
         if (o + n > cap_vertices) overflow = true;
         else
-            for (int v = 0; v < n; v++) { poly_xy[2 * (o + v)] = px[v]; poly_xy[2 * (o + v) + 1] = py[v]; }
-        // shoelace: 0.5 |x . roll(y,1) - y . roll(x,1)|
-        double s1 = 0.0, s2 = 0.0;
-        for (int v = 0; v < n; v++) {
-            const int u = (v + n - 1) % n;
-            s1 += px[v] * py[u];
-            s2 += py[v] * px[u];
+            for (int v = lane; v < n; v += 32) { poly_xy[2 * (o + v)] = px[v]; poly_xy[2 * (o + v) + 1] = py[v]; }
+        if (lane == 0) {
+            // shoelace: 0.5 |x . roll(y,1) - y . roll(x,1)|, summed in vertex order
+            double s1 = 0.0, s2 = 0.0;
+            for (int v = 0; v < n; v++) {
+                const int u = (v + n - 1) % n;
+                s1 += px[v] * py[u];
+                s2 += py[v] * px[u];
+            }
+            areas[i] = overflow ? __longlong_as_double(0x7ff8000000000000LL) : 0.5 * fabs(s1 - s2);   // NaN poisons loss / centroid
+            if (overflow) atomicExch(flag, 1);
         }
-        areas[i] = overflow ? __longlong_as_double(0x7ff8000000000000LL) : 0.5 * fabs(s1 - s2);   // NaN poisons loss / centroid
-        if (overflow) atomicExch(flag, 1);
+        __syncwarp();
     }
 }
 
@@ -1007,12 +1080,14 @@ __global__ void cov_finish_kernel(const double* __restrict__ cent, const double*
                                   const double* __restrict__ lossp, const double* __restrict__ areas_p, int Ap,
                                   const double* __restrict__ amax_val, const int64_t* __restrict__ amax_idx, double xmin,
                                   double xmax, double ymin, double ymax, const int32_t* __restrict__ flag0,
-                                  const int32_t* __restrict__ flag1, const int32_t* __restrict__ flag2, double* __restrict__ out) {
+                                  const int32_t* __restrict__ flag1, const int32_t* __restrict__ flag2,
+                                  const int32_t* __restrict__ flag3, double* __restrict__ out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i == 0) {
         out[1 + 4 * Ac] = flag0 ? (double)*flag0 : 0.0;      // e.g. the Cholesky `info` and the clip-capacity flags: the
         out[2 + 4 * Ac] = flag1 ? (double)*flag1 : 0.0;      // host learns about a failure without an extra sync
         out[3 + 4 * Ac] = flag2 ? (double)*flag2 : 0.0;
+        out[4 + 4 * Ac] = flag3 ? (double)*flag3 : 0.0;      // e.g. cov_assign_reduce's tie counter
         double loss = 0.0;
         for (int c = 0; c < Ap; c++) loss += (lossp[2 * c] / lossp[2 * c + 1]) * areas_p[c];     // cell order, like :215-219
         out[0] = Ap ? loss : 0.0;
@@ -1040,7 +1115,7 @@ extern "C" int cov_voronoi_clip(const double* seeds, int64_t A, double xmin, dou
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     MFGP_CUDA_CHECK(cudaMemsetAsync(flag, 0, sizeof(int32_t), st));
     const double h = 0.5 * eps;
-    cov_voronoi_clip_kernel<<<1, 256, 0, st>>>(seeds, (int)A, xmin - h, xmax + h, ymin - h, ymax + h, poly_xy, poly_off,
+    cov_voronoi_clip_kernel<<<1, VC_WARPS * 32, 0, st>>>(seeds, (int)A, xmin - h, xmax + h, ymin - h, ymax + h, poly_xy, poly_off,
                                                (int)cap_vertices, areas, flag);
     MFGP_LAUNCH_CHECK();
     return MFGP_OK;
@@ -1048,13 +1123,13 @@ extern "C" int cov_voronoi_clip(const double* seeds, int64_t A, double xmin, dou
 
 extern "C" int cov_finish(const double* cent, const double* areas_c, int64_t Ac, const double* lossp, const double* areas_p,
                           int64_t Ap, const double* amax_val, const int64_t* amax_idx, double xmin, double xmax, double ymin,
-                          double ymax, const int32_t* flag0, const int32_t* flag1, const int32_t* flag2, double* out,
-                          void* stream) {
+                          double ymax, const int32_t* flag0, const int32_t* flag1, const int32_t* flag2, const int32_t* flag3,
+                          double* out, void* stream) {
     if (!out || Ac < 0 || Ap < 0 || (Ac && (!cent || !areas_c)) || (Ap && (!lossp || !areas_p))) return MFGP_ERR_INVALID;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int n = (int)(Ac > 1 ? Ac : 1);
     cov_finish_kernel<<<(n + 127) / 128, 128, 0, st>>>(cent, areas_c, (int)Ac, lossp, areas_p, (int)Ap, amax_val, amax_idx, xmin, xmax,
-                                                      ymin, ymax, flag0, flag1, flag2, out);
+                                                      ymin, ymax, flag0, flag1, flag2, flag3, out);
     MFGP_LAUNCH_CHECK();
     return MFGP_OK;
 }

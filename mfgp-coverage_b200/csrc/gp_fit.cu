@@ -181,9 +181,232 @@ __device__ __forceinline__ void potrf_diag_body(const double* src, int64_t lds, 
         }
 }
 
+// ---- the same sweep, software-pipelined ------------------------------------------------------------------------------
+// The sweep above is one serial chain per step (barrier -> pivot block -> reciprocal -> scaled columns -> FMA -> publish,
+// ~310 cycles of dependent latency) FOLLOWED by the bulk rank-2 update of the registers (~200 issue cycles on the shared
+// FP64 pipe): 820 cycles per step.  Only the two columns / rows of the NEXT pivot pair feed the chain, so here
+//   iteration k:  wait(k)  ->  chain(k): pivot block, P^-1, t(k) = U P^-1 for the thread's rows
+//                          ->  update k applied to the next pair's columns of S / rows of M only, published, arrive(k+1)
+//   and, in the same basic block with no barrier in between, the DEFERRED bulk update of step k-1 on all other
+//   registers (operands re-read from a 3-deep ring of published pairs), whose independent FMAs fill the chain's latency.
+// Arrival and wait are split (one mbarrier, 256 arrivals per phase), so a thread publishes, arrives and goes on with
+// work that does not depend on the others.  Same arithmetic per element as potrf_diag_body (the reciprocal of the 2x2
+// determinant is MUFU + two Newton steps instead of a division: no slow-path branch inside the scheduling region).
+struct PotrfScratch {
+    double2 col[3][PB];      // (.x, .y) = columns (j0, j1) of S as published for a step
+    double2 row[3][PB];      // rows (j0, j1) of M
+    double piv[3][PB / 2];
+    double fin[3][PB / 2];
+    unsigned long long bar;
+    int bad;
+};
+
+__device__ __forceinline__ double rcp_newton(double d) {
+    double x;
+    asm("rcp.approx.ftz.f64 %0, %1;\n" : "=d"(x) : "d"(d));
+    double e = fma(-d, x, 1.0);
+    x = fma(x, e, x);
+    e = fma(-d, x, 1.0);
+    return fma(x, e, x);
+}
+
+__device__ __forceinline__ void potrf_diag_pipe(const double* src, int64_t lds, double* A, int64_t ld,
+                                                double* __restrict__ Winv, int64_t ldw, int32_t* __restrict__ info, int jblk,
+                                                PotrfScratch* sc) {
+    const int tid = threadIdx.x;
+    const int ti = tid >> 4, tc = tid & 15;
+    const unsigned bar = static_cast<unsigned>(__cvta_generic_to_shared(&sc->bar));
+    if (tid == 0) {
+        sc->bad = 0;
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(256));
+    }
+    double s[4][4], m[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; a++)
+#pragma unroll
+        for (int b = 0; b < 4; b++) {
+            const int r = ti + 16 * a, c = tc + 16 * b;
+            s[a][b] = (c <= r) ? src[(int64_t)r * lds + c] : 0.0;
+            m[a][b] = (r == c) ? 1.0 : 0.0;
+        }
+    __syncthreads();                      // barrier initialised; `src` may alias nothing the ring overwrites
+    // publish pair 0 into ring slot 0
+    if ((tc & 14) == 0) {
+        double* dst = reinterpret_cast<double*>(sc->col[0]) + (tc & 1);
+#pragma unroll
+        for (int a = 0; a < 4; a++) dst[2 * (ti + 16 * a)] = s[a][0];
+    }
+    if ((ti & 14) == 0) {
+        double* dst = reinterpret_cast<double*>(sc->row[0]) + (ti & 1);
+#pragma unroll
+        for (int b = 0; b < 4; b++) dst[2 * (tc + 16 * b)] = m[0][b];
+    }
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory");
+    double tp1[4] = {0.0, 0.0, 0.0, 0.0}, tp2[4] = {0.0, 0.0, 0.0, 0.0};      // t(k-1) of the thread's rows
+    int buf = 0;                          // ring slot of step k
+#pragma unroll
+    for (int jb = 0; jb < 4; jb++) {
+#pragma unroll 1
+        for (int jp = 0; jp < 8; jp++) {
+            const int k = jb * 8 + jp, j0 = 2 * k, j1 = j0 + 1, jj0 = 2 * jp;
+            const int nbuf = (buf == 2) ? 0 : buf + 1, pbuf = (buf == 0) ? 2 : buf - 1;
+            {       // wait for phase k: every thread has published pair k
+                unsigned done;
+                const unsigned par = k & 1;
+                do {
+                    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+                                 : "=r"(done) : "r"(bar), "r"(par) : "memory");
+                } while (!done);
+            }
+            const double2* col = sc->col[buf];
+            const double2* row = sc->row[buf];
+            const double2* colp = sc->col[pbuf];
+            const double2* rowp = sc->row[pbuf];
+            // ---- chain(k): pivot block and its inverse ----
+            double pa = col[j0].x;
+            const double2 p1 = col[j1];
+            double pb = p1.x, pc = p1.y;
+            double det = fma(pa, pc, -(pb * pb));
+            if (!(pa > 0.0) || !(det > 0.0)) {          // uniform
+                if (tid == 0 && !sc->bad) {
+                    sc->bad = 1;
+                    atomicCAS(info, 0, jblk * PB + ((pa > 0.0) ? j1 : j0) + 1);
+                }
+                pa = 1.0; pb = 0.0; pc = 1.0; det = 1.0;
+            }
+            if (tid == 0) { sc->piv[0][k] = pa; sc->piv[1][k] = pb; sc->piv[2][k] = pc; }
+            const double idet = rcp_newton(det);
+            const double qa = pc * idet, qb = -pb * idet, qc = pa * idet;      // P^-1
+            double t1[4], t2[4];
+#pragma unroll
+            for (int a = 0; a < 4; a++) {
+                t1[a] = 0.0; t2[a] = 0.0;
+                if (a < jb) continue;                       // rows of earlier 16-groups are final
+                const double2 x = col[ti + 16 * a];
+                t1[a] = fma(qa, x.x, qb * x.y);
+                t2[a] = fma(qb, x.x, qc * x.y);
+            }
+            // ---- deferred bulk update of step k-1 (independent of chain(k): fills its latency) ----
+            // columns j0, j1 of S and rows j0, j1 of M took update k-1 early, before they were published
+            if (k > 0) {
+                const int j1p = j0 - 1;
+                const int jbp = (jp == 0) ? jb - 1 : jb;    // 16-group of pair k-1
+#pragma unroll
+                for (int b = 0; b < 4; b++) {
+                    if (b < jb - 1) continue;               // (static bound: jbp >= jb - 1)
+                    const double2 y = colp[tc + 16 * b];
+                    const bool early = (b == jb) && ((tc & 14) == jj0);
+                    const bool live = (b >= jbp) && (tc + 16 * b > j1p) && !early;
+#pragma unroll
+                    for (int a = 0; a < 4; a++) {
+                        if (a < b || a < jb - 1) continue;
+                        if (live && a >= jbp) s[a][b] = fma(-tp1[a], y.x, fma(-tp2[a], y.y, s[a][b]));
+                    }
+                }
+#pragma unroll
+                for (int b = 0; b < 4; b++) {
+                    if (b > jb) continue;                   // rows of pair k-1 are zero right of column j1p
+                    const double2 z = rowp[tc + 16 * b];
+                    const bool inb = b <= jbp;
+#pragma unroll
+                    for (int a = 0; a < 4; a++) {
+                        if (a < jb - 1) continue;
+                        const bool early = (a == jb) && ((ti & 14) == jj0);
+                        const bool live = inb && (a >= jbp) && (ti + 16 * a > j1p) && !early;
+                        if (live) m[a][b] = fma(-tp1[a], z.x, fma(-tp2[a], z.y, m[a][b]));
+                    }
+                }
+            }
+            // ---- update k on the NEXT pair's columns of S / rows of M, publish them, arrive ----
+            if (k < 31) {
+                const int jjn = (jj0 + 2) & 15;
+                if (jp < 7) {
+                    if ((tc & 14) == jjn) {
+                        const double2 y = col[tc + 16 * jb];
+                        double* dst = reinterpret_cast<double*>(sc->col[nbuf]) + (tc & 1);
+#pragma unroll
+                        for (int a = 0; a < 4; a++) {
+                            if (a < jb) continue;
+                            s[a][jb] = fma(-t1[a], y.x, fma(-t2[a], y.y, s[a][jb]));
+                            dst[2 * (ti + 16 * a)] = s[a][jb];
+                        }
+                    }
+                    if ((ti & 14) == jjn) {
+                        double* dst = reinterpret_cast<double*>(sc->row[nbuf]) + (ti & 1);
+#pragma unroll
+                        for (int b = 0; b < 4; b++) {
+                            if (b <= jb) {
+                                const double2 z = row[tc + 16 * b];
+                                m[jb][b] = fma(-t1[jb], z.x, fma(-t2[jb], z.y, m[jb][b]));
+                            }
+                            dst[2 * (tc + 16 * b)] = m[jb][b];
+                        }
+                    }
+                } else if (jb < 3) {      // the next pair opens the next 16-group
+                    if ((tc & 14) == 0) {
+                        const double2 y = col[tc + 16 * (jb + 1)];
+                        double* dst = reinterpret_cast<double*>(sc->col[nbuf]) + (tc & 1);
+#pragma unroll
+                        for (int a = 0; a < 4; a++) {
+                            if (a < jb + 1) continue;
+                            s[a][(jb + 1) & 3] = fma(-t1[a], y.x, fma(-t2[a], y.y, s[a][(jb + 1) & 3]));
+                            dst[2 * (ti + 16 * a)] = s[a][(jb + 1) & 3];
+                        }
+                    }
+                    if ((ti & 14) == 0) {
+                        double* dst = reinterpret_cast<double*>(sc->row[nbuf]) + (ti & 1);
+#pragma unroll
+                        for (int b = 0; b < 4; b++) {
+                            if (b <= jb) {
+                                const double2 z = row[tc + 16 * b];
+                                m[(jb + 1) & 3][b] = fma(-t1[(jb + 1) & 3], z.x, fma(-t2[(jb + 1) & 3], z.y, m[(jb + 1) & 3][b]));
+                            }
+                            dst[2 * (tc + 16 * b)] = m[(jb + 1) & 3][b];
+                        }
+                    }
+                }
+                asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory");
+            }
+#pragma unroll
+            for (int a = 0; a < 4; a++) { tp1[a] = t1[a]; tp2[a] = t2[a]; }
+            buf = nbuf;
+        }
+    }
+    // update 31 touches nothing (no column right of 63, no row below): the sweep is complete
+    __syncthreads();
+    if (tid < PB / 2) {          // C = chol(P) of every pair
+        const double a = sc->piv[0][tid], b = sc->piv[1][tid], c = sc->piv[2][tid];
+        const double r1 = rsqrt(a);
+        const double g = b * r1 * r1;
+        sc->fin[0][tid] = r1;
+        sc->fin[1][tid] = rsqrt(fma(-g, b, c));
+        sc->fin[2][tid] = g;
+    }
+    __syncthreads();
+    const bool failed = sc->bad != 0;
+#pragma unroll
+    for (int a = 0; a < 4; a++)
+#pragma unroll
+        for (int b = 0; b < 4; b++) {
+            const int r = ti + 16 * a, c = tc + 16 * b;
+            const double v = s[a][b], w = m[a][b];
+            const double vp = __shfl_up_sync(0xffffffffu, v, 1);       // same row, column c-1
+            const double wp = __shfl_up_sync(0xffffffffu, w, 16);      // row r-1, same column
+            const int kc = c >> 1, kr = r >> 1;
+            const double lv = (c & 1) ? (v - sc->fin[2][kc] * vp) * sc->fin[1][kc] : v * sc->fin[0][kc];
+            const double wv = (r & 1) ? (w - sc->fin[2][kr] * wp) * sc->fin[1][kr] : w * sc->fin[0][kr];
+            if (c <= r) A[(int64_t)r * ld + c] = failed ? ((r == c) ? 1.0 : 0.0) : lv;
+            if (Winv != nullptr) Winv[(int64_t)r * ldw + c] = failed ? ((r == c) ? 1.0 : 0.0) : ((c <= r) ? wv : 0.0);
+        }
+    __syncthreads();             // the scratch (and its barrier word) may be reused by the caller
+    if (tid == 0) asm volatile("mbarrier.inval.shared::cta.b64 [%0];\n" ::"r"(bar) : "memory");
+}
+
 __global__ void __launch_bounds__(256, 1) potrf_diag_kernel(double* __restrict__ A, int64_t ld, double* __restrict__ Winv,
-                                                         int64_t ldw, int32_t* __restrict__ info, int jblk) {
-    potrf_diag_body(A, ld, A, ld, Winv, ldw, info, jblk);
+                                                         int64_t ldw, int32_t* __restrict__ info, int jblk, int pipelined) {
+    __shared__ __align__(16) PotrfScratch scratch;
+    if (pipelined) potrf_diag_pipe(A, ld, A, ld, Winv, ldw, info, jblk, &scratch);
+    else potrf_diag_body(A, ld, A, ld, Winv, ldw, info, jblk);
 }
 
 // ---- tiled Cholesky + forward substitution as ONE persistent dataflow kernel -----------------------------------------
@@ -224,6 +447,7 @@ struct DfArgs {
     int total;
     long long spin_limit;
     long long* trace;   // diagnostics (MFGP_DF_TRACE=1): 8 timestamps per chain task, else nullptr
+    int potrf_pipe;     // 1: software-pipelined diagonal-block sweep (potrf_diag_pipe)
 };
 
 __device__ __forceinline__ void df_stamp(long long* trace, int task, int k) {
@@ -251,18 +475,20 @@ __device__ __forceinline__ void df_st_release(int* p, int v) {
 __device__ __forceinline__ void df_st_relaxed(int* p, int v) {
     asm volatile("st.relaxed.gpu.global.s32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
 }
-// lane 0 of the calling warp spins until *f != 0 (or the abort flag is raised); every lane gets the verdict
+// lane 0 of the calling warp spins until *f != 0 (or the abort flag is raised); every lane gets the verdict.  The spin uses
+// relaxed loads (served by L2, no L1 invalidation per poll); ONE acquire load orders the tile reads behind the flag.
 __device__ __forceinline__ bool df_wait(const int* f, int* ctrl, int32_t* info, long long limit) {
     int ok = 1;
     if ((threadIdx.x & 31) == 0) {
-        if (!df_ld_acquire(f)) {
+        if (!df_ld_relaxed(f)) {
             const long long t0 = clock64();
-            while (!df_ld_acquire(f)) {
+            while (!df_ld_relaxed(f)) {
                 __nanosleep(32);
                 if (clock64() - t0 > limit) { atomicExch(ctrl + 1, 1); atomicExch(info, -1); }
                 if (*reinterpret_cast<volatile int*>(ctrl + 1)) { ok = 0; break; }
             }
         }
+        (void)df_ld_acquire(f);
     }
     ok = __shfl_sync(0xffffffffu, ok, 0);
     __syncwarp();                 // shuffles carry no memory ordering: order lane 0's acquire before the other lanes' tile loads
@@ -272,6 +498,7 @@ __device__ __forceinline__ bool df_wait(const int* f, int* ctrl, int32_t* info, 
 __global__ void __launch_bounds__(DF_THREADS, 2) chol_dataflow_kernel(DfArgs g) {
     extern __shared__ __align__(16) double df_smem[];
     __shared__ int task[4];
+    __shared__ int ready_s[4];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     // 8 warps as 4 x 2; a warp owns the 8x8 tiles (row tile (warp>>1) + 4x, column tile (warp&1) + 2y), x < 2, y < 4 --
     // interleaved, so that the triangular products of the chain task (W_cc lower, S symmetric) skip about the same share
@@ -344,20 +571,24 @@ __global__ void __launch_bounds__(DF_THREADS, 2) chol_dataflow_kernel(DfArgs g) 
             }
 
         bool ok = true;
-        int pre = 0;                                  // lane 0: both flags of the NEXT k tile, sampled one slab early
+        // Readiness of a k tile's two operand tiles: ONE thread samples the flags for the whole CTA (acquire loads cost an
+        // L1 invalidation each), one slab early, and hands the verdict over through shared memory across the slab barriers.
         auto stage = [&](int buf, int s) {
             const int k0 = s * DF_K;
             const int kt = s >> 1;
             if ((s & 1) == 0) {                       // first slab of a 64-wide k tile: its producers must be done
-                int ready = (lane == 0) ? pre : 0;    // (the early sample hides the L2 round trip of the common, ready case)
-                ready = __shfl_sync(0xffffffffu, ready, 0);
-                __syncwarp();                         // (memory ordering for the early-sampled acquire, see df_wait)
+                const int ready = (s == 0) ? 0 : ready_s[kt & 1];      // uniform; written before the last slab barrier
                 if (!ready) {
-                    ok = df_wait(fa + kt, g.ctrl, g.info, g.spin_limit) && ok;
-                    ok = df_wait(fb + (int64_t)kt * fbs, g.ctrl, g.info, g.spin_limit) && ok;
+                    if (warp == 0) {
+                        bool w = df_wait(fa + kt, g.ctrl, g.info, g.spin_limit);
+                        w = df_wait(fb + (int64_t)kt * fbs, g.ctrl, g.info, g.spin_limit) && w;
+                        if (lane == 0) ready_s[2] = w ? 1 : 0;
+                    }
+                    __syncthreads();                  // also orders warp 0's acquire before everybody's tile loads
+                    ok = (ready_s[2] != 0) && ok;
                 }
-            } else if (lane == 0) {
-                pre = (kt + 1 < nk) ? (df_ld_acquire(fa + kt + 1) & df_ld_acquire(fb + (int64_t)(kt + 1) * fbs)) : 0;
+            } else if (tid == 0) {
+                ready_s[(kt + 1) & 1] = (kt + 1 < nk) ? (df_ld_acquire(fa + kt + 1) & df_ld_acquire(fb + (int64_t)(kt + 1) * fbs)) : 0;
             }
             double* As = As0 + buf * DF_STAGE;
             double* Bs = Bs0 + buf * DF_STAGE;
@@ -442,7 +673,12 @@ __global__ void __launch_bounds__(DF_THREADS, 2) chol_dataflow_kernel(DfArgs g) 
                     Xs[r * DF_LDT + cc + 1] = -acc[x][y][1];
                     acc[x][y][0] = acc[x][y][1] = 0.0;
                 }
-            const bool okd = df_wait(g.flagsL + (int64_t)c * g.nb + c, g.ctrl, g.info, g.spin_limit);
+            if (warp == 0) {
+                const bool w = df_wait(g.flagsL + (int64_t)c * g.nb + c, g.ctrl, g.info, g.spin_limit);
+                if (lane == 0) ready_s[3] = w ? 1 : 0;
+            }
+            __syncthreads();                          // X is in shared memory, W_cc is final (warp 0 acquired its flag)
+            const bool okd = ready_s[3] != 0;
             if (chain && tid == 0) df_st_relaxed(my_pause, 1);
             if (chain) df_stamp(g.trace, idx, 1);
 #pragma unroll
@@ -521,21 +757,20 @@ __global__ void __launch_bounds__(DF_THREADS, 2) chol_dataflow_kernel(DfArgs g) 
                     Xs[r * DF_LDT + cc + 1] = -acc2[x][y][1];
                 }
             if (idx > 0) {                            // publish the sub-diagonal tile before the long factor step
-                __threadfence();
-                __syncthreads();
+                __syncthreads();                      // (release by one thread after the barrier covers the CTA's writes)
                 if (tid == 0) df_st_release(myflag, 1);
             } else {
                 __syncthreads();
             }
             df_stamp(g.trace, idx, 4);
-            potrf_diag_body(Xs, DF_LDT, Cd, g.ld, Wd, g.ldw, g.info, idx);
+            if (g.potrf_pipe) potrf_diag_pipe(Xs, DF_LDT, Cd, g.ld, Wd, g.ldw, g.info, idx, reinterpret_cast<PotrfScratch*>(Ws));
+            else potrf_diag_body(Xs, DF_LDT, Cd, g.ld, Wd, g.ldw, g.info, idx);
             myflag = g.flagsL + (int64_t)idx * g.nb + idx;
             df_stamp(g.trace, idx, 5);
         }
-        __threadfence();
         __syncthreads();
         if (tid == 0) {
-            df_st_release(myflag, 1);
+            df_st_release(myflag, 1);                 // cumulative: covers the tile stores of every thread before the barrier
             if (chain) df_st_relaxed(my_pause, 0);
         }
         if (chain) df_stamp(g.trace, idx, 6);
@@ -614,6 +849,14 @@ struct DfScratch {        // diagnostics (MFGP_DF_TRACE=1) and the cached SM cou
 };
 DfScratch g_df[16];
 
+int use_potrf_pipe() {        // MFGP_POTRF=classic: the unpipelined 64x64 sweep (A/B timing)
+    static const int v = [] {
+        const char* e = getenv("MFGP_POTRF");
+        return (e && std::strcmp(e, "classic") == 0) ? 0 : 1;
+    }();
+    return v;
+}
+
 bool use_panel_chain() {
     static const int v = [] {
         const char* e = getenv("MFGP_CHOL");
@@ -646,6 +889,7 @@ int chol_dataflow(double* K, int64_t npad, int64_t ld, double* W, int64_t ldw, i
         a.trace = nb <= 1024 ? sc.trace : nullptr;
         sc.trace_nb = nb;
     }
+    a.potrf_pipe = use_potrf_pipe();
     a.spin_limit = 4000000000LL;      // ~2 s of SM clocks: only a bug can get there
     constexpr int smem = DF_SMEM_DOUBLES * sizeof(double);
     MFGP_CUDA_CHECK(cudaFuncSetAttribute(chol_dataflow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -690,7 +934,7 @@ extern "C" int mfgp_cholesky(double* K, int64_t npad, int64_t ld, double* W, int
         double* Ajj = K + (int64_t)j * PB * (ld + 1);
         double* Wjj = W ? W + (int64_t)j * PB * (ldw + 1) : static_cast<double*>(work);
         const int64_t ldi = W ? ldw : PB;
-        potrf_diag_kernel<<<1, 256, POTRF_SMEM, st>>>(Ajj, ld, Wjj, ldi, info, j);
+        potrf_diag_kernel<<<1, 256, POTRF_SMEM, st>>>(Ajj, ld, Wjj, ldi, info, j, use_potrf_pipe());
         MFGP_LAUNCH_CHECK();
         const int rem = (int)(npad - (int64_t)(j + 1) * PB);
         if (rem <= 0) break;
@@ -772,7 +1016,7 @@ extern "C" int mfgp_cholesky_solve(double* K, int64_t npad, int64_t ld, double* 
     for (int j = 0; j < nb; j++) {
         double* Ajj = K + (int64_t)j * PB * (ld + 1);
         double* Wjj = W + (int64_t)j * PB * (ldw + 1);
-        potrf_diag_kernel<<<1, 256, POTRF_SMEM, st>>>(Ajj, ld, Wjj, ldw, info, j);
+        potrf_diag_kernel<<<1, 256, POTRF_SMEM, st>>>(Ajj, ld, Wjj, ldw, info, j, use_potrf_pipe());
         MFGP_LAUNCH_CHECK();
         MFGP_CUDA_CHECK(cudaEventRecord(side->ev_potrf[j & 1], st));
         const int rem = (int)(npad - (int64_t)(j + 1) * PB);
@@ -925,7 +1169,7 @@ extern "C" int mfgp_cholesky_append(const double* Xt, int64_t NL, int64_t NH_old
             splitk_reduce_kernel<<<dim3(1, PB), 64, 0, st>>>(part, nsplit, PB * PB, PB, Kbb, ld, PB, PB, -1.0, 1.0);        // S
             MFGP_LAUNCH_CHECK();
         }
-        potrf_diag_kernel<<<1, 256, POTRF_SMEM, st>>>(Kbb, ld, Wbb, ldw, info, (int)(rb / PB));
+        potrf_diag_kernel<<<1, 256, POTRF_SMEM, st>>>(Kbb, ld, Wbb, ldw, info, (int)(rb / PB), use_potrf_pipe());
         MFGP_LAUNCH_CHECK();
         if (rb > 0) {
             int nsplit = (int)(rb / 256);

@@ -14,6 +14,7 @@ coverage algorithms use: construction from arrays, `hyp` assigned after construc
 Every arithmetic step runs on the GPU through the C-ABI in include/mfgp_b200.h; there is no CPU fallback.
 """
 import copy
+import os
 import weakref
 
 import numpy as np
@@ -22,6 +23,14 @@ import torch
 from ._engine import DeviceGP
 
 JITTER = 1e-8
+
+# Deferred fit (default): updt_info / updt / updt_hifi upload the data and mark the factor stale; the first consumer
+# factorises -- on a tensor-product grid `predict` then runs ONE fused pass (Cholesky + forward substitution + posterior)
+# instead of Cholesky, explicit inverse, whitening and a status round trip per update.  A non-SPD covariance raises
+# np.linalg.LinAlgError from that consumer (`predict`, `factor`, `likelihood`, the coverage step) instead of from the update
+# call.  MFGP_EAGER_FIT=1 (or gaussian_process.EAGER_FIT = True before constructing a model) restores the reference's
+# timing of the error: np.linalg.cholesky raises inside updt_info (gaussian_process.py:254, :529).
+EAGER_FIT = os.environ.get("MFGP_EAGER_FIT", "0") == "1"
 
 
 def evaluate_hyp(hyp, raw_means=False):
@@ -88,6 +97,7 @@ class _GPBase:
 
     def _init_device(self):
         self._dev = DeviceGP()
+        self._dev.defer_fit = self._dev.lazy_check = not EAGER_FIT
         self._grid_key = None
         self._grid_dev = None
         self.L = np.empty([0, 0])
@@ -146,7 +156,7 @@ class _GPBase:
             self._refit(check=True)
         mu, var = self._dev.posterior(xs_dev, axes=axes)
         mu_h, var_h = _to_host_pinned(mu), _to_host_pinned(var)
-        torch.cuda.current_stream(mu.device).synchronize()
+        self._dev.check_factor(force=True)        # synchronises; raises LinAlgError for a non-SPD covariance (deferred fit)
         return mu_h.reshape(-1, 1), var_h
 
     # -- hyper-parameter training (gaussian_process.py:81-119, :344-399) ------------------------------------------------
@@ -191,7 +201,7 @@ class _GPBase:
         d = self._dev
         if d.N == 0:
             return np.empty([0, 0])
-        d.ensure_factor(need_inverse=False)
+        d.check_factor(force=True)
         return torch.tril(d.K[:d.N, :d.N]).cpu().numpy()
 
     def __deepcopy__(self, memo):

@@ -63,6 +63,8 @@ def allreduce_partials(res, group=None, amax_k0=0.0, amax_rel=0.0):
         dist.all_reduce(res["cent"], op=dist.ReduceOp.SUM, group=group)
     if res.get("lossp") is not None:
         dist.all_reduce(res["lossp"], op=dist.ReduceOp.SUM, group=group)
+    if res.get("ties") is not None:
+        dist.all_reduce(res["ties"], op=dist.ReduceOp.SUM, group=group)
     if res.get("amax_val") is not None:
         A = res["amax_val"].numel()
         vals = [torch.empty_like(res["amax_val"]) for _ in range(world)]
@@ -123,7 +125,8 @@ def gather_results_to_host(res, group=None, amax_k0=0.0, amax_rel=0.0):
         a = h.numpy()
     else:
         a = allp.numpy()
-    out = {"cent": None, "amax_val": None, "amax_idx": None, "lossp": None}
+    out = {"cent": None, "amax_val": None, "amax_idx": None, "lossp": None,
+           "ties": int(a[:, 6 * Ac + 2 * Ap:].copy().view(np.int32)[:, 0].sum())}
     if Ac:
         cent = np.zeros((Ac, 4))
         for r in range(world):                                   # rank order: the same sum on every rank, every run
@@ -134,7 +137,7 @@ def gather_results_to_host(res, group=None, amax_k0=0.0, amax_rel=0.0):
     if Ap:
         lossp = np.zeros((Ap, 2))
         for r in range(world):
-            lossp += a[r, 6 * Ac:].reshape(Ap, 2)
+            lossp += a[r, 6 * Ac:6 * Ac + 2 * Ap].reshape(Ap, 2)
         out["lossp"] = lossp
     return out
 
@@ -199,3 +202,50 @@ class ShardedGrid:
 
     def assign_reduce(self, *a, **k):
         return allreduce_partials(self.local.assign_reduce(*a, **k), self.group, k.get("amax_k0", 0.0), k.get("amax_rel", 0.0))
+
+
+class ShardedSim:
+    """Grid-sharded twin of simulator._Sim (config c4: the fixed grid split into whole-column slices, one per rank).
+
+    Every rank keeps its slice of the grid resident, factorises the (small) training system itself -- the fused
+    Cholesky + forward substitution of the factored posterior; the x expansion covers only the slice's interval, so the
+    right-hand-side count shrinks with the number of ranks -- and clips the SAME global Voronoi cells on its own device
+    (deterministic: identical on every rank, no broadcast).  One step needs ONE collective: the all-gather of the packed
+    per-cell results (6 A_c + 2 A_p + 1 doubles per rank), merged on the host in rank order with the kernels' arg-max tie
+    rule.  Tie points (grid points within TIE_TOL of a bisector, counted over all ranks) send every rank to Qhull's
+    polygons for that step, exactly like the single-GPU path."""
+
+    def __init__(self, xy_shard, f_shard, axes, base_index, bounding_box, group=None):
+        from ._coverage import CoverageGrid
+        self.group = group
+        self.bounding_box = np.asarray(bounding_box, dtype=np.float64)
+        self.grid = CoverageGrid(xy_shard, f_shard, base_index=base_index, axes=axes)
+        f64 = dict(dtype=torch.float64, device=self.grid.device)
+        self.mu = torch.empty(self.grid.G, **f64)
+        self.var = torch.empty(self.grid.G, **f64)
+        self._clip = [None, None]
+
+    def step(self, model, positions, centroids_t, voronoi="auto"):
+        """(loss, centroids[A,2], argmax grid indices[A], max variance[A]) -- global results, the same on every rank."""
+        from . import _coverage as cv
+        from .gaussian_process import prior_variance
+        bb = self.bounding_box
+        eng = model.engine
+        eng.lazy_check = eng.defer_fit = True
+        model.predict_device(self.grid.xy, self.mu, self.var, grid=self.grid)     # queued first; the host builds the cells meanwhile
+        if voronoi == "qhull":
+            loss_vor, lloyd_vor = cv.BoundedVoronoi(positions, bb), cv.BoundedVoronoi(centroids_t, bb)
+        else:
+            loss_vor = cv.HybridVoronoi(positions, bb, reuse=self._clip[0])
+            lloyd_vor = cv.HybridVoronoi(centroids_t, bb, reuse=self._clip[1])
+            self._clip = [loss_vor, lloyd_vor]
+        k0 = prior_variance(model.params())
+        kw = dict(w=self.mu, var=self.var, amax_k0=k0, amax_rel=cv.AMAX_REL)
+        host = gather_results_to_host(self.grid.assign_reduce(lloyd_vor, loss_vor, **kw), self.group, k0, cv.AMAX_REL)
+        if host["ties"] and voronoi != "qhull":
+            loss_vor.qhull(), lloyd_vor.qhull()
+            host = gather_results_to_host(self.grid.assign_reduce(lloyd_vor, loss_vor, **kw), self.group, k0, cv.AMAX_REL)
+        eng.check_factor(force=True)
+        loss = cv.loss_from_partials(host["lossp"], loss_vor.areas())
+        cent = cv.centroids_from_partials(host["cent"], lloyd_vor.areas(), bb[0], bb[1], bb[2], bb[3])
+        return loss, cent, host["amax_idx"], host["amax_val"]

@@ -115,24 +115,30 @@ def poly_area(x, y):
 in_box = cv.in_box
 
 
-# MFGP_VORONOI=clip (or simulator.VORONOI = "clip"): bounded Voronoi cells by half-plane clipping ON THE DEVICE
-# (cov_voronoi_clip) instead of scipy/Qhull on the host.  Same cells to ~1e-13; grid points lying EXACTLY on a bisector
-# may be classified differently, so the default stays "qhull" (tie parity is defined by live Qhull).
-VORONOI = os.environ.get("MFGP_VORONOI", "qhull")
+# How the bounded Voronoi cells are built (MFGP_VORONOI / simulator.VORONOI):
+#   "auto"  (default) cells clipped ON THE DEVICE (cov_voronoi_clip); scipy/Qhull -- the reference's builder -- runs on the
+#           host only for the passes that meet a grid point within TIE_TOL of a bisector (its membership is decided by the
+#           polygon vertices, and tie parity is defined by live Qhull) or when the host reads the vertices.
+#           Without tie points the two builders give the same memberships; cell areas agree to 1e-11.
+#   "qhull" always Qhull on the host, polygons uploaded (the round-1 default; bitwise the reference's areas);
+#   "clip"  never Qhull: grid points EXACTLY on a bisector may be classified differently (throughput mode).
+VORONOI = os.environ.get("MFGP_VORONOI", "auto")
 
 
 def voronoi_bounded(points, bounding_box):
     """reference simulator.py:154-191."""
     if VORONOI == "clip":
         return cv.ClippedVoronoi(points, bounding_box)
-    return BoundedVoronoi(points, bounding_box)
+    if VORONOI == "qhull":
+        return BoundedVoronoi(points, bounding_box)
+    return cv.HybridVoronoi(points, bounding_box)
 
 
 def compute_loss(vor, truth_arr):
     """reference simulator.py:194-228."""
     grid = _grid_for(truth_arr)
-    res = grid.assign_reduce(loss_vor=vor)
-    return cv.loss_from_partials(cv.CoverageGrid.results_to_host(res)["lossp"], vor.areas())
+    host = grid.reduce_to_host(loss_vor=vor)
+    return cv.loss_from_partials(host["lossp"], vor.areas())
 
 
 def compute_centroids(vor, x_star, mu_star):
@@ -141,8 +147,8 @@ def compute_centroids(vor, x_star, mu_star):
     grid = _grid_for(x_star)
     w = mu_star if torch.is_tensor(mu_star) else torch.from_numpy(
         np.ascontiguousarray(mu_star, dtype=np.float64).reshape(-1)).to(grid.device)
-    res = grid.assign_reduce(lloyd_vor=vor, w=w)
-    return cv.centroids_from_partials(cv.CoverageGrid.results_to_host(res)["cent"], vor.areas(), *grid.extent)
+    host = grid.reduce_to_host(lloyd_vor=vor, w=w)
+    return cv.centroids_from_partials(host["cent"], vor.areas(), *grid.extent)
 
 
 def _as_var_vector(var_star, device):
@@ -168,8 +174,8 @@ def compute_max_var(vor, truth_arr, var_star):
     """reference simulator.py:286-323; returns (argmax_xy[A,2], max_var[A,1])."""
     truth_arr = np.asarray(truth_arr)
     grid = _grid_for(truth_arr)
-    res = grid.assign_reduce(lloyd_vor=vor, var=_as_var_vector(var_star, grid.device))
-    xy, mv, _ = _max_var_from(res, truth_arr)
+    host = grid.reduce_to_host(lloyd_vor=vor, var=_as_var_vector(var_star, grid.device))
+    xy, mv, _ = _max_var_from(host, truth_arr)
     return xy, mv
 
 
@@ -191,6 +197,7 @@ def compute_sample_points(model, x_star, threshold, console=False, return_indice
     Vc = torch.empty((cap, G), dtype=torch.float64, device=dev)
     q = torch.empty(G, dtype=torch.float64, device=dev)
     _, var = model.predict_device(grid.xy, vcache=Vc if n else None, grid=grid, q_out=q)
+    eng.check_factor(force=True)
     lib = cv.nat.lib()
     work = torch.empty(int(lib.cov_workspace_bytes(G, 1, 0)) // 8 + (G // 256 + 2) * 2 + 64 + (1 << 15), dtype=torch.float64,
                        device=dev)
@@ -223,6 +230,8 @@ def compute_sample_clusters(vor, sample_points):
     clusters = [np.empty((0, 2)) for i in range(len(vor.filtered_regions))]
     if sample_points.shape[0] == 0:
         return clusters
+    if isinstance(vor, cv.HybridVoronoi):
+        vor = vor.qhull()       # sample points are grid points: bisector ties are common here, Qhull's vertices decide them
     res = CoverageGrid(sample_points).assign_reduce(lloyd_vor=vor, want_members=True)
     m = res["members"].cpu().numpy().view(np.uint64)
     for i in range(len(clusters)):
@@ -331,37 +340,50 @@ class _Sim:
 
     def step(self, model, positions, centroids_t, weights=None):
         """One hot-path iteration: posterior over the grid, then both partitions in one fused pass.
-        Returns (loss_t, centroids_t, argmax_var_t, max_var_t, loss_vor, lloyd_vor)."""
+        Returns (loss_t, centroids_t, argmax_var_t, max_var_t, loss_vor, lloyd_vor).
+
+        Nothing on the device waits for the host: the fit is deferred into the posterior call (fused Cholesky + forward
+        substitution on tensor grids), the cells are clipped on the device, the O(A) finishing runs on the device and ONE
+        packed copy brings the results, the Cholesky status and the pass's tie count home.  Host Qhull -- the reference's
+        cell builder -- runs only when that count is non-zero (VORONOI = "auto", see voronoi_bounded) or always
+        (VORONOI = "qhull")."""
         bb = self.bounding_box
-        clip = VORONOI == "clip"
-        if clip and model is not None:
-            model.engine.lazy_check = True       # cov_finish brings the Cholesky status home with the results
-            model.engine.defer_fit = True        # ... so a refit may fuse with the factored posterior (large tensor grids)
-        if model is not None:                    # queued first: the host builds the partitions while the GPU works
-            model.predict_device(self.grid.xy, self.mu, self.var, grid=self.grid)
-        if clip:                     # device-built cells, the two buffer sets of the previous iteration are recycled
-            loss_vor = cv.ClippedVoronoi(positions, bb, reuse=self._clip[0])
-            lloyd_vor = cv.ClippedVoronoi(centroids_t, bb, reuse=self._clip[1])
-            self._clip = [loss_vor, lloyd_vor]
-        else:
-            loss_vor = voronoi_bounded(positions, bb)
-            lloyd_vor = voronoi_bounded(centroids_t, bb)
-            loss_vor.areas()                     # host work that does not depend on the GPU goes before the launch
-            lloyd_vor.areas()
         if model is not None:
-            res = self.grid.assign_reduce(lloyd_vor, loss_vor, w=self.mu, var=self.var,
-                                          amax_k0=prior_variance(model.params()), amax_rel=cv.AMAX_REL)
+            eng = model.engine
+            eng.lazy_check = True            # cov_finish / the packed results bring the Cholesky status home: no sync per fit
+            eng.defer_fit = True             # a refit fuses with the factored posterior on large tensor grids
+            model.predict_device(self.grid.xy, self.mu, self.var, grid=self.grid)       # queued first: the host prepares
+            kw = dict(w=self.mu, var=self.var, amax_k0=prior_variance(model.params()), amax_rel=cv.AMAX_REL)     # the cells
+            info = eng.info                                                             # while the GPU works on it
         else:
-            res = self.grid.assign_reduce(lloyd_vor, loss_vor, w=weights)
-        if isinstance(lloyd_vor, cv.ClippedVoronoi) and isinstance(loss_vor, cv.ClippedVoronoi) and len(loss_vor) and len(lloyd_vor):
-            loss_t, centroids, max_var, idx = self.grid.finish(res, lloyd_vor, loss_vor, bb,
-                                                               info=model.engine.info if model is not None else None)
-            if model is None:
-                return loss_t, centroids, None, None, loss_vor, lloyd_vor
-            if np.any(idx < 0):
-                raise ValueError("zero-size array to reduction operation maximum which has no identity")   # np.amax([])
-            return loss_t, centroids, self.truth_arr[idx][:, [0, 1]], max_var.reshape(-1, 1), loss_vor, lloyd_vor
-        host = cv.CoverageGrid.results_to_host(res)      # one device->host copy for all the per-cell results
+            kw = dict(w=weights)
+            info = None
+        if VORONOI == "qhull":       # host Qhull; polygons uploaded afterwards
+            loss_vor = BoundedVoronoi(positions, bb)
+            lloyd_vor = BoundedVoronoi(centroids_t, bb)
+            loss_vor.areas()
+            lloyd_vor.areas()
+        else:                        # device-built cells (two small kernels), the buffers of the previous iteration are recycled
+            cls = cv.ClippedVoronoi if VORONOI == "clip" else cv.HybridVoronoi
+            loss_vor = cls(positions, bb, reuse=self._clip[0])
+            lloyd_vor = cls(centroids_t, bb, reuse=self._clip[1])
+            self._clip = [loss_vor, lloyd_vor]
+        device_cells = isinstance(lloyd_vor, cv.ClippedVoronoi) and len(loss_vor) and len(lloyd_vor) and \
+            loss_vor.seeds_inside and lloyd_vor.seeds_inside
+        if device_cells:
+            res = self.grid.assign_reduce(lloyd_vor, loss_vor, **kw)
+            loss_t, centroids, max_var, idx, ties = self.grid.finish(res, lloyd_vor, loss_vor, bb, info=info, with_ties=True)
+            if not (ties and VORONOI != "clip"):
+                if model is None:
+                    return loss_t, centroids, None, None, loss_vor, lloyd_vor
+                if np.any(idx < 0):
+                    raise ValueError("zero-size array to reduction operation maximum which has no identity")   # np.amax([])
+                return loss_t, centroids, self.truth_arr[idx][:, [0, 1]], max_var.reshape(-1, 1), loss_vor, lloyd_vor
+            loss_vor.qhull()                 # tie points: the pass below runs on Qhull's polygons, like the reference
+            lloyd_vor.qhull()
+        host = self.grid.reduce_to_host(lloyd_vor, loss_vor, **kw)     # one device->host copy for all the per-cell results
+        if model is not None:
+            model.engine.check_factor(force=True)
         loss_t = cv.loss_from_partials(host["lossp"], loss_vor.areas())
         centroids = cv.centroids_from_partials(host["cent"], lloyd_vor.areas(), bb[0], bb[1], bb[2], bb[3])
         if model is None:

@@ -142,7 +142,7 @@ def test_sweep_and_generic_kernels_agree(n, A, seed, on_grid):
     pos = seeds
     cen = synth.agents(A, seed + 50)
     bbox = ocov.bounding_box_of(xy)
-    lv, pv = sim.voronoi_bounded(cen, bbox), sim.voronoi_bounded(pos, bbox)
+    lv, pv = cv.BoundedVoronoi(cen, bbox), cv.BoundedVoronoi(pos, bbox)      # Qhull's polygons: on-grid seeds put grid points ON bisectors
     res = {}
     for sweep in (True, False):
         g = cv.CoverageGrid(xy, f)
@@ -177,7 +177,7 @@ def test_packed_partitions_and_packed_results_match_the_plain_path():
     cen = synth.agents(16, 77)
     bbox = ocov.bounding_box_of(xy)
     g = cv.CoverageGrid(xy, f)
-    lv, pv = sim.voronoi_bounded(cen, bbox), sim.voronoi_bounded(seeds, bbox)
+    lv, pv = cv.BoundedVoronoi(cen, bbox), cv.BoundedVoronoi(seeds, bbox)      # what broadcast_partitions packs: Qhull's cells
     plain = g.assign_reduce(lv, pv, w=mu, var=var)
     ref = {k: plain[k].cpu().numpy().copy() for k in ("cent", "amax_val", "amax_idx", "lossp")}
     pk_p, pk_l = sharding.broadcast_partitions([seeds, cen], bbox, g.device)
@@ -189,3 +189,31 @@ def test_packed_partitions_and_packed_results_match_the_plain_path():
     host2 = cv.CoverageGrid.results_to_host(plain)
     for k in ref:
         assert np.array_equal(host2[k], ref[k]), k
+
+
+@pytest.mark.parametrize("on_grid", [False, True])
+def test_hybrid_cells_fall_back_to_qhull_exactly_when_a_pass_meets_tie_points(on_grid):
+    """simulator.voronoi_bounded (default VORONOI = "auto"): cells clipped on the device, host Qhull only when the pass
+    reports grid points within TIE_TOL of a bisector (their membership hangs on the polygon vertices) -- and then the result
+    is what the always-Qhull path gives, bit for bit.  Off-grid seeds: no tie point, no Qhull run, areas from the device."""
+    from mfgp_coverage_b200 import _coverage as cv
+    from mfgp_coverage_b200 import simulator as sim
+    xy, f, truth, seeds = _setup(51, 8, 4, on_grid)
+    bbox = ocov.bounding_box_of(xy)
+    assert sim.VORONOI == "auto"
+    vor = sim.voronoi_bounded(seeds, bbox)
+    assert isinstance(vor, cv.HybridVoronoi) and vor._qhull is None
+    g = sim._grid_for(truth)
+    host = g.reduce_to_host(loss_vor=vor)
+    q = cv.BoundedVoronoi(seeds, bbox)
+    want = cv.CoverageGrid.results_to_host(g.assign_reduce(loss_vor=q))
+    if on_grid:
+        assert want["ties"] > 0 and vor._qhull is not None         # the pass was repeated on Qhull's polygons
+        assert np.array_equal(host["lossp"], want["lossp"]) and np.array_equal(vor.areas(), q.areas())
+    else:
+        assert host["ties"] == 0 and vor._qhull is None             # Qhull never ran
+        assert np.array_equal(host["lossp"], want["lossp"])         # nearest-seed membership: identical sums
+        assert np.max(np.abs(vor.areas() - q.areas()) / q.areas()) <= 1e-11
+    loss = sim.compute_loss(vor, truth)
+    assert abs(loss - ocov.compute_loss(ocov.voronoi_bounded(seeds, bbox), truth)) <= 1e-9 * abs(loss)
+    assert np.array_equal(vor.vertices, q.vertices) and vor.filtered_regions == q.filtered_regions    # host view = Qhull's

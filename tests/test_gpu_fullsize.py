@@ -116,12 +116,15 @@ def test_grid_sharded_equals_unsharded(workload):
         lo, hi = sharding.shard_bounds(G, 4, r)
         g = CoverageGrid(w["xy"][lo:hi], w["f"][lo:hi], base_index=lo, axes=w["g"].axes)
         mu, var = w["m"].predict_device(g.xy, grid=g)
-        assert torch.equal(var, w["var"][lo:hi]) and torch.equal(mu, w["mu"][lo:hi])      # posterior is per-point
+        # the posterior is per-point; a shard re-expands the x factor on ITS interval (lower Chebyshev order, fewer
+        # right-hand sides), so the two evaluations differ by rounding only
+        assert float((var - w["var"][lo:hi]).abs().max()) <= 1e-12 * k0 and float((mu - w["mu"][lo:hi]).abs().max()) <= 1e-12
         parts.append(g.assign_reduce(lv, pv, w=mu, var=var, amax_k0=k0, amax_rel=1e-10))
     cent = sum(p["cent"] for p in parts)
     lossp = sum(p["lossp"] for p in parts)
-    v, i = sharding.merge_argmax(torch.stack([p["amax_val"] for p in parts]), torch.stack([p["amax_idx"] for p in parts]))
-    assert torch.equal(i, full["amax_idx"]) and torch.equal(v, full["amax_val"])
+    v, i = sharding.merge_argmax(torch.stack([p["amax_val"] for p in parts]), torch.stack([p["amax_idx"] for p in parts]),
+                                 k0, 1e-10)
+    assert torch.equal(i, full["amax_idx"]) and float((v - full["amax_val"]).abs().max()) <= 1e-12 * k0
     assert torch.equal(cent[:, 3], full["cent"][:, 3]) and torch.equal(lossp[:, 1], full["lossp"][:, 1])   # counts
     assert float(((cent - full["cent"]).abs() / (full["cent"].abs() + 1e-300)).max()) <= 1e-11
     assert float(((lossp - full["lossp"]).abs() / (full["lossp"].abs() + 1e-300)).max()) <= 1e-11

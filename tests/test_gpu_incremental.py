@@ -118,9 +118,10 @@ def test_append_reports_non_spd():
     from mfgp_coverage_b200 import simulator as sim
     xy = synth.grid(12)
     m = sim.init_SFGP(synth.SF_HYP, np.empty((0, 3)))
+    e = m.engine
+    e.defer_fit = e.lazy_check = False       # engine-level test: the status is read back by every call (MFGP_EAGER_FIT behaviour)
     m.updt_info(xy[[3, 50, 77]], np.ones((3, 1)))
     m.incremental = True
-    e = m.engine
     bad = dict(e.params)
     bad["noise_H"] = -1.0          # new diagonal entries k(0) + noise < 0: the Schur complement of the border is not SPD
     e.set_params(bad)

@@ -45,7 +45,8 @@ def _worker(rank, world, port, out):
                amax_idx=torch.from_numpy(aidx))
     # the packed form the coverage kernels write: [cent | amax_val | amax_idx bits | lossp], merged on the host
     A = cent.shape[0]
-    pack = torch.cat([res["cent"].reshape(-1), res["amax_val"], res["amax_idx"].view(torch.float64), res["lossp"].reshape(-1)])
+    pack = torch.cat([res["cent"].reshape(-1), res["amax_val"], res["amax_idx"].view(torch.float64), res["lossp"].reshape(-1),
+                      torch.tensor([rank + 1, 0], dtype=torch.int32).view(torch.float64)])      # ... | tie count (int32)
     hosted = sharding.gather_results_to_host({"pack": pack, "pack_shape": (A, A)})
     sharding.allreduce_partials(res)
     if rank == 0:
@@ -71,6 +72,7 @@ def test_grid_sharded_reductions_match_unsharded(tmp_path):
     _, _, idx_o = ocov.compute_max_var(vor, np.column_stack((xy, f)), var)
     assert np.array_equal(res["amax_idx"].numpy(), idx_o)
     hosted = torch.load(out + ".host")            # the one-collective host merge gives the same global results
+    assert int(hosted.pop("ties")) == 1 + 2       # tie counts of the ranks add up
     assert np.allclose(hosted["cent"].numpy(), cent, rtol=1e-13, atol=1e-13)
     assert np.allclose(hosted["lossp"].numpy(), lossp, rtol=1e-13, atol=1e-13)
     assert np.array_equal(hosted["amax_idx"].numpy(), aidx) and np.array_equal(hosted["amax_val"].numpy(), aval)
