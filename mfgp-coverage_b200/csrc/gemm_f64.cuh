@@ -33,7 +33,8 @@ constexpr int GK = 16;        // K slab
 constexpr int GLD = GK + 4;   // padded smem row (doubles): rows land on distinct 8-bank groups for the fragment reads
 constexpr int GLDB = GT + 4;  // padded row for the non-transposed B slab [GK][GT]
 
-template <bool B_TRANS>
+// A_TRANS: the A operand is given as [k][m] (row-major, leading dimension lda), i.e. C = alpha * A^T * op(B) + beta * C
+template <bool B_TRANS, bool A_TRANS = false>
 __global__ void __launch_bounds__(128) gemm_f64_kernel(GemmArgs g) {
     const int m0 = blockIdx.y * GT, n0 = blockIdx.x * GT;
     if ((g.mode == GEMM_SYRK_LOWER || g.mode == GEMM_SYRK_LOWER_AUPPER) && n0 > m0) return;
@@ -42,7 +43,7 @@ __global__ void __launch_bounds__(128) gemm_f64_kernel(GemmArgs g) {
     const double* B = g.B + (splitk ? 0 : (int64_t)blockIdx.z * g.strideB);
     double* C = g.C + (int64_t)blockIdx.z * g.strideC;
 
-    __shared__ __align__(16) double As[2][GT * GLD];
+    __shared__ __align__(16) double As[2][A_TRANS ? GK * GLDB : GT * GLD];
     __shared__ __align__(16) double Bs[2][B_TRANS ? GT * GLD : GK * GLDB];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -67,10 +68,18 @@ __global__ void __launch_bounds__(128) gemm_f64_kernel(GemmArgs g) {
 
     auto stage = [&](int buf, int k0) {
         // A slab: 64 rows x 16 doubles = 512 16-byte chunks (chunks at or beyond kend / N are zero-filled, never read)
+        if (A_TRANS) {
 #pragma unroll
-        for (int c = tid; c < GT * (GK / 2); c += 128) {
-            int r = c >> 3, q = c & 7;
-            cp_async16(&As[buf][r * GLD + q * 2], A + (int64_t)(m0 + r) * g.lda + k0 + q * 2, k0 + q * 2 < kend);
+            for (int c = tid; c < GK * (GT / 2); c += 128) {
+                int r = c >> 5, q = c & 31;
+                cp_async16(&As[buf][r * GLDB + q * 2], A + (int64_t)(k0 + r) * g.lda + m0 + q * 2, k0 + r < kend);
+            }
+        } else {
+#pragma unroll
+            for (int c = tid; c < GT * (GK / 2); c += 128) {
+                int r = c >> 3, q = c & 7;
+                cp_async16(&As[buf][r * GLD + q * 2], A + (int64_t)(m0 + r) * g.lda + k0 + q * 2, k0 + q * 2 < kend);
+            }
         }
         if (B_TRANS) {
 #pragma unroll
@@ -103,7 +112,7 @@ __global__ void __launch_bounds__(128) gemm_f64_kernel(GemmArgs g) {
         for (int kk = 0; kk < GK; kk += 4) {
             double a[4], b[4];
 #pragma unroll
-            for (int i = 0; i < 4; i++) a[i] = As[buf][(wm + i * 8 + gq) * GLD + kk + tq];
+            for (int i = 0; i < 4; i++) a[i] = A_TRANS ? As[buf][(kk + tq) * GLDB + wm + i * 8 + gq] : As[buf][(wm + i * 8 + gq) * GLD + kk + tq];
 #pragma unroll
             for (int j = 0; j < 4; j++)
                 b[j] = B_TRANS ? Bs[buf][(wn + j * 8 + gq) * GLD + kk + tq] : Bs[buf][(kk + tq) * GLDB + wn + j * 8 + gq];
@@ -145,6 +154,15 @@ static __global__ void splitk_reduce_kernel(const double* __restrict__ part, int
     for (int z = 0; z < nsplit; z++) s += part[(int64_t)z * stride + (int64_t)r * ldp + c];
     double* o = out + (int64_t)r * ldo + c;
     *o = (beta != 0.0 ? beta * *o : 0.0) + alpha * s;
+}
+
+// C[M,N] (lower 64x64 tiles only: mode GEMM_SYRK_LOWER) = A^T A for A[K,M] row-major, optionally split over K (kchunk)
+inline int launch_syrk_ata(const GemmArgs& g, int nsplit, cudaStream_t st) {
+    if (g.M <= 0 || g.N <= 0 || nsplit <= 0) return MFGP_OK;
+    dim3 grid((g.N + GT - 1) / GT, g.M / GT, nsplit);
+    gemm_f64_kernel<false, true><<<grid, 128, 0, st>>>(g);
+    MFGP_LAUNCH_CHECK();
+    return MFGP_OK;
 }
 
 inline int launch_gemm(const GemmArgs& g, bool b_trans, int batch, cudaStream_t st) {

@@ -20,6 +20,8 @@
 // ~2e-14 k(0) (tests/test_gpu_factored.py).  Arbitrary point lists keep the dense path (gp_posterior.cu).
 #include "common.cuh"
 #include "gemm_f64.cuh"
+#include <cstdlib>
+#include <cstring>
 
 namespace mfgp {
 
@@ -365,6 +367,119 @@ __global__ void __launch_bounds__(128) gram_eval_kernel(GramArgs a) {
     }
 }
 
+// ---- the Gram route ("M route") of steps 4 + 5 -------------------------------------------------------------------------------
+// G'(ix)[l][l'] = sum_n Y'(ix)[n][l] Y'(ix)[n][l'],  Y'(ix)[n][l] = sum_k T_k(tx) Y[n][l][k]
+//              = sum_{k,k'} T_k(tx) T_k'(tx) M[(l,k)][(l',k')],        M = Y^T Y   (R x R, independent of the column ix).
+// So instead of contracting Y with T_k(tx) for every grid column (n_col N R MACs, a [n_col][N][ry] intermediate of 1.2 GB at
+// c4) and forming n_col Gram matrices over the N training rows (n_col N w^2 / 2 MACs), ONE symmetric product M = Y^T Y
+// (N R^2 / 2 MACs, split over K into a fixed number of partial sums added in order) is followed by ry (ry + 1) / 2 small
+// quadratic forms per column -- 4.3e9 instead of 9.4e9 MACs at c4 and no intermediate beyond M (14 MB).  The row of M that
+// belongs to the solved observation column z gives z^T Y (the mean's h'(ix)) for free.  Rounding: |Y|_F^2 = tr(B^T K^-1 B)
+// is O(k(0)) even for near-singular K (B lives in the smooth subspace), so the R^2-term sum is as accurate as the direct
+// Gram sum (measured: both 1e-14 k(0) against the oracle, well- and ill-conditioned hyper-parameters).
+__global__ void syrk_reduce_lower_kernel(const double* __restrict__ part, int nsplit, int64_t stride, int n, double* __restrict__ M) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y;
+    if (c >= n || (c >> 6) > (r >> 6)) return;          // tiles on or below the diagonal only
+    double s = 0.0;
+    for (int z = 0; z < nsplit; z++) s += part[(int64_t)z * stride + (int64_t)r * n + c];
+    M[(int64_t)r * n + c] = s;
+}
+
+struct QformArgs {
+    const double* M; int ldm;            // lower tiles of Y^T Y
+    const double* Ux; int kpad;          // [ncols_pad][kpad]  T_k(tx)
+    int ry, ncols, pairs_per_cta;
+    double* G;                           // [ncols][F_LW][F_LW], both triangles written
+    int col_begin;
+};
+// CTA = 64 grid columns x a range of (l, l') pairs, l' <= l; warp w owns columns 16 w .. 16 w + 15 (two 8-row DMMA tiles).
+// Per pair: T = U_blk (64 x kpad) * M_{l l'} (kpad x kpad) on DMMA, then the row-wise dot with U_blk straight off the
+// accumulator fragments (two lane shuffles).  The A fragments (U) stay in registers for the whole CTA.
+template <int NT>         // n tiles of 8: kpad <= 8 NT
+__global__ void __launch_bounds__(128) qform_kernel(QformArgs a) {
+    constexpr int KS = 2 * NT;                                   // k steps of 4
+    __shared__ double Us[64][8 * NT + 1];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, gq = lane >> 2, tq = lane & 3;
+    const int c0 = blockIdx.x * 64;
+    for (int e = tid; e < 64 * 8 * NT; e += 128) {
+        const int r = e / (8 * NT), k = e % (8 * NT);
+        Us[r][k] = (k < a.kpad) ? a.Ux[(int64_t)(c0 + r) * a.kpad + k] : 0.0;      // Ux rows beyond ncols are zero-padded
+    }
+    __syncthreads();
+    double af[2][KS];
+#pragma unroll
+    for (int rt = 0; rt < 2; rt++)
+#pragma unroll
+        for (int ks = 0; ks < KS; ks++) af[rt][ks] = Us[warp * 16 + rt * 8 + gq][ks * 4 + tq];
+    const int npairs = a.ry * (a.ry + 1) / 2;
+    int p = blockIdx.y * a.pairs_per_cta;
+    const int pend = min(npairs, p + a.pairs_per_cta);
+    int l = (int)((sqrt(8.0 * p + 1.0) - 1.0) * 0.5);
+    while ((l + 1) * (l + 2) / 2 <= p) l++;
+    while (l * (l + 1) / 2 > p) l--;
+    int lp = p - l * (l + 1) / 2;
+    for (; p < pend; p++) {
+        double acc[2][NT][2];
+#pragma unroll
+        for (int rt = 0; rt < 2; rt++)
+#pragma unroll
+            for (int j = 0; j < NT; j++) acc[rt][j][0] = acc[rt][j][1] = 0.0;
+        const int ra = l * a.kpad, rb = lp * a.kpad;
+#pragma unroll
+        for (int ks = 0; ks < KS; ks++) {
+            const int k = ks * 4 + tq;
+            double b[NT];
+#pragma unroll
+            for (int j = 0; j < NT; j++) {
+                const int n = j * 8 + gq;
+                double v = 0.0;
+                if (k < a.kpad && n < a.kpad) {
+                    const int r = ra + k, c = rb + n;              // M is symmetric, stored for row tile >= column tile
+                    v = (r >= c) ? __ldg(a.M + (int64_t)r * a.ldm + c) : __ldg(a.M + (int64_t)c * a.ldm + r);
+                }
+                b[j] = v;
+            }
+#pragma unroll
+            for (int rt = 0; rt < 2; rt++)
+#pragma unroll
+                for (int j = 0; j < NT; j++) dmma884(acc[rt][j][0], acc[rt][j][1], af[rt][ks], b[j]);
+        }
+#pragma unroll
+        for (int rt = 0; rt < 2; rt++) {
+            const int row = warp * 16 + rt * 8 + gq;
+            double q = 0.0;
+#pragma unroll
+            for (int j = 0; j < NT; j++) {
+                q = fma(acc[rt][j][0], Us[row][j * 8 + 2 * tq], q);
+                q = fma(acc[rt][j][1], Us[row][j * 8 + 2 * tq + 1], q);
+            }
+            q += __shfl_xor_sync(0xffffffffu, q, 1);
+            q += __shfl_xor_sync(0xffffffffu, q, 2);
+            if (tq == 0 && c0 + row < a.ncols) {
+                double* g = a.G + (int64_t)(a.col_begin + c0 + row) * F_LW * F_LW;
+                g[l * F_LW + lp] = q;
+                g[lp * F_LW + l] = q;
+            }
+        }
+        if (++lp > l) { l++; lp = 0; }
+    }
+}
+
+// rows / columns [ry, WM) of every G'(ix) must read as zero for gram_eval's padded quadratic form
+__global__ void gpad_zero_kernel(double* __restrict__ G, int ry, int wm, int col_begin) {
+    double* g = G + (int64_t)(col_begin + blockIdx.x) * F_LW * F_LW;
+    for (int e = threadIdx.x; e < wm * wm; e += blockDim.x) {
+        const int r = e / wm, c = e % wm;
+        if (r >= ry || c >= ry) g[r * F_LW + c] = 0.0;
+    }
+}
+
+// Hz[e] = M[zrow][e]  (z^T Y: the row of Y^T Y that belongs to the solved observation column)
+__global__ void hz_from_M_kernel(const double* __restrict__ M, int ldm, int zrow, int cols, double* __restrict__ Hz) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < cols) Hz[e] = M[(int64_t)zrow * ldm + e];
+}
+
 }  // namespace mfgp
 
 using namespace mfgp;
@@ -373,6 +488,7 @@ using namespace mfgp;
 static inline int64_t round_up(int64_t v, int64_t m) { return (v + m - 1) / m * m; }
 
 static inline int64_t imax(int64_t a, int64_t b) { return a > b ? a : b; }
+constexpr int MR_MAXSPLIT = 8;       // most K ranges of the Y^T Y product
 
 extern "C" int64_t mfgp_factored_workspace_bytes(int64_t npad, int64_t ncols, int64_t ny, int64_t rxL, int64_t ryL, int64_t rxH,
                                                  int64_t ryH, int64_t chunk_cols) {
@@ -383,7 +499,10 @@ extern "C" int64_t mfgp_factored_workspace_bytes(int64_t npad, int64_t ncols, in
     d += (rxL + ryL + rxH + ryH) * npad;                       // coefficient tables of both kernel parts
     d += 2 * npad * ry * kp;                                   // B and Y (merged over the parts)
     d += ncp * kp;                                             // Ux
-    d += ch * npad * ry;                                       // Y' of one chunk
+    const int64_t Rp = round_up(ry * kp + 1, 64);
+    const int64_t direct = ch * npad * ry;                     // Y' of one chunk (direct route)
+    const int64_t gram = (MR_MAXSPLIT + 1) * Rp * Rp + ncp * F_LW * F_LW;      // M = Y^T Y, its split-K partials, G'(ix)
+    d += direct > gram ? direct : gram;
     return d * 8 + 4096;
 }
 
@@ -444,7 +563,12 @@ void f_carve(const FGeom& g, void* work, FLayout& L) {
     f.Cx = f.Cy = nullptr;
     f.B = carve(g.npad * (int64_t)f.ry * f.kpad); f.Y = carve(g.npad * (int64_t)f.ry * f.kpad);
     f.Ux = carve(L.ncp * f.kpad);
-    f.Yp = carve(L.chunk * g.npad * f.ry);
+    {       // one region serves either route of steps 4 + 5: Y' of a chunk (direct) or M, its partials and G'(ix) (Gram route)
+        const int64_t Rp = round_up((int64_t)f.ry * f.kpad + 1, 64);
+        const int64_t direct = L.chunk * g.npad * f.ry;
+        const int64_t gram = (MR_MAXSPLIT + 1) * Rp * Rp + L.ncp * F_LW * F_LW;
+        f.Yp = carve(direct > gram ? direct : gram);
+    }
     f.Hz = carve((int64_t)f.ry * f.kpad);
 }
 
@@ -537,6 +661,93 @@ int f_tail(const FGeom& g, FLayout& L, const double* z, int64_t rows, double* Gs
     }
     return MFGP_OK;
 }
+// 0: cost model decides, 1: always the direct route (Y' + per-column Gram over the training rows), 2: always the Gram route
+int gram_route_override() {          // read per call: tests and A/B timings switch it inside one process
+    const char* e = getenv("MFGP_GRAM");
+    if (!e) return 0;
+    return std::strcmp(e, "direct") == 0 ? 1 : (std::strcmp(e, "m") == 0 ? 2 : 0);
+}
+
+// steps 4 - 6 by the Gram route from the solved right-hand sides Yall[npad][ldY] (columns [0, ry * kpad): Y, column
+// ry * kpad: z, then zero padding up to ldY, a multiple of 64).  Returns MFGP_OK, or 1 when the direct route is cheaper.
+int f_tail_gram(const FGeom& g, FLayout& L, const double* Yall, int64_t ldY, double* Gstore, double* Hz_store, double* mu,
+                double* var, double* qred, cudaStream_t st) {
+    FPart& f = L.parts[0];
+    const int64_t npad = g.npad, cols = (int64_t)f.ry * f.kpad;
+    const int wm = f.ry <= 40 ? 40 : 64;
+    const int nt8 = (f.kpad + 7) / 8;
+    if (ldY % 64 || ldY < cols + 1 || nt8 > 8) return 1;
+    const int ov = gram_route_override();
+    const double direct = (double)g.ncols * npad * cols + 0.6 * g.ncols * npad * wm * wm;
+    const double gram = 0.5 * npad * (double)ldY * ldY + (double)round_up(g.ncols, 64) * (f.ry * (f.ry + 1) / 2) * 64.0 * nt8 * nt8;
+    if (ov == 1 || (ov == 0 && gram >= direct)) return 1;
+    const DevParams dp = make_dev_params(*g.p);
+    // M and its partial sums live where the direct route keeps Y'
+    double* M = f.Yp;
+    double* part = M + ldY * ldY;
+    double* Gbuf = Gstore ? Gstore : part + (int64_t)MR_MAXSPLIT * ldY * ldY;
+    const int ntile = (int)(ldY / 64), tiles = ntile * (ntile + 1) / 2;
+    int nsplit = 740 / tiles;                       // ~5 CTAs of the tile kernel per SM: one resident wave
+    if (nsplit < 1) nsplit = 1;
+    if (nsplit > MR_MAXSPLIT) nsplit = MR_MAXSPLIT;
+    if (nsplit > npad / 128) nsplit = (int)imax(1, npad / 128);
+    const int kchunk = (int)((npad / 64 + nsplit - 1) / nsplit) * 64;
+    nsplit = (int)((npad + kchunk - 1) / kchunk);
+    GemmArgs gm{};
+    gm.A = Yall; gm.lda = ldY; gm.B = Yall; gm.ldb = ldY; gm.C = nsplit > 1 ? part : M; gm.ldc = ldY; gm.strideC = ldY * ldY;
+    gm.M = (int)ldY; gm.N = (int)ldY; gm.K = (int)npad; gm.alpha = 1.0; gm.beta = 0.0; gm.mode = GEMM_SYRK_LOWER;
+    gm.kchunk = nsplit > 1 ? kchunk : 0;
+    int rc = launch_syrk_ata(gm, nsplit, st);
+    if (rc) return rc;
+    if (nsplit > 1) {
+        syrk_reduce_lower_kernel<<<dim3((unsigned)((ldY + 127) / 128), (unsigned)ldY), 128, 0, st>>>(part, nsplit, ldY * ldY, (int)ldY, M);
+        MFGP_LAUNCH_CHECK();
+    }
+    if (Hz_store) f.Hz = Hz_store;
+    hz_from_M_kernel<<<(unsigned)((cols + 127) / 128), 128, 0, st>>>(M, (int)ldY, (int)cols, (int)cols, f.Hz);
+    MFGP_LAUNCH_CHECK();
+    QformArgs qa;
+    qa.M = M; qa.ldm = (int)ldY; qa.Ux = f.Ux; qa.kpad = f.kpad; qa.ry = f.ry; qa.ncols = (int)g.ncols; qa.G = Gbuf; qa.col_begin = 0;
+    const int npairs = f.ry * (f.ry + 1) / 2;
+    const int cblocks = (int)((g.ncols + 63) / 64);
+    int groups = (148 * 4 + cblocks - 1) / cblocks;              // ~4 CTAs per SM
+    if (groups > npairs) groups = npairs;
+    qa.pairs_per_cta = (npairs + groups - 1) / groups;
+    groups = (npairs + qa.pairs_per_cta - 1) / qa.pairs_per_cta;
+    const dim3 qgrid((unsigned)cblocks, (unsigned)groups);
+    switch (nt8) {
+        case 1: qform_kernel<1><<<qgrid, 128, 0, st>>>(qa); break;
+        case 2: qform_kernel<2><<<qgrid, 128, 0, st>>>(qa); break;
+        case 3: qform_kernel<3><<<qgrid, 128, 0, st>>>(qa); break;
+        case 4: qform_kernel<4><<<qgrid, 128, 0, st>>>(qa); break;
+        case 5: qform_kernel<5><<<qgrid, 128, 0, st>>>(qa); break;
+        case 6: qform_kernel<6><<<qgrid, 128, 0, st>>>(qa); break;
+        case 7: qform_kernel<7><<<qgrid, 128, 0, st>>>(qa); break;
+        default: qform_kernel<8><<<qgrid, 128, 0, st>>>(qa); break;
+    }
+    MFGP_LAUNCH_CHECK();
+    if (f.ry < wm) {
+        gpad_zero_kernel<<<(unsigned)g.ncols, 128, 0, st>>>(Gbuf, f.ry, wm, 0);
+        MFGP_LAUNCH_CHECK();
+    }
+    // step 6 (and h'(ix)) by the evaluation half of gram_eval_kernel: no training rows to add, G' comes from the store
+    const int pitch = (f.ry % 8 == 4) ? f.ry : f.ry + 4;
+    const int nstage = 2;
+    const size_t gsmem = sizeof(double) * ((size_t)nstage * G_ROWS * pitch + 8 + wm * (wm + 2) + 2 * F_LW) + 8 * G_MAXSTAGE + 64;
+    MFGP_CUDA_CHECK(cudaFuncSetAttribute(gram_eval_kernel<40>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));
+    MFGP_CUDA_CHECK(cudaFuncSetAttribute(gram_eval_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));
+    GramArgs ga;
+    ga.YpL = nullptr; ga.YpH = f.Yp; ga.ryL = 0; ga.ryH = f.ry;
+    ga.npad = 0; ga.Uy = L.Uy; ga.ny = (int)g.ny; ga.col_begin = 0;
+    ga.Gstore = Gbuf; ga.accumulate = 1;
+    ga.HzL = nullptr; ga.HzH = f.Hz; ga.UxL = nullptr; ga.UxH = f.Ux; ga.kL = 0; ga.kH = f.kpad;
+    ga.mean = dp.mean_H; ga.k0 = dp.k0; ga.mu = mu; ga.var = var; ga.qred = qred;
+    ga.pitch = pitch; ga.nstage = nstage;
+    if (wm == 40) gram_eval_kernel<40><<<(unsigned)g.ncols, 128, gsmem, st>>>(ga);
+    else gram_eval_kernel<64><<<(unsigned)g.ncols, 128, gsmem, st>>>(ga);
+    MFGP_LAUNCH_CHECK();
+    return MFGP_OK;
+}
 }  // namespace
 
 // Factored posterior for the whole columns [ix0, ix0 + ncols) of the tensor-product grid ux[nx] x uy[ny] (x-major); outputs
@@ -608,7 +819,13 @@ extern "C" int mfgp_posterior_grid_factored_solved(const double* ux, int64_t nx,
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     FLayout L;
     f_carve(g, work, L);
-    int64_t off = 0;
+    const int64_t zoff = (int64_t)L.parts[0].ry * L.parts[0].kpad;
+    unpack_z_kernel<<<(unsigned)((npad + 255) / 256), 256, 0, st>>>(Yall, ldY, (int)zoff, (int)npad, L.zbuf);
+    MFGP_LAUNCH_CHECK();
+    if (z_out) MFGP_CUDA_CHECK(cudaMemcpyAsync(z_out, L.zbuf, sizeof(double) * npad, cudaMemcpyDeviceToDevice, st));
+    rc = f_tail_gram(g, L, Yall, ldY, Gstore, Hz_store, mu, var, qred, st);      // Gram route: M = Y^T Y, then quadratic forms
+    if (rc <= 0) return rc;
+    int64_t off = 0;                                                             // direct route (cheaper for few training rows)
     for (int pi = 0; pi < L.nparts; pi++) {
         FPart& f = L.parts[pi];
         const int cols = f.ry * f.kpad;
@@ -617,9 +834,6 @@ extern "C" int mfgp_posterior_grid_factored_solved(const double* ux, int64_t nx,
         MFGP_LAUNCH_CHECK();
         off += cols;
     }
-    unpack_z_kernel<<<(unsigned)((npad + 255) / 256), 256, 0, st>>>(Yall, ldY, (int)off, (int)npad, L.zbuf);
-    MFGP_LAUNCH_CHECK();
-    if (z_out) MFGP_CUDA_CHECK(cudaMemcpyAsync(z_out, L.zbuf, sizeof(double) * npad, cudaMemcpyDeviceToDevice, st));
     return f_tail(g, L, L.zbuf, npad, Gstore, Hz_store, 0, mu, var, qred, st);
 }
 

@@ -849,10 +849,10 @@ struct DfScratch {        // diagnostics (MFGP_DF_TRACE=1) and the cached SM cou
 };
 DfScratch g_df[16];
 
-int use_potrf_pipe() {        // MFGP_POTRF=classic: the unpipelined 64x64 sweep (A/B timing)
-    static const int v = [] {
+int use_potrf_pipe() {        // MFGP_POTRF=pipe: the software-pipelined 64x64 sweep (measured SLOWER on B200: 30.1 k vs
+    static const int v = [] { //                  25.7 k cycles per block -- more LDS and predicate work than latency hidden)
         const char* e = getenv("MFGP_POTRF");
-        return (e && std::strcmp(e, "classic") == 0) ? 0 : 1;
+        return (e && std::strcmp(e, "pipe") == 0) ? 1 : 0;
     }();
     return v;
 }

@@ -115,12 +115,16 @@ def test_short_length_scale_keeps_the_dense_kernel():
     assert np.max(np.abs(mu.cpu().numpy() - mu_o)) <= TOL * max(1.0, np.max(np.abs(mu_o)))
 
 
+@pytest.mark.parametrize("route", ["direct", "m"])
 @pytest.mark.parametrize("nx,ny,N,multi", [(64, 64, 300, True), (96, 80, 700, True), (72, 72, 200, False)])
-def test_fused_fit_and_factored_posterior(nx, ny, N, multi):
+def test_fused_fit_and_factored_posterior(nx, ny, N, multi, route, monkeypatch):
     """Deferred fit: refactor(check=False) only marks the factor stale, the factored posterior then runs
     mfgp_cholesky_solve (right-hand sides forward-substituted inside the tiled Cholesky kernel) -- no explicit inverse, no W B product.
     Same results as the oracle; L and the lazily completed inverse W are right as well."""
     from mfgp_coverage_b200._coverage import CoverageGrid
+    # both routes of steps 4 + 5: "direct" (Y' per column, Gram over the training rows) and "m" (M = Y^T Y once, quadratic
+    # forms per column); the library's cost model picks one, MFGP_GRAM forces it
+    monkeypatch.setenv("MFGP_GRAM", route)
     xy = _tensor_grid(nx, ny)
     f = synth.truth_function(xy)
     X_L, y_L, X_H, y_H = synth.training_set(xy, f, N, multi=multi)
@@ -240,8 +244,8 @@ def test_factored_incremental_update(nx, ny, N0, adds, multi):
 
 
 @pytest.mark.parametrize("hyp_name", ["two_corners", "ex"])
-@pytest.mark.parametrize("fused", [False, True])
-def test_factored_posterior_with_near_zero_noise(golden_dir, hyp_name, fused):
+@pytest.mark.parametrize("fused", [False, "direct", "m"])
+def test_factored_posterior_with_near_zero_noise(golden_dir, hyp_name, fused, monkeypatch):
     """The reference's own hyper-parameter files with noises of e^-27 ... e^-58 (two_corners_mf_hyp.csv, ex_hyp.csv): the
     only regularisation left is the 1e-8 jitter, lambda_min(K) = 1e-8 and cond(K) ~ 2e9 at N = 512.  The Chebyshev
     re-expansion error of the cross-covariances (~5e-15 entrywise) is amplified by |L^-1| ~ 1e4 in the variance, so this is
@@ -254,6 +258,8 @@ def test_factored_posterior_with_near_zero_noise(golden_dir, hyp_name, fused):
     from scipy.linalg import solve_triangular
     import os
     from mfgp_coverage_b200._coverage import CoverageGrid
+    if fused:
+        monkeypatch.setenv("MFGP_GRAM", fused)          # the fused fit with either route of the per-column Gram stage
     hyp = {"two_corners": np.load(os.path.join(golden_dir, "inputs_two_corners.npz"))["mf_hyp"],
            "ex": np.load(os.path.join(golden_dir, "logged_ex_gp.npz"))["hyp"]}[hyp_name]
     xy = _tensor_grid(256, 256)
