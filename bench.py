@@ -586,17 +586,18 @@ def run_c5(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
-    sim.INCREMENTAL = os.environ.get("MFGP_INCREMENTAL", "1") == "1"
+    runs = args.steps                                      # a step is one whole run; the K runs of a rank are stepped TOGETHER
 
-    def one_run(k):
-        with contextlib.redirect_stdout(io.StringIO()):
-            out = sim.periodic("periodic_hmf", k, T, A, synth.agents(A, 1000 * rank + k), truth_arr, C5["sigma_n"],
-                               prior_arr, synth.MF_HYP, False, None, True, rng=random.Random(k),
-                               noise_rng=np.random.default_rng(1000 * rank + k))
-        return out[0][-1]["Loss"]
+    def sweep(tag):
+        """K periodic_hmf runs on the batched stepper (simulator.run_batched): host arrays in, log rows out."""
+        starts = np.stack([synth.agents(A, 100_000 * tag + 1000 * rank + k) for k in range(runs)])
+        rngs = [np.random.default_rng(100_000 * tag + 1000 * rank + k) for k in range(runs)]
+        logs = sim.run_batched("periodic_hmf", list(range(runs)), T, A, starts, truth_arr, C5["sigma_n"], prior_arr, synth.MF_HYP,
+                               noise_rngs=rngs)
+        return logs
 
-    for k in range(args.warmup):
-        one_run(10_000 + k)
+    for k in range(max(1, min(args.warmup, 2))):
+        sweep(10 + k)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -604,10 +605,12 @@ def run_c5(args):
     sampler.start()
     l0 = nat.lib().mfgp_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_host0 = time.perf_counter()
     e0.record()
-    losses = [one_run(k) for k in range(args.steps)]
+    logs = sweep(1)
     e1.record()
     torch.cuda.synchronize()
+    t_host = time.perf_counter() - t_host0
     launches = nat.lib().mfgp_launch_count() - l0
     ms = e0.elapsed_time(e1)
     if world > 1:
@@ -615,23 +618,39 @@ def run_c5(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     clocks = sampler.result()
+    # the same run, one simulation at a time through simulator.periodic (the round-1 path), for comparison
+    seq = None
     if rank == 0:
-        its = world * args.steps * T
+        import contextlib
+        import io
+        import random
+        sim.INCREMENTAL = True
+        ts = time.perf_counter()
+        with contextlib.redirect_stdout(io.StringIO()):
+            sim.periodic("periodic_hmf", 0, T, A, synth.agents(A, 100_000 + 1000 * rank), truth_arr, C5["sigma_n"], prior_arr,
+                         synth.MF_HYP, False, None, True, rng=random.Random(0), noise_rng=np.random.default_rng(100_000 + 1000 * rank))
+        torch.cuda.synchronize()
+        seq = T / (time.perf_counter() - ts)
+    if rank == 0:
+        its = world * runs * T
         value = its / (ms * 1e-3)
         G = truth_arr.shape[0]
         line = {"metric": "coverage iterations/s (periodic_hmf replicate sweep)", "value": value, "unit": "iterations/s",
-                "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+                "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / runs,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "data": "synthetic", "dtype": "f64",
                 "config": {"workload": C5["desc"], "grid_points": int(G), "agents": A, "iterations_per_run": T,
-                           "runs_per_gpu_timed": args.steps, "parallelism": f"run-sharded x{world} (one process per GPU)",
-                           "incremental": bool(sim.INCREMENTAL),
-                           "l2_policy": "every run re-uploads its grid and rebuilds its model; working set is launch-bound"},
+                           "runs_per_gpu_timed": runs, "parallelism": f"run-sharded x{world} (one process per GPU), {runs} runs "
+                           "per GPU stepped together (simulator.run_batched: 3 kernel launches per iteration for all runs)",
+                           "l2_policy": f"per-run state {4.0 * runs:.0f} MB per GPU: larger than L2 from ~32 runs on"},
                 "clocks": clocks, "gpu_launches": int(launches),
-                "e2e": {"value": value, "unit": "iterations/s", "h2d_bytes_per_step": int(G * 24 + 36 * 24),
-                        "d2h_bytes_per_step": int(T * A * 8 * 8),
-                        "note": "the timed region IS the public API (simulator.periodic with host arrays in, log rows out)"},
-                "sweep_512_runs_s": 512.0 / world * (ms * 1e-3 / args.steps),
-                "grid_points_per_s": value * G, "check": {"final_loss_run0": float(losses[0])}}
+                "e2e": {"value": world * runs * T / t_host, "unit": "iterations/s", "h2d_bytes_per_step": int(G * 24 + 36 * 24 + T * A * 8),
+                        "d2h_bytes_per_step": int(T * A * 11 * 8 + T * 8 + T * A * 5 * 8), "host_seconds": t_host,
+                        "note": "public API (simulator.run_batched: host arrays in, the reference's log-row dicts out), wall clock "
+                                "including the construction of the log rows on the host"},
+                "sweep_512_runs_s": {"device": 512.0 / (world * runs) * (ms * 1e-3), "with_host_log_rows": 512.0 / (world * runs) * t_host},
+                "sequential_single_run_iterations_per_s": seq,
+                "grid_points_per_s": value * G,
+                "check": {"final_loss_run0": float(logs[0][0][-1]["Loss"]), "samples_run0": len(logs[0][2])}}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -640,7 +659,7 @@ def run_c5(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS) + ["c5"])
@@ -648,6 +667,8 @@ def main():
                     help="N > 1: the fixed grid split over the GPUs (strong, default: BASELINE config 4) or a fixed per-GPU shard (weak)")
     args = ap.parse_args()
     args.scaling_given = any(a.startswith("--scaling") for a in sys.argv[1:])
+    if args.steps is None:      # c5: a step is one whole run and the runs of a rank are stepped together -> the full sweep
+        args.steps = max(1, C5["total_runs"] // max(1, int(os.environ.get("WORLD_SIZE", "1")))) if args.workload == "c5" else 5
     if args.workload == "c5":
         run_c5(args)
     elif args.impl == "reference":

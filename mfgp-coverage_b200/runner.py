@@ -9,6 +9,7 @@ The reference fans simulations out over a `multiprocessing.Pool` of CPU workers 
 worker processes are spawned one per GPU slot (worker r uses device r % #GPUs) and the replicate simulations are
 sharded over them -- run-sharding, no communication until the host concatenates the logs (:144-147).
 """
+import os
 import random
 import time
 
@@ -48,6 +49,43 @@ def run_sim(args):
     return loss_log_t, agent_log_t, sample_log_t
 
 
+# MFGP_BATCHED=1 (or runner.BATCHED = True, or run(batched=True)): the replicate simulations of lloyd / periodic / todescato
+# experiments are stepped TOGETHER on the device (simulator.run_batched: three kernel launches advance every run by one
+# iteration) instead of one host loop per simulation.  The random streams are consumed exactly as the sequential loop
+# consumes them: per simulation the 2 A start coordinates, then (todescato) one uniform per agent and iteration.
+BATCHED = os.environ.get("MFGP_BATCHED", "0") == "1"
+BATCH_RUNS = 512          # simulations per device batch (state: ~4 MB per run at 64x64 points, 520 samples)
+
+
+def _batchable(args):
+    algos = {a[1] for a in args}
+    return len(args) > 1 and len(algos) == 1 and not any("choi" in a for a in algos) and \
+        any(k in next(iter(algos)) for k in ("todescato", "lloyd", "periodic")) and all(a[10] is None for a in args)
+
+
+def run_sims_batched(args):
+    """run_sim for a list of argument tuples of ONE experiment, in order, on the batched stepper."""
+    from .simulator import run_batched
+    out = []
+    for b0 in range(0, len(args), BATCH_RUNS):
+        chunk = args[b0:b0 + BATCH_RUNS]
+        (_, algo, _, iterations, agents, truth, sigma_n, prior, hyp, _, _, _) = chunk[0]
+        pos, unif = [], []
+        for a in chunk:                                   # the draws of run_sim (:41-43) and of todescato (:943), in order
+            x_positions = [random.random() for i in range(agents)]
+            y_positions = [random.random() for i in range(agents)]
+            pos.append(np.column_stack((x_positions, y_positions)))
+            if "todescato" in algo and "choi" not in algo:
+                unif.append([[random.random() for i in range(agents)] for t in range(iterations)])
+        print(line_break + f"Start Simulations {chunk[0][2]}..{chunk[-1][2]} : {algo} (batched)" + line_break)
+        sim_start = time.time()
+        logs = run_batched(algo, [a[2] for a in chunk], iterations, agents, np.array(pos), truth, sigma_n, prior, hyp,
+                           uniforms=np.array(unif) if unif else None)
+        print(line_break + f"End Simulations : {algo}\nTime : {time.time() - sim_start}" + line_break)
+        out.extend(logs)
+    return out
+
+
 def _worker(rank, world, args, seed, queue, fn=None):
     """One worker process.  Whatever happens it reports exactly once: ("ok", rank, results) or ("error", rank, exception,
     traceback text) -- Pool.map in the reference (runner.py:131-141) re-raises worker exceptions in the parent too."""
@@ -59,8 +97,12 @@ def _worker(rank, world, args, seed, queue, fn=None):
         if seed is not None:
             random.seed(seed + rank)
         out = {}
-        for i in range(rank, len(args), world):       # run-sharding: simulation i goes to worker i mod world
-            out[i] = (fn or run_sim)(args[i])
+        mine = list(range(rank, len(args), world))    # run-sharding: simulation i goes to worker i mod world
+        if fn is None and BATCHED and _batchable([args[i] for i in mine]):
+            out = dict(zip(mine, run_sims_batched([args[i] for i in mine])))
+        else:
+            for i in mine:
+                out[i] = (fn or run_sim)(args[i])
         queue.put(("ok", rank, out))
     except BaseException as e:                         # noqa: BLE001 -- everything goes home, the parent re-raises
         tb = traceback.format_exc()
@@ -81,6 +123,8 @@ def _map_sims(args, n_processors, seed=None, fn=None):
     if n_processors <= 1:
         if seed is not None:
             random.seed(seed)
+        if fn is None and BATCHED and _batchable(args):
+            return run_sims_batched(args)
         return [(fn or run_sim)(a) for a in args]
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
@@ -124,8 +168,13 @@ def _map_sims(args, n_processors, seed=None, fn=None):
 
 def run(n_processors=4, name="Data/australia9", prefix="Data/australia9.3", agents=16, iterations=120,
         simulations=100, sigma_n=0.1, console=False, log=True, plotter=None, algorithms=None, seed=None,
-        null_prior_path="Data/null_prior.csv"):
-    """reference runner.py:72-161.  Keyword defaults are the literals the reference hard-codes."""
+        null_prior_path="Data/null_prior.csv", batched=None):
+    """reference runner.py:72-161.  Keyword defaults are the literals the reference hard-codes.  `batched`: step the
+    replicate simulations of an algorithm together on the device (see BATCHED above; default: the environment's setting)."""
+    global BATCHED
+    if batched is not None:
+        BATCHED = bool(batched)
+        os.environ["MFGP_BATCHED"] = "1" if BATCHED else "0"      # spawned workers read the environment
     np.random.seed(1234)
     if algorithms is None:
         algorithms = ["todescato_nsf", "choi_nsf", "todescato_hsf", "choi_hsf", "todescato_hmf", "choi_hmf", "lloyd"]
