@@ -588,12 +588,12 @@ def run_c5(args):
     dev = torch.device("cuda", local)
     runs = args.steps                                      # a step is one whole run; the K runs of a rank are stepped TOGETHER
 
-    def sweep(tag):
+    def sweep(tag, use_graph=False):
         """K periodic_hmf runs on the batched stepper (simulator.run_batched): host arrays in, log rows out."""
         starts = np.stack([synth.agents(A, 100_000 * tag + 1000 * rank + k) for k in range(runs)])
         rngs = [np.random.default_rng(100_000 * tag + 1000 * rank + k) for k in range(runs)]
         logs = sim.run_batched("periodic_hmf", list(range(runs)), T, A, starts, truth_arr, C5["sigma_n"], prior_arr, synth.MF_HYP,
-                               noise_rngs=rngs)
+                               noise_rngs=rngs, use_graph=use_graph)
         return logs
 
     for k in range(max(1, min(args.warmup, 2))):
@@ -618,6 +618,23 @@ def run_c5(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     clocks = sampler.result()
+    # the device loop alone, eager launches vs ONE CUDA graph replay (capture excluded), on fresh state each
+    from mfgp_coverage_b200._batched import BatchedRuns
+    loop_ms = {}
+    for mode in ("eager", "graph"):
+        starts = np.stack([synth.agents(A, 7_000_000 + 1000 * rank + k) for k in range(runs)])
+        br = BatchedRuns("periodic", truth_arr, prior_arr, synth.MF_HYP, A, T, starts,
+                         noise=np.random.default_rng(3).normal(0, C5["sigma_n"], (runs, T * A)))
+        if mode == "graph":
+            br.capture()
+        torch.cuda.synchronize()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        br.run(use_graph=mode == "graph")
+        g1.record()
+        torch.cuda.synchronize()
+        loop_ms[mode] = g0.elapsed_time(g1)
+        del br
     # the same run, one simulation at a time through simulator.periodic (the round-1 path), for comparison
     seq = None
     if rank == 0:
@@ -649,6 +666,8 @@ def run_c5(args):
                                 "including the construction of the log rows on the host"},
                 "sweep_512_runs_s": {"device": 512.0 / (world * runs) * (ms * 1e-3), "with_host_log_rows": 512.0 / (world * runs) * t_host},
                 "sequential_single_run_iterations_per_s": seq,
+                "device_loop_ms": {"eager_launches": loop_ms["eager"], "one_cuda_graph": loop_ms["graph"],
+                                   "what": f"{T} iterations x 3 launches for {runs} runs, device time of the loop only"},
                 "grid_points_per_s": value * G,
                 "check": {"final_loss_run0": float(logs[0][0][-1]["Loss"]), "samples_run0": len(logs[0][2])}}
         print(json.dumps(line))

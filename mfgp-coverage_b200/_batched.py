@@ -165,10 +165,29 @@ class BatchedRuns:
         nat.check(_lib().mfgp_batch_step(ctypes.byref(self._b), ctypes.byref(self.pstruct), int(it), nat.stream_ptr()),
                   "mfgp_batch_step")
 
-    def run(self):
-        """All iterations, no host round trip in between; returns when the device is done."""
-        for it in range(self.T):
-            self.step(it)
+    def capture(self):
+        """Record the whole run -- every iteration's three launches -- into ONE CUDA graph.  Nothing in the loop depends on
+        the host (sample counts, explore decisions and the growing training-set sizes live in device memory), so the graph
+        is valid for any state the buffers hold when it is replayed."""
+        graph = torch.cuda.CUDAGraph()
+        side = torch.cuda.Stream(device=self.dev)
+        side.wait_stream(torch.cuda.current_stream(self.dev))
+        with torch.cuda.graph(graph, stream=side):
+            for it in range(self.T):
+                self.step(it)
+        self.graph = graph
+        return self
+
+    def run(self, use_graph=False):
+        """All iterations, no host round trip in between; returns when the device is done.  `use_graph`: replay the run
+        from one CUDA graph (captured on first use) instead of 3 * iterations launches."""
+        if use_graph:
+            if self.graph is None:
+                self.capture()
+            self.graph.replay()
+        else:
+            for it in range(self.T):
+                self.step(it)
         torch.cuda.current_stream(self.dev).synchronize()
         st = self.status.cpu().numpy()
         bad = np.nonzero(st)[0]

@@ -587,7 +587,7 @@ def todescato(title, sim_num, iterations, agents, positions, truth, sigma_n, pri
 
 
 def run_batched(algo, sim_nums, iterations, agents, positions, truth, sigma_n, prior, hyp, uniforms=None, noise=None,
-                noise_rngs=None, exact_tie_loss=False):
+                noise_rngs=None, exact_tie_loss=False, use_graph=False):
     """Many independent runs of ONE experiment stepped together on the device (config c5, the replicate sweeps of
     runner.py:100, :131-147): `algo` in ("lloyd", "periodic", "todescato"), `positions[R, A, 2]` the runs' start positions
     (updated in place to the final ones, like the single-run functions do).  Returns a list of R (loss_log, agent_log,
@@ -603,7 +603,7 @@ def run_batched(algo, sim_nums, iterations, agents, positions, truth, sigma_n, p
     if prior is not None and len(prior) > 0:
         prior_arr = np.vstack(prior.values.tolist()) if hasattr(prior, "values") else np.asarray(prior, dtype=np.float64)
     br = BatchedRuns(kind, truth_arr, prior_arr, hyp, agents, iterations, positions, sigma_n, uniforms, noise, noise_rngs)
-    br.run()
+    br.run(use_graph=use_graph)          # use_graph: the whole device-resident loop replayed from one CUDA graph
     logs = br.logs(sim_nums, exact_tie_loss)
     np.asarray(positions)[...] = br.final_positions()
     return logs

@@ -85,3 +85,21 @@ def test_runner_batched_mode_writes_the_same_csvs(golden_dir, tmp_path):
                 a, b = a[a.Iteration == 0], b[b.Iteration == 0]
             num = [c for c in a.columns if c != "Fidelity"]
             assert np.allclose(a[num].values.astype(float), b[num].values.astype(float), rtol=1e-9, atol=1e-12), (algo, kind)
+
+
+def test_whole_run_replayed_from_one_cuda_graph_is_bitwise_the_eager_run():
+    """the device-resident iteration loop (sample -> append -> posterior -> both partitions -> decision ->
+    move, simulator.py:888-904) captured once as a CUDA graph: same log buffers, bit for bit."""
+    import torch
+    from mfgp_coverage_b200._batched import BatchedRuns
+    truth_arr, prior_arr, hyp = _inputs(32, True)
+    R, A, T = 6, 5, 20
+    starts = np.stack([synth.agents(A, 40 + r) for r in range(R)])
+    unif = np.random.default_rng(1).random((R, T, A))
+    noise = np.random.default_rng(2).normal(0, 0.1, (R, T * A))
+    a = BatchedRuns("todescato", truth_arr, prior_arr, hyp, A, T, starts, uniforms=unif, noise=noise).run()
+    b = BatchedRuns("todescato", truth_arr, prior_arr, hyp, A, T, starts, uniforms=unif, noise=noise).run(use_graph=True)
+    assert b.graph is not None
+    for name in ("log_loss", "log_agent", "log_sample", "nsamples", "Ncur", "mu", "var", "pos"):
+        assert torch.equal(getattr(a, name), getattr(b, name)), name
+    assert int(a.nsamples.sum()) > 0
