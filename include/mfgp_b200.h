@@ -228,8 +228,10 @@ int cov_assign_reduce_grid(const double* xy, const double* w, const double* var,
  * restricted to its first A cells.  Output in cov_assign_reduce's layout: poly_xy[<= cap_vertices, 2], poly_off[A+1],
  * plus areas[A] (shoelace).  Vertices agree with Qhull's to ~1e-13; only grid points exactly on a bisector can be
  * classified differently, so parity runs keep Qhull.  flag[0] = 1 (and NaN areas) if a polygon outgrew the capacity. */
+int64_t cov_voronoi_clip_workspace_bytes(int64_t A);
 int cov_voronoi_clip(const double* seeds, int64_t A, double xmin, double xmax, double ymin, double ymax, double eps,
-                     double* poly_xy, int32_t* poly_off, int64_t cap_vertices, double* areas, int32_t* flag, void* stream);
+                     double* poly_xy, int32_t* poly_off, int64_t cap_vertices, double* areas, int32_t* flag, void* work,
+                     int64_t work_bytes, void* stream);
 
 /* O(A) finishing of cov_assign_reduce's partial sums with the reference's arithmetic (simulator.py:215-219, :256-271):
  * out[0] = loss, out[1+2i], out[2+2i] = centroid i clamped to [xmin,xmax] x [ymin,ymax], out[1+2Ac+i] = max variance of
@@ -256,6 +258,41 @@ int64_t choi_greedy(const double* Xs, int64_t G, double* Vc, int64_t ldv, int64_
                     double* qred, const mfgp_params* p_host, double threshold, double tie_rel, int64_t max_picks,
                     int64_t* picks_host,
                     void* work, int64_t work_bytes, void* stream);
+
+/* ---- batched replicate stepper: the loop bodies of simulator.py periodic :618-785, todescato :788-954, lloyd :508-616 for many
+ *      independent runs of one experiment (runner.py:100, :131-147 fans the replicates out over a process pool) ----------------- */
+
+/* State of a batch of R runs; every pointer is a caller-owned device buffer with a leading run dimension.
+ * Shared by the runs: grid xy[G,2] (x-major tensor grid ux[nx] x uy[ny]), truth f[G].  Per run: training set Xt[cap,2], y[cap]
+ * (first NL rows: the lofi prior), W[cap,cap] = L^-1 (lower) and z[cap] of the standing fit, axis-factor tables
+ * T{x,y}{L,H}[cap][nx|ny] (exp(-0.5 ((u - U_n) / l)^2) per training point n), standing posterior mu[G] / var[G], positions /
+ * previous positions / Lloyd seeds pos, prev, cen [A,2], pos_idx[A] (grid index of the position or -1), prob[A], explore[A],
+ * counters Ncur, knew, status (0 ok, k > 0: pivot k-1 not positive, -4: empty cell, -1: capacity), noise_used, nsamples,
+ * ties[iterations] (grid points within TIE_TOL/10 of a bisector, per iteration).  Random numbers drawn by the host in the
+ * order the reference consumes them: noise[max_samples] (N(0, sigma_n) per sample, :707), unif[iterations, A] (:943).
+ * Logs: log_loss[iterations], log_agent[iterations, A, 11] (X, Y, XMax, YMax, VarMax, Var0, XCentroid, YCentroid, ProbExplore,
+ * Explore, Distance: the reference's agent row), log_sample[max_samples, 5] (Iteration, Agent, X, Y, Sample). */
+typedef struct mfgp_batch {
+    int64_t runs, G, nx, ny, A, NL, cap, algo /* 0 lloyd, 1 periodic, 2 todescato */, iterations, max_samples;
+    double xmin, xmax, ymin, ymax, eps, tie_tol, amax_rel;
+    const double* xy; const double* f; const double* ux; const double* uy;
+    double* Xt; double* y; double* W; double* z;
+    double* TxL; double* TyL; double* TxH; double* TyH;
+    double* mu; double* var;
+    double* pos; double* prev; double* cen;
+    int64_t* pos_idx;
+    double* prob; int32_t* explore;
+    int32_t* Ncur; int32_t* knew; int32_t* status; int32_t* noise_used; int32_t* nsamples; int32_t* ties;
+    const double* noise; const double* unif;
+    double* log_loss; double* log_agent; double* log_sample;
+} mfgp_batch;
+
+/* One iteration of every run: take the exploring agents' samples (:698-713), append them to the model by a block-bordered
+ * update of W and z (the reference refits, gaussian_process.py:266-268 / :540-542), add the new rows to the standing
+ * posterior (:723), evaluate both partitions -- loss (:194-228), centroids (:231-283), per-cell max variance (:286-323) --
+ * write the log rows (:740-768), decide (:771-775, :942-943) and move (:777-782).  Three launches, no host involvement
+ * between iterations: the whole run can be captured in one CUDA graph.  b_host / p_host are read on the host. */
+int mfgp_batch_step(const mfgp_batch* b_host, const mfgp_params* p_host, int64_t iteration, void* stream);
 
 /* ---- hyper-parameter training: replaces SFGP.likelihood / MFGP.likelihood gaussian_process.py:81-105, :344-384 and the
  *      autograd gradient behind SFGP.train / MFGP.train :107-119, :386-399 ------------------------------------------- */

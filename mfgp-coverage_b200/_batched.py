@@ -14,7 +14,6 @@ grid points lying exactly on a bisector; the reference resolves those through Qh
 them per (run, iteration); `exact_tie_loss=True` re-evaluates exactly those losses with Qhull cells on the single-run path.
 """
 import ctypes
-from ctypes import POINTER, Structure, c_double, c_int64, c_void_p
 
 import numpy as np
 import torch
@@ -25,23 +24,6 @@ from .gaussian_process import evaluate_hyp, prior_variance
 
 ALGOS = {"lloyd": 0, "periodic": 1, "todescato": 2}
 LOG_COLS = ("X", "Y", "XMax", "YMax", "VarMax", "Var0", "XCentroid", "YCentroid", "ProbExplore", "Explore", "Distance")
-
-
-class _BatchStruct(Structure):
-    _fields_ = [(n, c_int64) for n in ("runs", "G", "nx", "ny", "A", "NL", "cap", "algo", "iterations", "max_samples")] + \
-               [(n, c_double) for n in ("xmin", "xmax", "ymin", "ymax", "eps", "tie_tol", "amax_rel")] + \
-               [(n, c_void_p) for n in ("xy", "f", "ux", "uy", "Xt", "y", "W", "z", "TxL", "TyL", "TxH", "TyH", "mu", "var", "pos",
-                                        "prev", "cen", "pos_idx", "prob", "explore", "Ncur", "knew", "status", "noise_used",
-                                        "nsamples", "ties", "noise", "unif", "log_loss", "log_agent", "log_sample")]
-
-
-def _lib():
-    lib = nat.lib()
-    if not getattr(lib, "_batch_bound", False):
-        lib.mfgp_batch_step.restype = ctypes.c_int
-        lib.mfgp_batch_step.argtypes = [POINTER(_BatchStruct), POINTER(nat.MfgpParams), c_int64, c_void_p]
-        lib._batch_bound = True
-    return lib
 
 
 class BatchedRuns:
@@ -149,7 +131,7 @@ class BatchedRuns:
             self.unif = z(1)
         self.log_loss, self.log_agent = z(R, T), z(R, T, A, len(LOG_COLS))
         self.log_sample = z(R, self.max_samples, 5)
-        b = _BatchStruct()
+        b = nat.MfgpBatch()
         b.runs, b.G, b.nx, b.ny, b.A, b.NL, b.cap, b.algo, b.iterations, b.max_samples = R, G, nx, ny, A, NL, cap, self.code, T, \
             self.max_samples
         b.xmin, b.xmax, b.ymin, b.ymax = (float(v) for v in self.bbox)
@@ -162,7 +144,7 @@ class BatchedRuns:
         self.graph = None
 
     def step(self, it):
-        nat.check(_lib().mfgp_batch_step(ctypes.byref(self._b), ctypes.byref(self.pstruct), int(it), nat.stream_ptr()),
+        nat.check(nat.lib().mfgp_batch_step(ctypes.byref(self._b), ctypes.byref(self.pstruct), int(it), nat.stream_ptr()),
                   "mfgp_batch_step")
 
     def capture(self):

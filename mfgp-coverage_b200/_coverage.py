@@ -126,8 +126,8 @@ class ClippedVoronoi:
         self._stale = False
         if reuse is not None and reuse.A == self.A:
             reuse._stale = True      # its device buffers now belong to this object
-            self.seeds, self.poly, self.off, self.dev_areas, self.flag, self._stage = \
-                reuse.seeds, reuse.poly, reuse.off, reuse.dev_areas, reuse.flag, reuse._stage
+            self.seeds, self.poly, self.off, self.dev_areas, self.flag, self._stage, self._cwork = \
+                reuse.seeds, reuse.poly, reuse.off, reuse.dev_areas, reuse.flag, reuse._stage, reuse._cwork
             # page-locked staging + asynchronous copy: the host never waits for what is already queued on the stream
             # (the previous user of the staging buffer is long done: its iteration ended with a synchronising copy home)
             self._stage.numpy()[:] = c.reshape(-1)
@@ -140,10 +140,12 @@ class ClippedVoronoi:
             self.off = torch.empty(self.A + 2, dtype=torch.int32, device=self.device)
             self.dev_areas = torch.empty(max(self.A, 1), **f64)
             self.flag = torch.empty(1, dtype=torch.int32, device=self.device)
+            self._cwork = torch.empty(int(nat.lib().cov_voronoi_clip_workspace_bytes(max(self.A, 1))) // 8 + 8, **f64)
         if self.A:
             nat.check(nat.lib().cov_voronoi_clip(nat.ptr(self.seeds), self.A, bb[0], bb[1], bb[2], bb[3], EPS,
                                                  nat.ptr(self.poly), nat.ptr(self.off), self.nvert, nat.ptr(self.dev_areas),
-                                                 nat.ptr(self.flag), nat.stream_ptr()), "cov_voronoi_clip")
+                                                 nat.ptr(self.flag), nat.ptr(self._cwork), self._cwork.numel() * 8,
+                                                 nat.stream_ptr()), "cov_voronoi_clip")
         self._host = None
         self._areas_host = None
 

@@ -24,6 +24,14 @@ class MfgpParams(Structure):
                 ("jitter", c_double), ("multi", c_int32), ("reserved", c_int32)]
 
 
+class MfgpBatch(Structure):      # struct mfgp_batch (include/mfgp_b200.h)
+    _fields_ = [(n, c_int64) for n in ("runs", "G", "nx", "ny", "A", "NL", "cap", "algo", "iterations", "max_samples")] + \
+               [(n, c_double) for n in ("xmin", "xmax", "ymin", "ymax", "eps", "tie_tol", "amax_rel")] + \
+               [(n, c_void_p) for n in ("xy", "f", "ux", "uy", "Xt", "y", "W", "z", "TxL", "TyL", "TxH", "TyH", "mu", "var", "pos",
+                                        "prev", "cen", "pos_idx", "prob", "explore", "Ncur", "knew", "status", "noise_used",
+                                        "nsamples", "ties", "noise", "unif", "log_loss", "log_agent", "log_sample")]
+
+
 # name -> (restype, argtypes); this table is also what tests/test_abi.py checks against include/mfgp_b200.h
 SIGNATURES = {
     "mfgp_version": (c_char_p, []),
@@ -88,8 +96,9 @@ SIGNATURES = {
                                        c_void_p, c_int64, c_void_p, c_void_p, c_int64,
                                        c_double, c_double, c_double, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                        c_void_p, c_int64, c_void_p]),
+    "cov_voronoi_clip_workspace_bytes": (c_int64, [c_int64]),
     "cov_voronoi_clip": (c_int, [c_void_p, c_int64, c_double, c_double, c_double, c_double, c_double, c_void_p, c_void_p,
-                                 c_int64, c_void_p, c_void_p, c_void_p]),
+                                 c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "cov_finish": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_double,
                            c_double, c_double, c_double, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "cov_argmax": (c_int, [c_void_p, c_int64, c_int64, c_double, c_double, c_void_p, c_void_p, c_void_p, c_int64,
@@ -97,6 +106,7 @@ SIGNATURES = {
     "choi_greedy": (c_int64, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p,
                               POINTER(MfgpParams), c_double, c_double, c_int64, POINTER(c_int64), c_void_p, c_int64,
                               c_void_p]),
+    "mfgp_batch_step": (c_int, [POINTER(MfgpBatch), POINTER(MfgpParams), c_int64, c_void_p]),
     "mfgp_nlml_workspace_bytes": (c_int64, [c_int64]),
     "mfgp_nlml_grad": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int64,
                                POINTER(MfgpParams), c_void_p, c_void_p, c_int64, c_void_p]),

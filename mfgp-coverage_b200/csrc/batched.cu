@@ -429,20 +429,7 @@ using namespace mfgp;
 // (the host module mfgp-coverage_b200/_batched.py owns the buffers; this file only receives pointers)
 extern "C" {
 
-typedef struct mfgp_batch {
-    int64_t runs, G, nx, ny, A, NL, cap, algo, iterations, max_samples;
-    double xmin, xmax, ymin, ymax, eps, tie_tol, amax_rel;
-    const double* xy; const double* f; const double* ux; const double* uy;
-    double* Xt; double* y; double* W; double* z;
-    double* TxL; double* TyL; double* TxH; double* TyH;
-    double* mu; double* var;
-    double* pos; double* prev; double* cen;
-    int64_t* pos_idx;
-    double* prob; int32_t* explore;
-    int32_t* Ncur; int32_t* knew; int32_t* status; int32_t* noise_used; int32_t* nsamples; int32_t* ties;
-    const double* noise; const double* unif;
-    double* log_loss; double* log_agent; double* log_sample;
-} mfgp_batch;
+/* struct mfgp_batch: include/mfgp_b200.h */
 
 int mfgp_batch_step(const mfgp_batch* b, const mfgp_params* p_host, int64_t iteration, void* stream) {
     if (!b || !p_host || b->runs <= 0 || b->A <= 0 || b->A > BT_MAXA || b->G <= 0 || b->nx * b->ny != b->G || b->cap <= 0 ||

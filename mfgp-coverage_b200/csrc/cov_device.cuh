@@ -47,11 +47,21 @@ __device__ __forceinline__ int vc_clip_cell(const double* __restrict__ s_seeds, 
     which = 0;
     const double sx = s_seeds[2 * i], sy = s_seeds[2 * i + 1];
     const unsigned lt = (1u << lane) - 1u;
+    // r2max: squared distance of the farthest polygon vertex from the seed.  The bisector with seed j passes at distance
+    // |s_j - s_i| / 2 from s_i, so it cannot cut the polygon when |s_j - s_i|^2 > 4 r2max: those seeds are skipped by a
+    // scalar test (exact: the clip would have left the polygon unchanged).  After the first few neighbours r2max is a few
+    // cell radii and most seeds fall out here.
+    double r2max = 0.0;
+    {
+        const double ex = fmax(fabs(x0 - sx), fabs(x1 - sx)), ey = fmax(fabs(y0 - sy), fabs(y1 - sy));
+        r2max = ex * ex + ey * ey;
+    }
     for (int j = 0; j < A && n > 0; j++) {
         if (j == i) continue;
         const double tx = s_seeds[2 * j], ty = s_seeds[2 * j + 1];
         const double nx = tx - sx, ny = ty - sy;
         if (nx == 0.0 && ny == 0.0) continue;                      // coincident seeds share one cell
+        if (nx * nx + ny * ny > 4.0 * r2max * (1.0 + 1e-9)) continue;
         const double c = 0.5 * ((tx * tx + ty * ty) - (sx * sx + sy * sy));
         double bx[2], by[2], ax[2], ay[2], da[2], db[2];
         bool valid[2], inb[2], cross[2];
@@ -89,6 +99,15 @@ __device__ __forceinline__ int vc_clip_cell(const double* __restrict__ s_seeds, 
         double* T = P; P = Q; Q = T;
         which ^= 1;
         __syncwarp();
+        double r2 = 0.0;                                           // new extent of the polygon around its seed
+#pragma unroll
+        for (int sl = 0; sl < 2; sl++) {
+            const int v = lane + 32 * sl;
+            if (v < n) { const double dx = P[v] - sx, dy = P[64 + v] - sy; r2 = fmax(r2, dx * dx + dy * dy); }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) r2 = fmax(r2, __shfl_xor_sync(0xffffffffu, r2, o));
+        r2max = r2;
     }
     return n;
 }

@@ -942,49 +942,63 @@ extern "C" int cov_argmax(const double* v, int64_t G, int64_t base_index, double
 // One thread per cell; polygons are packed into poly_xy / poly_off in cell order; areas by the shoelace formula
 // (simulator.py:127-136).  flag[0] != 0: a polygon outgrew VC_MAXV or the packed capacity.
 namespace mfgp {
+// Two launches per partition: (1) a warp per cell, VC_WARPS cells per CTA, as many CTAs as it takes -- vertices into a
+// fixed-stride scratch, vertex count and shoelace area per cell; (2) one CTA packs the cells back to back (prefix sum of the
+// counts -> poly_off) for the coverage kernels.
 __global__ void __launch_bounds__(VC_WARPS * 32) cov_voronoi_clip_kernel(const double* __restrict__ seeds, int A, double x0, double x1,
-                                                                         double y0, double y1, double* __restrict__ poly_xy,
-                                                                         int32_t* __restrict__ poly_off, int cap_vertices,
-                                                                         double* __restrict__ areas, int32_t* __restrict__ flag) {
-    __shared__ int counts[COV_MAX_CELLS + 1];
+                                                                         double y0, double y1, double* __restrict__ scratch,
+                                                                         int32_t* __restrict__ counts, double* __restrict__ areas,
+                                                                         int32_t* __restrict__ flag) {
     __shared__ double s_seeds[2 * COV_MAX_CELLS];
     __shared__ double s_buf[VC_WARPS][256];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int e = tid; e < 2 * A; e += blockDim.x) s_seeds[e] = seeds[e];
-    if (tid == 0) counts[0] = 0;
     __syncthreads();
+    const int i = blockIdx.x * VC_WARPS + warp;
+    if (i >= A) return;
     bool overflow = false;
     int which = 0;
-    for (int i = warp; i < A; i += VC_WARPS) {                    // pass 1: vertex counts
-        const int n = vc_clip_cell(s_seeds, A, i, x0, x1, y0, y1, s_buf[warp], lane, overflow, which);
-        if (lane == 0) counts[i + 1] = n;
-        __syncwarp();
+    const int n = vc_clip_cell(s_seeds, A, i, x0, x1, y0, y1, s_buf[warp], lane, overflow, which);
+    const double* px = s_buf[warp] + 128 * which;
+    const double* py = px + 64;
+    double* dst = scratch + (int64_t)i * 2 * VC_MAXV;
+    for (int v = lane; v < n; v += 32) { dst[2 * v] = px[v]; dst[2 * v + 1] = py[v]; }
+    if (lane == 0) {
+        // shoelace: 0.5 |x . roll(y,1) - y . roll(x,1)|, summed in vertex order
+        double s1 = 0.0, s2 = 0.0;
+        for (int v = 0; v < n; v++) {
+            const int u = (v + n - 1) % n;
+            s1 += px[v] * py[u];
+            s2 += py[v] * px[u];
+        }
+        counts[i] = n;
+        areas[i] = overflow ? __longlong_as_double(0x7ff8000000000000LL) : 0.5 * fabs(s1 - s2);   // NaN poisons loss / centroid
+        if (overflow) atomicExch(flag, 1);
+    }
+}
+
+__global__ void __launch_bounds__(256) cov_voronoi_pack_kernel(const double* __restrict__ scratch, const int32_t* __restrict__ counts, int A,
+                                                               double* __restrict__ poly_xy, int32_t* __restrict__ poly_off,
+                                                               int cap_vertices, double* __restrict__ areas, int32_t* __restrict__ flag) {
+    __shared__ int off[COV_MAX_CELLS + 1];
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        off[0] = 0;
+        for (int c = 0; c < A; c++) off[c + 1] = off[c] + counts[c];
     }
     __syncthreads();
-    if (tid == 0)
-        for (int c = 1; c <= A; c++) counts[c] += counts[c - 1];
-    __syncthreads();
-    for (int e = tid; e <= A; e += blockDim.x) poly_off[e] = counts[e];
-    for (int i = warp; i < A; i += VC_WARPS) {                    // pass 2: vertices + area
-        const int n = vc_clip_cell(s_seeds, A, i, x0, x1, y0, y1, s_buf[warp], lane, overflow, which);
-        const double* px = s_buf[warp] + 128 * which;
-        const double* py = px + 64;
-        const int o = counts[i];
-        if (o + n > cap_vertices) overflow = true;
-        else
-            for (int v = lane; v < n; v += 32) { poly_xy[2 * (o + v)] = px[v]; poly_xy[2 * (o + v) + 1] = py[v]; }
-        if (lane == 0) {
-            // shoelace: 0.5 |x . roll(y,1) - y . roll(x,1)|, summed in vertex order
-            double s1 = 0.0, s2 = 0.0;
-            for (int v = 0; v < n; v++) {
-                const int u = (v + n - 1) % n;
-                s1 += px[v] * py[u];
-                s2 += py[v] * px[u];
-            }
-            areas[i] = overflow ? __longlong_as_double(0x7ff8000000000000LL) : 0.5 * fabs(s1 - s2);   // NaN poisons loss / centroid
-            if (overflow) atomicExch(flag, 1);
-        }
-        __syncwarp();
+    for (int e = tid; e <= A; e += blockDim.x) poly_off[e] = off[e];
+    if (off[A] > cap_vertices) {                                  // uniform
+        if (tid == 0) atomicExch(flag, 1);
+        for (int e = tid; e < A; e += blockDim.x) areas[e] = __longlong_as_double(0x7ff8000000000000LL);
+        return;
+    }
+    const int lane = tid & 31, warp = tid >> 5;
+    for (int c = warp; c < A; c += 8) {
+        const double* src = scratch + (int64_t)c * 2 * VC_MAXV;
+        double* dst = poly_xy + 2 * (int64_t)off[c];
+        const int n2 = 2 * (off[c + 1] - off[c]);
+        for (int e = lane; e < n2; e += 32) dst[e] = src[e];
     }
 }
 
@@ -1023,15 +1037,22 @@ __global__ void cov_finish_kernel(const double* __restrict__ cent, const double*
 }
 }  // namespace mfgp
 
+extern "C" int64_t cov_voronoi_clip_workspace_bytes(int64_t A) { return A * (2 * VC_MAXV * 8 + 4) + 256; }
+
 extern "C" int cov_voronoi_clip(const double* seeds, int64_t A, double xmin, double xmax, double ymin, double ymax, double eps,
                                 double* poly_xy, int32_t* poly_off, int64_t cap_vertices, double* areas, int32_t* flag,
-                                void* stream) {
+                                void* work, int64_t work_bytes, void* stream) {
     if (!seeds || A <= 0 || A > COV_MAX_CELLS || !poly_xy || !poly_off || !areas || !flag || cap_vertices < 4) return MFGP_ERR_INVALID;
+    if (!work || work_bytes < cov_voronoi_clip_workspace_bytes(A)) return MFGP_ERR_INVALID;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     MFGP_CUDA_CHECK(cudaMemsetAsync(flag, 0, sizeof(int32_t), st));
     const double h = 0.5 * eps;
-    cov_voronoi_clip_kernel<<<1, VC_WARPS * 32, 0, st>>>(seeds, (int)A, xmin - h, xmax + h, ymin - h, ymax + h, poly_xy, poly_off,
-                                               (int)cap_vertices, areas, flag);
+    double* scratch = static_cast<double*>(work);
+    int32_t* counts = reinterpret_cast<int32_t*>(scratch + A * 2 * VC_MAXV);
+    cov_voronoi_clip_kernel<<<(unsigned)((A + VC_WARPS - 1) / VC_WARPS), VC_WARPS * 32, 0, st>>>(seeds, (int)A, xmin - h, xmax + h, ymin - h,
+                                                                                         ymax + h, scratch, counts, areas, flag);
+    MFGP_LAUNCH_CHECK();
+    cov_voronoi_pack_kernel<<<1, 256, 0, st>>>(scratch, counts, (int)A, poly_xy, poly_off, (int)cap_vertices, areas, flag);
     MFGP_LAUNCH_CHECK();
     return MFGP_OK;
 }

@@ -465,6 +465,85 @@ __global__ void __launch_bounds__(128) qform_kernel(QformArgs a) {
     }
 }
 
+// step 6 on its own (Gram route: G'(ix) is already complete in global memory): one CTA per grid column, 256 threads, each
+// thread evaluates TWO grid points at a time (eight independent FMA chains), G' in shared memory (broadcast reads).
+//   var = k0 - uy^T G' uy,   mu = mean + h'(ix) . uy,   h'(ix)[l] = sum_k Ux(ix)[k] Hz[l][k]
+template <int WM, int NP>          // NP = 2: two points per thread (WM = 40), 1: one (WM = 64: the u vector alone takes 128 registers)
+__global__ void __launch_bounds__(256) geval_kernel(const double* __restrict__ G, const double* __restrict__ Hz, const double* __restrict__ Ux,
+                                                    int kpad, int ry, const double* __restrict__ Uy, int ny, double mean, double k0,
+                                                    double* __restrict__ mu, double* __restrict__ var, double* __restrict__ qred) {
+    constexpr int GP = WM + 2;
+    __shared__ __align__(16) double Gs[WM * GP];
+    __shared__ double hs[WM];
+    const int tid = threadIdx.x, col = blockIdx.x;
+    const double* g = G + (int64_t)col * F_LW * F_LW;
+    for (int e = tid; e < WM * WM; e += 256) {
+        const int r = e / WM, c = e % WM;
+        Gs[r * GP + c] = (r < ry && c < ry) ? g[r * F_LW + c] : 0.0;
+    }
+    if (tid < WM) {
+        double h = 0.0;
+        if (tid < ry) {
+            const double* ux = Ux + (int64_t)col * kpad;
+            const double* hz = Hz + (int64_t)tid * kpad;
+            for (int k = 0; k < kpad; k++) h = fma(ux[k], hz[k], h);
+        }
+        hs[tid] = h;
+    }
+    __syncthreads();
+    for (int iy0 = NP * tid; iy0 < ny; iy0 += NP * 256) {
+        double u[NP][WM];
+#pragma unroll
+        for (int p = 0; p < NP; p++) {
+            const double* up = Uy + (int64_t)min(iy0 + p, ny - 1) * F_LW;
+#pragma unroll
+            for (int l = 0; l < WM; l += 2) {
+                const double2 a = __ldg(reinterpret_cast<const double2*>(up + l));
+                u[p][l] = a.x; u[p][l + 1] = a.y;
+            }
+        }
+        double q[NP], m[NP];
+#pragma unroll
+        for (int p = 0; p < NP; p++) q[p] = m[p] = 0.0;
+#pragma unroll
+        for (int l = 0; l < WM; l += 2) {          // rows l, l+1 together: 16-byte loads of G; the same sums as gram_eval_kernel
+            const double* g0 = Gs + l * GP;
+            const double* g1 = g0 + GP;
+            double s0[NP], s1[NP];
+#pragma unroll
+            for (int p = 0; p < NP; p++) s0[p] = s1[p] = 0.0;
+#pragma unroll
+            for (int c = 0; c < l; c += 2) {
+                const double2 a0 = *reinterpret_cast<const double2*>(g0 + c);
+                const double2 a1 = *reinterpret_cast<const double2*>(g1 + c);
+#pragma unroll
+                for (int p = 0; p < NP; p++) {
+                    s0[p] = fma(a0.x, u[p][c], s0[p]); s0[p] = fma(a0.y, u[p][c + 1], s0[p]);
+                    s1[p] = fma(a1.x, u[p][c], s1[p]); s1[p] = fma(a1.y, u[p][c + 1], s1[p]);
+                }
+            }
+            const double2 d0 = *reinterpret_cast<const double2*>(g0 + l);
+            const double2 d1 = *reinterpret_cast<const double2*>(g1 + l);
+#pragma unroll
+            for (int p = 0; p < NP; p++) {
+                s1[p] = fma(d1.x, u[p][l], s1[p]);                              // G[l+1][l] is below the diagonal of row l+1
+                q[p] = fma(u[p][l], fma(2.0, s0[p], d0.x * u[p][l]), q[p]);
+                q[p] = fma(u[p][l + 1], fma(2.0, s1[p], d1.y * u[p][l + 1]), q[p]);
+                m[p] = fma(hs[l], u[p][l], m[p]);
+                m[p] = fma(hs[l + 1], u[p][l + 1], m[p]);
+            }
+        }
+#pragma unroll
+        for (int p = 0; p < NP; p++) {
+            if (iy0 + p >= ny) continue;
+            const int64_t gidx = (int64_t)col * ny + iy0 + p;
+            var[gidx] = k0 - q[p];
+            mu[gidx] = mean + m[p];
+            if (qred) qred[gidx] = q[p];
+        }
+    }
+}
+
 // rows / columns [ry, WM) of every G'(ix) must read as zero for gram_eval's padded quadratic form
 __global__ void gpad_zero_kernel(double* __restrict__ G, int ry, int wm, int col_begin) {
     double* g = G + (int64_t)(col_begin + blockIdx.x) * F_LW * F_LW;
@@ -726,26 +805,16 @@ int f_tail_gram(const FGeom& g, FLayout& L, const double* Yall, int64_t ldY, dou
         default: qform_kernel<8><<<qgrid, 128, 0, st>>>(qa); break;
     }
     MFGP_LAUNCH_CHECK();
-    if (f.ry < wm) {
+    // step 6 (and h'(ix)): G' comes from the buffer, nothing else to add
+    if (wm == 40)
+        geval_kernel<40, 2><<<(unsigned)g.ncols, 256, 0, st>>>(Gbuf, f.Hz, f.Ux, f.kpad, f.ry, L.Uy, (int)g.ny, dp.mean_H, dp.k0, mu, var, qred);
+    else
+        geval_kernel<64, 1><<<(unsigned)g.ncols, 256, 0, st>>>(Gbuf, f.Hz, f.Ux, f.kpad, f.ry, L.Uy, (int)g.ny, dp.mean_H, dp.k0, mu, var, qred);
+    MFGP_LAUNCH_CHECK();
+    if (Gstore && f.ry < wm) {        // the incremental update adds into the padded wm x wm block of the store: its padding must be finite
         gpad_zero_kernel<<<(unsigned)g.ncols, 128, 0, st>>>(Gbuf, f.ry, wm, 0);
         MFGP_LAUNCH_CHECK();
     }
-    // step 6 (and h'(ix)) by the evaluation half of gram_eval_kernel: no training rows to add, G' comes from the store
-    const int pitch = (f.ry % 8 == 4) ? f.ry : f.ry + 4;
-    const int nstage = 2;
-    const size_t gsmem = sizeof(double) * ((size_t)nstage * G_ROWS * pitch + 8 + wm * (wm + 2) + 2 * F_LW) + 8 * G_MAXSTAGE + 64;
-    MFGP_CUDA_CHECK(cudaFuncSetAttribute(gram_eval_kernel<40>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));
-    MFGP_CUDA_CHECK(cudaFuncSetAttribute(gram_eval_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));
-    GramArgs ga;
-    ga.YpL = nullptr; ga.YpH = f.Yp; ga.ryL = 0; ga.ryH = f.ry;
-    ga.npad = 0; ga.Uy = L.Uy; ga.ny = (int)g.ny; ga.col_begin = 0;
-    ga.Gstore = Gbuf; ga.accumulate = 1;
-    ga.HzL = nullptr; ga.HzH = f.Hz; ga.UxL = nullptr; ga.UxH = f.Ux; ga.kL = 0; ga.kH = f.kpad;
-    ga.mean = dp.mean_H; ga.k0 = dp.k0; ga.mu = mu; ga.var = var; ga.qred = qred;
-    ga.pitch = pitch; ga.nstage = nstage;
-    if (wm == 40) gram_eval_kernel<40><<<(unsigned)g.ncols, 128, gsmem, st>>>(ga);
-    else gram_eval_kernel<64><<<(unsigned)g.ncols, 128, gsmem, st>>>(ga);
-    MFGP_LAUNCH_CHECK();
     return MFGP_OK;
 }
 }  // namespace

@@ -181,232 +181,9 @@ __device__ __forceinline__ void potrf_diag_body(const double* src, int64_t lds, 
         }
 }
 
-// ---- the same sweep, software-pipelined ------------------------------------------------------------------------------
-// The sweep above is one serial chain per step (barrier -> pivot block -> reciprocal -> scaled columns -> FMA -> publish,
-// ~310 cycles of dependent latency) FOLLOWED by the bulk rank-2 update of the registers (~200 issue cycles on the shared
-// FP64 pipe): 820 cycles per step.  Only the two columns / rows of the NEXT pivot pair feed the chain, so here
-//   iteration k:  wait(k)  ->  chain(k): pivot block, P^-1, t(k) = U P^-1 for the thread's rows
-//                          ->  update k applied to the next pair's columns of S / rows of M only, published, arrive(k+1)
-//   and, in the same basic block with no barrier in between, the DEFERRED bulk update of step k-1 on all other
-//   registers (operands re-read from a 3-deep ring of published pairs), whose independent FMAs fill the chain's latency.
-// Arrival and wait are split (one mbarrier, 256 arrivals per phase), so a thread publishes, arrives and goes on with
-// work that does not depend on the others.  Same arithmetic per element as potrf_diag_body (the reciprocal of the 2x2
-// determinant is MUFU + two Newton steps instead of a division: no slow-path branch inside the scheduling region).
-struct PotrfScratch {
-    double2 col[3][PB];      // (.x, .y) = columns (j0, j1) of S as published for a step
-    double2 row[3][PB];      // rows (j0, j1) of M
-    double piv[3][PB / 2];
-    double fin[3][PB / 2];
-    unsigned long long bar;
-    int bad;
-};
-
-__device__ __forceinline__ double rcp_newton(double d) {
-    double x;
-    asm("rcp.approx.ftz.f64 %0, %1;\n" : "=d"(x) : "d"(d));
-    double e = fma(-d, x, 1.0);
-    x = fma(x, e, x);
-    e = fma(-d, x, 1.0);
-    return fma(x, e, x);
-}
-
-__device__ __forceinline__ void potrf_diag_pipe(const double* src, int64_t lds, double* A, int64_t ld,
-                                                double* __restrict__ Winv, int64_t ldw, int32_t* __restrict__ info, int jblk,
-                                                PotrfScratch* sc) {
-    const int tid = threadIdx.x;
-    const int ti = tid >> 4, tc = tid & 15;
-    const unsigned bar = static_cast<unsigned>(__cvta_generic_to_shared(&sc->bar));
-    if (tid == 0) {
-        sc->bad = 0;
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(256));
-    }
-    double s[4][4], m[4][4];
-#pragma unroll
-    for (int a = 0; a < 4; a++)
-#pragma unroll
-        for (int b = 0; b < 4; b++) {
-            const int r = ti + 16 * a, c = tc + 16 * b;
-            s[a][b] = (c <= r) ? src[(int64_t)r * lds + c] : 0.0;
-            m[a][b] = (r == c) ? 1.0 : 0.0;
-        }
-    __syncthreads();                      // barrier initialised; `src` may alias nothing the ring overwrites
-    // publish pair 0 into ring slot 0
-    if ((tc & 14) == 0) {
-        double* dst = reinterpret_cast<double*>(sc->col[0]) + (tc & 1);
-#pragma unroll
-        for (int a = 0; a < 4; a++) dst[2 * (ti + 16 * a)] = s[a][0];
-    }
-    if ((ti & 14) == 0) {
-        double* dst = reinterpret_cast<double*>(sc->row[0]) + (ti & 1);
-#pragma unroll
-        for (int b = 0; b < 4; b++) dst[2 * (tc + 16 * b)] = m[0][b];
-    }
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory");
-    double tp1[4] = {0.0, 0.0, 0.0, 0.0}, tp2[4] = {0.0, 0.0, 0.0, 0.0};      // t(k-1) of the thread's rows
-    int buf = 0;                          // ring slot of step k
-#pragma unroll
-    for (int jb = 0; jb < 4; jb++) {
-#pragma unroll 1
-        for (int jp = 0; jp < 8; jp++) {
-            const int k = jb * 8 + jp, j0 = 2 * k, j1 = j0 + 1, jj0 = 2 * jp;
-            const int nbuf = (buf == 2) ? 0 : buf + 1, pbuf = (buf == 0) ? 2 : buf - 1;
-            {       // wait for phase k: every thread has published pair k
-                unsigned done;
-                const unsigned par = k & 1;
-                do {
-                    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
-                                 : "=r"(done) : "r"(bar), "r"(par) : "memory");
-                } while (!done);
-            }
-            const double2* col = sc->col[buf];
-            const double2* row = sc->row[buf];
-            const double2* colp = sc->col[pbuf];
-            const double2* rowp = sc->row[pbuf];
-            // ---- chain(k): pivot block and its inverse ----
-            double pa = col[j0].x;
-            const double2 p1 = col[j1];
-            double pb = p1.x, pc = p1.y;
-            double det = fma(pa, pc, -(pb * pb));
-            if (!(pa > 0.0) || !(det > 0.0)) {          // uniform
-                if (tid == 0 && !sc->bad) {
-                    sc->bad = 1;
-                    atomicCAS(info, 0, jblk * PB + ((pa > 0.0) ? j1 : j0) + 1);
-                }
-                pa = 1.0; pb = 0.0; pc = 1.0; det = 1.0;
-            }
-            if (tid == 0) { sc->piv[0][k] = pa; sc->piv[1][k] = pb; sc->piv[2][k] = pc; }
-            const double idet = rcp_newton(det);
-            const double qa = pc * idet, qb = -pb * idet, qc = pa * idet;      // P^-1
-            double t1[4], t2[4];
-#pragma unroll
-            for (int a = 0; a < 4; a++) {
-                t1[a] = 0.0; t2[a] = 0.0;
-                if (a < jb) continue;                       // rows of earlier 16-groups are final
-                const double2 x = col[ti + 16 * a];
-                t1[a] = fma(qa, x.x, qb * x.y);
-                t2[a] = fma(qb, x.x, qc * x.y);
-            }
-            // ---- deferred bulk update of step k-1 (independent of chain(k): fills its latency) ----
-            // columns j0, j1 of S and rows j0, j1 of M took update k-1 early, before they were published
-            if (k > 0) {
-                const int j1p = j0 - 1;
-                const int jbp = (jp == 0) ? jb - 1 : jb;    // 16-group of pair k-1
-#pragma unroll
-                for (int b = 0; b < 4; b++) {
-                    if (b < jb - 1) continue;               // (static bound: jbp >= jb - 1)
-                    const double2 y = colp[tc + 16 * b];
-                    const bool early = (b == jb) && ((tc & 14) == jj0);
-                    const bool live = (b >= jbp) && (tc + 16 * b > j1p) && !early;
-#pragma unroll
-                    for (int a = 0; a < 4; a++) {
-                        if (a < b || a < jb - 1) continue;
-                        if (live && a >= jbp) s[a][b] = fma(-tp1[a], y.x, fma(-tp2[a], y.y, s[a][b]));
-                    }
-                }
-#pragma unroll
-                for (int b = 0; b < 4; b++) {
-                    if (b > jb) continue;                   // rows of pair k-1 are zero right of column j1p
-                    const double2 z = rowp[tc + 16 * b];
-                    const bool inb = b <= jbp;
-#pragma unroll
-                    for (int a = 0; a < 4; a++) {
-                        if (a < jb - 1) continue;
-                        const bool early = (a == jb) && ((ti & 14) == jj0);
-                        const bool live = inb && (a >= jbp) && (ti + 16 * a > j1p) && !early;
-                        if (live) m[a][b] = fma(-tp1[a], z.x, fma(-tp2[a], z.y, m[a][b]));
-                    }
-                }
-            }
-            // ---- update k on the NEXT pair's columns of S / rows of M, publish them, arrive ----
-            if (k < 31) {
-                const int jjn = (jj0 + 2) & 15;
-                if (jp < 7) {
-                    if ((tc & 14) == jjn) {
-                        const double2 y = col[tc + 16 * jb];
-                        double* dst = reinterpret_cast<double*>(sc->col[nbuf]) + (tc & 1);
-#pragma unroll
-                        for (int a = 0; a < 4; a++) {
-                            if (a < jb) continue;
-                            s[a][jb] = fma(-t1[a], y.x, fma(-t2[a], y.y, s[a][jb]));
-                            dst[2 * (ti + 16 * a)] = s[a][jb];
-                        }
-                    }
-                    if ((ti & 14) == jjn) {
-                        double* dst = reinterpret_cast<double*>(sc->row[nbuf]) + (ti & 1);
-#pragma unroll
-                        for (int b = 0; b < 4; b++) {
-                            if (b <= jb) {
-                                const double2 z = row[tc + 16 * b];
-                                m[jb][b] = fma(-t1[jb], z.x, fma(-t2[jb], z.y, m[jb][b]));
-                            }
-                            dst[2 * (tc + 16 * b)] = m[jb][b];
-                        }
-                    }
-                } else if (jb < 3) {      // the next pair opens the next 16-group
-                    if ((tc & 14) == 0) {
-                        const double2 y = col[tc + 16 * (jb + 1)];
-                        double* dst = reinterpret_cast<double*>(sc->col[nbuf]) + (tc & 1);
-#pragma unroll
-                        for (int a = 0; a < 4; a++) {
-                            if (a < jb + 1) continue;
-                            s[a][(jb + 1) & 3] = fma(-t1[a], y.x, fma(-t2[a], y.y, s[a][(jb + 1) & 3]));
-                            dst[2 * (ti + 16 * a)] = s[a][(jb + 1) & 3];
-                        }
-                    }
-                    if ((ti & 14) == 0) {
-                        double* dst = reinterpret_cast<double*>(sc->row[nbuf]) + (ti & 1);
-#pragma unroll
-                        for (int b = 0; b < 4; b++) {
-                            if (b <= jb) {
-                                const double2 z = row[tc + 16 * b];
-                                m[(jb + 1) & 3][b] = fma(-t1[(jb + 1) & 3], z.x, fma(-t2[(jb + 1) & 3], z.y, m[(jb + 1) & 3][b]));
-                            }
-                            dst[2 * (tc + 16 * b)] = m[(jb + 1) & 3][b];
-                        }
-                    }
-                }
-                asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory");
-            }
-#pragma unroll
-            for (int a = 0; a < 4; a++) { tp1[a] = t1[a]; tp2[a] = t2[a]; }
-            buf = nbuf;
-        }
-    }
-    // update 31 touches nothing (no column right of 63, no row below): the sweep is complete
-    __syncthreads();
-    if (tid < PB / 2) {          // C = chol(P) of every pair
-        const double a = sc->piv[0][tid], b = sc->piv[1][tid], c = sc->piv[2][tid];
-        const double r1 = rsqrt(a);
-        const double g = b * r1 * r1;
-        sc->fin[0][tid] = r1;
-        sc->fin[1][tid] = rsqrt(fma(-g, b, c));
-        sc->fin[2][tid] = g;
-    }
-    __syncthreads();
-    const bool failed = sc->bad != 0;
-#pragma unroll
-    for (int a = 0; a < 4; a++)
-#pragma unroll
-        for (int b = 0; b < 4; b++) {
-            const int r = ti + 16 * a, c = tc + 16 * b;
-            const double v = s[a][b], w = m[a][b];
-            const double vp = __shfl_up_sync(0xffffffffu, v, 1);       // same row, column c-1
-            const double wp = __shfl_up_sync(0xffffffffu, w, 16);      // row r-1, same column
-            const int kc = c >> 1, kr = r >> 1;
-            const double lv = (c & 1) ? (v - sc->fin[2][kc] * vp) * sc->fin[1][kc] : v * sc->fin[0][kc];
-            const double wv = (r & 1) ? (w - sc->fin[2][kr] * wp) * sc->fin[1][kr] : w * sc->fin[0][kr];
-            if (c <= r) A[(int64_t)r * ld + c] = failed ? ((r == c) ? 1.0 : 0.0) : lv;
-            if (Winv != nullptr) Winv[(int64_t)r * ldw + c] = failed ? ((r == c) ? 1.0 : 0.0) : ((c <= r) ? wv : 0.0);
-        }
-    __syncthreads();             // the scratch (and its barrier word) may be reused by the caller
-    if (tid == 0) asm volatile("mbarrier.inval.shared::cta.b64 [%0];\n" ::"r"(bar) : "memory");
-}
-
 __global__ void __launch_bounds__(256, 1) potrf_diag_kernel(double* __restrict__ A, int64_t ld, double* __restrict__ Winv,
-                                                         int64_t ldw, int32_t* __restrict__ info, int jblk, int pipelined) {
-    __shared__ __align__(16) PotrfScratch scratch;
-    if (pipelined) potrf_diag_pipe(A, ld, A, ld, Winv, ldw, info, jblk, &scratch);
-    else potrf_diag_body(A, ld, A, ld, Winv, ldw, info, jblk);
+                                                         int64_t ldw, int32_t* __restrict__ info, int jblk) {
+    potrf_diag_body(A, ld, A, ld, Winv, ldw, info, jblk);
 }
 
 // ---- tiled Cholesky + forward substitution as ONE persistent dataflow kernel -----------------------------------------
@@ -447,7 +224,6 @@ struct DfArgs {
     int total;
     long long spin_limit;
     long long* trace;   // diagnostics (MFGP_DF_TRACE=1): 8 timestamps per chain task, else nullptr
-    int potrf_pipe;     // 1: software-pipelined diagonal-block sweep (potrf_diag_pipe)
 };
 
 __device__ __forceinline__ void df_stamp(long long* trace, int task, int k) {
@@ -763,8 +539,7 @@ __global__ void __launch_bounds__(DF_THREADS, 2) chol_dataflow_kernel(DfArgs g) 
                 __syncthreads();
             }
             df_stamp(g.trace, idx, 4);
-            if (g.potrf_pipe) potrf_diag_pipe(Xs, DF_LDT, Cd, g.ld, Wd, g.ldw, g.info, idx, reinterpret_cast<PotrfScratch*>(Ws));
-            else potrf_diag_body(Xs, DF_LDT, Cd, g.ld, Wd, g.ldw, g.info, idx);
+            potrf_diag_body(Xs, DF_LDT, Cd, g.ld, Wd, g.ldw, g.info, idx);
             myflag = g.flagsL + (int64_t)idx * g.nb + idx;
             df_stamp(g.trace, idx, 5);
         }
@@ -772,396 +547,6 @@ __global__ void __launch_bounds__(DF_THREADS, 2) chol_dataflow_kernel(DfArgs g) 
         if (tid == 0) {
             df_st_release(myflag, 1);                 // cumulative: covers the tile stores of every thread before the barrier
             if (chain) df_st_relaxed(my_pause, 0);
-        }
-        if (chain) df_stamp(g.trace, idx, 6);
-    }
-}
-
-// ---- v2 scheduler: two queues ----------------------------------------------------------------------------------------------
-// The single ticket order above hands every free CTA the next task of the current block column, so in the first ~15 block
-// columns -- where a column offers less work than one hop of the serial chain takes -- nearly all CTAs sit on tasks that spin
-// on the chain's flags, and the right-hand-side work (half of all flops at c4) cannot fill those bubbles: a left-looking
-// Y tile of block row c only becomes available when the chain reaches c.  v2 separates the two kinds of work:
-//   CRITICAL queue  the factorisation proper, unchanged: chain tasks and left-looking L tiles in block-column order.  A task
-//                   of block column c is claimed only once the chain is within reach, done_col >= c - 1 - c / la_div (its k
-//                   loop is ~c tile products long, so it starts that much earlier), so few CTAs ever wait on the chain.
-//   BULK queue      all right-hand-side work in RIGHT-LOOKING, grouped form: as soon as the block rows of a group g (1, 1, 2,
-//                   2, 2, 4, 4, 4, 4, 8, 8, ... block rows) are solved -- YF(k, r): Y_kr = W_kk (B_kr - sum_{j in g, j < k}
-//                   L_kj Y_jr) -- every tile below takes its update YU(i, r, g): B_ir -= sum_{k in g} L_ik Y_kr.  That work
-//                   exists from the first block column on (63 x nr tile products after ONE hop) and depends on the chain only
-//                   through finished columns, so it fills whatever the critical queue leaves idle.
-// A free CTA takes the head of the critical queue if its gate is open, else the head of the bulk queue if that is ready, else
-// naps.  Both queues are FIFO with compare-and-swap claims, every task waits only on tasks that are earlier in its own queue
-// or (bulk) on critical tasks whose claim the readiness test has verified -- so whatever a running task waits for is running
-// or done, and the scheme cannot deadlock.  The updates of one tile are applied in group order (per-tile counter), so the
-// result is deterministic.
-__device__ __forceinline__ int df_group_of(int k) { return k < 2 ? k : (k < 8 ? 2 + ((k - 2) >> 1) : (k < 24 ? 5 + ((k - 8) >> 2) : 9 + ((k - 24) >> 3))); }
-__device__ __forceinline__ int df_group_start(int g) { return g < 2 ? g : (g < 5 ? 2 + 2 * (g - 2) : (g < 9 ? 8 + 4 * (g - 5) : 24 + 8 * (g - 9))); }
-
-struct DfArgs2 {
-    DfArgs a;
-    int* cntB;          // [nb][nr]: number of row groups whose update has been applied to tile (i, r) of the right-hand sides
-    int* done_col;      // number of diagonal blocks factored (W_dd published)
-    int* queues;        // [0] next critical task, [1] next bulk task
-    int ncrit, nbulk, ngroups, la_div;
-    int role;           // 1: serve the critical queue only, 2: the bulk queue only, 3: both
-};
-
-__global__ void __launch_bounds__(DF_THREADS, 2) chol_dataflow2_kernel(DfArgs2 h) {
-    extern __shared__ __align__(16) double df_smem[];
-    __shared__ int task[8];
-    __shared__ int ready_s[4];
-    const DfArgs& g = h.a;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int wm = (warp >> 1) * 8, wn = (warp & 1) * 8;
-    const int gq = lane >> 2, tq = lane & 3;
-    double* As0 = df_smem;
-    double* Bs0 = df_smem + 2 * DF_STAGE;
-    unsigned smid;
-    asm volatile("mov.u32 %0, %%smid;\n" : "=r"(smid));
-    int* my_pause = g.pause + smid;
-    const int nb = g.nb, nr = g.nr;
-    // state of thread 0: decode cursors (the tickets a CTA draws only ever grow), the frontier cursor of the critical queue,
-    // and at most ONE bulk ticket that was drawn before its task was ready
-    int cq_col = 0, cq_off = 1;          // critical: block column of the decode cursor, index of its first task (task 0 = chain 0)
-    int fr_col = 0, fr_off = 1;          // critical: tasks with an index below fr_off have an open gate
-    int bq_g = 0, bq_off = 0;            // bulk: group of the decode cursor, index of its first task
-    int deferred = -1;
-
-    for (;;) {
-        __syncthreads();                      // the previous task is done with shared memory and task[]
-        if (tid == 0) {
-            // Claims are plain atomic increments (every attempt succeeds: no compare-and-swap retries under contention).
-            // Critical queue: drawn while the head is inside the open gate (a few tickets may overshoot: they wait inside the
-            // task, like in the single-queue scheme).  Bulk queue: drawn unconditionally, one ticket at a time; a ticket whose
-            // task is not ready yet is KEPT while the CTA goes on serving the critical queue, and runs as soon as it is ready.
-            int kind = -1, ti = 0, tc = 0, tr = 0, kb = 0, ke = 0, tg = 0;
-            const long long t0 = clock64();
-            for (;;) {
-                const int dc = df_ld_relaxed(h.done_col);
-                int cn = df_ld_relaxed(h.queues);
-                while (fr_col <= nb - 2 && fr_col - 1 - fr_col / h.la_div <= dc) { fr_off += nb - 1 - fr_col; fr_col++; }
-                if ((h.role & 1) && cn < h.ncrit && cn < fr_off) {
-                    const int t = atomicAdd(h.queues, 1);
-                    if (t < h.ncrit) {
-                        if (t == 0) { kind = 2; ti = 0; tc = -1; kb = 0; ke = 0; break; }
-                        while (t >= cq_off + (nb - 1 - cq_col)) { cq_off += nb - 1 - cq_col; cq_col++; }
-                        const int col = cq_col, u = t - cq_off;        // 0: chain col + 1, then the tiles (col + 2 + ..., col)
-                        if (u == 0) { kind = 2; ti = col + 1; tc = col; kb = 0; ke = col; }
-                        else { kind = 0; ti = col + 1 + u; tc = col; kb = 0; ke = col; }
-                        break;
-                    }
-                    cn = h.ncrit;
-                }
-                int bn = h.nbulk;
-                if (deferred < 0 && (h.role & 2)) {
-                    bn = df_ld_relaxed(h.queues + 1);
-                    if (bn < h.nbulk) {
-                        const int t = atomicAdd(h.queues + 1, 1);
-                        if (t < h.nbulk) deferred = t;
-                    }
-                }
-                if (deferred >= 0) {
-                    for (;;) {                                          // locate the group of the ticket
-                        const int gs = df_group_start(bq_g);
-                        const int cnt = (nb - gs) * nr;
-                        if (deferred < bq_off + cnt) break;
-                        bq_off += cnt; bq_g++;
-                    }
-                    const int gs = df_group_start(bq_g), ge = min(df_group_start(bq_g + 1), nb);
-                    const int t = deferred - bq_off;
-                    const bool fin = t < (ge - gs) * nr;
-                    const int row = fin ? gs + t / nr : ge + (t - (ge - gs) * nr) / nr;
-                    const int r = t % nr;
-                    // ready: the diagonal blocks it reads are published AND every critical task of those columns is claimed
-                    const int need_col = fin ? row : ge - 1;
-                    const int c1 = need_col + 1;
-                    int crit_upto = 1 + c1 * (nb - 1) - c1 * (c1 - 1) / 2;      // index behind the critical tasks of columns <= need_col
-                    if (crit_upto > h.ncrit) crit_upto = h.ncrit;
-                    if (dc > need_col && cn >= crit_upto) {
-                        kind = fin ? 1 : 3; ti = row; tc = row; tr = r; kb = gs; ke = fin ? row : ge; tg = bq_g;
-                        deferred = -1;
-                        break;
-                    }
-                } else if ((!(h.role & 1) || cn >= h.ncrit) && bn >= h.nbulk) {
-                    break;                                              // the queues this CTA serves are exhausted, nothing is held
-                }
-                __nanosleep(64);
-                if (clock64() - t0 > g.spin_limit) { atomicExch(g.ctrl + 1, 1); atomicExch(g.info, -1); }
-                if (*reinterpret_cast<volatile int*>(g.ctrl + 1)) break;
-            }
-            task[0] = kind; task[1] = ti; task[2] = tc; task[3] = tr; task[4] = kb; task[5] = ke; task[6] = tg;
-        }
-        __syncthreads();
-        const int kind = task[0];
-        if (kind < 0) return;
-        const bool chain = kind == 2, ytype = kind == 1 || kind == 3, wmul = kind != 3;
-        const int i = task[1];                                   // block row of the A operand and of the output tile
-        const int c = task[2];                                   // block column whose W finishes the task (kinds 0, 1, 2)
-        const int r = task[3], kbeg = task[4], kend = task[5], grp = task[6];
-        const int idx = chain ? i : (ytype ? r : i);             // (chain: its diagonal block; kept for the trace hooks)
-        const int nk = kend - kbeg;
-        // operands of the k loop: A = L_i,k ([m][k]);  B = L_c,k ([n][k], transposed product) or Y_k,r ([k][n])
-        const double* Ag = g.K + (int64_t)i * PB * g.ld + (int64_t)kbeg * PB;
-        const double* Bg = ytype ? g.Bm + (int64_t)kbeg * PB * g.ldb + (int64_t)r * PB
-                                 : g.K + (int64_t)(c > 0 ? c : 0) * PB * g.ld + (int64_t)kbeg * PB;
-        const int* fa = g.flagsL + (int64_t)i * nb + kbeg;                                           // L_i,k ready
-        const int* fb = ytype ? g.flagsY + (int64_t)kbeg * nr + r : g.flagsL + (int64_t)(c > 0 ? c : 0) * nb + kbeg;
-        const int fbs = ytype ? nr : 1;
-        double* Ct = ytype ? g.Bm + (int64_t)i * PB * g.ldb + (int64_t)r * PB
-                           : g.K + (int64_t)i * PB * g.ld + (int64_t)(c > 0 ? c : 0) * PB;
-        const int64_t ldc = ytype ? g.ldb : g.ld;
-        double* Cd = g.K + (int64_t)(chain ? i : 0) * PB * (g.ld + 1);        // diagonal tile (i, i) of a chain task
-        const bool has_tile = !(chain && i == 0);
-        bool ok = true;
-        if (ytype) {       // the tile must have taken the updates of every earlier row group (in order: deterministic sums)
-            if (warp == 0) {
-                int okw = 1;
-                if (lane == 0) {
-                    const int* cp = h.cntB + (int64_t)i * nr + r;
-                    const long long t0 = clock64();
-                    while (df_ld_relaxed(cp) != grp) {
-                        __nanosleep(32);
-                        if (clock64() - t0 > g.spin_limit) { atomicExch(g.ctrl + 1, 1); atomicExch(g.info, -1); }
-                        if (*reinterpret_cast<volatile int*>(g.ctrl + 1)) { okw = 0; break; }
-                    }
-                    (void)df_ld_acquire(cp);
-                    ready_s[3] = okw;
-                }
-            }
-            __syncthreads();
-            ok = ready_s[3] != 0;
-        }
-        double acc[2][4][2], acc2[2][4][2];
-#pragma unroll
-        for (int x = 0; x < 2; x++)
-#pragma unroll
-            for (int y = 0; y < 4; y++) {
-                const int rr = wm + x * 32 + gq, cc = wn + y * 16 + tq * 2;
-                double2 v = make_double2(0.0, 0.0), d = make_double2(0.0, 0.0);
-                if (has_tile) v = __ldcg(reinterpret_cast<const double2*>(Ct + (int64_t)rr * ldc + cc));
-                if (chain) d = __ldcg(reinterpret_cast<const double2*>(Cd + (int64_t)rr * g.ld + cc));
-                acc[x][y][0] = -v.x; acc[x][y][1] = -v.y;
-                acc2[x][y][0] = -d.x; acc2[x][y][1] = -d.y;
-            }
-
-        auto stage = [&](int buf, int s) {
-            const int k0 = s * DF_K;
-            const int kt = s >> 1;
-            if ((s & 1) == 0) {                       // first slab of a 64-wide k tile: its producers must be done
-                const int ready = (s == 0) ? 0 : ready_s[kt & 1];
-                if (!ready) {
-                    if (warp == 0) {
-                        bool w = df_wait(fa + kt, g.ctrl, g.info, g.spin_limit);
-                        w = df_wait(fb + (int64_t)kt * fbs, g.ctrl, g.info, g.spin_limit) && w;
-                        if (lane == 0) ready_s[2] = w ? 1 : 0;
-                    }
-                    __syncthreads();
-                    ok = (ready_s[2] != 0) && ok;
-                }
-            } else if (tid == 0) {
-                ready_s[(kt + 1) & 1] = (kt + 1 < nk) ? (df_ld_acquire(fa + kt + 1) & df_ld_acquire(fb + (int64_t)(kt + 1) * fbs)) : 0;
-            }
-            double* As = As0 + buf * DF_STAGE;
-            double* Bs = Bs0 + buf * DF_STAGE;
-#pragma unroll
-            for (int e = tid; e < PB * (DF_K / 2); e += DF_THREADS) {     // 64 rows x 16 chunks of 16 bytes
-                const int rr = e >> 4, q = e & 15;
-                cp_async16(&As[rr * DF_LDA + q * 2], Ag + (int64_t)rr * g.ld + k0 + q * 2, true);
-            }
-            if (!ytype) {
-#pragma unroll
-                for (int e = tid; e < PB * (DF_K / 2); e += DF_THREADS) {
-                    const int rr = e >> 4, q = e & 15;
-                    cp_async16(&Bs[rr * DF_LDA + q * 2], Bg + (int64_t)rr * g.ld + k0 + q * 2, true);
-                }
-            } else {
-#pragma unroll
-                for (int e = tid; e < DF_K * (PB / 2); e += DF_THREADS) { // 32 rows x 32 chunks
-                    const int rr = e >> 5, q = e & 31;
-                    cp_async16(&Bs[rr * DF_LDT + q * 2], Bg + (int64_t)(k0 + rr) * g.ldb + q * 2, true);
-                }
-            }
-            cp_async_commit();
-        };
-
-        const int nslab = nk * (PB / DF_K);
-        if (nslab > 0) stage(0, 0);
-        int paused = 0;
-        for (int s = 0; s < nslab; s++) {
-            const int buf = s & 1;
-            if (s + 1 < nslab) {
-                stage(buf ^ 1, s + 1);
-                cp_async_wait<1>();
-            } else {
-                cp_async_wait<0>();
-            }
-            if (lane == 0) {                          // the SM's other CTA is in the tail of a chain task: stand back
-                while (paused && df_ld_relaxed(my_pause)) __nanosleep(200);
-                paused = df_ld_relaxed(my_pause);
-            }
-            if (__syncthreads_or(!ok)) return;        // abort raised: every thread of the CTA leaves together
-            const double* As = As0 + buf * DF_STAGE;
-            const double* Bs = Bs0 + buf * DF_STAGE;
-#pragma unroll
-            for (int kk = 0; kk < DF_K; kk += 4) {
-                double a[2], b[4];
-#pragma unroll
-                for (int x = 0; x < 2; x++) a[x] = As[(wm + x * 32 + gq) * DF_LDA + kk + tq];
-#pragma unroll
-                for (int y = 0; y < 4; y++)
-                    b[y] = ytype ? Bs[(kk + tq) * DF_LDT + wn + y * 16 + gq] : Bs[(wn + y * 16 + gq) * DF_LDA + kk + tq];
-#pragma unroll
-                for (int x = 0; x < 2; x++)
-#pragma unroll
-                    for (int y = 0; y < 4; y++) dmma884(acc[x][y][0], acc[x][y][1], a[x], b[y]);
-                if (chain) {                          // diagonal tile (i, i): L_ik L_ik^T out of the same A slab, lower tiles only
-#pragma unroll
-                    for (int y = 0; y < 4; y++) b[y] = As[(wn + y * 16 + gq) * DF_LDA + kk + tq];
-#pragma unroll
-                    for (int x = 0; x < 2; x++)
-#pragma unroll
-                        for (int y = 0; y < 4; y++)
-                            if (wn + y * 16 < wm + x * 32 + 8) dmma884(acc2[x][y][0], acc2[x][y][1], a[x], b[y]);
-                }
-            }
-            __syncthreads();
-        }
-        if (nslab == 0 && __syncthreads_or(!ok)) return;
-
-        // ---- epilogue ----
-        if (chain) df_stamp(g.trace, idx, 0);
-        double* Xs = df_smem;                 // [64][68]  X = C - acc   (later: the diagonal tile S)
-        double* Ws = df_smem + DF_TILE;       // [64][68]  W_cc
-        double* Ls = df_smem + 2 * DF_TILE;   // [64][68]  L_{i,c} of a chain task
-        if (!wmul) {                          // YU: the updated tile goes back as it is; the next group's update may follow
-#pragma unroll
-            for (int x = 0; x < 2; x++)
-#pragma unroll
-                for (int y = 0; y < 4; y++) {
-                    const int rr = wm + x * 32 + gq, cc = wn + y * 16 + tq * 2;
-                    double2 v;
-                    v.x = -acc[x][y][0]; v.y = -acc[x][y][1];
-                    *reinterpret_cast<double2*>(Ct + (int64_t)rr * ldc + cc) = v;
-                }
-            __syncthreads();
-            if (tid == 0) df_st_release(h.cntB + (int64_t)i * nr + r, grp + 1);
-            continue;
-        }
-        double* Wcc = g.W + (int64_t)(c > 0 ? c : 0) * PB * (g.ldw + 1);
-        int* myflag = ytype ? g.flagsY + (int64_t)c * nr + r : g.flagsL + (int64_t)i * nb + (c > 0 ? c : 0);
-        if (has_tile) {
-#pragma unroll
-            for (int x = 0; x < 2; x++)
-#pragma unroll
-                for (int y = 0; y < 4; y++) {
-                    const int rr = wm + x * 32 + gq, cc = wn + y * 16 + tq * 2;
-                    Xs[rr * DF_LDT + cc] = -acc[x][y][0];             // X = C - sum (the accumulator started at -C)
-                    Xs[rr * DF_LDT + cc + 1] = -acc[x][y][1];
-                    acc[x][y][0] = acc[x][y][1] = 0.0;
-                }
-            if (warp == 0) {
-                const bool w = df_wait(g.flagsL + (int64_t)c * nb + c, g.ctrl, g.info, g.spin_limit);
-                if (lane == 0) ready_s[3] = w ? 1 : 0;
-            }
-            __syncthreads();                          // X is in shared memory, W_cc is final (warp 0 acquired its flag)
-            const bool okd = ready_s[3] != 0;
-            if (chain && tid == 0) df_st_relaxed(my_pause, 1);
-            if (chain) df_stamp(g.trace, idx, 1);
-#pragma unroll
-            for (int e = tid; e < PB * (PB / 2); e += DF_THREADS) {
-                const int rr = e >> 5, q = e & 31;
-                cp_async16(&Ws[rr * DF_LDT + q * 2], Wcc + (int64_t)rr * g.ldw + q * 2, okd);
-            }
-            cp_async_commit();
-            cp_async_wait<0>();
-            if (__syncthreads_or(!okd)) {
-                if (chain && tid == 0) df_st_relaxed(my_pause, 0);
-                return;
-            }
-            if (chain) df_stamp(g.trace, idx, 2);
-#pragma unroll 4
-            for (int kk = 0; kk < PB; kk += 4) {
-                double a[2], b[4];
-                if (!ytype) {     // L_ic = X W_cc^T :  A = X [m][k],  B = W_cc [n][k] (lower triangular: k < n0 + 8)
-#pragma unroll
-                    for (int x = 0; x < 2; x++) a[x] = Xs[(wm + x * 32 + gq) * DF_LDT + kk + tq];
-#pragma unroll
-                    for (int y = 0; y < 4; y++) b[y] = (kk < wn + y * 16 + 8) ? Ws[(wn + y * 16 + gq) * DF_LDT + kk + tq] : 0.0;
-#pragma unroll
-                    for (int x = 0; x < 2; x++)
-#pragma unroll
-                        for (int y = 0; y < 4; y++)
-                            if (kk < wn + y * 16 + 8) dmma884(acc[x][y][0], acc[x][y][1], a[x], b[y]);
-                    continue;
-                } else {          // Y_cr = W_cc X :    A = W_cc [m][k],  B = X [k][n]
-#pragma unroll
-                    for (int x = 0; x < 2; x++) a[x] = Ws[(wm + x * 32 + gq) * DF_LDT + kk + tq];
-#pragma unroll
-                    for (int y = 0; y < 4; y++) b[y] = Xs[(kk + tq) * DF_LDT + wn + y * 16 + gq];
-                }
-#pragma unroll
-                for (int x = 0; x < 2; x++)
-#pragma unroll
-                    for (int y = 0; y < 4; y++) dmma884(acc[x][y][0], acc[x][y][1], a[x], b[y]);
-            }
-#pragma unroll
-            for (int x = 0; x < 2; x++)
-#pragma unroll
-                for (int y = 0; y < 4; y++) {
-                    const int rr = wm + x * 32 + gq, cc = wn + y * 16 + tq * 2;
-                    double2 v;
-                    v.x = acc[x][y][0]; v.y = acc[x][y][1];
-                    *reinterpret_cast<double2*>(Ct + (int64_t)rr * ldc + cc) = v;
-                    if (chain) { Ls[rr * DF_LDT + cc] = v.x; Ls[rr * DF_LDT + cc + 1] = v.y; }
-                }
-        }
-        if (chain) {
-            double* Wd = g.W + (int64_t)i * PB * (g.ldw + 1);
-            df_stamp(g.trace, idx, 3);
-            if (i > 0) {
-                __syncthreads();                      // L_{i,c} complete in shared memory; X is free
-#pragma unroll 4
-                for (int kk = 0; kk < PB; kk += 4) {  // acc2 += L_ic L_ic^T
-                    double a[2], b[4];
-#pragma unroll
-                    for (int x = 0; x < 2; x++) a[x] = Ls[(wm + x * 32 + gq) * DF_LDT + kk + tq];
-#pragma unroll
-                    for (int y = 0; y < 4; y++) b[y] = Ls[(wn + y * 16 + gq) * DF_LDT + kk + tq];
-#pragma unroll
-                    for (int x = 0; x < 2; x++)
-#pragma unroll
-                        for (int y = 0; y < 4; y++)
-                            if (wn + y * 16 < wm + x * 32 + 8) dmma884(acc2[x][y][0], acc2[x][y][1], a[x], b[y]);
-                }
-            }
-#pragma unroll
-            for (int x = 0; x < 2; x++)
-#pragma unroll
-                for (int y = 0; y < 4; y++) {
-                    const int rr = wm + x * 32 + gq, cc = wn + y * 16 + tq * 2;
-                    Xs[rr * DF_LDT + cc] = -acc2[x][y][0];             // S = A_dd - sum (acc2 started at -A_dd)
-                    Xs[rr * DF_LDT + cc + 1] = -acc2[x][y][1];
-                }
-            if (i > 0) {                              // publish the sub-diagonal tile before the long factor step
-                __syncthreads();                      // (release by one thread after the barrier covers the CTA's writes)
-                if (tid == 0) df_st_release(myflag, 1);
-            } else {
-                __syncthreads();
-            }
-            df_stamp(g.trace, idx, 4);
-            if (g.potrf_pipe) potrf_diag_pipe(Xs, DF_LDT, Cd, g.ld, Wd, g.ldw, g.info, i, reinterpret_cast<PotrfScratch*>(Ws));
-            else potrf_diag_body(Xs, DF_LDT, Cd, g.ld, Wd, g.ldw, g.info, i);
-            myflag = g.flagsL + (int64_t)i * nb + i;
-            df_stamp(g.trace, idx, 5);
-        }
-        __syncthreads();
-        if (tid == 0) {
-            df_st_release(myflag, 1);                 // cumulative: covers the tile stores of every thread before the barrier
-            if (chain) {
-                df_st_release(h.done_col, i + 1);
-                df_st_relaxed(my_pause, 0);
-            }
         }
         if (chain) df_stamp(g.trace, idx, 6);
     }
@@ -1208,7 +593,7 @@ extern "C" int64_t mfgp_npad(int64_t n) {
 // streams of one device, and nothing is allocated inside the library).
 static int64_t df_scratch_ints(int64_t npad, int64_t R) {
     const int64_t nb = npad / PB, nr = (R + PB - 1) / PB;
-    return 2 + 1024 + nb * nb + 2 * nb * nr + 4;       // ctrl, pause flags, L tile flags, Y tile flags + update counters, queue heads
+    return 2 + 1024 + nb * nb + nb * nr;               // ctrl, per-SM pause flags, L tile flags, Y tile flags
 }
 static int64_t df_scratch_bytes(int64_t npad, int64_t R) { return (df_scratch_ints(npad, R) * 4 + 255) / 256 * 256; }
 
@@ -1271,14 +656,6 @@ struct DfScratch {        // diagnostics (MFGP_DF_TRACE=1) and the cached SM cou
 };
 DfScratch g_df[16];
 
-int use_potrf_pipe() {        // MFGP_POTRF=pipe: the software-pipelined 64x64 sweep (measured SLOWER on B200: 30.1 k vs
-    static const int v = [] { //                  25.7 k cycles per block -- more LDS and predicate work than latency hidden)
-        const char* e = getenv("MFGP_POTRF");
-        return (e && std::strcmp(e, "pipe") == 0) ? 1 : 0;
-    }();
-    return v;
-}
-
 bool use_panel_chain() {
     static const int v = [] {
         const char* e = getenv("MFGP_CHOL");
@@ -1311,65 +688,13 @@ int chol_dataflow(double* K, int64_t npad, int64_t ld, double* W, int64_t ldw, i
         a.trace = nb <= 1024 ? sc.trace : nullptr;
         sc.trace_nb = nb;
     }
-    a.potrf_pipe = use_potrf_pipe();
     a.spin_limit = 4000000000LL;      // ~2 s of SM clocks: only a bug can get there
     constexpr int smem = DF_SMEM_DOUBLES * sizeof(double);
     static const int occ = [] { const char* e = getenv("MFGP_DF_OCC"); return e ? atoi(e) : 2; }();
-    // 1 (default): single ticket order; 2: two queues in one kernel; 3: two co-resident kernels.  Measured at c4 (N = 4096,
-    // 1344 right-hand sides): 2.40 / 2.52 / 2.46 ms -- see profiles/r02_chol_scheduler_experiments.txt
-    static const int sched = [] { const char* e = getenv("MFGP_DF_SCHED"); return e ? atoi(e) : 1; }();
-    static const int la_div = [] { const char* e = getenv("MFGP_DF_LA"); const int v = e ? atoi(e) : 4; return v < 1 ? 1 : v; }();
-    if (sched == 1) {
-        MFGP_CUDA_CHECK(cudaFuncSetAttribute(chol_dataflow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        int grid = (occ < 1 ? 1 : occ) * sc.sms;
-        if (grid > a.total) grid = a.total;
-        chol_dataflow_kernel<<<grid, DF_THREADS, smem, st>>>(a);
-        MFGP_LAUNCH_CHECK();
-        return MFGP_OK;
-    }
-    DfArgs2 h{};
-    h.a = a;
-    h.cntB = a.flagsY + (int64_t)nb * nr;
-    h.done_col = h.cntB + (int64_t)nb * nr;
-    h.queues = h.done_col + 1;
-    h.ncrit = 1 + nb * (nb - 1) / 2;
-    h.la_div = la_div;
-    {       // same grouping as df_group_start on the device: 1, 1, 2, 2, 2, 4, 4, 4, 4, 8, 8, ... block rows per group
-        auto gstart = [](int g) { return g < 2 ? g : (g < 5 ? 2 + 2 * (g - 2) : (g < 9 ? 8 + 4 * (g - 5) : 24 + 8 * (g - 9))); };
-        int ng = 0;
-        long long nbulk = 0;
-        while (gstart(ng) < nb) { nbulk += (long long)(nb - gstart(ng)) * nr; ng++; }
-        h.ngroups = ng;
-        h.nbulk = (int)nbulk;
-    }
-    MFGP_CUDA_CHECK(cudaFuncSetAttribute(chol_dataflow2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    if (sched == 3 && h.nbulk > 0) {
-        // Two co-resident persistent kernels, one CTA each per SM: the factorisation (critical queue, plain ticket order) and
-        // the right-hand-side work (bulk queue) on an internal stream.  The hardware interleaves them warp by warp: whenever
-        // the factorisation's CTA of an SM waits on the chain, the bulk CTA next to it has the tensor pipe to itself.  The
-        // bulk kernel only ever waits on the factorisation (flags in global memory), never the other way round, so the pair
-        // is correct whatever the placement -- even run back to back.
-        SideStream* side = nullptr;
-        int rcs = side_for_current_device(&side);
-        if (rcs) return rcs;
-        MFGP_CUDA_CHECK(cudaEventRecord(side->ev_begin, st));          // scratch zeroed, K and Bm produced on the caller's stream
-        MFGP_CUDA_CHECK(cudaStreamWaitEvent(side->st, side->ev_begin, 0));
-        DfArgs2 ha = h, hb = h;
-        ha.role = 1; ha.la_div = 1;                                   // gate always open: the single-queue ticket order
-        hb.role = 2;
-        int ga = sc.sms < ha.ncrit ? sc.sms : ha.ncrit, gb = sc.sms < hb.nbulk ? sc.sms : hb.nbulk;
-        chol_dataflow2_kernel<<<ga, DF_THREADS, smem, side->st>>>(ha);   // high-priority stream: placed first
-        MFGP_LAUNCH_CHECK();
-        chol_dataflow2_kernel<<<gb, DF_THREADS, smem, st>>>(hb);
-        MFGP_LAUNCH_CHECK();
-        MFGP_CUDA_CHECK(cudaEventRecord(side->ev_end, side->st));
-        MFGP_CUDA_CHECK(cudaStreamWaitEvent(st, side->ev_end, 0));
-        return MFGP_OK;
-    }
-    h.role = 3;
+    MFGP_CUDA_CHECK(cudaFuncSetAttribute(chol_dataflow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     int grid = (occ < 1 ? 1 : occ) * sc.sms;
-    if (grid > h.ncrit + h.nbulk) grid = h.ncrit + h.nbulk;
-    chol_dataflow2_kernel<<<grid, DF_THREADS, smem, st>>>(h);
+    if (grid > a.total) grid = a.total;
+    chol_dataflow_kernel<<<grid, DF_THREADS, smem, st>>>(a);
     MFGP_LAUNCH_CHECK();
     return MFGP_OK;
 }
@@ -1407,7 +732,7 @@ extern "C" int mfgp_cholesky(double* K, int64_t npad, int64_t ld, double* W, int
         double* Ajj = K + (int64_t)j * PB * (ld + 1);
         double* Wjj = W ? W + (int64_t)j * PB * (ldw + 1) : static_cast<double*>(work);
         const int64_t ldi = W ? ldw : PB;
-        potrf_diag_kernel<<<1, 256, POTRF_SMEM, st>>>(Ajj, ld, Wjj, ldi, info, j, use_potrf_pipe());
+        potrf_diag_kernel<<<1, 256, POTRF_SMEM, st>>>(Ajj, ld, Wjj, ldi, info, j);
         MFGP_LAUNCH_CHECK();
         const int rem = (int)(npad - (int64_t)(j + 1) * PB);
         if (rem <= 0) break;
@@ -1458,7 +783,7 @@ extern "C" int mfgp_cholesky_solve(double* K, int64_t npad, int64_t ld, double* 
     for (int j = 0; j < nb; j++) {
         double* Ajj = K + (int64_t)j * PB * (ld + 1);
         double* Wjj = W + (int64_t)j * PB * (ldw + 1);
-        potrf_diag_kernel<<<1, 256, POTRF_SMEM, st>>>(Ajj, ld, Wjj, ldw, info, j, use_potrf_pipe());
+        potrf_diag_kernel<<<1, 256, POTRF_SMEM, st>>>(Ajj, ld, Wjj, ldw, info, j);
         MFGP_LAUNCH_CHECK();
         MFGP_CUDA_CHECK(cudaEventRecord(side->ev_potrf[j & 1], st));
         const int rem = (int)(npad - (int64_t)(j + 1) * PB);
@@ -1611,7 +936,7 @@ extern "C" int mfgp_cholesky_append(const double* Xt, int64_t NL, int64_t NH_old
             splitk_reduce_kernel<<<dim3(1, PB), 64, 0, st>>>(part, nsplit, PB * PB, PB, Kbb, ld, PB, PB, -1.0, 1.0);        // S
             MFGP_LAUNCH_CHECK();
         }
-        potrf_diag_kernel<<<1, 256, POTRF_SMEM, st>>>(Kbb, ld, Wbb, ldw, info, (int)(rb / PB), use_potrf_pipe());
+        potrf_diag_kernel<<<1, 256, POTRF_SMEM, st>>>(Kbb, ld, Wbb, ldw, info, (int)(rb / PB));
         MFGP_LAUNCH_CHECK();
         if (rb > 0) {
             int nsplit = (int)(rb / 256);

@@ -107,3 +107,24 @@ def task_dependencies(task):
     for k in range(c):
         deps += [("Ltile", c, k), ("Ytile", k, r)]
     return deps
+
+
+def bordered_inverse_append(W, z, k_cols, k_nn, yc_new):
+    """The block-bordered update behind mfgp_batch_step (mfgp-coverage_b200/csrc/batched.cu, batch_append_kernel): q samples
+    are appended to a model whose factor is held as W = L^-1 (N x N, lower) and z = W (y - m).
+        K_new = [[K, k], [k^T, kk]],   l = W k,   S = kk - l^T l = C C^T,
+        L_new = [[L, 0], [l^T, C]],    W_new = [[W, 0], [-C^-1 l^T W, C^-1]],    z_new = [z ; W_new[N:, :] (y - m)].
+    k_cols[N, q]: covariance of the old points with the new ones, k_nn[q, q]: covariance among the new points including the
+    noise + jitter diagonal, yc_new[N + q]: ALL centred observations (old and new).  Returns (W_new, z_new).  The reference
+    refits from scratch (gaussian_process.py:266-268, :540-542); the leading block of the factor does not change."""
+    W = np.asarray(W, dtype=np.float64)
+    N, q = W.shape[0], k_nn.shape[0]
+    l = W @ k_cols                                   # N x q
+    C = np.linalg.cholesky(k_nn - l.T @ l)
+    Ci = np.linalg.inv(C)
+    Wn = np.zeros((N + q, N + q))
+    Wn[:N, :N] = W
+    Wn[N:, :N] = -Ci @ (l.T @ W)
+    Wn[N:, N:] = np.tril(Ci)
+    zn = np.concatenate((np.asarray(z, dtype=np.float64).reshape(-1), Wn[N:, :] @ np.asarray(yc_new, dtype=np.float64).reshape(-1)))
+    return Wn, zn

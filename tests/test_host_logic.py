@@ -275,3 +275,30 @@ def test_map_sims_shards_runs_and_propagates_worker_failures():
         runner._map_sims(list(range(7)), 3, fn=_sim_dies)
     with pytest.raises(ValueError, match="Invalid simulation algorithm"):  # the real run_sim, failing before any GPU call
         runner._map_sims([("o", "nonsense", 0, 1, 2, None, 0.1, None, None, False, None, False)] * 2, 2)
+
+
+def test_bordered_inverse_append_equals_a_refit():
+    """oracle.tiled_cholesky.bordered_inverse_append (the algorithm of the batched stepper's append kernel) against the
+    reference's refit-from-scratch: same W = L^-1 and z after every append, on an MF model that grows by 1..8 hifi samples."""
+    from oracle import tiled_cholesky as tc
+    xy = synth.grid(24)
+    f = synth.truth_function(xy)
+    X_L, y_L, X_H, y_H = synth.training_set(xy, f, 120)
+    p = ogp.GPParams.from_hyp(synth.MF_HYP)
+    n0 = 20
+    K = ogp.train_cov(p, X_L, X_H[:n0])
+    W = np.linalg.inv(np.linalg.cholesky(K))
+    yc = ogp.centered_y(p, y_L, y_H[:n0]).reshape(-1)
+    z = W @ yc
+    nh = n0
+    for q in (1, 8, 3, 8, 5):
+        Kfull = ogp.train_cov(p, X_L, X_H[:nh + q])
+        N = K.shape[0]
+        ycn = ogp.centered_y(p, y_L, y_H[:nh + q]).reshape(-1)
+        W, z = tc.bordered_inverse_append(W, z, Kfull[:N, N:], Kfull[N:, N:], ycn)
+        Lref = np.linalg.cholesky(Kfull)
+        Wref = np.linalg.inv(Lref)
+        assert np.max(np.abs(W - Wref)) <= 1e-11 * np.max(np.abs(Wref))
+        assert np.max(np.abs(z - Wref @ ycn)) <= 1e-11 * max(1.0, np.max(np.abs(z)))
+        assert np.allclose(np.triu(W, 1), 0.0)
+        K, nh = Kfull, nh + q
