@@ -71,12 +71,21 @@ __global__ void build_train_cov_kernel(const double* __restrict__ Xt, int NL, in
 constexpr int PB = 64;
 constexpr int PLD = PB + 1;
 
+struct PotrfScratch {
+    double2 colAB[2][PB], rowAB[2][PB];   // (.x, .y) = (column j0, column j1) of S / (row j0, row j1) of M
+    double piv[3][PB / 2];                // a, b, c of every pivot block
+    double fin[3][PB / 2];                // 1/sqrt(a), 1/sqrt(c - b^2/a), b/a
+    int bad;
+};
+
 __device__ __forceinline__ void potrf_diag_body(const double* src, int64_t lds, double* A, int64_t ld,
-                                                double* __restrict__ Winv, int64_t ldw, int32_t* __restrict__ info, int jblk) {
-    __shared__ double2 colAB[2][PB], rowAB[2][PB];     // (.x, .y) = (column j0, column j1) of S / (row j0, row j1) of M
-    __shared__ double piv[3][PB / 2];     // a, b, c of every pivot block
-    __shared__ double fin[3][PB / 2];     // 1/sqrt(a), 1/sqrt(c - b^2/a), b/a
-    __shared__ int bad;
+                                                double* __restrict__ Winv, int64_t ldw, int32_t* __restrict__ info, int jblk,
+                                                PotrfScratch* sc) {
+    double2 (*colAB)[PB] = sc->colAB;
+    double2 (*rowAB)[PB] = sc->rowAB;
+    double (*piv)[PB / 2] = sc->piv;
+    double (*fin)[PB / 2] = sc->fin;
+    int& bad = sc->bad;
     const int tid = threadIdx.x;
     const int ti = tid >> 4, tc = tid & 15;
     if (tid == 0) bad = 0;
@@ -183,7 +192,8 @@ __device__ __forceinline__ void potrf_diag_body(const double* src, int64_t lds, 
 
 __global__ void __launch_bounds__(256, 1) potrf_diag_kernel(double* __restrict__ A, int64_t ld, double* __restrict__ Winv,
                                                          int64_t ldw, int32_t* __restrict__ info, int jblk) {
-    potrf_diag_body(A, ld, A, ld, Winv, ldw, info, jblk);
+    __shared__ __align__(16) PotrfScratch scratch;
+    potrf_diag_body(A, ld, A, ld, Winv, ldw, info, jblk, &scratch);
 }
 
 // ---- tiled Cholesky + forward substitution as ONE persistent dataflow kernel -----------------------------------------
@@ -208,7 +218,8 @@ constexpr int DF_LDA = DF_K + 4;         // [m][k] / [n][k] slabs: rows land on 
 constexpr int DF_LDT = PB + 4;           // [k][n] slabs and the 64x64 epilogue tiles
 constexpr int DF_STAGE = PB * DF_LDA;    // doubles per operand per stage (64 x 36 = 2304 >= 32 x 68 = 2176)
 constexpr int DF_TILE = PB * DF_LDT;     // one padded 64x64 tile
-constexpr int DF_SMEM_DOUBLES = 3 * DF_TILE;      // epilogue: X, W, L tiles (13056) >= 2 stages x (A, B) = 9216
+constexpr int DF_NSTAGE = 3;             // slabs in flight: one slab of compute (~0.5 us) does not cover an L2 round trip under load
+constexpr int DF_SMEM_DOUBLES = DF_NSTAGE * 2 * DF_STAGE;     // 3 stages x (A, B) = 13824 doubles >= epilogue X, W, L tiles (13056)
 constexpr int DF_THREADS = 256;
 
 struct DfArgs {
@@ -224,6 +235,7 @@ struct DfArgs {
     int total;
     long long spin_limit;
     long long* trace;   // diagnostics (MFGP_DF_TRACE=1): 8 timestamps per chain task, else nullptr
+    int chain_la;       // chain task d draws its ticket d / chain_la block columns early (0: with its own column)
 };
 
 __device__ __forceinline__ void df_stamp(long long* trace, int task, int k) {
@@ -282,7 +294,7 @@ __global__ void __launch_bounds__(DF_THREADS, 2) chol_dataflow_kernel(DfArgs g) 
     const int wm = (warp >> 1) * 8, wn = (warp & 1) * 8;
     const int gq = lane >> 2, tq = lane & 3;
     double* As0 = df_smem;
-    double* Bs0 = df_smem + 2 * DF_STAGE;
+    double* Bs0 = df_smem + DF_NSTAGE * DF_STAGE;
     unsigned smid;
     asm volatile("mov.u32 %0, %%smid;\n" : "=r"(smid));
     int* my_pause = g.pause + smid;
@@ -295,18 +307,31 @@ __global__ void __launch_bounds__(DF_THREADS, 2) chol_dataflow_kernel(DfArgs g) 
             if (t == 0) {
                 kind = 2; idx = 0;            // chain task 0: the first diagonal block
             } else if (t < g.total) {
+                // Ticket order: per block column c -- the chain tasks PLACED there, the tiles (i, c) below the sub-diagonal, the
+                // Y tiles of block row c.  Chain task d (k loop of d - 1 tile pairs: the longest task of its column) is placed
+                // d / chain_la columns AHEAD of column d - 1, so that its accumulation is done by the time W_{d-1} arrives; it
+                // then waits on a few tiles with later tickets, which the other CTAs go on drawing (at most nb / chain_la + 1
+                // CTAs can ever be in that state).  Measured at N = 4096 with 1344 right-hand sides: 2.47 -> 2.12 ms.  Pulling
+                // the near-diagonal tiles forward as well made it slower (2.14 .. 2.41 ms): they crowd out the bulk.
                 t -= 1;
+                int dnext = 1;                // next chain task not placed yet
                 for (;;) {
-                    const int nchain = (c + 1 < g.nb) ? 1 : 0;
+                    int nchain = 0;
+                    while (dnext + nchain < g.nb) {
+                        const int d = dnext + nchain;
+                        const int place = max(0, d - 1 - (g.chain_la > 0 ? d / g.chain_la : 0));
+                        if (place != c) break;
+                        nchain++;
+                    }
                     const int ntile = g.nb - c - 2 > 0 ? g.nb - c - 2 : 0;
                     const int n = nchain + ntile + g.nr;
                     if (t < n) {
-                        if (t < nchain) { kind = 2; idx = c + 1; }
+                        if (t < nchain) { kind = 2; idx = dnext + t; }
                         else if (t < nchain + ntile) { kind = 0; idx = c + 2 + (t - nchain); }
                         else { kind = 1; idx = t - nchain - ntile; }
                         break;
                     }
-                    t -= n; c++;
+                    t -= n; c++; dnext += nchain;
                 }
             }
             task[0] = kind; task[1] = c; task[2] = idx;
@@ -347,27 +372,14 @@ __global__ void __launch_bounds__(DF_THREADS, 2) chol_dataflow_kernel(DfArgs g) 
             }
 
         bool ok = true;
-        // Readiness of a k tile's two operand tiles: ONE thread samples the flags for the whole CTA (acquire loads cost an
-        // L1 invalidation each), one slab early, and hands the verdict over through shared memory across the slab barriers.
-        auto stage = [&](int buf, int s) {
+        // k loop: DF_NSTAGE slabs in flight.  A slab that opens a new k tile may only be staged once both operand tiles are
+        // flagged ready; ONE thread samples those flags for the CTA every iteration (relaxed load, then one acquire when it
+        // sees them set) and hands the verdict over through shared memory across the slab barriers.  If the next tile is not
+        // ready, the slabs already in flight are computed first; the CTA only waits when nothing is left to compute.
+        auto issue = [&](int s) {
             const int k0 = s * DF_K;
-            const int kt = s >> 1;
-            if ((s & 1) == 0) {                       // first slab of a 64-wide k tile: its producers must be done
-                const int ready = (s == 0) ? 0 : ready_s[kt & 1];      // uniform; written before the last slab barrier
-                if (!ready) {
-                    if (warp == 0) {
-                        bool w = df_wait(fa + kt, g.ctrl, g.info, g.spin_limit);
-                        w = df_wait(fb + (int64_t)kt * fbs, g.ctrl, g.info, g.spin_limit) && w;
-                        if (lane == 0) ready_s[2] = w ? 1 : 0;
-                    }
-                    __syncthreads();                  // also orders warp 0's acquire before everybody's tile loads
-                    ok = (ready_s[2] != 0) && ok;
-                }
-            } else if (tid == 0) {
-                ready_s[(kt + 1) & 1] = (kt + 1 < nk) ? (df_ld_acquire(fa + kt + 1) & df_ld_acquire(fb + (int64_t)(kt + 1) * fbs)) : 0;
-            }
-            double* As = As0 + buf * DF_STAGE;
-            double* Bs = Bs0 + buf * DF_STAGE;
+            double* As = As0 + (s % DF_NSTAGE) * DF_STAGE;
+            double* Bs = Bs0 + (s % DF_NSTAGE) * DF_STAGE;
 #pragma unroll
             for (int e = tid; e < PB * (DF_K / 2); e += DF_THREADS) {     // 64 rows x 16 chunks of 16 bytes
                 const int r = e >> 4, q = e & 15;
@@ -388,25 +400,45 @@ __global__ void __launch_bounds__(DF_THREADS, 2) chol_dataflow_kernel(DfArgs g) 
             }
             cp_async_commit();
         };
-
+        auto sample = [&](int kt) -> int {            // both operand tiles of k tile kt flagged?  (thread 0 only)
+            if (kt >= nk) return 0;
+            if (!(df_ld_relaxed(fa + kt) & df_ld_relaxed(fb + (int64_t)kt * fbs))) return 0;
+            return df_ld_acquire(fa + kt) & df_ld_acquire(fb + (int64_t)kt * fbs);
+        };
         const int nslab = nk * (PB / DF_K);
-        if (nslab > 0) stage(0, 0);
+        int staged = 0, ready_kt = -1;                // tiles 0 .. ready_kt are known to be ready (uniform)
         int paused = 0;
+        if (tid == 0) ready_s[3] = sample(0) ? 0 : -1;
+        __syncthreads();
+        ready_kt = ready_s[3];
         for (int s = 0; s < nslab; s++) {
-            const int buf = s & 1;
-            if (s + 1 < nslab) {
-                stage(buf ^ 1, s + 1);
-                cp_async_wait<1>();
-            } else {
-                cp_async_wait<0>();
+            // stage ahead
+            while (staged < nslab && staged < s + DF_NSTAGE) {
+                const int kt = staged >> 1;
+                if (kt > ready_kt) {
+                    if (staged > s) break;            // something is in flight: compute it first, look again afterwards
+                    if (warp == 0) {                  // nothing to compute: wait for the tile
+                        bool w = df_wait(fa + kt, g.ctrl, g.info, g.spin_limit);
+                        w = df_wait(fb + (int64_t)kt * fbs, g.ctrl, g.info, g.spin_limit) && w;
+                        if (lane == 0) ready_s[2] = w ? 1 : 0;
+                    }
+                    __syncthreads();                  // also orders warp 0's acquire before everybody's tile loads
+                    ok = (ready_s[2] != 0) && ok;
+                    ready_kt = kt;
+                }
+                issue(staged);
+                staged++;
             }
+            const int inflight = staged - s - 1;      // groups that may stay pending while slab s is consumed
+            if (inflight >= 2) cp_async_wait<2>(); else if (inflight == 1) cp_async_wait<1>(); else cp_async_wait<0>();
             if (lane == 0) {                          // the SM's other CTA is in the tail of a chain task: stand back
                 while (paused && df_ld_relaxed(my_pause)) __nanosleep(200);
                 paused = df_ld_relaxed(my_pause);     // (sampled one slab ahead: the load is off the critical path)
             }
+            if (tid == 0) ready_s[s & 1] = sample(ready_kt + 1) ? ready_kt + 1 : ready_kt;
             if (__syncthreads_or(!ok)) return;        // abort raised: every thread of the CTA leaves together
-            const double* As = As0 + buf * DF_STAGE;
-            const double* Bs = Bs0 + buf * DF_STAGE;
+            const double* As = As0 + (s % DF_NSTAGE) * DF_STAGE;
+            const double* Bs = Bs0 + (s % DF_NSTAGE) * DF_STAGE;
 #pragma unroll
             for (int kk = 0; kk < DF_K; kk += 4) {
                 double a[2], b[4];
@@ -430,6 +462,7 @@ __global__ void __launch_bounds__(DF_THREADS, 2) chol_dataflow_kernel(DfArgs g) 
                 }
             }
             __syncthreads();
+            ready_kt = ready_s[s & 1];
         }
 
         // ---- epilogue ----
@@ -451,10 +484,10 @@ __global__ void __launch_bounds__(DF_THREADS, 2) chol_dataflow_kernel(DfArgs g) 
                 }
             if (warp == 0) {
                 const bool w = df_wait(g.flagsL + (int64_t)c * g.nb + c, g.ctrl, g.info, g.spin_limit);
-                if (lane == 0) ready_s[3] = w ? 1 : 0;
+                if (lane == 0) ready_s[2] = w ? 1 : 0;
             }
             __syncthreads();                          // X is in shared memory, W_cc is final (warp 0 acquired its flag)
-            const bool okd = ready_s[3] != 0;
+            const bool okd = ready_s[2] != 0;
             if (chain && tid == 0) df_st_relaxed(my_pause, 1);
             if (chain) df_stamp(g.trace, idx, 1);
 #pragma unroll
@@ -539,7 +572,7 @@ __global__ void __launch_bounds__(DF_THREADS, 2) chol_dataflow_kernel(DfArgs g) 
                 __syncthreads();
             }
             df_stamp(g.trace, idx, 4);
-            potrf_diag_body(Xs, DF_LDT, Cd, g.ld, Wd, g.ldw, g.info, idx);
+            potrf_diag_body(Xs, DF_LDT, Cd, g.ld, Wd, g.ldw, g.info, idx, reinterpret_cast<PotrfScratch*>(Ws));      // W_cc is spent
             myflag = g.flagsL + (int64_t)idx * g.nb + idx;
             df_stamp(g.trace, idx, 5);
         }
@@ -688,6 +721,8 @@ int chol_dataflow(double* K, int64_t npad, int64_t ld, double* W, int64_t ldw, i
         a.trace = nb <= 1024 ? sc.trace : nullptr;
         sc.trace_nb = nb;
     }
+    static const int chain_la = [] { const char* e = getenv("MFGP_DF_CHAIN_LA"); return e ? atoi(e) : 5; }();
+    a.chain_la = chain_la;
     a.spin_limit = 4000000000LL;      // ~2 s of SM clocks: only a bug can get there
     constexpr int smem = DF_SMEM_DOUBLES * sizeof(double);
     static const int occ = [] { const char* e = getenv("MFGP_DF_OCC"); return e ? atoi(e) : 2; }();

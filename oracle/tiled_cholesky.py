@@ -63,16 +63,40 @@ def pair_step_factor(S):
 # Task kinds (chol_dataflow_kernel): ("chain", d): sub-diagonal tile (d, d-1) + diagonal tile (d, d) + factor/inverse of block d;
 # ("L", i, c): tile (i, c) of L, i >= c + 2;  ("Y", c, r): tile (c, r) of Y = L^-1 B.
 
-def task_order(nb, nr):
-    """Tasks in ticket order: chain 0; then per block column c: chain c+1, the tiles (i, c) with i >= c+2, the Y tiles of
-    block row c."""
+def chain_place(d, chain_la=5):
+    """Block column whose ticket batch holds chain task d >= 1: d // chain_la columns ahead of column d - 1 (its k loop is
+    the longest of the column, so it starts early and is done accumulating when W_{d-1} arrives)."""
+    return max(0, d - 1 - (d // chain_la if chain_la > 0 else 0))
+
+
+def task_order(nb, nr, chain_la=5):
+    """Tasks in ticket order: chain 0; then per block column c: the chain tasks placed there (chain_place), the tiles (i, c)
+    with i >= c+2, the Y tiles of block row c.  chain_la = 0: chain c+1 sits in column c's batch (every task then depends on
+    smaller tickets only)."""
     order = [("chain", 0)]
+    dnext = 1
     for c in range(nb):
-        if c + 1 < nb:
-            order.append(("chain", c + 1))
+        while dnext < nb and chain_place(dnext, chain_la) == c:
+            order.append(("chain", dnext))
+            dnext += 1
         order += [("L", i, c) for i in range(c + 2, nb)]
         order += [("Y", c, r) for r in range(nr)]
     return order
+
+
+def early_tasks(nb, nr, chain_la=5):
+    """Tasks that wait on a LATER ticket (possible only for chain tasks drawn early) and, per such task, how many tickets
+    lie between it and the last ticket it depends on.  Progress argument: tasks that are not early depend on smaller tickets
+    only; a CTA holds a ticket only while resident; so as long as fewer CTAs can hold early tasks than the grid has, some
+    resident CTA always holds the smallest unfinished non-early ticket, whose dependencies are finished or running."""
+    order = task_order(nb, nr, chain_la)
+    pos = {t: k for k, t in enumerate(order)}
+    out = {}
+    for t in order:
+        last = max((pos[producer_of(d)] for d in task_dependencies(t)), default=-1)
+        if last > pos[t]:
+            out[t] = last - pos[t]
+    return out
 
 
 def producer_of(tile):

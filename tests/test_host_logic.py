@@ -164,6 +164,47 @@ def test_cross_rank_argmax_merge_applies_the_kernels_tie_rule():
         assert bi[a] == (idxs[live, a].min() if live.any() else -1)                    # all within tolerance: lowest index
 
 
+def test_dataflow_ticket_order_with_chain_lookahead_cannot_deadlock():
+    """The order the kernel uses (chain task d drawn d // 5 block columns early): the same tasks, each once; ONLY chain
+    tasks wait on later tickets; and however the resident CTAs are scheduled, at most nb // 5 + 2 of them can hold such a
+    task at one time -- every other resident CTA holds a task whose dependencies have smaller tickets, so the smallest
+    unfinished ticket among those always makes progress.  Simulated: tickets drawn in order by a small pool of CTAs, a task
+    completes when its dependencies have; the run must finish with as few CTAs as (early bound + 1)."""
+    from oracle import tiled_cholesky as tc
+    for nb, nr in ((1, 0), (2, 1), (7, 2), (20, 3), (64, 2)):
+        base = tc.task_order(nb, nr, chain_la=0)
+        order = tc.task_order(nb, nr)
+        assert sorted(map(str, order)) == sorted(map(str, base))
+        early = tc.early_tasks(nb, nr)
+        assert all(t[0] == "chain" for t in early)
+        bound = nb // 5 + 2
+        # worst case over time of chain tasks that are drawn but cannot have finished: chain d is early from its ticket to the
+        # ticket of its last dependency
+        pos = {t: k for k, t in enumerate(order)}
+        live = [0] * (len(order) + 1)
+        for t, span in early.items():
+            for k in range(pos[t], pos[t] + span):
+                live[k] += 1
+        assert max(live, default=0) <= bound, (nb, nr, max(live))
+        # event simulation with a pool of `bound + 1` CTAs
+        ncta = bound + 1
+        deps = {t: [tc.producer_of(d) for d in tc.task_dependencies(t)] for t in order}
+        done, running, nxt = set(), [], 0
+        for _ in range(10 * len(order) + 10):
+            while len(running) < ncta and nxt < len(order):
+                running.append(order[nxt])
+                nxt += 1
+            finished = [t for t in running if all(d in done for d in deps[t])]
+            if not finished and not running:
+                break
+            assert finished, (nb, nr, "deadlock with", ncta, "CTAs", running[:4])
+            done.update(finished)
+            running = [t for t in running if t not in done]
+            if len(done) == len(order):
+                break
+        assert len(done) == len(order)
+
+
 def test_vectorised_finishing_is_bitwise_the_reference_loop():
     """loss_from_partials / centroids_from_partials are elementwise over the cells; they must give bit for bit what the
     reference's per-cell statements give (simulator.py:215-219, :256-271), empty cells (0/0 -> NaN) included."""
@@ -225,7 +266,7 @@ def test_dataflow_ticket_order_is_topological():
     from oracle import tiled_cholesky as tc
     for nb in range(1, 21):
         for nr in (0, 1, 3):
-            order = tc.task_order(nb, nr)
+            order = tc.task_order(nb, nr, chain_la=0)     # chain tasks with their own column: strictly topological
             assert len(order) == len(set(order)) == nb + (nb - 1) * (nb - 2) // 2 + nb * nr       # a.total in gp_fit.cu
             ticket = {t: k for k, t in enumerate(order)}
             produced = set()
