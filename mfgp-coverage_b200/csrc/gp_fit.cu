@@ -405,6 +405,10 @@ __global__ void __launch_bounds__(DF_THREADS, 2) chol_dataflow_kernel(DfArgs g) 
             if (!(df_ld_relaxed(fa + kt) & df_ld_relaxed(fb + (int64_t)kt * fbs))) return 0;
             return df_ld_acquire(fa + kt) & df_ld_acquire(fb + (int64_t)kt * fbs);
         };
+        // the same in two halves: the relaxed loads are ISSUED before a slab's DMMA loop and consumed after it, so their L2
+        // round trip never sits between the CTA and its barrier; only a tile newly seen ready costs the acquire
+        auto peek = [&](int kt) -> int { return kt < nk ? (df_ld_relaxed(fa + kt) & df_ld_relaxed(fb + (int64_t)kt * fbs)) : 0; };
+        auto confirm = [&](int kt) -> int { return df_ld_acquire(fa + kt) & df_ld_acquire(fb + (int64_t)kt * fbs); };
         const int nslab = nk * (PB / DF_K);
         int staged = 0, ready_kt = -1;                // tiles 0 .. ready_kt are known to be ready (uniform)
         int paused = 0;
@@ -435,7 +439,7 @@ __global__ void __launch_bounds__(DF_THREADS, 2) chol_dataflow_kernel(DfArgs g) 
                 while (paused && df_ld_relaxed(my_pause)) __nanosleep(200);
                 paused = df_ld_relaxed(my_pause);     // (sampled one slab ahead: the load is off the critical path)
             }
-            if (tid == 0) ready_s[s & 1] = sample(ready_kt + 1) ? ready_kt + 1 : ready_kt;
+            const int seen = (tid == 0) ? peek(ready_kt + 1) : 0;
             if (__syncthreads_or(!ok)) return;        // abort raised: every thread of the CTA leaves together
             const double* As = As0 + (s % DF_NSTAGE) * DF_STAGE;
             const double* Bs = Bs0 + (s % DF_NSTAGE) * DF_STAGE;
@@ -461,6 +465,7 @@ __global__ void __launch_bounds__(DF_THREADS, 2) chol_dataflow_kernel(DfArgs g) 
                             if (wn + y * 16 < wm + x * 32 + 8) dmma884(acc2[x][y][0], acc2[x][y][1], a[x], b[y]);
                 }
             }
+            if (tid == 0) ready_s[s & 1] = (seen && confirm(ready_kt + 1)) ? ready_kt + 1 : ready_kt;
             __syncthreads();
             ready_kt = ready_s[s & 1];
         }

@@ -20,7 +20,7 @@ for k in want:
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(src)))
 hh = rows[1]
-body = [r for r in rows[2:] if len(r) == len(hh)]
+body = [r for r in rows[2:] if len(r) == len(hh) and r[hh.index("# Samples")].strip().isdigit()]      # (-c > 1 repeats the header)
 isamp, isrc = hh.index("# Samples"), hh.index("Source")
 stall = [i for i, k in enumerate(hh) if k.startswith("stall_") and "Not Issued" not in k]
 tot = sum(int(r[isamp]) for r in body)
