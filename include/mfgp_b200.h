@@ -178,6 +178,29 @@ int mfgp_posterior_grid_factored_solved(const double* ux, int64_t nx, const doub
                                         double* mu, double* var, double* qred, double* Gstore, double* Hz_store, void* work,
                                         int64_t work_bytes, void* stream);
 
+/* The same sequence with the Gram product of steps 4 + 5 folded into the factorisation kernel.  The Gram route of the
+ * factored posterior needs M = Yall^T Yall (R x R; csrc/gp_factored.cu); mfgp_cholesky_solve_gram accumulates its 64x64
+ * tiles with low-priority tasks of the SAME tile-dataflow kernel -- group of block rows by group, in a fixed order, so M is
+ * deterministic -- in the CTA slots that the factorisation leaves idle while it waits on its chain of diagonal blocks:
+ *   M = mfgp_factored_gram_target(...)   pointer into the prepare `work` buffer where the posterior call expects M, or NULL
+ *                                         when steps 4 + 5 will take the direct route (then use the plain pair above);
+ *   mfgp_cholesky_solve_gram(..., M, ldm = ldb = R, work of mfgp_cholesky_solve_gram_workspace_bytes(npad, R) bytes, ...);
+ *   mfgp_posterior_grid_factored_solved_gram(...)   same arguments as _solved; skips the product and its reduction.
+ * M == NULL in mfgp_cholesky_solve_gram is mfgp_cholesky_solve. */
+double* mfgp_factored_gram_target(int64_t nx, int64_t ny, int64_t ix0, int64_t ncols, int64_t NL, int64_t NH, int64_t npad,
+                                  const mfgp_params* p_host, int64_t rxL, int64_t ryL, int64_t rxH, int64_t ryH,
+                                  int64_t chunk_cols, int64_t ldY, void* work, int64_t work_bytes);
+int64_t mfgp_cholesky_solve_gram_workspace_bytes(int64_t npad, int64_t R);
+int mfgp_cholesky_solve_gram(double* K, int64_t npad, int64_t ld, double* W, int64_t ldw, int32_t* info, double* Bm, int64_t ldb,
+                             int64_t R, double* M, int64_t ldm, void* work, int64_t work_bytes, void* stream);
+int mfgp_posterior_grid_factored_solved_gram(const double* ux, int64_t nx, const double* uy, int64_t ny, int64_t ix0,
+                                             int64_t ncols, const double* Xt, int64_t NL, int64_t NH, int64_t npad,
+                                             const mfgp_params* p_host, int64_t rxL, int64_t ryL, int64_t rxH, int64_t ryH,
+                                             double xlo, double xhi, double ylo, double yhi, int64_t chunk_cols,
+                                             const double* Yall, int64_t ldY, double* z_out, double* mu, double* var,
+                                             double* qred, double* Gstore, double* Hz_store, void* work, int64_t work_bytes,
+                                             void* stream);
+
 /* ---- coverage step: replaces simulator.py in_polygon :105-124, compute_loss :194-228, compute_centroids :231-283,
  *      compute_max_var :286-323, compute_sample_clusters :377-412 ------------------------------------------------ */
 

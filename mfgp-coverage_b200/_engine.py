@@ -6,12 +6,17 @@ Cholesky factor K[npad,npad], its inverse W[npad,npad], scaled coordinates Tt[np
 streams only.  Layout notes are in DESIGN.md ("Data layout in HBM").
 """
 import ctypes
+import os
 import itertools
 
 import numpy as np
 import torch
 
 from . import _native as nat
+
+# MFGP_FUSED_GRAM=0: the Gram product M = Y^T Y of the factored posterior as a separate launch after the factorisation
+# (default: accumulated inside the tile-dataflow kernel, see include/mfgp_b200.h: mfgp_cholesky_solve_gram)
+FUSED_GRAM = os.environ.get("MFGP_FUSED_GRAM", "1") != "0"
 
 
 def chebyshev_order(length_scale, lo, hi, centre_lo, centre_hi, tol=5e-15, rmax=64):
@@ -469,19 +474,24 @@ class DeviceGP:
         ev = self.profile_events          # bench.py: (start, stop) CUDA events around the dominant kernel
         if ev is not None:
             ev[0].record()
-        cneed = int(lib.mfgp_cholesky_solve_workspace_bytes(self.cap, R))
+        cneed = int(lib.mfgp_cholesky_solve_gram_workspace_bytes(self.cap, R))
         if self._cwork is None or self._cwork.numel() * 8 < cneed:
             self._cwork = torch.empty(cneed // 8 + 8, dtype=torch.float64, device=self.device)
-        nat.check(lib.mfgp_cholesky_solve(nat.ptr(self.K), npad, ld, nat.ptr(self.W), ld, nat.ptr(self.info),
-                                          nat.ptr(self._fB), R, R, nat.ptr(self._cwork), self._cwork.numel() * 8, st),
-                  "mfgp_cholesky_solve")
+        # Gram route of steps 4 + 5: M = Y^T Y is accumulated inside the factorisation kernel (NULL: direct route)
+        M = lib.mfgp_factored_gram_target(axes.nx, axes.ny, plan["ix0"], plan["ncols"], self.NL, self.NH, npad, pp, *o,
+                                          plan["chunk"], R, nat.ptr(work), work.numel() * 8) if FUSED_GRAM else None
+        nat.check(lib.mfgp_cholesky_solve_gram(nat.ptr(self.K), npad, ld, nat.ptr(self.W), ld, nat.ptr(self.info),
+                                               nat.ptr(self._fB), R, R, ctypes.c_void_p(M), R, nat.ptr(self._cwork),
+                                               self._cwork.numel() * 8, st), "mfgp_cholesky_solve_gram")
         if ev is not None:
             ev[1].record()
         Gs, Hs = self._factored_stores(plan)
-        nat.check(lib.mfgp_posterior_grid_factored_solved(
+        solved = lib.mfgp_posterior_grid_factored_solved_gram if M else lib.mfgp_posterior_grid_factored_solved
+        nat.check(solved(
             nat.ptr(axes.ux), axes.nx, nat.ptr(axes.uy), axes.ny, plan["ix0"], plan["ncols"], nat.ptr(self.Xt), self.NL,
             self.NH, npad, pp, *o, *geom, nat.ptr(self._fB), R, nat.ptr(self.z), nat.ptr(mu), nat.ptr(var), nat.ptr(q_out),
             nat.ptr(Gs), nat.ptr(Hs), nat.ptr(work), work.numel() * 8, st), "mfgp_posterior_grid_factored_solved")
+        self.fused_gram = bool(M)
         self._dirty = False
         self._w_partial = True
 

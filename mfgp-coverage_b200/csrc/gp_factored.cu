@@ -749,38 +749,50 @@ int gram_route_override() {          // read per call: tests and A/B timings swi
 
 // steps 4 - 6 by the Gram route from the solved right-hand sides Yall[npad][ldY] (columns [0, ry * kpad): Y, column
 // ry * kpad: z, then zero padding up to ldY, a multiple of 64).  Returns MFGP_OK, or 1 when the direct route is cheaper.
+// route of steps 4 + 5 for solved right-hand sides with row stride ldY: true = Gram route (cost model, MFGP_GRAM overrides)
+bool f_gram_wanted(const FGeom& g, const FLayout& L, int64_t ldY) {
+    const FPart& f = L.parts[0];
+    const int64_t npad = g.npad, cols = (int64_t)f.ry * f.kpad;
+    const int wm = f.ry <= 40 ? 40 : 64;
+    const int nt8 = (f.kpad + 7) / 8;
+    if (ldY % 64 || ldY < cols + 1 || nt8 > 8) return false;
+    const int ov = gram_route_override();
+    const double direct = (double)g.ncols * npad * cols + 0.6 * g.ncols * npad * wm * wm;
+    const double gram = 0.5 * npad * (double)ldY * ldY + (double)round_up(g.ncols, 64) * (f.ry * (f.ry + 1) / 2) * 64.0 * nt8 * nt8;
+    return !(ov == 1 || (ov == 0 && gram >= direct));
+}
+
+// m_ready: M (f.Yp, row stride ldY) already holds Y^T Y (mfgp_cholesky_solve_gram wrote it)
 int f_tail_gram(const FGeom& g, FLayout& L, const double* Yall, int64_t ldY, double* Gstore, double* Hz_store, double* mu,
-                double* var, double* qred, cudaStream_t st) {
+                double* var, double* qred, bool m_ready, cudaStream_t st) {
     FPart& f = L.parts[0];
     const int64_t npad = g.npad, cols = (int64_t)f.ry * f.kpad;
     const int wm = f.ry <= 40 ? 40 : 64;
     const int nt8 = (f.kpad + 7) / 8;
-    if (ldY % 64 || ldY < cols + 1 || nt8 > 8) return 1;
-    const int ov = gram_route_override();
-    const double direct = (double)g.ncols * npad * cols + 0.6 * g.ncols * npad * wm * wm;
-    const double gram = 0.5 * npad * (double)ldY * ldY + (double)round_up(g.ncols, 64) * (f.ry * (f.ry + 1) / 2) * 64.0 * nt8 * nt8;
-    if (ov == 1 || (ov == 0 && gram >= direct)) return 1;
+    if (!f_gram_wanted(g, L, ldY)) return m_ready ? MFGP_ERR_INVALID : 1;
     const DevParams dp = make_dev_params(*g.p);
     // M and its partial sums live where the direct route keeps Y'
     double* M = f.Yp;
     double* part = M + ldY * ldY;
     double* Gbuf = Gstore ? Gstore : part + (int64_t)MR_MAXSPLIT * ldY * ldY;
-    const int ntile = (int)(ldY / 64), tiles = ntile * (ntile + 1) / 2;
-    int nsplit = 740 / tiles;                       // ~5 CTAs of the tile kernel per SM: one resident wave
-    if (nsplit < 1) nsplit = 1;
-    if (nsplit > MR_MAXSPLIT) nsplit = MR_MAXSPLIT;
-    if (nsplit > npad / 128) nsplit = (int)imax(1, npad / 128);
-    const int kchunk = (int)((npad / 64 + nsplit - 1) / nsplit) * 64;
-    nsplit = (int)((npad + kchunk - 1) / kchunk);
-    GemmArgs gm{};
-    gm.A = Yall; gm.lda = ldY; gm.B = Yall; gm.ldb = ldY; gm.C = nsplit > 1 ? part : M; gm.ldc = ldY; gm.strideC = ldY * ldY;
-    gm.M = (int)ldY; gm.N = (int)ldY; gm.K = (int)npad; gm.alpha = 1.0; gm.beta = 0.0; gm.mode = GEMM_SYRK_LOWER;
-    gm.kchunk = nsplit > 1 ? kchunk : 0;
-    int rc = launch_syrk_ata(gm, nsplit, st);
-    if (rc) return rc;
-    if (nsplit > 1) {
-        syrk_reduce_lower_kernel<<<dim3((unsigned)((ldY + 127) / 128), (unsigned)ldY), 128, 0, st>>>(part, nsplit, ldY * ldY, (int)ldY, M);
-        MFGP_LAUNCH_CHECK();
+    if (!m_ready) {
+        const int ntile = (int)(ldY / 64), tiles = ntile * (ntile + 1) / 2;
+        int nsplit = 740 / tiles;                       // ~5 CTAs of the tile kernel per SM: one resident wave
+        if (nsplit < 1) nsplit = 1;
+        if (nsplit > MR_MAXSPLIT) nsplit = MR_MAXSPLIT;
+        if (nsplit > npad / 128) nsplit = (int)imax(1, npad / 128);
+        const int kchunk = (int)((npad / 64 + nsplit - 1) / nsplit) * 64;
+        nsplit = (int)((npad + kchunk - 1) / kchunk);
+        GemmArgs gm{};
+        gm.A = Yall; gm.lda = ldY; gm.B = Yall; gm.ldb = ldY; gm.C = nsplit > 1 ? part : M; gm.ldc = ldY; gm.strideC = ldY * ldY;
+        gm.M = (int)ldY; gm.N = (int)ldY; gm.K = (int)npad; gm.alpha = 1.0; gm.beta = 0.0; gm.mode = GEMM_SYRK_LOWER;
+        gm.kchunk = nsplit > 1 ? kchunk : 0;
+        int rc = launch_syrk_ata(gm, nsplit, st);
+        if (rc) return rc;
+        if (nsplit > 1) {
+            syrk_reduce_lower_kernel<<<dim3((unsigned)((ldY + 127) / 128), (unsigned)ldY), 128, 0, st>>>(part, nsplit, ldY * ldY, (int)ldY, M);
+            MFGP_LAUNCH_CHECK();
+        }
     }
     if (Hz_store) f.Hz = Hz_store;
     hz_from_M_kernel<<<(unsigned)((cols + 127) / 128), 128, 0, st>>>(M, (int)ldY, (int)cols, (int)cols, f.Hz);
@@ -874,25 +886,20 @@ extern "C" int mfgp_factored_prepare(const double* ux, int64_t nx, const double*
 
 // Fused-fit form, part 2: Yall = L^-1 Ball (mfgp_cholesky_solve) -> steps 4 - 6.  `work` must be the workspace that
 // mfgp_factored_prepare filled (it holds the basis tables); z_out (optional) receives the whitened observations z[npad].
-extern "C" int mfgp_posterior_grid_factored_solved(const double* ux, int64_t nx, const double* uy, int64_t ny, int64_t ix0,
-                                                   int64_t ncols, const double* Xt, int64_t NL, int64_t NH, int64_t npad,
-                                                   const mfgp_params* p_host, int64_t rxL, int64_t ryL, int64_t rxH, int64_t ryH,
-                                                   double xlo, double xhi, double ylo, double yhi, int64_t chunk_cols,
-                                                   const double* Yall, int64_t ldY, double* z_out, double* mu, double* var,
-                                                   double* qred, double* Gstore, double* Hz_store, void* work,
-                                                   int64_t work_bytes, void* stream) {
-    if (!Yall || !mu || !var || ldY < mfgp_factored_rhs_cols(rxL, ryL, rxH, ryH)) return MFGP_ERR_INVALID;
-    FGeom g{ux, nx, uy, ny, ix0, ncols, Xt, NL, NH, npad, p_host, rxL, ryL, rxH, ryH, xlo, xhi, ylo, yhi, chunk_cols};
+namespace {
+int f_solved_impl(const FGeom& g, const double* Yall, int64_t ldY, double* z_out, double* mu, double* var, double* qred,
+                  double* Gstore, double* Hz_store, void* work, int64_t work_bytes, bool m_ready, cudaStream_t st) {
+    if (!Yall || !mu || !var || ldY < mfgp_factored_rhs_cols(g.rxL, g.ryL, g.rxH, g.ryH)) return MFGP_ERR_INVALID;
     int rc = f_validate(g, work, work_bytes);
     if (rc) return rc;
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
     FLayout L;
     f_carve(g, work, L);
+    const int64_t npad = g.npad;
     const int64_t zoff = (int64_t)L.parts[0].ry * L.parts[0].kpad;
     unpack_z_kernel<<<(unsigned)((npad + 255) / 256), 256, 0, st>>>(Yall, ldY, (int)zoff, (int)npad, L.zbuf);
     MFGP_LAUNCH_CHECK();
     if (z_out) MFGP_CUDA_CHECK(cudaMemcpyAsync(z_out, L.zbuf, sizeof(double) * npad, cudaMemcpyDeviceToDevice, st));
-    rc = f_tail_gram(g, L, Yall, ldY, Gstore, Hz_store, mu, var, qred, st);      // Gram route: M = Y^T Y, then quadratic forms
+    rc = f_tail_gram(g, L, Yall, ldY, Gstore, Hz_store, mu, var, qred, m_ready, st);      // Gram route: M = Y^T Y, then quadratic forms
     if (rc <= 0) return rc;
     int64_t off = 0;                                                             // direct route (cheaper for few training rows)
     for (int pi = 0; pi < L.nparts; pi++) {
@@ -904,6 +911,45 @@ extern "C" int mfgp_posterior_grid_factored_solved(const double* ux, int64_t nx,
         off += cols;
     }
     return f_tail(g, L, L.zbuf, npad, Gstore, Hz_store, 0, mu, var, qred, st);
+}
+}  // namespace
+
+extern "C" int mfgp_posterior_grid_factored_solved(const double* ux, int64_t nx, const double* uy, int64_t ny, int64_t ix0,
+                                                   int64_t ncols, const double* Xt, int64_t NL, int64_t NH, int64_t npad,
+                                                   const mfgp_params* p_host, int64_t rxL, int64_t ryL, int64_t rxH, int64_t ryH,
+                                                   double xlo, double xhi, double ylo, double yhi, int64_t chunk_cols,
+                                                   const double* Yall, int64_t ldY, double* z_out, double* mu, double* var,
+                                                   double* qred, double* Gstore, double* Hz_store, void* work,
+                                                   int64_t work_bytes, void* stream) {
+    FGeom g{ux, nx, uy, ny, ix0, ncols, Xt, NL, NH, npad, p_host, rxL, ryL, rxH, ryH, xlo, xhi, ylo, yhi, chunk_cols};
+    return f_solved_impl(g, Yall, ldY, z_out, mu, var, qred, Gstore, Hz_store, work, work_bytes, false, static_cast<cudaStream_t>(stream));
+}
+
+// Where mfgp_cholesky_solve_gram must leave M = Yall^T Yall (row stride ldY) for the posterior call that follows: a pointer
+// into `work` (the buffer of mfgp_factored_prepare), or NULL when steps 4 + 5 will take the direct route for this geometry
+// (few training rows; MFGP_GRAM=direct) -- then call plain mfgp_cholesky_solve and mfgp_posterior_grid_factored_solved.
+extern "C" double* mfgp_factored_gram_target(int64_t nx, int64_t ny, int64_t ix0, int64_t ncols, int64_t NL, int64_t NH, int64_t npad,
+                                             const mfgp_params* p_host, int64_t rxL, int64_t ryL, int64_t rxH, int64_t ryH,
+                                             int64_t chunk_cols, int64_t ldY, void* work, int64_t work_bytes) {
+    if (!p_host || !work || ldY < mfgp_factored_rhs_cols(rxL, ryL, rxH, ryH)) return nullptr;
+    if (work_bytes < mfgp_factored_workspace_bytes(npad, ncols, ny, rxL, ryL, rxH, ryH, chunk_cols)) return nullptr;
+    FGeom g{nullptr, nx, nullptr, ny, ix0, ncols, nullptr, NL, NH, npad, p_host, rxL, ryL, rxH, ryH, 0.0, 1.0, 0.0, 1.0, chunk_cols};
+    FLayout L;
+    f_carve(g, work, L);
+    return f_gram_wanted(g, L, ldY) ? L.parts[0].Yp : nullptr;
+}
+
+// mfgp_posterior_grid_factored_solved after mfgp_cholesky_solve_gram: M = Yall^T Yall is already standing at
+// mfgp_factored_gram_target(...) inside `work`, so the symmetric product and its reduction are skipped.
+extern "C" int mfgp_posterior_grid_factored_solved_gram(const double* ux, int64_t nx, const double* uy, int64_t ny, int64_t ix0,
+                                                        int64_t ncols, const double* Xt, int64_t NL, int64_t NH, int64_t npad,
+                                                        const mfgp_params* p_host, int64_t rxL, int64_t ryL, int64_t rxH,
+                                                        int64_t ryH, double xlo, double xhi, double ylo, double yhi,
+                                                        int64_t chunk_cols, const double* Yall, int64_t ldY, double* z_out,
+                                                        double* mu, double* var, double* qred, double* Gstore, double* Hz_store,
+                                                        void* work, int64_t work_bytes, void* stream) {
+    FGeom g{ux, nx, uy, ny, ix0, ncols, Xt, NL, NH, npad, p_host, rxL, ryL, rxH, ryH, xlo, xhi, ylo, yhi, chunk_cols};
+    return f_solved_impl(g, Yall, ldY, z_out, mu, var, qred, Gstore, Hz_store, work, work_bytes, true, static_cast<cudaStream_t>(stream));
 }
 
 // Incremental form (after mfgp_cholesky_append): rows [row_lo, NL+NH) of the training set are new since Gstore / Hz_store

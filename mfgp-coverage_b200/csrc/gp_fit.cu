@@ -78,6 +78,15 @@ struct PotrfScratch {
     int bad;
 };
 
+// barrier of the 256 threads that work on a tile: the whole CTA, or (NAMED: the warp-specialised dataflow kernel, whose CTA
+// has a ninth, producer warp) named barrier 1
+template <bool NAMED>
+__device__ __forceinline__ void tile_bar() {
+    if (NAMED) asm volatile("bar.sync 1, 256;\n" ::: "memory");
+    else __syncthreads();
+}
+
+template <bool NAMED = false>
 __device__ __forceinline__ void potrf_diag_body(const double* src, int64_t lds, double* A, int64_t ld,
                                                 double* __restrict__ Winv, int64_t ldw, int32_t* __restrict__ info, int jblk,
                                                 PotrfScratch* sc) {
@@ -113,7 +122,7 @@ __device__ __forceinline__ void potrf_diag_body(const double* src, int64_t lds, 
 #pragma unroll
                 for (int b = 0; b < 4; b++) dst[2 * (tc + 16 * b)] = m[jb][b];
             }
-            __syncthreads();
+            tile_bar<NAMED>();
             const double2* col = colAB[buf];
             const double2* row = rowAB[buf];
             double pa = col[j0].x;
@@ -162,7 +171,7 @@ __device__ __forceinline__ void potrf_diag_body(const double* src, int64_t lds, 
             }
         }
     }
-    __syncthreads();
+    tile_bar<NAMED>();
     if (tid < PB / 2) {          // C = chol(P) of every pair
         const double a = piv[0][tid], b = piv[1][tid], c = piv[2][tid];
         const double r1 = rsqrt(a);
@@ -171,7 +180,7 @@ __device__ __forceinline__ void potrf_diag_body(const double* src, int64_t lds, 
         fin[1][tid] = rsqrt(fma(-g, b, c));
         fin[2][tid] = g;
     }
-    __syncthreads();
+    tile_bar<NAMED>();
     const bool failed = bad != 0;
 #pragma unroll
     for (int a = 0; a < 4; a++)
@@ -230,9 +239,14 @@ struct DfArgs {
     int32_t* info;
     int* flagsL;        // [nb][nb]: tile (i, c) of L is final (diagonal: L_cc and W_cc)
     int* flagsY;        // [nb][nr]
-    int* ctrl;          // [0] ticket counter, [1] abort
+    int* ctrl;          // [0] ticket counter, [1] abort, [2] Gram ticket counter, [3] diagonal blocks factored, [4] last column drawn
     int* pause;         // [number of SMs]
     int total;
+    // optional Gram product M = Y^T Y of the SOLVED right-hand sides (lower 64x64 tiles), accumulated by low-priority tasks of
+    // the same kernel: task (group of mg block rows, tile) adds the group's rows to the tile in place, groups in order
+    double* M; int64_t ldm;
+    int* flagsM;        // [groups][m_tiles]: the tile holds the sum over groups 0 .. g
+    int mg, m_tiles, m_total, m_lead;
     long long spin_limit;
     long long* trace;   // diagnostics (MFGP_DF_TRACE=1): 8 timestamps per chain task, else nullptr
     int chain_la;       // chain task d draws its ticket d / chain_la block columns early (0: with its own column)
@@ -283,11 +297,59 @@ __device__ __forceinline__ bool df_wait(const int* f, int* ctrl, int32_t* info, 
     return ok != 0;
 }
 
-__global__ void __launch_bounds__(DF_THREADS, 2) chol_dataflow_kernel(DfArgs g) {
+// mbarrier / bulk-copy primitives of the warp-specialised variant
+__device__ __forceinline__ uint32_t df_smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void df_mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void df_mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void df_mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void df_mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+// global -> shared bulk copy (TMA engine), completion counted in bytes on an mbarrier; 16-byte aligned, size % 16 == 0
+__device__ __forceinline__ void df_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(dst), "l"(src),
+                 "r"(bytes), "r"(bar)
+                 : "memory");
+}
+
+// WS = false: 256 threads, every warp stages its share of the slabs (cp.async) and computes, one CTA barrier per slab.
+// WS = true:  288 threads, warp 8 is a PRODUCER -- it polls the tile flags and moves the slabs with bulk copies that complete
+//             on per-stage "full" mbarriers; the 8 consumer warps wait on those, run the DMMA loop and arrive on the stage's
+//             "empty" mbarrier.  No CTA-wide barrier inside the k loop: the warps of a CTA drift apart by up to two slabs
+//             instead of meeting twice per 32 k, and the staging instructions leave the consumers' issue slots.
+constexpr int DF_WS_THREADS = DF_THREADS + 32;
+// 2 CTAs per SM: 128 registers per thread at 256 threads, 112 at 288 (18 warps x 32 x 112 = 64512 of the SM's 65536)
+template <bool WS>
+__global__ void __launch_bounds__(WS ? DF_WS_THREADS : DF_THREADS) __maxnreg__(WS ? 112 : 128) chol_dataflow_kernel(DfArgs g) {
     extern __shared__ __align__(16) double df_smem[];
     __shared__ int task[4];
     __shared__ int ready_s[4];
+    __shared__ __align__(8) unsigned long long df_bars[2 * DF_NSTAGE];     // WS: full[stage], empty[stage]
+    __shared__ int abort_s;                                                // WS: a flag wait timed out (bug guard)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool producer = WS && warp == DF_THREADS / 32;
+    const uint32_t bar_full = df_smem_u32(&df_bars[0]), bar_empty = df_smem_u32(&df_bars[DF_NSTAGE]);
+    unsigned gs_base = 0;                     // WS: slabs this CTA has moved so far (ring slot = gs % 3, phase = gs / 3)
+    if (WS) {
+        if (tid == 0) {
+            for (int q = 0; q < DF_NSTAGE; q++) { df_mbar_init(bar_full + 8 * q, 1); df_mbar_init(bar_empty + 8 * q, DF_THREADS / 32); }
+            abort_s = 0;
+            asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+        }
+    }
     // 8 warps as 4 x 2; a warp owns the 8x8 tiles (row tile (warp>>1) + 4x, column tile (warp&1) + 2y), x < 2, y < 4 --
     // interleaved, so that the triangular products of the chain task (W_cc lower, S symmetric) skip about the same share
     // of DMMAs in every warp
@@ -298,15 +360,70 @@ __global__ void __launch_bounds__(DF_THREADS, 2) chol_dataflow_kernel(DfArgs g) 
     unsigned smid;
     asm volatile("mov.u32 %0, %%smid;\n" : "=r"(smid));
     int* my_pause = g.pause + smid;
+    // diagnostics (MFGP_DF_TRACE=1): SM clocks this CTA spent waiting for tile flags, in k loops, and in total
+#ifdef MFGP_DF_ACCOUNTING       // build with -DMFGP_DF_ACCOUNTING for profiles/tools/cta_account.py (costs ~10 registers)
+    long long t_wait = 0, t_loop = 0, t_begin = clock64(), t_mark = 0;
+    int n_tasks = 0;
+    const bool tracing = g.trace != nullptr;
+#else
+    long long t_wait = 0, t_loop = 0, t_begin = 0, t_mark = 0;
+    int n_tasks = 0;
+    constexpr bool tracing = false;
+#endif
+    int held_m = -1;                          // thread 0: a Gram ticket claimed before it became runnable
 
     for (;;) {
+        if (WS && !producer) asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // epilogue stores before the next bulk copies
         __syncthreads();                      // the previous task is done with shared memory and task[]
+        if (WS && abort_s) return;            // (uniform: written before the barrier)
         if (tid == 0) {
-            int t = atomicAdd(g.ctrl, 1);
-            int c = 0, kind = -1, idx = 0;
+            int c = 0, kind = -1, idx = 0, aux = 0;
+            int t = -1;
+            if (g.M == nullptr) {
+                t = atomicAdd(g.ctrl, 1);
+            } else {
+                // Two queues.  Critical = the factorisation and the substitution (ticket order as below); Gram = the tiles of
+                // M = Y^T Y per group of block rows.  A CTA takes a Gram ticket only when (a) every task the group's rows depend on
+                // has been DRAWN (a critical ticket of a later column was handed out), so that it cannot starve them of CTAs,
+                // (b) the rows are factored (no waiting inside the task) and (c) the critical queue is at least m_lead block
+                // columns ahead of the chain -- or when the critical queue is empty.  A ticket claimed too early (a race at a
+                // group boundary) is HELD while the CTA goes on with critical tasks, so no CTA ever waits on an undrawn task.
+                for (;;) {
+                    const int front = df_ld_relaxed(g.ctrl + 3), drawn = df_ld_relaxed(g.ctrl + 4);
+                    const bool crit_left = df_ld_relaxed(g.ctrl) < g.total;
+                    auto runnable = [&](int tm) {
+                        const int gi = tm / g.m_tiles;
+                        const int last_row = min(g.nb, (gi + 1) * g.mg) - 1;
+                        return !crit_left || (drawn > last_row && last_row + 2 <= front);
+                    };
+                    if (held_m < 0) {
+                        const int tm = df_ld_relaxed(g.ctrl + 2);
+                        if (tm < g.m_total && runnable(tm) && (!crit_left || drawn - front >= g.m_lead)) {
+                            const int got = atomicAdd(g.ctrl + 2, 1);
+                            if (got < g.m_total) held_m = got;
+                        }
+                    }
+                    if (held_m >= 0 && runnable(held_m)) {
+                        kind = 3; c = held_m / g.m_tiles; idx = held_m % g.m_tiles;
+                        int ti = 0;
+                        while ((ti + 1) * (ti + 2) / 2 <= idx) ti++;
+                        aux = idx - ti * (ti + 1) / 2;        // tile (ti, aux), aux <= ti
+                        idx = ti;
+                        held_m = -1;
+                        break;
+                    }
+                    if (crit_left) {
+                        t = atomicAdd(g.ctrl, 1);
+                        if (t < g.total) break;
+                        t = -1;
+                        continue;
+                    }
+                    if (held_m < 0 && df_ld_relaxed(g.ctrl + 2) >= g.m_total) break;      // both queues are empty
+                }
+            }
             if (t == 0) {
                 kind = 2; idx = 0;            // chain task 0: the first diagonal block
-            } else if (t < g.total) {
+            } else if (t > 0 && t < g.total) {
                 // Ticket order: per block column c -- the chain tasks PLACED there, the tiles (i, c) below the sub-diagonal, the
                 // Y tiles of block row c.  Chain task d (k loop of d - 1 tile pairs: the longest task of its column) is placed
                 // d / chain_la columns AHEAD of column d - 1, so that its accumulation is done by the time W_{d-1} arrives; it
@@ -333,31 +450,99 @@ __global__ void __launch_bounds__(DF_THREADS, 2) chol_dataflow_kernel(DfArgs g) 
                     }
                     t -= n; c++; dnext += nchain;
                 }
+                if (g.M != nullptr) atomicMax(g.ctrl + 4, c);
             }
+            task[3] = aux;
             task[0] = kind; task[1] = c; task[2] = idx;
         }
         __syncthreads();
         const int kind = task[0], idx = task[2];
-        if (kind < 0) return;
-        const bool rhs = kind == 1, chain = kind == 2;
+        if (kind < 0) {
+            if (tracing && tid == 0) {
+                unsigned long long tg;
+                asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(tg));
+                long long* o = g.trace + 1024 * 16 + (int64_t)blockIdx.x * 8;
+                o[0] = t_wait; o[1] = t_loop; o[2] = clock64() - t_begin; o[3] = n_tasks; o[4] = (long long)tg; o[5] = smid;
+            }
+            return;
+        }
+        n_tasks++;
+        const bool rhs = kind == 1, chain = kind == 2, gram = kind == 3;
+        const bool bkn = rhs || gram;                                    // B operand stored [k][n] (rows of Y)
         // c = block column whose diagonal inverse finishes the task; i = block row of the A operand / output tile
-        const int c = chain ? idx - 1 : task[1];
+        // (Gram task: task[1] = group of block rows, tile (idx, task[3]) of M)
+        const int c = chain ? idx - 1 : (gram ? 0 : task[1]);
         const int i = rhs ? c : idx;
-        const int nk = chain ? (idx > 0 ? idx - 1 : 0) : c;             // k tiles accumulated before the epilogue
-        // operands of the k loop: A = L_i,k ([m][k]);  B = L_c,k ([n][k], transposed product) or Y_k,r ([k][n])
-        const double* Ag = g.K + (int64_t)i * PB * g.ld;
-        const double* Bg = rhs ? g.Bm + (int64_t)idx * PB : g.K + (int64_t)(c > 0 ? c : 0) * PB * g.ld;
-        const int* fa = g.flagsL + (int64_t)i * g.nb;                                           // L_i,k ready
-        const int* fb = rhs ? g.flagsY + idx : g.flagsL + (int64_t)(c > 0 ? c : 0) * g.nb;      // Y_k,r (stride nr) or L_c,k
-        const int fbs = rhs ? g.nr : 1;
+        const int gi = gram ? task[1] : 0, tj = task[3];
+        const int kb = gram ? gi * g.mg : 0;                             // first k tile
+        const int nk = gram ? min(g.nb, kb + g.mg) - kb
+                            : (chain ? (idx > 0 ? idx - 1 : 0) : c);      // k tiles accumulated before the epilogue
+        // operands of the k loop: A = L_i,k ([m][k]) or Y_k,ti ([k][m]);  B = L_c,k ([n][k], transposed product) or Y_k,r ([k][n])
+        const double* Ag = gram ? g.Bm + (int64_t)kb * PB * g.ldb + (int64_t)idx * PB : g.K + (int64_t)i * PB * g.ld;
+        const double* Bg = gram ? g.Bm + (int64_t)kb * PB * g.ldb + (int64_t)tj * PB
+                                : (rhs ? g.Bm + (int64_t)idx * PB : g.K + (int64_t)(c > 0 ? c : 0) * PB * g.ld);
+        const int* fa = gram ? g.flagsY + (int64_t)kb * g.nr + idx : g.flagsL + (int64_t)i * g.nb;   // A tile of k tile kt ready
+        const int* fb = gram ? g.flagsY + (int64_t)kb * g.nr + tj
+                             : (rhs ? g.flagsY + idx : g.flagsL + (int64_t)(c > 0 ? c : 0) * g.nb);  // Y_k,r (stride nr) or L_c,k
+        const int fas = gram ? g.nr : 1, fbs = bkn ? g.nr : 1;
 
         // The accumulators START at minus the tile they will be subtracted from (A_ic or B_cr; chain tasks: also A_dd), so the
         // global reads of those tiles happen here, at the head of the task, instead of on the critical tail behind the flag.
-        double* Ct = rhs ? g.Bm + (int64_t)c * PB * g.ldb + (int64_t)idx * PB
-                         : g.K + (int64_t)i * PB * g.ld + (int64_t)(c > 0 ? c : 0) * PB;
-        const int64_t ldc = rhs ? g.ldb : g.ld;
+        // (Gram task: at plus the tile's sum over the earlier groups, once that is flagged.)
+        double* Ct = gram ? g.M + (int64_t)idx * PB * g.ldm + (int64_t)tj * PB
+                          : (rhs ? g.Bm + (int64_t)c * PB * g.ldb + (int64_t)idx * PB
+                                 : g.K + (int64_t)i * PB * g.ld + (int64_t)(c > 0 ? c : 0) * PB);
+        const int64_t ldc = gram ? g.ldm : (rhs ? g.ldb : g.ld);
         double* Cd = g.K + (int64_t)(chain ? idx : 0) * PB * (g.ld + 1);        // diagonal tile (idx, idx) of a chain task
-        const bool has_tile = !(chain && idx == 0);
+        const bool has_tile = gram ? gi > 0 : !(chain && idx == 0);
+        int* const mflag = gram ? g.flagsM + (int64_t)gi * g.m_tiles + idx * (idx + 1) / 2 + tj : nullptr;
+        const int nslab = nk * (PB / DF_K);
+        if (producer) {
+            // ---- producer warp: flags -> bulk copies of slab s into ring slot (gs_base + s) % 3 -------------------------------
+            for (int s = 0; s < nslab; s++) {
+                if ((s & 1) == 0) {
+                    const int kt = s >> 1;
+                    bool w = df_wait(fa + (int64_t)kt * fas, g.ctrl, g.info, g.spin_limit);
+                    w = df_wait(fb + (int64_t)kt * fbs, g.ctrl, g.info, g.spin_limit) && w;
+                    if (!w && lane == 0) abort_s = 1;          // keep moving (garbage): the consumers must not be left waiting
+                    asm volatile("fence.proxy.async.global;\n" ::: "memory");     // acquired tiles -> reads by the copy engine
+                }
+                const unsigned gs = gs_base + s;
+                const int slot = gs % DF_NSTAGE;
+                if (gs >= DF_NSTAGE) df_mbar_wait(bar_empty + 8 * slot, ((gs / DF_NSTAGE) + 1) & 1);
+                const uint32_t fbar = bar_full + 8 * slot;
+                if (lane == 0) df_mbar_arrive_expect_tx(fbar, 2 * PB * DF_K * 8);
+                __syncwarp();
+                const int k0 = s * DF_K;
+                const uint32_t As = df_smem_u32(As0 + slot * DF_STAGE), Bs = df_smem_u32(Bs0 + slot * DF_STAGE);
+                if (!gram) {
+                    for (int r = lane; r < PB; r += 32) df_bulk_g2s(As + r * DF_LDA * 8, Ag + (int64_t)r * g.ld + k0, DF_K * 8, fbar);
+                } else {
+                    df_bulk_g2s(As + lane * DF_LDT * 8, Ag + (int64_t)(k0 + lane) * g.ldb, PB * 8, fbar);
+                }
+                if (!bkn) {
+                    for (int r = lane; r < PB; r += 32) df_bulk_g2s(Bs + r * DF_LDA * 8, Bg + (int64_t)r * g.ld + k0, DF_K * 8, fbar);
+                } else {
+                    df_bulk_g2s(Bs + lane * DF_LDT * 8, Bg + (int64_t)(k0 + lane) * g.ldb, PB * 8, fbar);
+                }
+            }
+            gs_base += nslab;
+            continue;
+        }
+        bool ok = true;
+        if (gram && gi > 0) {
+            if (tracing) t_mark = clock64();
+            if (warp == 0) {
+                const bool w = df_wait(mflag - g.m_tiles, g.ctrl, g.info, g.spin_limit);
+                if (lane == 0) ready_s[2] = w ? 1 : 0;
+            }
+            tile_bar<WS>();
+            if (tracing) t_wait += clock64() - t_mark;
+            if (ready_s[2] == 0) {                    // abort raised (uniform)
+                if (!WS) return;
+                ok = false;                           // WS: the slabs the producer moves must still be consumed
+            }
+        }
         double acc[2][4][2], acc2[2][4][2];
 #pragma unroll
         for (int x = 0; x < 2; x++)
@@ -367,11 +552,10 @@ __global__ void __launch_bounds__(DF_THREADS, 2) chol_dataflow_kernel(DfArgs g) 
                 double2 v = make_double2(0.0, 0.0), d = make_double2(0.0, 0.0);
                 if (has_tile) v = *reinterpret_cast<const double2*>(Ct + (int64_t)r * ldc + cc);
                 if (chain) d = *reinterpret_cast<const double2*>(Cd + (int64_t)r * g.ld + cc);
-                acc[x][y][0] = -v.x; acc[x][y][1] = -v.y;
+                acc[x][y][0] = gram ? v.x : -v.x; acc[x][y][1] = gram ? v.y : -v.y;
                 acc2[x][y][0] = -d.x; acc2[x][y][1] = -d.y;
             }
 
-        bool ok = true;
         // k loop: DF_NSTAGE slabs in flight.  A slab that opens a new k tile may only be staged once both operand tiles are
         // flagged ready; ONE thread samples those flags for the CTA every iteration (relaxed load, then one acquire when it
         // sees them set) and hands the verdict over through shared memory across the slab barriers.  If the next tile is not
@@ -380,12 +564,20 @@ __global__ void __launch_bounds__(DF_THREADS, 2) chol_dataflow_kernel(DfArgs g) 
             const int k0 = s * DF_K;
             double* As = As0 + (s % DF_NSTAGE) * DF_STAGE;
             double* Bs = Bs0 + (s % DF_NSTAGE) * DF_STAGE;
+            if (!gram) {
 #pragma unroll
-            for (int e = tid; e < PB * (DF_K / 2); e += DF_THREADS) {     // 64 rows x 16 chunks of 16 bytes
-                const int r = e >> 4, q = e & 15;
-                cp_async16(&As[r * DF_LDA + q * 2], Ag + (int64_t)r * g.ld + k0 + q * 2, true);
+                for (int e = tid; e < PB * (DF_K / 2); e += DF_THREADS) {     // 64 rows x 16 chunks of 16 bytes
+                    const int r = e >> 4, q = e & 15;
+                    cp_async16(&As[r * DF_LDA + q * 2], Ag + (int64_t)r * g.ld + k0 + q * 2, true);
+                }
+            } else {
+#pragma unroll
+                for (int e = tid; e < DF_K * (PB / 2); e += DF_THREADS) {     // [k][m]: 32 rows x 32 chunks
+                    const int r = e >> 5, q = e & 31;
+                    cp_async16(&As[r * DF_LDT + q * 2], Ag + (int64_t)(k0 + r) * g.ldb + q * 2, true);
+                }
             }
-            if (!rhs) {
+            if (!bkn) {
 #pragma unroll
                 for (int e = tid; e < PB * (DF_K / 2); e += DF_THREADS) {
                     const int r = e >> 4, q = e & 15;
@@ -402,55 +594,27 @@ __global__ void __launch_bounds__(DF_THREADS, 2) chol_dataflow_kernel(DfArgs g) 
         };
         auto sample = [&](int kt) -> int {            // both operand tiles of k tile kt flagged?  (thread 0 only)
             if (kt >= nk) return 0;
-            if (!(df_ld_relaxed(fa + kt) & df_ld_relaxed(fb + (int64_t)kt * fbs))) return 0;
-            return df_ld_acquire(fa + kt) & df_ld_acquire(fb + (int64_t)kt * fbs);
+            if (!(df_ld_relaxed(fa + (int64_t)kt * fas) & df_ld_relaxed(fb + (int64_t)kt * fbs))) return 0;
+            return df_ld_acquire(fa + (int64_t)kt * fas) & df_ld_acquire(fb + (int64_t)kt * fbs);
         };
         // the same in two halves: the relaxed loads are ISSUED before a slab's DMMA loop and consumed after it, so their L2
         // round trip never sits between the CTA and its barrier; only a tile newly seen ready costs the acquire
-        auto peek = [&](int kt) -> int { return kt < nk ? (df_ld_relaxed(fa + kt) & df_ld_relaxed(fb + (int64_t)kt * fbs)) : 0; };
-        auto confirm = [&](int kt) -> int { return df_ld_acquire(fa + kt) & df_ld_acquire(fb + (int64_t)kt * fbs); };
-        const int nslab = nk * (PB / DF_K);
-        int staged = 0, ready_kt = -1;                // tiles 0 .. ready_kt are known to be ready (uniform)
-        int paused = 0;
-        if (tid == 0) ready_s[3] = sample(0) ? 0 : -1;
-        __syncthreads();
-        ready_kt = ready_s[3];
-        for (int s = 0; s < nslab; s++) {
-            // stage ahead
-            while (staged < nslab && staged < s + DF_NSTAGE) {
-                const int kt = staged >> 1;
-                if (kt > ready_kt) {
-                    if (staged > s) break;            // something is in flight: compute it first, look again afterwards
-                    if (warp == 0) {                  // nothing to compute: wait for the tile
-                        bool w = df_wait(fa + kt, g.ctrl, g.info, g.spin_limit);
-                        w = df_wait(fb + (int64_t)kt * fbs, g.ctrl, g.info, g.spin_limit) && w;
-                        if (lane == 0) ready_s[2] = w ? 1 : 0;
-                    }
-                    __syncthreads();                  // also orders warp 0's acquire before everybody's tile loads
-                    ok = (ready_s[2] != 0) && ok;
-                    ready_kt = kt;
-                }
-                issue(staged);
-                staged++;
-            }
-            const int inflight = staged - s - 1;      // groups that may stay pending while slab s is consumed
-            if (inflight >= 2) cp_async_wait<2>(); else if (inflight == 1) cp_async_wait<1>(); else cp_async_wait<0>();
-            if (lane == 0) {                          // the SM's other CTA is in the tail of a chain task: stand back
-                while (paused && df_ld_relaxed(my_pause)) __nanosleep(200);
-                paused = df_ld_relaxed(my_pause);     // (sampled one slab ahead: the load is off the critical path)
-            }
-            const int seen = (tid == 0) ? peek(ready_kt + 1) : 0;
-            if (__syncthreads_or(!ok)) return;        // abort raised: every thread of the CTA leaves together
-            const double* As = As0 + (s % DF_NSTAGE) * DF_STAGE;
-            const double* Bs = Bs0 + (s % DF_NSTAGE) * DF_STAGE;
+        auto peek = [&](int kt) -> int {
+            return kt < nk ? (df_ld_relaxed(fa + (int64_t)kt * fas) & df_ld_relaxed(fb + (int64_t)kt * fbs)) : 0;
+        };
+        auto confirm = [&](int kt) -> int { return df_ld_acquire(fa + (int64_t)kt * fas) & df_ld_acquire(fb + (int64_t)kt * fbs); };
+        auto compute = [&](int slot) {                // one 64 x 64 x 32 slab out of ring slot `slot`
+            const double* As = As0 + slot * DF_STAGE;
+            const double* Bs = Bs0 + slot * DF_STAGE;
 #pragma unroll
             for (int kk = 0; kk < DF_K; kk += 4) {
                 double a[2], b[4];
 #pragma unroll
-                for (int x = 0; x < 2; x++) a[x] = As[(wm + x * 32 + gq) * DF_LDA + kk + tq];
+                for (int x = 0; x < 2; x++)
+                    a[x] = gram ? As[(kk + tq) * DF_LDT + wm + x * 32 + gq] : As[(wm + x * 32 + gq) * DF_LDA + kk + tq];
 #pragma unroll
                 for (int y = 0; y < 4; y++)
-                    b[y] = rhs ? Bs[(kk + tq) * DF_LDT + wn + y * 16 + gq] : Bs[(wn + y * 16 + gq) * DF_LDA + kk + tq];
+                    b[y] = bkn ? Bs[(kk + tq) * DF_LDT + wn + y * 16 + gq] : Bs[(wn + y * 16 + gq) * DF_LDA + kk + tq];
 #pragma unroll
                 for (int x = 0; x < 2; x++)
 #pragma unroll
@@ -465,19 +629,86 @@ __global__ void __launch_bounds__(DF_THREADS, 2) chol_dataflow_kernel(DfArgs g) 
                             if (wn + y * 16 < wm + x * 32 + 8) dmma884(acc2[x][y][0], acc2[x][y][1], a[x], b[y]);
                 }
             }
-            if (tid == 0) ready_s[s & 1] = (seen && confirm(ready_kt + 1)) ? ready_kt + 1 : ready_kt;
-            __syncthreads();
-            ready_kt = ready_s[s & 1];
+        };
+        int paused = 0;
+        const long long t_loop0 = tracing ? clock64() : 0;
+        if (WS) {
+            // ---- consumer warps: wait for the slab, DMMA loop, hand the ring slot back -- no CTA-wide barrier
+            for (int s = 0; s < nslab; s++) {
+                const unsigned gs = gs_base + s;
+                const int slot = gs % DF_NSTAGE;
+                if (lane == 0) {                      // the SM's other CTA is in the tail of a chain task: stand back
+                    while (paused && df_ld_relaxed(my_pause)) __nanosleep(200);
+                    paused = df_ld_relaxed(my_pause);
+                }
+                __syncwarp();
+                df_mbar_wait(bar_full + 8 * slot, (gs / DF_NSTAGE) & 1);
+                compute(slot);
+                __syncwarp();
+                if (lane == 0) df_mbar_arrive(bar_empty + 8 * slot);
+            }
+            gs_base += nslab;
+        } else {
+        int staged = 0, ready_kt = -1;                // tiles 0 .. ready_kt are known to be ready (uniform)
+        if (tid == 0) ready_s[0] = sample(0) ? 0 : -1;
+        __syncthreads();
+        ready_kt = ready_s[0];
+        // ONE barrier per slab: slab s + 2 is staged right after the barrier of iteration s, into the ring slot that slab
+        // s - 1 occupied -- every warp has left that slab's DMMA loop by then.  Thread 0's verdict on the next k tile travels
+        // through ready_s[] across the same barrier (written after the DMMA loop of iteration s - 1, read after the barrier of s).
+        while (staged < nslab && staged < DF_NSTAGE - 1 && (staged >> 1) <= ready_kt) { issue(staged); staged++; }
+        for (int s = 0; s < nslab; s++) {
+            if (staged <= s) {                        // slab s could not be staged ahead: its k tile was not ready
+                const int kt = s >> 1;
+                if (tracing) t_mark = clock64();
+                if (warp == 0) {
+                    bool w = df_wait(fa + (int64_t)kt * fas, g.ctrl, g.info, g.spin_limit);
+                    w = df_wait(fb + (int64_t)kt * fbs, g.ctrl, g.info, g.spin_limit) && w;
+                    if (lane == 0) ready_s[2] = w ? 1 : 0;
+                }
+                __syncthreads();                      // also orders warp 0's acquire before everybody's tile loads
+                if (tracing) t_wait += clock64() - t_mark;
+                ok = (ready_s[2] != 0) && ok;
+                ready_kt = max(ready_kt, kt);
+                issue(s);
+                staged = s + 1;
+                if (staged < nslab && (staged >> 1) <= ready_kt) { issue(staged); staged++; }
+            }
+            if (staged - 1 - s >= 1) cp_async_wait<1>(); else cp_async_wait<0>();
+            if (lane == 0) {                          // the SM's other CTA is in the tail of a chain task: stand back
+                while (paused && df_ld_relaxed(my_pause)) __nanosleep(200);
+                paused = df_ld_relaxed(my_pause);     // (sampled one slab ahead: the load is off the critical path)
+            }
+            if (__syncthreads_or(!ok)) return;        // abort raised: every thread of the CTA leaves together
+            ready_kt = max(ready_kt, ready_s[s & 1]);
+            while (staged < nslab && staged <= s + DF_NSTAGE - 1 && (staged >> 1) <= ready_kt) { issue(staged); staged++; }
+            const int seen = (tid == 0) ? peek(ready_kt + 1) : 0;
+            compute(s % DF_NSTAGE);
+            if (tid == 0) ready_s[(s + 1) & 1] = (seen && confirm(ready_kt + 1)) ? ready_kt + 1 : ready_kt;
         }
+        }
+        tile_bar<WS>();                               // every warp is out of the last slab: shared memory is free for the epilogue
+        if (WS && !ok) { if (tid == 0) abort_s = 1; continue; }
 
         // ---- epilogue ----
+        if (tracing) t_loop += clock64() - t_loop0;
         if (chain) df_stamp(g.trace, idx, 0);
         double* Xs = df_smem;                 // [64][68]  X = C - acc   (later: the diagonal tile S)
         double* Ws = df_smem + DF_TILE;       // [64][68]  W_cc
         double* Ls = df_smem + 2 * DF_TILE;   // [64][68]  L_{i,c} of a chain task
         double* Wcc = g.W + (int64_t)(c > 0 ? c : 0) * PB * (g.ldw + 1);
-        int* myflag = rhs ? g.flagsY + (int64_t)c * g.nr + idx : g.flagsL + (int64_t)i * g.nb + (c > 0 ? c : 0);
-        if (!(chain && idx == 0)) {
+        int* myflag = gram ? mflag : (rhs ? g.flagsY + (int64_t)c * g.nr + idx : g.flagsL + (int64_t)i * g.nb + (c > 0 ? c : 0));
+        if (gram) {                                   // the tile's sum over groups 0 .. gi, back in place
+#pragma unroll
+            for (int x = 0; x < 2; x++)
+#pragma unroll
+                for (int y = 0; y < 4; y++) {
+                    const int r = wm + x * 32 + gq, cc = wn + y * 16 + tq * 2;
+                    double2 v;
+                    v.x = acc[x][y][0]; v.y = acc[x][y][1];
+                    *reinterpret_cast<double2*>(Ct + (int64_t)r * ldc + cc) = v;
+                }
+        } else if (!(chain && idx == 0)) {
 #pragma unroll
             for (int x = 0; x < 2; x++)
 #pragma unroll
@@ -487,11 +718,13 @@ __global__ void __launch_bounds__(DF_THREADS, 2) chol_dataflow_kernel(DfArgs g) 
                     Xs[r * DF_LDT + cc + 1] = -acc[x][y][1];
                     acc[x][y][0] = acc[x][y][1] = 0.0;
                 }
+            if (tracing) t_mark = clock64();
             if (warp == 0) {
                 const bool w = df_wait(g.flagsL + (int64_t)c * g.nb + c, g.ctrl, g.info, g.spin_limit);
                 if (lane == 0) ready_s[2] = w ? 1 : 0;
             }
-            __syncthreads();                          // X is in shared memory, W_cc is final (warp 0 acquired its flag)
+            tile_bar<WS>();                          // X is in shared memory, W_cc is final (warp 0 acquired its flag)
+            if (tracing) t_wait += clock64() - t_mark;
             const bool okd = ready_s[2] != 0;
             if (chain && tid == 0) df_st_relaxed(my_pause, 1);
             if (chain) df_stamp(g.trace, idx, 1);
@@ -502,9 +735,12 @@ __global__ void __launch_bounds__(DF_THREADS, 2) chol_dataflow_kernel(DfArgs g) 
             }
             cp_async_commit();
             cp_async_wait<0>();
-            if (__syncthreads_or(!okd)) {
+            tile_bar<WS>();
+            if (!okd) {                               // abort raised (uniform: okd came through shared memory)
                 if (chain && tid == 0) df_st_relaxed(my_pause, 0);
-                return;
+                if (!WS) return;
+                if (tid == 0) abort_s = 1;
+                continue;
             }
             if (chain) df_stamp(g.trace, idx, 2);
 #pragma unroll 4
@@ -547,7 +783,7 @@ __global__ void __launch_bounds__(DF_THREADS, 2) chol_dataflow_kernel(DfArgs g) 
             double* Wd = g.W + (int64_t)idx * PB * (g.ldw + 1);
             df_stamp(g.trace, idx, 3);
             if (idx > 0) {
-                __syncthreads();                      // L_{i,c} complete in shared memory; X is free
+                tile_bar<WS>();                      // L_{i,c} complete in shared memory; X is free
 #pragma unroll 4
                 for (int kk = 0; kk < PB; kk += 4) {  // acc2 += L_ic L_ic^T
                     double a[2], b[4];
@@ -571,20 +807,23 @@ __global__ void __launch_bounds__(DF_THREADS, 2) chol_dataflow_kernel(DfArgs g) 
                     Xs[r * DF_LDT + cc + 1] = -acc2[x][y][1];
                 }
             if (idx > 0) {                            // publish the sub-diagonal tile before the long factor step
-                __syncthreads();                      // (release by one thread after the barrier covers the CTA's writes)
+                tile_bar<WS>();                      // (release by one thread after the barrier covers the CTA's writes)
                 if (tid == 0) df_st_release(myflag, 1);
             } else {
-                __syncthreads();
+                tile_bar<WS>();
             }
             df_stamp(g.trace, idx, 4);
-            potrf_diag_body(Xs, DF_LDT, Cd, g.ld, Wd, g.ldw, g.info, idx, reinterpret_cast<PotrfScratch*>(Ws));      // W_cc is spent
+            potrf_diag_body<WS>(Xs, DF_LDT, Cd, g.ld, Wd, g.ldw, g.info, idx, reinterpret_cast<PotrfScratch*>(Ws));      // W_cc is spent
             myflag = g.flagsL + (int64_t)idx * g.nb + idx;
             df_stamp(g.trace, idx, 5);
         }
-        __syncthreads();
+        tile_bar<WS>();
         if (tid == 0) {
             df_st_release(myflag, 1);                 // cumulative: covers the tile stores of every thread before the barrier
-            if (chain) df_st_relaxed(my_pause, 0);
+            if (chain) {
+                df_st_relaxed(my_pause, 0);
+                if (g.M != nullptr) atomicMax(g.ctrl + 3, idx + 1);       // diagonal blocks factored (the Gram queue's gate)
+            }
         }
         if (chain) df_stamp(g.trace, idx, 6);
     }
@@ -629,11 +868,17 @@ extern "C" int64_t mfgp_npad(int64_t n) {
 // Synchronisation scratch of chol_dataflow_kernel: ticket counter + abort flag, per-SM pause flags, one ready flag per
 // 64x64 tile of L and of Y.  It lives in CALLER-provided workspace (so two models may factorise concurrently on different
 // streams of one device, and nothing is allocated inside the library).
-static int64_t df_scratch_ints(int64_t npad, int64_t R) {
+constexpr int DF_CTRL_INTS = 16;         // ticket counters, abort flag, progress gauges (DfArgs::ctrl)
+constexpr int DF_MIN_MG = 2;             // smallest group of block rows of a Gram task (sizes the flag array)
+static int64_t df_scratch_ints(int64_t npad, int64_t R, bool gram = false) {
     const int64_t nb = npad / PB, nr = (R + PB - 1) / PB;
-    return 2 + 1024 + nb * nb + nb * nr;               // ctrl, per-SM pause flags, L tile flags, Y tile flags
+    int64_t n = DF_CTRL_INTS + 1024 + nb * nb + nb * nr;               // ctrl, per-SM pause flags, L tile flags, Y tile flags
+    if (gram) n += ((nb + DF_MIN_MG - 1) / DF_MIN_MG) * (nr * (nr + 1) / 2);   // Gram tile flags per group of block rows
+    return n;
 }
-static int64_t df_scratch_bytes(int64_t npad, int64_t R) { return (df_scratch_ints(npad, R) * 4 + 255) / 256 * 256; }
+static int64_t df_scratch_bytes(int64_t npad, int64_t R, bool gram = false) {
+    return (df_scratch_ints(npad, R, gram) * 4 + 255) / 256 * 256;
+}
 
 extern "C" int64_t mfgp_workspace_bytes(int64_t npad) {
     // T blocks of the inverse (npad^2/4 doubles) + one 64x64 block, then the tile flags of mfgp_cholesky
@@ -641,6 +886,7 @@ extern "C" int64_t mfgp_workspace_bytes(int64_t npad) {
 }
 
 extern "C" int64_t mfgp_cholesky_solve_workspace_bytes(int64_t npad, int64_t R) { return df_scratch_bytes(npad, R); }
+extern "C" int64_t mfgp_cholesky_solve_gram_workspace_bytes(int64_t npad, int64_t R) { return df_scratch_bytes(npad, R, true); }
 
 extern "C" int mfgp_build_train_cov(const double* Xt, int64_t NL, int64_t NH, const mfgp_params* p_host, double* K,
                                     int64_t npad, int64_t ld, double* Tt, void* stream) {
@@ -690,6 +936,7 @@ namespace {
 struct DfScratch {        // diagnostics (MFGP_DF_TRACE=1) and the cached SM count only; no data-path state
     long long* trace = nullptr;
     int trace_nb = 0;
+    int trace_grid = 0;
     int sms = 0;
 };
 DfScratch g_df[16];
@@ -705,24 +952,39 @@ bool use_panel_chain() {
 // One launch: K -> L (lower, in place), diagonal blocks of W -> inverses of L's diagonal blocks, Bm[npad, R] -> L^-1 Bm
 // (R may be 0).  The ready flags live in `scratch` (df_scratch_bytes(npad, R) bytes of caller workspace), zeroed on `st`.
 int chol_dataflow(double* K, int64_t npad, int64_t ld, double* W, int64_t ldw, int32_t* info, double* Bm, int64_t ldb, int64_t R,
-                  int* scratch, cudaStream_t st) {
+                  double* M, int64_t ldm, int* scratch, cudaStream_t st) {
     int dev = 0;
     MFGP_CUDA_CHECK(cudaGetDevice(&dev));
     if (dev < 0 || dev >= 16 || !scratch) return MFGP_ERR_INVALID;
     DfScratch& sc = g_df[dev];
     const int nb = (int)(npad / PB), nr = (int)(R / PB);
-    const int64_t need = df_scratch_ints(npad, R);                            // ctrl, per-SM pause flags, tile flags
+    const int64_t need = df_scratch_ints(npad, R, M != nullptr);              // ctrl, per-SM pause flags, tile flags
     if (!sc.sms) MFGP_CUDA_CHECK(cudaDeviceGetAttribute(&sc.sms, cudaDevAttrMultiProcessorCount, dev));
     MFGP_CUDA_CHECK(cudaMemsetAsync(scratch, 0, need * sizeof(int), st));
     MFGP_CUDA_CHECK(cudaMemsetAsync(info, 0, sizeof(int32_t), st));
+    // diagnostics (MFGP_DF_NODEP=1): every tile flag preset, i.e. the same tasks with no waiting -- the results are garbage,
+    // the time is the throughput ceiling of the tile loops for this task mix
+    static const bool nodep = [] { const char* e = getenv("MFGP_DF_NODEP"); return e && atoi(e) != 0; }();
+    if (nodep) MFGP_CUDA_CHECK(cudaMemsetAsync(scratch + DF_CTRL_INTS + 1024, 1, (need - DF_CTRL_INTS - 1024) * sizeof(int), st));
     DfArgs a{};
     a.K = K; a.ld = ld; a.W = W; a.ldw = ldw; a.Bm = Bm; a.ldb = ldb; a.nb = nb; a.nr = nr; a.info = info;
-    a.ctrl = scratch; a.pause = scratch + 2; a.flagsL = scratch + 1026; a.flagsY = scratch + 1026 + (int64_t)nb * nb;
+    a.ctrl = scratch; a.pause = scratch + DF_CTRL_INTS; a.flagsL = a.pause + 1024; a.flagsY = a.flagsL + (int64_t)nb * nb;
     a.total = nb + (nb - 1) * (nb - 2) / 2 + nb * nr;     // nb chain tasks, the tiles two or more below the diagonal, Y tiles
+    if (M != nullptr && nr > 0) {
+        // Gram tasks: groups of mg block rows (short tasks fill the chain-bound tail better; every task re-reads and re-writes
+        // its 32 KB tile of M), drawn only while the critical queue is m_lead block columns ahead of the chain
+        static const int mg_env = [] { const char* e = getenv("MFGP_DF_MG"); return e ? atoi(e) : 8; }();
+        static const int lead_env = [] { const char* e = getenv("MFGP_DF_MLEAD"); return e ? atoi(e) : 8; }();
+        a.M = M; a.ldm = ldm; a.flagsM = a.flagsY + (int64_t)nb * nr;
+        a.mg = mg_env < DF_MIN_MG ? DF_MIN_MG : mg_env;
+        a.m_tiles = nr * (nr + 1) / 2;
+        a.m_total = (nb + a.mg - 1) / a.mg * a.m_tiles;
+        a.m_lead = lead_env;
+    }
     static const bool want_trace = [] { const char* e = getenv("MFGP_DF_TRACE"); return e && atoi(e) != 0; }();
     if (want_trace) {
-        if (!sc.trace) MFGP_CUDA_CHECK(cudaMalloc(&sc.trace, 1024 * 16 * sizeof(long long)));
-        MFGP_CUDA_CHECK(cudaMemsetAsync(sc.trace, 0, 1024 * 16 * sizeof(long long), st));
+        if (!sc.trace) MFGP_CUDA_CHECK(cudaMalloc(&sc.trace, 1024 * 24 * sizeof(long long)));
+        MFGP_CUDA_CHECK(cudaMemsetAsync(sc.trace, 0, 1024 * 24 * sizeof(long long), st));
         a.trace = nb <= 1024 ? sc.trace : nullptr;
         sc.trace_nb = nb;
     }
@@ -731,10 +993,14 @@ int chol_dataflow(double* K, int64_t npad, int64_t ld, double* W, int64_t ldw, i
     a.spin_limit = 4000000000LL;      // ~2 s of SM clocks: only a bug can get there
     constexpr int smem = DF_SMEM_DOUBLES * sizeof(double);
     static const int occ = [] { const char* e = getenv("MFGP_DF_OCC"); return e ? atoi(e) : 2; }();
-    MFGP_CUDA_CHECK(cudaFuncSetAttribute(chol_dataflow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    static const bool ws = [] { const char* e = getenv("MFGP_DF_WS"); return e ? atoi(e) != 0 : false; }();
+    MFGP_CUDA_CHECK(cudaFuncSetAttribute(chol_dataflow_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    MFGP_CUDA_CHECK(cudaFuncSetAttribute(chol_dataflow_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     int grid = (occ < 1 ? 1 : occ) * sc.sms;
-    if (grid > a.total) grid = a.total;
-    chol_dataflow_kernel<<<grid, DF_THREADS, smem, st>>>(a);
+    if (grid > a.total + a.m_total) grid = a.total + a.m_total;
+    sc.trace_grid = grid < 1024 ? grid : 1024;
+    if (ws) chol_dataflow_kernel<true><<<grid, DF_WS_THREADS, smem, st>>>(a);
+    else chol_dataflow_kernel<false><<<grid, DF_THREADS, smem, st>>>(a);
     MFGP_LAUNCH_CHECK();
     return MFGP_OK;
 }
@@ -747,6 +1013,10 @@ extern "C" int64_t mfgp_debug_chol_trace(int64_t* out, int64_t max_tasks) {
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return 0;
     DfScratch& sc = g_df[dev];
     if (!sc.trace || !out) return 0;
+    if (max_tasks < 0) {      // per-CTA accounting: out[1024][8] = {wait clocks, k-loop clocks, total clocks, tasks, exit time ns, SM}
+        if (cudaMemcpy(out, sc.trace + 1024 * 16, 1024 * 8 * sizeof(long long), cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
+        return sc.trace_grid;
+    }
     int64_t n = sc.trace_nb < max_tasks ? sc.trace_nb : max_tasks;
     if (cudaMemcpy(out, sc.trace, n * 16 * sizeof(long long), cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
     return n;
@@ -762,7 +1032,7 @@ extern "C" int mfgp_cholesky(double* K, int64_t npad, int64_t ld, double* W, int
         if (!work) return MFGP_ERR_INVALID;
         // the tile flags sit behind the part of `work` that mfgp_tri_inverse uses (see mfgp_workspace_bytes)
         int* scratch = reinterpret_cast<int*>(static_cast<char*>(work) + npad * npad * 2 + (int64_t)PB * PB * 8 + 256);
-        return chol_dataflow(K, npad, ld, W, ldw, info, nullptr, 0, 0, scratch, st);
+        return chol_dataflow(K, npad, ld, W, ldw, info, nullptr, 0, 0, nullptr, 0, scratch, st);
     }
     MFGP_CUDA_CHECK(cudaMemsetAsync(info, 0, sizeof(int32_t), st));
     const int nb = (int)(npad / PB);
@@ -807,7 +1077,7 @@ extern "C" int mfgp_cholesky_solve(double* K, int64_t npad, int64_t ld, double* 
     cudaStream_t caller = static_cast<cudaStream_t>(stream);
     if (!use_panel_chain()) {
         if (!work || work_bytes < df_scratch_bytes(npad, R)) return MFGP_ERR_INVALID;
-        return chol_dataflow(K, npad, ld, W, ldw, info, Bm, ldb, R, static_cast<int*>(work), caller);
+        return chol_dataflow(K, npad, ld, W, ldw, info, Bm, ldb, R, nullptr, 0, static_cast<int*>(work), caller);
     }
     SideStream* side = nullptr;
     int rcs = side_for_current_device(&side);
@@ -860,6 +1130,29 @@ extern "C" int mfgp_cholesky_solve(double* K, int64_t npad, int64_t ld, double* 
     MFGP_CUDA_CHECK(cudaEventRecord(side->ev_end, st));               // the caller's stream resumes when the chain is done too
     MFGP_CUDA_CHECK(cudaStreamWaitEvent(caller, side->ev_end, 0));
     return MFGP_OK;
+}
+
+// mfgp_cholesky_solve that ALSO leaves M = Y^T Y of the solved right-hand sides (R x R, row stride ldm >= R; the 64x64 tiles on
+// and below the diagonal) -- the Gram route of the factored posterior needs exactly that product.  Its tiles are accumulated by
+// low-priority tasks of the same tile-dataflow kernel, group of block rows by group of block rows in a fixed order (so M is
+// deterministic), in the CTA slots the factorisation leaves idle while it waits on its chain of diagonal blocks.
+extern "C" int mfgp_cholesky_solve_gram(double* K, int64_t npad, int64_t ld, double* W, int64_t ldw, int32_t* info, double* Bm,
+                                        int64_t ldb, int64_t R, double* M, int64_t ldm, void* work, int64_t work_bytes,
+                                        void* stream) {
+    if (!M) return mfgp_cholesky_solve(K, npad, ld, W, ldw, info, Bm, ldb, R, work, work_bytes, stream);
+    if (!K || !W || !info || !Bm || npad <= 0 || npad % MFGP_TILE || ld < npad || ldw < npad || R <= 0 || R % GT || ldb < R || ldm < R)
+        return MFGP_ERR_INVALID;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (!use_panel_chain()) {
+        if (!work || work_bytes < df_scratch_bytes(npad, R, true)) return MFGP_ERR_INVALID;
+        return chol_dataflow(K, npad, ld, W, ldw, info, Bm, ldb, R, M, ldm, static_cast<int*>(work), st);
+    }
+    int rc = mfgp_cholesky_solve(K, npad, ld, W, ldw, info, Bm, ldb, R, work, work_bytes, stream);
+    if (rc) return rc;
+    GemmArgs gm{};
+    gm.A = Bm; gm.lda = ldb; gm.B = Bm; gm.ldb = ldb; gm.C = M; gm.ldc = ldm;
+    gm.M = (int)R; gm.N = (int)R; gm.K = (int)npad; gm.alpha = 1.0; gm.beta = 0.0; gm.mode = GEMM_SYRK_LOWER;
+    return launch_syrk_ata(gm, 1, st);
 }
 
 extern "C" int mfgp_tri_inverse(const double* L, int64_t npad, int64_t ld, double* W, int64_t ldw, void* work,

@@ -133,6 +133,102 @@ def task_dependencies(task):
     return deps
 
 
+def gram_tasks(nb, nr, mg):
+    """Gram tickets of mfgp_cholesky_solve_gram in ticket order: group-major, then the lower tiles (ti, tj) of M = Y^T Y row by
+    row.  Task (g, ti, tj) adds the block rows [g mg, min(nb, (g+1) mg)) of Y to the tile, in place."""
+    tiles = [(ti, tj) for ti in range(nr) for tj in range(ti + 1)]
+    return [("M", g, ti, tj) for g in range((nb + mg - 1) // mg) for (ti, tj) in tiles]
+
+
+def gram_dependencies(task, nb, mg):
+    """What a Gram task waits for: the Y tiles of its block rows in both tile columns, and the same tile of the group before."""
+    _, g, ti, tj = task
+    deps = []
+    for k in range(g * mg, min(nb, (g + 1) * mg)):
+        deps += [("Y", k, ti), ("Y", k, tj)]
+    if g > 0:
+        deps.append(("M", g - 1, ti, tj))
+    return deps
+
+
+def simulate_two_queues(nb, nr, mg, m_lead, ncta, rng, chain_la=5, max_steps=None):
+    """Event simulation of the kernel's two-queue policy (chol_dataflow_kernel, thread 0 of every CTA) under an ADVERSARIAL
+    interleaving: at every step ONE randomly chosen CTA acts -- it finishes its task if the task's dependencies are done,
+    otherwise it idles; a free CTA draws by the kernel's rule:
+      * a Gram ticket may be CLAIMED when the next one is runnable and the critical queue is >= m_lead columns ahead of the
+        chain (or empty); runnable = critical queue empty, or a critical ticket of a column behind the group's last row was
+        drawn AND the chain is two diagonal blocks past that row;
+      * a claimed ticket that is not runnable (lost race at a group boundary: modelled by claiming WITHOUT the check with
+        probability 1/4) is held while the CTA takes critical tickets.
+    Returns the completion order; raises AssertionError on deadlock (no CTA can act and work is left)."""
+    crit = task_order(nb, nr, chain_la)
+    col_of = {}
+    c = 0
+    dnext = 1
+    col_of[("chain", 0)] = 0
+    for cc in range(nb):
+        while dnext < nb and chain_place(dnext, chain_la) == cc:
+            col_of[("chain", dnext)] = cc
+            dnext += 1
+        for i in range(cc + 2, nb):
+            col_of[("L", i, cc)] = cc
+        for r in range(nr):
+            col_of[("Y", cc, r)] = cc
+    gram = gram_tasks(nb, nr, mg)
+    deps = {t: [producer_of(d) for d in task_dependencies(t)] for t in crit}
+    deps.update({t: gram_dependencies(t, nb, mg) for t in gram})
+    done, order = set(), []
+    nc = nm = 0                 # ticket counters
+    front = drawn = 0           # ctrl[3], ctrl[4]
+    held = [None] * ncta        # deferred Gram ticket per CTA
+    running = [None] * ncta
+    total = len(crit) + len(gram)
+    steps = 0
+    limit = max_steps or 400 * total + 1000
+    idle_streak = 0
+
+    def runnable(t):
+        g = t[1]
+        last_row = min(nb, (g + 1) * mg) - 1
+        return nc >= len(crit) or (drawn > last_row and last_row + 2 <= front)
+
+    while len(done) < total:
+        steps += 1
+        assert steps < limit, "no progress"
+        k = int(rng.integers(ncta))
+        if running[k] is not None:
+            t = running[k]
+            if all(d in done for d in deps[t]):
+                done.add(t)
+                order.append(t)
+                running[k] = None
+                if t[0] == "chain":
+                    front = max(front, t[1] + 1)
+                idle_streak = 0
+            else:
+                idle_streak += 1
+                assert idle_streak < 50 * ncta * 50, ("deadlock", [r for r in running if r][:6])
+            continue
+        # free CTA: the kernel's selection loop (one pass)
+        crit_left = nc < len(crit)
+        if held[k] is None and nm < len(gram):
+            nxt = gram[nm]
+            lost_race = rng.integers(4) == 0
+            if (runnable(nxt) or lost_race) and (not crit_left or drawn - front >= m_lead or lost_race):
+                held[k] = nxt
+                nm += 1
+        if held[k] is not None and runnable(held[k]):
+            running[k], held[k] = held[k], None
+            continue
+        if crit_left:
+            t = crit[nc]
+            nc += 1
+            running[k] = t
+            drawn = max(drawn, col_of[t])
+            continue
+    return order
+
+
 def bordered_inverse_append(W, z, k_cols, k_nn, yc_new):
     """The block-bordered update behind mfgp_batch_step (mfgp-coverage_b200/csrc/batched.cu, batch_append_kernel): q samples
     are appended to a model whose factor is held as W = L^-1 (N x N, lower) and z = W (y - m).

@@ -93,6 +93,52 @@ def test_kernel_matrix_of_the_workload():
     assert np.max(np.abs(L @ L.T - Kfull)) <= 1e-13 * np.max(np.abs(Kfull))
 
 
+@pytest.mark.parametrize("n,R", [(64, 64), (100, 128), (700, 320), (1500, 192), (2100, 448)])
+def test_solve_with_fused_gram_product(n, R):
+    """mfgp_cholesky_solve_gram: same factor and solution as mfgp_cholesky_solve, plus M = Y^T Y (tiles on and below the
+    diagonal; the tiles above are not touched) accumulated by the Gram tasks of the same kernel -- against numpy, and bitwise
+    the same on a second call (the groups of block rows are added in a fixed order whatever the scheduling)."""
+    nat, lib = _lib()
+    Kh = _spd(n, n + 1)
+    npad = int(lib.mfgp_npad(n))
+    Kp = np.eye(npad)
+    Kp[:n, :n] = Kh
+    B0 = np.random.default_rng(n).standard_normal((npad, R))
+    st = nat.stream_ptr()
+    sw = torch.empty(int(lib.mfgp_cholesky_solve_gram_workspace_bytes(npad, R)) // 8 + 8, dtype=torch.float64, device="cuda")
+    out = []
+    for rep in range(2):
+        K = torch.from_numpy(Kp).cuda()
+        B = torch.from_numpy(B0).cuda()
+        W = torch.zeros((npad, npad), dtype=torch.float64, device="cuda")
+        M = torch.full((R, R), np.nan, dtype=torch.float64, device="cuda")
+        info = torch.zeros(1, dtype=torch.int32, device="cuda")
+        nat.check(lib.mfgp_cholesky_solve_gram(nat.ptr(K), npad, npad, nat.ptr(W), npad, nat.ptr(info), nat.ptr(B), R, R,
+                                               nat.ptr(M), R, nat.ptr(sw), sw.numel() * 8, st), "mfgp_cholesky_solve_gram")
+        torch.cuda.synchronize()
+        assert int(info.item()) == 0
+        out.append((np.tril(K.cpu().numpy()), B.cpu().numpy(), M.cpu().numpy()))
+    L, Y, M = out[0]
+    Lref = np.linalg.cholesky(Kp)
+    Yref = sl.solve_triangular(Lref, B0, lower=True)
+    assert np.max(np.abs(L - Lref)) <= 1e-11 * np.max(np.abs(Lref))
+    assert np.max(np.abs(Y - Yref)) <= 1e-9 * np.max(np.abs(Yref))
+    blk = np.arange(R) // 64
+    low = blk[:, None] >= blk[None, :]
+    Mref = Y.T @ Y
+    assert np.all(np.isnan(M[~low]))
+    assert np.max(np.abs(M[low] - Mref[low])) <= 1e-12 * np.max(np.abs(Mref))
+    assert np.array_equal(M[low], out[1][2][low]) and np.array_equal(Y, out[1][1])
+    # and the plain entry point is what M == NULL means
+    K = torch.from_numpy(Kp).cuda(); B = torch.from_numpy(B0).cuda()
+    W = torch.zeros((npad, npad), dtype=torch.float64, device="cuda")
+    info = torch.zeros(1, dtype=torch.int32, device="cuda")
+    nat.check(lib.mfgp_cholesky_solve_gram(nat.ptr(K), npad, npad, nat.ptr(W), npad, nat.ptr(info), nat.ptr(B), R, R,
+                                           None, 0, nat.ptr(sw), sw.numel() * 8, st), "mfgp_cholesky_solve_gram")
+    torch.cuda.synchronize()
+    assert np.array_equal(B.cpu().numpy(), Y)
+
+
 @pytest.mark.parametrize("n,bad", [(64, 0), (64, 5), (64, 38), (200, 70), (200, 129), (500, 448), (500, 499)])
 def test_first_non_positive_pivot_is_reported_like_lapack(n, bad):
     """np.linalg.cholesky raises on the first non-positive pivot; dpotrf's info names it (1-based) and so does `info` here."""

@@ -205,6 +205,25 @@ def test_dataflow_ticket_order_with_chain_lookahead_cannot_deadlock():
         assert len(done) == len(order)
 
 
+def test_two_queue_gram_policy_cannot_deadlock_and_keeps_group_order():
+    """mfgp_cholesky_solve_gram: the Gram tasks (M = Y^T Y per group of block rows) ride in a second ticket queue of the same
+    kernel.  Restated policy under adversarial random interleavings, lost races at group boundaries included, with very few
+    CTAs: every task completes (no CTA ever waits on a task nobody has drawn) and every tile of M receives its groups in
+    order -- which is what makes M bitwise reproducible."""
+    from oracle import tiled_cholesky as tc
+    rng = np.random.default_rng(11)
+    for nb, nr, mg, lead, ncta in ((4, 1, 2, 0, 2), (9, 2, 2, 3, 3), (16, 3, 4, 8, 4), (16, 2, 8, 2, 5), (24, 2, 4, 4, 7), (12, 3, 16, 1, 3)):
+        order = tc.simulate_two_queues(nb, nr, mg, lead, max(ncta, nb // 5 + 3), rng)
+        ngroups = (nb + mg - 1) // mg
+        assert len(order) == len(set(order)) == nb + (nb - 1) * (nb - 2) // 2 + nb * nr + ngroups * nr * (nr + 1) // 2
+        seen = {}
+        for t in order:
+            if t[0] == "M":
+                assert seen.get(t[2:], -1) == t[1] - 1, t
+                seen[t[2:]] = t[1]
+        assert all(v == ngroups - 1 for v in seen.values())
+
+
 def test_vectorised_finishing_is_bitwise_the_reference_loop():
     """loss_from_partials / centroids_from_partials are elementwise over the cells; they must give bit for bit what the
     reference's per-cell statements give (simulator.py:215-219, :256-271), empty cells (0/0 -> NaN) included."""
