@@ -78,15 +78,6 @@ struct PotrfScratch {
     int bad;
 };
 
-// barrier of the 256 threads that work on a tile: the whole CTA, or (NAMED: the warp-specialised dataflow kernel, whose CTA
-// has a ninth, producer warp) named barrier 1
-template <bool NAMED>
-__device__ __forceinline__ void tile_bar() {
-    if (NAMED) asm volatile("bar.sync 1, 256;\n" ::: "memory");
-    else __syncthreads();
-}
-
-template <bool NAMED = false>
 __device__ __forceinline__ void potrf_diag_body(const double* src, int64_t lds, double* A, int64_t ld,
                                                 double* __restrict__ Winv, int64_t ldw, int32_t* __restrict__ info, int jblk,
                                                 PotrfScratch* sc) {
@@ -122,7 +113,7 @@ __device__ __forceinline__ void potrf_diag_body(const double* src, int64_t lds, 
 #pragma unroll
                 for (int b = 0; b < 4; b++) dst[2 * (tc + 16 * b)] = m[jb][b];
             }
-            tile_bar<NAMED>();
+            __syncthreads();
             const double2* col = colAB[buf];
             const double2* row = rowAB[buf];
             double pa = col[j0].x;
@@ -171,7 +162,7 @@ __device__ __forceinline__ void potrf_diag_body(const double* src, int64_t lds, 
             }
         }
     }
-    tile_bar<NAMED>();
+    __syncthreads();
     if (tid < PB / 2) {          // C = chol(P) of every pair
         const double a = piv[0][tid], b = piv[1][tid], c = piv[2][tid];
         const double r1 = rsqrt(a);
@@ -180,7 +171,7 @@ __device__ __forceinline__ void potrf_diag_body(const double* src, int64_t lds, 
         fin[1][tid] = rsqrt(fma(-g, b, c));
         fin[2][tid] = g;
     }
-    tile_bar<NAMED>();
+    __syncthreads();
     const bool failed = bad != 0;
 #pragma unroll
     for (int a = 0; a < 4; a++)
@@ -297,59 +288,14 @@ __device__ __forceinline__ bool df_wait(const int* f, int* ctrl, int32_t* info, 
     return ok != 0;
 }
 
-// mbarrier / bulk-copy primitives of the warp-specialised variant
-__device__ __forceinline__ uint32_t df_smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
-__device__ __forceinline__ void df_mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void df_mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void df_mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void df_mbar_wait(uint32_t bar, uint32_t parity) {
-    uint32_t done;
-    do {
-        asm volatile(
-            "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
-            : "=r"(done)
-            : "r"(bar), "r"(parity)
-            : "memory");
-    } while (!done);
-}
-// global -> shared bulk copy (TMA engine), completion counted in bytes on an mbarrier; 16-byte aligned, size % 16 == 0
-__device__ __forceinline__ void df_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(dst), "l"(src),
-                 "r"(bytes), "r"(bar)
-                 : "memory");
-}
-
-// WS = false: 256 threads, every warp stages its share of the slabs (cp.async) and computes, one CTA barrier per slab.
-// WS = true:  288 threads, warp 8 is a PRODUCER -- it polls the tile flags and moves the slabs with bulk copies that complete
-//             on per-stage "full" mbarriers; the 8 consumer warps wait on those, run the DMMA loop and arrive on the stage's
-//             "empty" mbarrier.  No CTA-wide barrier inside the k loop: the warps of a CTA drift apart by up to two slabs
-//             instead of meeting twice per 32 k, and the staging instructions leave the consumers' issue slots.
-constexpr int DF_WS_THREADS = DF_THREADS + 32;
-// 2 CTAs per SM: 128 registers per thread at 256 threads, 112 at 288 (18 warps x 32 x 112 = 64512 of the SM's 65536)
-template <bool WS>
-__global__ void __launch_bounds__(WS ? DF_WS_THREADS : DF_THREADS) __maxnreg__(WS ? 112 : 128) chol_dataflow_kernel(DfArgs g) {
+// (A warp-specialised variant -- ninth warp as producer with mbarrier hand-off, bulk copies or cp.async -- was built and
+// measured this round: correct, but 2.48 ms against 2.07 ms; one warp cannot issue the 2048 16-byte copies of a slab fast enough,
+// and 128 row-sized bulk copies per slab are slower still.  profiles/r02_chol_scheduler_experiments.txt, experiment 12.)
+__global__ void __launch_bounds__(DF_THREADS, 2) chol_dataflow_kernel(DfArgs g) {
     extern __shared__ __align__(16) double df_smem[];
     __shared__ int task[4];
     __shared__ int ready_s[4];
-    __shared__ __align__(8) unsigned long long df_bars[2 * DF_NSTAGE];     // WS: full[stage], empty[stage]
-    __shared__ int abort_s;                                                // WS: a flag wait timed out (bug guard)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const bool producer = WS && warp == DF_THREADS / 32;
-    const uint32_t bar_full = df_smem_u32(&df_bars[0]), bar_empty = df_smem_u32(&df_bars[DF_NSTAGE]);
-    unsigned gs_base = 0;                     // WS: slabs this CTA has moved so far (ring slot = gs % 3, phase = gs / 3)
-    if (WS) {
-        if (tid == 0) {
-            for (int q = 0; q < DF_NSTAGE; q++) { df_mbar_init(bar_full + 8 * q, 1); df_mbar_init(bar_empty + 8 * q, DF_THREADS / 32); }
-            abort_s = 0;
-            asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
-        }
-    }
     // 8 warps as 4 x 2; a warp owns the 8x8 tiles (row tile (warp>>1) + 4x, column tile (warp&1) + 2y), x < 2, y < 4 --
     // interleaved, so that the triangular products of the chain task (W_cc lower, S symmetric) skip about the same share
     // of DMMAs in every warp
@@ -373,9 +319,7 @@ __global__ void __launch_bounds__(WS ? DF_WS_THREADS : DF_THREADS) __maxnreg__(W
     int held_m = -1;                          // thread 0: a Gram ticket claimed before it became runnable
 
     for (;;) {
-        if (WS && !producer) asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // epilogue stores before the next bulk copies
         __syncthreads();                      // the previous task is done with shared memory and task[]
-        if (WS && abort_s) return;            // (uniform: written before the barrier)
         if (tid == 0) {
             int c = 0, kind = -1, idx = 0, aux = 0;
             int t = -1;
@@ -497,38 +441,6 @@ __global__ void __launch_bounds__(WS ? DF_WS_THREADS : DF_THREADS) __maxnreg__(W
         const bool has_tile = gram ? gi > 0 : !(chain && idx == 0);
         int* const mflag = gram ? g.flagsM + (int64_t)gi * g.m_tiles + idx * (idx + 1) / 2 + tj : nullptr;
         const int nslab = nk * (PB / DF_K);
-        if (producer) {
-            // ---- producer warp: flags -> bulk copies of slab s into ring slot (gs_base + s) % 3 -------------------------------
-            for (int s = 0; s < nslab; s++) {
-                if ((s & 1) == 0) {
-                    const int kt = s >> 1;
-                    bool w = df_wait(fa + (int64_t)kt * fas, g.ctrl, g.info, g.spin_limit);
-                    w = df_wait(fb + (int64_t)kt * fbs, g.ctrl, g.info, g.spin_limit) && w;
-                    if (!w && lane == 0) abort_s = 1;          // keep moving (garbage): the consumers must not be left waiting
-                    asm volatile("fence.proxy.async.global;\n" ::: "memory");     // acquired tiles -> reads by the copy engine
-                }
-                const unsigned gs = gs_base + s;
-                const int slot = gs % DF_NSTAGE;
-                if (gs >= DF_NSTAGE) df_mbar_wait(bar_empty + 8 * slot, ((gs / DF_NSTAGE) + 1) & 1);
-                const uint32_t fbar = bar_full + 8 * slot;
-                if (lane == 0) df_mbar_arrive_expect_tx(fbar, 2 * PB * DF_K * 8);
-                __syncwarp();
-                const int k0 = s * DF_K;
-                const uint32_t As = df_smem_u32(As0 + slot * DF_STAGE), Bs = df_smem_u32(Bs0 + slot * DF_STAGE);
-                if (!gram) {
-                    for (int r = lane; r < PB; r += 32) df_bulk_g2s(As + r * DF_LDA * 8, Ag + (int64_t)r * g.ld + k0, DF_K * 8, fbar);
-                } else {
-                    df_bulk_g2s(As + lane * DF_LDT * 8, Ag + (int64_t)(k0 + lane) * g.ldb, PB * 8, fbar);
-                }
-                if (!bkn) {
-                    for (int r = lane; r < PB; r += 32) df_bulk_g2s(Bs + r * DF_LDA * 8, Bg + (int64_t)r * g.ld + k0, DF_K * 8, fbar);
-                } else {
-                    df_bulk_g2s(Bs + lane * DF_LDT * 8, Bg + (int64_t)(k0 + lane) * g.ldb, PB * 8, fbar);
-                }
-            }
-            gs_base += nslab;
-            continue;
-        }
         bool ok = true;
         if (gram && gi > 0) {
             if (tracing) t_mark = clock64();
@@ -536,12 +448,9 @@ __global__ void __launch_bounds__(WS ? DF_WS_THREADS : DF_THREADS) __maxnreg__(W
                 const bool w = df_wait(mflag - g.m_tiles, g.ctrl, g.info, g.spin_limit);
                 if (lane == 0) ready_s[2] = w ? 1 : 0;
             }
-            tile_bar<WS>();
+            __syncthreads();
             if (tracing) t_wait += clock64() - t_mark;
-            if (ready_s[2] == 0) {                    // abort raised (uniform)
-                if (!WS) return;
-                ok = false;                           // WS: the slabs the producer moves must still be consumed
-            }
+            if (ready_s[2] == 0) return;              // abort raised (uniform)
         }
         double acc[2][4][2], acc2[2][4][2];
 #pragma unroll
@@ -632,23 +541,6 @@ __global__ void __launch_bounds__(WS ? DF_WS_THREADS : DF_THREADS) __maxnreg__(W
         };
         int paused = 0;
         const long long t_loop0 = tracing ? clock64() : 0;
-        if (WS) {
-            // ---- consumer warps: wait for the slab, DMMA loop, hand the ring slot back -- no CTA-wide barrier
-            for (int s = 0; s < nslab; s++) {
-                const unsigned gs = gs_base + s;
-                const int slot = gs % DF_NSTAGE;
-                if (lane == 0) {                      // the SM's other CTA is in the tail of a chain task: stand back
-                    while (paused && df_ld_relaxed(my_pause)) __nanosleep(200);
-                    paused = df_ld_relaxed(my_pause);
-                }
-                __syncwarp();
-                df_mbar_wait(bar_full + 8 * slot, (gs / DF_NSTAGE) & 1);
-                compute(slot);
-                __syncwarp();
-                if (lane == 0) df_mbar_arrive(bar_empty + 8 * slot);
-            }
-            gs_base += nslab;
-        } else {
         int staged = 0, ready_kt = -1;                // tiles 0 .. ready_kt are known to be ready (uniform)
         if (tid == 0) ready_s[0] = sample(0) ? 0 : -1;
         __syncthreads();
@@ -686,9 +578,7 @@ __global__ void __launch_bounds__(WS ? DF_WS_THREADS : DF_THREADS) __maxnreg__(W
             compute(s % DF_NSTAGE);
             if (tid == 0) ready_s[(s + 1) & 1] = (seen && confirm(ready_kt + 1)) ? ready_kt + 1 : ready_kt;
         }
-        }
-        tile_bar<WS>();                               // every warp is out of the last slab: shared memory is free for the epilogue
-        if (WS && !ok) { if (tid == 0) abort_s = 1; continue; }
+        __syncthreads();                              // every warp is out of the last slab: shared memory is free for the epilogue
 
         // ---- epilogue ----
         if (tracing) t_loop += clock64() - t_loop0;
@@ -723,7 +613,7 @@ __global__ void __launch_bounds__(WS ? DF_WS_THREADS : DF_THREADS) __maxnreg__(W
                 const bool w = df_wait(g.flagsL + (int64_t)c * g.nb + c, g.ctrl, g.info, g.spin_limit);
                 if (lane == 0) ready_s[2] = w ? 1 : 0;
             }
-            tile_bar<WS>();                          // X is in shared memory, W_cc is final (warp 0 acquired its flag)
+            __syncthreads();                          // X is in shared memory, W_cc is final (warp 0 acquired its flag)
             if (tracing) t_wait += clock64() - t_mark;
             const bool okd = ready_s[2] != 0;
             if (chain && tid == 0) df_st_relaxed(my_pause, 1);
@@ -735,12 +625,10 @@ __global__ void __launch_bounds__(WS ? DF_WS_THREADS : DF_THREADS) __maxnreg__(W
             }
             cp_async_commit();
             cp_async_wait<0>();
-            tile_bar<WS>();
+            __syncthreads();
             if (!okd) {                               // abort raised (uniform: okd came through shared memory)
                 if (chain && tid == 0) df_st_relaxed(my_pause, 0);
-                if (!WS) return;
-                if (tid == 0) abort_s = 1;
-                continue;
+                return;
             }
             if (chain) df_stamp(g.trace, idx, 2);
 #pragma unroll 4
@@ -783,7 +671,7 @@ __global__ void __launch_bounds__(WS ? DF_WS_THREADS : DF_THREADS) __maxnreg__(W
             double* Wd = g.W + (int64_t)idx * PB * (g.ldw + 1);
             df_stamp(g.trace, idx, 3);
             if (idx > 0) {
-                tile_bar<WS>();                      // L_{i,c} complete in shared memory; X is free
+                __syncthreads();                      // L_{i,c} complete in shared memory; X is free
 #pragma unroll 4
                 for (int kk = 0; kk < PB; kk += 4) {  // acc2 += L_ic L_ic^T
                     double a[2], b[4];
@@ -807,17 +695,17 @@ __global__ void __launch_bounds__(WS ? DF_WS_THREADS : DF_THREADS) __maxnreg__(W
                     Xs[r * DF_LDT + cc + 1] = -acc2[x][y][1];
                 }
             if (idx > 0) {                            // publish the sub-diagonal tile before the long factor step
-                tile_bar<WS>();                      // (release by one thread after the barrier covers the CTA's writes)
+                __syncthreads();                      // (release by one thread after the barrier covers the CTA's writes)
                 if (tid == 0) df_st_release(myflag, 1);
             } else {
-                tile_bar<WS>();
+                __syncthreads();
             }
             df_stamp(g.trace, idx, 4);
-            potrf_diag_body<WS>(Xs, DF_LDT, Cd, g.ld, Wd, g.ldw, g.info, idx, reinterpret_cast<PotrfScratch*>(Ws));      // W_cc is spent
+            potrf_diag_body(Xs, DF_LDT, Cd, g.ld, Wd, g.ldw, g.info, idx, reinterpret_cast<PotrfScratch*>(Ws));      // W_cc is spent
             myflag = g.flagsL + (int64_t)idx * g.nb + idx;
             df_stamp(g.trace, idx, 5);
         }
-        tile_bar<WS>();
+        __syncthreads();
         if (tid == 0) {
             df_st_release(myflag, 1);                 // cumulative: covers the tile stores of every thread before the barrier
             if (chain) {
@@ -993,14 +881,11 @@ int chol_dataflow(double* K, int64_t npad, int64_t ld, double* W, int64_t ldw, i
     a.spin_limit = 4000000000LL;      // ~2 s of SM clocks: only a bug can get there
     constexpr int smem = DF_SMEM_DOUBLES * sizeof(double);
     static const int occ = [] { const char* e = getenv("MFGP_DF_OCC"); return e ? atoi(e) : 2; }();
-    static const bool ws = [] { const char* e = getenv("MFGP_DF_WS"); return e ? atoi(e) != 0 : false; }();
-    MFGP_CUDA_CHECK(cudaFuncSetAttribute(chol_dataflow_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    MFGP_CUDA_CHECK(cudaFuncSetAttribute(chol_dataflow_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    MFGP_CUDA_CHECK(cudaFuncSetAttribute(chol_dataflow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     int grid = (occ < 1 ? 1 : occ) * sc.sms;
     if (grid > a.total + a.m_total) grid = a.total + a.m_total;
     sc.trace_grid = grid < 1024 ? grid : 1024;
-    if (ws) chol_dataflow_kernel<true><<<grid, DF_WS_THREADS, smem, st>>>(a);
-    else chol_dataflow_kernel<false><<<grid, DF_THREADS, smem, st>>>(a);
+    chol_dataflow_kernel<<<grid, DF_THREADS, smem, st>>>(a);
     MFGP_LAUNCH_CHECK();
     return MFGP_OK;
 }
