@@ -168,6 +168,21 @@ def ptr(t):
     return None if t is None else c_void_p(t.data_ptr())
 
 
+_side_streams = {}
+
+
+def side_stream(device=None):
+    """A second stream per device for small independent launches (cell clipping, table building) that overlap the main
+    stream's work; joined back with events."""
+    import torch
+    dev = torch.cuda.current_device() if device is None else torch.device(device).index
+    if dev is None:
+        dev = torch.cuda.current_device()
+    if dev not in _side_streams:
+        _side_streams[dev] = torch.cuda.Stream(device=dev)
+    return _side_streams[dev]
+
+
 def stream_ptr(stream=None):
     """cudaStream_t of `stream` (default: torch's current stream on the current device)."""
     import torch

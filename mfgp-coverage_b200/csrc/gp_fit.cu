@@ -237,11 +237,31 @@ struct DfArgs {
     // the same kernel: task (group of mg block rows, tile) adds the group's rows to the tile in place, groups in order
     double* M; int64_t ldm;
     int* flagsM;        // [groups][m_tiles]: the tile holds the sum over groups 0 .. g
-    int mg, m_tiles, m_total, m_lead;
+    int mg, m_full, m_tiles, m_total, m_lead;      // m_full groups of mg block rows, then the rest in halving groups
     long long spin_limit;
     long long* trace;   // diagnostics (MFGP_DF_TRACE=1): 8 timestamps per chain task, else nullptr
     int chain_la;       // chain task d draws its ticket d / chain_la block columns early (0: with its own column)
 };
+
+// Block rows [kb, ke) of Gram group gi: m_full groups of mg rows, then the remaining rows (mg .. 2 mg - 1 of them) in groups that
+// halve down to single rows -- ..., 4, 2, 1, 1 -- so that what is left of the Gram product when the chain of diagonal blocks
+// ends is a two-slab task per tile instead of a 2 mg-slab one.  (Host twin: df_gram_groups.)
+__host__ __device__ __forceinline__ void df_group_rows(int gi, int nb, int mg, int m_full, int& kb, int& ke) {
+    if (gi < m_full) { kb = gi * mg; ke = kb + mg; return; }
+    kb = m_full * mg;
+    int left = nb - kb;
+    for (int j = m_full; ; j++) {
+        const int sz = left > 1 ? (left + 1) / 2 : left;
+        if (j == gi) { ke = kb + sz; return; }
+        kb += sz; left -= sz;
+    }
+}
+__host__ __forceinline__ int df_gram_groups(int nb, int mg, int& m_full) {
+    m_full = nb >= 2 * mg ? (nb - mg) / mg : 0;
+    int left = nb - m_full * mg, n = m_full;
+    while (left > 0) { left -= left > 1 ? (left + 1) / 2 : left; n++; }
+    return n;
+}
 
 __device__ __forceinline__ void df_stamp(long long* trace, int task, int k) {
     if (trace != nullptr && threadIdx.x == 0) {
@@ -317,6 +337,7 @@ __global__ void __launch_bounds__(DF_THREADS, 2) chol_dataflow_kernel(DfArgs g) 
     constexpr bool tracing = false;
 #endif
     int held_m = -1;                          // thread 0: a Gram ticket claimed before it became runnable
+    int dec_c = 0, dec_dnext = 1, dec_base = 1;     // thread 0: ticket decoder state (column, next chain task to place, its first ticket)
 
     for (;;) {
         __syncthreads();                      // the previous task is done with shared memory and task[]
@@ -336,8 +357,9 @@ __global__ void __launch_bounds__(DF_THREADS, 2) chol_dataflow_kernel(DfArgs g) 
                     const int front = df_ld_relaxed(g.ctrl + 3), drawn = df_ld_relaxed(g.ctrl + 4);
                     const bool crit_left = df_ld_relaxed(g.ctrl) < g.total;
                     auto runnable = [&](int tm) {
-                        const int gi = tm / g.m_tiles;
-                        const int last_row = min(g.nb, (gi + 1) * g.mg) - 1;
+                        int kb_, ke_;
+                        df_group_rows(tm / g.m_tiles, g.nb, g.mg, g.m_full, kb_, ke_);
+                        const int last_row = ke_ - 1;
                         return !crit_left || (drawn > last_row && last_row + 2 <= front);
                     };
                     if (held_m < 0) {
@@ -374,25 +396,26 @@ __global__ void __launch_bounds__(DF_THREADS, 2) chol_dataflow_kernel(DfArgs g) 
                 // then waits on a few tiles with later tickets, which the other CTAs go on drawing (at most nb / chain_la + 1
                 // CTAs can ever be in that state).  Measured at N = 4096 with 1344 right-hand sides: 2.47 -> 2.12 ms.  Pulling
                 // the near-diagonal tiles forward as well made it slower (2.14 .. 2.41 ms): they crowd out the bulk.
-                t -= 1;
-                int dnext = 1;                // next chain task not placed yet
+                // (a CTA's tickets only grow: the scan resumes at the column of its previous ticket -- dec_c, dec_dnext, dec_base)
                 for (;;) {
                     int nchain = 0;
-                    while (dnext + nchain < g.nb) {
-                        const int d = dnext + nchain;
+                    while (dec_dnext + nchain < g.nb) {
+                        const int d = dec_dnext + nchain;
                         const int place = max(0, d - 1 - (g.chain_la > 0 ? d / g.chain_la : 0));
-                        if (place != c) break;
+                        if (place != dec_c) break;
                         nchain++;
                     }
-                    const int ntile = g.nb - c - 2 > 0 ? g.nb - c - 2 : 0;
+                    const int ntile = g.nb - dec_c - 2 > 0 ? g.nb - dec_c - 2 : 0;
                     const int n = nchain + ntile + g.nr;
-                    if (t < n) {
-                        if (t < nchain) { kind = 2; idx = dnext + t; }
-                        else if (t < nchain + ntile) { kind = 0; idx = c + 2 + (t - nchain); }
-                        else { kind = 1; idx = t - nchain - ntile; }
+                    if (t < dec_base + n) {
+                        const int tl = t - dec_base;
+                        c = dec_c;
+                        if (tl < nchain) { kind = 2; idx = dec_dnext + tl; }
+                        else if (tl < nchain + ntile) { kind = 0; idx = c + 2 + (tl - nchain); }
+                        else { kind = 1; idx = tl - nchain - ntile; }
                         break;
                     }
-                    t -= n; c++; dnext += nchain;
+                    dec_base += n; dec_c++; dec_dnext += nchain;
                 }
                 if (g.M != nullptr) atomicMax(g.ctrl + 4, c);
             }
@@ -418,9 +441,9 @@ __global__ void __launch_bounds__(DF_THREADS, 2) chol_dataflow_kernel(DfArgs g) 
         const int c = chain ? idx - 1 : (gram ? 0 : task[1]);
         const int i = rhs ? c : idx;
         const int gi = gram ? task[1] : 0, tj = task[3];
-        const int kb = gram ? gi * g.mg : 0;                             // first k tile
-        const int nk = gram ? min(g.nb, kb + g.mg) - kb
-                            : (chain ? (idx > 0 ? idx - 1 : 0) : c);      // k tiles accumulated before the epilogue
+        int kb = 0, ke_g = 0;                                            // Gram task: block rows [kb, ke_g) of Y
+        if (gram) df_group_rows(gi, g.nb, g.mg, g.m_full, kb, ke_g);
+        const int nk = gram ? ke_g - kb : (chain ? (idx > 0 ? idx - 1 : 0) : c);      // k tiles accumulated before the epilogue
         // operands of the k loop: A = L_i,k ([m][k]) or Y_k,ti ([k][m]);  B = L_c,k ([n][k], transposed product) or Y_k,r ([k][n])
         const double* Ag = gram ? g.Bm + (int64_t)kb * PB * g.ldb + (int64_t)idx * PB : g.K + (int64_t)i * PB * g.ld;
         const double* Bg = gram ? g.Bm + (int64_t)kb * PB * g.ldb + (int64_t)tj * PB
@@ -761,7 +784,7 @@ constexpr int DF_MIN_MG = 2;             // smallest group of block rows of a Gr
 static int64_t df_scratch_ints(int64_t npad, int64_t R, bool gram = false) {
     const int64_t nb = npad / PB, nr = (R + PB - 1) / PB;
     int64_t n = DF_CTRL_INTS + 1024 + nb * nb + nb * nr;               // ctrl, per-SM pause flags, L tile flags, Y tile flags
-    if (gram) n += ((nb + DF_MIN_MG - 1) / DF_MIN_MG) * (nr * (nr + 1) / 2);   // Gram tile flags per group of block rows
+    if (gram) n += ((nb + DF_MIN_MG - 1) / DF_MIN_MG + 16) * (nr * (nr + 1) / 2);   // Gram tile flags per group of block rows
     return n;
 }
 static int64_t df_scratch_bytes(int64_t npad, int64_t R, bool gram = false) {
@@ -866,7 +889,7 @@ int chol_dataflow(double* K, int64_t npad, int64_t ld, double* W, int64_t ldw, i
         a.M = M; a.ldm = ldm; a.flagsM = a.flagsY + (int64_t)nb * nr;
         a.mg = mg_env < DF_MIN_MG ? DF_MIN_MG : mg_env;
         a.m_tiles = nr * (nr + 1) / 2;
-        a.m_total = (nb + a.mg - 1) / a.mg * a.m_tiles;
+        a.m_total = df_gram_groups(nb, a.mg, a.m_full) * a.m_tiles;
         a.m_lead = lead_env;
     }
     static const bool want_trace = [] { const char* e = getenv("MFGP_DF_TRACE"); return e && atoi(e) != 0; }();

@@ -30,6 +30,7 @@ import numpy as np
 import torch
 
 from . import _coverage as cv
+from . import _native as nat
 from ._coverage import BoundedVoronoi, CoverageGrid
 from .gaussian_process import MFGP, SFGP, prior_variance
 
@@ -331,6 +332,7 @@ class _Sim:
         self.mu = torch.empty(self.grid.G, **f64)
         self.var = torch.empty(self.grid.G, **f64)
         self._clip = [None, None]
+        self._step_begin = None
         self._index_of = None
 
     def index_of(self):
@@ -348,26 +350,44 @@ class _Sim:
         cell builder -- runs only when that count is non-zero (VORONOI = "auto", see voronoi_bounded) or always
         (VORONOI = "qhull")."""
         bb = self.bounding_box
+
+        def build_cells():
+            if VORONOI == "qhull":       # host Qhull; polygons uploaded afterwards
+                lv, cvor = BoundedVoronoi(positions, bb), BoundedVoronoi(centroids_t, bb)
+                lv.areas()
+                cvor.areas()
+                return lv, cvor
+            # device-built cells (two small kernels per partition), the buffers of the previous iteration are recycled
+            cls = cv.ClippedVoronoi if VORONOI == "clip" else cv.HybridVoronoi
+            lv = cls(positions, bb, reuse=self._clip[0])
+            cvor = cls(centroids_t, bb, reuse=self._clip[1])
+            self._clip = [lv, cvor]
+            return lv, cvor
+
         if model is not None:
             eng = model.engine
+            if self._step_begin is None:
+                self._step_begin = torch.cuda.Event()
+            self._step_begin.record()        # the previous iteration's kernels (readers of the recycled cell buffers) are behind it
             eng.lazy_check = True            # cov_finish / the packed results bring the Cholesky status home: no sync per fit
             eng.defer_fit = True             # a refit fuses with the factored posterior on large tensor grids
             model.predict_device(self.grid.xy, self.mu, self.var, grid=self.grid)       # queued first: the host prepares
-            kw = dict(w=self.mu, var=self.var, amax_k0=prior_variance(model.params()), amax_rel=cv.AMAX_REL)     # the cells
-            info = eng.info                                                             # while the GPU works on it
+            if VORONOI != "qhull" and self._clip[0] is not None:                        # the cells while the GPU works
+                # recycled device buffers: the clip kernels (4 CTAs each) go to a side stream, where they are placed as soon as
+                # the tiled Cholesky's CTAs start to leave the SMs -- inside its tail instead of behind the evaluation kernels
+                main, side = torch.cuda.current_stream(), nat.side_stream(self.grid.device)
+                side.wait_event(self._step_begin)
+                with torch.cuda.stream(side):
+                    loss_vor, lloyd_vor = build_cells()
+                main.wait_stream(side)
+            else:
+                loss_vor, lloyd_vor = build_cells()
+            kw = dict(w=self.mu, var=self.var, amax_k0=prior_variance(model.params()), amax_rel=cv.AMAX_REL)
+            info = eng.info
         else:
             kw = dict(w=weights)
             info = None
-        if VORONOI == "qhull":       # host Qhull; polygons uploaded afterwards
-            loss_vor = BoundedVoronoi(positions, bb)
-            lloyd_vor = BoundedVoronoi(centroids_t, bb)
-            loss_vor.areas()
-            lloyd_vor.areas()
-        else:                        # device-built cells (two small kernels), the buffers of the previous iteration are recycled
-            cls = cv.ClippedVoronoi if VORONOI == "clip" else cv.HybridVoronoi
-            loss_vor = cls(positions, bb, reuse=self._clip[0])
-            lloyd_vor = cls(centroids_t, bb, reuse=self._clip[1])
-            self._clip = [loss_vor, lloyd_vor]
+            loss_vor, lloyd_vor = build_cells()
         device_cells = isinstance(lloyd_vor, cv.ClippedVoronoi) and len(loss_vor) and len(lloyd_vor) and \
             loss_vor.seeds_inside and lloyd_vor.seeds_inside
         if device_cells:

@@ -133,18 +133,33 @@ def task_dependencies(task):
     return deps
 
 
+def gram_group_rows(nb, mg):
+    """Block-row ranges of the Gram groups (df_group_rows / df_gram_groups in csrc/gp_fit.cu): (nb - mg) // mg groups of mg
+    rows, then the remaining mg .. 2 mg - 1 rows in groups that halve down to single rows (..., 4, 2, 1, 1): the work left
+    behind the last diagonal block is one two-slab task per tile."""
+    m_full = (nb - mg) // mg if nb >= 2 * mg else 0
+    out = [(g * mg, (g + 1) * mg) for g in range(m_full)]
+    kb, left = m_full * mg, nb - m_full * mg
+    while left > 0:
+        sz = (left + 1) // 2 if left > 1 else left
+        out.append((kb, kb + sz))
+        kb, left = kb + sz, left - sz
+    return out
+
+
 def gram_tasks(nb, nr, mg):
     """Gram tickets of mfgp_cholesky_solve_gram in ticket order: group-major, then the lower tiles (ti, tj) of M = Y^T Y row by
-    row.  Task (g, ti, tj) adds the block rows [g mg, min(nb, (g+1) mg)) of Y to the tile, in place."""
+    row.  Task (g, ti, tj) adds the block rows of group g (gram_group_rows) of Y to the tile, in place."""
     tiles = [(ti, tj) for ti in range(nr) for tj in range(ti + 1)]
-    return [("M", g, ti, tj) for g in range((nb + mg - 1) // mg) for (ti, tj) in tiles]
+    return [("M", g, ti, tj) for g in range(len(gram_group_rows(nb, mg))) for (ti, tj) in tiles]
 
 
 def gram_dependencies(task, nb, mg):
     """What a Gram task waits for: the Y tiles of its block rows in both tile columns, and the same tile of the group before."""
     _, g, ti, tj = task
+    kb, ke = gram_group_rows(nb, mg)[g]
     deps = []
-    for k in range(g * mg, min(nb, (g + 1) * mg)):
+    for k in range(kb, ke):
         deps += [("Y", k, ti), ("Y", k, tj)]
     if g > 0:
         deps.append(("M", g - 1, ti, tj))
@@ -187,9 +202,10 @@ def simulate_two_queues(nb, nr, mg, m_lead, ncta, rng, chain_la=5, max_steps=Non
     limit = max_steps or 400 * total + 1000
     idle_streak = 0
 
+    rows = gram_group_rows(nb, mg)
+
     def runnable(t):
-        g = t[1]
-        last_row = min(nb, (g + 1) * mg) - 1
+        last_row = rows[t[1]][1] - 1
         return nc >= len(crit) or (drawn > last_row and last_row + 2 <= front)
 
     while len(done) < total:

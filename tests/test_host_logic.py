@@ -214,7 +214,10 @@ def test_two_queue_gram_policy_cannot_deadlock_and_keeps_group_order():
     rng = np.random.default_rng(11)
     for nb, nr, mg, lead, ncta in ((4, 1, 2, 0, 2), (9, 2, 2, 3, 3), (16, 3, 4, 8, 4), (16, 2, 8, 2, 5), (24, 2, 4, 4, 7), (12, 3, 16, 1, 3)):
         order = tc.simulate_two_queues(nb, nr, mg, lead, max(ncta, nb // 5 + 3), rng)
-        ngroups = (nb + mg - 1) // mg
+        rows = tc.gram_group_rows(nb, mg)
+        ngroups = len(rows)
+        assert rows[0][0] == 0 and rows[-1][1] == nb and all(a[1] == b[0] for a, b in zip(rows, rows[1:]))
+        assert rows[-1][1] - rows[-1][0] == 1
         assert len(order) == len(set(order)) == nb + (nb - 1) * (nb - 2) // 2 + nb * nr + ngroups * nr * (nr + 1) // 2
         seen = {}
         for t in order:
