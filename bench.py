@@ -46,11 +46,11 @@ WORKLOADS = {
 # profiles/r01_posterior_v3_ncu_summary.txt (18.883 GB read + 0.040 GB written); algorithmic minimum 32 G + 8 N^2 = 0.17 GB:
 # W (67 MB used) is re-read from L2 by every CTA and only partly stays resident next to the factor tables.
 POSTERIOR_TRAFFIC_C4_1GPU = 18.883344e9 + 39.72864e6
-# DRAM bytes (read + write) of ONE chol_dataflow_kernel launch at c4 (N = 4096, 1344 right-hand-side columns): mean over the 12
-# launches of the ncu pass over this command, profiles/r02_bench_c4_launches.csv (dram__bytes_read.sum 149.2 MB +
-# dram__bytes_write.sum 79.6 MB; the --set full capture of the kernel alone, profiles/r02_chol_dataflow_ncu_summary.txt, has
-# 146.5 + 83.7 MB); algorithmic: lower triangle of K in and L out (2 x 69 MB) + B in and Y out (2 x 44 MB) = 225 MB.
-CHOL_TRAFFIC_C4_1GPU = 149.173184e6 + 79.608341e6
+# DRAM bytes (read + write) of ONE chol_dataflow_kernel launch at c4 (N = 4096, 1344 right-hand-side columns, Gram product in the
+# same launch): mean over the 12 launches of the ncu pass over this command, profiles/r02_bench_c4_launches.csv
+# (dram__bytes_read.sum 148.4 MB + dram__bytes_write.sum 86.5 MB); algorithmic: lower triangle of K in and L out (2 x 69 MB) +
+# B in and Y out (2 x 44 MB) + lower tiles of M out (7.6 MB) = 233 MB.
+CHOL_TRAFFIC_C4_1GPU = 148.371797e6 + 86.466069e6
 DGEMM_PEAK_TFLOPS = 35.41   # cuBLAS DGEMM 8192^3 measured on this pool's B200 (profiles/r01_dgemm_peak.json);
 #                             MEASURED_PEAKS.json carries no FP64 figure.  DMMA issue peak: 37.15 (r01_fp64_pipes.log)
 

@@ -1,11 +1,13 @@
-"""A/B of the two routes of the factored posterior's per-column Gram stage at c4 (MFGP_GRAM=direct|m), whole posterior call."""
+"""A/B of the two routes of the factored posterior's per-column Gram stage at c4 (MFGP_GRAM=direct|m), whole posterior call.
+usage: ab_gram.py [c4] [world=1]"""
 import os, sys, numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from tests import synth
 from mfgp_coverage_b200 import simulator as sim
 import bench
 name = sys.argv[1] if len(sys.argv) > 1 else "c4"
-w = bench.make_workload(name, 1, 0, "strong")
+world = int(sys.argv[2]) if len(sys.argv) > 2 else 1          # > 1: the column slice of rank world // 2 of a strong-scaling run
+w = bench.make_workload(name, world, world // 2, "strong")
 model = sim.init_MFGP(synth.MF_HYP, np.column_stack((w["X_L"], w["y_L"])))
 model.updt_info(w["X_L"], w["y_L"], w["X_H"], w["y_H"])
 eng = model.engine
