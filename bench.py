@@ -71,7 +71,11 @@ def make_workload(name, world=1, rank=0, scaling="weak"):
         ux, uy = np.linspace(0, 1, n), np.linspace(0, 1, n)
         c0, c1 = (rank * n) // world, ((rank + 1) * n) // world
     xy = np.stack(np.meshgrid(ux[c0:c1], uy, indexing="ij"), axis=-1).reshape(-1, 2)
-    return dict(name=name, desc=desc, n=n, N=N, A=A, xy=xy, f=synth.truth_function(xy), ux=ux, uy=uy, lo=c0 * n, hi=c1 * n,
+    # the truth function is normalised over the points it is given: evaluate it on the WHOLE grid and take the rank's slice, so
+    # that every rank count sees the same global function (and the strong-scaling runs report the 1-GPU loss)
+    f = synth.truth_function(np.stack(np.meshgrid(ux, uy, indexing="ij"), axis=-1).reshape(-1, 2))[c0 * n:c1 * n] if world > 1 \
+        else synth.truth_function(xy)
+    return dict(name=name, desc=desc, n=n, N=N, A=A, xy=xy, f=f, ux=ux, uy=uy, lo=c0 * n, hi=c1 * n,
                 G_total=ux.size * uy.size, X_L=X_L, y_L=y_L, X_H=X_H, y_H=y_H, pos=synth.agents(A, 7), cen=synth.agents(A, 8))
 
 

@@ -253,7 +253,11 @@ class DeviceGP:
         if self.lazy_check and not force:
             return
         self.ensure_factor(need_inverse=False)
-        info = int(self.info.item())
+        self.raise_for_info(int(self.info.item()))
+
+    @staticmethod
+    def raise_for_info(info):
+        """The Cholesky status word as the exception the reference raises (np.linalg.cholesky, gaussian_process.py:254, :529)."""
         if info < 0:
             raise RuntimeError("libmfgp_b200: the tiled Cholesky kernel gave up waiting for a tile (internal error)")
         if info != 0:

@@ -99,15 +99,20 @@ def merge_argmax_host(vals, idxs, k0=0.0, rel=0.0):
     return bv, bi
 
 
-def gather_results_to_host(res, group=None, amax_k0=0.0, amax_rel=0.0):
+def gather_results_to_host(res, group=None, amax_k0=0.0, amax_rel=0.0, extras=None):
     """Global per-cell results of CoverageGrid.assign_reduce on the host with ONE collective and ONE device->host copy:
     the packed result buffers of all ranks are all-gathered, copied home, and combined there -- partial sums added in rank
     order (deterministic), arg-max pairs merged with the lowest-global-index rule.  Every rank gets the same dict of numpy
     arrays (cent, amax_val, amax_idx, lossp).  Cheaper than allreduce_partials (two all-reduces, two all-gathers and a
-    handful of small kernels) when the results go to the host anyway, as in the coverage loops."""
+    handful of small kernels) when the results go to the host anyway, as in the coverage loops.
+    `extras`: small float64 device tensors of THIS rank (cell areas, status flags) that ride home in the same copy;
+    returned as out["extras"] (list of numpy arrays)."""
     from ._coverage import CoverageGrid
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
-        return CoverageGrid.results_to_host(res)
+        out = CoverageGrid.results_to_host(res)
+        if extras:
+            out["extras"] = [e.detach().cpu().numpy() for e in extras]
+        return out
     world = dist.get_world_size(group)
     Ac, Ap = res["pack_shape"]
     pack = res["pack"]
@@ -118,13 +123,22 @@ def gather_results_to_host(res, group=None, amax_k0=0.0, amax_rel=0.0):
         parts = [torch.empty_like(pack) for _ in range(world)]
         dist.all_gather(parts, pack, group=group)
         allp = torch.stack(parts)
+    ex_host = None
     if allp.is_cuda:
-        h = torch.empty(allp.shape, dtype=allp.dtype, pin_memory=True)
-        h.copy_(allp, non_blocking=True)
+        flat = torch.cat([allp.reshape(-1)] + [e.reshape(-1) for e in extras]) if extras else allp.reshape(-1)
+        h = torch.empty(flat.shape, dtype=flat.dtype, pin_memory=True)
+        h.copy_(flat, non_blocking=True)
         torch.cuda.current_stream(allp.device).synchronize()
-        a = h.numpy()
+        a = h.numpy()[:allp.numel()].reshape(tuple(allp.shape))
+        if extras:
+            ex_host, o = [], allp.numel()
+            for e in extras:
+                ex_host.append(h.numpy()[o:o + e.numel()])
+                o += e.numel()
     else:
         a = allp.numpy()
+        if extras:
+            ex_host = [e.numpy().reshape(-1) for e in extras]
     out = {"cent": None, "amax_val": None, "amax_idx": None, "lossp": None,
            "ties": int(a[:, 6 * Ac + 2 * Ap:].copy().view(np.int32)[:, 0].sum())}
     if Ac:
@@ -139,6 +153,8 @@ def gather_results_to_host(res, group=None, amax_k0=0.0, amax_rel=0.0):
         for r in range(world):
             lossp += a[r, 6 * Ac:6 * Ac + 2 * Ap].reshape(Ap, 2)
         out["lossp"] = lossp
+    if ex_host is not None:
+        out["extras"] = ex_host
     return out
 
 
@@ -241,11 +257,23 @@ class ShardedSim:
             self._clip = [loss_vor, lloyd_vor]
         k0 = prior_variance(model.params())
         kw = dict(w=self.mu, var=self.var, amax_k0=k0, amax_rel=cv.AMAX_REL)
-        host = gather_results_to_host(self.grid.assign_reduce(lloyd_vor, loss_vor, **kw), self.group, k0, cv.AMAX_REL)
+        extras = None
+        if voronoi != "qhull" and self.grid.xy.is_cuda and len(loss_vor) and len(lloyd_vor):
+            # this rank's cell areas, the clip flags and the Cholesky status ride home in the gathered results' copy
+            extras = [lloyd_vor.dev_areas[:len(lloyd_vor)], loss_vor.dev_areas[:len(loss_vor)],
+                      torch.cat([eng.info.reshape(1), lloyd_vor.flag.reshape(1), loss_vor.flag.reshape(1)]).to(torch.float64)]
+        host = gather_results_to_host(self.grid.assign_reduce(lloyd_vor, loss_vor, **kw), self.group, k0, cv.AMAX_REL, extras)
+        if extras is not None:
+            ac, ap, st = host["extras"]
+            eng.raise_for_info(int(st[0]))
+            if st[1] != 0 or st[2] != 0:
+                raise RuntimeError("cov_voronoi_clip: polygon capacity exceeded")
+            lloyd_vor._areas_host, loss_vor._areas_host = ac.copy(), ap.copy()
         if host["ties"] and voronoi != "qhull":
             loss_vor.qhull(), lloyd_vor.qhull()
             host = gather_results_to_host(self.grid.assign_reduce(lloyd_vor, loss_vor, **kw), self.group, k0, cv.AMAX_REL)
-        eng.check_factor(force=True)
+        if extras is None:
+            eng.check_factor(force=True)
         loss = cv.loss_from_partials(host["lossp"], loss_vor.areas())
         cent = cv.centroids_from_partials(host["cent"], lloyd_vor.areas(), bb[0], bb[1], bb[2], bb[3])
         return loss, cent, host["amax_idx"], host["amax_val"]
