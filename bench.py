@@ -304,6 +304,9 @@ def run_ours(args):
     sampler.start()
     l0 = nat.lib().mfgp_launch_count()
     ms_dev, out = timed_region(lambda: arm.step(True), args.steps)
+    # layout and route of the TIMED steps' fused fit (later sections -- incremental mode -- use other settings)
+    timed_rhs_cols = getattr(arm.eng, "rhs_cols", None)
+    timed_fused_gram = bool(getattr(arm.eng, "fused_gram", False))
     launches = nat.lib().mfgp_launch_count() - l0
     clocks = sampler.result()
     chk = min(npts, 1 << 16)
@@ -448,6 +451,8 @@ def run_ours(args):
         if plan is not None:
             wv = max(plan["ryL"], plan["ryH"])                 # both kernel parts share one Chebyshev basis
             R = wv * max(plan["rxL"], plan["rxH"])
+            if timed_rhs_cols:                                 # truncated column layout: the columns actually carried
+                R = int(timed_rhs_cols[0])
             ncols = plan["ncols"]
             macs = 0.5 * N * N * R + float(ncols) * N * R + float(ncols) * N * wv * wv + float(npts) * wv * wv
             flops = 2.0 * macs + N ** 3 / 3.0
@@ -462,13 +467,14 @@ def run_ours(args):
                 # the dominant kernel of the step: ONE launch factors K and forward-substitutes [B | y - m] (R + 1 columns)
                 km = float(np.mean(chol_ms))
                 kfl = N ** 3 / 3.0 + float(N) * N * (R + 1)
-                fused_gram = bool(getattr(arm.eng, "fused_gram", False))
-                note = "N^3/3 + N^2 (R + 1), R = max rx * max ry"
+                fused_gram = timed_fused_gram
+                note = "N^3/3 + N^2 (R + 1), R = expansion columns carried (<= max rx * max ry: product-magnitude truncation)"
                 kname = ("chol_dataflow_kernel (tiled Cholesky of K fused with the forward substitution of the R + 1 "
                          "right-hand sides of the factored posterior; persistent tile-dataflow kernel, FP64 DMMA)")
                 if fused_gram:         # the same launch also accumulates M = Y^T Y (symmetric: N R (R + 1) / 2 MAC)
                     kfl += float(N) * R * (R + 1)
-                    note = "N^3/3 + N^2 (R + 1) + N R (R + 1), R = max rx * max ry (the last term: the Gram product M = Y^T Y)"
+                    note = ("N^3/3 + N^2 (R + 1) + N R (R + 1), R = expansion columns carried (<= max rx * max ry: product-magnitude "
+                            "truncation); the last term: the Gram product M = Y^T Y")
                     kname = ("chol_dataflow_kernel (tiled Cholesky of K fused with the forward substitution of the R + 1 "
                              "right-hand sides of the factored posterior AND their Gram product M = Y^T Y; persistent "
                              "tile-dataflow kernel, warp-specialised, FP64 DMMA)")
@@ -486,7 +492,10 @@ def run_ours(args):
                 roof = {"bound": "tensor", "kernel": "factored posterior (FP64 DMMA)", "achieved": call["achieved"],
                         "peak": DGEMM_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": call["frac"], "traffic": None,
                         "algorithmic_flops": flops, "kernel_ms": pm, "kernel_share_of_step": pm / ms_dev}
-            roof.update({"chebyshev_orders": [plan["rxL"], plan["ryL"], plan["rxH"], plan["ryH"]], "posterior_call": call,
+            roof.update({"chebyshev_orders": [plan["rxL"], plan["ryL"], plan["rxH"], plan["ryH"]],
+                         "rhs_columns": {"expansion": int(R), "full_tensor_block": int(wv * max(plan["rxL"], plan["rxH"])),
+                                         "padded": int(timed_rhs_cols[1]) if timed_rhs_cols else None},
+                         "posterior_call": call,
                          "peak_source": "cuBLAS DGEMM 8192^3 measured on this pool (profiles/r01_dgemm_peak.json); "
                                         "MEASURED_PEAKS.json has no FP64 figure; DMMA issue peak 37.15",
                          "dense_kernel": dense})

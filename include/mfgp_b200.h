@@ -186,10 +186,25 @@ int mfgp_posterior_grid_factored_solved(const double* ux, int64_t nx, const doub
  *                                         when steps 4 + 5 will take the direct route (then use the plain pair above);
  *   mfgp_cholesky_solve_gram(..., M, ldm = ldb = R, work of mfgp_cholesky_solve_gram_workspace_bytes(npad, R) bytes, ...);
  *   mfgp_posterior_grid_factored_solved_gram(...)   same arguments as _solved; skips the product and its reduction.
- * M == NULL in mfgp_cholesky_solve_gram is mfgp_cholesky_solve. */
+ * M == NULL in mfgp_cholesky_solve_gram is mfgp_cholesky_solve.
+ *
+ * Truncated column layout (optional, `kx`: HOST array of max(ryL, ryH) int32, or NULL for the uniform layout).  Term (l, k) of the
+ * expansion -- T_l(ty) T_k(tx) -- has a coefficient bounded by a_y[l] a_x[k], and both factors decay super-exponentially (the
+ * axis factors are entire functions), so the far corner of the rx x ry block is below rounding: per y term l only the first
+ * kx[l] x terms (a multiple of 4, 4 <= kx[l] <= round_up(max(rxL, rxH), 4)) are kept; the right-hand-side matrix shrinks to
+ * mfgp_factored_rhs_cols_trunc(ry, kx) columns (c4: 1344 -> 896) at the same entrywise accuracy -- the caller picks kx from the
+ * same coefficient envelopes that gave it the orders (mfgp_coverage_b200/_engine.py: chebyshev_truncation).  Only the Gram route
+ * reads this layout: give the same kx to mfgp_factored_prepare_trunc, mfgp_factored_gram_target (which then never returns
+ * NULL for a valid geometry) and mfgp_posterior_grid_factored_solved_gram; Gstore / Hz_store must be NULL. */
+int64_t mfgp_factored_rhs_cols_trunc(int64_t ry, const int32_t* kx);
+int mfgp_factored_prepare_trunc(const double* ux, int64_t nx, const double* uy, int64_t ny, int64_t ix0, int64_t ncols,
+                                const double* Xt, const double* y, int64_t NL, int64_t NH, int64_t npad, const mfgp_params* p_host,
+                                int64_t rxL, int64_t ryL, int64_t rxH, int64_t ryH, double xlo, double xhi, double ylo, double yhi,
+                                int64_t chunk_cols, const int32_t* kx, double* Ball, int64_t ldB, void* work, int64_t work_bytes,
+                                void* stream);
 double* mfgp_factored_gram_target(int64_t nx, int64_t ny, int64_t ix0, int64_t ncols, int64_t NL, int64_t NH, int64_t npad,
                                   const mfgp_params* p_host, int64_t rxL, int64_t ryL, int64_t rxH, int64_t ryH,
-                                  int64_t chunk_cols, int64_t ldY, void* work, int64_t work_bytes);
+                                  int64_t chunk_cols, const int32_t* kx, int64_t ldY, void* work, int64_t work_bytes);
 int64_t mfgp_cholesky_solve_gram_workspace_bytes(int64_t npad, int64_t R);
 int mfgp_cholesky_solve_gram(double* K, int64_t npad, int64_t ld, double* W, int64_t ldw, int32_t* info, double* Bm, int64_t ldb,
                              int64_t R, double* M, int64_t ldm, void* work, int64_t work_bytes, void* stream);
@@ -197,9 +212,9 @@ int mfgp_posterior_grid_factored_solved_gram(const double* ux, int64_t nx, const
                                              int64_t ncols, const double* Xt, int64_t NL, int64_t NH, int64_t npad,
                                              const mfgp_params* p_host, int64_t rxL, int64_t ryL, int64_t rxH, int64_t ryH,
                                              double xlo, double xhi, double ylo, double yhi, int64_t chunk_cols,
-                                             const double* Yall, int64_t ldY, double* z_out, double* mu, double* var,
-                                             double* qred, double* Gstore, double* Hz_store, void* work, int64_t work_bytes,
-                                             void* stream);
+                                             const int32_t* kx, const double* Yall, int64_t ldY, double* z_out, double* mu,
+                                             double* var, double* qred, double* Gstore, double* Hz_store, void* work,
+                                             int64_t work_bytes, void* stream);
 
 /* ---- coverage step: replaces simulator.py in_polygon :105-124, compute_loss :194-228, compute_centroids :231-283,
  *      compute_max_var :286-323, compute_sample_clusters :377-412 ------------------------------------------------ */

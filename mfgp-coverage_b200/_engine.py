@@ -38,6 +38,40 @@ def chebyshev_order(length_scale, lo, hi, centre_lo, centre_hi, tol=5e-15, rmax=
     return None
 
 
+def chebyshev_envelope(length_scale, lo, hi, centre_lo, centre_hi, r):
+    """|c_k| / max|c|, k < r, of the order-r Chebyshev interpolant of u -> exp(-0.5 ((u - c) / l)^2) on [lo, hi], maximised over
+    the centres c in [centre_lo, centre_hi] (the same sampling as chebyshev_order)."""
+    half, mid = 0.5 * (hi - lo), 0.5 * (hi + lo)
+    centres = np.linspace(min(centre_lo, lo), max(centre_hi, hi), 17)
+    j = np.arange(r)
+    nodes = mid + half * np.cos(np.pi * (j + 0.5) / r)
+    f = np.exp(-0.5 * ((nodes[:, None] - centres[None, :]) / length_scale) ** 2)
+    c = np.abs((np.cos(np.pi * np.outer(np.arange(r), j + 0.5) / r) @ f) * (2.0 / r))
+    return c.max(axis=1) / max(float(c.max()), 1e-300)
+
+
+def chebyshev_truncation(parts, kpad, ry, tol=1e-16):
+    """Truncated column layout of the factored posterior's right-hand sides (include/mfgp_b200.h: kx).  `parts`: per kernel
+    part (envelope over k of the x factor, envelope over l of the y factor).  Term (l, k) is kept while ANY part's bound
+    a_y[l] a_x[k] exceeds `tol`; per y term l the kept x terms are rounded up to a multiple of 4.  The dropped terms of a row
+    decay super-exponentially behind the first one (<= ~1.5 tol per row, ry rows): with tol = 1e-16 their sum stays below the
+    5e-15 the orders themselves were chosen for.  Returns an int32 array of ry entries."""
+    kx = np.empty(ry, dtype=np.int32)
+    for l in range(ry):
+        last = -1
+        for ax, ay in parts:
+            if l < ay.size:
+                keep = np.nonzero(ay[l] * ax > tol)[0]
+                if keep.size:
+                    last = max(last, int(keep[-1]))
+        kx[l] = min(kpad, max(4, -(-(last + 1) // 4) * 4))
+    return kx
+
+
+# MFGP_TRUNC=0: keep the full rx x ry tensor block of Chebyshev terms (default: product-magnitude truncation, ~1/3 fewer columns)
+TRUNCATE = os.environ.get("MFGP_TRUNC", "1") != "0"
+
+
 class TensorAxes:
     """Axis values of a tensor-product grid `[[x, y] for x in ux for y in uy]` (x-major, distribution.py:337-339)."""
 
@@ -99,6 +133,8 @@ class DeviceGP:
         self.factored_min_gain = 2.0  # ... i.e. when its MAC count is at least this factor below the dense kernel's
         self._fplan = None            # (key, plan, orders) of the last factored-posterior plan
         self._forders = None          # (key, hull, orders): Chebyshev orders and the training-point hull they cover
+        self._ftrunc = None           # truncated column layout (kx per y term) that goes with _forders, or None
+        self.rhs_cols = None          # (expansion columns, padded right-hand-side count) of the last fused fit
         self._fwork = None
         self._xrange = None           # (xmin, xmax, ymin, ymax) of the training points, refreshed by fit / append
         self.defer_fit = False        # True: refactor(check=False) only marks the factor stale; the first consumer factorises --
@@ -392,6 +428,16 @@ class DeviceGP:
             ryL = chebyshev_order(p["l_L"], ylo, yhi, hull[2], hull[3])
             ok = rxL is not None and ryL is not None
         orders = (rxL, ryL, rxH, ryH) if ok else None
+        self._ftrunc = None
+        if ok and TRUNCATE:
+            parts = [(chebyshev_envelope(p["l_H"], xlo, xhi, hull[0], hull[1], rxH),
+                      chebyshev_envelope(p["l_H"], ylo, yhi, hull[2], hull[3], ryH))]
+            if p["multi"]:
+                parts.append((chebyshev_envelope(p["l_L"], xlo, xhi, hull[0], hull[1], rxL),
+                              chebyshev_envelope(p["l_L"], ylo, yhi, hull[2], hull[3], ryL)))
+            kp = -(-max(rxL, rxH) // 4) * 4
+            parts = [(np.pad(ax, (0, kp - ax.size)), ay) for ax, ay in parts]
+            self._ftrunc = chebyshev_truncation(parts, kp, max(ryL, ryH))
         self._forders = ((axes.uid, xlo, xhi, p["l_L"], p["l_H"], p["multi"]), hull, orders)
         return orders
 
@@ -429,7 +475,7 @@ class DeviceGP:
             if fact * self.factored_min_gain < dense:
                 chunk = max(64, min(-(-ncols // 64) * 64, ((1 << 28) // max(self.cap * max(ryL, ryH), 1)) // 64 * 64))   # <= 2 GiB of Y'
                 plan = dict(rxL=rxL, ryL=ryL, rxH=rxH, ryH=ryH, xlo=xlo, xhi=xhi, ylo=axes.ylo, yhi=axes.yhi,
-                            ix0=ix0, ncols=ncols, chunk=chunk, macs=fact, dense_macs=dense)
+                            ix0=ix0, ncols=ncols, chunk=chunk, macs=fact, dense_macs=dense, kx=self._ftrunc)
         self._fplan = (key, plan, orders)
         return plan
 
@@ -463,38 +509,59 @@ class DeviceGP:
         pp = ctypes.byref(self.pstruct)
         npad, ld = self.npad, self.cap
         o = (plan["rxL"], plan["ryL"], plan["rxH"], plan["ryH"])
-        R = int(lib.mfgp_factored_rhs_cols(*o))
-        if self._fB is None or self._fB.numel() < self.cap * R:
-            self._fB = torch.empty(self.cap * R, dtype=torch.float64, device=self.device)
         work = self._factored_work(axes, plan)
         geom = (ctypes.c_double(plan["xlo"]), ctypes.c_double(plan["xhi"]), ctypes.c_double(plan["ylo"]),
                 ctypes.c_double(plan["yhi"]), plan["chunk"])
+        # Gram route of steps 4 + 5: M = Y^T Y is accumulated inside the factorisation kernel (NULL: direct route), and the
+        # right-hand sides may use the truncated column layout (not with the incremental stores, which keep the uniform one)
+        kx = plan.get("kx") if (FUSED_GRAM and not self.incremental) else None
+        M, R = None, 0
+        if FUSED_GRAM:
+            if kx is not None:
+                kxp = ctypes.c_void_p(kx.ctypes.data)
+                R = int(lib.mfgp_factored_rhs_cols_trunc(int(kx.size), kxp))
+                M = lib.mfgp_factored_gram_target(axes.nx, axes.ny, plan["ix0"], plan["ncols"], self.NL, self.NH, npad, pp, *o,
+                                                  plan["chunk"], kxp, R, nat.ptr(work), work.numel() * 8)
+            if not M:
+                kx, kxp = None, None
+                R = int(lib.mfgp_factored_rhs_cols(*o))
+                M = lib.mfgp_factored_gram_target(axes.nx, axes.ny, plan["ix0"], plan["ncols"], self.NL, self.NH, npad, pp, *o,
+                                                  plan["chunk"], None, R, nat.ptr(work), work.numel() * 8)
+        else:
+            kx, kxp = None, None
+            R = int(lib.mfgp_factored_rhs_cols(*o))
+        if self._fB is None or self._fB.numel() < self.cap * R:
+            self._fB = torch.empty(self.cap * R, dtype=torch.float64, device=self.device)
         nat.check(lib.mfgp_build_train_cov(nat.ptr(self.Xt), self.NL, self.NH, pp, nat.ptr(self.K), npad, ld,
                                            nat.ptr(self.Tt), st), "mfgp_build_train_cov")
-        nat.check(lib.mfgp_factored_prepare(nat.ptr(axes.ux), axes.nx, nat.ptr(axes.uy), axes.ny, plan["ix0"], plan["ncols"],
-                                            nat.ptr(self.Xt), nat.ptr(self.y), self.NL, self.NH, npad, pp, *o, *geom,
-                                            nat.ptr(self._fB), R, nat.ptr(work), work.numel() * 8, st),
-                  "mfgp_factored_prepare")
+        nat.check(lib.mfgp_factored_prepare_trunc(nat.ptr(axes.ux), axes.nx, nat.ptr(axes.uy), axes.ny, plan["ix0"], plan["ncols"],
+                                                  nat.ptr(self.Xt), nat.ptr(self.y), self.NL, self.NH, npad, pp, *o, *geom,
+                                                  kxp if kx is not None else None, nat.ptr(self._fB), R, nat.ptr(work),
+                                                  work.numel() * 8, st), "mfgp_factored_prepare")
         ev = self.profile_events          # bench.py: (start, stop) CUDA events around the dominant kernel
         if ev is not None:
             ev[0].record()
         cneed = int(lib.mfgp_cholesky_solve_gram_workspace_bytes(self.cap, R))
         if self._cwork is None or self._cwork.numel() * 8 < cneed:
             self._cwork = torch.empty(cneed // 8 + 8, dtype=torch.float64, device=self.device)
-        # Gram route of steps 4 + 5: M = Y^T Y is accumulated inside the factorisation kernel (NULL: direct route)
-        M = lib.mfgp_factored_gram_target(axes.nx, axes.ny, plan["ix0"], plan["ncols"], self.NL, self.NH, npad, pp, *o,
-                                          plan["chunk"], R, nat.ptr(work), work.numel() * 8) if FUSED_GRAM else None
         nat.check(lib.mfgp_cholesky_solve_gram(nat.ptr(self.K), npad, ld, nat.ptr(self.W), ld, nat.ptr(self.info),
                                                nat.ptr(self._fB), R, R, ctypes.c_void_p(M), R, nat.ptr(self._cwork),
                                                self._cwork.numel() * 8, st), "mfgp_cholesky_solve_gram")
         if ev is not None:
             ev[1].record()
         Gs, Hs = self._factored_stores(plan)
-        solved = lib.mfgp_posterior_grid_factored_solved_gram if M else lib.mfgp_posterior_grid_factored_solved
-        nat.check(solved(
-            nat.ptr(axes.ux), axes.nx, nat.ptr(axes.uy), axes.ny, plan["ix0"], plan["ncols"], nat.ptr(self.Xt), self.NL,
-            self.NH, npad, pp, *o, *geom, nat.ptr(self._fB), R, nat.ptr(self.z), nat.ptr(mu), nat.ptr(var), nat.ptr(q_out),
-            nat.ptr(Gs), nat.ptr(Hs), nat.ptr(work), work.numel() * 8, st), "mfgp_posterior_grid_factored_solved")
+        if M:
+            nat.check(lib.mfgp_posterior_grid_factored_solved_gram(
+                nat.ptr(axes.ux), axes.nx, nat.ptr(axes.uy), axes.ny, plan["ix0"], plan["ncols"], nat.ptr(self.Xt), self.NL,
+                self.NH, npad, pp, *o, *geom, kxp if kx is not None else None, nat.ptr(self._fB), R, nat.ptr(self.z), nat.ptr(mu),
+                nat.ptr(var), nat.ptr(q_out), nat.ptr(Gs), nat.ptr(Hs), nat.ptr(work), work.numel() * 8, st),
+                "mfgp_posterior_grid_factored_solved_gram")
+        else:
+            nat.check(lib.mfgp_posterior_grid_factored_solved(
+                nat.ptr(axes.ux), axes.nx, nat.ptr(axes.uy), axes.ny, plan["ix0"], plan["ncols"], nat.ptr(self.Xt), self.NL,
+                self.NH, npad, pp, *o, *geom, nat.ptr(self._fB), R, nat.ptr(self.z), nat.ptr(mu), nat.ptr(var), nat.ptr(q_out),
+                nat.ptr(Gs), nat.ptr(Hs), nat.ptr(work), work.numel() * 8, st), "mfgp_posterior_grid_factored_solved")
+        self.rhs_cols = (int(kx.sum()) if kx is not None else max(plan["ryL"], plan["ryH"]) * (-(-max(plan["rxL"], plan["rxH"]) // 4) * 4), R)
         self.fused_gram = bool(M)
         self._dirty = False
         self._w_partial = True

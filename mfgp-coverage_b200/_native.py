@@ -85,16 +85,21 @@ SIGNATURES = {
                                                     c_int64, c_double, c_double, c_double, c_double, c_int64, c_void_p,
                                                     c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                                     c_void_p, c_int64, c_void_p]),
+    "mfgp_factored_rhs_cols_trunc": (c_int64, [c_int64, c_void_p]),
+    "mfgp_factored_prepare_trunc": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_int64,
+                                            c_int64, c_int64, POINTER(MfgpParams), c_int64, c_int64, c_int64, c_int64, c_double,
+                                            c_double, c_double, c_double, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_int64,
+                                            c_void_p]),
     "mfgp_factored_gram_target": (c_void_p, [c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, POINTER(MfgpParams),
-                                             c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_void_p, c_int64]),
+                                             c_int64, c_int64, c_int64, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_int64]),
     "mfgp_cholesky_solve_gram_workspace_bytes": (c_int64, [c_int64, c_int64]),
     "mfgp_cholesky_solve_gram": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int64,
                                          c_void_p, c_int64, c_void_p, c_int64, c_void_p]),
     "mfgp_posterior_grid_factored_solved_gram": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64,
                                                          c_int64, c_int64, POINTER(MfgpParams), c_int64, c_int64, c_int64,
                                                          c_int64, c_double, c_double, c_double, c_double, c_int64, c_void_p,
-                                                         c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
-                                                         c_void_p, c_int64, c_void_p]),
+                                                         c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                                         c_void_p, c_void_p, c_int64, c_void_p]),
     "cov_assign_reduce": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64,
                                   c_void_p, c_int64, c_void_p, c_void_p, c_int64,
                                   c_void_p, c_int64, c_void_p, c_void_p, c_int64,

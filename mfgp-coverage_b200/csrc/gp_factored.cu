@@ -28,6 +28,16 @@ namespace mfgp {
 constexpr int F_LW = 64;             // padded number of y-expansion terms of both parts together (ryL + ryH <= 64)
 constexpr int F_MAXR = 64;           // largest supported Chebyshev order per axis and part
 
+// Column layout of the right-hand sides: term (l, k) -- T_l(ty) T_k(tx) -- sits in column off[l] + k, k < kx[l].  Uniform: kx[l] =
+// kpad for every l.  Truncated: the caller keeps, per y term l, only the x terms whose coefficient bound a_y[l] a_x[k] is above
+// its tolerance (the coefficients of an entire function decay super-exponentially in BOTH indices, so the tensor block's far
+// corner is below rounding): ~1/3 fewer columns at the same entrywise accuracy.  Passed to kernels by value.
+struct FTrunc {
+    short off[F_MAXR + 1];
+    short kx[F_MAXR];
+    int ry, cols;
+};
+
 struct FPart {                       // one kernel part (lofi / hifi) of the factored expansion
     int rx, ry, kpad;                // x terms, y terms (multiple of 4), x terms padded to a multiple of 4
     int loff;                        // first column of this part inside the 64-wide y-term vector
@@ -105,12 +115,14 @@ __global__ void cheb_basis_kernel(const double* __restrict__ u, int i0, int coun
 // rx = max(rxL, rxH), ry = max(ryL, ryH) instead of two (the lofi part's terms beyond its own orders are zero):
 //   B[n][l][k] = cL[n] CyL[l][n] CxL[k][n] [l < ryL, k < rxL]  +  cH[n] CyH[l][n] CxH[k][n] [l < ryH, k < rxH]
 struct BTab { const double* Cx; const double* Cy; int rx, ry; double coef_lo, coef_hi; };
-__global__ void build_B_merged_kernel(BTab t0, BTab t1, int ntab, int npad, int N, int NL, int ry, int kpad, double* __restrict__ B,
+__global__ void build_B_merged_kernel(BTab t0, BTab t1, int ntab, int npad, int N, int NL, FTrunc tr, double* __restrict__ B,
                                       int64_t ldB) {
     const int n = blockIdx.y;
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;       // (l, k)
-    if (e >= ry * kpad) return;
-    const int l = e / kpad, k = e % kpad;
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;       // column of term (l, k)
+    if (e >= tr.cols) return;
+    int l = 0;
+    while (tr.off[l + 1] <= e) l++;
+    const int k = e - tr.off[l];
     double v = 0.0;
     if (n < N) {
         if (l < t0.ry && k < t0.rx) v = (n < NL ? t0.coef_lo : t0.coef_hi) * t0.Cy[(int64_t)l * npad + n] * t0.Cx[(int64_t)k * npad + n];
@@ -388,6 +400,7 @@ __global__ void syrk_reduce_lower_kernel(const double* __restrict__ part, int ns
 struct QformArgs {
     const double* M; int ldm;            // lower tiles of Y^T Y
     const double* Ux; int kpad;          // [ncols_pad][kpad]  T_k(tx)
+    FTrunc tr;                           // block (l, l') of M: rows off[l] .. + kx[l], columns off[l'] .. + kx[l']
     int ry, ncols, pairs_per_cta;
     double* G;                           // [ncols][F_LW][F_LW], both triangles written
     int col_begin;
@@ -424,16 +437,17 @@ __global__ void __launch_bounds__(128) qform_kernel(QformArgs a) {
         for (int rt = 0; rt < 2; rt++)
 #pragma unroll
             for (int j = 0; j < NT; j++) acc[rt][j][0] = acc[rt][j][1] = 0.0;
-        const int ra = l * a.kpad, rb = lp * a.kpad;
+        const int ra = a.tr.off[l], rb = a.tr.off[lp], ka = a.tr.kx[l], kb = a.tr.kx[lp];
 #pragma unroll
         for (int ks = 0; ks < KS; ks++) {
+            if (ks * 4 >= ka) break;                               // (uniform) the block has only ka rows
             const int k = ks * 4 + tq;
             double b[NT];
 #pragma unroll
             for (int j = 0; j < NT; j++) {
                 const int n = j * 8 + gq;
                 double v = 0.0;
-                if (k < a.kpad && n < a.kpad) {
+                if (k < ka && n < kb) {
                     const int r = ra + k, c = rb + n;              // M is symmetric, stored for row tile >= column tile
                     v = (r >= c) ? __ldg(a.M + (int64_t)r * a.ldm + c) : __ldg(a.M + (int64_t)c * a.ldm + r);
                 }
@@ -442,14 +456,15 @@ __global__ void __launch_bounds__(128) qform_kernel(QformArgs a) {
 #pragma unroll
             for (int rt = 0; rt < 2; rt++)
 #pragma unroll
-                for (int j = 0; j < NT; j++) dmma884(acc[rt][j][0], acc[rt][j][1], af[rt][ks], b[j]);
+                for (int j = 0; j < NT; j++)
+                    if (j * 8 < kb) dmma884(acc[rt][j][0], acc[rt][j][1], af[rt][ks], b[j]);       // (uniform) kb columns
         }
 #pragma unroll
         for (int rt = 0; rt < 2; rt++) {
             const int row = warp * 16 + rt * 8 + gq;
             double q = 0.0;
 #pragma unroll
-            for (int j = 0; j < NT; j++) {
+            for (int j = 0; j < NT; j++) {                         // columns >= kb of the accumulators are zero
                 q = fma(acc[rt][j][0], Us[row][j * 8 + 2 * tq], q);
                 q = fma(acc[rt][j][1], Us[row][j * 8 + 2 * tq + 1], q);
             }
@@ -470,7 +485,7 @@ __global__ void __launch_bounds__(128) qform_kernel(QformArgs a) {
 //   var = k0 - uy^T G' uy,   mu = mean + h'(ix) . uy,   h'(ix)[l] = sum_k Ux(ix)[k] Hz[l][k]
 template <int WM, int NP>          // NP = 2: two points per thread (WM = 40), 1: one (WM = 64: the u vector alone takes 128 registers)
 __global__ void __launch_bounds__(256) geval_kernel(const double* __restrict__ G, const double* __restrict__ Hz, const double* __restrict__ Ux,
-                                                    int kpad, int ry, const double* __restrict__ Uy, int ny, double mean, double k0,
+                                                    int kpad, int ry, FTrunc tr, const double* __restrict__ Uy, int ny, double mean, double k0,
                                                     double* __restrict__ mu, double* __restrict__ var, double* __restrict__ qred) {
     constexpr int GP = WM + 2;
     __shared__ __align__(16) double Gs[WM * GP];
@@ -485,8 +500,8 @@ __global__ void __launch_bounds__(256) geval_kernel(const double* __restrict__ G
         double h = 0.0;
         if (tid < ry) {
             const double* ux = Ux + (int64_t)col * kpad;
-            const double* hz = Hz + (int64_t)tid * kpad;
-            for (int k = 0; k < kpad; k++) h = fma(ux[k], hz[k], h);
+            const double* hz = Hz + tr.off[tid];
+            for (int k = 0; k < tr.kx[tid]; k++) h = fma(ux[k], hz[k], h);
         }
         hs[tid] = h;
     }
@@ -591,6 +606,15 @@ extern "C" int64_t mfgp_factored_rhs_cols(int64_t rxL, int64_t ryL, int64_t rxH,
     return round_up(imax(ryL, ryH) * round_up(imax(rxL, rxH), 4) + 1, 64);
 }
 
+// Columns of the right-hand-side matrix for a truncated layout (kx[l] x terms kept for y term l, see FTrunc): sum kx + the
+// observation column, padded to a multiple of 64.
+extern "C" int64_t mfgp_factored_rhs_cols_trunc(int64_t ry, const int32_t* kx) {
+    if (!kx || ry <= 0 || ry > F_MAXR) return 0;
+    int64_t c = 0;
+    for (int64_t l = 0; l < ry; l++) c += kx[l];
+    return round_up(c + 1, 64);
+}
+
 namespace {
 struct FGeom {
     const double* ux; int64_t nx; const double* uy; int64_t ny; int64_t ix0, ncols;
@@ -605,7 +629,28 @@ struct FLayout {
     FTab tabs[2]; int ntabs;         // coefficient tables per kernel part
     FPart parts[1]; int nparts;      // ONE merged expansion (rx = max, ry = max)
     double* Uy; double* zbuf; int64_t ncp, chunk; bool multi;
+    FTrunc tr; bool truncated;       // column layout of the right-hand sides (uniform unless f_set_trunc was given a table)
 };
+
+// kx_host (optional, ry entries: x terms kept for y term l; multiples of 4 in [4, kpad]) -> column layout.  Returns false
+// for an invalid table.
+bool f_set_trunc(FLayout& L, const int32_t* kx_host) {
+    const FPart& f = L.parts[0];
+    FTrunc& t = L.tr;
+    t.ry = f.ry;
+    L.truncated = kx_host != nullptr;
+    int o = 0;
+    for (int l = 0; l < f.ry; l++) {
+        const int k = kx_host ? kx_host[l] : f.kpad;
+        if (k < 4 || k > f.kpad || (k & 3)) return false;
+        t.off[l] = (short)o; t.kx[l] = (short)k;
+        o += k;
+    }
+    for (int l = f.ry; l < F_MAXR; l++) { t.off[l] = (short)o; t.kx[l] = 0; }
+    t.off[F_MAXR] = (short)o;
+    t.cols = o;
+    return true;
+}
 
 int f_validate(const FGeom& g, void* work, int64_t work_bytes) {
     if (!g.ux || !g.uy || !g.Xt || !g.p || !work) return MFGP_ERR_INVALID;
@@ -649,6 +694,7 @@ void f_carve(const FGeom& g, void* work, FLayout& L) {
         f.Yp = carve(direct > gram ? direct : gram);
     }
     f.Hz = carve((int64_t)f.ry * f.kpad);
+    f_set_trunc(L, nullptr);
 }
 
 // steps 1 + 2: tables of both kernel parts, basis tables, then the merged B either into the part's own buffer
@@ -678,9 +724,9 @@ int f_tables_and_B(const FGeom& g, FLayout& L, double* Ball, int64_t ldB, cudaSt
         cheb_coef_kernel<<<cgrid, 256, 0, st>>>(g.Xt, (int)N, (int)npad, jobs);
         MFGP_LAUNCH_CHECK();
     }
-    const int cols = f.ry * f.kpad;
+    const int cols = L.tr.cols;                // ry * kpad, or fewer with a truncated layout (fused-fit form only)
     dim3 bgrid((unsigned)((cols + 127) / 128), (unsigned)npad);
-    build_B_merged_kernel<<<bgrid, 128, 0, st>>>(bt[0], bt[1], L.ntabs, (int)npad, (int)N, (int)g.NL, f.ry, f.kpad, Ball ? Ball : f.B,
+    build_B_merged_kernel<<<bgrid, 128, 0, st>>>(bt[0], bt[1], L.ntabs, (int)npad, (int)N, (int)g.NL, L.tr, Ball ? Ball : f.B,
                                                 Ball ? ldB : (int64_t)cols);
     MFGP_LAUNCH_CHECK();
     return MFGP_OK;
@@ -752,11 +798,12 @@ int gram_route_override() {          // read per call: tests and A/B timings swi
 // route of steps 4 + 5 for solved right-hand sides with row stride ldY: true = Gram route (cost model, MFGP_GRAM overrides)
 bool f_gram_wanted(const FGeom& g, const FLayout& L, int64_t ldY) {
     const FPart& f = L.parts[0];
-    const int64_t npad = g.npad, cols = (int64_t)f.ry * f.kpad;
+    const int64_t npad = g.npad, cols = L.tr.cols;
     const int wm = f.ry <= 40 ? 40 : 64;
     const int nt8 = (f.kpad + 7) / 8;
     if (ldY % 64 || ldY < cols + 1 || nt8 > 8) return false;
     const int ov = gram_route_override();
+    if (L.truncated) return ov != 1;       // the truncated layout exists for this route only (MFGP_GRAM=direct: caller falls back)
     const double direct = (double)g.ncols * npad * cols + 0.6 * g.ncols * npad * wm * wm;
     const double gram = 0.5 * npad * (double)ldY * ldY + (double)round_up(g.ncols, 64) * (f.ry * (f.ry + 1) / 2) * 64.0 * nt8 * nt8;
     return !(ov == 1 || (ov == 0 && gram >= direct));
@@ -766,10 +813,11 @@ bool f_gram_wanted(const FGeom& g, const FLayout& L, int64_t ldY) {
 int f_tail_gram(const FGeom& g, FLayout& L, const double* Yall, int64_t ldY, double* Gstore, double* Hz_store, double* mu,
                 double* var, double* qred, bool m_ready, cudaStream_t st) {
     FPart& f = L.parts[0];
-    const int64_t npad = g.npad, cols = (int64_t)f.ry * f.kpad;
+    const int64_t npad = g.npad, cols = L.tr.cols;
     const int wm = f.ry <= 40 ? 40 : 64;
     const int nt8 = (f.kpad + 7) / 8;
-    if (!f_gram_wanted(g, L, ldY)) return m_ready ? MFGP_ERR_INVALID : 1;
+    if (!f_gram_wanted(g, L, ldY)) return (m_ready || L.truncated) ? MFGP_ERR_INVALID : 1;
+    if (L.truncated && (Gstore || Hz_store)) return MFGP_ERR_INVALID;      // the incremental stores keep the uniform layout
     const DevParams dp = make_dev_params(*g.p);
     // M and its partial sums live where the direct route keeps Y'
     double* M = f.Yp;
@@ -798,7 +846,7 @@ int f_tail_gram(const FGeom& g, FLayout& L, const double* Yall, int64_t ldY, dou
     hz_from_M_kernel<<<(unsigned)((cols + 127) / 128), 128, 0, st>>>(M, (int)ldY, (int)cols, (int)cols, f.Hz);
     MFGP_LAUNCH_CHECK();
     QformArgs qa;
-    qa.M = M; qa.ldm = (int)ldY; qa.Ux = f.Ux; qa.kpad = f.kpad; qa.ry = f.ry; qa.ncols = (int)g.ncols; qa.G = Gbuf; qa.col_begin = 0;
+    qa.M = M; qa.ldm = (int)ldY; qa.Ux = f.Ux; qa.kpad = f.kpad; qa.tr = L.tr; qa.ry = f.ry; qa.ncols = (int)g.ncols; qa.G = Gbuf; qa.col_begin = 0;
     const int npairs = f.ry * (f.ry + 1) / 2;
     const int cblocks = (int)((g.ncols + 63) / 64);
     int groups = (148 * 4 + cblocks - 1) / cblocks;              // ~4 CTAs per SM
@@ -819,9 +867,9 @@ int f_tail_gram(const FGeom& g, FLayout& L, const double* Yall, int64_t ldY, dou
     MFGP_LAUNCH_CHECK();
     // step 6 (and h'(ix)): G' comes from the buffer, nothing else to add
     if (wm == 40)
-        geval_kernel<40, 2><<<(unsigned)g.ncols, 256, 0, st>>>(Gbuf, f.Hz, f.Ux, f.kpad, f.ry, L.Uy, (int)g.ny, dp.mean_H, dp.k0, mu, var, qred);
+        geval_kernel<40, 2><<<(unsigned)g.ncols, 256, 0, st>>>(Gbuf, f.Hz, f.Ux, f.kpad, f.ry, L.tr, L.Uy, (int)g.ny, dp.mean_H, dp.k0, mu, var, qred);
     else
-        geval_kernel<64, 1><<<(unsigned)g.ncols, 256, 0, st>>>(Gbuf, f.Hz, f.Ux, f.kpad, f.ry, L.Uy, (int)g.ny, dp.mean_H, dp.k0, mu, var, qred);
+        geval_kernel<64, 1><<<(unsigned)g.ncols, 256, 0, st>>>(Gbuf, f.Hz, f.Ux, f.kpad, f.ry, L.tr, L.Uy, (int)g.ny, dp.mean_H, dp.k0, mu, var, qred);
     MFGP_LAUNCH_CHECK();
     if (Gstore && f.ry < wm) {        // the incremental update adds into the padded wm x wm block of the store: its padding must be finite
         gpad_zero_kernel<<<(unsigned)g.ncols, 128, 0, st>>>(Gbuf, f.ry, wm, 0);
@@ -863,39 +911,57 @@ extern "C" int mfgp_posterior_grid_factored(const double* ux, int64_t nx, const 
 
 // Fused-fit form, part 1: steps 1 + 2 straight into the right-hand-side matrix of mfgp_cholesky_solve,
 // Ball[npad, ldB] = [B_L | B_H | (y - mean), 0 ...] with mfgp_factored_rhs_cols(...) columns.
-extern "C" int mfgp_factored_prepare(const double* ux, int64_t nx, const double* uy, int64_t ny, int64_t ix0, int64_t ncols,
-                                     const double* Xt, const double* y, int64_t NL, int64_t NH, int64_t npad,
-                                     const mfgp_params* p_host, int64_t rxL, int64_t ryL, int64_t rxH, int64_t ryH, double xlo,
-                                     double xhi, double ylo, double yhi, int64_t chunk_cols, double* Ball, int64_t ldB, void* work,
-                                     int64_t work_bytes, void* stream) {
-    if (!y || !Ball || ldB < mfgp_factored_rhs_cols(rxL, ryL, rxH, ryH)) return MFGP_ERR_INVALID;
+// kx (optional, host, max(ryL, ryH) entries): truncated column layout -- per y term l only the first kx[l] x terms are kept
+// (multiples of 4 in [4, round_up(max(rxL, rxH), 4)]); Ball then has mfgp_factored_rhs_cols_trunc(ry, kx) columns.  Only the
+// Gram route of steps 4 + 5 reads that layout: pair it with mfgp_factored_gram_target / mfgp_posterior_grid_factored_solved_gram
+// called with the same kx.
+extern "C" int mfgp_factored_prepare_trunc(const double* ux, int64_t nx, const double* uy, int64_t ny, int64_t ix0, int64_t ncols,
+                                           const double* Xt, const double* y, int64_t NL, int64_t NH, int64_t npad,
+                                           const mfgp_params* p_host, int64_t rxL, int64_t ryL, int64_t rxH, int64_t ryH, double xlo,
+                                           double xhi, double ylo, double yhi, int64_t chunk_cols, const int32_t* kx, double* Ball,
+                                           int64_t ldB, void* work, int64_t work_bytes, void* stream) {
+    if (!y || !Ball) return MFGP_ERR_INVALID;
     FGeom g{ux, nx, uy, ny, ix0, ncols, Xt, NL, NH, npad, p_host, rxL, ryL, rxH, ryH, xlo, xhi, ylo, yhi, chunk_cols};
     int rc = f_validate(g, work, work_bytes);
     if (rc) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     FLayout L;
     f_carve(g, work, L);
+    if (!f_set_trunc(L, kx)) return MFGP_ERR_INVALID;
+    const int64_t zoff = L.tr.cols;                                          // the column right behind B; the rest is zero padding
+    const int64_t R = round_up(zoff + 1, 64);
+    if (ldB < R) return MFGP_ERR_INVALID;
     rc = f_tables_and_B(g, L, Ball, ldB, st);
     if (rc) return rc;
-    const int64_t zoff = (int64_t)L.parts[0].ry * L.parts[0].kpad;           // the column right behind B; the rest is zero padding
-    const int zw = (int)(mfgp_factored_rhs_cols(rxL, ryL, rxH, ryH) - zoff);
-    build_z_block_kernel<<<(unsigned)npad, zw, 0, st>>>(y, (int)npad, (int)(NL + NH), (int)NL, p_host->mean_L, p_host->mean_H, Ball + zoff, ldB);
+    build_z_block_kernel<<<(unsigned)npad, (int)(R - zoff), 0, st>>>(y, (int)npad, (int)(NL + NH), (int)NL, p_host->mean_L, p_host->mean_H,
+                                                                     Ball + zoff, ldB);
     MFGP_LAUNCH_CHECK();
     return MFGP_OK;
+}
+
+extern "C" int mfgp_factored_prepare(const double* ux, int64_t nx, const double* uy, int64_t ny, int64_t ix0, int64_t ncols,
+                                     const double* Xt, const double* y, int64_t NL, int64_t NH, int64_t npad,
+                                     const mfgp_params* p_host, int64_t rxL, int64_t ryL, int64_t rxH, int64_t ryH, double xlo,
+                                     double xhi, double ylo, double yhi, int64_t chunk_cols, double* Ball, int64_t ldB, void* work,
+                                     int64_t work_bytes, void* stream) {
+    return mfgp_factored_prepare_trunc(ux, nx, uy, ny, ix0, ncols, Xt, y, NL, NH, npad, p_host, rxL, ryL, rxH, ryH, xlo, xhi, ylo, yhi,
+                                       chunk_cols, nullptr, Ball, ldB, work, work_bytes, stream);
 }
 
 // Fused-fit form, part 2: Yall = L^-1 Ball (mfgp_cholesky_solve) -> steps 4 - 6.  `work` must be the workspace that
 // mfgp_factored_prepare filled (it holds the basis tables); z_out (optional) receives the whitened observations z[npad].
 namespace {
-int f_solved_impl(const FGeom& g, const double* Yall, int64_t ldY, double* z_out, double* mu, double* var, double* qred,
-                  double* Gstore, double* Hz_store, void* work, int64_t work_bytes, bool m_ready, cudaStream_t st) {
-    if (!Yall || !mu || !var || ldY < mfgp_factored_rhs_cols(g.rxL, g.ryL, g.rxH, g.ryH)) return MFGP_ERR_INVALID;
+int f_solved_impl(const FGeom& g, const int32_t* kx, const double* Yall, int64_t ldY, double* z_out, double* mu, double* var,
+                  double* qred, double* Gstore, double* Hz_store, void* work, int64_t work_bytes, bool m_ready, cudaStream_t st) {
+    if (!Yall || !mu || !var) return MFGP_ERR_INVALID;
     int rc = f_validate(g, work, work_bytes);
     if (rc) return rc;
     FLayout L;
     f_carve(g, work, L);
+    if (!f_set_trunc(L, kx)) return MFGP_ERR_INVALID;
     const int64_t npad = g.npad;
-    const int64_t zoff = (int64_t)L.parts[0].ry * L.parts[0].kpad;
+    const int64_t zoff = L.tr.cols;
+    if (ldY < round_up(zoff + 1, 64)) return MFGP_ERR_INVALID;
     unpack_z_kernel<<<(unsigned)((npad + 255) / 256), 256, 0, st>>>(Yall, ldY, (int)zoff, (int)npad, L.zbuf);
     MFGP_LAUNCH_CHECK();
     if (z_out) MFGP_CUDA_CHECK(cudaMemcpyAsync(z_out, L.zbuf, sizeof(double) * npad, cudaMemcpyDeviceToDevice, st));
@@ -922,20 +988,23 @@ extern "C" int mfgp_posterior_grid_factored_solved(const double* ux, int64_t nx,
                                                    double* qred, double* Gstore, double* Hz_store, void* work,
                                                    int64_t work_bytes, void* stream) {
     FGeom g{ux, nx, uy, ny, ix0, ncols, Xt, NL, NH, npad, p_host, rxL, ryL, rxH, ryH, xlo, xhi, ylo, yhi, chunk_cols};
-    return f_solved_impl(g, Yall, ldY, z_out, mu, var, qred, Gstore, Hz_store, work, work_bytes, false, static_cast<cudaStream_t>(stream));
+    return f_solved_impl(g, nullptr, Yall, ldY, z_out, mu, var, qred, Gstore, Hz_store, work, work_bytes, false,
+                         static_cast<cudaStream_t>(stream));
 }
 
 // Where mfgp_cholesky_solve_gram must leave M = Yall^T Yall (row stride ldY) for the posterior call that follows: a pointer
 // into `work` (the buffer of mfgp_factored_prepare), or NULL when steps 4 + 5 will take the direct route for this geometry
 // (few training rows; MFGP_GRAM=direct) -- then call plain mfgp_cholesky_solve and mfgp_posterior_grid_factored_solved.
+// kx: the truncated column layout given to mfgp_factored_prepare_trunc, or NULL (uniform).
 extern "C" double* mfgp_factored_gram_target(int64_t nx, int64_t ny, int64_t ix0, int64_t ncols, int64_t NL, int64_t NH, int64_t npad,
                                              const mfgp_params* p_host, int64_t rxL, int64_t ryL, int64_t rxH, int64_t ryH,
-                                             int64_t chunk_cols, int64_t ldY, void* work, int64_t work_bytes) {
-    if (!p_host || !work || ldY < mfgp_factored_rhs_cols(rxL, ryL, rxH, ryH)) return nullptr;
+                                             int64_t chunk_cols, const int32_t* kx, int64_t ldY, void* work, int64_t work_bytes) {
+    if (!p_host || !work) return nullptr;
     if (work_bytes < mfgp_factored_workspace_bytes(npad, ncols, ny, rxL, ryL, rxH, ryH, chunk_cols)) return nullptr;
     FGeom g{nullptr, nx, nullptr, ny, ix0, ncols, nullptr, NL, NH, npad, p_host, rxL, ryL, rxH, ryH, 0.0, 1.0, 0.0, 1.0, chunk_cols};
     FLayout L;
     f_carve(g, work, L);
+    if (!f_set_trunc(L, kx) || ldY < round_up((int64_t)L.tr.cols + 1, 64)) return nullptr;
     return f_gram_wanted(g, L, ldY) ? L.parts[0].Yp : nullptr;
 }
 
@@ -945,11 +1014,12 @@ extern "C" int mfgp_posterior_grid_factored_solved_gram(const double* ux, int64_
                                                         int64_t ncols, const double* Xt, int64_t NL, int64_t NH, int64_t npad,
                                                         const mfgp_params* p_host, int64_t rxL, int64_t ryL, int64_t rxH,
                                                         int64_t ryH, double xlo, double xhi, double ylo, double yhi,
-                                                        int64_t chunk_cols, const double* Yall, int64_t ldY, double* z_out,
-                                                        double* mu, double* var, double* qred, double* Gstore, double* Hz_store,
-                                                        void* work, int64_t work_bytes, void* stream) {
+                                                        int64_t chunk_cols, const int32_t* kx, const double* Yall, int64_t ldY,
+                                                        double* z_out, double* mu, double* var, double* qred, double* Gstore,
+                                                        double* Hz_store, void* work, int64_t work_bytes, void* stream) {
     FGeom g{ux, nx, uy, ny, ix0, ncols, Xt, NL, NH, npad, p_host, rxL, ryL, rxH, ryH, xlo, xhi, ylo, yhi, chunk_cols};
-    return f_solved_impl(g, Yall, ldY, z_out, mu, var, qred, Gstore, Hz_store, work, work_bytes, true, static_cast<cudaStream_t>(stream));
+    return f_solved_impl(g, kx, Yall, ldY, z_out, mu, var, qred, Gstore, Hz_store, work, work_bytes, true,
+                         static_cast<cudaStream_t>(stream));
 }
 
 // Incremental form (after mfgp_cholesky_append): rows [row_lo, NL+NH) of the training set are new since Gstore / Hz_store

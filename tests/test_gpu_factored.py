@@ -115,7 +115,7 @@ def test_short_length_scale_keeps_the_dense_kernel():
     assert np.max(np.abs(mu.cpu().numpy() - mu_o)) <= TOL * max(1.0, np.max(np.abs(mu_o)))
 
 
-@pytest.mark.parametrize("route", ["direct", "m"])
+@pytest.mark.parametrize("route", ["direct", "m", "m-full"])
 @pytest.mark.parametrize("nx,ny,N,multi", [(64, 64, 300, True), (96, 80, 700, True), (72, 72, 200, False)])
 def test_fused_fit_and_factored_posterior(nx, ny, N, multi, route, monkeypatch):
     """Deferred fit: refactor(check=False) only marks the factor stale, the factored posterior then runs
@@ -124,7 +124,11 @@ def test_fused_fit_and_factored_posterior(nx, ny, N, multi, route, monkeypatch):
     from mfgp_coverage_b200._coverage import CoverageGrid
     # both routes of steps 4 + 5: "direct" (Y' per column, Gram over the training rows) and "m" (M = Y^T Y once, quadratic
     # forms per column); the library's cost model picks one, MFGP_GRAM forces it
-    monkeypatch.setenv("MFGP_GRAM", route)
+    # "m" carries the truncated column layout (product-magnitude truncation of the Chebyshev tensor block, the default),
+    # "m-full" the whole rx x ry block
+    from mfgp_coverage_b200 import _engine as eng_mod
+    monkeypatch.setenv("MFGP_GRAM", route.split("-")[0])
+    monkeypatch.setattr(eng_mod, "TRUNCATE", route != "m-full")
     xy = _tensor_grid(nx, ny)
     f = synth.truth_function(xy)
     X_L, y_L, X_H, y_H = synth.training_set(xy, f, N, multi=multi)
@@ -146,6 +150,10 @@ def test_fused_fit_and_factored_posterior(nx, ny, N, multi, route, monkeypatch):
         assert e._dirty
         m.predict_device(grid.xy, mu, var, grid=grid)
         assert not e._dirty and e._w_partial
+        plan = e._fplan[1]
+        full = max(plan["ryL"], plan["ryH"]) * (-(-max(plan["rxL"], plan["rxH"]) // 4) * 4)
+        assert e.fused_gram == (route != "direct")
+        assert e.rhs_cols[0] < full if route == "m" else e.rhs_cols[0] == full
         assert np.max(np.abs(var.cpu().numpy() - var_o)) <= TOL * p.k0
         assert np.max(np.abs(mu.cpu().numpy() - mu_o)) <= TOL * max(1.0, np.max(np.abs(mu_o)))
     e.check_factor(force=True)
@@ -300,3 +308,30 @@ def test_factored_posterior_with_near_zero_noise(golden_dir, hyp_name, fused, mo
     assert np.max(np.abs(var.cpu().numpy()[idx] - var_o)) <= TOL * p.k0
     assert np.max(np.abs(mu.cpu().numpy()[idx] - mu_o)) <= max(TOL * max(1.0, np.max(np.abs(mu_o))), 4.0 * spread_mu)
     assert float(var.min()) > -1e-12 * p.k0
+
+
+def test_truncated_layout_agrees_with_the_full_tensor_block(monkeypatch):
+    """The truncated column layout drops only terms whose coefficient bound is below 1e-16: mean and variance agree with the
+    full rx x ry block to 1e-13 k(0) (far inside the 1e-9 of the parity tests), with a third fewer right-hand sides."""
+    from mfgp_coverage_b200._coverage import CoverageGrid
+    from mfgp_coverage_b200 import _engine as eng_mod
+    xy = _tensor_grid(160, 128)
+    f = synth.truth_function(xy)
+    X_L, y_L, X_H, y_H = synth.training_set(xy, f, 900, multi=True)
+    p = ogp.GPParams.from_hyp(synth.MF_HYP)
+    grid = CoverageGrid(xy)
+    res, cols = {}, {}
+    for trunc in (True, False):
+        monkeypatch.setattr(eng_mod, "TRUNCATE", trunc)
+        m = _model(synth.MF_HYP, X_L, y_L, X_H, y_H, True)
+        m.engine.factored_min_gain = 0.0
+        m.engine.defer_fit = True
+        m.engine.refactor(check=False)
+        mu = torch.empty(grid.G, dtype=torch.float64, device=grid.device)
+        var = torch.empty(grid.G, dtype=torch.float64, device=grid.device)
+        m.predict_device(grid.xy, mu, var, grid=grid)
+        m.engine.check_factor(force=True)
+        res[trunc], cols[trunc] = (mu.cpu().numpy(), var.cpu().numpy()), m.engine.rhs_cols
+    assert cols[True][0] <= 0.8 * cols[False][0]
+    assert np.max(np.abs(res[True][1] - res[False][1])) <= 1e-13 * p.k0
+    assert np.max(np.abs(res[True][0] - res[False][0])) <= 1e-13 * max(1.0, np.max(np.abs(res[False][0])))

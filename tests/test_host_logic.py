@@ -227,6 +227,34 @@ def test_two_queue_gram_policy_cannot_deadlock_and_keeps_group_order():
         assert all(v == ngroups - 1 for v in seen.values())
 
 
+def test_chebyshev_truncation_table():
+    """The truncated column layout of the factored posterior (host side, _engine.chebyshev_truncation): per y term a multiple
+    of 4 between 4 and kpad, non-increasing, full width for the leading terms; every dropped term's coefficient bound is
+    below the tolerance and their sum stays under the 5e-15 the orders were chosen for; c4's 36 x 36 block shrinks by a third."""
+    from mfgp_coverage_b200 import _engine as E
+    hull = (-0.05, 1.05)
+    for lH, lL, lo, hi in ((0.2, 0.58, 0.0, 1.0), (0.2, 0.58, 0.5, 0.625), (0.35, 0.9, 0.0, 1.0)):
+        rH = E.chebyshev_order(lH, lo, hi, *hull)
+        rL = E.chebyshev_order(lL, lo, hi, *hull)
+        ryH, ryL = E.chebyshev_order(lH, 0.0, 1.0, *hull), E.chebyshev_order(lL, 0.0, 1.0, *hull)
+        kp = -(-max(rH, rL) // 4) * 4
+        parts = [(np.pad(E.chebyshev_envelope(lH, lo, hi, *hull, rH), (0, kp - rH)), E.chebyshev_envelope(lH, 0.0, 1.0, *hull, ryH)),
+                 (np.pad(E.chebyshev_envelope(lL, lo, hi, *hull, rL), (0, kp - rL)), E.chebyshev_envelope(lL, 0.0, 1.0, *hull, ryL))]
+        ry = max(ryH, ryL)
+        kx = E.chebyshev_truncation(parts, kp, ry)
+        assert kx.dtype == np.int32 and kx.size == ry and np.all(kx % 4 == 0) and kx.min() >= 4 and kx.max() <= kp
+        assert np.all(np.diff(kx) <= 0) and kx[0] == kp
+        dropped = 0.0
+        for ax, ay in parts:
+            for l in range(ay.size):
+                tail = ay[l] * ax[kx[l]:]
+                assert tail.size == 0 or tail.max() <= 1e-16
+                dropped += float(tail.sum())
+        assert dropped <= 5e-15
+        if (lH, lo, hi) == (0.2, 0.0, 1.0):
+            assert (rH, ryH) == (36, 36) and kx.sum() <= 0.7 * 36 * 36
+
+
 def test_vectorised_finishing_is_bitwise_the_reference_loop():
     """loss_from_partials / centroids_from_partials are elementwise over the cells; they must give bit for bit what the
     reference's per-cell statements give (simulator.py:215-219, :256-271), empty cells (0/0 -> NaN) included."""
