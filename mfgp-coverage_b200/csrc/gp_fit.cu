@@ -78,9 +78,14 @@ struct PotrfScratch {
     int bad;
 };
 
+// BS = 64: the whole tile (s, m: 4x4 cyclic sub-blocks per thread); BS = 32: one half of the two-level form below (2x2).
+// `col0`: global index of the block's first column (for the failing-pivot report).  Ls / Wsm (optional, shared memory, row
+// stride lds_out): copies of L and of its inverse for the caller's next step.
+template <int BS>
 __device__ __forceinline__ void potrf_diag_body(const double* src, int64_t lds, double* A, int64_t ld,
-                                                double* __restrict__ Winv, int64_t ldw, int32_t* __restrict__ info, int jblk,
-                                                PotrfScratch* sc) {
+                                                double* __restrict__ Winv, int64_t ldw, int32_t* __restrict__ info, int col0,
+                                                PotrfScratch* sc, double* Lsm = nullptr, double* Wsm = nullptr, int lds_out = 0) {
+    constexpr int NB = BS / 16;
     double2 (*colAB)[PB] = sc->colAB;
     double2 (*rowAB)[PB] = sc->rowAB;
     double (*piv)[PB / 2] = sc->piv;
@@ -89,29 +94,29 @@ __device__ __forceinline__ void potrf_diag_body(const double* src, int64_t lds, 
     const int tid = threadIdx.x;
     const int ti = tid >> 4, tc = tid & 15;
     if (tid == 0) bad = 0;
-    double s[4][4], m[4][4];
+    double s[NB][NB], m[NB][NB];
 #pragma unroll
-    for (int a = 0; a < 4; a++)
+    for (int a = 0; a < NB; a++)
 #pragma unroll
-        for (int b = 0; b < 4; b++) {
+        for (int b = 0; b < NB; b++) {
             const int r = ti + 16 * a, c = tc + 16 * b;
             s[a][b] = (c <= r) ? src[(int64_t)r * lds + c] : 0.0;
             m[a][b] = (r == c) ? 1.0 : 0.0;
         }
 #pragma unroll
-    for (int jb = 0; jb < 4; jb++) {
+    for (int jb = 0; jb < NB; jb++) {
 #pragma unroll 1
         for (int jp = 0; jp < 8; jp++) {
             const int k = jb * 8 + jp, j0 = 2 * k, j1 = j0 + 1, jj0 = 2 * jp, buf = k & 1;
             if ((tc & 14) == jj0) {          // owners of columns j0 (tc even) and j1 (tc odd); rows above are never read
                 double* dst = reinterpret_cast<double*>(colAB[buf]) + (tc & 1);
 #pragma unroll
-                for (int a = 0; a < 4; a++) dst[2 * (ti + 16 * a)] = s[a][jb];
+                for (int a = 0; a < NB; a++) dst[2 * (ti + 16 * a)] = s[a][jb];
             }
             if ((ti & 14) == jj0) {          // owners of rows j0, j1 of M
                 double* dst = reinterpret_cast<double*>(rowAB[buf]) + (ti & 1);
 #pragma unroll
-                for (int b = 0; b < 4; b++) dst[2 * (tc + 16 * b)] = m[jb][b];
+                for (int b = 0; b < NB; b++) dst[2 * (tc + 16 * b)] = m[jb][b];
             }
             __syncthreads();
             const double2* col = colAB[buf];
@@ -123,38 +128,38 @@ __device__ __forceinline__ void potrf_diag_body(const double* src, int64_t lds, 
             if (!(pa > 0.0) || !(det > 0.0)) {          // uniform
                 if (tid == 0 && !bad) {
                     bad = 1;
-                    atomicCAS(info, 0, jblk * PB + ((pa > 0.0) ? j1 : j0) + 1);
+                    atomicCAS(info, 0, col0 + ((pa > 0.0) ? j1 : j0) + 1);
                 }
                 pa = 1.0; pb = 0.0; pc = 1.0; det = 1.0;
             }
             if (tid == 0) { piv[0][k] = pa; piv[1][k] = pb; piv[2][k] = pc; }
             const double idet = 1.0 / det;
             const double qa = pc * idet, qb = -pb * idet, qc = pa * idet;      // P^-1
-            double t1[4], t2[4];
+            double t1[NB], t2[NB];
 #pragma unroll
-            for (int a = 0; a < 4; a++) {
+            for (int a = 0; a < NB; a++) {
                 if (a < jb) continue;                       // rows of earlier 16-groups are final
                 const double2 x = col[ti + 16 * a];
                 t1[a] = fma(qa, x.x, qb * x.y);
                 t2[a] = fma(qb, x.x, qc * x.y);
             }
 #pragma unroll
-            for (int b = 0; b < 4; b++) {
+            for (int b = 0; b < NB; b++) {
                 if (b < jb) continue;                       // columns of earlier 16-groups are final
                 const double2 y = col[tc + 16 * b];
                 const bool live = tc + 16 * b > j1;         // only columns right of the pair change
 #pragma unroll
-                for (int a = 0; a < 4; a++) {
+                for (int a = 0; a < NB; a++) {
                     if (a < b) continue;                    // register groups strictly above the diagonal are never read
                     if (live) s[a][b] = fma(-t1[a], y.x, fma(-t2[a], y.y, s[a][b]));
                 }
             }
 #pragma unroll
-            for (int b = 0; b < 4; b++) {
+            for (int b = 0; b < NB; b++) {
                 if (b > jb) continue;                       // rows j0, j1 of M are zero right of column j1
                 const double2 z = row[tc + 16 * b];
 #pragma unroll
-                for (int a = 0; a < 4; a++) {
+                for (int a = 0; a < NB; a++) {
                     if (a < jb) continue;                   // rows of earlier 16-groups are final
                     const bool live = ti + 16 * a > j1;     // only rows below the pair change
                     if (live) m[a][b] = fma(-t1[a], z.x, fma(-t2[a], z.y, m[a][b]));
@@ -163,7 +168,7 @@ __device__ __forceinline__ void potrf_diag_body(const double* src, int64_t lds, 
         }
     }
     __syncthreads();
-    if (tid < PB / 2) {          // C = chol(P) of every pair
+    if (tid < BS / 2) {          // C = chol(P) of every pair
         const double a = piv[0][tid], b = piv[1][tid], c = piv[2][tid];
         const double r1 = rsqrt(a);
         const double g = b * r1 * r1;
@@ -174,9 +179,9 @@ __device__ __forceinline__ void potrf_diag_body(const double* src, int64_t lds, 
     __syncthreads();
     const bool failed = bad != 0;
 #pragma unroll
-    for (int a = 0; a < 4; a++)
+    for (int a = 0; a < NB; a++)
 #pragma unroll
-        for (int b = 0; b < 4; b++) {
+        for (int b = 0; b < NB; b++) {
             const int r = ti + 16 * a, c = tc + 16 * b;
             const double v = s[a][b], w = m[a][b];
             const double vp = __shfl_up_sync(0xffffffffu, v, 1);       // same row, column c-1
@@ -185,15 +190,19 @@ __device__ __forceinline__ void potrf_diag_body(const double* src, int64_t lds, 
             const double lv = (c & 1) ? (v - fin[2][kc] * vp) * fin[1][kc] : v * fin[0][kc];
             const double wv = (r & 1) ? (w - fin[2][kr] * wp) * fin[1][kr] : w * fin[0][kr];
             // on failure leave a harmless identity so later kernels stay finite; the host raises on `info`
-            if (c <= r) A[(int64_t)r * ld + c] = failed ? ((r == c) ? 1.0 : 0.0) : lv;
-            if (Winv != nullptr) Winv[(int64_t)r * ldw + c] = failed ? ((r == c) ? 1.0 : 0.0) : ((c <= r) ? wv : 0.0);
+            const double lo = failed ? ((r == c) ? 1.0 : 0.0) : ((c <= r) ? lv : 0.0);
+            const double wo = failed ? ((r == c) ? 1.0 : 0.0) : ((c <= r) ? wv : 0.0);
+            if (c <= r) A[(int64_t)r * ld + c] = lo;
+            if (Winv != nullptr) Winv[(int64_t)r * ldw + c] = wo;
+            if (Lsm != nullptr) Lsm[r * lds_out + c] = lo;
+            if (Wsm != nullptr) Wsm[r * lds_out + c] = wo;
         }
 }
 
 __global__ void __launch_bounds__(256, 1) potrf_diag_kernel(double* __restrict__ A, int64_t ld, double* __restrict__ Winv,
                                                          int64_t ldw, int32_t* __restrict__ info, int jblk) {
     __shared__ __align__(16) PotrfScratch scratch;
-    potrf_diag_body(A, ld, A, ld, Winv, ldw, info, jblk, &scratch);
+    potrf_diag_body<PB>(A, ld, A, ld, Winv, ldw, info, jblk * PB, &scratch);
 }
 
 // ---- tiled Cholesky + forward substitution as ONE persistent dataflow kernel -----------------------------------------
@@ -724,7 +733,67 @@ __global__ void __launch_bounds__(DF_THREADS, 2) chol_dataflow_kernel(DfArgs g) 
                 __syncthreads();
             }
             df_stamp(g.trace, idx, 4);
-            potrf_diag_body(Xs, DF_LDT, Cd, g.ld, Wd, g.ldw, g.info, idx, reinterpret_cast<PotrfScratch*>(Ws));      // W_cc is spent
+            // Two-level factor + inverse of the 64x64 diagonal tile S (in Xs): the pair-step sweep is latency-bound per step, and a
+            // 32x32 block needs half the steps at half the work per step, so  [S11 .; S21 S22] -> L11, W11 = L11^-1 (sweep);
+            // L21 = S21 W11^T; S22 -= L21 L21^T; L22, W22 (sweep); W21 = -W22 (L21 W11), the four small products on DMMA.
+            {
+                PotrfScratch* sc = reinterpret_cast<PotrfScratch*>(Ws);       // W_cc is spent
+                constexpr int H = PB / 2, LO = DF_LDT;
+                double* L11s = Ls;                       // rows 0..31 of the Ls region: [L11 | W11]
+                double* W11s = Ls + H;
+                double* L21s = Ls + H * LO;              // rows 32..63: [L21 | T = L21 W11]
+                double* Tsm = Ls + H * LO + H;
+                double* W22s = Xs;                       // S11 is consumed by then
+                // 32x32x32 products on DMMA: warp w owns row tile w >> 1 and the column tiles 2 (w & 1), 2 (w & 1) + 1
+                const int m0 = (warp >> 1) * 8, n0 = (warp & 1) * 16;
+                auto mm32 = [&](const double* A, const double* B, bool b_nk, double (&c)[2][2]) {
+                    c[0][0] = c[0][1] = c[1][0] = c[1][1] = 0.0;
+#pragma unroll
+                    for (int kk = 0; kk < H; kk += 4) {
+                        const double av = A[(m0 + gq) * LO + kk + tq];
+#pragma unroll
+                        for (int j = 0; j < 2; j++) {
+                            const double bv = b_nk ? B[(n0 + 8 * j + gq) * LO + kk + tq] : B[(kk + tq) * LO + n0 + 8 * j + gq];
+                            dmma884(c[j][0], c[j][1], av, bv);
+                        }
+                    }
+                };
+                double c[2][2];
+                potrf_diag_body<H>(Xs, LO, Cd, g.ld, Wd, g.ldw, g.info, idx * PB, sc, L11s, W11s, LO);
+                __syncthreads();
+                mm32(Xs + H * LO, W11s, true, c);                    // L21 = S21 W11^T  (W11's upper part is stored as zeros)
+#pragma unroll
+                for (int j = 0; j < 2; j++) {
+                    const int r = m0 + gq, cc = n0 + 8 * j + tq * 2;
+                    *reinterpret_cast<double2*>(Cd + (int64_t)(H + r) * g.ld + cc) = make_double2(c[j][0], c[j][1]);
+                    L21s[r * LO + cc] = c[j][0]; L21s[r * LO + cc + 1] = c[j][1];
+                }
+                __syncthreads();
+                mm32(L21s, L21s, true, c);                           // S22 -= L21 L21^T
+#pragma unroll
+                for (int j = 0; j < 2; j++) {
+                    const int r = m0 + gq, cc = n0 + 8 * j + tq * 2;
+                    Xs[(H + r) * LO + H + cc] -= c[j][0]; Xs[(H + r) * LO + H + cc + 1] -= c[j][1];
+                }
+                __syncthreads();
+                potrf_diag_body<H>(Xs + H * LO + H, LO, Cd + (int64_t)H * g.ld + H, g.ld, Wd + (int64_t)H * g.ldw + H, g.ldw, g.info,
+                                   idx * PB + H, sc, nullptr, W22s, LO);
+                __syncthreads();
+                mm32(L21s, W11s, false, c);                          // T = L21 W11
+#pragma unroll
+                for (int j = 0; j < 2; j++) {
+                    const int r = m0 + gq, cc = n0 + 8 * j + tq * 2;
+                    Tsm[r * LO + cc] = c[j][0]; Tsm[r * LO + cc + 1] = c[j][1];
+                }
+                __syncthreads();
+                mm32(W22s, Tsm, false, c);                           // W21 = -W22 T;  W12 = 0
+#pragma unroll
+                for (int j = 0; j < 2; j++) {
+                    const int r = m0 + gq, cc = n0 + 8 * j + tq * 2;
+                    *reinterpret_cast<double2*>(Wd + (int64_t)(H + r) * g.ldw + cc) = make_double2(-c[j][0], -c[j][1]);
+                    *reinterpret_cast<double2*>(Wd + (int64_t)r * g.ldw + H + cc) = make_double2(0.0, 0.0);
+                }
+            }
             myflag = g.flagsL + (int64_t)idx * g.nb + idx;
             df_stamp(g.trace, idx, 5);
         }
@@ -883,9 +952,11 @@ int chol_dataflow(double* K, int64_t npad, int64_t ld, double* W, int64_t ldw, i
     a.total = nb + (nb - 1) * (nb - 2) / 2 + nb * nr;     // nb chain tasks, the tiles two or more below the diagonal, Y tiles
     if (M != nullptr && nr > 0) {
         // Gram tasks: groups of mg block rows (short tasks fill the chain-bound tail better; every task re-reads and re-writes
-        // its 32 KB tile of M), drawn only while the critical queue is m_lead block columns ahead of the chain
+        // its 32 KB tile of M), drawn only while the critical queue is m_lead block columns ahead of the chain.  Measured
+        // (N = 4096; 384 / 832 / 1344 right-hand sides): leads of 16 and more -- in effect "when the critical queue has run
+        // dry", the chain-bound last block columns -- are best (1.53 / 1.79 / 2.19 ms against 1.56 / 1.87 / 2.25 ms at 8)
         static const int mg_env = [] { const char* e = getenv("MFGP_DF_MG"); return e ? atoi(e) : 8; }();
-        static const int lead_env = [] { const char* e = getenv("MFGP_DF_MLEAD"); return e ? atoi(e) : 8; }();
+        static const int lead_env = [] { const char* e = getenv("MFGP_DF_MLEAD"); return e ? atoi(e) : 32; }();
         a.M = M; a.ldm = ldm; a.flagsM = a.flagsY + (int64_t)nb * nr;
         a.mg = mg_env < DF_MIN_MG ? DF_MIN_MG : mg_env;
         a.m_tiles = nr * (nr + 1) / 2;

@@ -63,6 +63,24 @@ def pair_step_factor(S):
 # Task kinds (chol_dataflow_kernel): ("chain", d): sub-diagonal tile (d, d-1) + diagonal tile (d, d) + factor/inverse of block d;
 # ("L", i, c): tile (i, c) of L, i >= c + 2;  ("Y", c, r): tile (c, r) of Y = L^-1 B.
 
+def two_level_factor(S):
+    """The diagonal tile of a chain task (csrc/gp_fit.cu, chol_dataflow_kernel): the pair-step sweep on the two 32x32 halves,
+    glued by three small products --  L11, W11 = sweep(S11);  L21 = S21 W11^T;  L22, W22 = sweep(S22 - L21 L21^T);
+    W21 = -W22 (L21 W11).  Returns (L, W = L^-1, info) like pair_step_factor; the first failing pivot wins."""
+    n = S.shape[0]
+    h = n // 2
+    L11, W11, info1 = pair_step_factor(S[:h, :h])
+    L21 = S[h:, :h] @ np.tril(W11).T
+    L22, W22, info2 = pair_step_factor(S[h:, h:] - L21 @ L21.T)
+    L = np.zeros_like(S)
+    W = np.zeros_like(S)
+    L[:h, :h], L[h:, :h], L[h:, h:] = L11, L21, L22
+    W[:h, :h], W[h:, h:] = W11, W22
+    W[h:, :h] = -np.tril(W22) @ (L21 @ np.tril(W11))
+    info = info1 if info1 else (info2 + h if info2 else 0)
+    return L, W, info
+
+
 def chain_place(d, chain_la=5):
     """Block column whose ticket batch holds chain task d >= 1: d // chain_la columns ahead of column d - 1 (its k loop is
     the longest of the column, so it starts early and is done accumulating when W_{d-1} arrives)."""

@@ -299,6 +299,11 @@ def test_pair_step_factorisation_matches_lapack():
         assert info == 0
         assert np.max(np.abs(L - Lref)) <= 1e-15 * cond * np.max(np.abs(Lref)) + 1e-15
         assert np.max(np.abs(W @ Lref - np.eye(n))) <= 1e-14 * cond
+        if n >= 4:                                         # the chain task's form: two half-size sweeps + three small products
+            L2, W2, info2 = tc.two_level_factor(S)
+            assert info2 == 0
+            assert np.max(np.abs(L2 - Lref)) <= 1e-15 * cond * np.max(np.abs(Lref)) + 1e-15
+            assert np.max(np.abs(W2 @ Lref - np.eye(n))) <= 1e-14 * cond
     S = (q * np.logspace(0, -3, 64)) @ q.T
     Lr = np.linalg.cholesky(S)
     for bad in (0, 5, 38, 63):
@@ -307,6 +312,7 @@ def test_pair_step_factorisation_matches_lapack():
         _, info_ref = sl.lapack.dpotrf(Sb, lower=1)
         L, W, info = tc.pair_step_factor(Sb)
         assert info == info_ref == bad + 1 and np.array_equal(L, np.eye(64)) and np.array_equal(W, np.eye(64))
+        assert tc.two_level_factor(Sb)[2] == info_ref
 
 
 def test_dataflow_ticket_order_is_topological():
