@@ -11,8 +11,22 @@ namespace mfgp {
 // K_LL = k_L + noise_L I, K_LH = rho k_L, K_HH = rho^2 k_L + k_H + noise_H I, then + jitter I (gaussian_process.py:
 // 523-529); SF: k + noise I + jitter I (:253-254).  Padding rows/cols [N, npad) carry the identity.  K is symmetric and
 // the factorisation reads its lower triangle only, so tiles strictly above the diagonal are left untouched.
+// Tt[i] = (x_i / l_L, y_i / l_L, x_i / l_H, y_i / l_H): the operands of rbf_scaled, divided ONCE per training point (the same
+// IEEE divisions the reference performs per pair, gaussian_process.py:75-79) -- the covariance assembly then has no division left.
+__global__ void scaled_coords_kernel(const double* __restrict__ Xt, int N, int npad, DevParams p, double* __restrict__ Tt) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npad) return;
+    double4 t = make_double4(0.0, 0.0, 0.0, 0.0);
+    if (i < N) {
+        const double xi = Xt[2 * i], yi = Xt[2 * i + 1];
+        t = make_double4(xi / p.l_L, yi / p.l_L, xi / p.l_H, yi / p.l_H);
+    }
+    reinterpret_cast<double4*>(Tt)[i] = t;
+}
+
+// Tt != nullptr: the pre-divided coordinates (scaled_coords_kernel ran before); nullptr: divide here.
 __global__ void build_train_cov_kernel(const double* __restrict__ Xt, int NL, int NH, DevParams p, double* __restrict__ K,
-                                       int npad, int64_t ld, double* __restrict__ Tt, int row_begin) {
+                                       int npad, int64_t ld, const double* __restrict__ Tt, int row_begin) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     const int i = row_begin + blockIdx.y * blockDim.y + threadIdx.y;
     const int N = NL + NH;
@@ -22,35 +36,35 @@ __global__ void build_train_cov_kernel(const double* __restrict__ Xt, int NL, in
     if (i >= N || j >= N) {
         v = (i == j) ? 1.0 : 0.0;
     } else {
-        const double xi = Xt[2 * i], yi = Xt[2 * i + 1], xj = Xt[2 * j], yj = Xt[2 * j + 1];
+        double4 a, b;          // (x / l_L, y / l_L, x / l_H, y / l_H) of points i and j
+        if (Tt != nullptr) {
+            a = reinterpret_cast<const double4*>(Tt)[i];
+            b = reinterpret_cast<const double4*>(Tt)[j];
+        } else {
+            const double xi = Xt[2 * i], yi = Xt[2 * i + 1], xj = Xt[2 * j], yj = Xt[2 * j + 1];
+            a = make_double4(xi / p.l_L, yi / p.l_L, xi / p.l_H, yi / p.l_H);
+            b = make_double4(xj / p.l_L, yj / p.l_L, xj / p.l_H, yj / p.l_H);
+        }
         const bool iL = i < NL, jL = j < NL;
         if (p.multi) {
-            const double kL = rbf_scaled(xi / p.l_L, yi / p.l_L, xj / p.l_L, yj / p.l_L, p.s_L);
+            const double kL = rbf_scaled(a.x, a.y, b.x, b.y, p.s_L);
             if (iL && jL) {
                 v = kL;
                 if (i == j) v = v + p.noise_L;
             } else if (iL != jL) {
                 v = p.rho * kL;
             } else {
-                const double kH = rbf_scaled(xi / p.l_H, yi / p.l_H, xj / p.l_H, yj / p.l_H, p.s_H);
+                const double kH = rbf_scaled(a.z, a.w, b.z, b.w, p.s_H);
                 v = __dadd_rn(__dmul_rn(p.rho2, kL), kH);
                 if (i == j) v = v + p.noise_H;
             }
         } else {
-            v = rbf_scaled(xi / p.l_H, yi / p.l_H, xj / p.l_H, yj / p.l_H, p.s_H);
+            v = rbf_scaled(a.z, a.w, b.z, b.w, p.s_H);
             if (i == j) v = v + p.noise_H;
         }
         if (i == j) v = v + p.jitter;
     }
     K[(int64_t)i * ld + j] = v;
-    if (j == 0 && Tt != nullptr) {
-        double4 t = make_double4(0.0, 0.0, 0.0, 0.0);
-        if (i < N) {
-            const double xi = Xt[2 * i], yi = Xt[2 * i + 1];
-            t = make_double4(xi / p.l_L, yi / p.l_L, xi / p.l_H, yi / p.l_H);
-        }
-        reinterpret_cast<double4*>(Tt)[i] = t;
-    }
 }
 
 // ---- 64x64 diagonal block: Cholesky + inverse in one CTA --------------------------------------------------------------
@@ -875,7 +889,12 @@ extern "C" int mfgp_build_train_cov(const double* Xt, int64_t NL, int64_t NH, co
     if (!p_host->multi && NL != 0) return MFGP_ERR_INVALID;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     dim3 block(32, 8), grid((unsigned)((npad + 31) / 32), (unsigned)((npad + 7) / 8));
-    build_train_cov_kernel<<<grid, block, 0, st>>>(Xt, (int)NL, (int)NH, make_dev_params(*p_host), K, (int)npad, ld, Tt, 0);
+    const DevParams dp = make_dev_params(*p_host);
+    if (Tt) {
+        scaled_coords_kernel<<<(unsigned)((npad + 255) / 256), 256, 0, st>>>(Xt, (int)(NL + NH), (int)npad, dp, Tt);
+        MFGP_LAUNCH_CHECK();
+    }
+    build_train_cov_kernel<<<grid, block, 0, st>>>(Xt, (int)NL, (int)NH, dp, K, (int)npad, ld, Tt, 0);
     MFGP_LAUNCH_CHECK();
     return MFGP_OK;
 }
@@ -1209,6 +1228,10 @@ extern "C" int mfgp_cholesky_append(const double* Xt, int64_t NL, int64_t NH_old
     constexpr int POTRF_SMEM = 0;   // the factor + inverse sweep lives in registers and static shared memory
     MFGP_CUDA_CHECK(cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, POTRF_SMEM));
     double* part = static_cast<double*>(work);
+    if (Tt) {              // pre-divided coordinates of ALL rows (the blocks below read the old rows' as well)
+        scaled_coords_kernel<<<(unsigned)((npad + 255) / 256), 256, 0, st>>>(Xt, (int)N_new, (int)npad, dp, Tt);
+        MFGP_LAUNCH_CHECK();
+    }
     for (int64_t rb = N_old / PB * PB; rb < npad; rb += PB) {
         {   // covariance rows of the block: columns [0, rb+64) are used, the rest of the row is rewritten too (harmless)
             dim3 block(32, 8), grid((unsigned)((rb + PB + 31) / 32), PB / 8);
