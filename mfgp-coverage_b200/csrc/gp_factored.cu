@@ -408,10 +408,17 @@ struct QformArgs {
 // CTA = 64 grid columns x a range of (l, l') pairs, l' <= l; warp w owns columns 16 w .. 16 w + 15 (two 8-row DMMA tiles).
 // Per pair: T = U_blk (64 x kpad) * M_{l l'} (kpad x kpad) on DMMA, then the row-wise dot with U_blk straight off the
 // accumulator fragments (two lane shuffles).  The A fragments (U) stay in registers for the whole CTA.
-template <int NT>         // n tiles of 8: kpad <= 8 NT
+// STAGED (kpad <= 48): the kx[l] x kx[l'] block of M goes through shared memory -- fetched by the whole CTA with coalesced loads
+// one pair AHEAD (into registers, parked in shared memory behind the current pair's barrier), so its L2 round trip hides behind
+// the DMMA work; !STAGED: every thread loads its B fragments straight from M (four-fold redundant scattered loads: 134 us at
+// c4 where the staged form needs 40).
+template <int NT, bool STAGED>         // n tiles of 8: kpad <= 8 NT
 __global__ void __launch_bounds__(128) qform_kernel(QformArgs a) {
     constexpr int KS = 2 * NT;                                   // k steps of 4
+    constexpr int LD = STAGED ? (NT <= 4 ? 36 : 52) : 1;         // 2 LD = 8 (mod 32): conflict-free [k][n] fragment reads
+    constexpr int PRE = STAGED ? (8 * NT * 8 * NT + 127) / 128 : 1;
     __shared__ double Us[64][8 * NT + 1];
+    __shared__ double Bs[STAGED ? 8 * NT * LD : 1];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, gq = lane >> 2, tq = lane & 3;
     const int c0 = blockIdx.x * 64;
     for (int e = tid; e < 64 * 8 * NT; e += 128) {
@@ -431,7 +438,38 @@ __global__ void __launch_bounds__(128) qform_kernel(QformArgs a) {
     while ((l + 1) * (l + 2) / 2 <= p) l++;
     while (l * (l + 1) / 2 > p) l--;
     int lp = p - l * (l + 1) / 2;
+    double pre[PRE];
+    auto fetch = [&](int fl, int flp) {              // this thread's share of block (fl, flp) of M -> registers
+        const int ra = a.tr.off[fl], rb = a.tr.off[flp], kb = a.tr.kx[flp], n_el = a.tr.kx[fl] * kb;
+#pragma unroll
+        for (int i = 0; i < PRE; i++) {
+            const int e = tid + 128 * i;
+            double v = 0.0;
+            if (e < n_el) {
+                const int r = ra + e / kb, c = rb + e % kb;        // M is symmetric, stored for row tile >= column tile
+                v = (r >= c) ? __ldg(a.M + (int64_t)r * a.ldm + c) : __ldg(a.M + (int64_t)c * a.ldm + r);
+            }
+            pre[i] = v;
+        }
+    };
+    auto stash = [&](int fl, int flp) {
+        const int kb = a.tr.kx[flp], n_el = a.tr.kx[fl] * kb;
+#pragma unroll
+        for (int i = 0; i < PRE; i++) {
+            const int e = tid + 128 * i;
+            if (e < n_el) Bs[(e / kb) * LD + e % kb] = pre[i];
+        }
+    };
+    if (STAGED && p < pend) {
+        fetch(l, lp);
+        stash(l, lp);
+        __syncthreads();
+    }
     for (; p < pend; p++) {
+        int nl = l, nlp = lp + 1;
+        if (nlp > nl) { nl++; nlp = 0; }
+        const bool more = p + 1 < pend;
+        if (STAGED && more) fetch(nl, nlp);          // in flight while this pair is computed
         double acc[2][NT][2];
 #pragma unroll
         for (int rt = 0; rt < 2; rt++)
@@ -448,8 +486,12 @@ __global__ void __launch_bounds__(128) qform_kernel(QformArgs a) {
                 const int n = j * 8 + gq;
                 double v = 0.0;
                 if (k < ka && n < kb) {
-                    const int r = ra + k, c = rb + n;              // M is symmetric, stored for row tile >= column tile
-                    v = (r >= c) ? __ldg(a.M + (int64_t)r * a.ldm + c) : __ldg(a.M + (int64_t)c * a.ldm + r);
+                    if (STAGED) {
+                        v = Bs[k * LD + n];
+                    } else {
+                        const int r = ra + k, c = rb + n;
+                        v = (r >= c) ? __ldg(a.M + (int64_t)r * a.ldm + c) : __ldg(a.M + (int64_t)c * a.ldm + r);
+                    }
                 }
                 b[j] = v;
             }
@@ -476,7 +518,14 @@ __global__ void __launch_bounds__(128) qform_kernel(QformArgs a) {
                 g[lp * F_LW + l] = q;
             }
         }
-        if (++lp > l) { l++; lp = 0; }
+        if (STAGED) {
+            __syncthreads();                         // every warp is done with this pair's block
+            if (more) {
+                stash(nl, nlp);
+                __syncthreads();
+            }
+        }
+        l = nl; lp = nlp;
     }
 }
 
@@ -855,14 +904,14 @@ int f_tail_gram(const FGeom& g, FLayout& L, const double* Yall, int64_t ldY, dou
     groups = (npairs + qa.pairs_per_cta - 1) / qa.pairs_per_cta;
     const dim3 qgrid((unsigned)cblocks, (unsigned)groups);
     switch (nt8) {
-        case 1: qform_kernel<1><<<qgrid, 128, 0, st>>>(qa); break;
-        case 2: qform_kernel<2><<<qgrid, 128, 0, st>>>(qa); break;
-        case 3: qform_kernel<3><<<qgrid, 128, 0, st>>>(qa); break;
-        case 4: qform_kernel<4><<<qgrid, 128, 0, st>>>(qa); break;
-        case 5: qform_kernel<5><<<qgrid, 128, 0, st>>>(qa); break;
-        case 6: qform_kernel<6><<<qgrid, 128, 0, st>>>(qa); break;
-        case 7: qform_kernel<7><<<qgrid, 128, 0, st>>>(qa); break;
-        default: qform_kernel<8><<<qgrid, 128, 0, st>>>(qa); break;
+        case 1: qform_kernel<1, true><<<qgrid, 128, 0, st>>>(qa); break;
+        case 2: qform_kernel<2, true><<<qgrid, 128, 0, st>>>(qa); break;
+        case 3: qform_kernel<3, true><<<qgrid, 128, 0, st>>>(qa); break;
+        case 4: qform_kernel<4, true><<<qgrid, 128, 0, st>>>(qa); break;
+        case 5: qform_kernel<5, true><<<qgrid, 128, 0, st>>>(qa); break;
+        case 6: qform_kernel<6, true><<<qgrid, 128, 0, st>>>(qa); break;
+        case 7: qform_kernel<7, false><<<qgrid, 128, 0, st>>>(qa); break;
+        default: qform_kernel<8, false><<<qgrid, 128, 0, st>>>(qa); break;
     }
     MFGP_LAUNCH_CHECK();
     // step 6 (and h'(ix)): G' comes from the buffer, nothing else to add
