@@ -608,6 +608,77 @@ __global__ void __launch_bounds__(256) geval_kernel(const double* __restrict__ G
     }
 }
 
+// The same step 6 on the tensor pipe: per grid column T' = Uy (ny x WM) B' (WM x WM) with B' the lower triangle of G'(ix), strictly
+// lower entries doubled (u^T G' u = sum_{n <= k} B'[k][n] u_k u_n), then the row-wise dot with Uy straight off the accumulator
+// fragments.  B' is lower triangular, so only the 8-column tiles j with 8 j <= 4 ks + 3 of k step ks are non-zero (30 of 50 at
+// WM = 40); its fragments stay in registers for the whole column.  The FMA form above is fully unrolled over the triangle
+// (~6000 FMAs of straight-line code per point pair, 224 registers, one CTA per SM) and reaches a quarter of the FP64 rate;
+// this one is a 30-DMMA loop body: 177 -> ~70 us at c4.
+template <int WM>
+__global__ void __launch_bounds__(128) geval_mma_kernel(const double* __restrict__ G, const double* __restrict__ Hz,
+                                                        const double* __restrict__ Ux, int kpad, int ry, FTrunc tr,
+                                                        const double* __restrict__ Uy, int ny, double mean, double k0,
+                                                        double* __restrict__ mu, double* __restrict__ var, double* __restrict__ qred) {
+    constexpr int NT = WM / 8, KS = WM / 4, GP = WM + 1;
+    __shared__ double Gs[WM * GP];
+    __shared__ double hs[WM];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, gq = lane >> 2, tq = lane & 3;
+    const int col = blockIdx.x;
+    const double* g = G + (int64_t)col * F_LW * F_LW;
+    for (int e = tid; e < WM * WM; e += 128) {
+        const int k = e / WM, n = e % WM;
+        double v = 0.0;
+        if (k < ry && n <= k) v = (n < k) ? 2.0 * g[k * F_LW + n] : g[k * F_LW + k];
+        Gs[k * GP + n] = v;
+    }
+    if (tid < WM) {
+        double h = 0.0;
+        if (tid < ry) {
+            const double* ux = Ux + (int64_t)col * kpad;
+            const double* hz = Hz + tr.off[tid];
+            for (int k = 0; k < tr.kx[tid]; k++) h = fma(ux[k], hz[k], h);
+        }
+        hs[tid] = h;
+    }
+    __syncthreads();
+    double bf[KS][NT];
+#pragma unroll
+    for (int ks = 0; ks < KS; ks++)
+#pragma unroll
+        for (int j = 0; j < NT; j++) bf[ks][j] = (8 * j <= 4 * ks + 3) ? Gs[(ks * 4 + tq) * GP + j * 8 + gq] : 0.0;
+    double h0[NT], h1[NT];
+#pragma unroll
+    for (int j = 0; j < NT; j++) { h0[j] = hs[j * 8 + 2 * tq]; h1[j] = hs[j * 8 + 2 * tq + 1]; }
+    for (int m0 = warp * 8; m0 < ny; m0 += 32) {
+        const double* up = Uy + (int64_t)min(m0 + gq, ny - 1) * F_LW;
+        double acc[NT][2];
+#pragma unroll
+        for (int j = 0; j < NT; j++) acc[j][0] = acc[j][1] = 0.0;
+#pragma unroll
+        for (int ks = 0; ks < KS; ks++) {
+            const double av = __ldg(up + ks * 4 + tq);
+#pragma unroll
+            for (int j = 0; j < NT; j++)
+                if (8 * j <= 4 * ks + 3) dmma884(acc[j][0], acc[j][1], av, bf[ks][j]);
+        }
+        double q = 0.0, m = 0.0;
+#pragma unroll
+        for (int j = 0; j < NT; j++) {
+            const double2 u = __ldg(reinterpret_cast<const double2*>(up + j * 8 + 2 * tq));
+            q = fma(acc[j][0], u.x, q); q = fma(acc[j][1], u.y, q);
+            m = fma(h0[j], u.x, m); m = fma(h1[j], u.y, m);
+        }
+        q += __shfl_xor_sync(0xffffffffu, q, 1); m += __shfl_xor_sync(0xffffffffu, m, 1);
+        q += __shfl_xor_sync(0xffffffffu, q, 2); m += __shfl_xor_sync(0xffffffffu, m, 2);
+        if (tq == 0 && m0 + gq < ny) {
+            const int64_t gidx = (int64_t)col * ny + m0 + gq;
+            var[gidx] = k0 - q;
+            mu[gidx] = mean + m;
+            if (qred) qred[gidx] = q;
+        }
+    }
+}
+
 // rows / columns [ry, WM) of every G'(ix) must read as zero for gram_eval's padded quadratic form
 __global__ void gpad_zero_kernel(double* __restrict__ G, int ry, int wm, int col_begin) {
     double* g = G + (int64_t)(col_begin + blockIdx.x) * F_LW * F_LW;
@@ -915,10 +986,17 @@ int f_tail_gram(const FGeom& g, FLayout& L, const double* Yall, int64_t ldY, dou
     }
     MFGP_LAUNCH_CHECK();
     // step 6 (and h'(ix)): G' comes from the buffer, nothing else to add
-    if (wm == 40)
-        geval_kernel<40, 2><<<(unsigned)g.ncols, 256, 0, st>>>(Gbuf, f.Hz, f.Ux, f.kpad, f.ry, L.tr, L.Uy, (int)g.ny, dp.mean_H, dp.k0, mu, var, qred);
-    else
-        geval_kernel<64, 1><<<(unsigned)g.ncols, 256, 0, st>>>(Gbuf, f.Hz, f.Ux, f.kpad, f.ry, L.tr, L.Uy, (int)g.ny, dp.mean_H, dp.k0, mu, var, qred);
+    static const bool eval_fma = [] { const char* e = getenv("MFGP_GEVAL"); return e && std::strcmp(e, "fma") == 0; }();
+    if (eval_fma) {
+        if (wm == 40)
+            geval_kernel<40, 2><<<(unsigned)g.ncols, 256, 0, st>>>(Gbuf, f.Hz, f.Ux, f.kpad, f.ry, L.tr, L.Uy, (int)g.ny, dp.mean_H, dp.k0, mu, var, qred);
+        else
+            geval_kernel<64, 1><<<(unsigned)g.ncols, 256, 0, st>>>(Gbuf, f.Hz, f.Ux, f.kpad, f.ry, L.tr, L.Uy, (int)g.ny, dp.mean_H, dp.k0, mu, var, qred);
+    } else if (wm == 40) {
+        geval_mma_kernel<40><<<(unsigned)g.ncols, 128, 0, st>>>(Gbuf, f.Hz, f.Ux, f.kpad, f.ry, L.tr, L.Uy, (int)g.ny, dp.mean_H, dp.k0, mu, var, qred);
+    } else {
+        geval_mma_kernel<64><<<(unsigned)g.ncols, 128, 0, st>>>(Gbuf, f.Hz, f.Ux, f.kpad, f.ry, L.tr, L.Uy, (int)g.ny, dp.mean_H, dp.k0, mu, var, qred);
+    }
     MFGP_LAUNCH_CHECK();
     if (Gstore && f.ry < wm) {        // the incremental update adds into the padded wm x wm block of the store: its padding must be finite
         gpad_zero_kernel<<<(unsigned)g.ncols, 128, 0, st>>>(Gbuf, f.ry, wm, 0);
