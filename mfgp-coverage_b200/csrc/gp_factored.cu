@@ -416,7 +416,7 @@ template <int NT, bool STAGED>         // n tiles of 8: kpad <= 8 NT
 __global__ void __launch_bounds__(128) qform_kernel(QformArgs a) {
     constexpr int KS = 2 * NT;                                   // k steps of 4
     constexpr int LD = STAGED ? (NT <= 4 ? 36 : 52) : 1;         // 2 LD = 8 (mod 32): conflict-free [k][n] fragment reads
-    constexpr int PRE = STAGED ? (8 * NT * 8 * NT + 127) / 128 : 1;
+    constexpr int PRE = STAGED ? 4 * NT : 1;                     // thread = (column n = tid & 63, rows (tid >> 6) + 2 i): no index division
     __shared__ double Us[64][8 * NT + 1];
     __shared__ double Bs[STAGED ? 8 * NT * LD : 1];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, gq = lane >> 2, tq = lane & 3;
@@ -440,24 +440,23 @@ __global__ void __launch_bounds__(128) qform_kernel(QformArgs a) {
     int lp = p - l * (l + 1) / 2;
     double pre[PRE];
     auto fetch = [&](int fl, int flp) {              // this thread's share of block (fl, flp) of M -> registers
-        const int ra = a.tr.off[fl], rb = a.tr.off[flp], kb = a.tr.kx[flp], n_el = a.tr.kx[fl] * kb;
+        const int ra = a.tr.off[fl], rb = a.tr.off[flp], ka = a.tr.kx[fl], kb = a.tr.kx[flp];
+        const int n = tid & 63, c = rb + n;
 #pragma unroll
         for (int i = 0; i < PRE; i++) {
-            const int e = tid + 128 * i;
+            const int k = (tid >> 6) + 2 * i, r = ra + k;
             double v = 0.0;
-            if (e < n_el) {
-                const int r = ra + e / kb, c = rb + e % kb;        // M is symmetric, stored for row tile >= column tile
+            if (k < ka && n < kb)                                  // M is symmetric, stored for row tile >= column tile
                 v = (r >= c) ? __ldg(a.M + (int64_t)r * a.ldm + c) : __ldg(a.M + (int64_t)c * a.ldm + r);
-            }
             pre[i] = v;
         }
     };
     auto stash = [&](int fl, int flp) {
-        const int kb = a.tr.kx[flp], n_el = a.tr.kx[fl] * kb;
+        const int ka = a.tr.kx[fl], kb = a.tr.kx[flp], n = tid & 63;
 #pragma unroll
         for (int i = 0; i < PRE; i++) {
-            const int e = tid + 128 * i;
-            if (e < n_el) Bs[(e / kb) * LD + e % kb] = pre[i];
+            const int k = (tid >> 6) + 2 * i;
+            if (k < ka && n < kb) Bs[k * LD + n] = pre[i];
         }
     };
     if (STAGED && p < pend) {
@@ -969,7 +968,8 @@ int f_tail_gram(const FGeom& g, FLayout& L, const double* Yall, int64_t ldY, dou
     qa.M = M; qa.ldm = (int)ldY; qa.Ux = f.Ux; qa.kpad = f.kpad; qa.tr = L.tr; qa.ry = f.ry; qa.ncols = (int)g.ncols; qa.G = Gbuf; qa.col_begin = 0;
     const int npairs = f.ry * (f.ry + 1) / 2;
     const int cblocks = (int)((g.ncols + 63) / 64);
-    int groups = (148 * 4 + cblocks - 1) / cblocks;              // ~4 CTAs per SM
+    int groups = (148 * 3) / cblocks;                            // 3 CTAs fit an SM (157 registers x 128 threads): one resident wave
+    if (groups < 1) groups = 1;
     if (groups > npairs) groups = npairs;
     qa.pairs_per_cta = (npairs + groups - 1) / groups;
     groups = (npairs + qa.pairs_per_cta - 1) / qa.pairs_per_cta;
