@@ -46,11 +46,12 @@ WORKLOADS = {
 # profiles/r01_posterior_v3_ncu_summary.txt (18.883 GB read + 0.040 GB written); algorithmic minimum 32 G + 8 N^2 = 0.17 GB:
 # W (67 MB used) is re-read from L2 by every CTA and only partly stays resident next to the factor tables.
 POSTERIOR_TRAFFIC_C4_1GPU = 18.883344e9 + 39.72864e6
-# DRAM bytes (read + write) of ONE chol_dataflow_kernel launch at c4 (N = 4096, 1344 right-hand-side columns, Gram product in the
-# same launch): mean over the 12 launches of the ncu pass over this command, profiles/r02_bench_c4_launches.csv
-# (dram__bytes_read.sum 148.4 MB + dram__bytes_write.sum 86.5 MB); algorithmic: lower triangle of K in and L out (2 x 69 MB) +
-# B in and Y out (2 x 44 MB) + lower tiles of M out (7.6 MB) = 233 MB.
-CHOL_TRAFFIC_C4_1GPU = 148.371797e6 + 86.466069e6
+# DRAM bytes (read + write) of ONE chol_dataflow_kernel launch at c4 (N = 4096, 832 right-hand-side columns after the truncation of
+# the Chebyshev block, Gram product in the same launch): mean over the 11 step launches of the ncu pass over this command,
+# profiles/r02_bench_c4_launches.csv (dram__bytes_read.sum 96.8 MB + dram__bytes_write.sum 46.3 MB).  Algorithmic: lower
+# triangle of K in and L out (2 x 69 MB) + B in and Y out (2 x 27 MB) + lower tiles of M out (3 MB) = 195 MB; the measured
+# traffic is lower because part of L, Y and M is still in the 126 MB L2 when the kernel ends (and B arrives from it).
+CHOL_TRAFFIC_C4_1GPU = 96.788829e6 + 46.284102e6
 DGEMM_PEAK_TFLOPS = 35.41   # cuBLAS DGEMM 8192^3 measured on this pool's B200 (profiles/r01_dgemm_peak.json);
 #                             MEASURED_PEAKS.json carries no FP64 figure.  DMMA issue peak: 37.15 (r01_fp64_pipes.log)
 
@@ -86,6 +87,8 @@ class ClockSampler(threading.Thread):
         super().__init__(daemon=True)
         self.index, self.samples, self.reasons, self.stop_flag = index, [], set(), False
         self.max_mhz = None
+        self.active = False          # samples are taken only while set (the timed region); NVML is initialised before that --
+        self.ready = threading.Event()   # nvmlInit takes driver locks that would stall the launches of a short timed region
 
     def run(self):
         try:
@@ -98,17 +101,21 @@ class ClockSampler(threading.Thread):
                      nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
                      nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
                      nv.nvmlClocksThrottleReasonHwPowerBrakeSlowdown: "hw_power_brake"}
+            self.ready.set()
             while not self.stop_flag:
-                self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
-                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
-                for bit, nm in names.items():
-                    if r & bit:
-                        self.reasons.add(nm)
-                time.sleep(0.1)
+                if self.active:
+                    self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                    for bit, nm in names.items():
+                        if r & bit:
+                            self.reasons.add(nm)
+                time.sleep(0.002)
         except Exception as e:   # NVML missing: report that rather than fake numbers
             self.reasons.add(f"nvml_unavailable:{type(e).__name__}")
+            self.ready.set()
 
     def result(self):
+        self.active = False
         self.stop_flag = True
         self.join(timeout=2)
         med = float(np.median(self.samples)) if self.samples else None
@@ -297,11 +304,13 @@ def run_ours(args):
     arm = Arm(main_scaling)
     w, eng, model = arm.w, arm.eng, arm.model
     G_total, npts = w["G_total"], w["hi"] - w["lo"]
+    sampler = ClockSampler(local)
+    sampler.start()
     for _ in range(args.warmup):
         arm.step()
     eng.check_factor(force=True)
-    sampler = ClockSampler(local)
-    sampler.start()
+    sampler.ready.wait(timeout=10)
+    sampler.active = True
     l0 = nat.lib().mfgp_launch_count()
     ms_dev, out = timed_region(lambda: arm.step(True), args.steps)
     # layout and route of the TIMED steps' fused fit (later sections -- incremental mode -- use other settings)
@@ -619,13 +628,15 @@ def run_c5(args):
                                noise_rngs=rngs, use_graph=use_graph)
         return logs
 
+    sampler = ClockSampler(local)
+    sampler.start()
     for k in range(max(1, min(args.warmup, 2))):
         sweep(10 + k)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    sampler = ClockSampler(local)
-    sampler.start()
+    sampler.ready.wait(timeout=10)
+    sampler.active = True
     l0 = nat.lib().mfgp_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_host0 = time.perf_counter()
