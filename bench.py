@@ -109,7 +109,7 @@ class ClockSampler(threading.Thread):
                     for bit, nm in names.items():
                         if r & bit:
                             self.reasons.add(nm)
-                time.sleep(0.002)
+                time.sleep(0.005 if self.active else 0.001)      # (idle wake-ups make no NVML call)
         except Exception as e:   # NVML missing: report that rather than fake numbers
             self.reasons.add(f"nvml_unavailable:{type(e).__name__}")
             self.ready.set()
