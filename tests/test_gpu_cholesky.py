@@ -168,3 +168,15 @@ def test_launch_per_panel_chain_still_agrees():
     env = dict(os.environ, MFGP_CHOL="chain")
     out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and "chain ok" in out.stdout, out.stderr[-2000:]
+
+
+@pytest.mark.parametrize("mg,lead", [("8", "32"), ("2", "0")])
+def test_random_sizes_terminate_and_agree(mg, lead):
+    """Stress of the fused kernel (profiles/tools/stress_solve_gram.py): 40 random (block columns, right-hand-side tiles) pairs per
+    queue setting -- every launch terminates (the subprocess has a time-out: a scheduling deadlock fails the test instead of
+    hanging the suite), info = 0, L / Y / M against LAPACK, and the Gram tasks leave L and Y bitwise untouched."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, MFGP_DF_MG=mg, MFGP_DF_MLEAD=lead)
+    out = subprocess.run([sys.executable, os.path.join(root, "profiles", "tools", "stress_solve_gram.py"), "40"], env=env,
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "40 cases ok" in out.stdout, (out.stdout[-500:], out.stderr[-2000:])
