@@ -961,10 +961,6 @@ int chol_dataflow(double* K, int64_t npad, int64_t ld, double* W, int64_t ldw, i
     if (!sc.sms) MFGP_CUDA_CHECK(cudaDeviceGetAttribute(&sc.sms, cudaDevAttrMultiProcessorCount, dev));
     MFGP_CUDA_CHECK(cudaMemsetAsync(scratch, 0, need * sizeof(int), st));
     MFGP_CUDA_CHECK(cudaMemsetAsync(info, 0, sizeof(int32_t), st));
-    // diagnostics (MFGP_DF_NODEP=1): every tile flag preset, i.e. the same tasks with no waiting -- the results are garbage,
-    // the time is the throughput ceiling of the tile loops for this task mix
-    static const bool nodep = [] { const char* e = getenv("MFGP_DF_NODEP"); return e && atoi(e) != 0; }();
-    if (nodep) MFGP_CUDA_CHECK(cudaMemsetAsync(scratch + DF_CTRL_INTS + 1024, 1, (need - DF_CTRL_INTS - 1024) * sizeof(int), st));
     DfArgs a{};
     a.K = K; a.ld = ld; a.W = W; a.ldw = ldw; a.Bm = Bm; a.ldb = ldb; a.nb = nb; a.nr = nr; a.info = info;
     a.ctrl = scratch; a.pause = scratch + DF_CTRL_INTS; a.flagsL = a.pause + 1024; a.flagsY = a.flagsL + (int64_t)nb * nb;
