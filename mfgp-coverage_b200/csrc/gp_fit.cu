@@ -230,10 +230,15 @@ __global__ void __launch_bounds__(256, 1) potrf_diag_kernel(double* __restrict__
 //   chain task d (the critical path, ONE hop per block column): accumulates BOTH the sub-diagonal tile (d, d-1) and the
 //                             diagonal tile (d, d) over k < d-1 (they share the A operand L_dk); when W_{d-1,d-1} is
 //                             flagged it forms L_{d,d-1} = X W^T, subtracts L_{d,d-1} L_{d,d-1}^T from the diagonal tile
-//                             out of shared memory, and factors + inverts it in place (potrf_diag_body) -> W_dd.
-// Ticket order: chain 0; then per block column c: chain c+1, the tiles (i, c) below it, the Y tiles of block row c.
-// A task waits only on tasks with a SMALLER ticket, and a CTA holds a ticket only while it is resident, so the scheme
-// cannot deadlock whatever the number of resident CTAs; a bounded spin (abort flag) guards against bugs all the same.
+//                             out of shared memory, and factors + inverts it in place (two 32x32 halves, potrf_diag_body) -> W_dd.
+//   Gram task (g, ti, tj) (optional, mfgp_cholesky_solve_gram): adds the block rows of group g of the SOLVED right-hand sides to
+//                             tile (ti, tj) of M = Y^T Y, in place, groups in order; a second, low-priority ticket queue.
+// Ticket order: chain 0; then per block column c: the chain tasks placed there (chain d sits d / chain_la columns ahead of
+// column d - 1), the tiles (i, c) below the sub-diagonal, the Y tiles of block row c.
+// A task other than an early chain task waits only on tasks with a SMALLER ticket, a CTA holds a ticket only while it is
+// resident, and at most nb / chain_la + 2 CTAs can hold early chain tasks, so the scheme cannot deadlock; a Gram ticket is
+// run only once every task its rows depend on has been drawn (oracle/tiled_cholesky.py restates both arguments and simulates
+// them); a bounded spin (abort flag) guards against bugs all the same.
 // Two CTAs share an SM; while one of them runs the latency-bound tail of a chain task it raises a per-SM pause flag and
 // the other one idles between its k slabs (its DMMA traffic would otherwise stretch the chain by ~25%).
 constexpr int DF_K = 32;                 // K slab
