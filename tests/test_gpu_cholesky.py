@@ -174,7 +174,8 @@ def test_launch_per_panel_chain_still_agrees():
 def test_random_sizes_terminate_and_agree(mg, lead):
     """Stress of the fused kernel (profiles/tools/stress_solve_gram.py): 40 random (block columns, right-hand-side tiles) pairs per
     queue setting -- every launch terminates (the subprocess has a time-out: a scheduling deadlock fails the test instead of
-    hanging the suite), info = 0, L / Y / M against LAPACK, and the Gram tasks leave L and Y bitwise untouched."""
+    hanging the suite), info = 0, L / Y / M against LAPACK, the Gram tasks leave L and Y bitwise untouched, and the canaries around
+    every buffer the kernel writes (its workspace sized exactly as the library asks) stay intact."""
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     env = dict(os.environ, MFGP_DF_MG=mg, MFGP_DF_MLEAD=lead)
     out = subprocess.run([sys.executable, os.path.join(root, "profiles", "tools", "stress_solve_gram.py"), "40"], env=env,
