@@ -68,6 +68,12 @@ def chebyshev_truncation(parts, kpad, ry, tol=1e-16):
     return kx
 
 
+# MFGP_GUARD=1 (tests): every workspace of the factored / fused path is allocated inside canary margins and sized EXACTLY as the
+# library asks; check_guards() then proves that no kernel wrote outside what it was given (compute-sanitizer stand-in)
+GUARD = os.environ.get("MFGP_GUARD", "0") != "0"
+_CANARY = -7.25e300
+
+
 # MFGP_TRUNC=0: keep the full rx x ry tensor block of Chebyshev terms (default: product-magnitude truncation, ~1/3 fewer columns)
 TRUNCATE = os.environ.get("MFGP_TRUNC", "1") != "0"
 
@@ -480,12 +486,27 @@ class DeviceGP:
         return plan
 
 
+    def _wsalloc(self, n, slack=8):
+        """n doubles of workspace (+ `slack`); with GUARD: exactly n, inside canary margins that check_guards() inspects."""
+        if not GUARD:
+            return torch.empty(n + slack, dtype=torch.float64, device=self.device)
+        big = torch.full((n + 1024,), _CANARY, dtype=torch.float64, device=self.device)
+        self._guards = [g for g in getattr(self, "_guards", []) if g[0] is not None]
+        self._guards.append((big, n))
+        return big[512:512 + n]
+
+    def check_guards(self):
+        """True iff no canary of a GUARD-mode workspace has been overwritten."""
+        torch.cuda.synchronize(self.device)
+        return all(bool((big[:512] == _CANARY).all().item()) and bool((big[512 + n:] == _CANARY).all().item())
+                   for big, n in getattr(self, "_guards", []))
+
     def _factored_work(self, axes, plan):
         # sized for the CAPACITY of the factor buffers, so appended samples do not reallocate gigabytes every iteration
         need = int(nat.lib().mfgp_factored_workspace_bytes(self.cap, plan["ncols"], axes.ny, plan["rxL"], plan["ryL"],
                                                            plan["rxH"], plan["ryH"], plan["chunk"]))
         if self._fwork is None or self._fwork.numel() * 8 < need:
-            self._fwork = torch.empty(need // 8 + 8, dtype=torch.float64, device=self.device)
+            self._fwork = self._wsalloc(need // 8)
         return self._fwork
 
     def _factored_stores(self, plan):
@@ -496,9 +517,9 @@ class DeviceGP:
         nG = plan["ncols"] * 64 * 64
         nH = int(lib.mfgp_factored_rhs_cols(plan["rxL"], plan["ryL"], plan["rxH"], plan["ryH"]))     # >= ry * kpad
         if self._fG is None or self._fG.numel() < nG:
-            self._fG = torch.empty(nG, dtype=torch.float64, device=self.device)
+            self._fG = self._wsalloc(nG, 0)
         if self._fHz is None or self._fHz.numel() < nH:
-            self._fHz = torch.empty(nH, dtype=torch.float64, device=self.device)
+            self._fHz = self._wsalloc(nH, 0)
         return self._fG, self._fHz
 
     def _fit_and_posterior_fused(self, axes, plan, mu, var, q_out):
@@ -531,7 +552,7 @@ class DeviceGP:
             kx, kxp = None, None
             R = int(lib.mfgp_factored_rhs_cols(*o))
         if self._fB is None or self._fB.numel() < self.cap * R:
-            self._fB = torch.empty(self.cap * R, dtype=torch.float64, device=self.device)
+            self._fB = self._wsalloc(self.cap * R, 0)
         nat.check(lib.mfgp_build_train_cov(nat.ptr(self.Xt), self.NL, self.NH, pp, nat.ptr(self.K), npad, ld,
                                            nat.ptr(self.Tt), st), "mfgp_build_train_cov")
         nat.check(lib.mfgp_factored_prepare_trunc(nat.ptr(axes.ux), axes.nx, nat.ptr(axes.uy), axes.ny, plan["ix0"], plan["ncols"],
@@ -543,7 +564,7 @@ class DeviceGP:
             ev[0].record()
         cneed = int(lib.mfgp_cholesky_solve_gram_workspace_bytes(self.cap, R))
         if self._cwork is None or self._cwork.numel() * 8 < cneed:
-            self._cwork = torch.empty(cneed // 8 + 8, dtype=torch.float64, device=self.device)
+            self._cwork = self._wsalloc(cneed // 8)
         nat.check(lib.mfgp_cholesky_solve_gram(nat.ptr(self.K), npad, ld, nat.ptr(self.W), ld, nat.ptr(self.info),
                                                nat.ptr(self._fB), R, R, ctypes.c_void_p(M), R, nat.ptr(self._cwork),
                                                self._cwork.numel() * 8, st), "mfgp_cholesky_solve_gram")

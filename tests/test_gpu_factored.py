@@ -335,3 +335,38 @@ def test_truncated_layout_agrees_with_the_full_tensor_block(monkeypatch):
     assert cols[True][0] <= 0.8 * cols[False][0]
     assert np.max(np.abs(res[True][1] - res[False][1])) <= 1e-13 * p.k0
     assert np.max(np.abs(res[True][0] - res[False][0])) <= 1e-13 * max(1.0, np.max(np.abs(res[False][0])))
+
+
+@pytest.mark.parametrize("nx,ny,N,multi,incremental", [(96, 80, 700, True, False), (72, 72, 200, False, False), (64, 64, 200, True, True)])
+def test_workspaces_are_not_overrun(nx, ny, N, multi, incremental, monkeypatch):
+    """Every workspace of the fused fit + factored posterior (tables, right-hand sides, Gram product, tile flags, incremental
+    stores) allocated inside canary margins and sized exactly as the library asks: no kernel writes outside what it was given
+    (the role compute-sanitizer would play), truncated and uniform column layouts, and the results are still the oracle's."""
+    from mfgp_coverage_b200._coverage import CoverageGrid
+    from mfgp_coverage_b200 import _engine as eng_mod
+    monkeypatch.setattr(eng_mod, "GUARD", True)
+    xy = _tensor_grid(nx, ny)
+    f = synth.truth_function(xy)
+    X_L, y_L, X_H, y_H = synth.training_set(xy, f, N, multi=multi)
+    hyp = synth.MF_HYP if multi else synth.SF_HYP
+    p = ogp.GPParams.from_hyp(hyp)
+    om = ogp.Model(p, X_L, y_L, X_H, y_H)
+    om.updt_info()
+    mu_o, var_o = om.predict(xy)
+    grid = CoverageGrid(xy)
+    for trunc in (True, False):
+        monkeypatch.setattr(eng_mod, "TRUNCATE", trunc)
+        m = _model(hyp, X_L, y_L, X_H, y_H, multi)
+        e = m.engine
+        e.factored_min_gain = 0.0
+        e.defer_fit = True
+        e.incremental = incremental
+        mu = torch.empty(grid.G, dtype=torch.float64, device=grid.device)
+        var = torch.empty(grid.G, dtype=torch.float64, device=grid.device)
+        for rep in range(2):
+            e.refactor(check=False)
+            m.predict_device(grid.xy, mu, var, grid=grid)
+        e.check_factor(force=True)
+        assert len(e._guards) >= 3 and e.check_guards(), (trunc, "a kernel wrote outside its workspace")
+        assert np.max(np.abs(var.cpu().numpy() - var_o)) <= TOL * p.k0
+        assert np.max(np.abs(mu.cpu().numpy() - mu_o)) <= TOL * max(1.0, np.max(np.abs(mu_o)))
