@@ -62,3 +62,43 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
+
+
+def test_header_prototypes_match_the_ctypes_table():
+    """Every prototype of include/mfgp_b200.h against _native.SIGNATURES: same number of arguments and, argument by argument, the
+    same class (pointer / double / 64-bit integer / int) -- a drift between the header and the ctypes table would pass garbage
+    to the library without any error."""
+    from mfgp_coverage_b200 import _native
+    text = open(os.path.join(ROOT, "include", "mfgp_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", " ", text, flags=re.S)
+    text = re.sub(r"//[^\n]*", " ", text)
+
+    def cls_of_c(arg):
+        arg = arg.strip()
+        if "*" in arg:
+            return "ptr"
+        if re.match(r"(const\s+)?double\b", arg):
+            return "double"
+        if re.match(r"(const\s+)?(int64_t|uint64_t)\b", arg):
+            return "i64"
+        if re.match(r"(const\s+)?(int|int32_t)\b", arg):
+            return "int"
+        raise AssertionError("unclassified C argument: " + arg)
+
+    def cls_of_ctypes(t):
+        if t is ctypes.c_double:
+            return "double"
+        if t in (ctypes.c_int64, ctypes.c_uint64):
+            return "i64"
+        if t in (ctypes.c_int, ctypes.c_int32):
+            return "int"
+        return "ptr"          # c_void_p, c_char_p, POINTER(struct)
+
+    for name, (restype, argtypes) in _native.SIGNATURES.items():
+        m = re.search(r"\b%s\s*\(([^;{]*)\)\s*;" % re.escape(name), text)
+        assert m, name
+        raw = m.group(1).strip()
+        args = [] if raw in ("", "void") else [a for a in raw.split(",")]
+        assert len(args) == len(argtypes), (name, len(args), len(argtypes))
+        for k, (a, t) in enumerate(zip(args, argtypes)):
+            assert cls_of_c(a) == cls_of_ctypes(t), (name, k, a.strip(), t)
