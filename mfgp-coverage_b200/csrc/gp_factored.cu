@@ -147,6 +147,11 @@ __global__ void unpack_Y_kernel(const double* __restrict__ Yall, int64_t ldY, in
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e < cols) Yp[(int64_t)n * cols + e] = Yall[(int64_t)n * ldY + off + e];
 }
+// column block [zoff, zoff + blockDim.x) of Yall: the whitened observations, then zeros (the layout mfgp_cholesky_solve leaves)
+__global__ void put_z_block_kernel(const double* __restrict__ z, int npad, double* __restrict__ Yall, int64_t ldY, int zoff) {
+    const int n = blockIdx.x, c = threadIdx.x;
+    Yall[(int64_t)n * ldY + zoff + c] = (c == 0) ? z[n] : 0.0;
+}
 __global__ void unpack_z_kernel(const double* __restrict__ Yall, int64_t ldY, int off, int npad, double* __restrict__ z) {
     const int n = blockIdx.x * blockDim.x + threadIdx.x;
     if (n < npad) z[n] = Yall[(int64_t)n * ldY + off];
@@ -710,9 +715,9 @@ extern "C" int64_t mfgp_factored_workspace_bytes(int64_t npad, int64_t ncols, in
     int64_t d = 0;
     d += ny * 64 + npad + ry * kp;                             // Uy, solved z, Hz
     d += (rxL + ryL + rxH + ryH) * npad;                       // coefficient tables of both kernel parts
-    d += 2 * npad * ry * kp;                                   // B and Y (merged over the parts)
-    d += ncp * kp;                                             // Ux
     const int64_t Rp = round_up(ry * kp + 1, 64);
+    d += 2 * npad * Rp;                                        // B and Y (merged over the parts; room for the observation column)
+    d += ncp * kp;                                             // Ux
     const int64_t direct = ch * npad * ry;                     // Y' of one chunk (direct route)
     const int64_t gram = (MR_MAXSPLIT + 1) * Rp * Rp + ncp * F_LW * F_LW;      // M = Y^T Y, its split-K partials, G'(ix)
     d += direct > gram ? direct : gram;
@@ -804,7 +809,10 @@ void f_carve(const FGeom& g, void* work, FLayout& L) {
     L.nparts = 1;
     f.rx = (int)imax(g.rxL, g.rxH); f.ry = (int)imax(g.ryL, g.ryH); f.kpad = (int)round_up(f.rx, 4); f.loff = 0; f.inv_l = 0.0;
     f.Cx = f.Cy = nullptr;
-    f.B = carve(g.npad * (int64_t)f.ry * f.kpad); f.Y = carve(g.npad * (int64_t)f.ry * f.kpad);
+    {
+        const int64_t Rp = round_up((int64_t)f.ry * f.kpad + 1, 64);         // [B | y - mean | 0 ...] / [Y | z | 0 ...] fit as well
+        f.B = carve(g.npad * Rp); f.Y = carve(g.npad * Rp);
+    }
     f.Ux = carve(L.ncp * f.kpad);
     {       // one region serves either route of steps 4 + 5: Y' of a chunk (direct) or M, its partials and G'(ix) (Gram route)
         const int64_t Rp = round_up((int64_t)f.ry * f.kpad + 1, 64);
@@ -1023,6 +1031,24 @@ extern "C" int mfgp_posterior_grid_factored(const double* ux, int64_t nx, const 
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     FLayout L;
     f_carve(g, work, L);
+    FPart& f0 = L.parts[0];
+    const int64_t cols0 = (int64_t)f0.ry * f0.kpad, Rp = round_up(cols0 + 1, 64);
+    if (!Gstore && !Hz_store && f_gram_wanted(g, L, Rp)) {
+        // Gram route with a standing factor: Yall = W [B | 0] in the padded layout of the fused form (row stride Rp), z into its
+        // observation column, then M = Yall^T Yall as a launch of its own and the quadratic forms / evaluation of f_tail_gram
+        rc = f_tables_and_B(g, L, f0.B, Rp, st);
+        if (rc) return rc;
+        put_z_block_kernel<<<(unsigned)npad, (int)(Rp - cols0), 0, st>>>(z, (int)npad, f0.B, Rp, (int)cols0);     // (zeros: W 0 = 0)
+        MFGP_LAUNCH_CHECK();
+        GemmArgs gm{};
+        gm.A = W; gm.lda = ldw; gm.B = f0.B; gm.ldb = Rp; gm.C = f0.Y; gm.ldc = Rp;
+        gm.M = (int)npad; gm.N = (int)Rp; gm.K = (int)npad; gm.alpha = 1.0; gm.beta = 0.0; gm.mode = GEMM_A_LOWER;
+        rc = launch_gemm(gm, false, 1, st);
+        if (rc) return rc;
+        put_z_block_kernel<<<(unsigned)npad, (int)(Rp - cols0), 0, st>>>(z, (int)npad, f0.Y, Rp, (int)cols0);
+        MFGP_LAUNCH_CHECK();
+        return f_tail_gram(g, L, f0.Y, Rp, nullptr, nullptr, mu, var, qred, false, st);
+    }
     rc = f_tables_and_B(g, L, nullptr, 0, st);
     if (rc) return rc;
     for (int pi = 0; pi < L.nparts; pi++) {       // step 3: Y = W B  (W lower triangular: k < m0 + 64)
@@ -1036,8 +1062,6 @@ extern "C" int mfgp_posterior_grid_factored(const double* ux, int64_t nx, const 
     return f_tail(g, L, z, npad, Gstore, Hz_store, 0, mu, var, qred, st);
 }
 
-// Fused-fit form, part 1: steps 1 + 2 straight into the right-hand-side matrix of mfgp_cholesky_solve,
-// Ball[npad, ldB] = [B_L | B_H | (y - mean), 0 ...] with mfgp_factored_rhs_cols(...) columns.
 // kx (optional, host, max(ryL, ryH) entries): truncated column layout -- per y term l only the first kx[l] x terms are kept
 // (multiples of 4 in [4, round_up(max(rxL, rxH), 4)]); Ball then has mfgp_factored_rhs_cols_trunc(ry, kx) columns.  Only the
 // Gram route of steps 4 + 5 reads that layout: pair it with mfgp_factored_gram_target / mfgp_posterior_grid_factored_solved_gram

@@ -370,3 +370,35 @@ def test_workspaces_are_not_overrun(nx, ny, N, multi, incremental, monkeypatch):
         assert len(e._guards) >= 3 and e.check_guards(), (trunc, "a kernel wrote outside its workspace")
         assert np.max(np.abs(var.cpu().numpy() - var_o)) <= TOL * p.k0
         assert np.max(np.abs(mu.cpu().numpy() - mu_o)) <= TOL * max(1.0, np.max(np.abs(mu_o)))
+
+
+@pytest.mark.parametrize("route", ["direct", "m"])
+@pytest.mark.parametrize("nx,ny,N,multi", [(96, 80, 700, True), (72, 72, 200, False)])
+def test_standing_factor_posterior_both_routes(nx, ny, N, multi, route, monkeypatch):
+    """mfgp_posterior_grid_factored (the factor is already standing: a second predict without new data, the eager fit): the Gram
+    route (Y = W [B | z] in the padded layout, M = Y^T Y as a launch of its own, quadratic forms, evaluation) and the direct
+    route give the oracle's posterior."""
+    from mfgp_coverage_b200._coverage import CoverageGrid
+    monkeypatch.setenv("MFGP_GRAM", route)
+    xy = _tensor_grid(nx, ny)
+    f = synth.truth_function(xy)
+    X_L, y_L, X_H, y_H = synth.training_set(xy, f, N, multi=multi)
+    hyp = synth.MF_HYP if multi else synth.SF_HYP
+    p = ogp.GPParams.from_hyp(hyp)
+    om = ogp.Model(p, X_L, y_L, X_H, y_H)
+    om.updt_info()
+    mu_o, var_o = om.predict(xy)
+    m = _model(hyp, X_L, y_L, X_H, y_H, multi)
+    e = m.engine
+    e.factored_min_gain = 0.0
+    e.defer_fit = False
+    e.refactor(check=True)                                  # eager: K -> L -> W -> z, all standing
+    assert not e._dirty
+    grid = CoverageGrid(xy)
+    mu = torch.empty(grid.G, dtype=torch.float64, device=grid.device)
+    var = torch.empty(grid.G, dtype=torch.float64, device=grid.device)
+    for rep in range(2):
+        m.predict_device(grid.xy, mu, var, grid=grid)
+        assert e._fplan is not None and e._fplan[1] is not None
+        assert np.max(np.abs(var.cpu().numpy() - var_o)) <= TOL * p.k0
+        assert np.max(np.abs(mu.cpu().numpy() - mu_o)) <= TOL * max(1.0, np.max(np.abs(mu_o)))
