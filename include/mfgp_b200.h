@@ -197,6 +197,12 @@ int mfgp_posterior_grid_factored_solved(const double* ux, int64_t nx, const doub
  * reads this layout: give the same kx to mfgp_factored_prepare_trunc, mfgp_factored_gram_target (which then never returns
  * NULL for a valid geometry) and mfgp_posterior_grid_factored_solved_gram; Gstore / Hz_store must be NULL. */
 int64_t mfgp_factored_rhs_cols_trunc(int64_t ry, const int32_t* kx);
+int mfgp_posterior_grid_factored_trunc(const double* ux, int64_t nx, const double* uy, int64_t ny, int64_t ix0, int64_t ncols,
+                                       const double* Xt, int64_t NL, int64_t NH, const double* W, int64_t npad, int64_t ldw,
+                                       const double* z, const mfgp_params* p_host, int64_t rxL, int64_t ryL, int64_t rxH, int64_t ryH,
+                                       double xlo, double xhi, double ylo, double yhi, int64_t chunk_cols, const int32_t* kx,
+                                       double* mu, double* var, double* qred, double* Gstore, double* Hz_store, void* work,
+                                       int64_t work_bytes, void* stream);   /* mfgp_posterior_grid_factored with the layout above */
 int mfgp_factored_prepare_trunc(const double* ux, int64_t nx, const double* uy, int64_t ny, int64_t ix0, int64_t ncols,
                                 const double* Xt, const double* y, int64_t NL, int64_t NH, int64_t npad, const mfgp_params* p_host,
                                 int64_t rxL, int64_t ryL, int64_t rxH, int64_t ryH, double xlo, double xhi, double ylo, double yhi,

@@ -602,9 +602,11 @@ class DeviceGP:
                 nat.ptr(mu), nat.ptr(var), nat.ptr(q_out), nat.ptr(Gs), nat.ptr(Hs), nat.ptr(work), work.numel() * 8,
                 nat.stream_ptr()), "mfgp_posterior_grid_factored_update")
             return
-        nat.check(lib.mfgp_posterior_grid_factored(
+        kx = plan.get("kx") if Gs is None else None      # truncated column layout (not with the incremental stores)
+        nat.check(lib.mfgp_posterior_grid_factored_trunc(
             nat.ptr(axes.ux), axes.nx, nat.ptr(axes.uy), axes.ny, plan["ix0"], plan["ncols"], nat.ptr(self.Xt), self.NL, self.NH,
-            nat.ptr(self.W), self.npad, self.cap, nat.ptr(self.z), ctypes.byref(self.pstruct), *o, *geom, nat.ptr(mu), nat.ptr(var),
+            nat.ptr(self.W), self.npad, self.cap, nat.ptr(self.z), ctypes.byref(self.pstruct), *o, *geom,
+            ctypes.c_void_p(kx.ctypes.data) if kx is not None else None, nat.ptr(mu), nat.ptr(var),
             nat.ptr(q_out), nat.ptr(Gs), nat.ptr(Hs), nat.ptr(work), work.numel() * 8, nat.stream_ptr()),
             "mfgp_posterior_grid_factored")
 

@@ -67,6 +67,11 @@ SIGNATURES = {
                                              c_int64, c_void_p, c_int64, c_int64, c_void_p, POINTER(MfgpParams), c_int64,
                                              c_int64, c_int64, c_int64, c_double, c_double, c_double, c_double, c_int64,
                                              c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+    "mfgp_posterior_grid_factored_trunc": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64,
+                                                   c_int64, c_void_p, c_int64, c_int64, c_void_p, POINTER(MfgpParams), c_int64,
+                                                   c_int64, c_int64, c_int64, c_double, c_double, c_double, c_double, c_int64,
+                                                   c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
+                                                   c_void_p]),
     "mfgp_posterior_grid_factored_update": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64,
                                                     c_int64, c_int64, c_void_p, c_int64, c_int64, c_void_p, POINTER(MfgpParams),
                                                     c_int64, c_int64, c_int64, c_int64, c_double, c_double, c_double, c_double,

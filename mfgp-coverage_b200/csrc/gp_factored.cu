@@ -1018,12 +1018,14 @@ int f_tail_gram(const FGeom& g, FLayout& L, const double* Yall, int64_t ldY, dou
 // are flat over those columns: index (ix - ix0) * ny + iy.  rx*/ry*: Chebyshev orders per axis and part (ryL, ryH multiples
 // of 4, ryL + ryH <= 64, all <= 64; rxL = ryL = 0 for a single-fidelity model) -- chosen by the caller so that the factor
 // tables are reproduced to rounding (mfgp_coverage_b200/_engine.py: chebyshev_order).
-extern "C" int mfgp_posterior_grid_factored(const double* ux, int64_t nx, const double* uy, int64_t ny, int64_t ix0, int64_t ncols,
-                                            const double* Xt, int64_t NL, int64_t NH, const double* W, int64_t npad, int64_t ldw,
-                                            const double* z, const mfgp_params* p_host, int64_t rxL, int64_t ryL, int64_t rxH,
-                                            int64_t ryH, double xlo, double xhi, double ylo, double yhi, int64_t chunk_cols,
-                                            double* mu, double* var, double* qred, double* Gstore, double* Hz_store, void* work,
-                                            int64_t work_bytes, void* stream) {
+// kx (optional, host): truncated column layout as in mfgp_factored_prepare_trunc; needs Gstore = Hz_store = NULL and takes the Gram
+// route (MFGP_GRAM=direct falls back to the uniform layout).
+extern "C" int mfgp_posterior_grid_factored_trunc(const double* ux, int64_t nx, const double* uy, int64_t ny, int64_t ix0, int64_t ncols,
+                                                  const double* Xt, int64_t NL, int64_t NH, const double* W, int64_t npad, int64_t ldw,
+                                                  const double* z, const mfgp_params* p_host, int64_t rxL, int64_t ryL, int64_t rxH,
+                                                  int64_t ryH, double xlo, double xhi, double ylo, double yhi, int64_t chunk_cols,
+                                                  const int32_t* kx, double* mu, double* var, double* qred, double* Gstore,
+                                                  double* Hz_store, void* work, int64_t work_bytes, void* stream) {
     if (!W || !z || !mu || !var || ldw < npad) return MFGP_ERR_INVALID;
     FGeom g{ux, nx, uy, ny, ix0, ncols, Xt, NL, NH, npad, p_host, rxL, ryL, rxH, ryH, xlo, xhi, ylo, yhi, chunk_cols};
     int rc = f_validate(g, work, work_bytes);
@@ -1032,7 +1034,10 @@ extern "C" int mfgp_posterior_grid_factored(const double* ux, int64_t nx, const 
     FLayout L;
     f_carve(g, work, L);
     FPart& f0 = L.parts[0];
-    const int64_t cols0 = (int64_t)f0.ry * f0.kpad, Rp = round_up(cols0 + 1, 64);
+    if (kx && !Gstore && !Hz_store && gram_route_override() != 1) {
+        if (!f_set_trunc(L, kx)) return MFGP_ERR_INVALID;
+    }
+    const int64_t cols0 = L.tr.cols, Rp = round_up(cols0 + 1, 64);
     if (!Gstore && !Hz_store && f_gram_wanted(g, L, Rp)) {
         // Gram route with a standing factor: Yall = W [B | 0] in the padded layout of the fused form (row stride Rp), z into its
         // observation column, then M = Yall^T Yall as a launch of its own and the quadratic forms / evaluation of f_tail_gram
@@ -1060,6 +1065,16 @@ extern "C" int mfgp_posterior_grid_factored(const double* ux, int64_t nx, const 
         if (rc) return rc;
     }
     return f_tail(g, L, z, npad, Gstore, Hz_store, 0, mu, var, qred, st);
+}
+
+extern "C" int mfgp_posterior_grid_factored(const double* ux, int64_t nx, const double* uy, int64_t ny, int64_t ix0, int64_t ncols,
+                                            const double* Xt, int64_t NL, int64_t NH, const double* W, int64_t npad, int64_t ldw,
+                                            const double* z, const mfgp_params* p_host, int64_t rxL, int64_t ryL, int64_t rxH,
+                                            int64_t ryH, double xlo, double xhi, double ylo, double yhi, int64_t chunk_cols,
+                                            double* mu, double* var, double* qred, double* Gstore, double* Hz_store, void* work,
+                                            int64_t work_bytes, void* stream) {
+    return mfgp_posterior_grid_factored_trunc(ux, nx, uy, ny, ix0, ncols, Xt, NL, NH, W, npad, ldw, z, p_host, rxL, ryL, rxH, ryH, xlo, xhi,
+                                              ylo, yhi, chunk_cols, nullptr, mu, var, qred, Gstore, Hz_store, work, work_bytes, stream);
 }
 
 // kx (optional, host, max(ryL, ryH) entries): truncated column layout -- per y term l only the first kx[l] x terms are kept
