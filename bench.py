@@ -2,11 +2,12 @@
 """bench.py -- the reference's headline hot path on B200: MF-GP posterior over the grid + coverage step.
 
 One "step" = one coverage iteration of the workload (default: BASELINE.json config 4 -- synthetic 1024x1024 grid,
-4096 MF training samples, 64 agents):
-    factor the training covariance (K assembly -> blocked Cholesky -> L^-1 -> whitened observations)
-    -> fused posterior mean + variance over every grid point
-    -> both bounded-Voronoi partitions in one pass (loss, weighted centroids, per-cell max-variance arg-max)
-    -> O(agents) host finishing (Qhull polygons, centroid / loss arithmetic), exactly what simulator.todescato does.
+4096 MF training samples, 64 agents), i.e. what simulator.todescato does per iteration (simulator.py:888-904), through the
+product's own stepper (simulator._Sim.step on one GPU, sharding.ShardedSim.step on a shard):
+    refit from scratch: K assembly -> ONE tile-dataflow kernel (tiled Cholesky + forward substitution of the Chebyshev-factored
+    posterior's right-hand sides + their Gram product) -> quadratic forms -> mean + variance at every grid point
+    -> both bounded-Voronoi partitions clipped on the device, one fused pass (loss, weighted centroids, per-cell max-variance
+    arg-max), O(agents) finishing on the device, ONE packed copy home (results, Cholesky status, clip flags, tie count).
 `value` = grid points / s with everything resident in HBM; `e2e` = the same iteration through the drop-in Python API
 with HOST numpy buffers (grid upload, mu/var download, re-upload into the coverage functions) inside the timed region.
 N > 1 (torchrun, one rank per GPU): the FIXED grid of the named config is split into whole-column slices (strong scaling,
