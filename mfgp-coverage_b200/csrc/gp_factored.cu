@@ -201,6 +201,7 @@ struct GramArgs {
     const double* YpL; const double* YpH; int ryL, ryH;        // step-4 outputs [cols][npad][ry]
     int npad;                                                  // rows of Y' held per column (all rows, or only the new ones)
     double* Gstore;                                            // optional [cols_total][F_LW][F_LW]: G'(ix) kept across calls
+    int skip_eval;                                             // 1: stop behind the Gstore update (step 6 runs as geval_mma_kernel)
     int accumulate;                                            // 1: G' = Gstore + (the rows given); the store is updated
     const double* HzL; const double* HzH;                      // z^T Y_P, [ry][kpad]  (h'(ix) = Ux(ix) . Hz)
     const double* UxL; const double* UxH; int kL, kH;          // T_k(tx) of this launch's columns, [cols][kpad]
@@ -331,6 +332,7 @@ __global__ void __launch_bounds__(128) gram_eval_kernel(GramArgs a) {
             if (a.accumulate) { v += gst[r * F_LW + c]; Gs[r * GP + c] = v; }
             gst[r * F_LW + c] = v;
         }
+        if (a.skip_eval) return;
     }
     // h'(ix)[l] = sum_k Ux(ix)[k] Hz_P[l][k]     (Hz = z^T Y, computed once per posterior by hz_kernel)
     if (tid < F_LW) {
@@ -902,6 +904,7 @@ int f_tail(const FGeom& g, FLayout& L, const double* z, int64_t rows, double* Gs
         ga.ryL = 0; ga.ryH = L.parts[0].ry;
         ga.npad = (int)npad; ga.Uy = L.Uy; ga.ny = (int)g.ny; ga.col_begin = (int)c0;
         ga.Gstore = Gstore; ga.accumulate = accumulate;
+        ga.skip_eval = Gstore != nullptr;              // with a store: the DMMA evaluation kernel below reads G'(ix) from it
         ga.HzL = nullptr; ga.HzH = L.parts[0].Hz;
         ga.UxL = nullptr; ga.UxH = L.parts[0].Ux + c0 * L.parts[0].kpad;
         ga.kL = 0; ga.kH = L.parts[0].kpad;
@@ -909,6 +912,14 @@ int f_tail(const FGeom& g, FLayout& L, const double* z, int64_t rows, double* Gs
         ga.pitch = pitch; ga.nstage = nstage;
         if (narrow) gram_eval_kernel<40><<<(unsigned)cc, 128, gsmem, st>>>(ga);
         else gram_eval_kernel<64><<<(unsigned)cc, 128, gsmem, st>>>(ga);
+        MFGP_LAUNCH_CHECK();
+    }
+    if (Gstore) {            // step 6 for every column off the stored Gram matrices (tensor pipe; uniform column layout)
+        FPart& f = L.parts[0];
+        if (narrow)
+            geval_mma_kernel<40><<<(unsigned)g.ncols, 128, 0, st>>>(Gstore, f.Hz, f.Ux, f.kpad, f.ry, L.tr, L.Uy, (int)g.ny, dp.mean_H, dp.k0, mu, var, qred);
+        else
+            geval_mma_kernel<64><<<(unsigned)g.ncols, 128, 0, st>>>(Gstore, f.Hz, f.Ux, f.kpad, f.ry, L.tr, L.Uy, (int)g.ny, dp.mean_H, dp.k0, mu, var, qred);
         MFGP_LAUNCH_CHECK();
     }
     return MFGP_OK;
