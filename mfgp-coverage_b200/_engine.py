@@ -470,8 +470,8 @@ class DeviceGP:
             return None
         key = (axes.uid, g_lo, G, self.npad, p["l_L"], p["l_H"], p["multi"], self.factored_min_gain)
         orders = self._cheb_orders(axes, p, xlo, xhi)
-        if self._fplan is not None and self._fplan[0] == key and self._fplan[2] == orders:
-            return self._fplan[1]
+        if self._fplan is not None and self._fplan[0] == key and self._fplan[2] == orders and self._fplan[3] is self._ftrunc:
+            return self._fplan[1]          # (same orders AND the truncation table they were cached with)
         plan = None
         if orders is not None:
             rxL, ryL, rxH, ryH = orders
@@ -482,7 +482,7 @@ class DeviceGP:
                 chunk = max(64, min(-(-ncols // 64) * 64, ((1 << 28) // max(self.cap * max(ryL, ryH), 1)) // 64 * 64))   # <= 2 GiB of Y'
                 plan = dict(rxL=rxL, ryL=ryL, rxH=rxH, ryH=ryH, xlo=xlo, xhi=xhi, ylo=axes.ylo, yhi=axes.yhi,
                             ix0=ix0, ncols=ncols, chunk=chunk, macs=fact, dense_macs=dense, kx=self._ftrunc)
-        self._fplan = (key, plan, orders)
+        self._fplan = (key, plan, orders, self._ftrunc)
         return plan
 
 
