@@ -132,7 +132,8 @@ __global__ void __launch_bounds__(BT_THREADS) batch_append_kernel(BatchArgs a, i
 #pragma unroll
         for (int j = 0; j < BT_MAXA; j++) acc[j] = 0.0;
         const double* wr = W + (int64_t)n * cap;
-        for (int m = lane; m <= n; m += 32) {
+#pragma unroll 4
+        for (int m = lane; m <= n; m += 32) {         // (unrolled: four loads of W in flight per lane; same order of the sums)
             const double w = wr[m];
 #pragma unroll
             for (int j = 0; j < BT_MAXA; j++)
@@ -190,6 +191,7 @@ __global__ void __launch_bounds__(BT_THREADS) batch_append_kernel(BatchArgs a, i
         double t[BT_MAXA];
 #pragma unroll
         for (int j = 0; j < BT_MAXA; j++) t[j] = 0.0;
+#pragma unroll 4
         for (int n = m; n < N; n++) {
             const double w = W[(int64_t)n * cap + m];
 #pragma unroll
