@@ -268,7 +268,6 @@ struct DfArgs {
     int mg, m_full, m_tiles, m_total, m_lead;      // m_full groups of mg block rows, then the rest in halving groups
     long long spin_limit;
     long long* trace;   // diagnostics (MFGP_DF_TRACE=1): 8 timestamps per chain task, else nullptr
-    int use_pause;      // 1: a chain task's tail pauses the SM's other CTA between its slabs
     int chain_la;       // chain task d draws its ticket d / chain_la block columns early (0: with its own column)
 };
 
@@ -668,7 +667,7 @@ __global__ void __launch_bounds__(DF_THREADS, 2) chol_dataflow_kernel(DfArgs g) 
             __syncthreads();                          // X is in shared memory, W_cc is final (warp 0 acquired its flag)
             if (tracing) t_wait += clock64() - t_mark;
             const bool okd = ready_s[2] != 0;
-            if (chain && tid == 0 && g.use_pause) df_st_relaxed(my_pause, 1);
+            if (chain && tid == 0) df_st_relaxed(my_pause, 1);
             if (chain) df_stamp(g.trace, idx, 1);
 #pragma unroll
             for (int e = tid; e < PB * (PB / 2); e += DF_THREADS) {
@@ -993,8 +992,6 @@ int chol_dataflow(double* K, int64_t npad, int64_t ld, double* W, int64_t ldw, i
     }
     static const int chain_la = [] { const char* e = getenv("MFGP_DF_CHAIN_LA"); return e ? atoi(e) : 5; }();
     a.chain_la = chain_la;
-    static const int use_pause = [] { const char* e = getenv("MFGP_DF_PAUSE"); return e ? atoi(e) : 1; }();
-    a.use_pause = use_pause;
     a.spin_limit = 4000000000LL;      // ~2 s of SM clocks: only a bug can get there
     constexpr int smem = DF_SMEM_DOUBLES * sizeof(double);
     static const int occ = [] { const char* e = getenv("MFGP_DF_OCC"); return e ? atoi(e) : 2; }();
